@@ -1,0 +1,76 @@
+"""Seeded synthetic inputs.  Pure numpy so the GPU box reproduces them bit-for-bit.
+
+Uniform noise gives the networks nothing to detect, so frames are structured: random filled
+rotated rectangles + anti-aliased line segments on a flat background, light blur, sensor noise.
+"""
+import numpy as np
+
+
+def _blur3(img, sigma=0.8):
+    k = np.exp(-0.5 * (np.arange(-1, 2) / sigma) ** 2)
+    k /= k.sum()
+    p = np.pad(img, 1, mode="edge")
+    t = k[0] * p[:, :-2] + k[1] * p[:, 1:-1] + k[2] * p[:, 2:]
+    return k[0] * t[:-2] + k[1] * t[1:-1] + k[2] * t[2:]
+
+
+def frame(seed, width, height, n_rect=40, n_line=30):
+    """-> (height, width) uint8 structured frame."""
+    rs = np.random.RandomState(seed)
+    W, H = width, height
+    img = np.full((H, W), float(rs.randint(60, 120)), dtype=np.float64)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    for _ in range(n_rect):
+        cx, cy = rs.uniform(0, W), rs.uniform(0, H)
+        w, h = rs.uniform(20, max(21.0, W / 4)), rs.uniform(20, max(21.0, H / 4))
+        a = rs.uniform(0, np.pi)
+        g = float(rs.randint(0, 256))
+        ca, sa = np.cos(a), np.sin(a)
+        u = (xx - cx) * ca + (yy - cy) * sa
+        v = -(xx - cx) * sa + (yy - cy) * ca
+        # soft edge of ~1 px so rectangle borders are anti-aliased
+        cov = np.clip(w / 2 - np.abs(u) + 0.5, 0, 1) * np.clip(h / 2 - np.abs(v) + 0.5, 0, 1)
+        img = img * (1 - cov) + g * cov
+    for _ in range(n_line):
+        x0, y0, x1, y1 = rs.uniform(0, W), rs.uniform(0, H), rs.uniform(0, W), rs.uniform(0, H)
+        t = rs.uniform(1, 3)
+        g = float(rs.randint(0, 256))
+        dx, dy = x1 - x0, y1 - y0
+        L2 = dx * dx + dy * dy + 1e-9
+        s = np.clip(((xx - x0) * dx + (yy - y0) * dy) / L2, 0, 1)
+        d = np.hypot(xx - (x0 + s * dx), yy - (y0 + s * dy))
+        cov = np.clip(t / 2 - d + 0.5, 0, 1)
+        img = img * (1 - cov) + g * cov
+    img = _blur3(img)
+    img = img + rs.normal(0, 3, size=img.shape)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def frames(seeds, width, height):
+    return np.stack([frame(s, width, height) for s in seeds])
+
+
+def association_inputs(seed, frame_desc, kp_xy, n_map, width, height, th=10.0, planted_frac=0.5):
+    """Map-side inputs for the image<->map association.
+
+    frame_desc (N,256) unit rows; kp_xy (N,2) undistorted positions.
+    -> dict(map_desc (M,256) f32, proj_uv (M,2) f32, view_cos (M,) f32, n_edges (M,) i32)
+    Planted rows = a frame descriptor + N(0,0.05) noise renormalised, projected near its keypoint.
+    """
+    rs = np.random.RandomState(seed)
+    N = frame_desc.shape[0]
+    M = n_map
+    d = rs.normal(size=(M, 256)).astype(np.float32)
+    uv = np.stack([rs.uniform(0, width, M), rs.uniform(0, height, M)], 1).astype(np.float32)
+    view_cos = rs.uniform(0.9, 1.0, M).astype(np.float32)
+    if N > 0:
+        n_pl = min(int(M * planted_frac), M)
+        rows = rs.choice(M, n_pl, replace=False)
+        src = rs.randint(0, N, n_pl)
+        d[rows] = frame_desc[src] + rs.normal(0, 0.05, size=(n_pl, 256)).astype(np.float32)
+        r = np.where(view_cos[rows] > 0.998, 2.5, 4.0) * th
+        uv[rows] = kp_xy[src] + (rs.uniform(-0.5, 0.5, size=(n_pl, 2)) * r[:, None]).astype(np.float32)
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-12)
+    n_edges = rs.randint(0, 6, M).astype(np.int32)
+    return dict(map_desc=d.astype(np.float32), proj_uv=uv.astype(np.float32),
+                view_cos=view_cos, n_edges=n_edges)
