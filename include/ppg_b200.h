@@ -1,0 +1,205 @@
+/*
+ * ppg_b200.h -- C ABI of the B200-native PPG-SLAM front-end (libppg_b200.so).
+ *
+ * Drop-in boundary for two reference classes (all file:line relative to the PPG-SLAM tree):
+ *   PPGExtractor   feature/include/PPGExtractor.h:34-148, feature/src/PPGExtractor.cpp:55-603
+ *   Matcher        matching/include/Matcher.h:20-64, search core matching/src/Matcher.cpp:224-281
+ * The header-only C++ shims (include/ppg_shim.hpp) rebuild those classes on top of these entry points.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 (PPG_OK) or a negative
+ * ppg_status, never throws, never aborts.  One ppg_ctx per GPU; calls on one ctx are serialised by the
+ * caller (the reference extractor is single-threaded too); different ctxs are
+ * independent.  There is NO CPU fallback: without a CUDA device ppg_create fails with PPG_ERR_CUDA.
+ */
+#ifndef PPG_B200_H
+#define PPG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPG_API_VERSION 1
+#define PPG_DESC_DIM 256 /* PPGExtractor::DESC_DIM_SIZE, PPGExtractor.cpp:44 */
+
+typedef enum {
+    PPG_OK = 0,
+    PPG_ERR_ARG = -1,      /* bad argument / unsupported shape */
+    PPG_ERR_CUDA = -2,     /* CUDA runtime or driver error (ppg_last_error has the string) */
+    PPG_ERR_WEIGHTS = -3,  /* weight blob missing or malformed */
+    PPG_ERR_CAPACITY = -4, /* a per-frame capacity (edges, colines, pair candidates) was exceeded;
+                              the frame's `status` word says which.  Results for that frame are invalid. */
+    PPG_ERR_NCCL = -5
+} ppg_status;
+
+/* bits of ppg_frame_out.status */
+#define PPG_FRAME_OVF_ACCEPT 1u /* > acc_cap NMS survivors */
+#define PPG_FRAME_OVF_PAIRS 2u  /* > pair_cap point pairs passed the 3-point heat test */
+#define PPG_FRAME_OVF_DEGREE 4u /* a keypoint exceeded the adjacency capacity */
+#define PPG_FRAME_OVF_EDGES 8u  /* > max_edges final edges */
+#define PPG_FRAME_OVF_COLINE 16u
+
+typedef struct ppg_ctx ppg_ctx;
+
+/* Replaces the PPGExtractor constructor arguments (GeometricCamera*, net dir; PPGExtractor.cpp:55-107)
+ * plus the class's static tunables (PPGExtractor.cpp:44-53) and Matcher::TH_LOW/TH_HIGH
+ * (Matcher.cpp:12-13). */
+typedef struct {
+    int device;               /* CUDA ordinal (reference hard-codes cuda:0, PPGExtractor.cpp:41) */
+    int width, height;        /* GeometricCamera::imWidth/imHeight; both must be multiples of 16 */
+    float K[9];               /* GeometricCamera::toK(), row major */
+    float D[4];               /* GeometricCamera::toD(): pinhole k1 k2 p1 p2, KB8 k0..k3 */
+    int fisheye;              /* mnType == CAM_FISHEYE */
+    const char* weights_path; /* flat export of net/*.pt (tools/export_weights.py) */
+    float junction_thresh;    /* JUNCTION_THRESH 1/128 */
+    int junction_nms_radius;  /* JUNCTION_NMS_RADIUS 4 (<= 8) */
+    int junction_max_num;     /* JUNCTION_MAX_NUM 500 */
+    float line_valid_thresh;  /* LINE_VALID_THRESH 0.01 */
+    float line_valid_ratio;   /* LINE_VALID_RATIO 0.3 */
+    float line_dist_thresh;   /* LINE_DISTTHRESH 2.0 */
+    int heatmap_refine_sz;    /* HEATMAP_REFINE_SZ: only 16 is supported */
+    float line_heatmap_thresh;/* LINE_HEATMAP_THRESH 0.2 */
+    float line_inlier_rate;   /* LINE_INLIER_RATE 0.8 */
+    float th_low, th_high;    /* Matcher::TH_LOW 0.7, TH_HIGH 0.8 */
+    int max_batch;            /* frames per ppg_extract call (the reference is batch 1) */
+    int max_edges;            /* capacity of the per-frame edge list */
+    int max_colines;          /* capacity of the per-frame coline-pair list */
+    int max_map_points;       /* capacity of the resident map-descriptor table (rows on this GPU) */
+} ppg_config;
+
+/* Output record of PPGExtractor::run (PPGExtractor.cpp:118-147) for one frame, SoA.
+ * Pointers refer to ctx-owned pinned host memory, valid until the next call on the ctx.
+ *   KeyPointEx  (sensors/include/GeometricCamera.h:22-37):
+ *     mPos   = (kp_x, kp_y)   -- as run() returns it: pinhole mPos <- mPosUn (:141-145)
+ *     mPosUn = (kp_xun, kp_yun), mfScore = kp_score, mbOut = kp_out
+ *     mvConnected[i] = conn_idx[conn_off[i] .. conn_off[i+1])
+ *     mvColine[i]    = pairs col_pairs[2k], col_pairs[2k+1] for k in [col_off[i], col_off[i+1])
+ *   KeyEdge (feature/include/PPGGraph.h:32-55): startIdx, endIdx, lscore (isBad is always false)
+ *   descriptors: n_kp x 256 fp32 rows (cv::Mat CV_32FC1 in the reference) */
+typedef struct {
+    int n_kp, n_edges, n_colines;
+    uint32_t status;       /* 0, or PPG_FRAME_OVF_* bits */
+    int n_candidates;      /* pixels >= junction_thresh (diagnostic) */
+    int n_pairs_tested_ok; /* point pairs passing the 3-point heat test (diagnostic) */
+    int n_candidate_lines; /* candidateLines.size() after the overlap filter (diagnostic) */
+    int nms_rounds;        /* parallel NMS rounds used (diagnostic) */
+    const float* kp_x;
+    const float* kp_y;
+    const int32_t* kp_px; /* detection pixel (integer mPos before :141-145) */
+    const int32_t* kp_py;
+    const float* kp_score;
+    const float* kp_xun;
+    const float* kp_yun;
+    const uint8_t* kp_out;
+    const int32_t* edge_start;
+    const int32_t* edge_end;
+    const float* edge_score;
+    const int32_t* conn_off; /* n_kp + 1 */
+    const int32_t* conn_idx;
+    const int32_t* col_off;  /* n_kp + 1 */
+    const int32_t* col_pairs;
+    const float* desc;       /* n_kp x 256 */
+} ppg_frame_out;
+
+void ppg_default_config(ppg_config* cfg);
+int ppg_create(const ppg_config* cfg, ppg_ctx** out);
+void ppg_destroy(ppg_ctx* ctx);
+/* Thread-local message of the last failure on this ctx (or of ppg_create when ctx is NULL). */
+const char* ppg_last_error(const ppg_ctx* ctx);
+int ppg_api_version(void);
+
+/* ---- extraction: PPGExtractor::run for n_frames independent frames ------------------------------
+ * gray[f] points to an 8-bit single-channel image with row stride stride[f] bytes (cv::Mat data/step;
+ * PPGExtractor.cpp:121 asserts one channel).  Host memory.  Synchronous: copies in, runs the networks
+ * and the post-processing on the GPU, copies the records out.  Returns PPG_ERR_CAPACITY if any frame's
+ * status is non-zero (records of the other frames are still valid). */
+int ppg_extract(ppg_ctx* ctx, const uint8_t* const* gray, const int* stride, int n_frames, ppg_frame_out* out);
+
+/* The same three steps separately, so that a caller (bench.py) can time the device part alone or
+ * overlap copies itself.  ppg_upload_frames: host -> device staging.  ppg_run: networks +
+ * post-processing on frames already resident (asynchronous on the ctx stream).  ppg_download:
+ * device -> pinned host, synchronises, fills `out`. */
+int ppg_upload_frames(ppg_ctx* ctx, const uint8_t* const* gray, const int* stride, int n_frames);
+int ppg_run(ppg_ctx* ctx, int n_frames);
+int ppg_download(ppg_ctx* ctx, int n_frames, ppg_frame_out* out);
+int ppg_sync(ppg_ctx* ctx);
+
+/* ---- parity / debug entry points ----------------------------------------------------------------
+ * ppg_extract_from_maps: PPGExtractor::run minus the networks (detectKeyPoint, detectLines,
+ * genPointDescriptor; PPGExtractor.cpp:126-146) fed with caller-supplied dense maps (host fp32):
+ * prob n x H x W (softmax + pixel_shuffle junction map, :161-162), heat n x H x W (softmax[:,1] BEFORE
+ * refine, :242), desc n x 256 x Hc x Wc (raw dense descriptors, CHW as LibTorch holds them). */
+int ppg_extract_from_maps(ppg_ctx* ctx, const float* prob, const float* heat, const float* desc_chw, int n_frames,
+                          ppg_frame_out* out);
+/* Dense maps of frame `frame` of the last ppg_run/ppg_extract*, copied to host.  Any pointer may be
+ * NULL.  prob/heat_raw/heat_final are H x W; desc_chw is 256 x Hc x Wc; feature_chw is 128 x Hc x Wc. */
+int ppg_get_maps(ppg_ctx* ctx, int frame, float* prob, float* heat_raw, float* heat_final, float* desc_chw,
+                 float* feature_chw);
+/* Runs every tensor-core convolution layer of the last batch's frame 0 again through a plain fp32
+ * CUDA-core convolution over the same fp16 operands and reports the max abs difference per layer.
+ * names: up to max_layers pointers to static strings. */
+int ppg_selftest_conv(ppg_ctx* ctx, int max_layers, const char** names, float* max_abs_diff, float* max_abs_ref,
+                      int* n_layers);
+
+/* Per-stage device times of the last ppg_run when profiling is on (CUDA events between launches on
+ * the ctx stream).  names[i] are static strings; returns the stage count through n_stages. */
+int ppg_set_profiling(ppg_ctx* ctx, int on);
+int ppg_get_stage_times(ppg_ctx* ctx, int max_stages, const char** names, float* ms, int* n_stages);
+/* Kernel launches issued on the ctx stream since creation (own kernels only). */
+long long ppg_launch_count(const ppg_ctx* ctx);
+/* CUDA-event stopwatch on the ctx stream: start/stop enqueue events, elapsed synchronises. */
+int ppg_timer_start(ppg_ctx* ctx);
+int ppg_timer_stop(ppg_ctx* ctx, float* ms);
+
+/* ---- association: search core of Matcher::ExtendMapMatches (Matcher.cpp:224-281) ----------------
+ * The map-descriptor table (MapPoint::GetDescriptor rows, feature/src/MapPoint.cpp:304-308) is kept
+ * resident on the GPU.  `row0` is the global index of this ctx's first row when the table is row-sharded
+ * across ctxs/GPUs (0 otherwise); indices returned are keypoint indices, rows are local. */
+int ppg_upload_map(ppg_ctx* ctx, const float* map_desc, int n_rows);
+
+typedef struct {
+    int n_kp;                /* frame keypoints N */
+    const float* kp_x;       /* mvKeysUn[i].mPos (Frame.cpp:138-156) */
+    const float* kp_y;
+    const float* frame_desc; /* N x 256 fp32, unit rows (Frame::mDescriptors) */
+    const uint8_t* free_mask;/* N: 1 = keypoint may be matched (Matcher.cpp:253 inverted) */
+    int n_rows;              /* map points M (<= rows uploaded) */
+    const float* proj_uv;    /* M x 2: MapPoint::mTrackProjX/Y */
+    const float* view_cos;   /* M: MapPoint::mTrackViewCos */
+    float th;                /* search radius factor (Matcher.cpp:240-244: r = th * (cos>0.998 ? 2.5 : 4)) */
+    float ratio;             /* Matcher::mfNNratio */
+} ppg_assoc_in;
+
+typedef struct {       /* caller-allocated host arrays of n_rows */
+    int32_t* best_idx;   /* -1 when the window is empty */
+    int32_t* second_idx; /* -1 when fewer than two candidates */
+    float* best_dist;    /* DescriptorDistance (MapPoint.cpp:22-29); 1e6 when absent */
+    float* second_dist;
+    uint8_t* accept;     /* !(best > TH_HIGH && best > ratio*second), Matcher.cpp:276 */
+} ppg_assoc_out;
+
+/* Inputs/outputs in host memory; synchronous. */
+int ppg_associate(ppg_ctx* ctx, const ppg_assoc_in* in, ppg_assoc_out* out);
+/* Device-resident variant for timing: inputs staged by ppg_assoc_stage, kernels enqueued by
+ * ppg_assoc_run (asynchronous), results fetched by ppg_assoc_fetch. */
+int ppg_assoc_stage(ppg_ctx* ctx, const ppg_assoc_in* in);
+int ppg_assoc_run(ppg_ctx* ctx);
+int ppg_assoc_fetch(ppg_ctx* ctx, ppg_assoc_out* out);
+/* Associates frame `frame` of the last extraction batch (descriptors and keypoints still on the
+ * device) against the staged projections -- the extract+associate step of the benchmark. */
+int ppg_assoc_run_frame(ppg_ctx* ctx, int frame);
+/* Rows whose tensor-core candidate filter could not guarantee the exact top-2 and were re-scored
+ * over the whole window (diagnostic). */
+int ppg_assoc_fallback_rows(ppg_ctx* ctx, int* n);
+
+/* Device pointers of the staged association results (n_rows each), for the sharded all-gather that
+ * the multi-GPU host layer issues through NCCL (ppg_slam_b200/sharded.py). */
+int ppg_assoc_device_results(ppg_ctx* ctx, void** best_idx, void** second_idx, void** best_dist, void** second_dist,
+                             void** accept);
+void* ppg_stream(ppg_ctx* ctx); /* cudaStream_t of the ctx */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPG_B200_H */

@@ -1,0 +1,227 @@
+"""ctypes front of oracle/ppg_oracle.c: L1 (post-processing) and L2 (association) oracle.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Follows feature/src/PPGExtractor.cpp:118-147
+(run) for the orchestration: detectKeyPoint -> detectLines -> genPointDescriptor, then the
+pinhole-only `mPos = mPosUn` copy (:141-145).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+
+class Cfg(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("K", C.c_float * 9), ("D", C.c_float * 4),
+                ("fisheye", C.c_int), ("junction_thresh", C.c_float), ("junction_nms_radius", C.c_int),
+                ("junction_max_num", C.c_int), ("line_valid_thresh", C.c_float),
+                ("line_valid_ratio", C.c_float), ("line_dist_thresh", C.c_float),
+                ("heatmap_refine_sz", C.c_int), ("line_heatmap_thresh", C.c_float),
+                ("line_inlier_rate", C.c_float)]
+
+
+class Bounds(C.Structure):
+    _fields_ = [("minX", C.c_int), ("minY", C.c_int), ("maxX", C.c_int), ("maxY", C.c_int),
+                ("wInv", C.c_float), ("hInv", C.c_float)]
+
+
+_libs = {}
+
+
+def lib(variant=""):
+    if variant not in _libs:
+        _build.build()
+        _libs[variant] = C.CDLL(_build.lib_path(variant))
+        _libs[variant].ppgo_descriptor_distance.restype = C.c_float
+    return _libs[variant]
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def make_cfg(cam, **over):
+    c = Cfg()
+    lib().ppgo_default_cfg(C.byref(c))
+    c.width, c.height, c.fisheye = cam.width, cam.height, int(cam.fisheye)
+    c.K[:] = cam.K
+    c.D[:] = cam.D
+    for k, v in over.items():
+        setattr(c, k, v)
+    return c
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def undistort_points(cam, xy):
+    xy = f32(xy).reshape(-1, 2)
+    out = np.empty_like(xy)
+    K, D = f32(cam.K), f32(cam.D)
+    fn = lib().ppgo_undistort_points_fisheye if cam.fisheye else lib().ppgo_undistort_points_pinhole
+    fn(_p(K, C.c_float), _p(D, C.c_float), _p(xy, C.c_float), len(xy), _p(out, C.c_float))
+    return out
+
+
+def init_undistort_map(cam):
+    mx = np.empty((cam.height, cam.width), np.float32)
+    my = np.empty_like(mx)
+    K, D = f32(cam.K), f32(cam.D)
+    fn = lib().ppgo_init_undistort_map_fisheye if cam.fisheye else lib().ppgo_init_undistort_map_pinhole
+    fn(_p(K, C.c_float), _p(D, C.c_float), cam.width, cam.height, _p(mx, C.c_float), _p(my, C.c_float))
+    return mx, my
+
+
+def remap_linear(src, mx, my):
+    src = f32(src)
+    H, W = src.shape
+    dst = np.empty_like(src)
+    lib().ppgo_remap_linear(_p(src, C.c_float), W, H, _p(f32(mx), C.c_float), _p(f32(my), C.c_float),
+                            _p(dst, C.c_float))
+    return dst
+
+
+def detect_keypoints(cfg, prob):
+    prob = f32(prob)
+    cap = max(cfg.junction_max_num, 1)
+    kx, ky = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    sc, xu, yu = np.zeros(cap, np.float32), np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+    out = np.zeros(cap, np.uint8)
+    nc = C.c_int(0)
+    n = lib().ppgo_detect_keypoints(C.byref(cfg), _p(prob, C.c_float), _p(kx, C.c_int), _p(ky, C.c_int),
+                                    _p(sc, C.c_float), _p(xu, C.c_float), _p(yu, C.c_float),
+                                    _p(out, C.c_uint8), C.byref(nc))
+    return dict(n=n, x=kx[:n].copy(), y=ky[:n].copy(), score=sc[:n].copy(), xun=xu[:n].copy(),
+                yun=yu[:n].copy(), out=out[:n].copy(), n_cand=nc.value)
+
+
+def refine_heat(cfg, heat):
+    h = f32(heat).copy()
+    lib().ppgo_refine_heat(C.byref(cfg), _p(h, C.c_float))
+    return h
+
+
+def detect_lines(cfg, heat_final, kp, max_edges=131072, max_col=131072, variant=""):
+    n = kp["n"]
+    heat_final = f32(heat_final)
+    es, ee = np.zeros(max_edges, np.int32), np.zeros(max_edges, np.int32)
+    esc = np.zeros(max_edges, np.float32)
+    coff, cidx = np.zeros(n + 1, np.int32), np.zeros(2 * max_edges, np.int32)
+    loff, lpairs = np.zeros(n + 1, np.int32), np.zeros(2 * max_col, np.int32)
+    ncol = C.c_int(0)
+    stats = np.zeros(4, np.int32)
+    xun, yun, kout = f32(kp["xun"]), f32(kp["yun"]), np.ascontiguousarray(kp["out"], np.uint8)
+    E = lib(variant).ppgo_detect_lines(C.byref(cfg), _p(heat_final, C.c_float), n, _p(xun, C.c_float),
+                                       _p(yun, C.c_float), _p(kout, C.c_uint8), max_edges, _p(es, C.c_int),
+                                       _p(ee, C.c_int), _p(esc, C.c_float), _p(coff, C.c_int),
+                                       _p(cidx, C.c_int), max_col, _p(loff, C.c_int), _p(lpairs, C.c_int),
+                                       C.byref(ncol), _p(stats, C.c_int))
+    assert E >= 0 and ncol.value >= 0, "oracle capacity exceeded"
+    return dict(n_edges=E, edge_start=es[:E].copy(), edge_end=ee[:E].copy(), edge_score=esc[:E].copy(),
+                conn_off=coff, conn_idx=cidx[:coff[n]].copy(), col_off=loff,
+                col_pairs=lpairs[:2 * ncol.value].reshape(-1, 2).copy(), stats=stats)
+
+
+def sample_descriptors(cfg, desc_chw, kx, ky):
+    desc_chw = f32(desc_chw)
+    Cc, Hc, Wc = desc_chw.shape
+    n = len(kx)
+    out = np.zeros((n, Cc), np.float32)
+    kx, ky = np.ascontiguousarray(kx, np.int32), np.ascontiguousarray(ky, np.int32)
+    lib().ppgo_sample_descriptors(C.byref(cfg), _p(desc_chw, C.c_float), Cc, Hc, Wc, n, _p(kx, C.c_int),
+                                  _p(ky, C.c_int), _p(out, C.c_float))
+    return out
+
+
+_prev_edges = {}
+
+
+def extract_post(cam, prob, heat_raw, desc_chw, maps=None, variant="", **over):
+    """PPGExtractor::run minus the networks (PPGExtractor.cpp:126-146).
+
+    prob (H,W) junction map, heat_raw (H,W) softmax[:,1] BEFORE refine, desc_chw (256,Hc,Wc).
+    -> dict with the output record of run(): kp_x/kp_y = output mPos (pinhole: = mPosUn, :141-145),
+    px/py = detection pixel, xun/yun, out, score, edges, CSR adjacency, colines, desc, plus the
+    intermediate refined/remapped heat map (heat_final).
+    """
+    cfg = make_cfg(cam, **over)
+    kp = detect_keypoints(cfg, prob)
+    res = dict(n_kp=kp["n"], px=kp["x"], py=kp["y"], score=kp["score"], xun=kp["xun"], yun=kp["yun"],
+               out=kp["out"], n_cand=kp["n_cand"])
+    n = kp["n"]
+    if n == 0:
+        # detectLines returns before touching mvKeyEdges (:239-240): the reference leaks the previous
+        # frame's edges here; the oracle (and the product) report zero edges.  DESIGN.md "divergences".
+        res.update(n_edges=0, edge_start=np.zeros(0, np.int32), edge_end=np.zeros(0, np.int32),
+                   edge_score=np.zeros(0, np.float32), conn_off=np.zeros(1, np.int32),
+                   conn_idx=np.zeros(0, np.int32), col_off=np.zeros(1, np.int32),
+                   col_pairs=np.zeros((0, 2), np.int32), heat_final=None,
+                   desc=np.zeros((0, desc_chw.shape[0]), np.float32),
+                   kp_x=np.zeros(0, np.float32), kp_y=np.zeros(0, np.float32))
+        return res
+    heat = refine_heat(cfg, heat_raw)
+    if cam.D[0] != 0.0:  # :261
+        mx, my = maps if maps is not None else init_undistort_map(cam)
+        heat = remap_linear(heat, mx, my)
+    res["heat_final"] = heat
+    res.update(detect_lines(cfg, heat, kp, variant=variant))
+    res["desc"] = sample_descriptors(cfg, desc_chw, kp["x"], kp["y"])
+    if cam.fisheye:
+        res["kp_x"], res["kp_y"] = kp["x"].astype(np.float32), kp["y"].astype(np.float32)
+    else:
+        res["kp_x"], res["kp_y"] = kp["xun"].copy(), kp["yun"].copy()
+    return res
+
+
+# ---------------------------------------------------------------- association (L2)
+def image_bounds(cam):
+    b = Bounds()
+    cfg = make_cfg(cam)
+    lib().ppgo_image_bounds(C.byref(cfg), C.byref(b))
+    return b
+
+
+def descriptor_distance(a, b):
+    a, b = f32(a), f32(b)
+    return float(lib().ppgo_descriptor_distance(_p(a, C.c_float), _p(b, C.c_float), a.size))
+
+
+def features_in_area(cam, kx, ky, x, y, r):
+    b = image_bounds(cam)
+    kx, ky = f32(kx), f32(ky)
+    n = len(kx)
+    goff, gidx = np.zeros(64 * 48 + 1, np.int32), np.zeros(max(n, 1), np.int32)
+    lib().ppgo_grid_build(C.byref(b), n, _p(kx, C.c_float), _p(ky, C.c_float), _p(goff, C.c_int), _p(gidx, C.c_int))
+    out = np.zeros(max(n, 1), np.int32)
+    cnt = lib().ppgo_features_in_area(C.byref(b), _p(goff, C.c_int), _p(gidx, C.c_int), _p(kx, C.c_float),
+                                      _p(ky, C.c_float), C.c_float(x), C.c_float(y), C.c_float(r),
+                                      _p(out, C.c_int))
+    return out[:cnt].copy()
+
+
+def indexable(cam, kx, ky):
+    b = image_bounds(cam)
+    px, py = C.c_int(0), C.c_int(0)
+    return np.array([lib().ppgo_pos_in_grid(C.byref(b), C.c_float(float(x)), C.c_float(float(y)),
+                                            C.byref(px), C.byref(py)) for x, y in zip(kx, ky)], np.uint8)
+
+
+def search_all(cam, kx, ky, frame_desc, free_mask, map_desc, proj_uv, view_cos, th, ratio, th_high=0.8):
+    """Search core of Matcher::ExtendMapMatches (Matcher.cpp:224-281) for every map point, frame
+    state frozen.  -> dict(best_idx, second_idx, best_d, second_d, accept)."""
+    cfg = make_cfg(cam)
+    kx, ky, frame_desc = f32(kx), f32(ky), f32(frame_desc)
+    map_desc, proj_uv, view_cos = f32(map_desc), f32(proj_uv), f32(view_cos)
+    free_mask = np.ascontiguousarray(free_mask, np.uint8)
+    n, m = len(kx), len(map_desc)
+    bi, si = np.zeros(m, np.int32), np.zeros(m, np.int32)
+    bd, sd = np.zeros(m, np.float32), np.zeros(m, np.float32)
+    acc = np.zeros(m, np.uint8)
+    lib().ppgo_search_all(C.byref(cfg), n, _p(kx, C.c_float), _p(ky, C.c_float), _p(frame_desc, C.c_float),
+                          _p(free_mask, C.c_uint8), m, _p(map_desc, C.c_float), _p(proj_uv, C.c_float),
+                          _p(view_cos, C.c_float), C.c_float(th), C.c_float(ratio), C.c_float(th_high),
+                          _p(bi, C.c_int), _p(si, C.c_int), _p(bd, C.c_float), _p(sd, C.c_float),
+                          _p(acc, C.c_uint8))
+    return dict(best_idx=bi, second_idx=si, best_d=bd, second_d=sd, accept=acc)

@@ -1,0 +1,789 @@
+/*
+ * ppg_oracle.c -- CPU restatement of the PPG-SLAM front-end post-processing and association.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference leg may load this.  The product (ppg_slam_b200/, include/) never does.
+ *
+ * Parity status: the reference ships no tests / golden vectors => "parity unpinned"
+ * by the reference's own tests.  What pins this file instead:
+ *   - the four OpenCV routines are checked bit-for-bit against cv2 4.13 (tests/test_oracle_cv.py);
+ *   - the descriptor sampler is checked against torch.grid_sampler + F.normalize;
+ *   - everything else follows the cited reference lines statement by statement.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math -shared -fPIC ppg_oracle.c -lm   (oracle/build.py)
+ * -ffp-contract=off matters: the reference is built without -march (SSE2, no FMA; CMakeLists.txt:8-9).
+ *
+ * Two documented divergences from the literal reference (DESIGN.md "Oracle"):
+ *   1. std::sort ties (PPGExtractor.cpp:180, Matcher.cpp:221) are broken by a stable order
+ *      (raster index / input order); std::sort leaves them unspecified.
+ *   2. libm float transcendentals (atan2f :283, sin(double) :330, sinf :413) are evaluated as the
+ *      correctly rounded float of the double routine ((float)atan2((double)y,(double)x) ...), which
+ *      is what a correctly-rounded libm (glibc >= 2.41) returns; PPGO_LIBM_FLOAT=1 at compile time
+ *      switches to the literal float libm calls so tests can show the graph does not depend on it.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define PPGO_PI 3.1415926535897932384626433832795 /* CV_PI  */
+#define PPGO_2PI 6.283185307179586476925286766559 /* CV_2PI */
+
+#ifndef PPGO_LIBM_FLOAT
+#define PPGO_LIBM_FLOAT 0
+#endif
+
+static float o_atan2f(float y, float x) {
+#if PPGO_LIBM_FLOAT
+    return atan2f(y, x);
+#else
+    return (float)atan2((double)y, (double)x);
+#endif
+}
+static float o_sinf(float a) {
+#if PPGO_LIBM_FLOAT
+    return sinf(a);
+#else
+    return (float)sin((double)a);
+#endif
+}
+
+typedef struct {
+    int width, height;
+    float K[9]; /* row-major fx 0 cx 0 fy cy 0 0 1 (toK(), Pinhole.cpp / KannalaBrandt8.cpp:136) */
+    float D[4]; /* pinhole: k1 k2 p1 p2; KB8: k0..k3 (toD()) */
+    int fisheye;
+    /* static tunables, PPGExtractor.cpp:44-53 */
+    float junction_thresh;   /* 1/128 */
+    int junction_nms_radius; /* 4     */
+    int junction_max_num;    /* 500   */
+    float line_valid_thresh; /* 0.01  */
+    float line_valid_ratio;  /* 0.3   */
+    float line_dist_thresh;  /* 2.0   */
+    int heatmap_refine_sz;   /* 16    */
+    float line_heatmap_thresh; /* 0.2 */
+    float line_inlier_rate;  /* 0.8   */
+} ppgo_cfg;
+
+void ppgo_default_cfg(ppgo_cfg *c) {
+    memset(c, 0, sizeof(*c));
+    c->junction_thresh = 1.0f / 128.0f;
+    c->junction_nms_radius = 4;
+    c->junction_max_num = 500;
+    c->line_valid_thresh = 1.0e-2f;
+    c->line_valid_ratio = 0.3f;
+    c->line_dist_thresh = 2.0f;
+    c->heatmap_refine_sz = 16;
+    c->line_heatmap_thresh = 0.2f;
+    c->line_inlier_rate = 0.8f;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* OpenCV routines the extractor calls (source not under /root/reference: OpenCV >= 4.2,       */
+/* README.md:26; restated from the published algorithm, pinned against cv2 4.13 in the tests). */
+/* ------------------------------------------------------------------------------------------- */
+
+/* cv::undistortPoints(pts,K,D,noArray(),K) with D=(k1,k2,p1,p2): PPGExtractor.cpp:223 and
+ * GeometricCamera.cpp:40.  5 fixed-point iterations in double, output cast to float. */
+void ppgo_undistort_points_pinhole(const float *K, const float *D, const float *xy, int n, float *out) {
+    double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    double ifx = 1. / fx, ify = 1. / fy;
+    double k1 = D[0], k2 = D[1], p1 = D[2], p2 = D[3];
+    for (int i = 0; i < n; i++) {
+        double u = xy[2 * i], v = xy[2 * i + 1];
+        double x = (u - cx) * ifx, y = (v - cy) * ify;
+        double x0 = x, y0 = y;
+        for (int it = 0; it < 5; it++) {
+            double r2 = x * x + y * y;
+            double icdist = (1 + ((0. * r2 + 0.) * r2 + 0.) * r2) / (1 + ((0. * r2 + k2) * r2 + k1) * r2);
+            if (icdist < 0) {
+                x = (u - cx) * ifx;
+                y = (v - cy) * ify;
+                break;
+            }
+            double dX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x) + 0. * r2 + 0. * r2 * r2;
+            double dY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y + 0. * r2 + 0. * r2 * r2;
+            x = (x0 - dX) * icdist;
+            y = (y0 - dY) * icdist;
+        }
+        /* P = K, R = I */
+        double xx = fx * x + 0. * y + cx, yy = 0. * x + fy * y + cy, ww = 1. / (0. * x + 0. * y + 1.);
+        out[2 * i] = (float)(xx * ww);
+        out[2 * i + 1] = (float)(yy * ww);
+    }
+}
+
+/* cv::fisheye::undistortPoints(pts,pts,K,D,Mat(),K): PPGExtractor.cpp:221.  Newton, <=10 its, eps 1e-8. */
+void ppgo_undistort_points_fisheye(const float *K, const float *D, const float *xy, int n, float *out) {
+    double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    double k[4] = {D[0], D[1], D[2], D[3]};
+    for (int i = 0; i < n; i++) {
+        double px = xy[2 * i], py = xy[2 * i + 1];
+        double pwx = (px - cx) / fx, pwy = (py - cy) / fy;
+        double theta_d = sqrt(pwx * pwx + pwy * pwy);
+        theta_d = fmin(fmax(-PPGO_PI / 2., theta_d), PPGO_PI / 2.);
+        int converged = 0;
+        double theta = theta_d, scale = 0.0;
+        if (fabs(theta_d) > 1e-8) {
+            for (int j = 0; j < 10; j++) {
+                double t2 = theta * theta, t4 = t2 * t2, t6 = t4 * t2, t8 = t6 * t2;
+                double k0t2 = k[0] * t2, k1t4 = k[1] * t4, k2t6 = k[2] * t6, k3t8 = k[3] * t8;
+                double fix = (theta * (1 + k0t2 + k1t4 + k2t6 + k3t8) - theta_d) /
+                             (1 + 3 * k0t2 + 5 * k1t4 + 7 * k2t6 + 9 * k3t8);
+                theta = theta - fix;
+                if (fabs(fix) < 1e-8) {
+                    converged = 1;
+                    break;
+                }
+            }
+            scale = tan(theta) / theta_d;
+        } else {
+            converged = 1;
+        }
+        int flipped = ((theta_d < 0 && theta > 0) || (theta_d > 0 && theta < 0));
+        if (converged && !flipped) {
+            double pux = pwx * scale, puy = pwy * scale;
+            double pr0 = fx * pux + 0. * puy + cx * 1.0, pr1 = 0. * pux + fy * puy + cy * 1.0;
+            double pr2 = 0. * pux + 0. * puy + 1.0;
+            out[2 * i] = (float)(pr0 / pr2);
+            out[2 * i + 1] = (float)(pr1 / pr2);
+        } else {
+            out[2 * i] = -1000000.0f;
+            out[2 * i + 1] = -1000000.0f;
+        }
+    }
+}
+
+/* cv::initUndistortRectifyMap(K,D,I,K,size,CV_32F,mX,mY): PPGExtractor.cpp:69 (pinhole). */
+void ppgo_init_undistort_map_pinhole(const float *K, const float *D, int W, int H, float *mx, float *my) {
+    double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    double k1 = D[0], k2 = D[1], p1 = D[2], p2 = D[3];
+    for (int v = 0; v < H; v++)
+        for (int u = 0; u < W; u++) {
+            double x = ((double)u - cx) / fx, y = ((double)v - cy) / fy;
+            double x2 = x * x, y2 = y * y, r2 = x2 + y2, _2xy = 2 * x * y;
+            double kr = 1 + ((0. * r2 + k2) * r2 + k1) * r2;
+            double xd = x * kr + p1 * _2xy + p2 * (r2 + 2 * x2);
+            double yd = y * kr + p1 * (r2 + 2 * y2) + p2 * _2xy;
+            mx[v * W + u] = (float)(fx * xd + cx);
+            my[v * W + u] = (float)(fy * yd + cy);
+        }
+}
+
+/* cv::fisheye::initUndistortRectifyMap(K,D,I,K,size,CV_32F,mX,mY): PPGExtractor.cpp:66.
+ * (Computed by the reference but unused for every shipped config because D[0]==0, :261.) */
+void ppgo_init_undistort_map_fisheye(const float *K, const float *D, int W, int H, float *mx, float *my) {
+    double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    double k[4] = {D[0], D[1], D[2], D[3]};
+    for (int v = 0; v < H; v++)
+        for (int u = 0; u < W; u++) {
+            double x = ((double)u - cx) / fx, y = ((double)v - cy) / fy;
+            double r = sqrt(x * x + y * y);
+            double theta = atan(r);
+            double t2 = theta * theta, t4 = t2 * t2, t6 = t4 * t2, t8 = t4 * t4;
+            double theta_d = theta * (1 + k[0] * t2 + k[1] * t4 + k[2] * t6 + k[3] * t8);
+            double scale = (r == 0) ? 1.0 : theta_d / r;
+            mx[v * W + u] = (float)(fx * x * scale + cx);
+            my[v * W + u] = (float)(fy * y * scale + cy);
+        }
+}
+
+/* cv::remap(src,dst,mX,mY,INTER_LINEAR) with BORDER_CONSTANT 0: PPGExtractor.cpp:262.
+ * Fixed-point (1/32) bilinear exactly as cv2 4.13 evaluates it for CV_32F. */
+void ppgo_remap_linear(const float *src, int W, int H, const float *mx, const float *my, float *dst) {
+    for (int i = 0; i < W * H; i++) {
+        int sx = (int)lrint((double)(mx[i] * 32.0f)), sy = (int)lrint((double)(my[i] * 32.0f));
+        int ix = sx >> 5, iy = sy >> 5;
+        float fx = (float)(sx & 31) * (1.0f / 32.0f), fy = (float)(sy & 31) * (1.0f / 32.0f);
+        float w00 = (1.0f - fy) * (1.0f - fx), w01 = (1.0f - fy) * fx, w10 = fy * (1.0f - fx), w11 = fy * fx;
+        float s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+        if (iy >= 0 && iy < H) {
+            if (ix >= 0 && ix < W) s00 = src[iy * W + ix];
+            if (ix + 1 >= 0 && ix + 1 < W) s01 = src[iy * W + ix + 1];
+        }
+        if (iy + 1 >= 0 && iy + 1 < H) {
+            if (ix >= 0 && ix < W) s10 = src[(iy + 1) * W + ix];
+            if (ix + 1 >= 0 && ix + 1 < W) s11 = src[(iy + 1) * W + ix + 1];
+        }
+        dst[i] = ((s00 * w00 + s01 * w01) + s10 * w10) + s11 * w11;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* PPGExtractor::detectKeyPoint, feature/src/PPGExtractor.cpp:158-234 (from the H x W prob map) */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct {
+    float score;
+    int idx;
+} cand_t;
+static int cand_cmp(const void *a, const void *b) {
+    const cand_t *x = a, *y = b;
+    if (x->score > y->score) return -1; /* :180 descending by score */
+    if (x->score < y->score) return 1;
+    return (x->idx > y->idx) - (x->idx < y->idx); /* divergence 1: ties by raster index */
+}
+
+/* -> N.  x,y integer pixel, score, (xun,yun) = mPosUn, out = mbOut.  n_cand receives the number of
+ * pixels >= threshold (diagnostic). */
+int ppgo_detect_keypoints(const ppgo_cfg *c, const float *prob, int *kx, int *ky, float *kscore, float *kxun,
+                          float *kyun, uint8_t *kout, int *n_cand) {
+    int W = c->width, H = c->height, R = c->junction_nms_radius;
+    cand_t *cand = malloc(sizeof(cand_t) * (size_t)W * H);
+    int nc = 0;
+    for (int i = 0; i < H; i++) /* :168-177 */
+        for (int j = 0; j < W; j++) {
+            float s = prob[i * W + j];
+            if (s < c->junction_thresh) continue;
+            cand[nc].score = s;
+            cand[nc].idx = i * W + j;
+            nc++;
+        }
+    if (n_cand) *n_cand = nc;
+    qsort(cand, nc, sizeof(cand_t), cand_cmp);
+    unsigned char *flag = calloc((size_t)W * H, 1); /* :181 */
+    int n = 0;
+    for (int t = 0; t < nc; t++) { /* :185-206 */
+        int px = cand[t].idx % W, py = cand[t].idx / W;
+        if (px < R || px > (W - R - 1) || py < R || py > (H - R - 1) || flag[py * W + px] != 0) continue;
+        flag[py * W + px] = 1;
+        kx[n] = px;
+        ky[n] = py;
+        kscore[n] = cand[t].score;
+        n++;
+        if ((unsigned)n + 1 > (unsigned)c->junction_max_num) break;
+        for (int i = py - R; i <= py + R; i++)
+            for (int j = px - R; j <= px + R; j++) {
+                if (i < 0 || i > H || j < 0 || j > W) continue;
+                flag[i * W + j] = (unsigned char)-1;
+            }
+    }
+    free(flag);
+    free(cand);
+    if (n == 0) return 0; /* :210 */
+    float *pts = malloc(sizeof(float) * 2 * n), *und = malloc(sizeof(float) * 2 * n);
+    for (int i = 0; i < n; i++) {
+        pts[2 * i] = (float)kx[i];
+        pts[2 * i + 1] = (float)ky[i];
+    }
+    if (c->fisheye)
+        ppgo_undistort_points_fisheye(c->K, c->D, pts, n, und);
+    else
+        ppgo_undistort_points_pinhole(c->K, c->D, pts, n, und);
+    for (int i = 0; i < n; i++) { /* :226-233 */
+        float u = und[2 * i], v = und[2 * i + 1];
+        kout[i] = 1; /* KeyPointEx ctor: mbOut(true) */
+        if (u >= 1 && u < W - 1 && v >= 1 && v < H - 1) kout[i] = 0;
+        kxun[i] = u;
+        kyun[i] = v;
+    }
+    free(pts);
+    free(und);
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* PPGExtractor::refineHeatMap :540-578 applied tile by tile as in detectLines :243-256          */
+/* ------------------------------------------------------------------------------------------- */
+static int fdesc_cmp(const void *a, const void *b) {
+    float x = *(const float *)a, y = *(const float *)b;
+    return (x < y) - (x > y);
+}
+static void refine_tile(const ppgo_cfg *c, float *s, int stride, int segH, int segW) {
+    float *v = malloc(sizeof(float) * (size_t)segH * segW);
+    size_t n = 0;
+    for (int i = 0; i < segH; i++)
+        for (int j = 0; j < segW; j++)
+            if (s[i * stride + j] > c->line_valid_thresh) v[n++] = s[i * stride + j];
+    int valCount = (int)(c->line_valid_ratio * (float)n); /* :554 float * size_t */
+    if (valCount < 1) {
+        free(v);
+        return;
+    }
+    if ((double)n >= (double)(segH * segW) * 0.9 && (double)v[(size_t)((double)n * 0.9)] > 0.1) { /* :557 */
+        for (int i = 0; i < segH; i++)
+            for (int j = 0; j < segW; j++) s[i * stride + j] = 0.0f;
+        free(v);
+        return;
+    }
+    qsort(v, n, sizeof(float), fdesc_cmp); /* :562 descending */
+    double acc = 0.0;
+    for (int i = 0; i < valCount; i++) acc += (double)v[i];       /* std::accumulate(...,0.0) */
+    float ave = (float)(acc / (double)(float)valCount);            /* :563 */
+    for (int i = 0; i < segH; i++)
+        for (int j = 0; j < segW; j++) {
+            float cur = s[i * stride + j];
+            if (cur > c->line_valid_thresh) {
+                float ns = cur / ave;
+                s[i * stride + j] = ((double)ns > 1.0) ? 1.0f : ns;
+            } else
+                s[i * stride + j] = 0.0f;
+        }
+    free(v);
+}
+
+void ppgo_refine_heat(const ppgo_cfg *c, float *heat) {
+    int W = c->width, H = c->height, S = c->heatmap_refine_sz;
+    int gx = W / S, gy = H / S;
+    for (int i = 0; i < gy; i++)
+        for (int j = 0; j < gx; j++) {
+            int h0 = i * S, w0 = j * S;
+            int h1 = (i == gy - 1) ? H : (i + 1) * S, w1 = (j == gx - 1) ? W : (j + 1) * S;
+            refine_tile(c, heat + h0 * W + w0, W, h1 - h0, w1 - w0);
+        }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* PPGExtractor::detectLines :259-441 from the refined (and, for pinhole, remapped) heat map     */
+/* ------------------------------------------------------------------------------------------- */
+static const float invSampleGapTable[4] = {0.3333, 0.200, 0.1427, 0.1111}; /* :19 */
+
+typedef struct {
+    int s, e;
+    int bad;
+    float lscore;
+} line_t;
+typedef struct {
+    int *v;
+    int n, cap;
+} ivec;
+static void ivec_push(ivec *a, int x) {
+    if (a->n == a->cap) {
+        a->cap = a->cap ? a->cap * 2 : 8;
+        a->v = realloc(a->v, sizeof(int) * a->cap);
+    }
+    a->v[a->n++] = x;
+}
+
+static float bilinear(const float *M, int W, float ptX, float ptY) { /* :580-589 */
+    int x1 = (int)ptX, x2 = x1 + 1, y1 = (int)ptY, y2 = y1 + 1;
+    float data1 = ((float)x2 - ptX) * M[y1 * W + x1] + (ptX - (float)x1) * M[y1 * W + x2];
+    float data2 = ((float)x2 - ptX) * M[y2 * W + x1] + (ptX - (float)x1) * M[y2 * W + x2];
+    return ((float)y2 - ptY) * data1 + (ptY - (float)y1) * data2;
+}
+
+static void seg_params(float dist, float invScale, int *segNum, float *step) {
+    int lenLevel = (int)((double)(dist * invScale) * 4.0);       /* :485 */
+    *segNum = (int)(dist * invSampleGapTable[lenLevel]);          /* :486 */
+    *step = (float)(1.0 / (double)(float)(*segNum));              /* :487 */
+}
+
+static float inlier_rate(const ppgo_cfg *c, const float *heat, float invScale, float psx, float psy, float pex,
+                         float pey) { /* :461-498 */
+    int W = c->width;
+    float dx = psx - pex, dy = psy - pey;
+    float dist = sqrtf(dx * dx + dy * dy);
+    int segNum;
+    float step;
+    seg_params(dist, invScale, &segNum, &step);
+    int cnt = 0;
+    for (int i = 1; i < segNum; i++) {
+        float sx = (psx * step) * (float)i + (pex * step) * (float)(segNum - i);
+        float sy = (psy * step) * (float)i + (pey * step) * (float)(segNum - i);
+        int posx = (int)((double)sx + 0.5), posy = (int)((double)sy + 0.5);
+        if (heat[posy * W + posx] > c->line_heatmap_thresh) cnt++;
+    }
+    return (float)cnt / (float)(segNum - 1);
+}
+
+static float line_score(const ppgo_cfg *c, const float *heat, float invScale, float psx, float psy, float pex,
+                        float pey) { /* :500-513 */
+    int W = c->width;
+    float dx = psx - pex, dy = psy - pey;
+    float dist = sqrtf(dx * dx + dy * dy);
+    int segNum;
+    float step;
+    seg_params(dist, invScale, &segNum, &step);
+    float sum = 0.f;
+    for (int i = 1; i < segNum; i++) {
+        float sx = (psx * step) * (float)i + (pex * step) * (float)(segNum - i);
+        float sy = (psy * step) * (float)i + (pey * step) * (float)(segNum - i);
+        sum += bilinear(heat, W, sx, sy);
+    }
+    return sum / (float)(segNum - 1);
+}
+
+/* dirMat/distMat entries are pure functions of the two endpoints (:268-288); evaluate on demand. */
+static float dist_of(const float *xun, const float *yun, int a, int b) {
+    int i = a < b ? a : b, j = a < b ? b : a;
+    float dx = xun[j] - xun[i], dy = yun[j] - yun[i];
+    return sqrtf(dx * dx + dy * dy);
+}
+static float dir_of(const float *xun, const float *yun, int a, int b) {
+    int i = a < b ? a : b, j = a < b ? b : a;
+    float dx = xun[j] - xun[i], dy = yun[j] - yun[i];
+    float dist = sqrtf(dx * dx + dy * dy);
+    float d = o_atan2f(dy / dist, dx / dist); /* :280-283 */
+    if (a < b) return d;
+    float r = (float)((double)d - PPGO_PI);   /* :284 */
+    if ((double)r < -PPGO_PI) r = (float)((double)r + PPGO_2PI); /* :285-286 */
+    return r;
+}
+
+/* one adjacency scan of the overlap filter, :316-335 / :338-357.  p = shared endpoint, q = new other. */
+static int overlap_scan(const ppgo_cfg *c, const float *xun, const float *yun, line_t *lines, const ivec *adj, int p,
+                        int q) {
+    int isOverlap = 0;
+    for (int t = 0; t < adj->n; t++) {
+        line_t *lo = &lines[adj->v[t]];
+        if (lo->bad) continue;
+        int pid_old = (p == lo->s) ? lo->e : lo->s;
+        float a = dir_of(xun, yun, p, q) - dir_of(xun, yun, p, pid_old);
+        if ((double)a < -PPGO_PI) a = (float)((double)a + PPGO_2PI);
+        if ((double)a > PPGO_PI) a = (float)((double)a - PPGO_2PI);
+        a = fabsf(a);
+        if ((double)a > 0.2 * PPGO_PI) continue;
+        float distNew = dist_of(xun, yun, p, q), distOld = dist_of(xun, yun, p, pid_old);
+#if PPGO_LIBM_FLOAT == 2
+        float s = sinf(a);
+#else
+        float s = (float)sin((double)a); /* :330 unqualified sin -> double overload */
+#endif
+        if (distNew <= distOld && distNew * s < c->line_dist_thresh) lo->bad = 1;
+        if (distOld < distNew && distOld * s < c->line_dist_thresh) isOverlap = 1;
+    }
+    return isOverlap;
+}
+
+/* Outputs (caller-allocated, capacities in brackets):
+ *   edge_s/edge_e/edge_score [max_edges]  final mvKeyEdges (:433-441), returns E (or -1 if > max_edges)
+ *   conn_off [n+1], conn_idx [2*max_edges]     CSR of KeyPointEx::mvConnected (final edge indices)
+ *   col_off [n+1], col_pairs [2*max_col]       CSR of KeyPointEx::mvColine (p1,p2 pairs), *n_col total pairs
+ *   stats[0]=pairs passing the 3-point test, stats[1]=candidateLines.size(), stats[2]=bad after filter */
+int ppgo_detect_lines(const ppgo_cfg *c, const float *heat, int n, const float *xun, const float *yun,
+                      const uint8_t *kout, int max_edges, int *edge_s, int *edge_e, float *edge_score, int *conn_off,
+                      int *conn_idx, int max_col, int *col_off, int *col_pairs, int *n_col, int *stats) {
+    int W = c->width, H = c->height;
+    float invScale = 1.0f / sqrtf((float)(H * H + W * W)); /* :74 */
+    line_t *lines = NULL;
+    int nl = 0, capl = 0;
+    ivec *adj = calloc(n > 0 ? n : 1, sizeof(ivec));
+    int npass = 0;
+    for (int i = 0; i < n; i++) { /* :293-365 */
+        if (kout[i]) continue;
+        for (int j = i + 1; j < n; j++) {
+            if (kout[j]) continue;
+            float c1x = xun[j] * 0.2f + xun[i] * 0.8f, c1y = yun[j] * 0.2f + yun[i] * 0.8f;
+            float c2x = xun[j] * 0.8f + xun[i] * 0.2f, c2y = yun[j] * 0.8f + yun[i] * 0.2f;
+            float c3x = xun[j] * 0.5f + xun[i] * 0.5f, c3y = yun[j] * 0.5f + yun[i] * 0.5f;
+            if (heat[(int)((double)c1y + 0.5) * W + (int)((double)c1x + 0.5)] < c->line_heatmap_thresh) continue;
+            if (heat[(int)((double)c2y + 0.5) * W + (int)((double)c2x + 0.5)] < c->line_heatmap_thresh) continue;
+            if (heat[(int)((double)c3y + 0.5) * W + (int)((double)c3x + 0.5)] < c->line_heatmap_thresh) continue;
+            npass++;
+            if (overlap_scan(c, xun, yun, lines, &adj[i], i, j)) continue;
+            if (overlap_scan(c, xun, yun, lines, &adj[j], j, i)) continue;
+            if (nl == capl) {
+                capl = capl ? capl * 2 : 256;
+                lines = realloc(lines, sizeof(line_t) * capl);
+            }
+            lines[nl].s = i;
+            lines[nl].e = j;
+            lines[nl].bad = 0;
+            lines[nl].lscore = 0.f;
+            ivec_push(&adj[i], nl);
+            ivec_push(&adj[j], nl);
+            nl++;
+        }
+    }
+    if (stats) {
+        stats[0] = npass;
+        stats[1] = nl;
+        int nb = 0;
+        for (int i = 0; i < nl; i++) nb += lines[i].bad;
+        stats[2] = nb;
+    }
+    for (int i = 0; i < n; i++) adj[i].n = 0; /* :366 */
+    for (int i = 0; i < nl; i++) {            /* :367-389 */
+        line_t *kl = &lines[i];
+        if (kl->bad) continue;
+        float psx = xun[kl->s], psy = yun[kl->s], pex = xun[kl->e], pey = yun[kl->e];
+        float si = inlier_rate(c, heat, invScale, psx, psy, pex, pey);
+        if (si < c->line_inlier_rate) {
+            kl->bad = 1;
+            continue;
+        }
+        float sh = line_score(c, heat, invScale, psx, psy, pex, pey);
+        if (sh < c->line_heatmap_thresh) {
+            kl->bad = 1;
+            continue;
+        }
+        kl->lscore = si * sh;
+        ivec_push(&adj[kl->s], i);
+        ivec_push(&adj[kl->e], i);
+    }
+    /* colinearity :392-432 */
+    int ncol = 0, col_overflow = 0;
+    for (int p = 0; p < n; p++) {
+        col_off[p] = ncol;
+        int m = adj[p].n;
+        int *ti = malloc(sizeof(int) * (m > 0 ? m : 1));
+        memcpy(ti, adj[p].v, sizeof(int) * m);
+        while (m > 1) {
+            double minPD = 1e9;
+            int bp1 = -1, bp2 = -1, bestId = -1;
+            line_t *kl1 = &lines[ti[m - 1]];
+            if (kl1->bad) {
+                m--;
+                continue;
+            }
+            for (int i = 0; i < m - 1; i++) {
+                line_t *kl2 = &lines[ti[i]];
+                if (kl2->bad) continue;
+                int p1 = (p == kl1->s) ? kl1->e : kl1->s, p2 = (p == kl2->s) ? kl2->e : kl2->s;
+                float ad = dir_of(xun, yun, p, p1) - dir_of(xun, yun, p, p2);
+                double pd = 0.5 * (double)(dist_of(xun, yun, p, p1) + dist_of(xun, yun, p, p2)) *
+                            (double)fabsf(o_sinf(ad)); /* :413 */
+                if (minPD > pd) {
+                    minPD = pd;
+                    bestId = i;
+                    bp1 = p1;
+                    bp2 = p2;
+                }
+            }
+            if (minPD > (double)c->line_dist_thresh) {
+                m--;
+                continue;
+            }
+            if (ncol < max_col) {
+                col_pairs[2 * ncol] = bp1;
+                col_pairs[2 * ncol + 1] = bp2;
+            } else
+                col_overflow = 1;
+            ncol++;
+            m--;
+            ti[bestId] = ti[m - 1];
+            m--;
+        }
+        free(ti);
+    }
+    col_off[n] = ncol;
+    *n_col = col_overflow ? -1 : ncol;
+    /* final edges + mvConnected :433-441 */
+    int E = 0, overflow = 0;
+    ivec *fin = calloc(n > 0 ? n : 1, sizeof(ivec));
+    for (int i = 0; i < nl; i++) {
+        if (lines[i].bad) continue;
+        if (E < max_edges) {
+            edge_s[E] = lines[i].s;
+            edge_e[E] = lines[i].e;
+            edge_score[E] = lines[i].lscore;
+        } else
+            overflow = 1;
+        ivec_push(&fin[lines[i].s], E);
+        ivec_push(&fin[lines[i].e], E);
+        E++;
+    }
+    int k = 0;
+    for (int p = 0; p < n; p++) {
+        conn_off[p] = k;
+        for (int t = 0; t < fin[p].n; t++) {
+            if (!overflow) conn_idx[k] = fin[p].v[t];
+            k++;
+        }
+        free(fin[p].v);
+        free(adj[p].v);
+    }
+    conn_off[n] = k;
+    free(fin);
+    free(adj);
+    free(lines);
+    return overflow ? -1 : E;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* PPGExtractor::genPointDescriptor :515-538.  desc is the raw dense map, CHW (256,Hc,Wc) fp32.  */
+/* grid_sampler(bilinear, zeros, align_corners=false) + F.normalize(dim=1) restated from ATen.    */
+/* ------------------------------------------------------------------------------------------- */
+void ppgo_sample_descriptors(const ppgo_cfg *c, const float *desc, int C, int Hc, int Wc, int n, const int *kx,
+                             const int *ky, float *out) {
+    if (n < 10) { /* :520-524 */
+        memset(out, 0, sizeof(float) * (size_t)n * C);
+        return;
+    }
+    for (int i = 0; i < n; i++) {
+        float gx = (float)((double)((float)kx[i] / (float)c->width) * 2. - 1.);  /* :530 */
+        float gy = (float)((double)((float)ky[i] / (float)c->height) * 2. - 1.); /* :531 */
+        float ix = ((gx + 1.f) * (float)Wc - 1.f) / 2.f, iy = ((gy + 1.f) * (float)Hc - 1.f) / 2.f;
+        float x0f = floorf(ix), y0f = floorf(iy);
+        int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
+        float nw = ((float)x1 - ix) * ((float)y1 - iy), ne = (ix - (float)x0) * ((float)y1 - iy);
+        float sw = ((float)x1 - ix) * (iy - (float)y0), se = (ix - (float)x0) * (iy - (float)y0);
+        double ss = 0.0;
+        float *o = out + (size_t)i * C;
+        for (int ch = 0; ch < C; ch++) {
+            const float *p = desc + (size_t)ch * Hc * Wc;
+            float r = 0.f;
+            if (y0 >= 0 && y0 < Hc && x0 >= 0 && x0 < Wc) r += p[y0 * Wc + x0] * nw;
+            if (y0 >= 0 && y0 < Hc && x1 >= 0 && x1 < Wc) r += p[y0 * Wc + x1] * ne;
+            if (y1 >= 0 && y1 < Hc && x0 >= 0 && x0 < Wc) r += p[y1 * Wc + x0] * sw;
+            if (y1 >= 0 && y1 < Hc && x1 >= 0 && x1 < Wc) r += p[y1 * Wc + x1] * se;
+            o[ch] = r;
+            ss += (double)r * (double)r;
+        }
+        float nrm = (float)sqrt(ss);
+        if (nrm < 1e-12f) nrm = 1e-12f;
+        for (int ch = 0; ch < C; ch++) o[ch] = o[ch] / nrm;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* Association: DescriptorDistance, the Frame grid, the ExtendMapMatches search core             */
+/* ------------------------------------------------------------------------------------------- */
+
+/* DescriptorDistance, feature/src/MapPoint.cpp:22-29: ||a-b||_2 over 256 floats.  Eigen's vectorised
+ * reduction order is unspecified; the contract shared with the CUDA path is the fixed order below:
+ * 32 strided partial sums (lane l adds elements l, l+32, ... in order), then a butterfly
+ * (xor 16,8,4,2,1) -- every lane ends with the same value. */
+float ppgo_descriptor_distance(const float *a, const float *b, int dim) {
+    float part[32];
+    for (int l = 0; l < 32; l++) {
+        float s = 0.f;
+        for (int k = l; k < dim; k += 32) {
+            float d = a[k] - b[k];
+            s = s + d * d;
+        }
+        part[l] = s;
+    }
+    for (int m = 16; m >= 1; m >>= 1) {
+        float t[32];
+        for (int l = 0; l < 32; l++) t[l] = part[l] + part[l ^ m];
+        memcpy(part, t, sizeof(t));
+    }
+    return sqrtf(part[0]);
+}
+
+typedef struct {
+    int minX, minY, maxX, maxY; /* mnMinX.. GeometricCamera.cpp:26-61 */
+    float wInv, hInv;           /* mfGridElementWidthInv/HeightInv */
+} ppgo_bounds;
+
+/* GeometricCamera::InitializeImageBounds, sensors/src/GeometricCamera.cpp:26-61 */
+void ppgo_image_bounds(const ppgo_cfg *c, ppgo_bounds *b) {
+    if (!c->fisheye) {
+        float cor[8] = {0.f, 0.f, (float)c->width, 0.f, 0.f, (float)c->height, (float)c->width, (float)c->height};
+        float u[8];
+        ppgo_undistort_points_pinhole(c->K, c->D, cor, 4, u);
+        b->minX = (int)fminf(u[0], u[4]);
+        b->maxX = (int)fmaxf(u[2], u[6]);
+        b->minY = (int)fminf(u[1], u[3]);
+        b->maxY = (int)fmaxf(u[5], u[7]);
+    } else {
+        b->minX = 0;
+        b->minY = 0;
+        b->maxX = c->width;
+        b->maxY = c->height;
+    }
+    b->wInv = 64.0f / (float)(b->maxX - b->minX);
+    b->hInv = 48.0f / (float)(b->maxY - b->minY);
+}
+
+/* Frame::PosInGrid, map/src/Frame.cpp:317-327.  -> 1 if indexable */
+int ppgo_pos_in_grid(const ppgo_bounds *b, float x, float y, int *px, int *py) {
+    *px = (int)roundf((x - (float)b->minX) * b->wInv);
+    *py = (int)roundf((y - (float)b->minY) * b->hInv);
+    if (*px < 0 || *px >= 64 || *py < 0 || *py >= 48) return 0;
+    return 1;
+}
+
+/* Frame::AssignFeaturesToGrid + GetFeaturesInArea, map/src/Frame.cpp:138-156, 262-315, literally.
+ * grid_off[64*48+1] / grid_idx[n] is the cell lists in (ix*48+iy) order.  -> count, indices into out. */
+void ppgo_grid_build(const ppgo_bounds *b, int n, const float *x, const float *y, int *grid_off, int *grid_idx) {
+    int *cell = malloc(sizeof(int) * (n > 0 ? n : 1));
+    memset(grid_off, 0, sizeof(int) * (64 * 48 + 1));
+    for (int i = 0; i < n; i++) {
+        int px, py;
+        cell[i] = ppgo_pos_in_grid(b, x[i], y[i], &px, &py) ? px * 48 + py : -1;
+        if (cell[i] >= 0) grid_off[cell[i] + 1]++;
+    }
+    for (int k = 0; k < 64 * 48; k++) grid_off[k + 1] += grid_off[k];
+    int *fill = calloc(64 * 48, sizeof(int));
+    for (int i = 0; i < n; i++)
+        if (cell[i] >= 0) grid_idx[grid_off[cell[i]] + fill[cell[i]]++] = i;
+    free(fill);
+    free(cell);
+}
+
+int ppgo_features_in_area(const ppgo_bounds *b, const int *grid_off, const int *grid_idx, const float *kx,
+                          const float *ky, float x, float y, float r, int *out) {
+    int cnt = 0;
+    int nMinCellX = (int)floorf((x - (float)b->minX - r) * b->wInv);
+    if (nMinCellX < 0) nMinCellX = 0;
+    if (nMinCellX >= 64) return 0;
+    int nMaxCellX = (int)ceilf((x - (float)b->minX + r) * b->wInv);
+    if (nMaxCellX > 63) nMaxCellX = 63;
+    if (nMaxCellX < 0) return 0;
+    int nMinCellY = (int)floorf((y - (float)b->minY - r) * b->hInv);
+    if (nMinCellY < 0) nMinCellY = 0;
+    if (nMinCellY >= 48) return 0;
+    int nMaxCellY = (int)ceilf((y - (float)b->minY + r) * b->hInv);
+    if (nMaxCellY > 47) nMaxCellY = 47;
+    if (nMaxCellY < 0) return 0;
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            int c0 = grid_off[ix * 48 + iy], c1 = grid_off[ix * 48 + iy + 1];
+            for (int t = c0; t < c1; t++) {
+                int id = grid_idx[t];
+                float dx = kx[id] - x, dy = ky[id] - y;
+                if (fabsf(dx) < r && fabsf(dy) < r) out[cnt++] = id;
+            }
+        }
+    return cnt;
+}
+
+/* Search core of Matcher::ExtendMapMatches, matching/src/Matcher.cpp:224-281, for one map point with
+ * the frame state frozen (free_mask[idx]!=0 <=> keypoint idx is NOT skipped at :253).  This is the
+ * data-parallel contract of ppg_associate(): the sequential consumption (:278-378) stays in the host
+ * shim.  Candidate order = GetFeaturesInArea order (cell-major), ties keep the first (strict <).
+ * -> accept flag; outputs best/second idx and distances (second_idx=-1, d=1e6 when absent). */
+int ppgo_search_core(const ppgo_bounds *b, const int *grid_off, const int *grid_idx, int n, const float *kx,
+                     const float *ky, const float *frame_desc, const uint8_t *free_mask, const float *mp_desc,
+                     float proj_x, float proj_y, float view_cos, float th, float ratio, float th_high,
+                     int *best_idx, int *second_idx, float *best_d, float *second_d) {
+    float bestDist = 1e6f, bestDist2 = 1e6f;
+    int bestIdx = -1, bestIdx2 = -1;
+    float r = th;
+    if ((double)view_cos > 0.998) /* :240-244: float compared with a double literal, r *= double */
+        r = (float)((double)r * 2.5);
+    else
+        r = (float)((double)r * 4.0);
+    int *cand = malloc(sizeof(int) * (n > 0 ? n : 1));
+    int nc = ppgo_features_in_area(b, grid_off, grid_idx, kx, ky, proj_x, proj_y, r, cand);
+    for (int t = 0; t < nc; t++) {
+        int idx = cand[t];
+        if (!free_mask[idx]) continue;
+        float dist = ppgo_descriptor_distance(mp_desc, frame_desc + (size_t)idx * 256, 256);
+        if (dist < bestDist) {
+            bestDist2 = bestDist;
+            bestIdx2 = bestIdx;
+            bestDist = dist;
+            bestIdx = idx;
+        } else if (dist < bestDist2) {
+            bestDist2 = dist;
+            bestIdx2 = idx;
+        }
+    }
+    free(cand);
+    *best_idx = bestIdx;
+    *second_idx = bestIdx2;
+    *best_d = bestDist;
+    *second_d = bestDist2;
+    if (nc == 0 || bestIdx < 0) return 0;
+    if (bestDist > th_high && bestDist > ratio * bestDist2) return 0; /* :276 */
+    return 1;
+}
+
+void ppgo_search_all(const ppgo_cfg *c, int n, const float *kx, const float *ky, const float *frame_desc,
+                     const uint8_t *free_mask, int m, const float *map_desc, const float *proj_uv,
+                     const float *view_cos, float th, float ratio, float th_high, int *best_idx, int *second_idx,
+                     float *best_d, float *second_d, uint8_t *accept) {
+    ppgo_bounds b;
+    ppgo_image_bounds(c, &b);
+    int *goff = malloc(sizeof(int) * (64 * 48 + 1)), *gidx = malloc(sizeof(int) * (n > 0 ? n : 1));
+    ppgo_grid_build(&b, n, kx, ky, goff, gidx);
+    for (int j = 0; j < m; j++)
+        accept[j] = (uint8_t)ppgo_search_core(&b, goff, gidx, n, kx, ky, frame_desc, free_mask,
+                                              map_desc + (size_t)j * 256, proj_uv[2 * j], proj_uv[2 * j + 1],
+                                              view_cos[j], th, ratio, th_high, &best_idx[j], &second_idx[j],
+                                              &best_d[j], &second_d[j]);
+    free(goff);
+    free(gidx);
+}

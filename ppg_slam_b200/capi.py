@@ -1,0 +1,309 @@
+"""ctypes binding of the C ABI in include/ppg_b200.h (libppg_b200.so).
+
+This is the same binding a maintainer would write for any FFI host; tests and bench.py drive the
+product exclusively through it.  There is no fallback: if the library is missing, loading raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libppg_b200.so")
+DEFAULT_WEIGHTS = os.path.join(HERE, "weights", "ppg_weights.bin")
+
+PPG_OK, PPG_ERR_ARG, PPG_ERR_CUDA, PPG_ERR_WEIGHTS, PPG_ERR_CAPACITY, PPG_ERR_NCCL = 0, -1, -2, -3, -4, -5
+
+
+class PpgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("ppg error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("width", C.c_int), ("height", C.c_int), ("K", C.c_float * 9),
+                ("D", C.c_float * 4), ("fisheye", C.c_int), ("weights_path", C.c_char_p),
+                ("junction_thresh", C.c_float), ("junction_nms_radius", C.c_int), ("junction_max_num", C.c_int),
+                ("line_valid_thresh", C.c_float), ("line_valid_ratio", C.c_float), ("line_dist_thresh", C.c_float),
+                ("heatmap_refine_sz", C.c_int), ("line_heatmap_thresh", C.c_float), ("line_inlier_rate", C.c_float),
+                ("th_low", C.c_float), ("th_high", C.c_float), ("max_batch", C.c_int), ("max_edges", C.c_int),
+                ("max_colines", C.c_int), ("max_map_points", C.c_int)]
+
+
+class FrameOut(C.Structure):
+    _fields_ = [("n_kp", C.c_int), ("n_edges", C.c_int), ("n_colines", C.c_int), ("status", C.c_uint32),
+                ("n_candidates", C.c_int), ("n_pairs_tested_ok", C.c_int), ("n_candidate_lines", C.c_int),
+                ("nms_rounds", C.c_int),
+                ("kp_x", C.POINTER(C.c_float)), ("kp_y", C.POINTER(C.c_float)),
+                ("kp_px", C.POINTER(C.c_int32)), ("kp_py", C.POINTER(C.c_int32)),
+                ("kp_score", C.POINTER(C.c_float)), ("kp_xun", C.POINTER(C.c_float)),
+                ("kp_yun", C.POINTER(C.c_float)), ("kp_out", C.POINTER(C.c_uint8)),
+                ("edge_start", C.POINTER(C.c_int32)), ("edge_end", C.POINTER(C.c_int32)),
+                ("edge_score", C.POINTER(C.c_float)), ("conn_off", C.POINTER(C.c_int32)),
+                ("conn_idx", C.POINTER(C.c_int32)), ("col_off", C.POINTER(C.c_int32)),
+                ("col_pairs", C.POINTER(C.c_int32)), ("desc", C.POINTER(C.c_float))]
+
+
+class AssocIn(C.Structure):
+    _fields_ = [("n_kp", C.c_int), ("kp_x", C.POINTER(C.c_float)), ("kp_y", C.POINTER(C.c_float)),
+                ("frame_desc", C.POINTER(C.c_float)), ("free_mask", C.POINTER(C.c_uint8)), ("n_rows", C.c_int),
+                ("proj_uv", C.POINTER(C.c_float)), ("view_cos", C.POINTER(C.c_float)), ("th", C.c_float),
+                ("ratio", C.c_float)]
+
+
+class AssocOut(C.Structure):
+    _fields_ = [("best_idx", C.POINTER(C.c_int32)), ("second_idx", C.POINTER(C.c_int32)),
+                ("best_dist", C.POINTER(C.c_float)), ("second_dist", C.POINTER(C.c_float)),
+                ("accept", C.POINTER(C.c_uint8))]
+
+
+# every symbol include/ppg_b200.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", "ppg_api_version", "ppg_extract",
+           "ppg_upload_frames", "ppg_run", "ppg_download", "ppg_sync", "ppg_extract_from_maps", "ppg_get_maps",
+           "ppg_selftest_conv", "ppg_set_profiling", "ppg_get_stage_times", "ppg_launch_count", "ppg_timer_start",
+           "ppg_timer_stop", "ppg_upload_map", "ppg_associate", "ppg_assoc_stage", "ppg_assoc_run",
+           "ppg_assoc_fetch", "ppg_assoc_run_frame", "ppg_assoc_fallback_rows", "ppg_assoc_device_results",
+           "ppg_stream"]
+
+_lib = None
+
+
+def load():
+    """Loads libppg_b200.so (raises OSError if it has not been built: there is no fallback)."""
+    global _lib
+    if _lib is None:
+        lib = C.CDLL(LIB_PATH)
+        lib.ppg_last_error.restype = C.c_char_p
+        lib.ppg_last_error.argtypes = [C.c_void_p]
+        lib.ppg_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        lib.ppg_destroy.argtypes = [C.c_void_p]
+        lib.ppg_destroy.restype = None
+        lib.ppg_launch_count.restype = C.c_longlong
+        lib.ppg_launch_count.argtypes = [C.c_void_p]
+        lib.ppg_stream.restype = C.c_void_p
+        lib.ppg_stream.argtypes = [C.c_void_p]
+        for name in ["ppg_extract", "ppg_upload_frames", "ppg_run", "ppg_download", "ppg_sync",
+                     "ppg_extract_from_maps", "ppg_get_maps", "ppg_selftest_conv", "ppg_set_profiling",
+                     "ppg_get_stage_times", "ppg_timer_start", "ppg_timer_stop", "ppg_upload_map", "ppg_associate",
+                     "ppg_assoc_stage", "ppg_assoc_run", "ppg_assoc_fetch", "ppg_assoc_run_frame",
+                     "ppg_assoc_fallback_rows", "ppg_assoc_device_results"]:
+            getattr(lib, name).restype = C.c_int
+        _lib = lib
+    return _lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _frame_to_dict(o):
+    """Copies one ppg_frame_out record out of the ctx-owned pinned memory into numpy arrays."""
+    n, E, nc = o.n_kp, o.n_edges, o.n_colines
+
+    def arr(ptr, cnt, dt):
+        if cnt <= 0:
+            return np.zeros(0, dt)
+        return np.ctypeslib.as_array(ptr, shape=(cnt,)).astype(dt, copy=True)
+
+    conn_off = arr(o.conn_off, n + 1, np.int32) if n > 0 else np.zeros(1, np.int32)
+    col_off = arr(o.col_off, n + 1, np.int32) if n > 0 else np.zeros(1, np.int32)
+    return dict(
+        n_kp=n, n_edges=E, n_colines=nc, status=int(o.status), n_cand=o.n_candidates,
+        n_pairs_ok=o.n_pairs_tested_ok, n_candidate_lines=o.n_candidate_lines, nms_rounds=o.nms_rounds,
+        kp_x=arr(o.kp_x, n, np.float32), kp_y=arr(o.kp_y, n, np.float32),
+        px=arr(o.kp_px, n, np.int32), py=arr(o.kp_py, n, np.int32), score=arr(o.kp_score, n, np.float32),
+        xun=arr(o.kp_xun, n, np.float32), yun=arr(o.kp_yun, n, np.float32), out=arr(o.kp_out, n, np.uint8),
+        edge_start=arr(o.edge_start, E, np.int32), edge_end=arr(o.edge_end, E, np.int32),
+        edge_score=arr(o.edge_score, E, np.float32), conn_off=conn_off,
+        conn_idx=arr(o.conn_idx, int(conn_off[-1]), np.int32), col_off=col_off,
+        col_pairs=arr(o.col_pairs, 2 * nc, np.int32).reshape(-1, 2),
+        desc=arr(o.desc, n * 256, np.float32).reshape(-1, 256))
+
+
+class Extractor:
+    """Host-side mirror of the reference's PPGExtractor (feature/include/PPGExtractor.h:34-148) over
+    the C ABI: constructed from a camera + weight path, `run()` takes 8-bit gray frames and returns the
+    keypoints / edges / descriptors record of PPGExtractor::run (PPGExtractor.cpp:118-147)."""
+
+    def __init__(self, cam, weights=DEFAULT_WEIGHTS, device=0, max_batch=1, **over):
+        lib = load()
+        cfg = Config()
+        lib.ppg_default_config(C.byref(cfg))
+        cfg.device, cfg.width, cfg.height, cfg.fisheye = device, cam.width, cam.height, int(cam.fisheye)
+        cfg.K[:] = cam.K
+        cfg.D[:] = cam.D
+        self._wp = os.fsencode(weights)
+        cfg.weights_path = self._wp
+        cfg.max_batch = max_batch
+        for k, v in over.items():
+            setattr(cfg, k, v)
+        self.cfg, self.cam, self.lib = cfg, cam, lib
+        self.W, self.H, self.max_batch = cam.width, cam.height, max_batch
+        h = C.c_void_p()
+        rc = lib.ppg_create(C.byref(cfg), C.byref(h))
+        if rc != PPG_OK:
+            raise PpgError(rc, lib.ppg_last_error(None).decode())
+        self.h = h
+        self._outs = (FrameOut * max_batch)()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ppg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, allow_capacity=False):
+        if rc == PPG_OK or (allow_capacity and rc == PPG_ERR_CAPACITY):
+            return rc
+        raise PpgError(rc, self.lib.ppg_last_error(self.h).decode())
+
+    # ---- PPGExtractor::run
+    def _frame_ptrs(self, frames):
+        frames = [np.ascontiguousarray(f, dtype=np.uint8) for f in frames]
+        for f in frames:
+            if f.shape != (self.H, self.W):
+                raise ValueError("frame shape %r != (%d, %d)" % (f.shape, self.H, self.W))
+        n = len(frames)
+        ptrs = (C.POINTER(C.c_uint8) * n)(*[f.ctypes.data_as(C.POINTER(C.c_uint8)) for f in frames])
+        strides = (C.c_int * n)(*[f.strides[0] for f in frames])
+        return frames, ptrs, strides, n
+
+    def run(self, frames, allow_capacity=False):
+        """frames: list of (H,W) uint8 arrays (<= max_batch).  -> list of per-frame dicts."""
+        keep, ptrs, strides, n = self._frame_ptrs(frames)
+        self._check(self.lib.ppg_extract(self.h, ptrs, strides, n, self._outs), allow_capacity)
+        return [_frame_to_dict(self._outs[i]) for i in range(n)]
+
+    def upload(self, frames):
+        keep, ptrs, strides, n = self._frame_ptrs(frames)
+        self._check(self.lib.ppg_upload_frames(self.h, ptrs, strides, n))
+        self._check(self.lib.ppg_sync(self.h))
+        return n
+
+    def run_device(self, n):
+        self._check(self.lib.ppg_run(self.h, n))
+
+    def sync(self):
+        self._check(self.lib.ppg_sync(self.h))
+
+    def download(self, n, allow_capacity=False, as_dicts=True):
+        self._check(self.lib.ppg_download(self.h, n, self._outs), allow_capacity)
+        return [_frame_to_dict(self._outs[i]) for i in range(n)] if as_dicts else None
+
+    def run_from_maps(self, prob, heat, desc_chw, allow_capacity=False):
+        """Post-processing only, fed with reference dense maps (parity entry point)."""
+        prob = np.ascontiguousarray(prob, np.float32).reshape(-1, self.H, self.W)
+        heat = np.ascontiguousarray(heat, np.float32).reshape(-1, self.H, self.W)
+        n = prob.shape[0]
+        desc = np.ascontiguousarray(desc_chw, np.float32).reshape(n, 256, self.H // 8, self.W // 8)
+        self._check(self.lib.ppg_extract_from_maps(self.h, _fp(prob), _fp(heat), _fp(desc), n, self._outs),
+                    allow_capacity)
+        return [_frame_to_dict(self._outs[i]) for i in range(n)]
+
+    def get_maps(self, frame=0, feature=False):
+        H, W = self.H, self.W
+        prob, hr, hf = (np.empty((H, W), np.float32) for _ in range(3))
+        desc = np.empty((256, H // 8, W // 8), np.float32)
+        feat = np.empty((128, H // 8, W // 8), np.float32) if feature else None
+        self._check(self.lib.ppg_get_maps(self.h, frame, _fp(prob), _fp(hr), _fp(hf), _fp(desc),
+                                          _fp(feat) if feature else None))
+        r = dict(prob=prob, heat=hr, heat_final=hf, desc=desc)
+        if feature:
+            r["feature"] = feat
+        return r
+
+    def selftest_conv(self):
+        names = (C.c_char_p * 32)()
+        d, r = (C.c_float * 32)(), (C.c_float * 32)()
+        n = C.c_int(0)
+        self._check(self.lib.ppg_selftest_conv(self.h, 32, names, d, r, C.byref(n)))
+        return [(names[i].decode(), float(d[i]), float(r[i])) for i in range(n.value)]
+
+    def set_profiling(self, on=True):
+        self._check(self.lib.ppg_set_profiling(self.h, int(on)))
+
+    def stage_times(self):
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        n = C.c_int(0)
+        self._check(self.lib.ppg_get_stage_times(self.h, 64, names, ms, C.byref(n)))
+        return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
+    def launch_count(self):
+        return int(self.lib.ppg_launch_count(self.h))
+
+    def timer_start(self):
+        self._check(self.lib.ppg_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._check(self.lib.ppg_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    # ---- association (search core of Matcher::ExtendMapMatches, matching/src/Matcher.cpp:224-281)
+    def upload_map(self, map_desc):
+        m = np.ascontiguousarray(map_desc, np.float32)
+        self._check(self.lib.ppg_upload_map(self.h, _fp(m), m.shape[0]))
+        self._n_rows = m.shape[0]
+
+    def _assoc_in(self, kp_x, kp_y, frame_desc, free_mask, proj_uv, view_cos, th, ratio):
+        a = AssocIn()
+        keep = [np.ascontiguousarray(kp_x, np.float32), np.ascontiguousarray(kp_y, np.float32),
+                np.ascontiguousarray(frame_desc, np.float32), np.ascontiguousarray(free_mask, np.uint8),
+                np.ascontiguousarray(proj_uv, np.float32), np.ascontiguousarray(view_cos, np.float32)]
+        a.n_kp = len(keep[0])
+        a.kp_x, a.kp_y, a.frame_desc = _fp(keep[0]), _fp(keep[1]), _fp(keep[2])
+        a.free_mask = keep[3].ctypes.data_as(C.POINTER(C.c_uint8))
+        a.n_rows = len(keep[5])
+        a.proj_uv, a.view_cos = _fp(keep[4]), _fp(keep[5])
+        a.th, a.ratio = th, ratio
+        return a, keep
+
+    @staticmethod
+    def _assoc_out(m):
+        r = dict(best_idx=np.zeros(m, np.int32), second_idx=np.zeros(m, np.int32),
+                 best_d=np.zeros(m, np.float32), second_d=np.zeros(m, np.float32), accept=np.zeros(m, np.uint8))
+        o = AssocOut()
+        o.best_idx = r["best_idx"].ctypes.data_as(C.POINTER(C.c_int32))
+        o.second_idx = r["second_idx"].ctypes.data_as(C.POINTER(C.c_int32))
+        o.best_dist, o.second_dist = _fp(r["best_d"]), _fp(r["second_d"])
+        o.accept = r["accept"].ctypes.data_as(C.POINTER(C.c_uint8))
+        return o, r
+
+    def associate(self, kp_x, kp_y, frame_desc, free_mask, proj_uv, view_cos, th, ratio):
+        a, keep = self._assoc_in(kp_x, kp_y, frame_desc, free_mask, proj_uv, view_cos, th, ratio)
+        o, r = self._assoc_out(a.n_rows)
+        self._check(self.lib.ppg_associate(self.h, C.byref(a), C.byref(o)))
+        return r
+
+    def assoc_stage(self, kp_x, kp_y, frame_desc, free_mask, proj_uv, view_cos, th, ratio):
+        a, keep = self._assoc_in(kp_x, kp_y, frame_desc, free_mask, proj_uv, view_cos, th, ratio)
+        self._check(self.lib.ppg_assoc_stage(self.h, C.byref(a)))
+        self._assoc_rows = a.n_rows
+
+    def assoc_run(self):
+        self._check(self.lib.ppg_assoc_run(self.h))
+
+    def assoc_run_frame(self, frame):
+        self._check(self.lib.ppg_assoc_run_frame(self.h, frame))
+
+    def assoc_fetch(self):
+        o, r = self._assoc_out(self._assoc_rows)
+        self._check(self.lib.ppg_assoc_fetch(self.h, C.byref(o)))
+        return r
+
+    def assoc_fallback_rows(self):
+        n = C.c_int(0)
+        self._check(self.lib.ppg_assoc_fallback_rows(self.h, C.byref(n)))
+        return n.value
+
+    def assoc_device_results(self):
+        p = [C.c_void_p() for _ in range(5)]
+        self._check(self.lib.ppg_assoc_device_results(self.h, *[C.byref(x) for x in p]))
+        return [x.value for x in p]

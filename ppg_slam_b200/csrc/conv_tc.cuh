@@ -1,0 +1,56 @@
+// Implicit-GEMM 3x3 / 1x1 convolution on tcgen05 tensor cores (sm_100a), NHWC fp16 activations.
+//
+// Replaces the cuDNN convolutions LibTorch runs for net/Backbone.pt, PointHeatmap.pt, EdgeHeatmap.pt
+// and Descriptor.pt (reference call sites feature/src/PPGExtractor.cpp:152-155).
+//
+// GEMM view:  D[pixel, cout] = sum_{tap, cin} A[pixel shifted by tap, cin] * Wt[tap][cout][cin]
+//   M tile  = 128 output pixels = an 8-row x 16-column image patch (TMEM lane = 16*row + col)
+//   N       = Cout (padded to a multiple of 16, <= 256), one UMMA N
+//   K step  = 64 input channels of one tap = one 128-byte swizzled smem row per pixel
+// A tiles come straight from the NHWC activation tensor with one 4-D TMA box per (tap, 64-channel
+// chunk); out-of-image coordinates are zero-filled by TMA, which is exactly the conv's zero padding.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-5 = epilogue.
+// Two TMEM accumulators (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ppg {
+
+enum ConvEpilogue {
+    EPI_F16 = 0,       // bias (+ReLU) -> NHWC fp16
+    EPI_F16_POOL = 1,  // bias + ReLU + 2x2 max-pool -> NHWC fp16 at half resolution
+    EPI_F16_PS2 = 2,   // bias + ReLU + pixel_shuffle(2) -> NHWC fp16, Cout/4 channels at double resolution
+    EPI_F32 = 3,       // bias (+ReLU) -> NHWC fp32 (all N padded channels stored)
+};
+
+struct ConvTcParams {
+    int B, H, W;       // batch actually processed, conv (input == output) resolution
+    int cin_chunks;    // Cin / 64
+    int taps;          // 9 (3x3, pad 1) or 1 (1x1)
+    int N;             // UMMA N (padded Cout)
+    int mode, relu;
+    int stages;
+    int tiles_x, tiles_y, total_tiles;
+    const float* bias; // [N]
+    void* out;
+    int out_ld;        // channels per output pixel in the destination tensor
+};
+
+struct ConvLayer {
+    CUtensorMap mapA, mapB;
+    ConvTcParams p;
+    int smem_bytes;
+    int cin, cout;
+};
+
+constexpr int CONV_TILE_W = 16, CONV_TILE_H = 8, CONV_A_BYTES = 16384, CONV_THREADS = 192;
+
+// Fills stages / tiles / smem size for the given shape. Tensor maps are encoded by the caller (api).
+void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded, int taps, int mode, int relu,
+                  const float* bias, void* out, int out_ld);
+cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStream_t st);
+
+}  // namespace ppg

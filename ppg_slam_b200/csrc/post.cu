@@ -1,0 +1,906 @@
+// Post-processing kernels: the CPU stages of PPGExtractor (feature/src/PPGExtractor.cpp:158-589) on the GPU.
+//
+// Compiled with -fmad=false: the reference is built for baseline x86-64 (no FMA contraction,
+// CMakeLists.txt:8-9), and keypoints / graph must come out bit-identical given the same dense maps.
+// Everything order- or rounding-dependent in the reference is kept:
+//   detectKeyPoint :158-234  threshold scan, (score desc, raster asc) order, greedy 9x9 NMS, top-500, undistort
+//   refineHeatMap  :540-578  per 16x16 tile top-30% mean rescale
+//   remap          :259-263  cv::remap INTER_LINEAR in 1/32 fixed point (pinhole only)
+//   detectLines    :265-441  3-point heat test, greedy (i,j)-ordered overlap filter, line scoring, colinearity
+//   genPointDescriptor :515-538  bilinear sampling + L2 normalisation
+#include "post.cuh"
+
+#include <math.h>
+
+namespace ppg {
+
+namespace {
+
+#define PPG_PI 3.1415926535897932384626433832795
+#define PPG_2PI 6.283185307179586476925286766559
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ int* hdr_of(const PostParams& p, int b) {
+    return reinterpret_cast<int*>(p.out + (size_t)b * p.lay.total + p.lay.hdr);
+}
+template <typename T>
+__device__ __forceinline__ T* out_of(const PostParams& p, int b, size_t off) {
+    return reinterpret_cast<T*>(p.out + (size_t)b * p.lay.total + off);
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        int t = __shfl_up_sync(FULL, v, s);
+        if (lane >= s) v += t;
+    }
+    return v;
+}
+
+// Exclusive prefix of one value per thread over the whole block; *total = block sum.  `ws` = 33 ints.
+__device__ int block_excl_scan(int v, int* ws, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    int inc = warp_incl_scan(v, lane);
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < nw ? ws[lane] : 0;
+        int wi = warp_incl_scan(w, lane);
+        ws[lane] = wi - w;
+        if (lane == 31) ws[32] = wi;
+    }
+    __syncthreads();
+    int r = ws[warp] + inc - v;
+    *total = ws[32];
+    __syncthreads();
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: threshold scan.  state[pix] = 1 for in-border pixels with score >= thresh (:173 skips "<", so a
+// NaN would pass); their indices are appended (unordered) to cand[].  Pixels closer than R to the border
+// can never be accepted and never suppress (:190-193), so they are dropped here.
+__global__ void __launch_bounds__(256) scan_kernel(const PostParams p) {
+    const int b = blockIdx.y;
+    const int HW = p.H * p.W;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;  // quad index
+    const int lane = threadIdx.x & 31;
+    const int R = p.nms_radius;
+    int c = 0, call = 0;
+    uint32_t idxs[4];
+    if (q * 4 < HW) {
+        const float4 v = *reinterpret_cast<const float4*>(p.prob + (size_t)b * HW + q * 4);
+        const float s[4] = {v.x, v.y, v.z, v.w};
+        const int pix = q * 4, y = pix / p.W, x0 = pix - y * p.W;
+        const bool yin = (y >= R) && (y <= p.H - R - 1);
+        uint32_t st = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool pass = !(s[k] < p.junction_thresh);
+            const int x = x0 + k;
+            const bool inb = yin && (x >= R) && (x <= p.W - R - 1);
+            call += pass;
+            if (pass && inb) {
+                st |= 1u << (8 * k);
+                idxs[c++] = pix + k;
+            }
+        }
+        *reinterpret_cast<uint32_t*>(p.state + (size_t)b * HW + pix) = st;
+    }
+    // warp-aggregated append
+    const int inc = warp_incl_scan(c, lane);
+    const int tot = __shfl_sync(FULL, inc, 31);
+    int call_w = call;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) call_w += __shfl_xor_sync(FULL, call_w, s);
+    int base = 0;
+    if (lane == 0) {
+        if (tot) base = atomicAdd(&p.counters[b * 8 + 0], tot);
+        if (call_w) atomicAdd(&p.counters[b * 8 + 1], call_w);
+    }
+    base = __shfl_sync(FULL, base, 0);
+    uint32_t* cl = p.cand + (size_t)b * HW;
+    for (int k = 0; k < c; k++) cl[base + inc - c + k] = idxs[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6+K7: exact greedy NMS without the sequential walk, then rank + top-k + undistort.
+//
+// The reference walks candidates in (score desc) order and accepts one iff no previously ACCEPTED
+// candidate lies within Chebyshev distance R (:185-206).  Equivalent fixed point: a candidate is
+//   suppressed  if some higher-priority candidate within R is accepted,
+//   accepted    if every higher-priority candidate within R is suppressed.
+// Rounds of that rule converge to the unique greedy result in any evaluation order (decisions are
+// final and only read other final decisions), so stale reads are benign.  Priority = (score desc,
+// raster index asc) -- the stable order the oracle uses for std::sort ties.  The 500 cap (:196-197) only
+// truncates the walk, so it is applied afterwards on the ranked survivors.
+__global__ void __launch_bounds__(1024) nms_kernel(const PostParams p) {
+    extern __shared__ unsigned long long keys[];  // [acc_cap]
+    __shared__ int s_remaining, s_nacc, s_ovf;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int HW = p.H * p.W, W = p.W, R = p.nms_radius;
+    const float* prob = p.prob + (size_t)b * HW;
+    volatile uint8_t* state = p.state + (size_t)b * HW;
+    const uint32_t* cl = p.cand + (size_t)b * HW;
+    int n = p.counters[b * 8 + 0];
+    if (n > HW) n = HW;
+    if (tid == 0) {
+        s_nacc = 0;
+        s_ovf = 0;
+    }
+    int rounds = 0;
+    for (;;) {
+        if (tid == 0) s_remaining = 0;
+        __syncthreads();
+        for (int c = tid; c < n; c += blockDim.x) {
+            const int idx = cl[c];
+            if (state[idx] != 1) continue;
+            const float s = prob[idx];
+            const int y = idx / W, x = idx - y * W;
+            bool sup = false, wait = false;
+            for (int dy = -R; dy <= R && !sup; dy++) {
+                const int rowi = (y + dy) * W + x;
+                for (int dx = -R; dx <= R; dx++) {
+                    const int ni = rowi + dx;
+                    const uint8_t st = state[ni];
+                    if (st == 0 || st == 3 || ni == idx) continue;
+                    const float sn = prob[ni];
+                    const bool higher = (sn > s) || (sn == s && ni < idx);
+                    if (!higher) continue;
+                    if (st == 2) {
+                        sup = true;
+                        break;
+                    }
+                    wait = true;
+                }
+            }
+            if (sup) {
+                state[idx] = 3;
+            } else if (!wait) {
+                state[idx] = 2;
+                const int k = atomicAdd(&s_nacc, 1);
+                if (k < p.acc_cap)
+                    keys[k] = ((unsigned long long)(~__float_as_uint(s)) << 32) | (unsigned)idx;
+                else
+                    s_ovf = 1;
+            } else {
+                atomicAdd(&s_remaining, 1);
+            }
+        }
+        __syncthreads();
+        rounds++;
+        const int rem = s_remaining;
+        __syncthreads();
+        if (rem == 0 || rounds > n + 1) break;
+    }
+    int nacc = s_nacc;
+    int* hdr = hdr_of(p, b);
+    if (nacc > p.acc_cap) nacc = p.acc_cap;
+    // bitonic sort of the survivors' keys (ascending = score desc, index asc)
+    int P = 1;
+    while (P < nacc) P <<= 1;
+    for (int t = nacc + tid; t < P; t += blockDim.x) keys[t] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < P; t += blockDim.x) {
+                const int u = t ^ j;
+                if (u > t) {
+                    const bool asc = (t & k) == 0;
+                    const unsigned long long a = keys[t], c = keys[u];
+                    if ((a > c) == asc) {
+                        keys[t] = c;
+                        keys[u] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    const int nkp = nacc < p.max_kp ? nacc : p.max_kp;
+    float* kp_x = out_of<float>(p, b, p.lay.kp_x);
+    float* kp_y = out_of<float>(p, b, p.lay.kp_y);
+    int* opx = out_of<int>(p, b, p.lay.px);
+    int* opy = out_of<int>(p, b, p.lay.py);
+    float* osc = out_of<float>(p, b, p.lay.score);
+    float* oxu = out_of<float>(p, b, p.lay.xun);
+    float* oyu = out_of<float>(p, b, p.lay.yun);
+    uint8_t* oout = out_of<uint8_t>(p, b, p.lay.kout);
+    for (int t = tid; t < nkp; t += blockDim.x) {
+        const unsigned long long key = keys[t];
+        const int idx = (int)(unsigned)(key & 0xffffffffull);
+        const float s = __uint_as_float(~(unsigned)(key >> 32));
+        const int y = idx / W, x = idx - y * W;
+        const float2 un = p.undist_lut[idx];  // cv::[fisheye::]undistortPoints of the integer pixel, :220-223
+        uint8_t o = 1;                        // KeyPointEx ctor: mbOut(true)
+        if (un.x >= 1.f && un.x < (float)(p.W - 1) && un.y >= 1.f && un.y < (float)(p.H - 1)) o = 0;  // :230
+        opx[t] = x;
+        opy[t] = y;
+        osc[t] = s;
+        oxu[t] = un.x;
+        oyu[t] = un.y;
+        oout[t] = o;
+        if (p.fisheye) {  // run(): pinhole only mPos <- mPosUn (:141-145)
+            kp_x[t] = (float)x;
+            kp_y[t] = (float)y;
+        } else {
+            kp_x[t] = un.x;
+            kp_y[t] = un.y;
+        }
+    }
+    if (tid == 0) {
+        hdr[HDR_NKP] = nkp;
+        hdr[HDR_NEDGES] = 0;
+        hdr[HDR_NCOL] = 0;
+        hdr[HDR_STATUS] = s_ovf ? ST_OVF_ACCEPT : 0;
+        hdr[HDR_NCAND] = p.counters[b * 8 + 1];
+        hdr[HDR_NACC] = s_nacc;
+        hdr[HDR_NPASS] = 0;
+        hdr[HDR_NLINES] = 0;
+        hdr[HDR_NMS_ROUNDS] = rounds;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: refineHeatMap (:540-578) -- one warp per 16x16 tile, 8 raster-consecutive values per lane.
+__global__ void __launch_bounds__(256) refine_kernel(const PostParams p, float* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int tiles_x = p.W >> 4, tiles_y = p.H >> 4;
+    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int per = tiles_x * tiles_y;
+    if (tile >= per * p.B) return;
+    const int b = tile / per, r = tile - b * per, ty = r / tiles_x, tx = r - ty * tiles_x;
+    const size_t base = (size_t)b * p.H * p.W + (size_t)(ty * 16 + (lane >> 1)) * p.W + tx * 16 + (lane & 1) * 8;
+    const float4 a0 = *reinterpret_cast<const float4*>(p.heat_raw + base);
+    const float4 a1 = *reinterpret_cast<const float4*>(p.heat_raw + base + 4);
+    float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    uint32_t u[8];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const bool valid = v[k] > p.line_valid_thresh;  // :549
+        u[k] = valid ? __float_as_uint(v[k]) : 0u;
+        cnt += valid;
+    }
+    const int inc = warp_incl_scan(cnt, lane);
+    const int n = __shfl_sync(FULL, inc, 31);
+    const int valCount = (int)(p.line_valid_ratio * (float)n);  // :554
+    bool unchanged = valCount < 1, zero = false;                // :555 leaves the tile as it is
+    if (!unchanged && (double)n >= 256.0 * 0.9) {               // :557
+        const int k = (int)((double)n * 0.9);                   // index into the raster-ordered valid list
+        const int excl = inc - cnt;
+        float cand = 0.f;
+        const bool mine = (k >= excl) && (k < inc);
+        if (mine) {
+            int want = k - excl, seen = 0;
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+                if (u[e]) {
+                    if (seen == want) cand = v[e];
+                    seen++;
+                }
+        }
+        const unsigned who = __ballot_sync(FULL, mine);
+        const float vk = who ? __shfl_sync(FULL, cand, __ffs(who) - 1) : 0.f;
+        zero = who && ((double)vk > 0.1);
+    }
+    float o[8];
+    if (unchanged) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = v[k];
+    } else if (zero) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = 0.f;
+    } else {
+        // valCount-th largest valid value by bitwise binary search (positive floats order as uints)
+        uint32_t t = 0;
+        for (int bit = 30; bit >= 0; bit--) {
+            const uint32_t c = t | (1u << bit);
+            int ge = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) ge += (u[k] >= c);
+            ge = __reduce_add_sync(FULL, ge);
+            if (ge >= valCount) t = c;
+        }
+        // sum of the top valCount values; double accumulation of <= 76 floats in (0.01, 1] is exact, so
+        // the order is irrelevant (:563 std::accumulate(..., 0.0) over the sorted prefix)
+        double sum = 0.0;
+        int gt = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (u[k] > t) {
+                sum += (double)v[k];
+                gt++;
+            }
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            sum += __shfl_xor_sync(FULL, sum, s);
+            gt += __shfl_xor_sync(FULL, gt, s);
+        }
+        sum += (double)(valCount - gt) * (double)__uint_as_float(t);
+        const float ave = (float)(sum / (double)(float)valCount);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (u[k]) {
+                const float ns = __fdiv_rn(v[k], ave);
+                o[k] = ((double)ns > 1.0) ? 1.0f : ns;  // :570
+            } else {
+                o[k] = 0.f;  // :573
+            }
+        }
+    }
+    *reinterpret_cast<float4*>(dst + base) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(dst + base + 4) = make_float4(o[4], o[5], o[6], o[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9: cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) as OpenCV evaluates it for CV_32F: coordinates in
+// 1/32 fixed point (remap_lut holds rint(map*32), built once at ppg_create), four f32 weights, sequential
+// f32 sum.  4 pixels per thread.
+__global__ void __launch_bounds__(256) remap_kernel(const PostParams p) {
+    const int b = blockIdx.y, HW = p.H * p.W, W = p.W, H = p.H;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q * 4 >= HW) return;
+    const float* src = p.heat_ref + (size_t)b * HW;
+    const int4 l0 = *reinterpret_cast<const int4*>(p.remap_lut + q * 4);
+    const int4 l1 = *reinterpret_cast<const int4*>(p.remap_lut + q * 4 + 2);
+    const int sxs[4] = {l0.x, l0.z, l1.x, l1.z}, sys[4] = {l0.y, l0.w, l1.y, l1.w};
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int sx = sxs[k], sy = sys[k];
+        const int ix = sx >> 5, iy = sy >> 5;
+        const float fx = (float)(sx & 31) * (1.0f / 32.0f), fy = (float)(sy & 31) * (1.0f / 32.0f);
+        const float w00 = (1.0f - fy) * (1.0f - fx), w01 = (1.0f - fy) * fx, w10 = fy * (1.0f - fx), w11 = fy * fx;
+        float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+        const bool x0 = ix >= 0 && ix < W, x1 = ix + 1 >= 0 && ix + 1 < W;
+        if (iy >= 0 && iy < H) {
+            if (x0) s00 = src[iy * W + ix];
+            if (x1) s01 = src[iy * W + ix + 1];
+        }
+        if (iy + 1 >= 0 && iy + 1 < H) {
+            if (x0) s10 = src[(iy + 1) * W + ix];
+            if (x1) s11 = src[(iy + 1) * W + ix + 1];
+        }
+        o[k] = ((s00 * w00 + s01 * w01) + s10 * w10) + s11 * w11;
+    }
+    *reinterpret_cast<float4*>(p.heat_final + (size_t)b * HW + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10: 3-point heat test for every pair i<j of in-bounds keypoints (:293-313).  One warp per row i;
+// the result is a bit matrix so that the (i asc, j asc) order the greedy filter needs is implicit.
+__global__ void __launch_bounds__(256) pair_test_kernel(const PostParams p) {
+    __shared__ float sx[POST_MAX_KP], sy[POST_MAX_KP];
+    __shared__ uint8_t so[POST_MAX_KP];
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int n = hdr_of(p, b)[HDR_NKP];
+    const float* xun = out_of<float>(p, b, p.lay.xun);
+    const float* yun = out_of<float>(p, b, p.lay.yun);
+    const uint8_t* ko = out_of<uint8_t>(p, b, p.lay.kout);
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        sx[t] = xun[t];
+        sy[t] = yun[t];
+        so[t] = ko[t];
+    }
+    __syncthreads();
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const float* heat = p.heat_final + (size_t)b * p.H * p.W;
+    uint32_t* bits = p.pair_bits + ((size_t)b * p.max_kp + i) * p.pair_words;
+    const float xi = sx[i], yi = sy[i];
+    const bool iout = so[i] != 0;
+    const float th = p.line_heatmap_thresh;
+    int total = 0;
+    const int words = (n + 31) >> 5;
+    for (int w = 0; w < words; w++) {
+        const int j = w * 32 + lane;
+        bool pass = false;
+        if (!iout && j > i && j < n && !so[j]) {
+            const float xj = sx[j], yj = sy[j];
+            const float c1x = xj * 0.2f + xi * 0.8f, c1y = yj * 0.2f + yi * 0.8f;  // :304
+            const float c2x = xj * 0.8f + xi * 0.2f, c2y = yj * 0.8f + yi * 0.2f;  // :305
+            const float c3x = xj * 0.5f + xi * 0.5f, c3y = yj * 0.5f + yi * 0.5f;  // :306
+            pass = !(heat[(int)((double)c1y + 0.5) * p.W + (int)((double)c1x + 0.5)] < th) &&
+                   !(heat[(int)((double)c2y + 0.5) * p.W + (int)((double)c2x + 0.5)] < th) &&
+                   !(heat[(int)((double)c3y + 0.5) * p.W + (int)((double)c3x + 0.5)] < th);
+        }
+        const unsigned m = __ballot_sync(FULL, pass);
+        if (lane == 0) bits[w] = m;
+        total += __popc(m);
+    }
+    if (lane == 0) p.row_cnt[b * p.max_kp + i] = total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K11+K12: one CTA per frame.  Shared-memory resident candidate-line table and adjacency lists.
+//   A  row offsets of the bit matrix -> candidate ids in (i,j) order; dist / dir per candidate (:265-288)
+//   B  greedy overlap filter, sequential over candidates, one warp, lanes scan the adjacency list (:314-365)
+//   C  line scoring, one thread per surviving candidate (:366-389, :461-513)
+//   D  final edges, mvConnected CSR (:433-441)
+//   E  colinearity per keypoint, one thread per keypoint (:391-432), mvColine CSR
+struct LineSmem {
+    float* dist;
+    float* dirf;   // dir(s,e)
+    float* dirb;   // dir(e,s)
+    uint32_t* se;  // s | e << 16
+    uint8_t* flag; // 1 created, 2 bad
+    uint16_t* adj; // [max_kp][deg_cap]
+    int* adj_cnt;  // [max_kp]
+    int* row_off;  // [max_kp + 1]
+    float* kx;
+    float* ky;
+    int* ws;       // 40 ints scan scratch / flags
+};
+
+__device__ __forceinline__ LineSmem carve_lines(const PostParams& p, uint8_t* s) {
+    LineSmem m;
+    m.dist = reinterpret_cast<float*>(s);
+    m.dirf = m.dist + p.pair_cap;
+    m.dirb = m.dirf + p.pair_cap;
+    m.se = reinterpret_cast<uint32_t*>(m.dirb + p.pair_cap);
+    m.adj_cnt = reinterpret_cast<int*>(m.se + p.pair_cap);
+    m.row_off = m.adj_cnt + p.max_kp;
+    m.kx = reinterpret_cast<float*>(m.row_off + p.max_kp + 1);
+    m.ky = m.kx + p.max_kp;
+    m.ws = reinterpret_cast<int*>(m.ky + p.max_kp);
+    m.adj = reinterpret_cast<uint16_t*>(m.ws + 40);
+    m.flag = reinterpret_cast<uint8_t*>(m.adj + (size_t)p.max_kp * p.deg_cap);
+    return m;
+}
+
+__constant__ float c_inv_gap[4] = {0.3333, 0.200, 0.1427, 0.1111};  // invSampleGapTable, PPGExtractor.cpp:19
+
+__device__ __forceinline__ float bilinear_heat(const float* M, int W, float ptX, float ptY) {  // :580-589
+    const int x1 = (int)ptX, x2 = x1 + 1, y1 = (int)ptY, y2 = y1 + 1;
+    const float d1 = ((float)x2 - ptX) * M[y1 * W + x1] + (ptX - (float)x1) * M[y1 * W + x2];
+    const float d2 = ((float)x2 - ptX) * M[y2 * W + x1] + (ptX - (float)x1) * M[y2 * W + x2];
+    return ((float)y2 - ptY) * d1 + (ptY - (float)y1) * d2;
+}
+
+// One adjacency scan of the overlap filter (:316-335 / :338-357), executed by a full warp.
+__device__ __forceinline__ bool overlap_scan(const PostParams& p, const LineSmem& m, int pt, float dir_new,
+                                             float dist_new, int lane) {
+    const int cnt = m.adj_cnt[pt];
+    bool ov = false;
+    for (int t0 = 0; t0 < cnt; t0 += 32) {
+        const int t = t0 + lane;
+        if (t < cnt) {
+            const int lo = m.adj[pt * p.deg_cap + t];
+            if (!(m.flag[lo] & 2)) {
+                const int s_old = m.se[lo] & 0xffff;
+                const float dir_old = (pt == s_old) ? m.dirf[lo] : m.dirb[lo];
+                float a = dir_new - dir_old;
+                if ((double)a < -PPG_PI) a = (float)((double)a + PPG_2PI);
+                if ((double)a > PPG_PI) a = (float)((double)a - PPG_2PI);
+                a = fabsf(a);
+                if (!((double)a > 0.2 * PPG_PI)) {
+                    const float dist_old = m.dist[lo];
+                    const float sn = (float)sin((double)a);  // :330 unqualified sin -> double overload
+                    if (dist_new <= dist_old && dist_new * sn < p.line_dist_thresh) m.flag[lo] |= 2;
+                    if (dist_old < dist_new && dist_old * sn < p.line_dist_thresh) ov = true;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    return __any_sync(FULL, ov);
+}
+
+__global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
+    extern __shared__ __align__(16) uint8_t smem_lines[];
+    const LineSmem m = carve_lines(p, smem_lines);
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    int* hdr = hdr_of(p, b);
+    const int n = hdr[HDR_NKP];
+    int* conn_off = out_of<int>(p, b, p.lay.conn_off);
+    int* col_off = out_of<int>(p, b, p.lay.col_off);
+    if (n == 0) {  // detectLines returns at :239-240; the record carries no edges
+        if (tid == 0) {
+            conn_off[0] = 0;
+            col_off[0] = 0;
+        }
+        return;
+    }
+    const float* heat = p.heat_final + (size_t)b * p.H * p.W;
+    const uint8_t* ko = out_of<uint8_t>(p, b, p.lay.kout);
+    unsigned status = 0;
+
+    // ---- A: row offsets + candidate table
+    for (int t = tid; t < n; t += blockDim.x) {
+        m.kx[t] = out_of<float>(p, b, p.lay.xun)[t];
+        m.ky[t] = out_of<float>(p, b, p.lay.yun)[t];
+        m.adj_cnt[t] = 0;
+    }
+    int carry = 0;
+    for (int t0 = 0; t0 < n; t0 += blockDim.x) {
+        const int t = t0 + tid;
+        const int v = t < n ? p.row_cnt[b * p.max_kp + t] : 0;
+        int tot;
+        const int ex = block_excl_scan(v, m.ws, &tot);
+        if (t < n) m.row_off[t] = carry + ex;
+        carry += tot;
+    }
+    const int npass_all = carry;
+    int npass = npass_all;
+    if (npass > p.pair_cap) {
+        npass = p.pair_cap;
+        status |= ST_OVF_PAIRS;
+    }
+    __syncthreads();
+    const int words = (n + 31) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        const uint32_t* bits = p.pair_bits + ((size_t)b * p.max_kp + i) * p.pair_words;
+        int pos = m.row_off[i];
+        const float xi = m.kx[i], yi = m.ky[i];
+        for (int w = 0; w < words; w++) {
+            const uint32_t mw = bits[w];
+            if (mw & (1u << lane)) {
+                const int id = pos + __popc(mw & ((1u << lane) - 1u));
+                if (id < npass) {
+                    const int j = w * 32 + lane;
+                    const float dx = m.kx[j] - xi, dy = m.ky[j] - yi;  // :278
+                    const float dist = sqrtf(dx * dx + dy * dy);       // :279
+                    const float ux = __fdiv_rn(dx, dist), uy = __fdiv_rn(dy, dist);
+                    const float d = (float)atan2((double)uy, (double)ux);  // :283 (see oracle divergence 2)
+                    float r = (float)((double)d - PPG_PI);                 // :284
+                    if ((double)r < -PPG_PI) r = (float)((double)r + PPG_2PI);
+                    m.dist[id] = dist;
+                    m.dirf[id] = d;
+                    m.dirb[id] = r;
+                    m.se[id] = (uint32_t)i | ((uint32_t)j << 16);
+                    m.flag[id] = 0;
+                }
+            }
+            pos += __popc(mw);
+        }
+    }
+    __syncthreads();
+
+    // ---- B: greedy overlap filter, candidates in (i asc, j asc) order
+    if (warp == 0) {
+        int created = 0;
+        bool deg_ovf = false;
+        for (int c = 0; c < npass; c++) {
+            const uint32_t se = m.se[c];
+            const int i = se & 0xffff, j = se >> 16;
+            const float dist_new = m.dist[c];
+            if (overlap_scan(p, m, i, m.dirf[c], dist_new, lane)) continue;  // :336-337
+            if (overlap_scan(p, m, j, m.dirb[c], dist_new, lane)) continue;  // :358-359
+            if (lane == 0) {
+                const int ci = m.adj_cnt[i], cj = m.adj_cnt[j];
+                if (ci < p.deg_cap && cj < p.deg_cap) {
+                    m.flag[c] = 1;
+                    m.adj[i * p.deg_cap + ci] = (uint16_t)c;
+                    m.adj[j * p.deg_cap + cj] = (uint16_t)c;
+                    m.adj_cnt[i] = ci + 1;
+                    m.adj_cnt[j] = cj + 1;
+                } else {
+                    deg_ovf = true;
+                }
+            }
+            created++;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            m.ws[34] = created;
+            m.ws[35] = deg_ovf ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    if (m.ws[35]) status |= ST_OVF_DEGREE;
+    const int ncreated = m.ws[34];
+
+    // ---- C: line scoring (:367-389)
+    float* lscore = p.l_score + (size_t)b * p.pair_cap;
+    int* ledge = p.l_edge + (size_t)b * p.pair_cap;
+    for (int c = tid; c < npass; c += blockDim.x) {
+        if (m.flag[c] != 1) continue;
+        const uint32_t se = m.se[c];
+        const int s = se & 0xffff, e = se >> 16;
+        const float psx = m.kx[s], psy = m.ky[s], pex = m.kx[e], pey = m.ky[e];
+        const float dist = m.dist[c];
+        int lenLevel = (int)((double)(dist * p.inv_scale) * 4.0);  // :485
+        if (lenLevel > 3) lenLevel = 3;                            // dist == diagonal cannot happen (points >= 1 px inside)
+        if (lenLevel < 0) lenLevel = 0;
+        const int segNum = (int)(dist * c_inv_gap[lenLevel]);      // :486
+        const float step = (float)(1.0 / (double)(float)segNum);   // :487
+        int cnt = 0;
+        float sum = 0.f;
+        for (int i = 1; i < segNum; i++) {
+            const float qx = (psx * step) * (float)i + (pex * step) * (float)(segNum - i);
+            const float qy = (psy * step) * (float)i + (pey * step) * (float)(segNum - i);
+            const int posx = (int)((double)qx + 0.5), posy = (int)((double)qy + 0.5);
+            if (heat[posy * p.W + posx] > p.line_heatmap_thresh) cnt++;
+            sum += bilinear_heat(heat, p.W, qx, qy);
+        }
+        const float rate = __fdiv_rn((float)cnt, (float)(segNum - 1));  // segNum == 1 -> 0/0 = NaN, accepted (:376)
+        bool bad = false;
+        float sh = 0.f;
+        if (rate < p.line_inlier_rate) {
+            bad = true;
+        } else {
+            sh = __fdiv_rn(sum, (float)(segNum - 1));
+            if (sh < p.line_heatmap_thresh) bad = true;
+        }
+        if (bad)
+            m.flag[c] = 3;
+        else
+            lscore[c] = rate * sh;
+    }
+    __syncthreads();
+
+    // ---- D: final edge list = surviving candidates in candidate order (:433-441)
+    int ecarry = 0;
+    int* es = out_of<int>(p, b, p.lay.edge_s);
+    int* ee = out_of<int>(p, b, p.lay.edge_e);
+    float* esc = out_of<float>(p, b, p.lay.edge_score);
+    for (int c0 = 0; c0 < npass; c0 += blockDim.x) {
+        const int c = c0 + tid;
+        const int v = (c < npass && m.flag[c] == 1) ? 1 : 0;
+        int tot;
+        const int ex = block_excl_scan(v, m.ws, &tot);
+        if (v) {
+            const int E = ecarry + ex;
+            ledge[c] = E;
+            if (E < p.lay.max_edges) {
+                es[E] = m.se[c] & 0xffff;
+                ee[E] = m.se[c] >> 16;
+                esc[E] = lscore[c];
+            }
+        }
+        ecarry += tot;
+    }
+    const int nedges = ecarry;
+    if (nedges > p.lay.max_edges) status |= ST_OVF_EDGES;
+    __syncthreads();
+
+    // adjacency rows: drop bad lines in place (order kept = ascending candidate id, as :366-388 rebuilds it)
+    for (int t = tid; t < n; t += blockDim.x) {
+        uint16_t* row = m.adj + t * p.deg_cap;
+        const int cnt = m.adj_cnt[t];
+        int k = 0;
+        for (int q = 0; q < cnt; q++) {
+            const uint16_t l = row[q];
+            if (m.flag[l] == 1) row[k++] = l;
+        }
+        m.adj_cnt[t] = k;
+    }
+    __syncthreads();
+    // mvConnected CSR
+    int* conn_idx = out_of<int>(p, b, p.lay.conn_idx);
+    int ccarry = 0;
+    for (int t0 = 0; t0 < n; t0 += blockDim.x) {
+        const int t = t0 + tid;
+        const int v = t < n ? m.adj_cnt[t] : 0;
+        int tot;
+        const int ex = block_excl_scan(v, m.ws, &tot);
+        if (t < n) {
+            const int off = ccarry + ex;
+            conn_off[t] = off;
+            if (nedges <= p.lay.max_edges)
+                for (int q = 0; q < v; q++) conn_idx[off + q] = ledge[m.adj[t * p.deg_cap + q]];
+        }
+        ccarry += tot;
+    }
+    if (tid == 0) conn_off[n] = ccarry;
+
+    // ---- E: colinearity (:392-432), in place on the adjacency row; pair k is parked at row[D-2(k+1)..]
+    int ncol_mine = 0;
+    int colcarry = 0;
+    int* col_pairs = out_of<int>(p, b, p.lay.col_pairs);
+    for (int t0 = 0; t0 < n; t0 += blockDim.x) {
+        const int pt = t0 + tid;
+        int D = 0;
+        ncol_mine = 0;
+        if (pt < n) {
+            uint16_t* row = m.adj + pt * p.deg_cap;
+            D = m.adj_cnt[pt];
+            int mm = D;
+            while (mm > 1) {
+                const int l1 = row[mm - 1];
+                const int s1 = m.se[l1] & 0xffff, e1 = m.se[l1] >> 16;
+                const int p1 = (pt == s1) ? e1 : s1;
+                const float dir1 = (pt == s1) ? m.dirf[l1] : m.dirb[l1];
+                const float dist1 = m.dist[l1];
+                double minPD = 1e9;
+                int best = -1, bp2 = -1;
+                for (int i = 0; i < mm - 1; i++) {
+                    const int l2 = row[i];
+                    const int s2 = m.se[l2] & 0xffff, e2 = m.se[l2] >> 16;
+                    const int p2 = (pt == s2) ? e2 : s2;
+                    const float dir2 = (pt == s2) ? m.dirf[l2] : m.dirb[l2];
+                    const float ad = dir1 - dir2;
+                    const double pd = 0.5 * (double)(dist1 + m.dist[l2]) * (double)fabsf((float)sin((double)ad));  // :413
+                    if (minPD > pd) {
+                        minPD = pd;
+                        best = i;
+                        bp2 = p2;
+                    }
+                }
+                if (minPD > (double)p.line_dist_thresh) {  // :421
+                    mm--;
+                    continue;
+                }
+                mm--;
+                row[best] = row[mm - 1];  // :427-430
+                mm--;
+                const int slot = D - 2 * (ncol_mine + 1);
+                row[slot] = (uint16_t)p1;
+                row[slot + 1] = (uint16_t)bp2;
+                ncol_mine++;
+            }
+        }
+        int tot;
+        const int ex = block_excl_scan(ncol_mine, m.ws, &tot);
+        if (pt < n) {
+            const int off = colcarry + ex;
+            col_off[pt] = off;
+            const uint16_t* row = m.adj + pt * p.deg_cap;
+            for (int k = 0; k < ncol_mine; k++) {
+                const int slot = D - 2 * (k + 1);
+                if (off + k < p.lay.max_col) {
+                    col_pairs[2 * (off + k)] = row[slot];
+                    col_pairs[2 * (off + k) + 1] = row[slot + 1];
+                }
+            }
+        }
+        colcarry += tot;
+    }
+    if (colcarry > p.lay.max_col) status |= ST_OVF_COLINE;
+    if (tid == 0) {
+        col_off[n] = colcarry;
+        hdr[HDR_NEDGES] = nedges;
+        hdr[HDR_NCOL] = colcarry;
+        hdr[HDR_STATUS] |= (int)status;
+        hdr[HDR_NPASS] = npass_all;
+        hdr[HDR_NLINES] = ncreated;
+    }
+    (void)ko;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K13: genPointDescriptor (:515-538): grid_sampler(bilinear, zeros, align_corners=false) at the DISTORTED
+// integer pixel + F.normalize.  One warp per keypoint, lane = 8 consecutive channels of the NHWC map.
+__global__ void __launch_bounds__(256) desc_kernel(const PostParams p) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int n = hdr_of(p, b)[HDR_NKP];
+    if (k >= n) return;
+    float* o = out_of<float>(p, b, p.lay.desc) + (size_t)k * 256 + lane * 8;
+    if (n < 10) {  // :520-524
+        *reinterpret_cast<float4*>(o) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const int px = out_of<int>(p, b, p.lay.px)[k], py = out_of<int>(p, b, p.lay.py)[k];
+    const float gx = (float)((double)__fdiv_rn((float)px, (float)p.W) * 2. - 1.);  // :530
+    const float gy = (float)((double)__fdiv_rn((float)py, (float)p.H) * 2. - 1.);  // :531
+    const float ix = __fdiv_rn((gx + 1.f) * (float)p.Wc - 1.f, 2.f), iy = __fdiv_rn((gy + 1.f) * (float)p.Hc - 1.f, 2.f);
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
+    const float nw = ((float)x1 - ix) * ((float)y1 - iy), ne = (ix - (float)x0) * ((float)y1 - iy);
+    const float sw = ((float)x1 - ix) * (iy - (float)y0), se = (ix - (float)x0) * (iy - (float)y0);
+    const float* d = p.desc + (size_t)b * p.Hc * p.Wc * 256 + lane * 8;
+    float r[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) r[c] = 0.f;
+    auto tap = [&](int yy, int xx, float w) {
+        if (yy >= 0 && yy < p.Hc && xx >= 0 && xx < p.Wc) {
+            const float* q = d + ((size_t)yy * p.Wc + xx) * 256;
+            const float4 a = *reinterpret_cast<const float4*>(q), c4 = *reinterpret_cast<const float4*>(q + 4);
+            const float v[8] = {a.x, a.y, a.z, a.w, c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int c = 0; c < 8; c++) r[c] += v[c] * w;
+        }
+    };
+    tap(y0, x0, nw);
+    tap(y0, x1, ne);
+    tap(y1, x0, sw);
+    tap(y1, x1, se);
+    double ss = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) ss += (double)r[c] * (double)r[c];
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) ss += __shfl_xor_sync(FULL, ss, s);
+    float nrm = (float)sqrt(ss);
+    if (nrm < 1e-12f) nrm = 1e-12f;  // F.normalize eps
+#pragma unroll
+    for (int c = 0; c < 8; c++) r[c] = __fdiv_rn(r[c], nrm);
+    *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(r[4], r[5], r[6], r[7]);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+OutLayout make_out_layout(int max_kp, int max_edges, int max_col) {
+    OutLayout L;
+    L.max_kp = max_kp;
+    L.max_edges = max_edges;
+    L.max_col = max_col;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t r = o;
+        o = align_up(o + bytes, 16);
+        return r;
+    };
+    L.hdr = take(HDR_WORDS * 4);
+    L.kp_x = take((size_t)max_kp * 4);
+    L.kp_y = take((size_t)max_kp * 4);
+    L.px = take((size_t)max_kp * 4);
+    L.py = take((size_t)max_kp * 4);
+    L.score = take((size_t)max_kp * 4);
+    L.xun = take((size_t)max_kp * 4);
+    L.yun = take((size_t)max_kp * 4);
+    L.kout = take((size_t)max_kp);
+    L.edge_s = take((size_t)max_edges * 4);
+    L.edge_e = take((size_t)max_edges * 4);
+    L.edge_score = take((size_t)max_edges * 4);
+    L.conn_off = take((size_t)(max_kp + 1) * 4);
+    L.conn_idx = take((size_t)max_edges * 8);
+    L.col_off = take((size_t)(max_kp + 1) * 4);
+    L.col_pairs = take((size_t)max_col * 8);
+    o = align_up(o, 256);
+    L.small_total = o;
+    L.desc = take((size_t)max_kp * 256 * 4);
+    L.total = align_up(o, 256);
+    return L;
+}
+
+size_t post_nms_smem(const PostParams& p) { return (size_t)p.acc_cap * 8; }
+
+size_t post_lines_smem(const PostParams& p) {
+    size_t s = (size_t)p.pair_cap * 16;                    // dist, dirf, dirb, se
+    s += (size_t)(p.max_kp * 4 + 1) * 4 + 40 * 4;          // adj_cnt, row_off, kx, ky, ws
+    s += (size_t)p.max_kp * p.deg_cap * 2 + p.pair_cap;    // adj, flag
+    return align_up(s, 16);
+}
+
+cudaError_t post_init_attrs(const PostParams& p) {
+    cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_nms_smem(p));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(lines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_lines_smem(p));
+}
+
+cudaError_t post_keypoints_launch(const PostParams& p, cudaStream_t st, long long* launches) {
+    const int HW = p.H * p.W;
+    cudaError_t e = cudaMemsetAsync(p.counters, 0, sizeof(int) * 8 * p.B, st);
+    if (e != cudaSuccess) return e;
+    dim3 g((HW / 4 + 255) / 256, p.B);
+    scan_kernel<<<g, 256, 0, st>>>(p);
+    nms_kernel<<<p.B, 1024, post_nms_smem(p), st>>>(p);
+    *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t post_heat_launch(const PostParams& p, cudaStream_t st, long long* launches) {
+    const int tiles = (p.W >> 4) * (p.H >> 4) * p.B;
+    refine_kernel<<<(tiles + 7) / 8, 256, 0, st>>>(p, p.do_remap ? p.heat_ref : p.heat_final);
+    *launches += 1;
+    if (p.do_remap) {
+        dim3 g((p.H * p.W / 4 + 255) / 256, p.B);
+        remap_kernel<<<g, 256, 0, st>>>(p);
+        *launches += 1;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t post_lines_launch(const PostParams& p, cudaStream_t st, long long* launches) {
+    dim3 g((p.max_kp + 7) / 8, p.B);
+    pair_test_kernel<<<g, 256, 0, st>>>(p);
+    lines_kernel<<<p.B, 512, post_lines_smem(p), st>>>(p);
+    *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t post_desc_launch(const PostParams& p, cudaStream_t st, long long* launches) {
+    dim3 g((p.max_kp + 7) / 8, p.B);
+    desc_kernel<<<g, 256, 0, st>>>(p);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace ppg

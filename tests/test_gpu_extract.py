@@ -1,0 +1,137 @@
+"""GPU parity tests of the extraction path, driven through the C ABI (ppg_slam_b200/capi.py).
+
+  * tcgen05 convolutions vs a plain CUDA-core convolution over the same operands (self-test);
+  * dense network outputs vs the L0 oracle (torch fp32 CPU with the reference weights) -- tolerance:
+        junction prob map  max-abs error <= 5e-3
+        heat score map     max-abs error <= 1e-2
+        sampled descriptors cosine >= 0.999          (north-star tolerances);
+  * keypoints / point-pair graph / colines given the REFERENCE maps: bit-exact vs the L1 oracle.
+"""
+import numpy as np
+import pytest
+
+from ppg_slam_b200 import cameras, synth
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL, HEAT_TOL, COS_MIN = 5e-3, 1e-2, 0.999
+
+
+@pytest.fixture(scope="module")
+def net():
+    from oracle.net_ref import NetRef
+    return NetRef()
+
+
+@pytest.fixture(scope="module")
+def ex_euroc():
+    from ppg_slam_b200 import capi
+    e = capi.Extractor(cameras.EUROC, max_batch=4)
+    yield e
+    e.close()
+
+
+def test_conv_selftest(ex_euroc):
+    ex_euroc.run([synth.frame(0, 752, 480)])
+    for name, d, r in ex_euroc.selftest_conv():
+        assert d <= 2e-2 * max(1.0, r), "layer %s: tcgen05 vs CUDA-core conv differ by %g (ref max %g)" % (name, d, r)
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_dense_maps_within_tolerance(ex_euroc, net, seed):
+    g = synth.frame(seed, 752, 480)
+    rec = ex_euroc.run([g], allow_capacity=True)[0]
+    m = ex_euroc.get_maps(0)
+    ref = net.forward_u8(g)
+    assert np.abs(m["prob"] - ref["prob"]).max() <= PROB_TOL
+    assert np.abs(m["heat"] - ref["heat"]).max() <= HEAT_TOL
+    a, b = m["desc"].reshape(256, -1), ref["desc"].reshape(256, -1)
+    cos = (a * b).sum(0) / (np.linalg.norm(a, axis=0) * np.linalg.norm(b, axis=0) + 1e-12)
+    assert cos.min() >= COS_MIN
+    assert rec["n_kp"] > 50
+
+
+@pytest.mark.parametrize("cam,seeds", [(cameras.EUROC, [0, 1, 2, 5]), (cameras.TUMVI, [1, 4]),
+                                       (cameras.UMA, [2])], ids=lambda v: getattr(v, "name", str(v)))
+def test_post_bit_exact_from_reference_maps(net, cam, seeds):
+    from ppg_slam_b200 import capi
+    from tests.parity_util import diff_records, oracle_post
+    e = capi.Extractor(cam, max_batch=len(seeds))
+    try:
+        maps = [net.forward_u8(synth.frame(s, cam.width, cam.height)) for s in seeds]
+        got = e.run_from_maps(np.stack([m["prob"] for m in maps]), np.stack([m["heat"] for m in maps]),
+                              np.stack([m["desc"] for m in maps]))
+        for f, m in enumerate(maps):
+            ref = oracle_post(cam, m["prob"], m["heat"], m["desc"])
+            assert got[f]["status"] == 0
+            bad = diff_records(got[f], ref)
+            assert not bad, "%s seed %d: %s" % (cam.name, seeds[f], "; ".join(bad))
+            hf = e.get_maps(f)["heat_final"]
+            np.testing.assert_array_equal(hf.view(np.uint32), ref["heat_final"].view(np.uint32))
+            assert got[f]["n_cand"] == ref["n_cand"]
+    finally:
+        e.close()
+
+
+def test_edge_cases_from_maps():
+    """Empty map (N == 0), fewer than 10 keypoints (zero descriptors, :520-524), keypoints on the NMS
+    border, the 500 cap, exact score ties."""
+    from ppg_slam_b200 import capi
+    from tests.parity_util import diff_records, oracle_post
+    cam = cameras.EUROC
+    H, W = cam.height, cam.width
+    e = capi.Extractor(cam, max_batch=1)
+    try:
+        rs = np.random.RandomState(0)
+        desc = rs.normal(size=(256, H // 8, W // 8)).astype(np.float32)
+        heat = (rs.rand(H, W) * 0.5).astype(np.float32)
+        cases = {}
+        cases["empty"] = np.zeros((H, W), np.float32)
+        few = np.zeros((H, W), np.float32)
+        for k, (x, y) in enumerate([(100, 100), (3, 50), (200, 3), (W - 5, 60), (W - 4, 90), (300, H - 5), (400, 200)]):
+            few[y, x] = 0.5 + 0.01 * k
+        cases["few_and_border"] = few
+        ties = np.zeros((H, W), np.float32)
+        ties[40:440:3, 40:700:3] = 0.25  # dense lattice of exactly tied scores -> raster order decides, cap 500
+        cases["ties_and_cap"] = ties
+        ramp = np.zeros((H, W), np.float32)
+        ramp[100, 50:700] = np.linspace(0.1, 0.9, 650).astype(np.float32)  # long suppression chain
+        cases["ramp_chain"] = ramp
+        for name, prob in cases.items():
+            got = e.run_from_maps(prob[None], heat[None], desc[None])[0]
+            ref = oracle_post(cam, prob, heat, desc)
+            bad = diff_records(got, ref)
+            assert not bad, "%s: %s" % (name, "; ".join(bad))
+        assert e.run_from_maps(cases["empty"][None], heat[None], desc[None])[0]["n_kp"] == 0
+    finally:
+        e.close()
+
+
+def test_batch_equals_single(ex_euroc):
+    """Frames are independent: a batch of 4 gives the same records as four single-frame calls."""
+    frames = [synth.frame(s, 752, 480) for s in (0, 1, 2, 3)]
+    batch = ex_euroc.run(frames)
+    for f in range(4):
+        single = ex_euroc.run([frames[f]])[0]
+        for k in ("px", "py", "edge_start", "edge_end", "col_pairs"):
+            np.testing.assert_array_equal(batch[f][k], single[k])
+        np.testing.assert_array_equal(batch[f]["desc"], single["desc"])
+
+
+def test_full_path_agrees_with_oracle_graph(ex_euroc, net):
+    """End to end (fp16 tensor-core networks): keypoint sets must overlap the fp32 oracle's almost entirely."""
+    from tests.parity_util import oracle_post
+    g = synth.frame(0, 752, 480)
+    got = ex_euroc.run([g])[0]
+    m = net.forward_u8(g)
+    ref = oracle_post(cameras.EUROC, m["prob"], m["heat"], m["desc"])
+    a = set(zip(got["px"].tolist(), got["py"].tolist()))
+    b = set(zip(ref["px"].tolist(), ref["py"].tolist()))
+    assert len(a & b) >= 0.9 * len(b)
+    # descriptors of the common keypoints: cosine >= 0.999
+    ia = {p: i for i, p in enumerate(zip(got["px"].tolist(), got["py"].tolist()))}
+    ib = {p: i for i, p in enumerate(zip(ref["px"].tolist(), ref["py"].tolist()))}
+    common = sorted(a & b)
+    da = got["desc"][[ia[p] for p in common]]
+    db = ref["desc"][[ib[p] for p in common]]
+    assert (da * db).sum(1).min() >= COS_MIN
