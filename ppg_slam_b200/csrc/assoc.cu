@@ -1,17 +1,690 @@
-// Image<->map association (placeholder until the tensor-core path lands in this file).
+// Image<->map descriptor association: the search core of Matcher::ExtendMapMatches
+// (matching/src/Matcher.cpp:224-281) for every map point at once, frame state frozen.
+//
+//   K14a prep     map / frame descriptors fp32 -> bf16 + squared norms; Frame::PosInGrid cells of the
+//                 keypoints (map/src/Frame.cpp:317-327); per-map-point search window and the grid-cell
+//                 range Frame::GetFeaturesInArea would visit (Frame.cpp:262-315)
+//   K14b gemm     brute-force (M x 256) . (256 x N) bf16 GEMM on tcgen05/TMEM fed by TMA; the epilogue
+//                 turns dots into approximate squared distances, applies the window mask and keeps the
+//                 per-row 4 best candidates + the 5th best value (the guard)
+//   K14c rescore  exact fp32 DescriptorDistance (feature/src/MapPoint.cpp:22-29) of the <= 4 candidates
+//                 in the fixed summation order the oracle defines, best / second best with the reference's
+//                 tie rule (first in GetFeaturesInArea order), ratio test (Matcher.cpp:276).  If the guard
+//                 cannot prove that no other candidate can beat the second best (bf16 error bound), the row
+//                 is re-scored exactly over its whole window on the GPU (counted in fallback_rows).
+// Built with -fmad=false (bit-exact distances).
+#include <cuda_bf16.h>
+#include <math.h>
+#include <string.h>
+
 #include "ctx.cuh"
-using namespace ppg;
+#include "ptx.cuh"
+
 namespace ppg {
-struct AssocState {};
-void assoc_destroy(ppg_ctx* c) { delete c->assoc; c->assoc = nullptr; }
+
+bool make_kmajor_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, bool bf16);
+
+constexpr int A_BM = 128, A_BN = 128, A_STAGES = 6, A_STAGE_BYTES = 32768, A_THREADS = 192, A_TOPK = 4;
+constexpr unsigned AFULL = 0xffffffffu;
+
+struct RowParam {  // per map point
+    float u, v, r, na2;
+    uint32_t cells;  // minCx | maxCx << 8 | minCy << 16 | maxCy << 24 ; 0xffffffff = empty window
+};
+
+struct AssocState {
+    int max_rows = 0, n_rows = 0, ncap = 0;  // ncap: keypoint capacity (multiple of 128)
+    // map side
+    float* map_f32 = nullptr;
+    __nv_bfloat16* map_bf = nullptr;
+    float* map_n2 = nullptr;
+    CUtensorMap mapA, mapB;
+    // frame side (staged or taken from the extraction output block)
+    float *kx = nullptr, *ky = nullptr, *fdesc = nullptr, *fn2 = nullptr;
+    uint8_t *free_mask = nullptr, *ones = nullptr;
+    __nv_bfloat16* f_bf = nullptr;
+    uint32_t* kinfo = nullptr;  // cx | cy << 8 | ok << 16
+    uint32_t* korder = nullptr; // (cx*48+cy) << 16 | i  : GetFeaturesInArea visiting order
+    int* d_nkp = nullptr;       // staged N on the device
+    float* nbmax = nullptr;     // max squared norm of the frame descriptors (as float bits, atomicMax)
+    int staged_n = 0;
+    // row side
+    float *proj = nullptr, *vcos = nullptr;
+    RowParam* rowp = nullptr;
+    float th = 0.f, ratio = 0.f;
+    int staged_rows = 0;
+    // results
+    int* cand = nullptr;  // [rows][4]
+    float* guard = nullptr;
+    int *best_idx = nullptr, *second_idx = nullptr;
+    float *best_d = nullptr, *second_d = nullptr;
+    uint8_t* accept = nullptr;
+    int* fallback = nullptr;
+    // pinned host staging for fetch
+    uint8_t* h_res = nullptr;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_desc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                        float* __restrict__ n2, const int* n_ptr, int n_val,
+                                                        int rows_padded, float* nbmax) {
+    // one warp per row; rows >= n are zero-filled (so that padded GEMM columns are inert)
+    const int n = n_ptr ? *n_ptr : n_val;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows_padded) return;
+    float v[8];
+    if (row < n) {
+        const float4 a = *reinterpret_cast<const float4*>(src + (size_t)row * 256 + lane * 8);
+        const float4 b = *reinterpret_cast<const float4*>(src + (size_t)row * 256 + lane * 8 + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = 0.f;
+    }
+    float s = 0.f;
+    __nv_bfloat162 o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        o[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+        s += v[2 * k] * v[2 * k] + v[2 * k + 1] * v[2 * k + 1];
+    }
+    *reinterpret_cast<uint4*>(dst + (size_t)row * 256 + lane * 8) = *reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(AFULL, s, m);
+    if (lane == 0) {
+        n2[row] = s;
+        if (nbmax && row < n) atomicMax(reinterpret_cast<int*>(nbmax), __float_as_int(s));
+    }
 }
+
+struct GridParam {
+    int minX, minY;
+    float wInv, hInv;
+};
+
+// Frame::PosInGrid (Frame.cpp:317-327) for every keypoint + the free mask (Matcher.cpp:253).
+__global__ void prep_kp_kernel(const float* __restrict__ kx, const float* __restrict__ ky,
+                               const uint8_t* __restrict__ free_mask, const int* n_ptr, int n_val, int ncap,
+                               GridParam g, uint32_t* __restrict__ kinfo, uint32_t* __restrict__ korder) {
+    const int n = n_ptr ? *n_ptr : n_val;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncap) return;
+    uint32_t info = 0, order = 0xffffffffu;
+    if (i < n) {
+        const int px = (int)roundf((kx[i] - (float)g.minX) * g.wInv);
+        const int py = (int)roundf((ky[i] - (float)g.minY) * g.hInv);
+        const bool indexable = !(px < 0 || px >= 64 || py < 0 || py >= 48);
+        if (indexable) {
+            info = (uint32_t)px | ((uint32_t)py << 8) | ((free_mask[i] ? 1u : 0u) << 16);
+            order = ((uint32_t)(px * 48 + py) << 16) | (uint32_t)i;
+        }
+    }
+    kinfo[i] = info;
+    korder[i] = order;
+}
+
+// Search window of each map point: r (Matcher.cpp:240-244) and the cell range of GetFeaturesInArea
+// (Frame.cpp:270-292) including its early returns.
+__global__ void prep_rows_kernel(const float* __restrict__ proj, const float* __restrict__ vcos,
+                                 const float* __restrict__ n2, int rows, float th, GridParam g,
+                                 RowParam* __restrict__ rp) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= rows) return;
+    RowParam p;
+    p.u = proj[2 * m];
+    p.v = proj[2 * m + 1];
+    float r = th;
+    if ((double)vcos[m] > 0.998)
+        r = (float)((double)r * 2.5);
+    else
+        r = (float)((double)r * 4.0);
+    p.r = r;
+    p.na2 = n2[m];
+    bool empty = false;
+    int x0 = (int)floorf((p.u - (float)g.minX - r) * g.wInv);
+    if (x0 < 0) x0 = 0;
+    if (x0 >= 64) empty = true;
+    int x1 = (int)ceilf((p.u - (float)g.minX + r) * g.wInv);
+    if (x1 > 63) x1 = 63;
+    if (x1 < 0) empty = true;
+    int y0 = (int)floorf((p.v - (float)g.minY - r) * g.hInv);
+    if (y0 < 0) y0 = 0;
+    if (y0 >= 48) empty = true;
+    int y1 = (int)ceilf((p.v - (float)g.minY + r) * g.hInv);
+    if (y1 > 47) y1 = 47;
+    if (y1 < 0) empty = true;
+    p.cells = empty ? 0xffffffffu : ((uint32_t)x0 | ((uint32_t)x1 << 8) | ((uint32_t)y0 << 16) | ((uint32_t)y1 << 24));
+    rp[m] = p;
+}
+
+__device__ __forceinline__ bool in_window(const RowParam& p, uint32_t info, float x, float y) {
+    if (!(info & 0x10000u) || p.cells == 0xffffffffu) return false;
+    const uint32_t cx = info & 0xff, cy = (info >> 8) & 0xff;
+    if (cx < (p.cells & 0xff) || cx > ((p.cells >> 8) & 0xff) || cy < ((p.cells >> 16) & 0xff) || cy > (p.cells >> 24))
+        return false;
+    return fabsf(x - p.u) < p.r && fabsf(y - p.v) < p.r;  // Frame.cpp:305-309
+}
+
+// ------------------------------------------------------------------------------------------------
+// K14b.  GEMM view: D[map row, keypoint] = <a, b>.  M tile = 128 map rows (TMEM lanes), N tile = 128
+// keypoints, K = 256 = 4 chunks of 64 bf16 (one 128-byte swizzled smem row per descriptor per chunk).
+// warp 0: TMA producer, warp 1: MMA issuer / TMEM owner, warps 2-5: epilogue (one map row per thread).
+struct GemmParams {
+    int rows, n_tiles_n;
+    const int* n_ptr;
+    int n_val;
+    const RowParam* rowp;
+    const float* kx;
+    const float* ky;
+    const float* fn2;
+    const uint32_t* kinfo;
+    int* cand;
+    float* guard;
+};
+
+__global__ void __launch_bounds__(A_THREADS, 1)
+assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)A_STAGES * A_STAGE_BYTES);
+    uint64_t* empty = full + 8;
+    uint64_t* tfull = empty + 8;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float4* kp = reinterpret_cast<float4*>(tmem_slot + 4);  // [ncols] x, y, n2, info(bits)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = p.n_ptr ? *p.n_ptr : p.n_val;
+    const int ncols = p.n_tiles_n * A_BN;
+    const int m_tiles = (p.rows + A_BM - 1) / A_BM;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < A_STAGES; i++) {
+            ptx::mbar_init(&full[i], 1);
+            ptx::mbar_init(&empty[i], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            ptx::mbar_init(&tfull[a], 1);
+            ptx::mbar_init(&tempty[a], 4);
+        }
+        ptx::fence_barrier_init();
+        ptx::prefetch_tmap(&mapA);
+        ptx::prefetch_tmap(&mapB);
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, 256);
+        ptx::tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) v = make_float4(p.kx[i], p.ky[i], p.fn2[i], __uint_as_float(p.kinfo[i]));
+        kp[i] = v;
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int used_tiles_n = (n + A_BN - 1) / A_BN;  // keypoint tiles that hold at least one keypoint
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
+                for (int nt = 0; nt < used_tiles_n; nt++)
+                    for (int kc = 0; kc < 4; kc++, it++) {
+                        const uint32_t s = it % A_STAGES, ph = (it / A_STAGES) & 1;
+                        ptx::mbar_wait(&empty[s], ph ^ 1);
+                        ptx::mbar_expect_tx(&full[s], A_STAGE_BYTES);
+                        uint8_t* a = smem + (size_t)s * A_STAGE_BYTES;
+                        ptx::tma_load_2d(a, &mapA, &full[s], kc * 64, mt * A_BM);
+                        ptx::tma_load_2d(a + 16384, &mapB, &full[s], kc * 64, nt * A_BN);
+                    }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::make_idesc_f16(A_BM, A_BN, 1);
+            uint32_t it = 0, lt = 0;
+            for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
+                for (int nt = 0; nt < used_tiles_n; nt++, lt++) {
+                    const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
+                    ptx::mbar_wait(&tempty[acc], aph ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * A_BN;
+                    for (int kc = 0; kc < 4; kc++, it++) {
+                        const uint32_t s = it % A_STAGES, ph = (it / A_STAGES) & 1;
+                        ptx::mbar_wait(&full[s], ph);
+                        ptx::tc_fence_after();
+                        const uint32_t a_addr = ptx::smem_u32(smem + (size_t)s * A_STAGE_BYTES);
+                        const uint64_t adesc = ptx::make_sw128_desc(a_addr);
+                        const uint64_t bdesc = ptx::make_sw128_desc(a_addr + 16384);
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            ptx::umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kc | k) != 0));
+                        ptx::umma_commit(&empty[s]);
+                    }
+                    ptx::umma_commit(&tfull[acc]);
+                }
+        }
+    } else {
+        const int q = warp & 3;
+        const int rloc = q * 32 + lane;
+        uint32_t lt = 0;
+        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+            const int row = mt * A_BM + rloc;
+            RowParam rp;
+            rp.u = rp.v = rp.r = rp.na2 = 0.f;
+            rp.cells = 0xffffffffu;
+            if (row < p.rows) rp = p.rowp[row];
+            float bd[A_TOPK];
+            int bi[A_TOPK];
+#pragma unroll
+            for (int k = 0; k < A_TOPK; k++) {
+                bd[k] = INFINITY;
+                bi[k] = -1;
+            }
+            float a5 = INFINITY;
+            for (int nt = 0; nt < used_tiles_n; nt++, lt++) {
+                const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
+                ptx::mbar_wait(&tfull[acc], aph);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * A_BN;
+                for (int c0 = 0; c0 < A_BN; c0 += 16) {
+                    uint32_t rr[16];
+                    ptx::tmem_ld16(taddr + c0, rr);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int col = nt * A_BN + c0 + j;
+                        const float4 k4 = kp[col];
+                        if (!in_window(rp, __float_as_uint(k4.w), k4.x, k4.y)) continue;
+                        const float d2 = (rp.na2 + k4.z) - 2.0f * __uint_as_float(rr[j]);
+                        if (d2 < bd[A_TOPK - 1]) {
+                            a5 = bd[A_TOPK - 1];
+                            float cd = d2;
+                            int ci = col;
+#pragma unroll
+                            for (int k = 0; k < A_TOPK; k++) {
+                                if (cd < bd[k]) {
+                                    const float td = bd[k];
+                                    const int ti = bi[k];
+                                    bd[k] = cd;
+                                    bi[k] = ci;
+                                    cd = td;
+                                    ci = ti;
+                                }
+                            }
+                        } else if (d2 < a5) {
+                            a5 = d2;
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+            }
+            if (row < p.rows) {
+                *reinterpret_cast<int4*>(p.cand + (size_t)row * 4) = make_int4(bi[0], bi[1], bi[2], bi[3]);
+                p.guard[row] = a5;
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DescriptorDistance in the fixed order shared with the oracle (ppgo_descriptor_distance): lane l sums
+// elements l, l+32, ... in order, then an xor butterfly 16,8,4,2,1; every lane ends with the same value.
+__device__ __forceinline__ float exact_distance(const float* __restrict__ a, const float* __restrict__ b, int lane) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const float d = a[lane + 32 * k] - b[lane + 32 * k];
+        s = s + d * d;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) s = s + __shfl_xor_sync(AFULL, s, m);
+    return sqrtf(s);
+}
+
+struct RescoreParams {
+    int rows;
+    const int* n_ptr;
+    int n_val;
+    const RowParam* rowp;
+    const float* map_f32;
+    const float* fdesc;
+    const float* kx;
+    const float* ky;
+    const uint32_t* kinfo;
+    const uint32_t* korder;
+    const int* cand;
+    const float* guard;
+    const float* nbmax;
+    float ratio, th_high;
+    int force_exact;  // 1: ignore the GEMM candidates and score every window exactly (validation)
+    int *best_idx, *second_idx;
+    float *best_d, *second_d;
+    uint8_t* accept;
+    int* fallback;
+};
+
+// best = first minimum, second = first minimum of the rest, both in GetFeaturesInArea order
+// (equivalent to the strict-< update at Matcher.cpp:262-271).
+__device__ __forceinline__ void top2_update(float d, uint32_t ord, int idx, float& b1, uint32_t& o1, int& i1, float& b2,
+                                            uint32_t& o2, int& i2) {
+    if (d < b1 || (d == b1 && ord < o1)) {
+        b2 = b1; o2 = o1; i2 = i1;
+        b1 = d; o1 = ord; i1 = idx;
+    } else if (d < b2 || (d == b2 && ord < o2)) {
+        b2 = d; o2 = ord; i2 = idx;
+    }
+}
+
+__global__ void __launch_bounds__(256) assoc_rescore_kernel(const RescoreParams p) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= p.rows) return;
+    const int n = p.n_ptr ? *p.n_ptr : p.n_val;
+    const RowParam rp = p.rowp[row];
+    const float* a = p.map_f32 + (size_t)row * 256;
+    float b1 = 1e6f, b2 = 1e6f;  // Matcher.cpp:248-249 initial values
+    uint32_t o1 = 0xffffffffu, o2 = 0xffffffffu;
+    int i1 = -1, i2 = -1;
+    bool exact_all = p.force_exact != 0;
+    if (!exact_all) {
+        const int4 c4 = *reinterpret_cast<const int4*>(p.cand + (size_t)row * 4);
+        const int cs[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (cs[k] < 0) continue;
+            const float d = exact_distance(a, p.fdesc + (size_t)cs[k] * 256, lane);
+            top2_update(d, p.korder[cs[k]], cs[k], b1, o1, i1, b2, o2, i2);
+        }
+        const float g = p.guard[row];
+        if (g < INFINITY) {
+            // bf16 operands: |dot_bf16 - dot| <= (2^-8 + 2^-16) |a||b| (+ fp32 accumulation); in squared distance x2
+            const float delta = 0.0080f * sqrtf(rp.na2 * (*p.nbmax)) + 2e-4f;
+            const float e2 = b2 * b2;
+            if (!(g - delta > e2 + delta)) exact_all = true;
+        }
+    }
+    if (exact_all) {
+        if (!p.force_exact && lane == 0) atomicAdd(p.fallback, 1);
+        b1 = b2 = 1e6f;
+        o1 = o2 = 0xffffffffu;
+        i1 = i2 = -1;
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int c = c0 + lane;
+            bool in = false;
+            if (c < n) in = in_window(rp, p.kinfo[c], p.kx[c], p.ky[c]);
+            unsigned mask = __ballot_sync(AFULL, in);
+            while (mask) {
+                const int cc = c0 + __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float d = exact_distance(a, p.fdesc + (size_t)cc * 256, lane);
+                top2_update(d, p.korder[cc], cc, b1, o1, i1, b2, o2, i2);
+            }
+        }
+    }
+    if (lane == 0) {
+        p.best_idx[row] = i1;
+        p.second_idx[row] = i2;
+        p.best_d[row] = b1;
+        p.second_d[row] = b2;
+        uint8_t acc = 0;
+        if (i1 >= 0) acc = !(b1 > p.th_high && b1 > p.ratio * b2);  // Matcher.cpp:276
+        p.accept[row] = acc;
+    }
+}
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+}
+
+int ensure_state(ppg_ctx* c) {
+    if (c->assoc) return PPG_OK;
+    AssocState* s = new AssocState();
+    c->assoc = s;
+    s->max_rows = c->cfg.max_map_points > 0 ? c->cfg.max_map_points : 65536;
+    s->ncap = 1024;
+    const size_t R = s->max_rows, N = s->ncap;
+    PPG_CUDA(c, dalloc(&s->map_f32, R * 256));
+    PPG_CUDA(c, dalloc(&s->map_bf, R * 256));
+    PPG_CUDA(c, dalloc(&s->map_n2, R));
+    PPG_CUDA(c, dalloc(&s->kx, N));
+    PPG_CUDA(c, dalloc(&s->ky, N));
+    PPG_CUDA(c, dalloc(&s->fdesc, N * 256));
+    PPG_CUDA(c, dalloc(&s->fn2, N));
+    PPG_CUDA(c, dalloc(&s->free_mask, N));
+    PPG_CUDA(c, dalloc(&s->ones, N));
+    PPG_CUDA(c, cudaMemset(s->ones, 1, N));
+    PPG_CUDA(c, dalloc(&s->f_bf, N * 256));
+    PPG_CUDA(c, dalloc(&s->kinfo, N));
+    PPG_CUDA(c, dalloc(&s->korder, N));
+    PPG_CUDA(c, dalloc(&s->d_nkp, 1));
+    PPG_CUDA(c, dalloc(&s->nbmax, 1));
+    PPG_CUDA(c, dalloc(&s->proj, R * 2));
+    PPG_CUDA(c, dalloc(&s->vcos, R));
+    PPG_CUDA(c, dalloc(&s->rowp, R));
+    PPG_CUDA(c, dalloc(&s->cand, R * 4));
+    PPG_CUDA(c, dalloc(&s->guard, R));
+    PPG_CUDA(c, dalloc(&s->best_idx, R));
+    PPG_CUDA(c, dalloc(&s->second_idx, R));
+    PPG_CUDA(c, dalloc(&s->best_d, R));
+    PPG_CUDA(c, dalloc(&s->second_d, R));
+    PPG_CUDA(c, dalloc(&s->accept, R));
+    PPG_CUDA(c, dalloc(&s->fallback, 1));
+    PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&s->h_res), R * 17));
+    if (!make_kmajor_map(&s->mapA, s->map_bf, R, 256, A_BM, true) ||
+        !make_kmajor_map(&s->mapB, s->f_bf, N, 256, A_BN, true))
+        return set_err(c, PPG_ERR_CUDA, "cuTensorMapEncodeTiled failed for the association operands");
+    const int smem = A_STAGES * A_STAGE_BYTES + 1024 + 20 * 8 + 16 + (int)N * 16 + 64;
+    PPG_CUDA(c, cudaFuncSetAttribute(assoc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return PPG_OK;
+}
+
+// prep + gemm + rescore on the ctx stream.  Frame-side inputs are given as device pointers.
+int run_assoc(ppg_ctx* c, const float* kx, const float* ky, const float* fdesc, const uint8_t* free_mask,
+              const int* n_ptr, int n_val, int force_exact) {
+    AssocState* s = c->assoc;
+    const int rows = s->staged_rows;
+    if (rows < 1 || rows > s->n_rows) return set_err(c, PPG_ERR_ARG, "association: stage rows first (<= uploaded rows)");
+    GridParam g{c->minX, c->minY, c->wInv, c->hInv};
+    PPG_CUDA(c, cudaMemsetAsync(s->nbmax, 0, 4, c->st));
+    PPG_CUDA(c, cudaMemsetAsync(s->fallback, 0, 4, c->st));
+    prep_desc_kernel<<<s->ncap / 8, 256, 0, c->st>>>(fdesc, s->f_bf, s->fn2, n_ptr, n_val, s->ncap, s->nbmax);
+    prep_kp_kernel<<<(s->ncap + 255) / 256, 256, 0, c->st>>>(kx, ky, free_mask, n_ptr, n_val, s->ncap, g, s->kinfo,
+                                                            s->korder);
+    prep_rows_kernel<<<(rows + 255) / 256, 256, 0, c->st>>>(s->proj, s->vcos, s->map_n2, rows, s->th, g, s->rowp);
+    c->launches += 3;
+    if (!force_exact) {
+        GemmParams gp;
+        gp.rows = rows;
+        gp.n_tiles_n = s->ncap / A_BN;
+        gp.n_ptr = n_ptr;
+        gp.n_val = n_val;
+        gp.rowp = s->rowp;
+        gp.kx = kx;
+        gp.ky = ky;
+        gp.fn2 = s->fn2;
+        gp.kinfo = s->kinfo;
+        gp.cand = s->cand;
+        gp.guard = s->guard;
+        const int m_tiles = (rows + A_BM - 1) / A_BM;
+        const int grid = m_tiles < c->num_sms ? m_tiles : c->num_sms;
+        const int smem = A_STAGES * A_STAGE_BYTES + 1024 + 20 * 8 + 16 + s->ncap * 16 + 64;
+        assoc_gemm_kernel<<<grid, A_THREADS, smem, c->st>>>(s->mapA, s->mapB, gp);
+        c->launches++;
+    }
+    RescoreParams rp;
+    rp.rows = rows;
+    rp.n_ptr = n_ptr;
+    rp.n_val = n_val;
+    rp.rowp = s->rowp;
+    rp.map_f32 = s->map_f32;
+    rp.fdesc = fdesc;
+    rp.kx = kx;
+    rp.ky = ky;
+    rp.kinfo = s->kinfo;
+    rp.korder = s->korder;
+    rp.cand = s->cand;
+    rp.guard = s->guard;
+    rp.nbmax = s->nbmax;
+    rp.ratio = s->ratio;
+    rp.th_high = c->cfg.th_high;
+    rp.force_exact = force_exact;
+    rp.best_idx = s->best_idx;
+    rp.second_idx = s->second_idx;
+    rp.best_d = s->best_d;
+    rp.second_d = s->second_d;
+    rp.accept = s->accept;
+    rp.fallback = s->fallback;
+    assoc_rescore_kernel<<<(rows + 7) / 8, 256, 0, c->st>>>(rp);
+    c->launches++;
+    PPG_CUDA(c, cudaGetLastError());
+    return PPG_OK;
+}
+
+}  // namespace
+
+void assoc_destroy(ppg_ctx* c) {
+    AssocState* s = c->assoc;
+    if (!s) return;
+    void* bufs[] = {s->map_f32, s->map_bf, s->map_n2, s->kx, s->ky, s->fdesc, s->fn2, s->free_mask, s->ones, s->f_bf,
+                    s->kinfo, s->korder, s->d_nkp, s->nbmax, s->proj, s->vcos, s->rowp, s->cand, s->guard,
+                    s->best_idx, s->second_idx, s->best_d, s->second_d, s->accept, s->fallback};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    if (s->h_res) cudaFreeHost(s->h_res);
+    delete s;
+    c->assoc = nullptr;
+}
+
+}  // namespace ppg
+
+using namespace ppg;
+
 extern "C" {
-int ppg_upload_map(ppg_ctx* c, const float*, int) { return set_err(c, PPG_ERR_ARG, "association not built"); }
-int ppg_associate(ppg_ctx* c, const ppg_assoc_in*, ppg_assoc_out*) { return set_err(c, PPG_ERR_ARG, "association not built"); }
-int ppg_assoc_stage(ppg_ctx* c, const ppg_assoc_in*) { return set_err(c, PPG_ERR_ARG, "association not built"); }
-int ppg_assoc_run(ppg_ctx* c) { return set_err(c, PPG_ERR_ARG, "association not built"); }
-int ppg_assoc_fetch(ppg_ctx* c, ppg_assoc_out*) { return set_err(c, PPG_ERR_ARG, "association not built"); }
-int ppg_assoc_run_frame(ppg_ctx* c, int) { return set_err(c, PPG_ERR_ARG, "association not built"); }
-int ppg_assoc_fallback_rows(ppg_ctx* c, int*) { return set_err(c, PPG_ERR_ARG, "association not built"); }
-int ppg_assoc_device_results(ppg_ctx* c, void**, void**, void**, void**, void**) { return set_err(c, PPG_ERR_ARG, "association not built"); }
+
+int ppg_upload_map(ppg_ctx* c, const float* map_desc, int n_rows) {
+    if (!c || !map_desc || n_rows < 1) return set_err(c, PPG_ERR_ARG, "ppg_upload_map: bad arguments");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    int rc = ensure_state(c);
+    if (rc != PPG_OK) return rc;
+    AssocState* s = c->assoc;
+    if (n_rows > s->max_rows) return set_err(c, PPG_ERR_ARG, "ppg_upload_map: more rows than max_map_points");
+    PPG_CUDA(c, cudaMemcpyAsync(s->map_f32, map_desc, (size_t)n_rows * 1024, cudaMemcpyHostToDevice, c->st));
+    const int padded = (n_rows + 7) / 8 * 8 <= s->max_rows ? (n_rows + 7) / 8 * 8 : n_rows;
+    prep_desc_kernel<<<(padded + 7) / 8, 256, 0, c->st>>>(s->map_f32, s->map_bf, s->map_n2, nullptr, n_rows, padded,
+                                                          nullptr);
+    c->launches++;
+    PPG_CUDA(c, cudaGetLastError());
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    s->n_rows = n_rows;
+    return PPG_OK;
 }
+
+int ppg_assoc_stage(ppg_ctx* c, const ppg_assoc_in* in) {
+    if (!c || !in) return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage: null argument");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    int rc = ensure_state(c);
+    if (rc != PPG_OK) return rc;
+    AssocState* s = c->assoc;
+    if (in->n_rows < 1 || in->n_rows > s->n_rows || !in->proj_uv || !in->view_cos)
+        return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage: n_rows must be in [1, uploaded rows]");
+    if (in->n_kp < 0 || in->n_kp > s->ncap) return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage: too many keypoints");
+    PPG_CUDA(c, cudaMemcpyAsync(s->proj, in->proj_uv, (size_t)in->n_rows * 8, cudaMemcpyHostToDevice, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(s->vcos, in->view_cos, (size_t)in->n_rows * 4, cudaMemcpyHostToDevice, c->st));
+    if (in->n_kp > 0 && in->kp_x && in->kp_y && in->frame_desc) {
+        PPG_CUDA(c, cudaMemcpyAsync(s->kx, in->kp_x, (size_t)in->n_kp * 4, cudaMemcpyHostToDevice, c->st));
+        PPG_CUDA(c, cudaMemcpyAsync(s->ky, in->kp_y, (size_t)in->n_kp * 4, cudaMemcpyHostToDevice, c->st));
+        PPG_CUDA(c, cudaMemcpyAsync(s->fdesc, in->frame_desc, (size_t)in->n_kp * 1024, cudaMemcpyHostToDevice, c->st));
+        if (in->free_mask)
+            PPG_CUDA(c, cudaMemcpyAsync(s->free_mask, in->free_mask, (size_t)in->n_kp, cudaMemcpyHostToDevice, c->st));
+        else
+            PPG_CUDA(c, cudaMemsetAsync(s->free_mask, 1, (size_t)in->n_kp, c->st));
+    }
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    s->staged_n = in->n_kp;
+    s->staged_rows = in->n_rows;
+    s->th = in->th;
+    s->ratio = in->ratio;
+    return PPG_OK;
+}
+
+int ppg_assoc_run(ppg_ctx* c) {
+    if (!c || !c->assoc) return set_err(c, PPG_ERR_ARG, "ppg_assoc_run: nothing staged");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    AssocState* s = c->assoc;
+    return run_assoc(c, s->kx, s->ky, s->fdesc, s->free_mask, nullptr, s->staged_n, 0);
+}
+
+int ppg_assoc_run_frame(ppg_ctx* c, int frame) {
+    if (!c || !c->assoc || frame < 0 || frame >= c->maxB)
+        return set_err(c, PPG_ERR_ARG, "ppg_assoc_run_frame: bad frame or nothing staged");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    AssocState* s = c->assoc;
+    const OutLayout& L = c->post.lay;
+    const uint8_t* blk = c->d_out + (size_t)frame * L.total;
+    // mvKeysUn[i].mPos as run() returns it (kp_x, kp_y) and the descriptors, still on the device
+    return run_assoc(c, reinterpret_cast<const float*>(blk + L.kp_x), reinterpret_cast<const float*>(blk + L.kp_y),
+                     reinterpret_cast<const float*>(blk + L.desc), s->ones,
+                     reinterpret_cast<const int*>(blk + L.hdr) + HDR_NKP, 0, 0);
+}
+
+int ppg_assoc_fetch(ppg_ctx* c, ppg_assoc_out* out) {
+    if (!c || !c->assoc || !out) return set_err(c, PPG_ERR_ARG, "ppg_assoc_fetch: null argument");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    AssocState* s = c->assoc;
+    const size_t R = s->staged_rows;
+    uint8_t* h = s->h_res;
+    PPG_CUDA(c, cudaMemcpyAsync(h, s->best_idx, R * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(h + R * 4, s->second_idx, R * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(h + R * 8, s->best_d, R * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(h + R * 12, s->second_d, R * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(h + R * 16, s->accept, R, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    if (out->best_idx) memcpy(out->best_idx, h, R * 4);
+    if (out->second_idx) memcpy(out->second_idx, h + R * 4, R * 4);
+    if (out->best_dist) memcpy(out->best_dist, h + R * 8, R * 4);
+    if (out->second_dist) memcpy(out->second_dist, h + R * 12, R * 4);
+    if (out->accept) memcpy(out->accept, h + R * 16, R);
+    return PPG_OK;
+}
+
+int ppg_associate(ppg_ctx* c, const ppg_assoc_in* in, ppg_assoc_out* out) {
+    int rc = ppg_assoc_stage(c, in);
+    if (rc != PPG_OK) return rc;
+    if ((rc = ppg_assoc_run(c)) != PPG_OK) return rc;
+    return ppg_assoc_fetch(c, out);
+}
+
+int ppg_assoc_fallback_rows(ppg_ctx* c, int* n) {
+    if (!c || !c->assoc || !n) return set_err(c, PPG_ERR_ARG, "ppg_assoc_fallback_rows: null argument");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    PPG_CUDA(c, cudaMemcpy(n, c->assoc->fallback, 4, cudaMemcpyDeviceToHost));
+    return PPG_OK;
+}
+
+int ppg_assoc_device_results(ppg_ctx* c, void** best_idx, void** second_idx, void** best_dist, void** second_dist,
+                             void** accept) {
+    if (!c || !c->assoc) return set_err(c, PPG_ERR_ARG, "ppg_assoc_device_results: nothing staged");
+    AssocState* s = c->assoc;
+    if (best_idx) *best_idx = s->best_idx;
+    if (second_idx) *second_idx = s->second_idx;
+    if (best_dist) *best_dist = s->best_d;
+    if (second_dist) *second_dist = s->second_d;
+    if (accept) *accept = s->accept;
+    return PPG_OK;
+}
+
+}  // extern "C"

@@ -28,8 +28,11 @@ def diff_records(got, ref, desc_tol=1e-6):
             bad.append("%s differs (%s vs %s)" % (k, a.shape, b.shape))
     for k in F32_EXACT_FIELDS:
         a, b = np.asarray(got[k], np.float32), np.asarray(ref[k], np.float32)
-        if a.shape != b.shape or not np.array_equal(a.view(np.uint32), b.view(np.uint32)):
-            n = int((a.view(np.uint32) != b.view(np.uint32)).sum()) if a.shape == b.shape else -1
+        # bit-identical, except that any NaN matches any NaN (x86 0/0 gives the negative quiet NaN, the GPU the
+        # positive one; lscore of the 5 <= dist < 6 lines is NaN in the reference too, PPGExtractor.cpp:376)
+        same = a.shape == b.shape and bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+        if not same:
+            n = int(((a.view(np.uint32) != b.view(np.uint32)) & ~(np.isnan(a) & np.isnan(b))).sum()) if a.shape == b.shape else -1
             bad.append("%s differs in %d entries" % (k, n))
     if got["n_kp"] > 0:
         d = np.abs(np.asarray(got["desc"]) - np.asarray(ref["desc"])).max()

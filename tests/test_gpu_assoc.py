@@ -1,0 +1,110 @@
+"""GPU parity of the image<->map association (search core of Matcher::ExtendMapMatches,
+matching/src/Matcher.cpp:224-281) against the L2 oracle: best / second-best indices, distances (bit-exact:
+both sides use the same fixed summation order) and the accept flag of the ratio test."""
+import numpy as np
+import pytest
+
+from ppg_slam_b200 import cameras, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _unit(a):
+    return (a / np.maximum(np.linalg.norm(a, axis=1, keepdims=True), 1e-12)).astype(np.float32)
+
+
+def _synthetic_keypoints(seed, cam, n):
+    rs = np.random.RandomState(seed)
+    gx, gy = np.meshgrid(np.arange(8, cam.width - 8, 6), np.arange(8, cam.height - 8, 6))
+    sel = rs.choice(gx.size, n, replace=False)
+    kx = gx.ravel()[sel].astype(np.float32) + rs.uniform(-0.4, 0.4, n).astype(np.float32)
+    ky = gy.ravel()[sel].astype(np.float32) + rs.uniform(-0.4, 0.4, n).astype(np.float32)
+    return kx, ky, _unit(rs.normal(size=(n, 256)))
+
+
+def _check(e, cam, kx, ky, fdesc, free, inp, th, ratio):
+    from oracle import post_ref as O
+    got = e.associate(kx, ky, fdesc, free, inp["proj_uv"], inp["view_cos"], th, ratio)
+    ref = O.search_all(cam, kx, ky, fdesc, free, inp["map_desc"], inp["proj_uv"], inp["view_cos"], th, ratio)
+    np.testing.assert_array_equal(got["best_idx"], ref["best_idx"])
+    np.testing.assert_array_equal(got["second_idx"], ref["second_idx"])
+    np.testing.assert_array_equal(got["best_d"].view(np.uint32), ref["best_d"].view(np.uint32))
+    np.testing.assert_array_equal(got["second_d"].view(np.uint32), ref["second_d"].view(np.uint32))
+    np.testing.assert_array_equal(got["accept"], ref["accept"])
+    return got, ref
+
+
+@pytest.mark.parametrize("cam,n,m,th", [(cameras.UMA, 1000, 50000, 10.0), (cameras.EUROC, 357, 8192, 10.0),
+                                        (cameras.TUMVI, 500, 3000, 15.0), (cameras.EUROC, 37, 300, 3.0)],
+                         ids=["uma-1000x50k", "euroc-357x8k", "tumvi-500x3k", "euroc-37x300"])
+def test_assoc_matches_oracle(cam, n, m, th):
+    from ppg_slam_b200 import capi
+    kx, ky, fdesc = _synthetic_keypoints(11, cam, n)
+    inp = synth.association_inputs(5, fdesc, np.stack([kx, ky], 1), m, cam.width, cam.height, th=th)
+    rs = np.random.RandomState(3)
+    free = (rs.rand(n) > 0.1).astype(np.uint8)
+    e = capi.Extractor(cam, max_batch=1, max_map_points=max(m, 1024))
+    try:
+        e.upload_map(inp["map_desc"])
+        got, ref = _check(e, cam, kx, ky, fdesc, free, inp, th, 0.8)
+        assert ref["accept"].sum() > 0.2 * m / 2  # planted matches are found
+        assert (ref["best_idx"] < 0).any() or m < 1000  # some windows are empty
+        fb = e.assoc_fallback_rows()
+        assert fb <= 0.25 * m, "too many rows (%d of %d) fell back to the exact window scan" % (fb, m)
+    finally:
+        e.close()
+
+
+def test_assoc_edge_cases():
+    from ppg_slam_b200 import capi
+    cam = cameras.EUROC
+    kx, ky, fdesc = _synthetic_keypoints(2, cam, 200)
+    # exact duplicates: identical descriptors on neighbouring keypoints -> tie broken by grid order
+    fdesc[10:20] = fdesc[10]
+    kx[10:20] = 300 + np.arange(10, dtype=np.float32) * 1.5
+    ky[10:20] = 200 + (np.arange(10, dtype=np.float32) % 3) * 2.0
+    # keypoints outside the undistorted image bounds are not indexable (Frame.cpp:317-327)
+    kx[0], ky[0] = -80.0, 100.0
+    kx[1], ky[1] = 900.0, 600.0
+    m = 600
+    inp = synth.association_inputs(9, fdesc, np.stack([kx, ky], 1), m, cam.width, cam.height, th=6.0)
+    inp["map_desc"][:40] = fdesc[10]          # rows that tie exactly on the duplicated keypoints
+    inp["proj_uv"][:40] = [306.0, 202.0]
+    inp["proj_uv"][40:60] = [-500.0, -500.0]  # windows entirely outside the grid (early returns :270-292)
+    inp["proj_uv"][60:70] = [5000.0, 100.0]
+    e = capi.Extractor(cam, max_batch=1, max_map_points=1024)
+    try:
+        e.upload_map(inp["map_desc"])
+        for free in (np.ones(200, np.uint8), np.zeros(200, np.uint8), (np.arange(200) % 2).astype(np.uint8)):
+            for ratio in (0.6, 0.9):
+                got, ref = _check(e, cam, kx, ky, fdesc, free, inp, 6.0, ratio)
+        assert (got["second_idx"] == -1).any()
+    finally:
+        e.close()
+
+
+def test_assoc_on_extracted_frame():
+    """extract -> associate with the frame's own keypoints/descriptors left on the device."""
+    from oracle import post_ref as O
+    from ppg_slam_b200 import capi
+    cam = cameras.EUROC
+    e = capi.Extractor(cam, max_batch=2, max_map_points=8192)
+    try:
+        recs = e.run([synth.frame(0, cam.width, cam.height), synth.frame(1, cam.width, cam.height)])
+        r = recs[1]
+        kp = np.stack([r["kp_x"], r["kp_y"]], 1)
+        inp = synth.association_inputs(4, r["desc"], kp, 8192, cam.width, cam.height, th=10.0)
+        e.upload_map(inp["map_desc"])
+        n = r["n_kp"]
+        e.assoc_stage(np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros((0, 256), np.float32),
+                      np.zeros(0, np.uint8), inp["proj_uv"], inp["view_cos"], 10.0, 0.8)
+        e.assoc_run_frame(1)
+        got = e.assoc_fetch()
+        ref = O.search_all(cam, r["kp_x"], r["kp_y"], r["desc"], np.ones(n, np.uint8), inp["map_desc"],
+                           inp["proj_uv"], inp["view_cos"], 10.0, 0.8)
+        np.testing.assert_array_equal(got["best_idx"], ref["best_idx"])
+        np.testing.assert_array_equal(got["second_idx"], ref["second_idx"])
+        np.testing.assert_array_equal(got["best_d"].view(np.uint32), ref["best_d"].view(np.uint32))
+        np.testing.assert_array_equal(got["accept"], ref["accept"])
+    finally:
+        e.close()
