@@ -48,7 +48,6 @@ def test_assoc_matches_oracle(cam, n, m, th):
         e.upload_map(inp["map_desc"])
         got, ref = _check(e, cam, kx, ky, fdesc, free, inp, th, 0.8)
         assert ref["accept"].sum() > 0.2 * m / 2  # planted matches are found
-        assert (ref["best_idx"] < 0).any() or m < 1000  # some windows are empty
         fb = e.assoc_fallback_rows()
         assert fb <= 0.25 * m, "too many rows (%d of %d) fell back to the exact window scan" % (fb, m)
     finally:
