@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the PPG-SLAM front-end hot path on B200 (BASELINE.json metric: frames/sec extract+associate
+at 752x480 on 1/2/4/8 B200).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (libppg_b200.so through the C ABI)
+  python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (oracle port) on host cores
+  torchrun --nproc-per-node N ... bench.py --gpus N ...     # N>1: one rank per GPU, frames sharded, no collective
+
+One step = one batch of 32 synthetic EuRoC-shaped frames per GPU through the whole path:
+networks (tcgen05 convolutions) -> keypoints -> point-pair graph -> descriptors -> association of every
+frame against a resident table of M map-point descriptors (search core of ExtendMapMatches).
+`value` times the device work with the frames already in HBM; `e2e` goes through the host-facing calls
+(ppg_extract with HOST frames, per-frame ppg_assoc_stage / run / fetch) including all copies.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 32
+MAP_ROWS = 8192
+TH, RATIO = 10.0, 0.8
+GFLOP_PER_FRAME = 66.633          # conv MACs x 2 at 752x480
+CONV1B_GFLOP_PER_FRAME = 2 * 13.307  # 64->64 3x3 at full resolution
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1399.0), d.get("hbm_gbs", 6538.6), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 6:
+                continue
+            try:
+                sm.append(float(c[0]))
+                mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def make_workload(batch, seed0=0):
+    from ppg_slam_b200 import cameras, synth
+    cam = cameras.EUROC
+    frames = [synth.frame(seed0 + s, cam.width, cam.height) for s in range(batch)]
+    return cam, frames
+
+
+def make_assoc_inputs(cam, recs, rows):
+    """Per-frame projections of the SAME resident map table: planted around frame 0's keypoints."""
+    from ppg_slam_b200 import synth
+    r0 = recs[0]
+    kp = np.stack([r0["kp_x"], r0["kp_y"]], 1)
+    base = synth.association_inputs(17, r0["desc"], kp, rows, cam.width, cam.height, th=TH)
+    per_frame = []
+    for f, r in enumerate(recs):
+        rs = np.random.RandomState(100 + f)
+        uv = base["proj_uv"] + rs.uniform(-2, 2, base["proj_uv"].shape).astype(np.float32)
+        per_frame.append((uv, base["view_cos"]))
+    return base["map_desc"], per_frame
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_pass(n_frames, seed0, threads, rows=MAP_ROWS):
+    """The reference path restated on the CPU (oracle): LibTorch-CPU fp32 networks, single-threaded C
+    post-processing and windowed association.  -> (seconds, frames)."""
+    import torch
+    from oracle import post_ref as O
+    from oracle.net_ref import NetRef
+    from ppg_slam_b200 import cameras, synth
+    torch.set_num_threads(threads)
+    cam = cameras.EUROC
+    net = cpu_reference_pass.net if hasattr(cpu_reference_pass, "net") else NetRef()
+    cpu_reference_pass.net = net
+    frames = [synth.frame(seed0 + s, cam.width, cam.height) for s in range(n_frames)]
+    first = None
+    t0 = time.perf_counter()
+    for g in frames:
+        m = net.forward_u8(g)
+        rec = O.extract_post(cam, m["prob"], m["heat"], m["desc"])
+        if first is None:
+            first = rec
+        if not hasattr(cpu_reference_pass, "assoc"):
+            from ppg_slam_b200 import synth as S
+            kp = np.stack([rec["kp_x"], rec["kp_y"]], 1)
+            cpu_reference_pass.assoc = S.association_inputs(17, rec["desc"], kp, rows, cam.width, cam.height, th=TH)
+        a = cpu_reference_pass.assoc
+        n = rec["n_kp"]
+        if n > 0:
+            O.search_all(cam, rec["kp_x"], rec["kp_y"], rec["desc"], np.ones(n, np.uint8), a["map_desc"],
+                         a["proj_uv"], a["view_cos"], TH, RATIO)
+    return time.perf_counter() - t0, n_frames
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 4
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_pass(1, 1000, threads)
+    t = 0.0
+    for k in range(args.steps):
+        dt, _ = cpu_reference_pass(sample, 2000 + k * sample, threads)
+        t += dt
+    fps = args.steps * sample / t
+    line = {"metric": "frames/sec extract+associate at 752x480", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": "EuRoC 752x480 synthetic frames, extract + point-pair graph + association vs "
+                                   "%d map points (CPU reference path: %d-frame sample per step)" % (MAP_ROWS, sample)},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": "%d frames per step x %d steps; networks torch-CPU fp32 with %d threads, "
+                                       "post-processing and association single-threaded C (oracle/)" %
+                                       (sample, args.steps, threads)},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, rank, local_rank, world):
+    import torch
+    from ppg_slam_b200 import capi
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = args.batch
+    cam, frames = make_workload(B, seed0=rank * B)
+    e = capi.Extractor(cam, device=local_rank, max_batch=B, max_map_points=max(args.map_rows, 1024))
+    recs = e.run(frames)
+    map_desc, per_frame = make_assoc_inputs(cam, recs, args.map_rows)
+    e.upload_map(map_desc)
+    empty = (np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros((0, 256), np.float32), np.zeros(0, np.uint8))
+
+    def device_step():
+        e.run_device(B)
+        for f in range(B):
+            e.assoc_run_frame(f)
+
+    def e2e_step():
+        rc = e.lib.ppg_extract(e.h, fptrs, fstrides, B, e._outs)
+        if rc not in (0, capi.PPG_ERR_CAPACITY):
+            raise capi.PpgError(rc, e.lib.ppg_last_error(e.h).decode())
+        for f in range(B):
+            uv, vc = per_frame[f]
+            e.assoc_stage(*empty, uv, vc, TH, RATIO)
+            e.assoc_run_frame(f)
+            e.assoc_fetch()
+
+    # ---- device-timed arm: frames resident in HBM
+    e.upload(frames)
+    e.assoc_stage(*empty, per_frame[0][0], per_frame[0][1], TH, RATIO)
+    e.set_profiling(True)
+    clocks = ClockSampler(local_rank)
+    t_w = time.perf_counter()
+    k = 0
+    while k < args.warmup or (time.perf_counter() - t_w < 1.5 and clocks.p is not None):
+        device_step()  # warm-up; keeps the GPU under load until nvidia-smi delivers its first samples
+        e.sync()
+        k += 1
+    barrier()
+    l0 = e.launch_count()
+    e.timer_start()
+    for _ in range(args.steps):
+        device_step()
+    ms = e.timer_stop()
+    launches = e.launch_count() - l0
+    barrier()
+    clk = clocks.stop()
+    stage = e.stage_times()  # last step of the timed region
+    e.set_profiling(False)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+    else:
+        ms_max = ms
+    fps = world * B * args.steps / (ms_max * 1e-3)
+
+    # ---- end-to-end arm: host frames in, host records out, every step
+    keep, fptrs, fstrides, _ = e._frame_ptrs(frames)
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    e.sync()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    if dist is not None:
+        t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    fps_e2e = world * B * args.steps / t_e2e
+    recs = [capi._frame_to_dict(e._outs[i]) for i in range(B)]
+    lay_small = 64 + sum(r["n_kp"] * 29 + r["n_edges"] * 20 + r["n_colines"] * 8 + (r["n_kp"] + 1) * 8 for r in recs)
+    h2d = B * cam.width * cam.height + B * args.map_rows * 12
+    d2h = int(lay_small + sum(r["n_kp"] for r in recs) * 1024 + B * args.map_rows * 17)
+
+    # ---- batch-1 latency (p50 ms/frame), host in -> host out
+    lat = []
+    for k in range(12):
+        t0 = time.perf_counter()
+        e.lib.ppg_extract(e.h, fptrs, fstrides, 1, e._outs)
+        e.assoc_stage(*empty, per_frame[0][0], per_frame[0][1], TH, RATIO)
+        e.assoc_run_frame(0)
+        e.assoc_fetch()
+        lat.append((time.perf_counter() - t0) * 1e3)
+    p50 = float(np.median(lat[2:]))
+
+    if rank == 0:
+        tf_peak, hbm_peak, how = _peaks()
+        sd = dict(stage)
+        conv1b_ms = sd.get("conv1b")
+        roof = None
+        if conv1b_ms:
+            ach = CONV1B_GFLOP_PER_FRAME * B / conv1b_ms  # GFLOP / ms = TFLOP/s
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "conv1b_traffic.json")
+            if os.path.exists(tp):
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            roof = {"bound": "tensor", "kernel": "conv_tc_kernel[conv1b 64->64 3x3 @752x480 + ReLU + 2x2 pool]",
+                    "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
+                    "peak_source": how + " (sustained bf16 cuBLAS; fp16 runs on the same pipe)",
+                    "ms_per_launch": conv1b_ms, "frames_per_launch": B}
+        conv_ms = sum(v for k, v in stage if k.startswith("conv") and k != "conv1a" or k.startswith("edge0")
+                      or k.startswith("edge1"))
+        cpu_t, cpu_n = 0.0, 0
+        cpu_threads = os.cpu_count() or 1
+        cpu_reference_pass(1, 1000, cpu_threads)
+        while cpu_t < 8.0 and cpu_n < 40:
+            dt, n = cpu_reference_pass(4, 3000 + cpu_n, cpu_threads)
+            cpu_t += dt
+            cpu_n += n
+        line = {"metric": "frames/sec extract+associate at 752x480", "value": fps, "unit": "frames/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+                "data": "synthetic",
+                "config": {"workload": "EuRoC 752x480 batch-%d synthetic frames per GPU: extract + point-pair graph "
+                                       "+ association of every frame vs %d resident map points" % (B, args.map_rows),
+                           "batch_per_gpu": B, "map_rows": args.map_rows, "sharding": "frames (no collective)",
+                           "l2": "per-step working set ~3.4 GB of activations streams through the 126 MB L2 "
+                                 "(inputs larger than L2; no explicit flush)"},
+                "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": d2h},
+                "latency": {"p50_ms_per_frame_batch1": p50},
+                "gpu_launches": int(launches),
+                "clocks": clk,
+                "roofline": roof,
+                "stages_ms_per_step": {k: round(v, 4) for k, v in stage},
+                "conv_tflops_all_tc_layers": (GFLOP_PER_FRAME - 0.84) * B / conv_ms if conv_ms else None,
+                "cpu_baseline": {"value": cpu_n / cpu_t, "unit": "frames/s", "cores": cpu_threads, "kind": "port",
+                                 "sample": "%d frames (same synthetic workload); networks torch-CPU fp32 on %d "
+                                           "threads, post-processing + association single-threaded C oracle" %
+                                           (cpu_n, cpu_threads)}}
+        print(json.dumps(line), flush=True)
+    e.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--map-rows", type=int, default=MAP_ROWS)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -195,12 +195,12 @@ static EncodeTiledFn get_encode() {
 }
 
 // NHWC fp16 activation [B][H][W][C] viewed as a 4-D tensor (C, W, H, B); box = 64 channels x 16 x 8 pixels.
-static bool make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, int C) {
+static bool make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_w, int box_h) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)CONV_TILE_W, (cuuint32_t)CONV_TILE_H, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -277,7 +277,7 @@ static int add_tc_layer(ppg_ctx* c, const Blob& blob, const char* name, const st
     PPG_CUDA(c, cudaMemcpy(li.w, hw.data(), hw.size() * sizeof(__half), cudaMemcpyHostToDevice));
     PPG_CUDA(c, cudaMemcpy(li.bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
     conv_tc_plan(li.L, c->maxB, H, W, cin, N, taps, mode, relu, li.bias, out, out_ld);
-    if (!make_act_map(&li.L.mapA, in, c->maxB, H, W, cin) ||
+    if (!make_act_map(&li.L.mapA, in, c->maxB, H, W, cin, li.L.box_w, li.L.box_h) ||
         !make_kmajor_map(&li.L.mapB, li.w, (uint64_t)taps * N, cin, (uint32_t)N, false))
         return set_err(c, PPG_ERR_CUDA, std::string("cuTensorMapEncodeTiled failed for ") + name);
     c->tc.push_back(li);

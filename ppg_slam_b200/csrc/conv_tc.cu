@@ -2,6 +2,8 @@
 #include "conv_tc.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace ppg {
 
 namespace {
@@ -23,6 +25,69 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
+}
+
+
+// Epilogue of one 16-channel group of one output pixel (one thread = one pixel = one TMEM lane).
+// XL / YL: lane-xor distance of the x / y neighbour inside the warp (for the fused 2x2 max-pool).
+template <int XL, int YL>
+__device__ __forceinline__ void epilogue_store(const ConvTcParams& p, const float* sbias, const uint32_t (&r)[16],
+                                               int c0, int n, int y, int x, bool inb, int lane) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        v[j] = __uint_as_float(r[j]) + sbias[c0 + j];
+        if (p.relu) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.mode == EPI_F16) {
+        if (inb) {
+            __half* o = reinterpret_cast<__half*>(p.out) + ((size_t)(n * p.H + y) * p.W + x) * p.out_ld + c0;
+            uint4 u0 = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
+                                  pack_half2(v[6], v[7]));
+            uint4 u1 = make_uint4(pack_half2(v[8], v[9]), pack_half2(v[10], v[11]), pack_half2(v[12], v[13]),
+                                  pack_half2(v[14], v[15]));
+            reinterpret_cast<uint4*>(o)[0] = u0;
+            reinterpret_cast<uint4*>(o)[1] = u1;
+        }
+    } else if (p.mode == EPI_F16_POOL) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], XL));  // x neighbour
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], YL));  // y neighbour
+        }
+        const int Ho = p.H >> 1, Wo = p.W >> 1, yo = y >> 1, xo = x >> 1;
+        if ((lane & (XL | YL)) == 0 && yo < Ho && xo < Wo) {
+            __half* o = reinterpret_cast<__half*>(p.out) + ((size_t)(n * Ho + yo) * Wo + xo) * p.out_ld + c0;
+            uint4 u0 = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
+                                  pack_half2(v[6], v[7]));
+            uint4 u1 = make_uint4(pack_half2(v[8], v[9]), pack_half2(v[10], v[11]), pack_half2(v[12], v[13]),
+                                  pack_half2(v[14], v[15]));
+            reinterpret_cast<uint4*>(o)[0] = u0;
+            reinterpret_cast<uint4*>(o)[1] = u1;
+        }
+    } else if (p.mode == EPI_F16_PS2) {
+        // out[2y+i][2x+j][c] = in[y][x][4c + 2i + j]  (torch.pixel_shuffle(2))
+        if (inb) {
+            const int Ho = p.H * 2, Wo = p.W * 2;
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int jj = 0; jj < 2; jj++) {
+                    const int o4 = 2 * i + jj;
+                    uint2 u = make_uint2(pack_half2(v[o4], v[4 + o4]), pack_half2(v[8 + o4], v[12 + o4]));
+                    __half* o = reinterpret_cast<__half*>(p.out) +
+                                ((size_t)(n * Ho + 2 * y + i) * Wo + 2 * x + jj) * p.out_ld + (c0 >> 2);
+                    *reinterpret_cast<uint2*>(o) = u;
+                }
+        }
+    } else {  // EPI_F32
+        if (inb) {
+            float* o = reinterpret_cast<float*>(p.out) + ((size_t)(n * p.H + y) * p.W + x) * p.out_ld + c0;
+#pragma unroll
+            for (int g = 0; g < 4; g++)
+                reinterpret_cast<float4*>(o)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
@@ -131,64 +196,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 uint32_t r[16];
                 ptx::tmem_ld16(taddr + c0, r);
                 ptx::tmem_ld_wait();
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    v[j] = __uint_as_float(r[j]) + sbias[c0 + j];
-                    if (p.relu) v[j] = fmaxf(v[j], 0.f);
-                }
-                if (p.mode == EPI_F16) {
-                    if (inb) {
-                        __half* o = reinterpret_cast<__half*>(p.out) +
-                                    ((size_t)(t.n * p.H + y) * p.W + x) * p.out_ld + c0;
-                        uint4 u0 = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
-                                              pack_half2(v[6], v[7]));
-                        uint4 u1 = make_uint4(pack_half2(v[8], v[9]), pack_half2(v[10], v[11]),
-                                              pack_half2(v[12], v[13]), pack_half2(v[14], v[15]));
-                        reinterpret_cast<uint4*>(o)[0] = u0;
-                        reinterpret_cast<uint4*>(o)[1] = u1;
-                    }
-                } else if (p.mode == EPI_F16_POOL) {
-#pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));   // x neighbour
-                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 16));  // y neighbour
-                    }
-                    const int Ho = p.H >> 1, Wo = p.W >> 1, yo = y >> 1, xo = x >> 1;
-                    if ((lane & 17) == 0 && yo < Ho && xo < Wo) {
-                        __half* o = reinterpret_cast<__half*>(p.out) +
-                                    ((size_t)(t.n * Ho + yo) * Wo + xo) * p.out_ld + c0;
-                        uint4 u0 = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
-                                              pack_half2(v[6], v[7]));
-                        uint4 u1 = make_uint4(pack_half2(v[8], v[9]), pack_half2(v[10], v[11]),
-                                              pack_half2(v[12], v[13]), pack_half2(v[14], v[15]));
-                        reinterpret_cast<uint4*>(o)[0] = u0;
-                        reinterpret_cast<uint4*>(o)[1] = u1;
-                    }
-                } else if (p.mode == EPI_F16_PS2) {
-                    // out[2y+i][2x+j][c] = in[y][x][4c + 2i + j]  (torch.pixel_shuffle(2))
-                    if (inb) {
-                        const int Ho = p.H * 2, Wo = p.W * 2;
-#pragma unroll
-                        for (int i = 0; i < 2; i++)
-#pragma unroll
-                            for (int jj = 0; jj < 2; jj++) {
-                                const int o4 = 2 * i + jj;
-                                uint2 u = make_uint2(pack_half2(v[o4], v[4 + o4]), pack_half2(v[8 + o4], v[12 + o4]));
-                                __half* o = reinterpret_cast<__half*>(p.out) +
-                                            ((size_t)(t.n * Ho + 2 * y + i) * Wo + 2 * x + jj) * p.out_ld + (c0 >> 2);
-                                *reinterpret_cast<uint2*>(o) = u;
-                            }
-                    }
-                } else {  // EPI_F32
-                    if (inb) {
-                        float* o = reinterpret_cast<float*>(p.out) +
-                                   ((size_t)(t.n * p.H + y) * p.W + x) * p.out_ld + c0;
-#pragma unroll
-                        for (int g = 0; g < 4; g++)
-                            reinterpret_cast<float4*>(o)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-                    }
-                }
+                epilogue_store<1, 16>(p, sbias, r, c0, t.n, y, x, inb, lane);
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -200,6 +208,151 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// v2 "halo" kernel for 3x3 convolutions with Cin = 64 (conv1b, conv2a/b, conv3a, edge block 1).
+// The generic kernel re-fetches the shifted A tile for each of the 9 taps (9 x 16 KB + 9 x N x 128 B per
+// tile through TMA); its ncu capture shows it bound by that traffic (tensor pipe 19 % active).  Here
+//   * all 9 weight taps stay resident in shared memory for the whole kernel (9 x N x 128 B),
+//   * one TMA box per tile brings the (8+2) x (16+2) pixel halo, one 128-byte swizzled row per pixel,
+//   * the A operand of tap (dy,dx) is a descriptor into that halo: start = pixel (dy+1, dx+1), rows of a
+//     group = 8 consecutive pixels in x, group stride (SBO) = one halo row.
+// Output tile = 8 (x) x 16 (y) pixels, TMEM lane = 8*y + x.
+struct Conv2Smem {
+    uint8_t* w;      // resident weights
+    uint8_t* halo;   // S stages
+    uint64_t *full, *empty, *tfull, *tempty, *wbar;
+    uint32_t* tmem_slot;
+    float* sbias;
+};
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const ConvTcParams p, const int halo_pitch, const int halo_stage_bytes, const int base_off_mode) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int S = p.stages;
+    const uint32_t w_bytes = 9u * (uint32_t)p.N * 128u;
+    uint8_t* sw = smem;
+    uint8_t* shalo = smem + w_bytes;  // w_bytes is a multiple of 1024 (N % 8 == 0)
+    uint64_t* full = reinterpret_cast<uint64_t*>(shalo + (size_t)S * halo_stage_bytes);
+    uint64_t* empty = full + 8;
+    uint64_t* tfull = empty + 8;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* wbar = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tmem_cols = p.N <= 64 ? 128u : 256u;  // two accumulators of N columns
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; i++) {
+            ptx::mbar_init(&full[i], 1);
+            ptx::mbar_init(&empty[i], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            ptx::mbar_init(&tfull[a], 1);
+            ptx::mbar_init(&tempty[a], 4);
+        }
+        ptx::mbar_init(wbar, 1);
+        ptx::fence_barrier_init();
+        ptx::prefetch_tmap(&mapA);
+        ptx::prefetch_tmap(&mapB);
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) sbias[i] = p.bias[i];
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t halo_bytes = (uint32_t)halo_pitch * (CONV2_TILE_H + 2) * 128u;
+
+    auto decode = [&](int tile, int& n, int& y0, int& x0) {
+        const int per = p.tiles_x * p.tiles_y;
+        n = tile / per;
+        const int r = tile - n * per, ty = r / p.tiles_x;
+        y0 = ty * CONV2_TILE_H;
+        x0 = (r - ty * p.tiles_x) * CONV2_TILE_W;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::mbar_expect_tx(wbar, w_bytes);
+            for (int tap = 0; tap < 9; tap++) ptx::tma_load_2d(sw + (size_t)tap * p.N * 128, &mapB, wbar, 0, tap * p.N);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+                int n, y0, x0;
+                decode(tile, n, y0, x0);
+                const uint32_t s = it % S, ph = (it / S) & 1;
+                ptx::mbar_wait(&empty[s], ph ^ 1);
+                ptx::mbar_expect_tx(&full[s], halo_bytes);
+                ptx::tma_load_4d(shalo + (size_t)s * halo_stage_bytes, &mapA, &full[s], 0, x0 - 1, y0 - 1, n);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::make_idesc_f16(128, p.N, 0);
+            ptx::mbar_wait(wbar, 0);
+            ptx::tc_fence_after();
+            const uint32_t w_addr = ptx::smem_u32(sw);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+                const uint32_t s = it % S, ph = (it / S) & 1;
+                ptx::mbar_wait(&tempty[acc], aph ^ 1);
+                ptx::mbar_wait(&full[s], ph);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.N;
+                const uint32_t h_addr = ptx::smem_u32(shalo + (size_t)s * halo_stage_bytes);
+#pragma unroll
+                for (int tap = 0; tap < 9; tap++) {
+                    const uint32_t a0 = h_addr + (uint32_t)((tap / 3) * halo_pitch + (tap % 3)) * 128u;
+                    const uint64_t adesc =
+                        ptx::make_sw128_desc_ex(a0, (uint32_t)halo_pitch * 128u, base_off_mode ? (a0 >> 7) & 7u : 0u);
+                    const uint64_t bdesc = ptx::make_sw128_desc(w_addr + (uint32_t)tap * p.N * 128u);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        ptx::umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((tap | k) != 0));
+                }
+                ptx::umma_commit(&empty[s]);
+                ptx::umma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane, h = row >> 3, w = row & 7;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+            const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+            int n, y0, x0;
+            decode(tile, n, y0, x0);
+            const int y = y0 + h, x = x0 + w;
+            const bool inb = (y < p.H) && (x < p.W);
+            ptx::mbar_wait(&tfull[acc], aph);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.N;
+            for (int c0 = 0; c0 < p.N; c0 += 16) {
+                uint32_t r[16];
+                ptx::tmem_ld16(taddr + c0, r);
+                ptx::tmem_ld_wait();
+                epilogue_store<1, 8>(p, sbias, r, c0, n, y, x, inb, lane);
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, tmem_cols);
     }
 }
 
@@ -216,25 +369,53 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
     p.N = cout_padded;
     p.mode = mode;
     p.relu = relu;
-    p.tiles_x = (W + CONV_TILE_W - 1) / CONV_TILE_W;
-    p.tiles_y = (H + CONV_TILE_H - 1) / CONV_TILE_H;
-    p.total_tiles = maxB * p.tiles_x * p.tiles_y;
     p.bias = bias;
     p.out = out;
     p.out_ld = out_ld;
+    L.cin = cin;
+    L.cout = cout_padded;
+    // PPG_CONV_V2=0 forces the generic kernel everywhere (A/B comparison); default = halo kernel where it applies.
+    // Measured on B200 (tools/conv_variants.py): UMMA applies the 128-byte swizzle XOR on absolute shared-memory
+    // address bits, so a descriptor may start at any 128-byte row of a swizzled tile with base_offset = 0.
+    int v2mode = 1;
+    if (const char* e = getenv("PPG_CONV_V2")) v2mode = atoi(e);
+    L.v2 = (v2mode != 0 && taps == 9 && cin == 64 && cout_padded <= 128) ? 1 : 0;
+    if (L.v2) {
+        L.halo_pitch = CONV2_TILE_W + 2;
+        L.base_off_mode = 0;
+        L.box_w = L.halo_pitch;
+        L.box_h = CONV2_TILE_H + 2;
+        p.tiles_x = (W + CONV2_TILE_W - 1) / CONV2_TILE_W;
+        p.tiles_y = (H + CONV2_TILE_H - 1) / CONV2_TILE_H;
+        p.total_tiles = maxB * p.tiles_x * p.tiles_y;
+        const int stage = (L.halo_pitch * L.box_h * 128 + 1023) / 1024 * 1024;
+        const int wbytes = 9 * cout_padded * 128;
+        int S = (222 * 1024 - wbytes - 4096) / stage;
+        if (S > 6) S = 6;
+        p.stages = S;
+        L.smem_bytes = wbytes + S * stage + 1024 + 21 * 8 + 16 + 256 * 4 + 64;
+        return;
+    }
+    L.halo_pitch = 0;
+    L.base_off_mode = 0;
+    L.box_w = CONV_TILE_W;
+    L.box_h = CONV_TILE_H;
+    p.tiles_x = (W + CONV_TILE_W - 1) / CONV_TILE_W;
+    p.tiles_y = (H + CONV_TILE_H - 1) / CONV_TILE_H;
+    p.total_tiles = maxB * p.tiles_x * p.tiles_y;
     const int stage_bytes = CONV_A_BYTES + cout_padded * 128;
     int S = (200 * 1024) / stage_bytes;
     if (S > 8) S = 8;
     p.stages = S;
     L.smem_bytes = S * stage_bytes + 1024 /*align*/ + 20 * 8 + 16 + 256 * 4 + 64;
-    L.cin = cin;
-    L.cout = cout_padded;
 }
 
 cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -243,7 +424,13 @@ cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStrea
     p.total_tiles = batch * p.tiles_x * p.tiles_y;
     int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     if (grid <= 0) return cudaSuccess;
-    conv_tc_kernel<<<grid, CONV_THREADS, L.smem_bytes, st>>>(L.mapA, L.mapB, p);
+    if (L.v2) {
+        const int stage = (L.halo_pitch * L.box_h * 128 + 1023) / 1024 * 1024;
+        conv_tc2_kernel<<<grid, CONV_THREADS, L.smem_bytes, st>>>(L.mapA, L.mapB, p, L.halo_pitch, stage,
+                                                                  L.base_off_mode);
+    } else {
+        conv_tc_kernel<<<grid, CONV_THREADS, L.smem_bytes, st>>>(L.mapA, L.mapB, p);
+    }
     return cudaGetLastError();
 }
 

@@ -44,9 +44,15 @@ struct ConvLayer {
     ConvTcParams p;
     int smem_bytes;
     int cin, cout;
+    // v2 ("halo") kernel: 3x3, Cin = 64, weights resident in shared memory, one TMA halo tile per output tile
+    int v2;             // 0 = generic kernel, 1 = halo kernel
+    int box_w, box_h;   // TMA box of the activation map (pixels): generic 16 x 8, halo (8+2 | 16) x 18
+    int halo_pitch;     // pixels per halo row in shared memory (= box_w)
+    int base_off_mode;  // 1: put (start >> 7) & 7 into the descriptor's base-offset field
 };
 
 constexpr int CONV_TILE_W = 16, CONV_TILE_H = 8, CONV_A_BYTES = 16384, CONV_THREADS = 192;
+constexpr int CONV2_TILE_W = 8, CONV2_TILE_H = 16;
 
 // Fills stages / tiles / smem size for the given shape. Tensor maps are encoded by the caller (api).
 void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded, int taps, int mode, int relu,

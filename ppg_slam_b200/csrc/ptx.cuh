@@ -136,6 +136,19 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                       // SWIZZLE_128B, bits [61,64)
     return d;
 }
+// Same, with an explicit stride between 8-row groups and an optional base offset (start address not on a
+// 1024-byte swizzle-pattern boundary): used by the halo-tile convolution whose operand rows are a shifted
+// window of a larger swizzled tile.
+__device__ __forceinline__ uint64_t make_sw128_desc_ex(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_off) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(base_off & 7) << 49;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // Instruction descriptor for kind::f16: fp16 A/B (format 0; bf16 = 1), fp32 accumulate, K-major A and B.
 __host__ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N, int bf16) {
     uint32_t d = 0;

@@ -107,3 +107,19 @@ def test_assoc_on_extracted_frame():
         np.testing.assert_array_equal(got["accept"], ref["accept"])
     finally:
         e.close()
+
+
+def test_sharded_association_nccl_two_gpus():
+    """Row-sharded table over 2 GPUs + NCCL all-gather of the top-2 records == un-sharded oracle."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "sharded_assoc_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"parity_vs_oracle": true' in r.stdout

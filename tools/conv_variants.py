@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Tries the halo-convolution descriptor variants (PPG_CONV_V2=0..4) and reports self-test errors + timings."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ppg_slam_b200 import cameras, capi, synth  # noqa: E402
+
+cam = cameras.EUROC
+B = 32
+frames = [synth.frame(s, cam.width, cam.height) for s in range(B)]
+out = {}
+for v in sys.argv[1:] or ["0", "1", "2", "3", "4"]:
+    os.environ["PPG_CONV_V2"] = v
+    try:
+        e = capi.Extractor(cam, max_batch=B)
+        e.upload(frames)
+        e.run_device(B)
+        e.sync()
+        st = e.selftest_conv()
+        e.set_profiling(True)
+        e.run_device(B)
+        times = dict(e.stage_times())
+        e.set_profiling(False)
+        e.timer_start()
+        for _ in range(5):
+            e.run_device(B)
+        ms = e.timer_stop() / 5
+        out[v] = dict(selftest={n: d for n, d, r in st}, ms=ms, fps=B / ms * 1e3,
+                      conv={k: round(t, 4) for k, t in times.items() if k.startswith(("conv", "edge"))})
+        e.close()
+    except Exception as ex:  # noqa: BLE001
+        out[v] = dict(error=str(ex))
+    print(v, json.dumps(out[v]), flush=True)
