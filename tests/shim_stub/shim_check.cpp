@@ -1,0 +1,12 @@
+#define PPG_SHIM_NO_REFERENCE_HEADERS
+#include "stub_types.h"
+#include "ppg_shim.hpp"
+int shim_instantiate(GeometricCamera* cam, Frame& F, std::vector<MapPoint*>& mps) {
+    ppg_shim::PPGExtractor ex(cam, "net");
+    std::vector<KeyPointEx> a, b;
+    std::vector<KeyEdge> e;
+    cv::Mat d;
+    ex.run(cv::Mat(), a, b, e, d);
+    ppg_shim::upload_map_descriptors(ex.context(), mps);
+    return (int)ppg_shim::search_local_points(ex.context(), F, mps, 10.f, 0.8f).accept.size();
+}

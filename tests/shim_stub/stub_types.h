@@ -1,0 +1,61 @@
+// Minimal stand-ins for the reference / OpenCV / Eigen types the shim touches, ONLY so that
+// tests/test_shim_compiles.py can syntax-check include/ppg_shim.hpp in a container without those libraries.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <utility>
+#include <vector>
+#define CV_32FC1 5
+namespace cv {
+struct Mat {
+    int rows = 0, cols = 0;
+    unsigned char* data = nullptr;
+    size_t step = 0;
+    Mat() {}
+    Mat(int r, int c, int) : rows(r), cols(c) {}
+    int channels() const { return 1; }
+    template <typename T> T& at(int, int = 0) { static T t; return t; }
+    template <typename T> T* ptr(int = 0) { return nullptr; }
+    template <typename T> const T* ptr(int = 0) const { return nullptr; }
+};
+}  // namespace cv
+struct Vec2f {
+    float v[2];
+    float& operator[](int i) { return v[i]; }
+    struct Init { Vec2f* p; int k; Init operator,(float x) { p->v[k] = x; return Init{p, k + 1}; } };
+    Init operator<<(float x) { v[0] = x; return Init{this, 1}; }
+};
+struct KeyPointEx {
+    KeyPointEx() {}
+    KeyPointEx(float x, float y, float sc) : mfScore(sc), mbOut(true) { mPos.v[0] = x; mPos.v[1] = y; }
+    Vec2f mPos, mPosUn;
+    float mfScore;
+    std::vector<unsigned int> mvConnected;
+    std::vector<std::pair<unsigned int, unsigned int>> mvColine;
+    bool mbOut;
+};
+struct KeyEdge {
+    KeyEdge() {}
+    KeyEdge(const unsigned int& a, const unsigned int& b) : startIdx(a), endIdx(b) {}
+    unsigned int startIdx, endIdx;
+    bool isBad;
+    float lscore, length;
+};
+struct GeometricCamera {
+    static const unsigned int CAM_PINHOLE = 0, CAM_FISHEYE = 1;
+    virtual cv::Mat toK() = 0;
+    virtual cv::Mat toD() = 0;
+    virtual int imWidth() = 0;
+    virtual int imHeight() = 0;
+    unsigned int mnType;
+};
+struct MapPoint {
+    float mTrackProjX, mTrackProjY, mTrackViewCos;
+    int Observations() { return 0; }
+    cv::Mat GetDescriptor() { return cv::Mat(); }
+};
+struct Frame {
+    std::vector<KeyPointEx> mvKeysUn;
+    std::vector<MapPoint*> mvpMapPoints;
+    cv::Mat mDescriptors;
+};
