@@ -10,7 +10,7 @@ One step = one batch of 32 synthetic EuRoC-shaped frames per GPU through the who
 networks (tcgen05 convolutions) -> keypoints -> point-pair graph -> descriptors -> association of every
 frame against a resident table of M map-point descriptors (search core of ExtendMapMatches).
 `value` times the device work with the frames already in HBM; `e2e` goes through the host-facing calls
-(ppg_extract with HOST frames, per-frame ppg_assoc_stage / run / fetch) including all copies.
+(ppg_extract with HOST frames, ppg_assoc_stage_batch / run_batch / fetch_batch) including all copies.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -194,24 +194,24 @@ def run_b200(args, rank, local_rank, world):
     e.upload_map(map_desc)
     empty = (np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros((0, 256), np.float32), np.zeros(0, np.uint8))
 
+    proj_all = np.stack([uv for uv, _ in per_frame])
+    vcos_all = np.stack([vc for _, vc in per_frame])
+
     def device_step():
         e.run_device(B)
-        for f in range(B):
-            e.assoc_run_frame(f)
+        e.assoc_run_batch(B)
 
     def e2e_step():
         rc = e.lib.ppg_extract(e.h, fptrs, fstrides, B, e._outs)
         if rc not in (0, capi.PPG_ERR_CAPACITY):
             raise capi.PpgError(rc, e.lib.ppg_last_error(e.h).decode())
-        for f in range(B):
-            uv, vc = per_frame[f]
-            e.assoc_stage(*empty, uv, vc, TH, RATIO)
-            e.assoc_run_frame(f)
-            e.assoc_fetch()
+        e.assoc_stage_batch(proj_all, vcos_all, TH, RATIO)
+        e.assoc_run_batch(B)
+        e.assoc_fetch_batch(B)
 
     # ---- device-timed arm: frames resident in HBM
     e.upload(frames)
-    e.assoc_stage(*empty, per_frame[0][0], per_frame[0][1], TH, RATIO)
+    e.assoc_stage_batch(proj_all, vcos_all, TH, RATIO)
     e.set_profiling(True)
     clocks = ClockSampler(local_rank)
     t_w = time.perf_counter()

@@ -189,6 +189,13 @@ int ppg_assoc_fetch(ppg_ctx* ctx, ppg_assoc_out* out);
 /* Associates frame `frame` of the last extraction batch (descriptors and keypoints still on the
  * device) against the staged projections -- the extract+associate step of the benchmark. */
 int ppg_assoc_run_frame(ppg_ctx* ctx, int frame);
+/* Throughput form of the same step: every frame of the last extraction batch against the resident table in
+ * ONE set of launches.  proj_uv is n_frames x n_rows x 2, view_cos n_frames x n_rows (host, each frame has its
+ * own projections of the same map points); results come back per frame through outs[0..n_frames). */
+int ppg_assoc_stage_batch(ppg_ctx* ctx, int n_frames, int n_rows, const float* proj_uv, const float* view_cos, float th,
+                          float ratio);
+int ppg_assoc_run_batch(ppg_ctx* ctx, int n_frames);
+int ppg_assoc_fetch_batch(ppg_ctx* ctx, int n_frames, ppg_assoc_out* outs);
 /* Rows whose tensor-core candidate filter could not guarantee the exact top-2 and were re-scored
  * over the whole window (diagnostic). */
 int ppg_assoc_fallback_rows(ppg_ctx* ctx, int* n);

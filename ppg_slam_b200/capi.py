@@ -63,7 +63,8 @@ SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", 
            "ppg_upload_frames", "ppg_run", "ppg_download", "ppg_sync", "ppg_extract_from_maps", "ppg_get_maps",
            "ppg_selftest_conv", "ppg_set_profiling", "ppg_get_stage_times", "ppg_launch_count", "ppg_timer_start",
            "ppg_timer_stop", "ppg_upload_map", "ppg_associate", "ppg_assoc_stage", "ppg_assoc_run",
-           "ppg_assoc_fetch", "ppg_assoc_run_frame", "ppg_assoc_fallback_rows", "ppg_assoc_device_results",
+           "ppg_assoc_fetch", "ppg_assoc_run_frame", "ppg_assoc_stage_batch", "ppg_assoc_run_batch",
+           "ppg_assoc_fetch_batch", "ppg_assoc_fallback_rows", "ppg_assoc_device_results",
            "ppg_stream"]
 
 _lib = None
@@ -86,8 +87,10 @@ def load():
         for name in ["ppg_extract", "ppg_upload_frames", "ppg_run", "ppg_download", "ppg_sync",
                      "ppg_extract_from_maps", "ppg_get_maps", "ppg_selftest_conv", "ppg_set_profiling",
                      "ppg_get_stage_times", "ppg_timer_start", "ppg_timer_stop", "ppg_upload_map", "ppg_associate",
-                     "ppg_assoc_stage", "ppg_assoc_run", "ppg_assoc_fetch", "ppg_assoc_run_frame",
-                     "ppg_assoc_fallback_rows", "ppg_assoc_device_results"]:
+                     "ppg_assoc_stage", "ppg_assoc_run", "ppg_assoc_fetch", "ppg_assoc_run_frame", "ppg_assoc_stage_batch", "ppg_assoc_run_batch",
+           "ppg_assoc_fetch_batch",
+                     "ppg_assoc_fallback_rows", "ppg_assoc_device_results", "ppg_assoc_stage_batch",
+                     "ppg_assoc_run_batch", "ppg_assoc_fetch_batch"]:
             getattr(lib, name).restype = C.c_int
         _lib = lib
     return _lib
@@ -292,6 +295,31 @@ class Extractor:
 
     def assoc_run_frame(self, frame):
         self._check(self.lib.ppg_assoc_run_frame(self.h, frame))
+
+    def assoc_stage_batch(self, proj_uv, view_cos, th, ratio):
+        """proj_uv (F, M, 2), view_cos (F, M): per-frame projections of the resident map points."""
+        uv = np.ascontiguousarray(proj_uv, np.float32)
+        vc = np.ascontiguousarray(view_cos, np.float32)
+        F, M = vc.shape
+        self._check(self.lib.ppg_assoc_stage_batch(self.h, F, M, _fp(uv), _fp(vc), C.c_float(th), C.c_float(ratio)))
+        self._assoc_rows, self._assoc_frames = M, F
+        self._batch_out = None
+
+    def assoc_run_batch(self, n_frames):
+        self._check(self.lib.ppg_assoc_run_batch(self.h, n_frames))
+
+    def assoc_fetch_batch(self, n_frames):
+        if getattr(self, "_batch_out", None) is None or len(self._batch_out[1]) != n_frames:
+            outs = (AssocOut * n_frames)()
+            res = []
+            for f in range(n_frames):
+                o, r = self._assoc_out(self._assoc_rows)
+                outs[f] = o
+                res.append(r)
+            self._batch_out = (outs, res)
+        outs, res = self._batch_out
+        self._check(self.lib.ppg_assoc_fetch_batch(self.h, n_frames, outs))
+        return res
 
     def assoc_fetch(self):
         o, r = self._assoc_out(self._assoc_rows)

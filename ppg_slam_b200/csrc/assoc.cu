@@ -32,48 +32,58 @@ struct RowParam {  // per map point
     uint32_t cells;  // minCx | maxCx << 8 | minCy << 16 | maxCy << 24 ; 0xffffffff = empty window
 };
 
+// Where the keypoints / descriptors of frame f live: staged arrays (one frame) or the extraction output blocks
+// of the last batch (byte stride = one output block).
+struct FrameSrc {
+    const uint8_t *kx, *ky, *desc, *free_mask, *n;
+    size_t stride, free_stride;
+    int n_val;  // used when n == nullptr
+    __host__ __device__ const float* kx_of(int f) const { return reinterpret_cast<const float*>(kx + f * stride); }
+    __host__ __device__ const float* ky_of(int f) const { return reinterpret_cast<const float*>(ky + f * stride); }
+    __host__ __device__ const float* desc_of(int f) const { return reinterpret_cast<const float*>(desc + f * stride); }
+    __host__ __device__ const uint8_t* free_of(int f) const { return free_mask + f * free_stride; }
+    __device__ int n_of(int f) const { return n ? *reinterpret_cast<const int*>(n + f * stride) : n_val; }
+};
+
 struct AssocState {
-    int max_rows = 0, n_rows = 0, ncap = 0;  // ncap: keypoint capacity (multiple of 128)
-    // map side
+    int max_rows = 0, n_rows = 0, ncap = 0;  // ncap: keypoint capacity per frame (multiple of 128)
+    int bcap = 1;                            // frames per batched call
+    // map side (shared by all frames)
     float* map_f32 = nullptr;
     __nv_bfloat16* map_bf = nullptr;
     float* map_n2 = nullptr;
     CUtensorMap mapA, mapB;
-    // frame side (staged or taken from the extraction output block)
-    float *kx = nullptr, *ky = nullptr, *fdesc = nullptr, *fn2 = nullptr;
+    // frame side: staged single frame, or the extraction output blocks of the last batch
+    float *kx = nullptr, *ky = nullptr, *fdesc = nullptr;
     uint8_t *free_mask = nullptr, *ones = nullptr;
-    __nv_bfloat16* f_bf = nullptr;
-    uint32_t* kinfo = nullptr;  // cx | cy << 8 | ok << 16
-    uint32_t* korder = nullptr; // (cx*48+cy) << 16 | i  : GetFeaturesInArea visiting order
-    int* d_nkp = nullptr;       // staged N on the device
-    float* nbmax = nullptr;     // max squared norm of the frame descriptors (as float bits, atomicMax)
+    float* fn2 = nullptr;            // [bcap][ncap]
+    __nv_bfloat16* f_bf = nullptr;   // [bcap][ncap][256]
+    uint32_t* kinfo = nullptr;       // [bcap][ncap]  cx | cy << 8 | ok << 16
+    uint32_t* korder = nullptr;      // [bcap][ncap]  (cx*48+cy) << 16 | i : GetFeaturesInArea visiting order
+    float* nbmax = nullptr;          // [bcap] max squared norm of the frame descriptors (float bits, atomicMax)
     int staged_n = 0;
-    // row side
+    // row side, [bcap][max_rows]
     float *proj = nullptr, *vcos = nullptr;
     RowParam* rowp = nullptr;
     float th = 0.f, ratio = 0.f;
-    int staged_rows = 0;
-    // results
-    int* cand = nullptr;  // [rows][4]
+    int staged_rows = 0, staged_frames = 0;
+    // results, [bcap][max_rows]
+    int* cand = nullptr;  // x4
     float* guard = nullptr;
     int *best_idx = nullptr, *second_idx = nullptr;
     float *best_d = nullptr, *second_d = nullptr;
     uint8_t* accept = nullptr;
     int* fallback = nullptr;
-    // pinned host staging for fetch
-    uint8_t* h_res = nullptr;
+    uint8_t* h_res = nullptr;  // pinned staging for fetch
+    size_t h_res_bytes = 0;
 };
 
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) prep_desc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                        float* __restrict__ n2, const int* n_ptr, int n_val,
-                                                        int rows_padded, float* nbmax) {
-    // one warp per row; rows >= n are zero-filled (so that padded GEMM columns are inert)
-    const int n = n_ptr ? *n_ptr : n_val;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= rows_padded) return;
+// fp32 -> bf16 + squared norm, one warp per row.  Rows >= n are zero-filled (inert GEMM columns).
+__device__ __forceinline__ void prep_row(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                         float* __restrict__ n2, int row, int n, int lane, float* nbmax) {
     float v[8];
     if (row < n) {
         const float4 a = *reinterpret_cast<const float4*>(src + (size_t)row * 256 + lane * 8);
@@ -99,44 +109,59 @@ __global__ void __launch_bounds__(256) prep_desc_kernel(const float* __restrict_
     }
 }
 
+__global__ void __launch_bounds__(256) prep_map_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                       float* __restrict__ n2, int n, int rows_padded) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows_padded) return;
+    prep_row(src, dst, n2, row, n, threadIdx.x & 31, nullptr);
+}
+
 struct GridParam {
     int minX, minY;
     float wInv, hInv;
 };
 
-// Frame::PosInGrid (Frame.cpp:317-327) for every keypoint + the free mask (Matcher.cpp:253).
-__global__ void prep_kp_kernel(const float* __restrict__ kx, const float* __restrict__ ky,
-                               const uint8_t* __restrict__ free_mask, const int* n_ptr, int n_val, int ncap,
-                               GridParam g, uint32_t* __restrict__ kinfo, uint32_t* __restrict__ korder) {
-    const int n = n_ptr ? *n_ptr : n_val;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ncap) return;
-    uint32_t info = 0, order = 0xffffffffu;
-    if (i < n) {
-        const int px = (int)roundf((kx[i] - (float)g.minX) * g.wInv);
-        const int py = (int)roundf((ky[i] - (float)g.minY) * g.hInv);
-        const bool indexable = !(px < 0 || px >= 64 || py < 0 || py >= 48);
-        if (indexable) {
-            info = (uint32_t)px | ((uint32_t)py << 8) | ((free_mask[i] ? 1u : 0u) << 16);
-            order = ((uint32_t)(px * 48 + py) << 16) | (uint32_t)i;
+// Frame side of one call, grid (ncap/8, frames): descriptors -> bf16 + norms; Frame::PosInGrid
+// (Frame.cpp:317-327) of every keypoint + the free mask (Matcher.cpp:253).
+__global__ void __launch_bounds__(256) prep_frame_kernel(const FrameSrc src, int ncap, GridParam g,
+                                                         __nv_bfloat16* __restrict__ f_bf, float* __restrict__ fn2,
+                                                         uint32_t* __restrict__ kinfo, uint32_t* __restrict__ korder,
+                                                         float* __restrict__ nbmax) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int n = min(src.n_of(f), ncap);
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= ncap) return;
+    prep_row(src.desc_of(f), f_bf + (size_t)f * ncap * 256, fn2 + (size_t)f * ncap, row, n, lane, nbmax + f);
+    if (lane == 0) {
+        uint32_t info = 0, order = 0xffffffffu;
+        if (row < n) {
+            const float x = src.kx_of(f)[row], y = src.ky_of(f)[row];
+            const int px = (int)roundf((x - (float)g.minX) * g.wInv);
+            const int py = (int)roundf((y - (float)g.minY) * g.hInv);
+            const bool indexable = !(px < 0 || px >= 64 || py < 0 || py >= 48);
+            if (indexable) {
+                info = (uint32_t)px | ((uint32_t)py << 8) | ((src.free_of(f)[row] ? 1u : 0u) << 16);
+                order = ((uint32_t)(px * 48 + py) << 16) | (uint32_t)row;
+            }
         }
+        kinfo[(size_t)f * ncap + row] = info;
+        korder[(size_t)f * ncap + row] = order;
     }
-    kinfo[i] = info;
-    korder[i] = order;
 }
 
 // Search window of each map point: r (Matcher.cpp:240-244) and the cell range of GetFeaturesInArea
-// (Frame.cpp:270-292) including its early returns.
+// (Frame.cpp:270-292) including its early returns.  grid (rows/256, frames).
 __global__ void prep_rows_kernel(const float* __restrict__ proj, const float* __restrict__ vcos,
-                                 const float* __restrict__ n2, int rows, float th, GridParam g,
+                                 const float* __restrict__ n2, int rows, int max_rows, float th, GridParam g,
                                  RowParam* __restrict__ rp) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
     if (m >= rows) return;
+    const size_t o = (size_t)f * max_rows + m;
     RowParam p;
-    p.u = proj[2 * m];
-    p.v = proj[2 * m + 1];
+    p.u = proj[2 * o];
+    p.v = proj[2 * o + 1];
     float r = th;
-    if ((double)vcos[m] > 0.998)
+    if ((double)vcos[o] > 0.998)
         r = (float)((double)r * 2.5);
     else
         r = (float)((double)r * 4.0);
@@ -156,7 +181,7 @@ __global__ void prep_rows_kernel(const float* __restrict__ proj, const float* __
     if (y1 > 47) y1 = 47;
     if (y1 < 0) empty = true;
     p.cells = empty ? 0xffffffffu : ((uint32_t)x0 | ((uint32_t)x1 << 8) | ((uint32_t)y0 << 16) | ((uint32_t)y1 << 24));
-    rp[m] = p;
+    rp[o] = p;
 }
 
 __device__ __forceinline__ bool in_window(const RowParam& p, uint32_t info, float x, float y) {
@@ -171,18 +196,19 @@ __device__ __forceinline__ bool in_window(const RowParam& p, uint32_t info, floa
 // K14b.  GEMM view: D[map row, keypoint] = <a, b>.  M tile = 128 map rows (TMEM lanes), N tile = 128
 // keypoints, K = 256 = 4 chunks of 64 bf16 (one 128-byte swizzled smem row per descriptor per chunk).
 // warp 0: TMA producer, warp 1: MMA issuer / TMEM owner, warps 2-5: epilogue (one map row per thread).
+// Work items = (frame, M tile); each CTA takes a contiguous range so that the per-frame keypoint table in
+// shared memory is reloaded only when the frame changes.
 struct GemmParams {
-    int rows, n_tiles_n;
-    const int* n_ptr;
-    int n_val;
+    int rows, max_rows, ncap, frames;
+    FrameSrc src;
     const RowParam* rowp;
-    const float* kx;
-    const float* ky;
     const float* fn2;
     const uint32_t* kinfo;
     int* cand;
     float* guard;
 };
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 __global__ void __launch_bounds__(A_THREADS, 1)
 assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -194,12 +220,13 @@ assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     uint64_t* tfull = empty + 8;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float4* kp = reinterpret_cast<float4*>(tmem_slot + 4);  // [ncols] x, y, n2, info(bits)
+    float4* kp = reinterpret_cast<float4*>(tmem_slot + 4);  // [ncap] x, y, n2, info(bits) of the current frame
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = p.n_ptr ? *p.n_ptr : p.n_val;
-    const int ncols = p.n_tiles_n * A_BN;
     const int m_tiles = (p.rows + A_BM - 1) / A_BM;
+    const int total = m_tiles * p.frames;
+    const int per = (total + gridDim.x - 1) / gridDim.x;
+    const int t0 = blockIdx.x * per, t1 = min(total, t0 + per);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < A_STAGES; i++) {
@@ -218,37 +245,36 @@ assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         ptx::tmem_alloc(tmem_slot, 256);
         ptx::tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < n) v = make_float4(p.kx[i], p.ky[i], p.fn2[i], __uint_as_float(p.kinfo[i]));
-        kp[i] = v;
-    }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int used_tiles_n = (n + A_BN - 1) / A_BN;  // keypoint tiles that hold at least one keypoint
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
-            for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
-                for (int nt = 0; nt < used_tiles_n; nt++)
+            for (int t = t0; t < t1; t++) {
+                const int f = t / m_tiles, mt = t - f * m_tiles;
+                const int n_tiles = (min(p.src.n_of(f), p.ncap) + A_BN - 1) / A_BN;
+                for (int nt = 0; nt < n_tiles; nt++)
                     for (int kc = 0; kc < 4; kc++, it++) {
                         const uint32_t s = it % A_STAGES, ph = (it / A_STAGES) & 1;
                         ptx::mbar_wait(&empty[s], ph ^ 1);
                         ptx::mbar_expect_tx(&full[s], A_STAGE_BYTES);
                         uint8_t* a = smem + (size_t)s * A_STAGE_BYTES;
                         ptx::tma_load_2d(a, &mapA, &full[s], kc * 64, mt * A_BM);
-                        ptx::tma_load_2d(a + 16384, &mapB, &full[s], kc * 64, nt * A_BN);
+                        ptx::tma_load_2d(a + 16384, &mapB, &full[s], kc * 64, f * p.ncap + nt * A_BN);
                     }
+            }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = ptx::make_idesc_f16(A_BM, A_BN, 1);
             uint32_t it = 0, lt = 0;
-            for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
-                for (int nt = 0; nt < used_tiles_n; nt++, lt++) {
+            for (int t = t0; t < t1; t++) {
+                const int f = t / m_tiles;
+                const int n_tiles = (min(p.src.n_of(f), p.ncap) + A_BN - 1) / A_BN;
+                for (int nt = 0; nt < n_tiles; nt++, lt++) {
                     const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
                     ptx::mbar_wait(&tempty[acc], aph ^ 1);
                     ptx::tc_fence_after();
@@ -267,17 +293,37 @@ assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     }
                     ptx::umma_commit(&tfull[acc]);
                 }
+            }
         }
     } else {
         const int q = warp & 3;
-        const int rloc = q * 32 + lane;
+        const int rloc = q * 32 + lane, etid = threadIdx.x - 64;
         uint32_t lt = 0;
-        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+        int cur_f = -1, n = 0;
+        for (int t = t0; t < t1; t++) {
+            const int f = t / m_tiles, mt = t - f * m_tiles;
+            if (f != cur_f) {  // (re)load the frame's keypoint table; all four epilogue warps take this branch together
+                epi_bar();
+                n = min(p.src.n_of(f), p.ncap);
+                const float* kx = p.src.kx_of(f);
+                const float* ky = p.src.ky_of(f);
+                const int ncols = (n + A_BN - 1) / A_BN * A_BN;
+                for (int i = etid; i < ncols; i += 128) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < n)
+                        v = make_float4(kx[i], ky[i], p.fn2[(size_t)f * p.ncap + i],
+                                        __uint_as_float(p.kinfo[(size_t)f * p.ncap + i]));
+                    kp[i] = v;
+                }
+                epi_bar();
+                cur_f = f;
+            }
+            const int n_tiles = (n + A_BN - 1) / A_BN;
             const int row = mt * A_BM + rloc;
             RowParam rp;
             rp.u = rp.v = rp.r = rp.na2 = 0.f;
             rp.cells = 0xffffffffu;
-            if (row < p.rows) rp = p.rowp[row];
+            if (row < p.rows) rp = p.rowp[(size_t)f * p.max_rows + row];
             float bd[A_TOPK];
             int bi[A_TOPK];
 #pragma unroll
@@ -286,7 +332,7 @@ assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 bi[k] = -1;
             }
             float a5 = INFINITY;
-            for (int nt = 0; nt < used_tiles_n; nt++, lt++) {
+            for (int nt = 0; nt < n_tiles; nt++, lt++) {
                 const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
                 ptx::mbar_wait(&tfull[acc], aph);
                 ptx::tc_fence_after();
@@ -326,8 +372,9 @@ assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
             }
             if (row < p.rows) {
-                *reinterpret_cast<int4*>(p.cand + (size_t)row * 4) = make_int4(bi[0], bi[1], bi[2], bi[3]);
-                p.guard[row] = a5;
+                const size_t o = (size_t)f * p.max_rows + row;
+                *reinterpret_cast<int4*>(p.cand + o * 4) = make_int4(bi[0], bi[1], bi[2], bi[3]);
+                p.guard[o] = a5;
             }
         }
     }
@@ -355,14 +402,10 @@ __device__ __forceinline__ float exact_distance(const float* __restrict__ a, con
 }
 
 struct RescoreParams {
-    int rows;
-    const int* n_ptr;
-    int n_val;
+    int rows, max_rows, ncap;
+    FrameSrc src;
     const RowParam* rowp;
     const float* map_f32;
-    const float* fdesc;
-    const float* kx;
-    const float* ky;
     const uint32_t* kinfo;
     const uint32_t* korder;
     const int* cand;
@@ -390,27 +433,31 @@ __device__ __forceinline__ void top2_update(float d, uint32_t ord, int idx, floa
 
 __global__ void __launch_bounds__(256) assoc_rescore_kernel(const RescoreParams p) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int f = blockIdx.y;
     if (row >= p.rows) return;
-    const int n = p.n_ptr ? *p.n_ptr : p.n_val;
-    const RowParam rp = p.rowp[row];
+    const size_t o = (size_t)f * p.max_rows + row;
+    const int n = min(p.src.n_of(f), p.ncap);
+    const RowParam rp = p.rowp[o];
     const float* a = p.map_f32 + (size_t)row * 256;
+    const float* fdesc = p.src.desc_of(f);
+    const uint32_t* korder = p.korder + (size_t)f * p.ncap;
     float b1 = 1e6f, b2 = 1e6f;  // Matcher.cpp:248-249 initial values
     uint32_t o1 = 0xffffffffu, o2 = 0xffffffffu;
     int i1 = -1, i2 = -1;
     bool exact_all = p.force_exact != 0;
     if (!exact_all) {
-        const int4 c4 = *reinterpret_cast<const int4*>(p.cand + (size_t)row * 4);
+        const int4 c4 = *reinterpret_cast<const int4*>(p.cand + o * 4);
         const int cs[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             if (cs[k] < 0) continue;
-            const float d = exact_distance(a, p.fdesc + (size_t)cs[k] * 256, lane);
-            top2_update(d, p.korder[cs[k]], cs[k], b1, o1, i1, b2, o2, i2);
+            const float d = exact_distance(a, fdesc + (size_t)cs[k] * 256, lane);
+            top2_update(d, korder[cs[k]], cs[k], b1, o1, i1, b2, o2, i2);
         }
-        const float g = p.guard[row];
+        const float g = p.guard[o];
         if (g < INFINITY) {
             // bf16 operands: |dot_bf16 - dot| <= (2^-8 + 2^-16) |a||b| (+ fp32 accumulation); in squared distance x2
-            const float delta = 0.0080f * sqrtf(rp.na2 * (*p.nbmax)) + 2e-4f;
+            const float delta = 0.0080f * sqrtf(rp.na2 * p.nbmax[f]) + 2e-4f;
             const float e2 = b2 * b2;
             if (!(g - delta > e2 + delta)) exact_all = true;
         }
@@ -420,27 +467,30 @@ __global__ void __launch_bounds__(256) assoc_rescore_kernel(const RescoreParams 
         b1 = b2 = 1e6f;
         o1 = o2 = 0xffffffffu;
         i1 = i2 = -1;
+        const float* kx = p.src.kx_of(f);
+        const float* ky = p.src.ky_of(f);
+        const uint32_t* kinfo = p.kinfo + (size_t)f * p.ncap;
         for (int c0 = 0; c0 < n; c0 += 32) {
             const int c = c0 + lane;
             bool in = false;
-            if (c < n) in = in_window(rp, p.kinfo[c], p.kx[c], p.ky[c]);
+            if (c < n) in = in_window(rp, kinfo[c], kx[c], ky[c]);
             unsigned mask = __ballot_sync(AFULL, in);
             while (mask) {
                 const int cc = c0 + __ffs(mask) - 1;
                 mask &= mask - 1;
-                const float d = exact_distance(a, p.fdesc + (size_t)cc * 256, lane);
-                top2_update(d, p.korder[cc], cc, b1, o1, i1, b2, o2, i2);
+                const float d = exact_distance(a, fdesc + (size_t)cc * 256, lane);
+                top2_update(d, korder[cc], cc, b1, o1, i1, b2, o2, i2);
             }
         }
     }
     if (lane == 0) {
-        p.best_idx[row] = i1;
-        p.second_idx[row] = i2;
-        p.best_d[row] = b1;
-        p.second_d[row] = b2;
+        p.best_idx[o] = i1;
+        p.second_idx[o] = i2;
+        p.best_d[o] = b1;
+        p.second_d[o] = b2;
         uint8_t acc = 0;
         if (i1 >= 0) acc = !(b1 > p.th_high && b1 > p.ratio * b2);  // Matcher.cpp:276
-        p.accept[row] = acc;
+        p.accept[o] = acc;
     }
 }
 
@@ -449,90 +499,118 @@ cudaError_t dalloc(T** p, size_t count) {
     return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
 }
 
+int gemm_smem(const AssocState* s) { return A_STAGES * A_STAGE_BYTES + 1024 + 20 * 8 + 16 + s->ncap * 16 + 64; }
+
 int ensure_state(ppg_ctx* c) {
     if (c->assoc) return PPG_OK;
     AssocState* s = new AssocState();
     c->assoc = s;
     s->max_rows = c->cfg.max_map_points > 0 ? c->cfg.max_map_points : 65536;
     s->ncap = 1024;
-    const size_t R = s->max_rows, N = s->ncap;
+    s->bcap = c->maxB;
+    const size_t R = s->max_rows, N = s->ncap, B = s->bcap;
     PPG_CUDA(c, dalloc(&s->map_f32, R * 256));
     PPG_CUDA(c, dalloc(&s->map_bf, R * 256));
     PPG_CUDA(c, dalloc(&s->map_n2, R));
     PPG_CUDA(c, dalloc(&s->kx, N));
     PPG_CUDA(c, dalloc(&s->ky, N));
     PPG_CUDA(c, dalloc(&s->fdesc, N * 256));
-    PPG_CUDA(c, dalloc(&s->fn2, N));
     PPG_CUDA(c, dalloc(&s->free_mask, N));
     PPG_CUDA(c, dalloc(&s->ones, N));
     PPG_CUDA(c, cudaMemset(s->ones, 1, N));
-    PPG_CUDA(c, dalloc(&s->f_bf, N * 256));
-    PPG_CUDA(c, dalloc(&s->kinfo, N));
-    PPG_CUDA(c, dalloc(&s->korder, N));
-    PPG_CUDA(c, dalloc(&s->d_nkp, 1));
-    PPG_CUDA(c, dalloc(&s->nbmax, 1));
-    PPG_CUDA(c, dalloc(&s->proj, R * 2));
-    PPG_CUDA(c, dalloc(&s->vcos, R));
-    PPG_CUDA(c, dalloc(&s->rowp, R));
-    PPG_CUDA(c, dalloc(&s->cand, R * 4));
-    PPG_CUDA(c, dalloc(&s->guard, R));
-    PPG_CUDA(c, dalloc(&s->best_idx, R));
-    PPG_CUDA(c, dalloc(&s->second_idx, R));
-    PPG_CUDA(c, dalloc(&s->best_d, R));
-    PPG_CUDA(c, dalloc(&s->second_d, R));
-    PPG_CUDA(c, dalloc(&s->accept, R));
+    PPG_CUDA(c, dalloc(&s->fn2, B * N));
+    PPG_CUDA(c, dalloc(&s->f_bf, B * N * 256));
+    PPG_CUDA(c, dalloc(&s->kinfo, B * N));
+    PPG_CUDA(c, dalloc(&s->korder, B * N));
+    PPG_CUDA(c, dalloc(&s->nbmax, B));
+    PPG_CUDA(c, dalloc(&s->proj, B * R * 2));
+    PPG_CUDA(c, dalloc(&s->vcos, B * R));
+    PPG_CUDA(c, dalloc(&s->rowp, B * R));
+    PPG_CUDA(c, dalloc(&s->cand, B * R * 4));
+    PPG_CUDA(c, dalloc(&s->guard, B * R));
+    PPG_CUDA(c, dalloc(&s->best_idx, B * R));
+    PPG_CUDA(c, dalloc(&s->second_idx, B * R));
+    PPG_CUDA(c, dalloc(&s->best_d, B * R));
+    PPG_CUDA(c, dalloc(&s->second_d, B * R));
+    PPG_CUDA(c, dalloc(&s->accept, B * R));
     PPG_CUDA(c, dalloc(&s->fallback, 1));
-    PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&s->h_res), R * 17));
+    s->h_res_bytes = B * R * 17;
+    PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&s->h_res), s->h_res_bytes));
     if (!make_kmajor_map(&s->mapA, s->map_bf, R, 256, A_BM, true) ||
-        !make_kmajor_map(&s->mapB, s->f_bf, N, 256, A_BN, true))
+        !make_kmajor_map(&s->mapB, s->f_bf, B * N, 256, A_BN, true))
         return set_err(c, PPG_ERR_CUDA, "cuTensorMapEncodeTiled failed for the association operands");
-    const int smem = A_STAGES * A_STAGE_BYTES + 1024 + 20 * 8 + 16 + (int)N * 16 + 64;
-    PPG_CUDA(c, cudaFuncSetAttribute(assoc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PPG_CUDA(c, cudaFuncSetAttribute(assoc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(s)));
     return PPG_OK;
 }
 
-// prep + gemm + rescore on the ctx stream.  Frame-side inputs are given as device pointers.
-int run_assoc(ppg_ctx* c, const float* kx, const float* ky, const float* fdesc, const uint8_t* free_mask,
-              const int* n_ptr, int n_val, int force_exact) {
+FrameSrc staged_src(const AssocState* s) {
+    FrameSrc f;
+    f.kx = reinterpret_cast<const uint8_t*>(s->kx);
+    f.ky = reinterpret_cast<const uint8_t*>(s->ky);
+    f.desc = reinterpret_cast<const uint8_t*>(s->fdesc);
+    f.free_mask = s->free_mask;
+    f.n = nullptr;
+    f.stride = 0;
+    f.free_stride = 0;
+    f.n_val = s->staged_n;
+    return f;
+}
+
+// Frames first..first+frames-1 of the last extraction batch: mvKeysUn[i].mPos as run() returns it (kp_x, kp_y)
+// and the descriptors, still on the device.
+FrameSrc extracted_src(const ppg_ctx* c, int first) {
+    const OutLayout& L = c->post.lay;
+    const uint8_t* blk = c->d_out + (size_t)first * L.total;
+    FrameSrc f;
+    f.kx = blk + L.kp_x;
+    f.ky = blk + L.kp_y;
+    f.desc = blk + L.desc;
+    f.free_mask = c->assoc->ones;
+    f.n = blk + L.hdr + HDR_NKP * sizeof(int);
+    f.stride = L.total;
+    f.free_stride = 0;
+    f.n_val = 0;
+    return f;
+}
+
+// prep + gemm + rescore on the ctx stream for `frames` frames; results land in slots 0..frames-1.
+int run_assoc(ppg_ctx* c, const FrameSrc& src, int frames, int force_exact) {
     AssocState* s = c->assoc;
     const int rows = s->staged_rows;
     if (rows < 1 || rows > s->n_rows) return set_err(c, PPG_ERR_ARG, "association: stage rows first (<= uploaded rows)");
+    if (frames < 1 || frames > s->bcap) return set_err(c, PPG_ERR_ARG, "association: bad frame count");
     GridParam g{c->minX, c->minY, c->wInv, c->hInv};
-    PPG_CUDA(c, cudaMemsetAsync(s->nbmax, 0, 4, c->st));
+    PPG_CUDA(c, cudaMemsetAsync(s->nbmax, 0, 4 * frames, c->st));
     PPG_CUDA(c, cudaMemsetAsync(s->fallback, 0, 4, c->st));
-    prep_desc_kernel<<<s->ncap / 8, 256, 0, c->st>>>(fdesc, s->f_bf, s->fn2, n_ptr, n_val, s->ncap, s->nbmax);
-    prep_kp_kernel<<<(s->ncap + 255) / 256, 256, 0, c->st>>>(kx, ky, free_mask, n_ptr, n_val, s->ncap, g, s->kinfo,
-                                                            s->korder);
-    prep_rows_kernel<<<(rows + 255) / 256, 256, 0, c->st>>>(s->proj, s->vcos, s->map_n2, rows, s->th, g, s->rowp);
-    c->launches += 3;
+    prep_frame_kernel<<<dim3(s->ncap / 8, frames), 256, 0, c->st>>>(src, s->ncap, g, s->f_bf, s->fn2, s->kinfo,
+                                                                    s->korder, s->nbmax);
+    prep_rows_kernel<<<dim3((rows + 255) / 256, frames), 256, 0, c->st>>>(s->proj, s->vcos, s->map_n2, rows,
+                                                                          s->max_rows, s->th, g, s->rowp);
+    c->launches += 2;
     if (!force_exact) {
         GemmParams gp;
         gp.rows = rows;
-        gp.n_tiles_n = s->ncap / A_BN;
-        gp.n_ptr = n_ptr;
-        gp.n_val = n_val;
+        gp.max_rows = s->max_rows;
+        gp.ncap = s->ncap;
+        gp.frames = frames;
+        gp.src = src;
         gp.rowp = s->rowp;
-        gp.kx = kx;
-        gp.ky = ky;
         gp.fn2 = s->fn2;
         gp.kinfo = s->kinfo;
         gp.cand = s->cand;
         gp.guard = s->guard;
-        const int m_tiles = (rows + A_BM - 1) / A_BM;
-        const int grid = m_tiles < c->num_sms ? m_tiles : c->num_sms;
-        const int smem = A_STAGES * A_STAGE_BYTES + 1024 + 20 * 8 + 16 + s->ncap * 16 + 64;
-        assoc_gemm_kernel<<<grid, A_THREADS, smem, c->st>>>(s->mapA, s->mapB, gp);
+        const int total = (rows + A_BM - 1) / A_BM * frames;
+        const int grid = total < c->num_sms ? total : c->num_sms;
+        assoc_gemm_kernel<<<grid, A_THREADS, gemm_smem(s), c->st>>>(s->mapA, s->mapB, gp);
         c->launches++;
     }
     RescoreParams rp;
     rp.rows = rows;
-    rp.n_ptr = n_ptr;
-    rp.n_val = n_val;
+    rp.max_rows = s->max_rows;
+    rp.ncap = s->ncap;
+    rp.src = src;
     rp.rowp = s->rowp;
     rp.map_f32 = s->map_f32;
-    rp.fdesc = fdesc;
-    rp.kx = kx;
-    rp.ky = ky;
     rp.kinfo = s->kinfo;
     rp.korder = s->korder;
     rp.cand = s->cand;
@@ -547,10 +625,34 @@ int run_assoc(ppg_ctx* c, const float* kx, const float* ky, const float* fdesc, 
     rp.second_d = s->second_d;
     rp.accept = s->accept;
     rp.fallback = s->fallback;
-    assoc_rescore_kernel<<<(rows + 7) / 8, 256, 0, c->st>>>(rp);
+    assoc_rescore_kernel<<<dim3((rows + 7) / 8, frames), 256, 0, c->st>>>(rp);
     c->launches++;
     PPG_CUDA(c, cudaGetLastError());
     return PPG_OK;
+}
+
+int fetch_slot(ppg_ctx* c, int slot, ppg_assoc_out* out) {
+    AssocState* s = c->assoc;
+    const size_t R = s->staged_rows, o = (size_t)slot * s->max_rows;
+    uint8_t* h = s->h_res + (size_t)slot * s->max_rows * 17;
+    PPG_CUDA(c, cudaMemcpyAsync(h, s->best_idx + o, R * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(h + R * 4, s->second_idx + o, R * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(h + R * 8, s->best_d + o, R * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(h + R * 12, s->second_d + o, R * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(h + R * 16, s->accept + o, R, cudaMemcpyDeviceToHost, c->st));
+    (void)out;
+    return PPG_OK;
+}
+
+void unpack_slot(ppg_ctx* c, int slot, ppg_assoc_out* out) {
+    AssocState* s = c->assoc;
+    const size_t R = s->staged_rows;
+    const uint8_t* h = s->h_res + (size_t)slot * s->max_rows * 17;
+    if (out->best_idx) memcpy(out->best_idx, h, R * 4);
+    if (out->second_idx) memcpy(out->second_idx, h + R * 4, R * 4);
+    if (out->best_dist) memcpy(out->best_dist, h + R * 8, R * 4);
+    if (out->second_dist) memcpy(out->second_dist, h + R * 12, R * 4);
+    if (out->accept) memcpy(out->accept, h + R * 16, R);
 }
 
 }  // namespace
@@ -559,7 +661,7 @@ void assoc_destroy(ppg_ctx* c) {
     AssocState* s = c->assoc;
     if (!s) return;
     void* bufs[] = {s->map_f32, s->map_bf, s->map_n2, s->kx, s->ky, s->fdesc, s->fn2, s->free_mask, s->ones, s->f_bf,
-                    s->kinfo, s->korder, s->d_nkp, s->nbmax, s->proj, s->vcos, s->rowp, s->cand, s->guard,
+                    s->kinfo, s->korder, s->nbmax, s->proj, s->vcos, s->rowp, s->cand, s->guard,
                     s->best_idx, s->second_idx, s->best_d, s->second_d, s->accept, s->fallback};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -582,13 +684,30 @@ int ppg_upload_map(ppg_ctx* c, const float* map_desc, int n_rows) {
     AssocState* s = c->assoc;
     if (n_rows > s->max_rows) return set_err(c, PPG_ERR_ARG, "ppg_upload_map: more rows than max_map_points");
     PPG_CUDA(c, cudaMemcpyAsync(s->map_f32, map_desc, (size_t)n_rows * 1024, cudaMemcpyHostToDevice, c->st));
-    const int padded = (n_rows + 7) / 8 * 8 <= s->max_rows ? (n_rows + 7) / 8 * 8 : n_rows;
-    prep_desc_kernel<<<(padded + 7) / 8, 256, 0, c->st>>>(s->map_f32, s->map_bf, s->map_n2, nullptr, n_rows, padded,
-                                                          nullptr);
+    prep_map_kernel<<<(n_rows + 7) / 8, 256, 0, c->st>>>(s->map_f32, s->map_bf, s->map_n2, n_rows, n_rows);
     c->launches++;
     PPG_CUDA(c, cudaGetLastError());
     PPG_CUDA(c, cudaStreamSynchronize(c->st));
     s->n_rows = n_rows;
+    return PPG_OK;
+}
+
+static int stage_rows(ppg_ctx* c, int frames, int n_rows, const float* proj_uv, const float* view_cos, float th,
+                      float ratio) {
+    AssocState* s = c->assoc;
+    if (n_rows < 1 || n_rows > s->n_rows || !proj_uv || !view_cos)
+        return set_err(c, PPG_ERR_ARG, "association: n_rows must be in [1, uploaded rows]");
+    if (frames < 1 || frames > s->bcap) return set_err(c, PPG_ERR_ARG, "association: bad frame count");
+    for (int f = 0; f < frames; f++) {
+        PPG_CUDA(c, cudaMemcpyAsync(s->proj + (size_t)f * s->max_rows * 2, proj_uv + (size_t)f * n_rows * 2,
+                                    (size_t)n_rows * 8, cudaMemcpyHostToDevice, c->st));
+        PPG_CUDA(c, cudaMemcpyAsync(s->vcos + (size_t)f * s->max_rows, view_cos + (size_t)f * n_rows,
+                                    (size_t)n_rows * 4, cudaMemcpyHostToDevice, c->st));
+    }
+    s->staged_rows = n_rows;
+    s->staged_frames = frames;
+    s->th = th;
+    s->ratio = ratio;
     return PPG_OK;
 }
 
@@ -598,11 +717,8 @@ int ppg_assoc_stage(ppg_ctx* c, const ppg_assoc_in* in) {
     int rc = ensure_state(c);
     if (rc != PPG_OK) return rc;
     AssocState* s = c->assoc;
-    if (in->n_rows < 1 || in->n_rows > s->n_rows || !in->proj_uv || !in->view_cos)
-        return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage: n_rows must be in [1, uploaded rows]");
     if (in->n_kp < 0 || in->n_kp > s->ncap) return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage: too many keypoints");
-    PPG_CUDA(c, cudaMemcpyAsync(s->proj, in->proj_uv, (size_t)in->n_rows * 8, cudaMemcpyHostToDevice, c->st));
-    PPG_CUDA(c, cudaMemcpyAsync(s->vcos, in->view_cos, (size_t)in->n_rows * 4, cudaMemcpyHostToDevice, c->st));
+    if ((rc = stage_rows(c, 1, in->n_rows, in->proj_uv, in->view_cos, in->th, in->ratio)) != PPG_OK) return rc;
     if (in->n_kp > 0 && in->kp_x && in->kp_y && in->frame_desc) {
         PPG_CUDA(c, cudaMemcpyAsync(s->kx, in->kp_x, (size_t)in->n_kp * 4, cudaMemcpyHostToDevice, c->st));
         PPG_CUDA(c, cudaMemcpyAsync(s->ky, in->kp_y, (size_t)in->n_kp * 4, cudaMemcpyHostToDevice, c->st));
@@ -614,49 +730,60 @@ int ppg_assoc_stage(ppg_ctx* c, const ppg_assoc_in* in) {
     }
     PPG_CUDA(c, cudaStreamSynchronize(c->st));
     s->staged_n = in->n_kp;
-    s->staged_rows = in->n_rows;
-    s->th = in->th;
-    s->ratio = in->ratio;
+    return PPG_OK;
+}
+
+int ppg_assoc_stage_batch(ppg_ctx* c, int n_frames, int n_rows, const float* proj_uv, const float* view_cos, float th,
+                          float ratio) {
+    if (!c) return PPG_ERR_ARG;
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    int rc = ensure_state(c);
+    if (rc != PPG_OK) return rc;
+    if ((rc = stage_rows(c, n_frames, n_rows, proj_uv, view_cos, th, ratio)) != PPG_OK) return rc;
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
     return PPG_OK;
 }
 
 int ppg_assoc_run(ppg_ctx* c) {
     if (!c || !c->assoc) return set_err(c, PPG_ERR_ARG, "ppg_assoc_run: nothing staged");
     PPG_CUDA(c, cudaSetDevice(c->dev));
-    AssocState* s = c->assoc;
-    return run_assoc(c, s->kx, s->ky, s->fdesc, s->free_mask, nullptr, s->staged_n, 0);
+    return run_assoc(c, staged_src(c->assoc), 1, 0);
 }
 
 int ppg_assoc_run_frame(ppg_ctx* c, int frame) {
     if (!c || !c->assoc || frame < 0 || frame >= c->maxB)
         return set_err(c, PPG_ERR_ARG, "ppg_assoc_run_frame: bad frame or nothing staged");
     PPG_CUDA(c, cudaSetDevice(c->dev));
-    AssocState* s = c->assoc;
-    const OutLayout& L = c->post.lay;
-    const uint8_t* blk = c->d_out + (size_t)frame * L.total;
-    // mvKeysUn[i].mPos as run() returns it (kp_x, kp_y) and the descriptors, still on the device
-    return run_assoc(c, reinterpret_cast<const float*>(blk + L.kp_x), reinterpret_cast<const float*>(blk + L.kp_y),
-                     reinterpret_cast<const float*>(blk + L.desc), s->ones,
-                     reinterpret_cast<const int*>(blk + L.hdr) + HDR_NKP, 0, 0);
+    return run_assoc(c, extracted_src(c, frame), 1, 0);
+}
+
+int ppg_assoc_run_batch(ppg_ctx* c, int n_frames) {
+    if (!c || !c->assoc || n_frames < 1 || n_frames > c->maxB || n_frames > c->assoc->staged_frames)
+        return set_err(c, PPG_ERR_ARG, "ppg_assoc_run_batch: stage projections for every frame first");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    return run_assoc(c, extracted_src(c, 0), n_frames, 0);
 }
 
 int ppg_assoc_fetch(ppg_ctx* c, ppg_assoc_out* out) {
     if (!c || !c->assoc || !out) return set_err(c, PPG_ERR_ARG, "ppg_assoc_fetch: null argument");
     PPG_CUDA(c, cudaSetDevice(c->dev));
-    AssocState* s = c->assoc;
-    const size_t R = s->staged_rows;
-    uint8_t* h = s->h_res;
-    PPG_CUDA(c, cudaMemcpyAsync(h, s->best_idx, R * 4, cudaMemcpyDeviceToHost, c->st));
-    PPG_CUDA(c, cudaMemcpyAsync(h + R * 4, s->second_idx, R * 4, cudaMemcpyDeviceToHost, c->st));
-    PPG_CUDA(c, cudaMemcpyAsync(h + R * 8, s->best_d, R * 4, cudaMemcpyDeviceToHost, c->st));
-    PPG_CUDA(c, cudaMemcpyAsync(h + R * 12, s->second_d, R * 4, cudaMemcpyDeviceToHost, c->st));
-    PPG_CUDA(c, cudaMemcpyAsync(h + R * 16, s->accept, R, cudaMemcpyDeviceToHost, c->st));
+    int rc = fetch_slot(c, 0, out);
+    if (rc != PPG_OK) return rc;
     PPG_CUDA(c, cudaStreamSynchronize(c->st));
-    if (out->best_idx) memcpy(out->best_idx, h, R * 4);
-    if (out->second_idx) memcpy(out->second_idx, h + R * 4, R * 4);
-    if (out->best_dist) memcpy(out->best_dist, h + R * 8, R * 4);
-    if (out->second_dist) memcpy(out->second_dist, h + R * 12, R * 4);
-    if (out->accept) memcpy(out->accept, h + R * 16, R);
+    unpack_slot(c, 0, out);
+    return PPG_OK;
+}
+
+int ppg_assoc_fetch_batch(ppg_ctx* c, int n_frames, ppg_assoc_out* outs) {
+    if (!c || !c->assoc || !outs || n_frames < 1 || n_frames > c->assoc->bcap)
+        return set_err(c, PPG_ERR_ARG, "ppg_assoc_fetch_batch: bad arguments");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    for (int f = 0; f < n_frames; f++) {
+        int rc = fetch_slot(c, f, &outs[f]);
+        if (rc != PPG_OK) return rc;
+    }
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    for (int f = 0; f < n_frames; f++) unpack_slot(c, f, &outs[f]);
     return PPG_OK;
 }
 

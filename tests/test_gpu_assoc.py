@@ -123,3 +123,34 @@ def test_sharded_association_nccl_two_gpus():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"parity_vs_oracle": true' in r.stdout
+
+
+def test_assoc_batch_equals_oracle_per_frame():
+    """Throughput form: all frames of an extraction batch against the resident table in one set of launches."""
+    from oracle import post_ref as O
+    from ppg_slam_b200 import capi
+    cam = cameras.EUROC
+    Bn, M = 4, 4096
+    e = capi.Extractor(cam, max_batch=Bn, max_map_points=M)
+    try:
+        recs = e.run([synth.frame(s, cam.width, cam.height) for s in range(Bn)])
+        kp0 = np.stack([recs[0]["kp_x"], recs[0]["kp_y"]], 1)
+        base = synth.association_inputs(4, recs[0]["desc"], kp0, M, cam.width, cam.height, th=10.0)
+        e.upload_map(base["map_desc"])
+        rs = np.random.RandomState(0)
+        uv = np.stack([base["proj_uv"] + rs.uniform(-3, 3, base["proj_uv"].shape).astype(np.float32) for _ in range(Bn)])
+        vc = np.stack([base["view_cos"]] * Bn)
+        e.assoc_stage_batch(uv, vc, 10.0, 0.8)
+        e.assoc_run_batch(Bn)
+        got = e.assoc_fetch_batch(Bn)
+        for f in range(Bn):
+            r = recs[f]
+            ref = O.search_all(cam, r["kp_x"], r["kp_y"], r["desc"], np.ones(r["n_kp"], np.uint8), base["map_desc"],
+                               uv[f], vc[f], 10.0, 0.8)
+            np.testing.assert_array_equal(got[f]["best_idx"], ref["best_idx"])
+            np.testing.assert_array_equal(got[f]["second_idx"], ref["second_idx"])
+            np.testing.assert_array_equal(got[f]["best_d"].view(np.uint32), ref["best_d"].view(np.uint32))
+            np.testing.assert_array_equal(got[f]["accept"], ref["accept"])
+        assert got[0]["accept"].sum() > 100
+    finally:
+        e.close()
