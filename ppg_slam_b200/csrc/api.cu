@@ -389,7 +389,9 @@ void ppg_destroy(ppg_ctx* c) {
                     c->feat, c->p1,      c->d1,       c->e1,       c->e2,         c->jlogits,    c->desc,
                     c->prob, c->heat_raw, c->heat_ref, c->heat_final, c->prob_in,  c->heat_in,    c->desc_in,
                     c->undist_lut, c->remap_lut, c->d_out, c->post.state, c->post.cand, c->post.counters,
-                    c->post.pair_bits, c->post.row_cnt, c->post.l_score, c->post.l_edge};
+                    c->post.pair_bits, c->post.row_cnt, c->post.l_score, c->post.l_edge, c->post.row_prefix,
+                    c->post.row_off, c->post.c_se, c->post.c_dist, c->post.c_dirf, c->post.c_dirb, c->post.inter,
+                    c->post.inter_cnt, c->post.inter_off, c->post.inter_pool};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (c->h_gray) cudaFreeHost(c->h_gray);
@@ -609,10 +611,10 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
     p.remap_lut = c->remap_lut;
     p.acc_cap = 8192;
     p.pair_words = (p.max_kp + 31) / 32;
-    p.pair_cap = 6144;
+    p.pair_cap = 16384;
     {
         const size_t budget = 220 * 1024;
-        const size_t fixed = (size_t)p.pair_cap * 17 + (size_t)(p.max_kp * 4 + 1) * 4 + 160 + 64;
+        const size_t fixed = post_lines_fixed_smem(p.max_kp, p.pair_words) + 64;
         int deg = (int)((budget - fixed) / ((size_t)p.max_kp * 2));
         if (deg > 128) deg = 128;
         if (deg < 8) return set_err(c, PPG_ERR_ARG, "junction_max_num too large for the line-graph kernel");
@@ -624,6 +626,17 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
     PPG_CUDA(c, dalloc(&p.counters, (size_t)B * 8));
     PPG_CUDA(c, dalloc(&p.pair_bits, (size_t)B * p.max_kp * p.pair_words));
     PPG_CUDA(c, dalloc(&p.row_cnt, (size_t)B * p.max_kp));
+    PPG_CUDA(c, dalloc(&p.row_prefix, (size_t)B * p.max_kp * p.pair_words));
+    PPG_CUDA(c, dalloc(&p.row_off, (size_t)B * (p.max_kp + 1)));
+    PPG_CUDA(c, dalloc(&p.c_se, (size_t)B * p.pair_cap));
+    PPG_CUDA(c, dalloc(&p.c_dist, (size_t)B * p.pair_cap));
+    PPG_CUDA(c, dalloc(&p.c_dirf, (size_t)B * p.pair_cap));
+    PPG_CUDA(c, dalloc(&p.c_dirb, (size_t)B * p.pair_cap));
+    PPG_CUDA(c, dalloc(&p.inter, (size_t)B * p.pair_cap * 16));
+    PPG_CUDA(c, dalloc(&p.inter_cnt, (size_t)B * p.pair_cap));
+    PPG_CUDA(c, dalloc(&p.inter_off, (size_t)B * p.pair_cap));
+    p.pool_cap = p.pair_cap * 8;
+    PPG_CUDA(c, dalloc(&p.inter_pool, (size_t)B * p.pool_cap));
     PPG_CUDA(c, dalloc(&p.l_score, (size_t)B * p.pair_cap));
     PPG_CUDA(c, dalloc(&p.l_edge, (size_t)B * p.pair_cap));
     PPG_CUDA(c, dalloc(&c->d_out, (size_t)B * p.lay.total));

@@ -369,7 +369,8 @@ __global__ void __launch_bounds__(256) remap_kernel(const PostParams p) {
 
 // ------------------------------------------------------------------------------------------------
 // K10: 3-point heat test for every pair i<j of in-bounds keypoints (:293-313).  One warp per row i;
-// the result is a bit matrix so that the (i asc, j asc) order the greedy filter needs is implicit.
+// the result is a bit matrix so that the (i asc, j asc) order the greedy filter needs is implicit:
+// candidate id(i,j) = row_off[i] + row_prefix[i][j/32] + popc(bits[i][j/32] below j).
 __global__ void __launch_bounds__(256) pair_test_kernel(const PostParams p) {
     __shared__ float sx[POST_MAX_KP], sy[POST_MAX_KP];
     __shared__ uint8_t so[POST_MAX_KP];
@@ -388,6 +389,7 @@ __global__ void __launch_bounds__(256) pair_test_kernel(const PostParams p) {
     if (i >= n) return;
     const float* heat = p.heat_final + (size_t)b * p.H * p.W;
     uint32_t* bits = p.pair_bits + ((size_t)b * p.max_kp + i) * p.pair_words;
+    uint16_t* prefix = p.row_prefix + ((size_t)b * p.max_kp + i) * p.pair_words;
     const float xi = sx[i], yi = sy[i];
     const bool iout = so[i] != 0;
     const float th = p.line_heatmap_thresh;
@@ -406,46 +408,225 @@ __global__ void __launch_bounds__(256) pair_test_kernel(const PostParams p) {
                    !(heat[(int)((double)c3y + 0.5) * p.W + (int)((double)c3x + 0.5)] < th);
         }
         const unsigned m = __ballot_sync(FULL, pass);
-        if (lane == 0) bits[w] = m;
+        if (lane == 0) {
+            bits[w] = m;
+            prefix[w] = (uint16_t)total;
+        }
         total += __popc(m);
     }
     if (lane == 0) p.row_cnt[b * p.max_kp + i] = total;
 }
 
+// Candidate tables in global memory, per frame [pair_cap].
+struct CandTables {
+    uint32_t* se;  // s | e << 16
+    float* dist;
+    float* dirf;   // dir(s,e)  (:283)
+    float* dirb;   // dir(e,s)  (:284-286)
+};
+__device__ __forceinline__ CandTables cand_of(const PostParams& p, int b) {
+    CandTables t;
+    const size_t o = (size_t)b * p.pair_cap;
+    t.se = p.c_se + o;
+    t.dist = p.c_dist + o;
+    t.dirf = p.c_dirf + o;
+    t.dirb = p.c_dirb + o;
+    return t;
+}
+__device__ __forceinline__ int cand_id(const PostParams& p, int b, const int* row_off, int lo, int hi) {
+    const size_t r = ((size_t)b * p.max_kp + lo) * p.pair_words + (hi >> 5);
+    return row_off[lo] + p.row_prefix[r] + __popc(p.pair_bits[r] & ((1u << (hi & 31)) - 1u));
+}
+
+// K10b: row offsets (every block rescans the <= 1024 row counts) + candidate table (:265-288 evaluated only
+// for the pairs that passed).  grid (ceil(max_kp/8), B), one warp per row.
+__global__ void __launch_bounds__(256) cand_build_kernel(const PostParams p) {
+    __shared__ int s_off[POST_MAX_KP + 1];
+    __shared__ int ws[40];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int n = hdr_of(p, b)[HDR_NKP];
+    int carry = 0;
+    for (int t0 = 0; t0 < n; t0 += blockDim.x) {
+        const int t = t0 + tid;
+        const int v = t < n ? p.row_cnt[b * p.max_kp + t] : 0;
+        int tot;
+        const int ex = block_excl_scan(v, ws, &tot);
+        if (t < n) s_off[t] = carry + ex;
+        carry += tot;
+    }
+    if (tid == 0) s_off[n] = carry;
+    __syncthreads();
+    int* row_off = p.row_off + (size_t)b * (p.max_kp + 1);
+    if (blockIdx.x == 0)
+        for (int t = tid; t <= n; t += blockDim.x) row_off[t] = s_off[t];
+    const int i = blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+    if (i >= n) return;
+    const float* xun = out_of<float>(p, b, p.lay.xun);
+    const float* yun = out_of<float>(p, b, p.lay.yun);
+    const CandTables T = cand_of(p, b);
+    const uint32_t* bits = p.pair_bits + ((size_t)b * p.max_kp + i) * p.pair_words;
+    const float xi = xun[i], yi = yun[i];
+    int pos = s_off[i];
+    const int words = (n + 31) >> 5;
+    for (int w = 0; w < words; w++) {
+        const uint32_t mw = bits[w];
+        if (mw & (1u << lane)) {
+            const int id = pos + __popc(mw & ((1u << lane) - 1u));
+            if (id < p.pair_cap) {
+                const int j = w * 32 + lane;
+                const float dx = xun[j] - xi, dy = yun[j] - yi;    // :278
+                const float dist = sqrtf(dx * dx + dy * dy);       // :279
+                const float ux = __fdiv_rn(dx, dist), uy = __fdiv_rn(dy, dist);
+                const float d = (float)atan2((double)uy, (double)ux);  // :283 (see oracle divergence 2)
+                float r = (float)((double)d - PPG_PI);                 // :284
+                if ((double)r < -PPG_PI) r = (float)((double)r + PPG_2PI);
+                T.dist[id] = dist;
+                T.dirf[id] = d;
+                T.dirb[id] = r;
+                T.se[id] = (uint32_t)i | ((uint32_t)j << 16);
+            }
+        }
+        pos += __popc(mw);
+    }
+}
+
+// K11a: the pairwise part of the overlap filter (:316-335 / :338-357), evaluated for EVERY (new candidate,
+// earlier candidate sharing an endpoint) in parallel.  Whether the earlier line is still alive when the new
+// one is processed is the only sequential state; everything else is a pure function of the two candidates:
+//   kill  : distNew <= distOld && distNew*sin(a) < thr   -> the old line becomes bad
+//   block : distOld <  distNew && distOld*sin(a) < thr   -> the new line is not created
+// One warp per candidate; entries = other endpoint q of the old line | type << 15, <= INTER_K per side.
+constexpr int INTER_K = 8;
+
+__device__ __forceinline__ int interact_one(const PostParams& p, const CandTables& T, int b, const int* row_off, int pt,
+                                            int q, float dir_new, float dist_new) {
+    const int lo = pt < q ? pt : q, hi = pt < q ? q : pt;
+    const int id = cand_id(p, b, row_off, lo, hi);
+    if (id >= p.pair_cap) return -1;
+    const float dir_old = (pt == lo) ? T.dirf[id] : T.dirb[id];
+    float a = dir_new - dir_old;
+    if ((double)a < -PPG_PI) a = (float)((double)a + PPG_2PI);
+    if ((double)a > PPG_PI) a = (float)((double)a - PPG_2PI);
+    a = fabsf(a);
+    if ((double)a > 0.2 * PPG_PI) return -1;
+    const float dist_old = T.dist[id];
+    const float sn = (float)sin((double)a);  // :330 unqualified sin -> double overload
+    if (dist_new <= dist_old && dist_new * sn < p.line_dist_thresh) return 0;
+    if (dist_old < dist_new && dist_old * sn < p.line_dist_thresh) return 1;
+    return -1;
+}
+
+// One pass over the earlier candidates that share an endpoint with candidate (i,j):
+//   side i: old lines (q,i) with q < i (rows above), and (i,q) with i < q < j (same row, earlier columns)
+//   side j: old lines (q,j) with q < i (rows above row i); later rows are not created yet
+// Entries are written in ascending q (= the order of the reference's adjacency lists) while they fit.
+__device__ __forceinline__ void interact_scan(const PostParams& p, const CandTables& T, int b, const int* row_off,
+                                              const uint32_t* bits, int i, int j, float dirf, float dirb, float dist_new,
+                                              int lane, uint16_t* ent_i, int cap_i, uint16_t* ent_j, int cap_j,
+                                              int* out_cnt_i, int* out_cnt_j) {
+    int cnt_i = 0, cnt_j = 0;
+    for (int q0 = 0; q0 < j; q0 += 32) {
+        const int q = q0 + lane;
+        int ti = -1, tj = -1;
+        if (q < i) {
+            if ((bits[(size_t)q * p.pair_words + (i >> 5)] >> (i & 31)) & 1u) ti = interact_one(p, T, b, row_off, i, q, dirf, dist_new);
+            if ((bits[(size_t)q * p.pair_words + (j >> 5)] >> (j & 31)) & 1u) tj = interact_one(p, T, b, row_off, j, q, dirb, dist_new);
+        } else if (q > i && q < j) {
+            if ((bits[(size_t)i * p.pair_words + (q >> 5)] >> (q & 31)) & 1u) ti = interact_one(p, T, b, row_off, i, q, dirf, dist_new);
+        }
+        const unsigned mi = __ballot_sync(FULL, ti >= 0), mj = __ballot_sync(FULL, tj >= 0);
+        if (ti >= 0) {
+            const int k = cnt_i + __popc(mi & ((1u << lane) - 1u));
+            if (k < cap_i) ent_i[k] = (uint16_t)(q | (ti << 15));
+        }
+        if (tj >= 0) {
+            const int k = cnt_j + __popc(mj & ((1u << lane) - 1u));
+            if (k < cap_j) ent_j[k] = (uint16_t)(q | (tj << 15));
+        }
+        cnt_i += __popc(mi);
+        cnt_j += __popc(mj);
+    }
+    *out_cnt_i = cnt_i;
+    *out_cnt_j = cnt_j;
+}
+
+// Lists longer than INTER_K per side (dense fans of near-parallel candidates) spill to a per-frame pool: the warp
+// reserves cnt_i + cnt_j entries and repeats the scan into them.  inter_off = pool offset, or ~0 for inline.
+__global__ void __launch_bounds__(256) interact_kernel(const PostParams p) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int n = hdr_of(p, b)[HDR_NKP];
+    if (n == 0) return;
+    const int* row_off = p.row_off + (size_t)b * (p.max_kp + 1);
+    int npass = row_off[n];
+    if (npass > p.pair_cap) npass = p.pair_cap;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= npass) return;
+    const CandTables T = cand_of(p, b);
+    const uint32_t se = T.se[c];
+    const int i = se & 0xffff, j = se >> 16;
+    const float dist_new = T.dist[c], dirf = T.dirf[c], dirb = T.dirb[c];
+    uint16_t* ent = p.inter + ((size_t)b * p.pair_cap + c) * (2 * INTER_K);
+    const uint32_t* bits = p.pair_bits + (size_t)b * p.max_kp * p.pair_words;
+    int cnt_i, cnt_j;
+    interact_scan(p, T, b, row_off, bits, i, j, dirf, dirb, dist_new, lane, ent, INTER_K, ent + INTER_K, INTER_K, &cnt_i, &cnt_j);
+    uint32_t off = 0xffffffffu;
+    if (cnt_i > INTER_K || cnt_j > INTER_K) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&p.counters[b * 8 + 2], cnt_i + cnt_j);
+        base = __shfl_sync(FULL, base, 0);
+        if (base + cnt_i + cnt_j <= p.pool_cap) {
+            uint16_t* pool = p.inter_pool + (size_t)b * p.pool_cap + base;
+            int ci2, cj2;
+            interact_scan(p, T, b, row_off, bits, i, j, dirf, dirb, dist_new, lane, pool, cnt_i, pool + cnt_i, cnt_j, &ci2, &cj2);
+            off = (uint32_t)base;
+        } else {
+            off = 0xfffffffeu;  // pool exhausted: reported as ST_OVF_DEGREE by lines_kernel
+        }
+    }
+    if (lane == 0) {
+        p.inter_cnt[(size_t)b * p.pair_cap + c] = (uint32_t)cnt_i | ((uint32_t)cnt_j << 16);
+        p.inter_off[(size_t)b * p.pair_cap + c] = off;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
-// K11+K12: one CTA per frame.  Shared-memory resident candidate-line table and adjacency lists.
-//   A  row offsets of the bit matrix -> candidate ids in (i,j) order; dist / dir per candidate (:265-288)
-//   B  greedy overlap filter, sequential over candidates, one warp, lanes scan the adjacency list (:314-365)
+// K11b+K12: one CTA per frame.
+//   A  alive[p] = bit set over the other endpoint q of every candidate line at p (symmetric matrix)
+//   B  the sequential part of the greedy overlap filter: only candidates that HAVE an interaction entry are
+//      visited (in candidate order, one thread); kills clear the old line's bits, a block clears the new one's
 //   C  line scoring, one thread per surviving candidate (:366-389, :461-513)
 //   D  final edges, mvConnected CSR (:433-441)
 //   E  colinearity per keypoint, one thread per keypoint (:391-432), mvColine CSR
 struct LineSmem {
-    float* dist;
-    float* dirf;   // dir(s,e)
-    float* dirb;   // dir(e,s)
-    uint32_t* se;  // s | e << 16
-    uint8_t* flag; // 1 created, 2 bad
-    uint16_t* adj; // [max_kp][deg_cap]
-    int* adj_cnt;  // [max_kp]
-    int* row_off;  // [max_kp + 1]
+    uint32_t* alive;   // [max_kp][pair_words]
+    uint16_t* adj;     // [max_kp][deg_cap] candidate ids of the final lines at p, ascending
+    int* adj_cnt;      // [max_kp]
+    int* row_off;      // [max_kp + 1]
     float* kx;
     float* ky;
-    int* ws;       // 40 ints scan scratch / flags
+    int* ws;           // 48 ints scan scratch / flags
+    uint32_t* seq_se;  // [SEQ_WIN] s | e << 16 of the candidates with interactions in the current window
+    uint32_t* seq_cnt; // [SEQ_WIN] entries at s | entries at e << 16
+    uint32_t* seq_off; // [SEQ_WIN] pool offset of spilled lists, ~0 = inline
+    uint16_t* seq_ent; // [SEQ_WIN][2*INTER_K] inline lists
 };
+constexpr int SEQ_WIN = 1024;
 
 __device__ __forceinline__ LineSmem carve_lines(const PostParams& p, uint8_t* s) {
     LineSmem m;
-    m.dist = reinterpret_cast<float*>(s);
-    m.dirf = m.dist + p.pair_cap;
-    m.dirb = m.dirf + p.pair_cap;
-    m.se = reinterpret_cast<uint32_t*>(m.dirb + p.pair_cap);
-    m.adj_cnt = reinterpret_cast<int*>(m.se + p.pair_cap);
+    m.alive = reinterpret_cast<uint32_t*>(s);
+    m.adj_cnt = reinterpret_cast<int*>(m.alive + (size_t)p.max_kp * p.pair_words);
     m.row_off = m.adj_cnt + p.max_kp;
     m.kx = reinterpret_cast<float*>(m.row_off + p.max_kp + 1);
     m.ky = m.kx + p.max_kp;
     m.ws = reinterpret_cast<int*>(m.ky + p.max_kp);
-    m.adj = reinterpret_cast<uint16_t*>(m.ws + 40);
-    m.flag = reinterpret_cast<uint8_t*>(m.adj + (size_t)p.max_kp * p.deg_cap);
+    uintptr_t q = reinterpret_cast<uintptr_t>(m.ws + 48);
+    q = (q + 15) & ~static_cast<uintptr_t>(15);  // seq_ent rows are copied as uint4
+    m.seq_se = reinterpret_cast<uint32_t*>(q);
+    m.seq_cnt = m.seq_se + SEQ_WIN;
+    m.seq_off = m.seq_cnt + SEQ_WIN;
+    m.seq_ent = reinterpret_cast<uint16_t*>(m.seq_off + SEQ_WIN);
+    m.adj = m.seq_ent + SEQ_WIN * 2 * INTER_K;
     return m;
 }
 
@@ -458,39 +639,18 @@ __device__ __forceinline__ float bilinear_heat(const float* M, int W, float ptX,
     return ((float)y2 - ptY) * d1 + (ptY - (float)y1) * d2;
 }
 
-// One adjacency scan of the overlap filter (:316-335 / :338-357), executed by a full warp.
-__device__ __forceinline__ bool overlap_scan(const PostParams& p, const LineSmem& m, int pt, float dir_new,
-                                             float dist_new, int lane) {
-    const int cnt = m.adj_cnt[pt];
-    bool ov = false;
-    for (int t0 = 0; t0 < cnt; t0 += 32) {
-        const int t = t0 + lane;
-        if (t < cnt) {
-            const int lo = m.adj[pt * p.deg_cap + t];
-            if (!(m.flag[lo] & 2)) {
-                const int s_old = m.se[lo] & 0xffff;
-                const float dir_old = (pt == s_old) ? m.dirf[lo] : m.dirb[lo];
-                float a = dir_new - dir_old;
-                if ((double)a < -PPG_PI) a = (float)((double)a + PPG_2PI);
-                if ((double)a > PPG_PI) a = (float)((double)a - PPG_2PI);
-                a = fabsf(a);
-                if (!((double)a > 0.2 * PPG_PI)) {
-                    const float dist_old = m.dist[lo];
-                    const float sn = (float)sin((double)a);  // :330 unqualified sin -> double overload
-                    if (dist_new <= dist_old && dist_new * sn < p.line_dist_thresh) m.flag[lo] |= 2;
-                    if (dist_old < dist_new && dist_old * sn < p.line_dist_thresh) ov = true;
-                }
-            }
-        }
-    }
-    __syncwarp();
-    return __any_sync(FULL, ov);
+__device__ __forceinline__ bool alive_bit(const LineSmem& m, int words, int pt, int q) {
+    return (m.alive[pt * words + (q >> 5)] >> (q & 31)) & 1u;
+}
+__device__ __forceinline__ void clear_line(const LineSmem& m, int words, int a, int b2) {
+    atomicAnd(&m.alive[a * words + (b2 >> 5)], ~(1u << (b2 & 31)));
+    atomicAnd(&m.alive[b2 * words + (a >> 5)], ~(1u << (a & 31)));
 }
 
 __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
     extern __shared__ __align__(16) uint8_t smem_lines[];
     const LineSmem m = carve_lines(p, smem_lines);
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int b = blockIdx.x, tid = threadIdx.x;
     int* hdr = hdr_of(p, b);
     const int n = hdr[HDR_NKP];
     int* conn_off = out_of<int>(p, b, p.lay.conn_off);
@@ -503,103 +663,134 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
         return;
     }
     const float* heat = p.heat_final + (size_t)b * p.H * p.W;
-    const uint8_t* ko = out_of<uint8_t>(p, b, p.lay.kout);
+    const CandTables T = cand_of(p, b);
+    const int words = p.pair_words, nwords = (n + 31) >> 5;
     unsigned status = 0;
 
-    // ---- A: row offsets + candidate table
+    // ---- A: keypoints, row offsets, symmetric alive matrix
+    const int* g_row_off = p.row_off + (size_t)b * (p.max_kp + 1);
     for (int t = tid; t < n; t += blockDim.x) {
         m.kx[t] = out_of<float>(p, b, p.lay.xun)[t];
         m.ky[t] = out_of<float>(p, b, p.lay.yun)[t];
         m.adj_cnt[t] = 0;
     }
-    int carry = 0;
-    for (int t0 = 0; t0 < n; t0 += blockDim.x) {
-        const int t = t0 + tid;
-        const int v = t < n ? p.row_cnt[b * p.max_kp + t] : 0;
-        int tot;
-        const int ex = block_excl_scan(v, m.ws, &tot);
-        if (t < n) m.row_off[t] = carry + ex;
-        carry += tot;
+    for (int t = tid; t <= n; t += blockDim.x) m.row_off[t] = g_row_off[t];
+    const uint32_t* bits = p.pair_bits + (size_t)b * p.max_kp * words;
+    for (int t = tid; t < n * words; t += blockDim.x) {
+        const int w = t % words;
+        m.alive[t] = (w < nwords) ? bits[t] : 0u;
     }
-    const int npass_all = carry;
+    __syncthreads();
+    const int npass_all = m.row_off[n];
     int npass = npass_all;
     if (npass > p.pair_cap) {
         npass = p.pair_cap;
         status |= ST_OVF_PAIRS;
     }
-    __syncthreads();
-    const int words = (n + 31) >> 5;
-    for (int i = warp; i < n; i += nwarps) {
-        const uint32_t* bits = p.pair_bits + ((size_t)b * p.max_kp + i) * p.pair_words;
-        int pos = m.row_off[i];
-        const float xi = m.kx[i], yi = m.ky[i];
-        for (int w = 0; w < words; w++) {
-            const uint32_t mw = bits[w];
-            if (mw & (1u << lane)) {
-                const int id = pos + __popc(mw & ((1u << lane) - 1u));
-                if (id < npass) {
-                    const int j = w * 32 + lane;
-                    const float dx = m.kx[j] - xi, dy = m.ky[j] - yi;  // :278
-                    const float dist = sqrtf(dx * dx + dy * dy);       // :279
-                    const float ux = __fdiv_rn(dx, dist), uy = __fdiv_rn(dy, dist);
-                    const float d = (float)atan2((double)uy, (double)ux);  // :283 (see oracle divergence 2)
-                    float r = (float)((double)d - PPG_PI);                 // :284
-                    if ((double)r < -PPG_PI) r = (float)((double)r + PPG_2PI);
-                    m.dist[id] = dist;
-                    m.dirf[id] = d;
-                    m.dirb[id] = r;
-                    m.se[id] = (uint32_t)i | ((uint32_t)j << 16);
-                    m.flag[id] = 0;
-                }
-            }
-            pos += __popc(mw);
-        }
+    for (int c = tid; c < npass; c += blockDim.x) {  // transpose: bit i of row j
+        const uint32_t se = T.se[c];
+        const int i = se & 0xffff, j = se >> 16;
+        atomicOr(&m.alive[j * words + (i >> 5)], 1u << (i & 31));
+    }
+    if (tid == 0) {
+        m.ws[40] = 0;  // blocked count
+        m.ws[41] = 0;  // interaction-list overflow
     }
     __syncthreads();
 
-    // ---- B: greedy overlap filter, candidates in (i asc, j asc) order
-    if (warp == 0) {
-        int created = 0;
-        bool deg_ovf = false;
-        for (int c = 0; c < npass; c++) {
-            const uint32_t se = m.se[c];
-            const int i = se & 0xffff, j = se >> 16;
-            const float dist_new = m.dist[c];
-            if (overlap_scan(p, m, i, m.dirf[c], dist_new, lane)) continue;  // :336-337
-            if (overlap_scan(p, m, j, m.dirb[c], dist_new, lane)) continue;  // :358-359
-            if (lane == 0) {
-                const int ci = m.adj_cnt[i], cj = m.adj_cnt[j];
-                if (ci < p.deg_cap && cj < p.deg_cap) {
-                    m.flag[c] = 1;
-                    m.adj[i * p.deg_cap + ci] = (uint16_t)c;
-                    m.adj[j * p.deg_cap + cj] = (uint16_t)c;
-                    m.adj_cnt[i] = ci + 1;
-                    m.adj_cnt[j] = cj + 1;
-                } else {
-                    deg_ovf = true;
+    // ---- B: sequential pass over the candidates that interact, window by window
+    const uint32_t* g_cnt = p.inter_cnt + (size_t)b * p.pair_cap;
+    const uint32_t* g_off = p.inter_off + (size_t)b * p.pair_cap;
+    const uint16_t* g_ent = p.inter + (size_t)b * p.pair_cap * (2 * INTER_K);
+    const uint16_t* g_pool = p.inter_pool + (size_t)b * p.pool_cap;
+    for (int c0 = 0; c0 < npass;) {
+        // compact up to SEQ_WIN interacting candidates starting at c0 (block-wide, order preserved)
+        int filled = 0, c_next = c0;
+        while (filled < SEQ_WIN && c_next < npass) {
+            const int c = c_next + tid;
+            uint32_t cnt = 0;
+            if (c < npass) cnt = g_cnt[c];
+            int tot;
+            const int ex = block_excl_scan(cnt != 0 ? 1 : 0, m.ws, &tot);
+            if (filled + tot > SEQ_WIN) break;  // this chunk does not fit: process what we have first
+            if (cnt != 0) {
+                const int k = filled + ex;
+                const uint32_t off = g_off[c];
+                m.seq_cnt[k] = cnt;
+                m.seq_off[k] = off;
+                m.seq_se[k] = T.se[c];
+                if (off == 0xffffffffu) {
+                    const uint4* src = reinterpret_cast<const uint4*>(g_ent + (size_t)c * 2 * INTER_K);
+                    uint4* dst = reinterpret_cast<uint4*>(m.seq_ent + (size_t)k * 2 * INTER_K);
+                    dst[0] = src[0];
+                    dst[1] = src[1];
                 }
             }
-            created++;
-            __syncwarp();
+            filled += tot;
+            c_next += blockDim.x;
         }
-        if (lane == 0) {
-            m.ws[34] = created;
-            m.ws[35] = deg_ovf ? 1 : 0;
+        __syncthreads();
+        if (tid == 0) {
+            int blocked = 0, ovf = 0;
+            for (int k = 0; k < filled; k++) {
+                const uint32_t se = m.seq_se[k];
+                const int i = se & 0xffff, j = se >> 16;
+                const int ci = m.seq_cnt[k] & 0xffff, cj = m.seq_cnt[k] >> 16;
+                const uint32_t off = m.seq_off[k];
+                const uint16_t *ei, *ej;
+                if (off == 0xffffffffu) {
+                    ei = m.seq_ent + (size_t)k * 2 * INTER_K;
+                    ej = ei + INTER_K;
+                } else if (off == 0xfffffffeu) {
+                    ovf = 1;
+                    continue;
+                } else {
+                    ei = g_pool + off;
+                    ej = ei + ci;
+                }
+                bool blk = false;
+                for (int t = 0; t < ci; t++) {  // scan of adj[i] (:316-335)
+                    const int e = ei[t];
+                    const int q = e & 0x7fff;
+                    if (!alive_bit(m, words, i, q)) continue;
+                    if (e >> 15)
+                        blk = true;
+                    else
+                        clear_line(m, words, i, q);
+                }
+                if (!blk)
+                    for (int t = 0; t < cj; t++) {  // scan of adj[j] (:338-357), only if not yet overlapping
+                        const int e = ej[t];
+                        const int q = e & 0x7fff;
+                        if (!alive_bit(m, words, j, q)) continue;
+                        if (e >> 15)
+                            blk = true;
+                        else
+                            clear_line(m, words, j, q);
+                    }
+                if (blk) {
+                    clear_line(m, words, i, j);
+                    blocked++;
+                }
+            }
+            m.ws[40] += blocked;
+            m.ws[41] |= ovf;
         }
+        __syncthreads();
+        c0 = c_next;
     }
-    __syncthreads();
-    if (m.ws[35]) status |= ST_OVF_DEGREE;
-    const int ncreated = m.ws[34];
+    if (m.ws[41]) status |= ST_OVF_DEGREE;
+    const int ncreated = npass - m.ws[40];
 
     // ---- C: line scoring (:367-389)
     float* lscore = p.l_score + (size_t)b * p.pair_cap;
     int* ledge = p.l_edge + (size_t)b * p.pair_cap;
     for (int c = tid; c < npass; c += blockDim.x) {
-        if (m.flag[c] != 1) continue;
-        const uint32_t se = m.se[c];
+        const uint32_t se = T.se[c];
         const int s = se & 0xffff, e = se >> 16;
+        if (!alive_bit(m, words, s, e)) continue;
         const float psx = m.kx[s], psy = m.ky[s], pex = m.kx[e], pey = m.ky[e];
-        const float dist = m.dist[c];
+        const float dist = T.dist[c];
         int lenLevel = (int)((double)(dist * p.inv_scale) * 4.0);  // :485
         if (lenLevel > 3) lenLevel = 3;                            // dist == diagonal cannot happen (points >= 1 px inside)
         if (lenLevel < 0) lenLevel = 0;
@@ -624,9 +815,16 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
             if (sh < p.line_heatmap_thresh) bad = true;
         }
         if (bad)
-            m.flag[c] = 3;
+            lscore[c] = -INFINITY;  // marker; bits are cleared after the barrier (other threads still read them)
         else
             lscore[c] = rate * sh;
+        ledge[c] = bad ? -2 : -1;
+    }
+    __syncthreads();
+    for (int c = tid; c < npass; c += blockDim.x) {
+        const uint32_t se = T.se[c];
+        const int s = se & 0xffff, e = se >> 16;
+        if (alive_bit(m, words, s, e) && ledge[c] == -2) clear_line(m, words, s, e);
     }
     __syncthreads();
 
@@ -637,15 +835,20 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
     float* esc = out_of<float>(p, b, p.lay.edge_score);
     for (int c0 = 0; c0 < npass; c0 += blockDim.x) {
         const int c = c0 + tid;
-        const int v = (c < npass && m.flag[c] == 1) ? 1 : 0;
+        uint32_t se = 0;
+        int v = 0;
+        if (c < npass) {
+            se = T.se[c];
+            v = alive_bit(m, words, se & 0xffff, se >> 16) ? 1 : 0;
+        }
         int tot;
         const int ex = block_excl_scan(v, m.ws, &tot);
         if (v) {
             const int E = ecarry + ex;
             ledge[c] = E;
             if (E < p.lay.max_edges) {
-                es[E] = m.se[c] & 0xffff;
-                ee[E] = m.se[c] >> 16;
+                es[E] = se & 0xffff;
+                ee[E] = se >> 16;
                 esc[E] = lscore[c];
             }
         }
@@ -655,18 +858,28 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
     if (nedges > p.lay.max_edges) status |= ST_OVF_EDGES;
     __syncthreads();
 
-    // adjacency rows: drop bad lines in place (order kept = ascending candidate id, as :366-388 rebuilds it)
+    // adjacency rows: final lines at p in ascending other-endpoint order = ascending candidate id (= the order
+    // in which :366-388 re-pushes them)
+    bool deg_ovf = false;
     for (int t = tid; t < n; t += blockDim.x) {
-        uint16_t* row = m.adj + t * p.deg_cap;
-        const int cnt = m.adj_cnt[t];
+        uint16_t* row = m.adj + (size_t)t * p.deg_cap;
         int k = 0;
-        for (int q = 0; q < cnt; q++) {
-            const uint16_t l = row[q];
-            if (m.flag[l] == 1) row[k++] = l;
+        for (int w = 0; w < nwords; w++) {
+            uint32_t mw = m.alive[t * words + w];
+            while (mw) {
+                const int q = w * 32 + __ffs(mw) - 1;
+                mw &= mw - 1;
+                const int lo = t < q ? t : q, hi = t < q ? q : t;
+                if (k < p.deg_cap)
+                    row[k] = (uint16_t)cand_id(p, b, m.row_off, lo, hi);
+                else
+                    deg_ovf = true;
+                k++;
+            }
         }
-        m.adj_cnt[t] = k;
+        m.adj_cnt[t] = k < p.deg_cap ? k : p.deg_cap;
     }
-    __syncthreads();
+    if (__syncthreads_or(deg_ovf)) status |= ST_OVF_DEGREE;
     // mvConnected CSR
     int* conn_idx = out_of<int>(p, b, p.lay.conn_idx);
     int ccarry = 0;
@@ -679,7 +892,7 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
             const int off = ccarry + ex;
             conn_off[t] = off;
             if (nedges <= p.lay.max_edges)
-                for (int q = 0; q < v; q++) conn_idx[off + q] = ledge[m.adj[t * p.deg_cap + q]];
+                for (int q = 0; q < v; q++) conn_idx[off + q] = ledge[m.adj[(size_t)t * p.deg_cap + q]];
         }
         ccarry += tot;
     }
@@ -694,24 +907,26 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
         int D = 0;
         ncol_mine = 0;
         if (pt < n) {
-            uint16_t* row = m.adj + pt * p.deg_cap;
+            uint16_t* row = m.adj + (size_t)pt * p.deg_cap;
             D = m.adj_cnt[pt];
             int mm = D;
             while (mm > 1) {
                 const int l1 = row[mm - 1];
-                const int s1 = m.se[l1] & 0xffff, e1 = m.se[l1] >> 16;
+                const uint32_t se1 = T.se[l1];
+                const int s1 = se1 & 0xffff, e1 = se1 >> 16;
                 const int p1 = (pt == s1) ? e1 : s1;
-                const float dir1 = (pt == s1) ? m.dirf[l1] : m.dirb[l1];
-                const float dist1 = m.dist[l1];
+                const float dir1 = (pt == s1) ? T.dirf[l1] : T.dirb[l1];
+                const float dist1 = T.dist[l1];
                 double minPD = 1e9;
                 int best = -1, bp2 = -1;
                 for (int i = 0; i < mm - 1; i++) {
                     const int l2 = row[i];
-                    const int s2 = m.se[l2] & 0xffff, e2 = m.se[l2] >> 16;
+                    const uint32_t se2 = T.se[l2];
+                    const int s2 = se2 & 0xffff, e2 = se2 >> 16;
                     const int p2 = (pt == s2) ? e2 : s2;
-                    const float dir2 = (pt == s2) ? m.dirf[l2] : m.dirb[l2];
+                    const float dir2 = (pt == s2) ? T.dirf[l2] : T.dirb[l2];
                     const float ad = dir1 - dir2;
-                    const double pd = 0.5 * (double)(dist1 + m.dist[l2]) * (double)fabsf((float)sin((double)ad));  // :413
+                    const double pd = 0.5 * (double)(dist1 + T.dist[l2]) * (double)fabsf((float)sin((double)ad));  // :413
                     if (minPD > pd) {
                         minPD = pd;
                         best = i;
@@ -736,7 +951,7 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
         if (pt < n) {
             const int off = colcarry + ex;
             col_off[pt] = off;
-            const uint16_t* row = m.adj + pt * p.deg_cap;
+            const uint16_t* row = m.adj + (size_t)pt * p.deg_cap;
             for (int k = 0; k < ncol_mine; k++) {
                 const int slot = D - 2 * (k + 1);
                 if (off + k < p.lay.max_col) {
@@ -756,7 +971,6 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
         hdr[HDR_NPASS] = npass_all;
         hdr[HDR_NLINES] = ncreated;
     }
-    (void)ko;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -852,11 +1066,15 @@ OutLayout make_out_layout(int max_kp, int max_edges, int max_col) {
 
 size_t post_nms_smem(const PostParams& p) { return (size_t)p.acc_cap * 8; }
 
-size_t post_lines_smem(const PostParams& p) {
-    size_t s = (size_t)p.pair_cap * 16;                    // dist, dirf, dirb, se
-    s += (size_t)(p.max_kp * 4 + 1) * 4 + 40 * 4;          // adj_cnt, row_off, kx, ky, ws
-    s += (size_t)p.max_kp * p.deg_cap * 2 + p.pair_cap;    // adj, flag
+size_t post_lines_fixed_smem(int max_kp, int pair_words) {
+    size_t s = (size_t)max_kp * pair_words * 4;                     // alive
+    s += (size_t)(max_kp * 4 + 1) * 4 + 48 * 4 + 16;                // adj_cnt, row_off, kx, ky, ws (+ alignment)
+    s += (size_t)SEQ_WIN * (4 + 4 + 4 + 2 * INTER_K * 2);           // seq_se, seq_cnt, seq_off, seq_ent
     return align_up(s, 16);
+}
+
+size_t post_lines_smem(const PostParams& p) {
+    return align_up(post_lines_fixed_smem(p.max_kp, p.pair_words) + (size_t)p.max_kp * p.deg_cap * 2, 16);
 }
 
 cudaError_t post_init_attrs(const PostParams& p) {
@@ -891,8 +1109,10 @@ cudaError_t post_heat_launch(const PostParams& p, cudaStream_t st, long long* la
 cudaError_t post_lines_launch(const PostParams& p, cudaStream_t st, long long* launches) {
     dim3 g((p.max_kp + 7) / 8, p.B);
     pair_test_kernel<<<g, 256, 0, st>>>(p);
+    cand_build_kernel<<<g, 256, 0, st>>>(p);
+    interact_kernel<<<dim3((p.pair_cap + 7) / 8, p.B), 256, 0, st>>>(p);
     lines_kernel<<<p.B, 512, post_lines_smem(p), st>>>(p);
-    *launches += 2;
+    *launches += 4;
     return cudaGetLastError();
 }
 

@@ -51,12 +51,21 @@ struct PostParams {
     // scratch, per frame
     uint8_t* state;     // [B][H*W]   0 none, 1 undecided candidate, 2 accepted, 3 suppressed
     uint32_t* cand;     // [B][H*W]   pixel indices of in-border candidates (unordered)
-    int* counters;      // [B][8]     0: candidates in border, 1: pixels >= threshold
+    int* counters;      // [B][8]     0: candidates in border, 1: pixels >= threshold, 2: inter_pool entries used
     int acc_cap;        // NMS survivors that can be ranked (power of two)
     uint32_t* pair_bits;  // [B][max_kp][pair_words] bit j of row i: pair (i,j) passed the 3-point test
     int pair_words;
     int* row_cnt;       // [B][max_kp]
+    uint16_t* row_prefix;  // [B][max_kp][pair_words] set bits of the row before each word
+    int* row_off;       // [B][max_kp + 1] candidate id of the first pair of each row
     int pair_cap, deg_cap;
+    uint32_t* c_se;     // [B][pair_cap] candidate lines: s | e << 16
+    float *c_dist, *c_dirf, *c_dirb;
+    uint16_t* inter;    // [B][pair_cap][16] overlap-filter interactions (8 per endpoint)
+    uint32_t* inter_cnt;  // [B][pair_cap] count at s | count at e << 16
+    uint32_t* inter_off;  // [B][pair_cap] offset of a spilled list in inter_pool, ~0 = inline
+    uint16_t* inter_pool; // [B][pool_cap] spilled lists (s side then e side); counters[b][2] = used
+    int pool_cap;
     float* l_score;     // [B][pair_cap]
     int* l_edge;        // [B][pair_cap]
     uint8_t* out;       // [B][lay.total]
@@ -65,6 +74,7 @@ struct PostParams {
 
 size_t post_nms_smem(const PostParams& p);
 size_t post_lines_smem(const PostParams& p);
+size_t post_lines_fixed_smem(int max_kp, int pair_words);
 cudaError_t post_init_attrs(const PostParams& p);
 // each returns the number of kernels it launched through *launches (added)
 cudaError_t post_keypoints_launch(const PostParams& p, cudaStream_t st, long long* launches);  // scan + NMS + top-k
