@@ -277,6 +277,8 @@ static int add_tc_layer(ppg_ctx* c, const Blob& blob, const char* name, const st
     PPG_CUDA(c, cudaMemcpy(li.w, hw.data(), hw.size() * sizeof(__half), cudaMemcpyHostToDevice));
     PPG_CUDA(c, cudaMemcpy(li.bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
     conv_tc_plan(li.L, c->maxB, H, W, cin, N, taps, mode, relu, li.bias, out, out_ld);
+    memset(&li.L.hb, 0, sizeof(li.L.hb));
+    memcpy(li.L.hb.v, hb.data(), hb.size() * sizeof(float));
     if (!make_act_map(&li.L.mapA, in, c->maxB, H, W, cin, li.L.box_w, li.L.box_h) ||
         !make_kmajor_map(&li.L.mapB, li.w, (uint64_t)taps * N, cin, (uint32_t)N, false))
         return set_err(c, PPG_ERR_CUDA, std::string("cuTensorMapEncodeTiled failed for ") + name);
@@ -388,7 +390,7 @@ void ppg_destroy(ppg_ctx* c) {
                     c->a1,   c->a2,      c->a3,       c->a4,       c->a5,         c->a6,         c->a7,
                     c->feat, c->p1,      c->d1,       c->e1,       c->e2,         c->jlogits,    c->desc,
                     c->prob, c->heat_raw, c->heat_ref, c->heat_final, c->prob_in,  c->heat_in,    c->desc_in,
-                    c->undist_lut, c->remap_lut, c->d_out, c->post.state, c->post.cand, c->post.counters,
+                    c->undist_lut, c->remap_lut, c->d_out, c->post.state, c->post.state2, c->post.cand, c->post.counters,
                     c->post.pair_bits, c->post.row_cnt, c->post.l_score, c->post.l_edge, c->post.row_prefix,
                     c->post.row_off, c->post.c_se, c->post.c_dist, c->post.c_dirf, c->post.c_dirb, c->post.inter,
                     c->post.inter_cnt, c->post.inter_off, c->post.inter_pool};
@@ -609,7 +611,12 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
     p.desc = c->desc;
     p.undist_lut = c->undist_lut;
     p.remap_lut = c->remap_lut;
-    p.acc_cap = 8192;
+    post_plan_nms(p);
+    if (const char* e = getenv("PPG_NMS_GLOBAL"))  // A/B switch: force the global-memory NMS variant
+        if (atoi(e)) {
+            p.nms_smem = 0;
+            p.acc_cap = 8192;
+        }
     p.pair_words = (p.max_kp + 31) / 32;
     p.pair_cap = 16384;
     {
@@ -622,6 +629,7 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
     }
     p.lay = make_out_layout(p.max_kp, cfg->max_edges, cfg->max_colines);
     PPG_CUDA(c, dalloc(&p.state, B * HW));
+    PPG_CUDA(c, dalloc(&p.state2, B * HW / 4 + 16));
     PPG_CUDA(c, dalloc(&p.cand, B * HW));
     PPG_CUDA(c, dalloc(&p.counters, (size_t)B * 8));
     PPG_CUDA(c, dalloc(&p.pair_bits, (size_t)B * p.max_kp * p.pair_words));

@@ -31,12 +31,12 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // Epilogue of one 16-channel group of one output pixel (one thread = one pixel = one TMEM lane).
 // XL / YL: lane-xor distance of the x / y neighbour inside the warp (for the fused 2x2 max-pool).
 template <int XL, int YL>
-__device__ __forceinline__ void epilogue_store(const ConvTcParams& p, const float* sbias, const uint32_t (&r)[16],
+__device__ __forceinline__ void epilogue_store(const ConvTcParams& p, const ConvBias& cb, const uint32_t (&r)[16],
                                                int c0, int n, int y, int x, bool inb, int lane) {
     float v[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-        v[j] = __uint_as_float(r[j]) + sbias[c0 + j];
+        v[j] = __uint_as_float(r[j]) + cb.v[c0 + j];
         if (p.relu) v[j] = fmaxf(v[j], 0.f);
     }
     if (p.mode == EPI_F16) {
@@ -90,9 +90,83 @@ __device__ __forceinline__ void epilogue_store(const ConvTcParams& p, const floa
     }
 }
 
+// Epilogue of 64 channels of one output pixel (halo kernel).  No shared-memory traffic at all: the bias comes from
+// the constant bank, and the fused 2x2 max-pool is a reduce-scatter over the 4 lanes of a pool window (48 SHFL per
+// thread instead of 128): after the exchange with the x neighbour a lane keeps 32 of the 64 channels, after the y
+// neighbour 16, and every lane stores the 16 channels it ends up with.  max commutes with the monotone
+// x -> fp16(relu(x)), so pooling the fp32 sums (bias already added) first gives bit-identical results.
+template <int XL, int YL>
+__device__ __forceinline__ void epilogue64(const ConvTcParams& p, const ConvBias& cb, const uint32_t (&r)[64], int c0,
+                                           int n, int y, int x, bool inb, int lane) {
+    float v[64];
+#pragma unroll
+    for (int j = 0; j < 64; j++) v[j] = __uint_as_float(r[j]) + cb.v[c0 + j];
+    if (p.mode == EPI_F16_POOL) {
+        const bool hx = (lane & XL) != 0, hy = (lane & YL) != 0;
+        float a[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const float keep = hx ? v[32 + j] : v[j], send = hx ? v[j] : v[32 + j];
+            a[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, XL));
+        }
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const float keep = hy ? a[16 + j] : a[j], send = hy ? a[j] : a[16 + j];
+            o[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, YL));
+            if (p.relu) o[j] = fmaxf(o[j], 0.f);
+        }
+        const int Ho = p.H >> 1, Wo = p.W >> 1, yo = y >> 1, xo = x >> 1;
+        if (yo < Ho && xo < Wo) {
+            __half* dst = reinterpret_cast<__half*>(p.out) + ((size_t)(n * Ho + yo) * Wo + xo) * p.out_ld + c0 +
+                          (hx ? 32 : 0) + (hy ? 16 : 0);
+            reinterpret_cast<uint4*>(dst)[0] = make_uint4(pack_half2(o[0], o[1]), pack_half2(o[2], o[3]),
+                                                          pack_half2(o[4], o[5]), pack_half2(o[6], o[7]));
+            reinterpret_cast<uint4*>(dst)[1] = make_uint4(pack_half2(o[8], o[9]), pack_half2(o[10], o[11]),
+                                                          pack_half2(o[12], o[13]), pack_half2(o[14], o[15]));
+        }
+        return;
+    }
+    if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 64; j++) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (!inb) return;
+    if (p.mode == EPI_F16) {
+        __half* dst = reinterpret_cast<__half*>(p.out) + ((size_t)(n * p.H + y) * p.W + x) * p.out_ld + c0;
+#pragma unroll
+        for (int g = 0; g < 8; g++)
+            reinterpret_cast<uint4*>(dst)[g] =
+                make_uint4(pack_half2(v[8 * g], v[8 * g + 1]), pack_half2(v[8 * g + 2], v[8 * g + 3]),
+                           pack_half2(v[8 * g + 4], v[8 * g + 5]), pack_half2(v[8 * g + 6], v[8 * g + 7]));
+    } else if (p.mode == EPI_F16_PS2) {
+        // out[2y+i][2x+j][c] = in[y][x][4c + 2i + j]  (torch.pixel_shuffle(2)); 16 output channels per 64 inputs
+        const int Ho = p.H * 2, Wo = p.W * 2;
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int jj = 0; jj < 2; jj++) {
+                const int s4 = 2 * i + jj;
+                __half* dst = reinterpret_cast<__half*>(p.out) +
+                              ((size_t)(n * Ho + 2 * y + i) * Wo + 2 * x + jj) * p.out_ld + (c0 >> 2);
+                reinterpret_cast<uint4*>(dst)[0] =
+                    make_uint4(pack_half2(v[s4], v[4 + s4]), pack_half2(v[8 + s4], v[12 + s4]),
+                               pack_half2(v[16 + s4], v[20 + s4]), pack_half2(v[24 + s4], v[28 + s4]));
+                reinterpret_cast<uint4*>(dst)[1] =
+                    make_uint4(pack_half2(v[32 + s4], v[36 + s4]), pack_half2(v[40 + s4], v[44 + s4]),
+                               pack_half2(v[48 + s4], v[52 + s4]), pack_half2(v[56 + s4], v[60 + s4]));
+            }
+    } else {  // EPI_F32
+        float* dst = reinterpret_cast<float*>(p.out) + ((size_t)(n * p.H + y) * p.W + x) * p.out_ld + c0;
+#pragma unroll
+        for (int g = 0; g < 16; g++)
+            reinterpret_cast<float4*>(dst)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    }
+}
+
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const ConvTcParams p) {
+               const ConvTcParams p, const __grid_constant__ ConvBias cb) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operands need 1024-byte aligned tiles.
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -103,7 +177,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint64_t* tfull = empty + 8;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -124,7 +197,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         ptx::tmem_alloc(tmem_slot, 512);
         ptx::tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < p.N; i += blockDim.x) sbias[i] = p.bias[i];
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -196,7 +268,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 uint32_t r[16];
                 ptx::tmem_ld16(taddr + c0, r);
                 ptx::tmem_ld_wait();
-                epilogue_store<1, 16>(p, sbias, r, c0, t.n, y, x, inb, lane);
+                epilogue_store<1, 16>(p, cb, r, c0, t.n, y, x, inb, lane);
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -230,7 +302,8 @@ struct Conv2Smem {
 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                const ConvTcParams p, const int halo_pitch, const int halo_stage_bytes, const int base_off_mode) {
+                const ConvTcParams p, const __grid_constant__ ConvBias cb, const int halo_pitch,
+                const int halo_stage_bytes, const int base_off_mode) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     const int S = p.stages;
@@ -243,7 +316,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     uint64_t* tempty = tfull + 2;
     uint64_t* wbar = tempty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
-    float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tmem_cols = p.N <= 64 ? 128u : 256u;  // two accumulators of N columns
@@ -266,7 +338,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         ptx::tmem_alloc(tmem_slot, tmem_cols);
         ptx::tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < p.N; i += blockDim.x) sbias[i] = p.bias[i];
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -337,11 +408,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             ptx::mbar_wait(&tfull[acc], aph);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.N;
-            for (int c0 = 0; c0 < p.N; c0 += 16) {
-                uint32_t r[16];
-                ptx::tmem_ld16(taddr + c0, r);
+            for (int c0 = 0; c0 < p.N; c0 += 64) {
+                uint32_t r[64];
+                ptx::tmem_ld64(taddr + c0, r);
                 ptx::tmem_ld_wait();
-                epilogue_store<1, 8>(p, sbias, r, c0, n, y, x, inb, lane);
+                epilogue64<1, 8>(p, cb, r, c0, n, y, x, inb, lane);
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -379,7 +450,7 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
     // address bits, so a descriptor may start at any 128-byte row of a swizzled tile with base_offset = 0.
     int v2mode = 1;
     if (const char* e = getenv("PPG_CONV_V2")) v2mode = atoi(e);
-    L.v2 = (v2mode != 0 && taps == 9 && cin == 64 && cout_padded <= 128) ? 1 : 0;
+    L.v2 = (v2mode != 0 && taps == 9 && cin == 64 && cout_padded <= 128 && cout_padded % 64 == 0) ? 1 : 0;
     if (L.v2) {
         L.halo_pitch = CONV2_TILE_W + 2;
         L.base_off_mode = 0;
@@ -426,10 +497,10 @@ cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStrea
     if (grid <= 0) return cudaSuccess;
     if (L.v2) {
         const int stage = (L.halo_pitch * L.box_h * 128 + 1023) / 1024 * 1024;
-        conv_tc2_kernel<<<grid, CONV_THREADS, L.smem_bytes, st>>>(L.mapA, L.mapB, p, L.halo_pitch, stage,
+        conv_tc2_kernel<<<grid, CONV_THREADS, L.smem_bytes, st>>>(L.mapA, L.mapB, p, L.hb, L.halo_pitch, stage,
                                                                   L.base_off_mode);
     } else {
-        conv_tc_kernel<<<grid, CONV_THREADS, L.smem_bytes, st>>>(L.mapA, L.mapB, p);
+        conv_tc_kernel<<<grid, CONV_THREADS, L.smem_bytes, st>>>(L.mapA, L.mapB, p, L.hb);
     }
     return cudaGetLastError();
 }

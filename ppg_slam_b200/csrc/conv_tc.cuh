@@ -39,9 +39,18 @@ struct ConvTcParams {
     int out_ld;        // channels per output pixel in the destination tensor
 };
 
+// Bias of one layer, passed BY VALUE as a __grid_constant__ kernel parameter: the epilogue then reads it from the
+// constant bank (LDC / uniform operands) instead of shared memory.  The first ncu captures showed the shared-memory
+// data pipe saturated (tensor-core operand reads 55 % + LDS/SHFL of the epilogue 31 %), so the epilogue must stay
+// off that pipe.
+struct ConvBias {
+    float v[256];
+};
+
 struct ConvLayer {
     CUtensorMap mapA, mapB;
     ConvTcParams p;
+    ConvBias hb;        // host copy of the (padded) bias, see above
     int smem_bytes;
     int cin, cout;
     // v2 ("halo") kernel: 3x3, Cin = 64, weights resident in shared memory, one TMA halo tile per output tile

@@ -9,19 +9,18 @@
 namespace ppg {
 
 // ------------------------------------------------------------------------------------------------
-// conv1a: 8 threads per pixel, each produces 8 output channels (one 16-byte store); a warp writes 512
-// contiguous bytes.  Input tile (+1 halo) staged in shared memory as fp32 already divided by 255.
-__global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t* __restrict__ gray, const float* __restrict__ w,
-                                                     const float* __restrict__ bias, __half* __restrict__ out, int H,
-                                                     int W) {
-    constexpr int TX = 32, TY = 8;  // 256 pixels per block pass, 8 channel-groups -> loop
+// conv1a: 8 threads per pixel column, each owns 8 output channels whose 72 weights live in REGISTERS (the
+// first version read every weight from shared memory: one LDS per FMA, LSU-bound at 4x the FMA time).  A
+// thread walks down TY rows with a sliding 3x3 window, so a pixel costs 3 shared-memory loads and 72 FMAs.
+// One 16-byte store per pixel and thread; a warp writes 4 pixels x 128 B = 512 contiguous bytes.
+// Input tile (+1 halo) staged in shared memory as fp32 already divided by 255.
+__global__ void __launch_bounds__(256, 2) conv1a_kernel(const uint8_t* __restrict__ gray, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, __half* __restrict__ out,
+                                                        int H, int W) {
+    constexpr int TX = 32, TY = 32;
     __shared__ float tile[TY + 2][TX + 2];
-    __shared__ float sw[64 * 9];
-    __shared__ float sb[64];
     const int n = blockIdx.z, x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const uint8_t* g = gray + (size_t)n * H * W;
-    for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
-    if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
     for (int i = threadIdx.x; i < (TY + 2) * (TX + 2); i += blockDim.x) {
         int ty = i / (TX + 2), tx = i - ty * (TX + 2);
         int y = y0 + ty - 1, x = x0 + tx - 1;
@@ -29,118 +28,174 @@ __global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t* __restrict__
         if (y >= 0 && y < H && x >= 0 && x < W) v = __fdiv_rn((float)g[(size_t)y * W + x], 255.0f);  // :151
         tile[ty][tx] = v;
     }
+    const int grp = threadIdx.x & 7, px = threadIdx.x >> 3;
+    float wr[8][9], br[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        br[c] = bias[grp * 8 + c];
+#pragma unroll
+        for (int k = 0; k < 9; k++) wr[c][k] = w[(grp * 8 + c) * 9 + k];
+    }
     __syncthreads();
-    // thread -> (pixel = t/8 + 32*pass, group = t%8)
-    const int grp = threadIdx.x & 7;
-    for (int pass = 0; pass < 8; pass++) {
-        int pix = (threadIdx.x >> 3) + 32 * pass;
-        int py = pix / TX, px = pix - py * TX;
-        int y = y0 + py, x = x0 + px;
-        float in[9];
+    const int x = x0 + px;
+    float r0[3], r1[3], r2[3];
 #pragma unroll
-        for (int ky = 0; ky < 3; ky++)
+    for (int k = 0; k < 3; k++) {
+        r0[k] = tile[0][px + k];
+        r1[k] = tile[1][px + k];
+    }
+    __half* o = out + (((size_t)n * H + y0) * W + x) * 64 + grp * 8;
+#pragma unroll 4
+    for (int py = 0; py < TY; py++) {
 #pragma unroll
-            for (int kx = 0; kx < 3; kx++) in[ky * 3 + kx] = tile[py + ky][px + kx];
+        for (int k = 0; k < 3; k++) r2[k] = tile[py + 2][px + k];
         float acc[8];
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            const float* wc = &sw[(grp * 8 + c) * 9];
-            float a = sb[grp * 8 + c];
+            // same summation order as before: bias, then taps in (ky, kx) raster order
+            float a = br[c];
 #pragma unroll
-            for (int k = 0; k < 9; k++) a = fmaf(in[k], wc[k], a);
+            for (int k = 0; k < 3; k++) a = fmaf(r0[k], wr[c][k], a);
+#pragma unroll
+            for (int k = 0; k < 3; k++) a = fmaf(r1[k], wr[c][3 + k], a);
+#pragma unroll
+            for (int k = 0; k < 3; k++) a = fmaf(r2[k], wr[c][6 + k], a);
             acc[c] = fmaxf(a, 0.f);
         }
-        if (y < H && x < W) {
+        if (y0 + py < H && x < W) {
             __half2 h0 = __floats2half2_rn(acc[0], acc[1]), h1 = __floats2half2_rn(acc[2], acc[3]);
             __half2 h2 = __floats2half2_rn(acc[4], acc[5]), h3 = __floats2half2_rn(acc[6], acc[7]);
             uint4 u = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
                                  *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-            *reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + x) * 64 + grp * 8) = u;
+            *reinterpret_cast<uint4*>(o + (size_t)py * W * 64) = u;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            r0[k] = r1[k];
+            r1[k] = r2[k];
         }
     }
 }
 
 cudaError_t conv1a_launch(const uint8_t* gray, const float* w, const float* bias, __half* out, int B, int H, int W,
                           cudaStream_t st) {
-    dim3 grid((W + 31) / 32, (H + 7) / 8, B);
+    dim3 grid((W + 31) / 32, (H + 31) / 32, B);
     conv1a_kernel<<<grid, 256, 0, st>>>(gray, w, bias, out, H, W);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
-// Edge decoder tail.  in: NHWC fp16, 16 channels at (Hh x Wh) = (H/2 x W/2).  One thread per low-res
-// pixel: 16 conv outputs = 4 channels x 2x2 sub-pixels, then the 4->2 1x1 conv and the 2-way softmax
-// for each of the 4 full-resolution pixels.  w3: [16 out][3][3][16 in] fp32, BN folded.
+// Edge decoder tail.  in: NHWC fp16, 16 channels at (Hh x Wh) = (H/2 x W/2).
+// conv3x3 16->16 is 9 taps of a (16 pixels x 16 ci) x (16 ci x 16 co) product: warp-level mma.sync m16n8k16
+// (fp16 operands, fp32 accumulate) with the A fragments ldmatrix'ed straight out of the fp16 halo tile.  The
+// layer is 0.2 GMAC with N = 16 -- far too small for a tcgen05 tile -- and with the MMAs it is bound by its
+// 4.3 MB/frame of HBM traffic.  The first version (fp32 FMAs, one shared-memory load per FMA) took 0.51 ms per
+// 32 frames.
+// The output-channel order of B is permuted so that thread t = lane%4 of the C fragment holds the four
+// channels {t, 4+t, 8+t, 12+t} = pixel_shuffle(2) sub-pixel (i = t/2, j = t%2); the 4->2 1x1 conv and the
+// 2-way softmax then need no exchange.  w3: [16 out][3][3][16 in] fp32, BN folded.
+__device__ __forceinline__ uint32_t edge_pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
 __global__ void __launch_bounds__(128) edge_tail_kernel(const __half* __restrict__ in, const float* __restrict__ w3,
                                                         const float* __restrict__ b3, const float* __restrict__ w1,
                                                         const float* __restrict__ b1, float* __restrict__ heat,
                                                         int Hh, int Wh) {
-    constexpr int TX = 16, TY = 8;
-    __shared__ float tile[TY + 2][TX + 2][17];  // +1 pad against bank conflicts
-    __shared__ float sw[16 * 9 * 16];
-    __shared__ float sb[16], s1[8], sb1[2];
+    constexpr int TX = 16, TY = 8, PW = TX + 2;
+    // pixel p of the halo tile = 32 bytes; its two 16-byte halves are swapped when (p >> 2) & 1 so that the 8
+    // rows of an ldmatrix 8x8 block (8 consecutive pixels) fall into 8 different 16-byte bank groups
+    __shared__ __align__(16) uint8_t tile[(TY + 2) * PW * 32];
     const int n = blockIdx.z, x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-    for (int i = threadIdx.x; i < 16 * 9 * 16; i += blockDim.x) sw[i] = w3[i];
-    if (threadIdx.x < 16) sb[threadIdx.x] = b3[threadIdx.x];
-    if (threadIdx.x < 8) s1[threadIdx.x] = w1[threadIdx.x];
-    if (threadIdx.x < 2) sb1[threadIdx.x] = b1[threadIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const __half* src = in + (size_t)n * Hh * Wh * 16;
-    for (int i = threadIdx.x; i < (TY + 2) * (TX + 2) * 2; i += blockDim.x) {
-        int half8 = i & 1, pi = i >> 1;
-        int ty = pi / (TX + 2), tx = pi - ty * (TX + 2);
-        int y = y0 + ty - 1, x = x0 + tx - 1;
+    for (int i = threadIdx.x; i < (TY + 2) * PW * 2; i += blockDim.x) {
+        const int half8 = i & 1, pi = i >> 1;
+        const int ty = pi / PW, tx = pi - ty * PW;
+        const int y = y0 + ty - 1, x = x0 + tx - 1;
         uint4 u = make_uint4(0, 0, 0, 0);
         if (y >= 0 && y < Hh && x >= 0 && x < Wh)
             u = *reinterpret_cast<const uint4*>(src + ((size_t)y * Wh + x) * 16 + half8 * 8);
-        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            float2 f = __half22float2(h2[k]);
-            tile[ty][tx][half8 * 8 + 2 * k] = f.x;
-            tile[ty][tx][half8 * 8 + 2 * k + 1] = f.y;
-        }
+        *reinterpret_cast<uint4*>(tile + pi * 32 + ((half8 ^ ((pi >> 2) & 1)) << 4)) = u;
     }
-    __syncthreads();
-    const int py = threadIdx.x / TX, px = threadIdx.x - py * TX;
-    const int y = y0 + py, x = x0 + px;
-    float o[16];
+    // B fragments (all 9 taps, both 8-column halves) in registers; column nn of half nh <-> channel
+    // co = 4 * (2 * nh + (nn & 1)) + (nn >> 1)
+    const int t = lane & 3, g = lane >> 2;
+    uint32_t bf[9][2][2];
+    float cb[2][2];
 #pragma unroll
-    for (int co = 0; co < 16; co++) o[co] = sb[co];
-    for (int ky = 0; ky < 3; ky++)
-        for (int kx = 0; kx < 3; kx++) {
-            float iv[16];
+    for (int nh = 0; nh < 2; nh++) {
+        const int co = 4 * (2 * nh + (g & 1)) + (g >> 1);  // B column index = g
+        const float* wc = w3 + (size_t)co * 9 * 16;
 #pragma unroll
-            for (int ci = 0; ci < 16; ci++) iv[ci] = tile[py + ky][px + kx][ci];
-#pragma unroll
-            for (int co = 0; co < 16; co++) {
-                const float* wc = &sw[((co * 3 + ky) * 3 + kx) * 16];
-                float a = o[co];
-#pragma unroll
-                for (int ci = 0; ci < 16; ci++) a = fmaf(iv[ci], wc[ci], a);
-                o[co] = a;
-            }
+        for (int tap = 0; tap < 9; tap++) {
+            bf[tap][nh][0] = edge_pack_h2(wc[tap * 16 + 2 * t], wc[tap * 16 + 2 * t + 1]);
+            bf[tap][nh][1] = edge_pack_h2(wc[tap * 16 + 8 + 2 * t], wc[tap * 16 + 8 + 2 * t + 1]);
         }
-    if (y >= Hh || x >= Wh) return;
+        // C columns of this thread: nn = 2t, 2t+1 -> channels 4*(2nh) + t and 4*(2nh+1) + t
+        cb[nh][0] = b3[4 * (2 * nh) + t];
+        cb[nh][1] = b3[4 * (2 * nh + 1) + t];
+    }
+    float s1[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) s1[k] = w1[k];
+    const float sb10 = b1[0], sb11 = b1[1];
+    __syncthreads();
+    const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(tile);
     const int H = Hh * 2, W = Wh * 2;
     float* dst = heat + (size_t)n * H * W;
+    // ldmatrix.x4: lane l supplies row (l & 7) of matrix (l >> 3); matrices 0/1 = pixels 0-7 / 8-15 of the
+    // channel half 0, matrices 2/3 = the same pixels of channel half 1
+    const int lm_px = ((lane >> 3) & 1) * 8 + (lane & 7), lm_half = lane >> 4;
 #pragma unroll
-    for (int i = 0; i < 2; i++) {
-        float hv[2];
+    for (int mt = 0; mt < 2; mt++) {
+        const int py = warp * 2 + mt;
+        float acc[2][4];
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            // pixel_shuffle(2): full-res channel c at (2y+i, 2x+j) = low-res channel 4c + 2i + j
-            float l0 = sb1[0], l1 = sb1[1];
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                float v = fmaxf(o[4 * c + 2 * i + j], 0.f);
-                l0 = fmaf(s1[c], v, l0);
-                l1 = fmaf(s1[4 + c], v, l1);
-            }
-            float m = fmaxf(l0, l1);
-            float e0 = expf(l0 - m), e1 = expf(l1 - m);
-            hv[j] = e1 / (e0 + e1);  // softmax(dim=1)[:,1], PPGExtractor.cpp:242
+        for (int nh = 0; nh < 2; nh++) {
+            acc[nh][0] = cb[nh][0];
+            acc[nh][1] = cb[nh][1];
+            acc[nh][2] = cb[nh][0];
+            acc[nh][3] = cb[nh][1];
         }
-        *reinterpret_cast<float2*>(dst + (size_t)(2 * y + i) * W + 2 * x) = make_float2(hv[0], hv[1]);
+#pragma unroll
+        for (int tap = 0; tap < 9; tap++) {
+            const int pi = (py + tap / 3) * PW + lm_px + tap % 3;
+            const uint32_t addr = tile_addr + pi * 32 + ((lm_half ^ ((pi >> 2) & 1)) << 4);
+            uint32_t a0, a1, a2, a3;
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                         : "r"(addr));
+#pragma unroll
+            for (int nh = 0; nh < 2; nh++)
+                asm volatile(
+                    "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+                    "{%0,%1,%2,%3};"
+                    : "+f"(acc[nh][0]), "+f"(acc[nh][1]), "+f"(acc[nh][2]), "+f"(acc[nh][3])
+                    : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf[tap][nh][0]), "r"(bf[tap][nh][1]));
+        }
+        const int y = y0 + py;
+#pragma unroll
+        for (int r = 0; r < 2; r++) {  // C rows g and g + 8
+            const int x = x0 + g + 8 * r;
+            // channels 4c + t for c = 0..3
+            const float v0 = fmaxf(acc[0][2 * r], 0.f), v1 = fmaxf(acc[0][2 * r + 1], 0.f);
+            const float v2 = fmaxf(acc[1][2 * r], 0.f), v3 = fmaxf(acc[1][2 * r + 1], 0.f);
+            float l0 = sb10, l1 = sb11;
+            l0 = fmaf(s1[0], v0, l0);
+            l1 = fmaf(s1[4], v0, l1);
+            l0 = fmaf(s1[1], v1, l0);
+            l1 = fmaf(s1[5], v1, l1);
+            l0 = fmaf(s1[2], v2, l0);
+            l1 = fmaf(s1[6], v2, l1);
+            l0 = fmaf(s1[3], v3, l0);
+            l1 = fmaf(s1[7], v3, l1);
+            const float m = fmaxf(l0, l1);
+            const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+            // pixel_shuffle(2): sub-pixel (i, j) = (t >> 1, t & 1); softmax(dim=1)[:,1], PPGExtractor.cpp:242
+            if (y < Hh && x < Wh) dst[(size_t)(2 * y + (t >> 1)) * W + 2 * x + (t & 1)] = e1 / (e0 + e1);
+        }
     }
 }
 

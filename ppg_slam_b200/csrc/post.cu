@@ -86,7 +86,13 @@ __global__ void __launch_bounds__(256) scan_kernel(const PostParams p) {
                 idxs[c++] = pix + k;
             }
         }
-        *reinterpret_cast<uint32_t*>(p.state + (size_t)b * HW + pix) = st;
+        if (p.nms_smem) {
+            // 2 bits per pixel, 4 pixels per byte (pixel k of the quad in bits 2k..2k+1)
+            const uint32_t packed = (st & 1u) | ((st >> 6) & 4u) | ((st >> 12) & 16u) | ((st >> 18) & 64u);
+            p.state2[(size_t)b * (HW / 4) + q] = (uint8_t)packed;
+        } else {
+            *reinterpret_cast<uint32_t*>(p.state + (size_t)b * HW + pix) = st;
+        }
     }
     // warp-aggregated append
     const int inc = warp_incl_scan(c, lane);
@@ -115,7 +121,79 @@ __global__ void __launch_bounds__(256) scan_kernel(const PostParams p) {
 // final and only read other final decisions), so stale reads are benign.  Priority = (score desc,
 // raster index asc) -- the stable order the oracle uses for std::sort ties.  The 500 cap (:196-197) only
 // truncates the walk, so it is applied afterwards on the ranked survivors.
-__global__ void __launch_bounds__(1024) nms_kernel(const PostParams p) {
+// Rank the NMS survivors (bitonic sort of (~score, index) keys = score desc, raster asc), keep the first max_kp
+// (:196-197), undistort them through the LUT and write the keypoint SoA + header of the frame record.
+__device__ void nms_finish(const PostParams& p, int b, unsigned long long* keys, int nacc_all, int ovf, int rounds) {
+    const int tid = threadIdx.x, W = p.W;
+    int nacc = nacc_all;
+    int* hdr = hdr_of(p, b);
+    if (nacc > p.acc_cap) nacc = p.acc_cap;
+    // bitonic sort of the survivors' keys (ascending = score desc, index asc)
+    int P = 1;
+    while (P < nacc) P <<= 1;
+    for (int t = nacc + tid; t < P; t += blockDim.x) keys[t] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < P; t += blockDim.x) {
+                const int u = t ^ j;
+                if (u > t) {
+                    const bool asc = (t & k) == 0;
+                    const unsigned long long a = keys[t], c = keys[u];
+                    if ((a > c) == asc) {
+                        keys[t] = c;
+                        keys[u] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    const int nkp = nacc < p.max_kp ? nacc : p.max_kp;
+    float* kp_x = out_of<float>(p, b, p.lay.kp_x);
+    float* kp_y = out_of<float>(p, b, p.lay.kp_y);
+    int* opx = out_of<int>(p, b, p.lay.px);
+    int* opy = out_of<int>(p, b, p.lay.py);
+    float* osc = out_of<float>(p, b, p.lay.score);
+    float* oxu = out_of<float>(p, b, p.lay.xun);
+    float* oyu = out_of<float>(p, b, p.lay.yun);
+    uint8_t* oout = out_of<uint8_t>(p, b, p.lay.kout);
+    for (int t = tid; t < nkp; t += blockDim.x) {
+        const unsigned long long key = keys[t];
+        const int idx = (int)(unsigned)(key & 0xffffffffull);
+        const float s = __uint_as_float(~(unsigned)(key >> 32));
+        const int y = idx / W, x = idx - y * W;
+        const float2 un = p.undist_lut[idx];  // cv::[fisheye::]undistortPoints of the integer pixel, :220-223
+        uint8_t o = 1;                        // KeyPointEx ctor: mbOut(true)
+        if (un.x >= 1.f && un.x < (float)(p.W - 1) && un.y >= 1.f && un.y < (float)(p.H - 1)) o = 0;  // :230
+        opx[t] = x;
+        opy[t] = y;
+        osc[t] = s;
+        oxu[t] = un.x;
+        oyu[t] = un.y;
+        oout[t] = o;
+        if (p.fisheye) {  // run(): pinhole only mPos <- mPosUn (:141-145)
+            kp_x[t] = (float)x;
+            kp_y[t] = (float)y;
+        } else {
+            kp_x[t] = un.x;
+            kp_y[t] = un.y;
+        }
+    }
+    if (tid == 0) {
+        hdr[HDR_NKP] = nkp;
+        hdr[HDR_NEDGES] = 0;
+        hdr[HDR_NCOL] = 0;
+        hdr[HDR_STATUS] = ovf ? ST_OVF_ACCEPT : 0;
+        hdr[HDR_NCAND] = p.counters[b * 8 + 1];
+        hdr[HDR_NACC] = nacc_all;
+        hdr[HDR_NPASS] = 0;
+        hdr[HDR_NLINES] = 0;
+        hdr[HDR_NMS_ROUNDS] = rounds;
+    }
+}
+
+
+__global__ void __launch_bounds__(1024) nms_global_kernel(const PostParams p) {
     extern __shared__ unsigned long long keys[];  // [acc_cap]
     __shared__ int s_remaining, s_nacc, s_ovf;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -174,71 +252,87 @@ __global__ void __launch_bounds__(1024) nms_kernel(const PostParams p) {
         __syncthreads();
         if (rem == 0 || rounds > n + 1) break;
     }
-    int nacc = s_nacc;
-    int* hdr = hdr_of(p, b);
-    if (nacc > p.acc_cap) nacc = p.acc_cap;
-    // bitonic sort of the survivors' keys (ascending = score desc, index asc)
-    int P = 1;
-    while (P < nacc) P <<= 1;
-    for (int t = nacc + tid; t < P; t += blockDim.x) keys[t] = ~0ull;
-    __syncthreads();
-    for (int k = 2; k <= P; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < P; t += blockDim.x) {
-                const int u = t ^ j;
-                if (u > t) {
-                    const bool asc = (t & k) == 0;
-                    const unsigned long long a = keys[t], c = keys[u];
-                    if ((a > c) == asc) {
-                        keys[t] = c;
-                        keys[u] = a;
-                    }
+    nms_finish(p, b, keys, s_nacc, s_ovf, rounds);
+}
+
+// Same fixed point with the per-pixel state held in SHARED memory as 2 bits per pixel (90 KB at 752x480): the
+// global-memory version above spends its time in 81 dependent L2 reads per candidate and round (0.51 ms for 32
+// frames in the first ncu capture).  A 9-pixel row of the window is one 18-bit field of a 64-bit load.
+//   * an ACCEPTED pixel inside the window always has higher priority than an undecided one (it could not have been
+//     accepted while this candidate was neither suppressed nor of lower priority), so it suppresses without a score
+//     comparison;
+//   * only UNDECIDED neighbours need their score (read-only global loads) to know whether to wait for them.
+// Used whenever the bitmap and the ranking keys fit (all shipped shapes except 1024x1024, which takes the kernel above).
+__global__ void __launch_bounds__(1024) nms_smem_kernel(const PostParams p) {
+    extern __shared__ unsigned long long nms_dyn[];
+    __shared__ int s_remaining, s_nacc, s_ovf;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int HW = p.H * p.W, W = p.W, R = p.nms_radius;
+    unsigned long long* keys = nms_dyn;                                   // [acc_cap]
+    uint32_t* st2 = reinterpret_cast<uint32_t*>(nms_dyn + p.acc_cap);     // [HW/16 + 2]
+    const int nwords = HW / 16;
+    const float* prob = p.prob + (size_t)b * HW;
+    const uint32_t* cl = p.cand + (size_t)b * HW;
+    const uint32_t* g2 = reinterpret_cast<const uint32_t*>(p.state2 + (size_t)b * (HW / 4));
+    for (int t = tid; t < nwords + 2; t += blockDim.x) st2[t] = t < nwords ? g2[t] : 0u;
+    int n = p.counters[b * 8 + 0];
+    if (n > HW) n = HW;
+    if (tid == 0) {
+        s_nacc = 0;
+        s_ovf = 0;
+    }
+    const int span = 2 * R + 1;
+    const uint32_t field = (span >= 16) ? 0xffffffffu : ((1u << (2 * span)) - 1u);
+    int rounds = 0;
+    for (;;) {
+        if (tid == 0) s_remaining = 0;
+        __syncthreads();
+        for (int c = tid; c < n; c += blockDim.x) {
+            const int idx = cl[c];
+            if (((st2[idx >> 4] >> ((idx & 15) * 2)) & 3u) != 1u) continue;
+            const float s = __ldg(prob + idx);
+            const int y = idx / W, x = idx - y * W;
+            bool sup = false, wait = false;
+            for (int dy = -R; dy <= R; dy++) {
+                const int p0 = (y + dy) * W + x - R;
+                const int wd = p0 >> 4, sh = (p0 & 15) * 2;
+                const unsigned long long two = (unsigned long long)st2[wd] | ((unsigned long long)st2[wd + 1] << 32);
+                const uint32_t bits = (uint32_t)(two >> sh) & field;
+                const uint32_t lo = bits & 0x55555555u, hi = (bits >> 1) & 0x55555555u;
+                if (hi & ~lo) {  // an accepted neighbour
+                    sup = true;
+                    break;
+                }
+                uint32_t und = lo & ~hi;
+                if (dy == 0) und &= ~(1u << (2 * R));  // the candidate itself
+                while (und && !wait) {
+                    const int k = (__ffs(und) - 1) >> 1;
+                    und &= und - 1;
+                    const int ni = p0 + k;
+                    const float sn = __ldg(prob + ni);
+                    if ((sn > s) || (sn == s && ni < idx)) wait = true;
                 }
             }
-            __syncthreads();
+            if (sup) {
+                atomicOr(&st2[idx >> 4], 2u << ((idx & 15) * 2));  // 01 -> 11 suppressed
+            } else if (!wait) {
+                atomicXor(&st2[idx >> 4], 3u << ((idx & 15) * 2));  // 01 -> 10 accepted
+                const int k = atomicAdd(&s_nacc, 1);
+                if (k < p.acc_cap)
+                    keys[k] = ((unsigned long long)(~__float_as_uint(s)) << 32) | (unsigned)idx;
+                else
+                    s_ovf = 1;
+            } else {
+                atomicAdd(&s_remaining, 1);
+            }
         }
-    const int nkp = nacc < p.max_kp ? nacc : p.max_kp;
-    float* kp_x = out_of<float>(p, b, p.lay.kp_x);
-    float* kp_y = out_of<float>(p, b, p.lay.kp_y);
-    int* opx = out_of<int>(p, b, p.lay.px);
-    int* opy = out_of<int>(p, b, p.lay.py);
-    float* osc = out_of<float>(p, b, p.lay.score);
-    float* oxu = out_of<float>(p, b, p.lay.xun);
-    float* oyu = out_of<float>(p, b, p.lay.yun);
-    uint8_t* oout = out_of<uint8_t>(p, b, p.lay.kout);
-    for (int t = tid; t < nkp; t += blockDim.x) {
-        const unsigned long long key = keys[t];
-        const int idx = (int)(unsigned)(key & 0xffffffffull);
-        const float s = __uint_as_float(~(unsigned)(key >> 32));
-        const int y = idx / W, x = idx - y * W;
-        const float2 un = p.undist_lut[idx];  // cv::[fisheye::]undistortPoints of the integer pixel, :220-223
-        uint8_t o = 1;                        // KeyPointEx ctor: mbOut(true)
-        if (un.x >= 1.f && un.x < (float)(p.W - 1) && un.y >= 1.f && un.y < (float)(p.H - 1)) o = 0;  // :230
-        opx[t] = x;
-        opy[t] = y;
-        osc[t] = s;
-        oxu[t] = un.x;
-        oyu[t] = un.y;
-        oout[t] = o;
-        if (p.fisheye) {  // run(): pinhole only mPos <- mPosUn (:141-145)
-            kp_x[t] = (float)x;
-            kp_y[t] = (float)y;
-        } else {
-            kp_x[t] = un.x;
-            kp_y[t] = un.y;
-        }
+        __syncthreads();
+        rounds++;
+        const int rem = s_remaining;
+        __syncthreads();
+        if (rem == 0 || rounds > n + 1) break;
     }
-    if (tid == 0) {
-        hdr[HDR_NKP] = nkp;
-        hdr[HDR_NEDGES] = 0;
-        hdr[HDR_NCOL] = 0;
-        hdr[HDR_STATUS] = s_ovf ? ST_OVF_ACCEPT : 0;
-        hdr[HDR_NCAND] = p.counters[b * 8 + 1];
-        hdr[HDR_NACC] = s_nacc;
-        hdr[HDR_NPASS] = 0;
-        hdr[HDR_NLINES] = 0;
-        hdr[HDR_NMS_ROUNDS] = rounds;
-    }
+    nms_finish(p, b, keys, s_nacc, s_ovf, rounds);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -730,51 +824,64 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
             c_next += blockDim.x;
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid < 32) {
+            // One warp walks the window in candidate order.  Inside one candidate the entries are independent (each
+            // looks only at its own old line), so lanes 0-7 take the list at s and lanes 8-15 the list at e in one
+            // step: the kills at s always apply, the list at e is scanned only if no live line at s blocks the
+            // candidate (:336-337), and a blocked candidate clears its own bit.
+            const int lane = tid;
             int blocked = 0, ovf = 0;
             for (int k = 0; k < filled; k++) {
                 const uint32_t se = m.seq_se[k];
                 const int i = se & 0xffff, j = se >> 16;
                 const int ci = m.seq_cnt[k] & 0xffff, cj = m.seq_cnt[k] >> 16;
                 const uint32_t off = m.seq_off[k];
-                const uint16_t *ei, *ej;
-                if (off == 0xffffffffu) {
-                    ei = m.seq_ent + (size_t)k * 2 * INTER_K;
-                    ej = ei + INTER_K;
-                } else if (off == 0xfffffffeu) {
+                if (off == 0xfffffffeu) {
                     ovf = 1;
                     continue;
+                }
+                bool blk;
+                if (off == 0xffffffffu) {
+                    const int side = lane >> 3, t = lane & (INTER_K - 1);
+                    const bool valid = lane < 2 * INTER_K && t < (side ? cj : ci);
+                    const int e = valid ? m.seq_ent[(size_t)k * 2 * INTER_K + lane] : 0;
+                    const int pt = side ? j : i, q = e & 0x7fff;
+                    const bool al = valid && alive_bit(m, words, pt, q);
+                    const unsigned mb = __ballot_sync(FULL, al && (e >> 15));
+                    const bool blk_i = (mb & 0x00ffu) != 0;
+                    if (al && !(e >> 15) && (side == 0 || !blk_i)) clear_line(m, words, pt, q);
+                    blk = mb != 0;  // a block at e only counts when s did not block, and then blk_i is set anyway
                 } else {
-                    ei = g_pool + off;
-                    ej = ei + ci;
-                }
-                bool blk = false;
-                for (int t = 0; t < ci; t++) {  // scan of adj[i] (:316-335)
-                    const int e = ei[t];
-                    const int q = e & 0x7fff;
-                    if (!alive_bit(m, words, i, q)) continue;
-                    if (e >> 15)
-                        blk = true;
-                    else
-                        clear_line(m, words, i, q);
-                }
-                if (!blk)
-                    for (int t = 0; t < cj; t++) {  // scan of adj[j] (:338-357), only if not yet overlapping
-                        const int e = ej[t];
+                    bool blk_i = false, blk_j = false;
+                    for (int t0 = 0; t0 < ci; t0 += 32) {  // scan of adj[s] (:316-335)
+                        const int t = t0 + lane;
+                        const int e = t < ci ? g_pool[off + t] : 0;
                         const int q = e & 0x7fff;
-                        if (!alive_bit(m, words, j, q)) continue;
-                        if (e >> 15)
-                            blk = true;
-                        else
-                            clear_line(m, words, j, q);
+                        const bool al = t < ci && alive_bit(m, words, i, q);
+                        if (al && !(e >> 15)) clear_line(m, words, i, q);
+                        blk_i |= __any_sync(FULL, al && (e >> 15));
                     }
+                    if (!blk_i)
+                        for (int t0 = 0; t0 < cj; t0 += 32) {  // scan of adj[e] (:338-357)
+                            const int t = t0 + lane;
+                            const int e = t < cj ? g_pool[off + ci + t] : 0;
+                            const int q = e & 0x7fff;
+                            const bool al = t < cj && alive_bit(m, words, j, q);
+                            if (al && !(e >> 15)) clear_line(m, words, j, q);
+                            blk_j |= __any_sync(FULL, al && (e >> 15));
+                        }
+                    blk = blk_i || blk_j;
+                }
                 if (blk) {
-                    clear_line(m, words, i, j);
+                    if (lane == 0) clear_line(m, words, i, j);
                     blocked++;
                 }
+                __syncwarp();
             }
-            m.ws[40] += blocked;
-            m.ws[41] |= ovf;
+            if (lane == 0) {
+                m.ws[40] += blocked;
+                m.ws[41] |= ovf;
+            }
         }
         __syncthreads();
         c0 = c_next;
@@ -1064,7 +1171,24 @@ OutLayout make_out_layout(int max_kp, int max_edges, int max_col) {
     return L;
 }
 
-size_t post_nms_smem(const PostParams& p) { return (size_t)p.acc_cap * 8; }
+size_t post_nms_smem(const PostParams& p) {
+    return (size_t)p.acc_cap * 8 + (p.nms_smem ? ((size_t)p.H * p.W / 16 + 2) * 4 : 0);
+}
+
+// Chooses the NMS variant for the frame shape: bitmap in shared memory when it fits next to >= 2048 ranking keys.
+void post_plan_nms(PostParams& p) {
+    const size_t budget = 226 * 1024;
+    const size_t bitmap = ((size_t)p.H * p.W / 16 + 2) * 4;
+    p.nms_smem = 0;
+    p.acc_cap = 8192;
+    if ((p.H * p.W) % 16 != 0) return;
+    for (int cap = 8192; cap >= 2048; cap >>= 1)
+        if (bitmap + (size_t)cap * 8 <= budget) {
+            p.nms_smem = 1;
+            p.acc_cap = cap;
+            return;
+        }
+}
 
 size_t post_lines_fixed_smem(int max_kp, int pair_words) {
     size_t s = (size_t)max_kp * pair_words * 4;                     // alive
@@ -1078,7 +1202,8 @@ size_t post_lines_smem(const PostParams& p) {
 }
 
 cudaError_t post_init_attrs(const PostParams& p) {
-    cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_nms_smem(p));
+    cudaError_t e = cudaFuncSetAttribute(p.nms_smem ? nms_smem_kernel : nms_global_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_nms_smem(p));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(lines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_lines_smem(p));
 }
@@ -1089,7 +1214,10 @@ cudaError_t post_keypoints_launch(const PostParams& p, cudaStream_t st, long lon
     if (e != cudaSuccess) return e;
     dim3 g((HW / 4 + 255) / 256, p.B);
     scan_kernel<<<g, 256, 0, st>>>(p);
-    nms_kernel<<<p.B, 1024, post_nms_smem(p), st>>>(p);
+    if (p.nms_smem)
+        nms_smem_kernel<<<p.B, 1024, post_nms_smem(p), st>>>(p);
+    else
+        nms_global_kernel<<<p.B, 1024, post_nms_smem(p), st>>>(p);
     *launches += 2;
     return cudaGetLastError();
 }

@@ -50,6 +50,8 @@ struct PostParams {
     const int2* remap_lut;     // [H*W] fixed-point (sx, sy) = rint(map*32)
     // scratch, per frame
     uint8_t* state;     // [B][H*W]   0 none, 1 undecided candidate, 2 accepted, 3 suppressed
+    uint8_t* state2;    // [B][H*W/4] the same, 2 bits per pixel (shared-memory NMS variant)
+    int nms_smem;       // 1: state2 + nms_smem_kernel, 0: state + nms_global_kernel
     uint32_t* cand;     // [B][H*W]   pixel indices of in-border candidates (unordered)
     int* counters;      // [B][8]     0: candidates in border, 1: pixels >= threshold, 2: inter_pool entries used
     int acc_cap;        // NMS survivors that can be ranked (power of two)
@@ -73,6 +75,7 @@ struct PostParams {
 };
 
 size_t post_nms_smem(const PostParams& p);
+void post_plan_nms(PostParams& p);  // sets nms_smem and acc_cap from H, W
 size_t post_lines_smem(const PostParams& p);
 size_t post_lines_fixed_smem(int max_kp, int pair_words);
 cudaError_t post_init_attrs(const PostParams& p);

@@ -52,7 +52,7 @@ def test_dense_maps_within_tolerance(ex_euroc, net, seed):
 
 
 @pytest.mark.parametrize("cam,seeds", [(cameras.EUROC, [0, 1, 2, 5]), (cameras.TUMVI, [1, 4]),
-                                       (cameras.UMA, [2])], ids=lambda v: getattr(v, "name", str(v)))
+                                       (cameras.UMA, [2]), (cameras.TUMVI1024, [0])], ids=lambda v: getattr(v, "name", str(v)))
 def test_post_bit_exact_from_reference_maps(net, cam, seeds):
     from ppg_slam_b200 import capi
     from tests.parity_util import diff_records, oracle_post
@@ -103,6 +103,30 @@ def test_edge_cases_from_maps():
             bad = diff_records(got, ref)
             assert not bad, "%s: %s" % (name, "; ".join(bad))
         assert e.run_from_maps(cases["empty"][None], heat[None], desc[None])[0]["n_kp"] == 0
+    finally:
+        e.close()
+
+
+def test_nms_global_memory_variant(net, monkeypatch):
+    """Frames whose 2-bit state map does not fit in shared memory (1024x1024) take nms_global_kernel; force it on an
+    EuRoC frame and on the tie / chain cases and require the same bit-exact records."""
+    from ppg_slam_b200 import capi
+    from tests.parity_util import diff_records, oracle_post
+    monkeypatch.setenv("PPG_NMS_GLOBAL", "1")
+    cam = cameras.EUROC
+    H, W = cam.height, cam.width
+    e = capi.Extractor(cam, max_batch=1)
+    try:
+        m = net.forward_u8(synth.frame(1, W, H))
+        ties = np.zeros((H, W), np.float32)
+        ties[40:440:3, 40:700:3] = 0.25
+        ramp = np.zeros((H, W), np.float32)
+        ramp[100, 50:700] = np.linspace(0.1, 0.9, 650).astype(np.float32)
+        for name, prob in (("frame", m["prob"]), ("ties", ties), ("ramp", ramp)):
+            got = e.run_from_maps(prob[None], m["heat"][None], m["desc"][None])[0]
+            ref = oracle_post(cam, prob, m["heat"], m["desc"])
+            bad = diff_records(got, ref)
+            assert not bad, "%s: %s" % (name, "; ".join(bad))
     finally:
         e.close()
 
