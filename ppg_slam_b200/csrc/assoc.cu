@@ -250,39 +250,42 @@ assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // warps 0 and 1: the whole warp runs the (warp-uniform) loop and one elected lane issues the TMA / MMA
+    // instructions, so that their operands stay in uniform registers (see conv_tc.cu)
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int t = t0; t < t1; t++) {
-                const int f = t / m_tiles, mt = t - f * m_tiles;
-                const int n_tiles = (min(p.src.n_of(f), p.ncap) + A_BN - 1) / A_BN;
-                for (int nt = 0; nt < n_tiles; nt++)
-                    for (int kc = 0; kc < 4; kc++, it++) {
-                        const uint32_t s = it % A_STAGES, ph = (it / A_STAGES) & 1;
-                        ptx::mbar_wait(&empty[s], ph ^ 1);
+        uint32_t it = 0;
+        for (int t = t0; t < t1; t++) {
+            const int f = t / m_tiles, mt = t - f * m_tiles;
+            const int n_tiles = (min(p.src.n_of(f), p.ncap) + A_BN - 1) / A_BN;
+            for (int nt = 0; nt < n_tiles; nt++)
+                for (int kc = 0; kc < 4; kc++, it++) {
+                    const uint32_t s = it % A_STAGES, ph = (it / A_STAGES) & 1;
+                    ptx::mbar_wait(&empty[s], ph ^ 1);
+                    if (ptx::elect_one()) {
                         ptx::mbar_expect_tx(&full[s], A_STAGE_BYTES);
                         uint8_t* a = smem + (size_t)s * A_STAGE_BYTES;
                         ptx::tma_load_2d(a, &mapA, &full[s], kc * 64, mt * A_BM);
                         ptx::tma_load_2d(a + 16384, &mapB, &full[s], kc * 64, f * p.ncap + nt * A_BN);
                     }
-            }
+                    __syncwarp();
+                }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = ptx::make_idesc_f16(A_BM, A_BN, 1);
-            uint32_t it = 0, lt = 0;
-            for (int t = t0; t < t1; t++) {
-                const int f = t / m_tiles;
-                const int n_tiles = (min(p.src.n_of(f), p.ncap) + A_BN - 1) / A_BN;
-                for (int nt = 0; nt < n_tiles; nt++, lt++) {
-                    const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
-                    ptx::mbar_wait(&tempty[acc], aph ^ 1);
+        const uint32_t idesc = ptx::make_idesc_f16(A_BM, A_BN, 1);
+        uint32_t it = 0, lt = 0;
+        for (int t = t0; t < t1; t++) {
+            const int f = t / m_tiles;
+            const int n_tiles = (min(p.src.n_of(f), p.ncap) + A_BN - 1) / A_BN;
+            for (int nt = 0; nt < n_tiles; nt++, lt++) {
+                const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
+                ptx::mbar_wait(&tempty[acc], aph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * A_BN;
+                for (int kc = 0; kc < 4; kc++, it++) {
+                    const uint32_t s = it % A_STAGES, ph = (it / A_STAGES) & 1;
+                    ptx::mbar_wait(&full[s], ph);
                     ptx::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc * A_BN;
-                    for (int kc = 0; kc < 4; kc++, it++) {
-                        const uint32_t s = it % A_STAGES, ph = (it / A_STAGES) & 1;
-                        ptx::mbar_wait(&full[s], ph);
-                        ptx::tc_fence_after();
+                    if (ptx::elect_one()) {
                         const uint32_t a_addr = ptx::smem_u32(smem + (size_t)s * A_STAGE_BYTES);
                         const uint64_t adesc = ptx::make_sw128_desc(a_addr);
                         const uint64_t bdesc = ptx::make_sw128_desc(a_addr + 16384);
@@ -290,8 +293,9 @@ assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                         for (int k = 0; k < 4; k++)
                             ptx::umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kc | k) != 0));
                         ptx::umma_commit(&empty[s]);
+                        if (kc == 3) ptx::umma_commit(&tfull[acc]);
                     }
-                    ptx::umma_commit(&tfull[acc]);
+                    __syncwarp();
                 }
             }
         }

@@ -205,41 +205,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                TileCoord t = decode_tile(p, tile);
-                for (int tap = 0; tap < p.taps; tap++) {
-                    int dy = 0, dx = 0;
-                    if (p.taps == 9) {
-                        dy = tap / 3 - 1;
-                        dx = tap - (tap / 3) * 3 - 1;
-                    }
-                    for (int cc = 0; cc < p.cin_chunks; cc++, it++) {
-                        uint32_t s = it % S, ph = (it / S) & 1;
-                        ptx::mbar_wait(&empty[s], ph ^ 1);
+        // The whole warp runs the loop (warp-uniform control flow and operands); only the TMA / MMA instructions
+        // themselves sit under elect.sync.  With `if (lane == 0)` around the loop the compiler cannot prove the
+        // operands uniform and wraps every UTMALDG / UTCHMMA in an R2UR + ELECT + BRA.U.ANY loop (~50 cycles per
+        // MMA in the first version's SASS, more than the 32-cycle MMA itself).
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            TileCoord t = decode_tile(p, tile);
+            for (int tap = 0; tap < p.taps; tap++) {
+                int dy = 0, dx = 0;
+                if (p.taps == 9) {
+                    dy = tap / 3 - 1;
+                    dx = tap - (tap / 3) * 3 - 1;
+                }
+                for (int cc = 0; cc < p.cin_chunks; cc++, it++) {
+                    uint32_t s = it % S, ph = (it / S) & 1;
+                    ptx::mbar_wait(&empty[s], ph ^ 1);
+                    if (ptx::elect_one()) {
                         ptx::mbar_expect_tx(&full[s], stage_bytes);
                         uint8_t* a = smem + (size_t)s * stage_bytes;
                         ptx::tma_load_4d(a, &mapA, &full[s], cc * 64, t.x0 + dx, t.y0 + dy, t.n);
                         ptx::tma_load_2d(a + CONV_A_BYTES, &mapB, &full[s], cc * 64, tap * p.N);
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = ptx::make_idesc_f16(128, p.N, 0);
-            uint32_t it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, lt++) {
-                uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
-                ptx::mbar_wait(&tempty[acc], aph ^ 1);
+        // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+        const uint32_t idesc = ptx::make_idesc_f16(128, p.N, 0);
+        uint32_t it = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, lt++) {
+            uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
+            ptx::mbar_wait(&tempty[acc], aph ^ 1);
+            ptx::tc_fence_after();
+            uint32_t d_tmem = tmem_base + acc * 256;
+            for (int step = 0; step < nsteps; step++, it++) {
+                uint32_t s = it % S, ph = (it / S) & 1;
+                ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
-                uint32_t d_tmem = tmem_base + acc * 256;
-                for (int step = 0; step < nsteps; step++, it++) {
-                    uint32_t s = it % S, ph = (it / S) & 1;
-                    ptx::mbar_wait(&full[s], ph);
-                    ptx::tc_fence_after();
+                if (ptx::elect_one()) {
                     uint32_t a_addr = ptx::smem_u32(smem + (size_t)s * stage_bytes);
                     uint64_t adesc = ptx::make_sw128_desc(a_addr);
                     uint64_t bdesc = ptx::make_sw128_desc(a_addr + CONV_A_BYTES);
@@ -247,17 +252,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     for (int k = 0; k < 4; k++)  // 4 x (K = 16) per 64-channel chunk: +32 B in the swizzle atom
                         ptx::umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((step | k) != 0));
                     ptx::umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+                    if (step == nsteps - 1) ptx::umma_commit(&tfull[acc]);  // accumulator complete
                 }
-                ptx::umma_commit(&tfull[acc]);  // accumulator complete
+                __syncwarp();
             }
         }
     } else {
-        // ===================== epilogue (4 warps, TMEM lane quarter = warp & 3) =====================
-        const int q = warp & 3;
+        // ===================== epilogue (2 groups of 4 warps, TMEM lane quarter = warp & 3) =====================
+        // Group g drains accumulator g, i.e. every second tile: one warp per SM sub-partition runs the dependent
+        // ld -> bias -> pool -> store chain at low IPC, and with a single group that chain, not the MMAs, set the
+        // tile period (tensor pipe 37 % active in the ncu capture).
+        const int q = warp & 3, grp = (warp - 2) >> 2;
         const int row = q * 32 + lane, h = row >> 4, w = row & 15;
         uint32_t lt = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, lt++) {
             uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
+            if ((int)acc != grp) continue;
             TileCoord t = decode_tile(p, tile);
             const int y = t.y0 + h, x = t.x0 + w;
             const bool inb = (y < p.H) && (x < p.W);
@@ -300,10 +310,12 @@ struct Conv2Smem {
     float* sbias;
 };
 
+// flags: bit 0 = issue the MMAs of two consecutive tiles interleaved (independent accumulators back to back);
+// bits 8.. = timing experiments only (wrong results): 0x100 no halo TMA, 0x200 no epilogue work, 0x400 one tap.
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const ConvTcParams p, const __grid_constant__ ConvBias cb, const int halo_pitch,
-                const int halo_stage_bytes, const int base_off_mode) {
+                const int halo_stage_bytes, const int flags) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     const int S = p.stages;
@@ -313,19 +325,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     uint64_t* full = reinterpret_cast<uint64_t*>(shalo + (size_t)S * halo_stage_bytes);
     uint64_t* empty = full + 8;
     uint64_t* tfull = empty + 8;
-    uint64_t* tempty = tfull + 2;
-    uint64_t* wbar = tempty + 2;
+    uint64_t* tempty = tfull + 4;
+    uint64_t* wbar = tempty + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tmem_cols = p.N <= 64 ? 128u : 256u;  // two accumulators of N columns
+    const uint32_t tmem_cols = p.N <= 64 ? 256u : 512u;  // four accumulators of N columns
+    const bool pair_mode = (flags & 1) != 0;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < S; i++) {
             ptx::mbar_init(&full[i], 1);
             ptx::mbar_init(&empty[i], 1);
         }
-        for (int a = 0; a < 2; a++) {
+        for (int a = 0; a < 4; a++) {
             ptx::mbar_init(&tfull[a], 1);
             ptx::mbar_init(&tempty[a], 4);
         }
@@ -351,69 +364,100 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         y0 = ty * CONV2_TILE_H;
         x0 = (r - ty * p.tiles_x) * CONV2_TILE_W;
     };
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...; local index it -> halo stage it % S,
+    // accumulator it & 3 (phase (it >> 2) & 1), epilogue group it & 1
+    const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
+    // warps 0 and 1: the whole warp runs the loop, one elected lane issues (see conv_tc_kernel)
     if (warp == 0) {
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             ptx::mbar_expect_tx(wbar, w_bytes);
             for (int tap = 0; tap < 9; tap++) ptx::tma_load_2d(sw + (size_t)tap * p.N * 128, &mapB, wbar, 0, tap * p.N);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
-                int n, y0, x0;
-                decode(tile, n, y0, x0);
-                const uint32_t s = it % S, ph = (it / S) & 1;
-                ptx::mbar_wait(&empty[s], ph ^ 1);
-                ptx::mbar_expect_tx(&full[s], halo_bytes);
-                ptx::tma_load_4d(shalo + (size_t)s * halo_stage_bytes, &mapA, &full[s], 0, x0 - 1, y0 - 1, n);
+        }
+        __syncwarp();
+        for (int it = 0; it < my_tiles; it++) {
+            int n, y0, x0;
+            decode(blockIdx.x + it * gridDim.x, n, y0, x0);
+            const uint32_t s = it % S, ph = (it / S) & 1;
+            ptx::mbar_wait(&empty[s], ph ^ 1);
+            if (ptx::elect_one()) {
+                if ((flags & 0x100) && it >= S) {
+                    ptx::mbar_arrive(&full[s]);
+                } else {
+                    ptx::mbar_expect_tx(&full[s], halo_bytes);
+                    ptx::tma_load_4d(shalo + (size_t)s * halo_stage_bytes, &mapA, &full[s], 0, x0 - 1, y0 - 1, n);
+                }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             const uint32_t idesc = ptx::make_idesc_f16(128, p.N, 0);
             ptx::mbar_wait(wbar, 0);
             ptx::tc_fence_after();
             const uint32_t w_addr = ptx::smem_u32(sw);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
-                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
-                const uint32_t s = it % S, ph = (it / S) & 1;
-                ptx::mbar_wait(&tempty[acc], aph ^ 1);
-                ptx::mbar_wait(&full[s], ph);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.N;
-                const uint32_t h_addr = ptx::smem_u32(shalo + (size_t)s * halo_stage_bytes);
-#pragma unroll
-                for (int tap = 0; tap < 9; tap++) {
-                    const uint32_t a0 = h_addr + (uint32_t)((tap / 3) * halo_pitch + (tap % 3)) * 128u;
-                    const uint64_t adesc =
-                        ptx::make_sw128_desc_ex(a0, (uint32_t)halo_pitch * 128u, base_off_mode ? (a0 >> 7) & 7u : 0u);
-                    const uint64_t bdesc = ptx::make_sw128_desc(w_addr + (uint32_t)tap * p.N * 128u);
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        ptx::umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((tap | k) != 0));
+            const int ntaps = (flags & 0x400) ? 1 : 9;
+            const int step = pair_mode ? 2 : 1;
+            for (int it = 0; it < my_tiles; it += step) {
+                const int cnt = (pair_mode && it + 1 < my_tiles) ? 2 : 1;
+                uint32_t d_tmem[2], h_addr[2], st[2];
+                for (int u = 0; u < cnt; u++) {
+                    const uint32_t t = it + u, acc = t & 3, aph = (t >> 2) & 1;
+                    st[u] = t % S;
+                    ptx::mbar_wait(&tempty[acc], aph ^ 1);
+                    ptx::mbar_wait(&full[st[u]], (t / S) & 1);
+                    d_tmem[u] = tmem_base + acc * (uint32_t)p.N;
+                    h_addr[u] = ptx::smem_u32(shalo + (size_t)st[u] * halo_stage_bytes);
                 }
-                ptx::umma_commit(&empty[s]);
-                ptx::umma_commit(&tfull[acc]);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                for (int tap = 0; tap < ntaps; tap++) {
+                    const uint32_t toff = (uint32_t)((tap / 3) * halo_pitch + (tap % 3)) * 128u;
+                    const uint64_t bdesc = ptx::make_sw128_desc(w_addr + (uint32_t)tap * p.N * 128u);
+                    const uint64_t adesc0 = ptx::make_sw128_desc_ex(h_addr[0] + toff, (uint32_t)halo_pitch * 128u, 0u);
+                    if (cnt == 2) {
+                        // the two tiles' MMAs alternate: consecutive instructions accumulate into different TMEM
+                        // regions, so neither waits for the previous one's accumulator update
+                        const uint64_t adesc1 =
+                            ptx::make_sw128_desc_ex(h_addr[1] + toff, (uint32_t)halo_pitch * 128u, 0u);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            ptx::umma_f16(d_tmem[0], adesc0 + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((tap | k) != 0));
+                            ptx::umma_f16(d_tmem[1], adesc1 + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((tap | k) != 0));
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            ptx::umma_f16(d_tmem[0], adesc0 + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((tap | k) != 0));
+                    }
+                }
+                for (int u = 0; u < cnt; u++) {
+                    ptx::umma_commit(&empty[st[u]]);
+                    ptx::umma_commit(&tfull[(it + u) & 3]);
+                }
+                }
+                __syncwarp();
             }
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3, grp = (warp - 2) >> 2;  // two epilogue groups, see conv_tc_kernel
         const int row = q * 32 + lane, h = row >> 3, w = row & 7;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
-            const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+        for (int it = grp; it < my_tiles; it += 2) {
+            const uint32_t acc = it & 3, aph = (it >> 2) & 1;
             int n, y0, x0;
-            decode(tile, n, y0, x0);
+            decode(blockIdx.x + it * gridDim.x, n, y0, x0);
             const int y = y0 + h, x = x0 + w;
             const bool inb = (y < p.H) && (x < p.W);
             ptx::mbar_wait(&tfull[acc], aph);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.N;
-            for (int c0 = 0; c0 < p.N; c0 += 64) {
-                uint32_t r[64];
-                ptx::tmem_ld64(taddr + c0, r);
-                ptx::tmem_ld_wait();
-                epilogue64<1, 8>(p, cb, r, c0, n, y, x, inb, lane);
-            }
+            if (!(flags & 0x200))
+                for (int c0 = 0; c0 < p.N; c0 += 64) {
+                    uint32_t r[64];
+                    ptx::tmem_ld64(taddr + c0, r);
+                    ptx::tmem_ld_wait();
+                    epilogue64<1, 8>(p, cb, r, c0, n, y, x, inb, lane);
+                }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
@@ -453,7 +497,8 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
     L.v2 = (v2mode != 0 && taps == 9 && cin == 64 && cout_padded <= 128 && cout_padded % 64 == 0) ? 1 : 0;
     if (L.v2) {
         L.halo_pitch = CONV2_TILE_W + 2;
-        L.base_off_mode = 0;
+        L.flags = 1;  // interleaved tile pairs
+        if (const char* e = getenv("PPG_CONV_FLAGS")) L.flags = (int)strtol(e, nullptr, 0);
         L.box_w = L.halo_pitch;
         L.box_h = CONV2_TILE_H + 2;
         p.tiles_x = (W + CONV2_TILE_W - 1) / CONV2_TILE_W;
@@ -464,11 +509,11 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
         int S = (222 * 1024 - wbytes - 4096) / stage;
         if (S > 6) S = 6;
         p.stages = S;
-        L.smem_bytes = wbytes + S * stage + 1024 + 21 * 8 + 16 + 256 * 4 + 64;
+        L.smem_bytes = wbytes + S * stage + 1024 + 25 * 8 + 16 + 64;
         return;
     }
     L.halo_pitch = 0;
-    L.base_off_mode = 0;
+    L.flags = 0;
     L.box_w = CONV_TILE_W;
     L.box_h = CONV_TILE_H;
     p.tiles_x = (W + CONV_TILE_W - 1) / CONV_TILE_W;
@@ -498,7 +543,7 @@ cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStrea
     if (L.v2) {
         const int stage = (L.halo_pitch * L.box_h * 128 + 1023) / 1024 * 1024;
         conv_tc2_kernel<<<grid, CONV_THREADS, L.smem_bytes, st>>>(L.mapA, L.mapB, p, L.hb, L.halo_pitch, stage,
-                                                                  L.base_off_mode);
+                                                                  L.flags);
     } else {
         conv_tc_kernel<<<grid, CONV_THREADS, L.smem_bytes, st>>>(L.mapA, L.mapB, p, L.hb);
     }

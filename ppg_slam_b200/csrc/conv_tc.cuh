@@ -9,7 +9,8 @@
 //   K step  = 64 input channels of one tap = one 128-byte swizzled smem row per pixel
 // A tiles come straight from the NHWC activation tensor with one 4-D TMA box per (tap, 64-channel
 // chunk); out-of-image coordinates are zero-filled by TMA, which is exactly the conv's zero padding.
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-5 = epilogue.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-5 / 6-9 = epilogue of the
+// even / odd tiles.
 // Two TMEM accumulators (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #pragma once
 #include <cuda.h>
@@ -57,10 +58,10 @@ struct ConvLayer {
     int v2;             // 0 = generic kernel, 1 = halo kernel
     int box_w, box_h;   // TMA box of the activation map (pixels): generic 16 x 8, halo (8+2 | 16) x 18
     int halo_pitch;     // pixels per halo row in shared memory (= box_w)
-    int base_off_mode;  // 1: put (start >> 7) & 7 into the descriptor's base-offset field
+    int flags;          // conv_tc2_kernel flags: bit 0 = interleaved tile pairs; 0x100.. timing experiments
 };
 
-constexpr int CONV_TILE_W = 16, CONV_TILE_H = 8, CONV_A_BYTES = 16384, CONV_THREADS = 192;
+constexpr int CONV_TILE_W = 16, CONV_TILE_H = 8, CONV_A_BYTES = 16384, CONV_THREADS = 320;
 constexpr int CONV2_TILE_W = 8, CONV2_TILE_H = 16;
 
 // Fills stages / tiles / smem size for the given shape. Tensor maps are encoded by the caller (api).

@@ -102,23 +102,13 @@ __device__ __forceinline__ uint32_t edge_pack_h2(float a, float b) {
 __global__ void __launch_bounds__(128) edge_tail_kernel(const __half* __restrict__ in, const float* __restrict__ w3,
                                                         const float* __restrict__ b3, const float* __restrict__ w1,
                                                         const float* __restrict__ b1, float* __restrict__ heat,
-                                                        int Hh, int Wh) {
+                                                        int Hh, int Wh, int tiles_x, int tiles_y,
+                                                        int total_tiles) {
     constexpr int TX = 16, TY = 8, PW = TX + 2;
     // pixel p of the halo tile = 32 bytes; its two 16-byte halves are swapped when (p >> 2) & 1 so that the 8
     // rows of an ldmatrix 8x8 block (8 consecutive pixels) fall into 8 different 16-byte bank groups
     __shared__ __align__(16) uint8_t tile[(TY + 2) * PW * 32];
-    const int n = blockIdx.z, x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const __half* src = in + (size_t)n * Hh * Wh * 16;
-    for (int i = threadIdx.x; i < (TY + 2) * PW * 2; i += blockDim.x) {
-        const int half8 = i & 1, pi = i >> 1;
-        const int ty = pi / PW, tx = pi - ty * PW;
-        const int y = y0 + ty - 1, x = x0 + tx - 1;
-        uint4 u = make_uint4(0, 0, 0, 0);
-        if (y >= 0 && y < Hh && x >= 0 && x < Wh)
-            u = *reinterpret_cast<const uint4*>(src + ((size_t)y * Wh + x) * 16 + half8 * 8);
-        *reinterpret_cast<uint4*>(tile + pi * 32 + ((half8 ^ ((pi >> 2) & 1)) << 4)) = u;
-    }
     // B fragments (all 9 taps, both 8-column halves) in registers; column nn of half nh <-> channel
     // co = 4 * (2 * nh + (nn & 1)) + (nn >> 1)
     const int t = lane & 3, g = lane >> 2;
@@ -141,9 +131,24 @@ __global__ void __launch_bounds__(128) edge_tail_kernel(const __half* __restrict
 #pragma unroll
     for (int k = 0; k < 8; k++) s1[k] = w1[k];
     const float sb10 = b1[0], sb11 = b1[1];
-    __syncthreads();
     const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(tile);
     const int H = Hh * 2, W = Wh * 2;
+    // persistent blocks: the 36 B-fragment registers are built once and reused for every tile of the block
+    for (int tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
+    const int n = tl / (tiles_x * tiles_y), trem = tl - n * tiles_x * tiles_y;
+    const int y0 = (trem / tiles_x) * TY, x0 = (trem % tiles_x) * TX;
+    const __half* src = in + (size_t)n * Hh * Wh * 16;
+    __syncthreads();  // the previous tile's ldmatrix reads are done
+    for (int i = threadIdx.x; i < (TY + 2) * PW * 2; i += blockDim.x) {
+        const int half8 = i & 1, pi = i >> 1;
+        const int ty = pi / PW, tx = pi - ty * PW;
+        const int y = y0 + ty - 1, x = x0 + tx - 1;
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (y >= 0 && y < Hh && x >= 0 && x < Wh)
+            u = *reinterpret_cast<const uint4*>(src + ((size_t)y * Wh + x) * 16 + half8 * 8);
+        *reinterpret_cast<uint4*>(tile + pi * 32 + ((half8 ^ ((pi >> 2) & 1)) << 4)) = u;
+    }
+    __syncthreads();
     float* dst = heat + (size_t)n * H * W;
     // ldmatrix.x4: lane l supplies row (l & 7) of matrix (l >> 3); matrices 0/1 = pixels 0-7 / 8-15 of the
     // channel half 0, matrices 2/3 = the same pixels of channel half 1
@@ -197,12 +202,18 @@ __global__ void __launch_bounds__(128) edge_tail_kernel(const __half* __restrict
             if (y < Hh && x < Wh) dst[(size_t)(2 * y + (t >> 1)) * W + 2 * x + (t & 1)] = e1 / (e0 + e1);
         }
     }
+    }
 }
 
 cudaError_t edge_tail_launch(const __half* in, const float* w3, const float* b3, const float* w1, const float* b1,
                              float* heat, int B, int Hh, int Wh, cudaStream_t st) {
-    dim3 grid((Wh + 15) / 16, (Hh + 7) / 8, B);
-    edge_tail_kernel<<<grid, 128, 0, st>>>(in, w3, b3, w1, b1, heat, Hh, Wh);
+    const int tiles_x = (Wh + 15) / 16, tiles_y = (Hh + 7) / 8, total = tiles_x * tiles_y * B;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = total < sms * 5 ? total : sms * 5;
+    if (grid <= 0) return cudaSuccess;
+    edge_tail_kernel<<<grid, 128, 0, st>>>(in, w3, b3, w1, b1, heat, Hh, Wh, tiles_x, tiles_y, total);
     return cudaGetLastError();
 }
 
