@@ -100,6 +100,8 @@ typedef struct {
     const int32_t* col_off;  /* n_kp + 1 */
     const int32_t* col_pairs;
     const float* desc;       /* n_kp x 256 */
+    int diag[8];             /* SM clock cycles / 16 of the phases of the point-pair graph kernel (diagnostic):
+                                setup, overlap filter, scoring, edges + adjacency, colinearity */
 } ppg_frame_out;
 
 void ppg_default_config(ppg_config* cfg);

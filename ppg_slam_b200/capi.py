@@ -42,7 +42,7 @@ class FrameOut(C.Structure):
                 ("edge_start", C.POINTER(C.c_int32)), ("edge_end", C.POINTER(C.c_int32)),
                 ("edge_score", C.POINTER(C.c_float)), ("conn_off", C.POINTER(C.c_int32)),
                 ("conn_idx", C.POINTER(C.c_int32)), ("col_off", C.POINTER(C.c_int32)),
-                ("col_pairs", C.POINTER(C.c_int32)), ("desc", C.POINTER(C.c_float))]
+                ("col_pairs", C.POINTER(C.c_int32)), ("desc", C.POINTER(C.c_float)), ("diag", C.c_int * 8)]
 
 
 class AssocIn(C.Structure):
@@ -121,7 +121,7 @@ def _frame_to_dict(o):
         edge_score=arr(o.edge_score, E, np.float32), conn_off=conn_off,
         conn_idx=arr(o.conn_idx, int(conn_off[-1]), np.int32), col_off=col_off,
         col_pairs=arr(o.col_pairs, 2 * nc, np.int32).reshape(-1, 2),
-        desc=arr(o.desc, n * 256, np.float32).reshape(-1, 256))
+        desc=arr(o.desc, n * 256, np.float32).reshape(-1, 256), diag=[int(v) for v in o.diag])
 
 
 class Extractor:

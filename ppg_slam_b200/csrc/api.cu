@@ -327,6 +327,7 @@ static void fill_out(const ppg_ctx* c, int f, ppg_frame_out* o) {
     o->col_off = reinterpret_cast<const int32_t*>(base + L.col_off);
     o->col_pairs = reinterpret_cast<const int32_t*>(base + L.col_pairs);
     o->desc = reinterpret_cast<const float*>(base + L.desc);
+    for (int k = 0; k < 8; k++) o->diag[k] = k < HDR_WORDS - HDR_DIAG ? hdr[HDR_DIAG + k] : 0;
 }
 
 // Post-processing launches shared by ppg_run and ppg_extract_from_maps.
@@ -393,7 +394,7 @@ void ppg_destroy(ppg_ctx* c) {
                     c->undist_lut, c->remap_lut, c->d_out, c->post.state, c->post.state2, c->post.cand, c->post.counters,
                     c->post.pair_bits, c->post.row_cnt, c->post.l_score, c->post.l_edge, c->post.row_prefix,
                     c->post.row_off, c->post.c_se, c->post.c_dist, c->post.c_dirf, c->post.c_dirb, c->post.inter,
-                    c->post.inter_cnt, c->post.inter_off, c->post.inter_pool};
+                    c->post.inter_cnt, c->post.inter_off, c->post.inter_pool, c->post.alive_g};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (c->h_gray) cudaFreeHost(c->h_gray);
@@ -640,11 +641,12 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
     PPG_CUDA(c, dalloc(&p.c_dist, (size_t)B * p.pair_cap));
     PPG_CUDA(c, dalloc(&p.c_dirf, (size_t)B * p.pair_cap));
     PPG_CUDA(c, dalloc(&p.c_dirb, (size_t)B * p.pair_cap));
-    PPG_CUDA(c, dalloc(&p.inter, (size_t)B * p.pair_cap * 16));
+    PPG_CUDA(c, dalloc(&p.inter, (size_t)B * p.pair_cap * 32));
     PPG_CUDA(c, dalloc(&p.inter_cnt, (size_t)B * p.pair_cap));
     PPG_CUDA(c, dalloc(&p.inter_off, (size_t)B * p.pair_cap));
     p.pool_cap = p.pair_cap * 8;
     PPG_CUDA(c, dalloc(&p.inter_pool, (size_t)B * p.pool_cap));
+    PPG_CUDA(c, dalloc(&p.alive_g, (size_t)B * p.max_kp * p.pair_words));
     PPG_CUDA(c, dalloc(&p.l_score, (size_t)B * p.pair_cap));
     PPG_CUDA(c, dalloc(&p.l_edge, (size_t)B * p.pair_cap));
     PPG_CUDA(c, dalloc(&c->d_out, (size_t)B * p.lay.total));

@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const PostParams p) {
 //   kill  : distNew <= distOld && distNew*sin(a) < thr   -> the old line becomes bad
 //   block : distOld <  distNew && distOld*sin(a) < thr   -> the new line is not created
 // One warp per candidate; entries = other endpoint q of the old line | type << 15, <= INTER_K per side.
-constexpr int INTER_K = 8;
+constexpr int INTER_K = 16;  // lanes 0-15 <-> list at s, lanes 16-31 <-> list at e in the sequential pass
 
 __device__ __forceinline__ int interact_one(const PostParams& p, const CandTables& T, int b, const int* row_off, int pt,
                                             int q, float dir_new, float dist_new) {
@@ -700,11 +700,19 @@ struct LineSmem {
     float* ky;
     int* ws;           // 48 ints scan scratch / flags
     uint32_t* seq_se;  // [SEQ_WIN] s | e << 16 of the candidates with interactions in the current window
+    uint32_t* seq_own; // [SEQ_WIN] packed alive-bit address of the candidate's own line (see pack_bit)
     uint32_t* seq_cnt; // [SEQ_WIN] entries at s | entries at e << 16
     uint32_t* seq_off; // [SEQ_WIN] pool offset of spilled lists, ~0 = inline
-    uint16_t* seq_ent; // [SEQ_WIN][2*INTER_K] inline lists
+    uint32_t* seq_ent; // [SEQ_WIN][2*INTER_K] inline lists, one packed alive-bit address per entry, ~0 = none
 };
-constexpr int SEQ_WIN = 1024;
+constexpr int SEQ_WIN = 512;  // >= blockDim.x of lines_kernel
+
+// During the sequential pass a line (a,b) owns ONE bit: row min(a,b), column max(a,b) of the alive matrix (the mirror
+// bits are rebuilt afterwards).  Packed address: bit index [0,5), word index [5,31), entry type (1 = block) bit 31.
+__device__ __forceinline__ uint32_t pack_bit(int words, int a, int b2, uint32_t type) {
+    const int lo = a < b2 ? a : b2, hi = a < b2 ? b2 : a;
+    return (type << 31) | ((uint32_t)(lo * words + (hi >> 5)) << 5) | (uint32_t)(hi & 31);
+}
 
 __device__ __forceinline__ LineSmem carve_lines(const PostParams& p, uint8_t* s) {
     LineSmem m;
@@ -714,13 +722,14 @@ __device__ __forceinline__ LineSmem carve_lines(const PostParams& p, uint8_t* s)
     m.kx = reinterpret_cast<float*>(m.row_off + p.max_kp + 1);
     m.ky = m.kx + p.max_kp;
     m.ws = reinterpret_cast<int*>(m.ky + p.max_kp);
-    uintptr_t q = reinterpret_cast<uintptr_t>(m.ws + 48);
-    q = (q + 15) & ~static_cast<uintptr_t>(15);  // seq_ent rows are copied as uint4
-    m.seq_se = reinterpret_cast<uint32_t*>(q);
-    m.seq_cnt = m.seq_se + SEQ_WIN;
+    // plain pointer arithmetic only: an integer round trip would lose the shared address space and turn every
+    // access of the sequential pass into a generic LD/ST
+    m.seq_se = reinterpret_cast<uint32_t*>(m.ws + 48);
+    m.seq_own = m.seq_se + SEQ_WIN;
+    m.seq_cnt = m.seq_own + SEQ_WIN;
     m.seq_off = m.seq_cnt + SEQ_WIN;
-    m.seq_ent = reinterpret_cast<uint16_t*>(m.seq_off + SEQ_WIN);
-    m.adj = m.seq_ent + SEQ_WIN * 2 * INTER_K;
+    m.seq_ent = m.seq_off + SEQ_WIN;
+    m.adj = reinterpret_cast<uint16_t*>(m.seq_ent + SEQ_WIN * 2 * INTER_K);
     return m;
 }
 
@@ -741,33 +750,30 @@ __device__ __forceinline__ void clear_line(const LineSmem& m, int words, int a, 
     atomicAnd(&m.alive[b2 * words + (a >> 5)], ~(1u << (a & 31)));
 }
 
-__global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
+// K11b: one CTA per frame -- phases A and B; the alive matrix goes to global memory for the next two kernels.
+__global__ void __launch_bounds__(512) lines_filter_kernel(const PostParams p) {
     extern __shared__ __align__(16) uint8_t smem_lines[];
     const LineSmem m = carve_lines(p, smem_lines);
     const int b = blockIdx.x, tid = threadIdx.x;
     int* hdr = hdr_of(p, b);
     const int n = hdr[HDR_NKP];
-    int* conn_off = out_of<int>(p, b, p.lay.conn_off);
-    int* col_off = out_of<int>(p, b, p.lay.col_off);
-    if (n == 0) {  // detectLines returns at :239-240; the record carries no edges
-        if (tid == 0) {
-            conn_off[0] = 0;
-            col_off[0] = 0;
-        }
-        return;
-    }
-    const float* heat = p.heat_final + (size_t)b * p.H * p.W;
+    if (n == 0) return;  // detectLines returns at :239-240
     const CandTables T = cand_of(p, b);
     const int words = p.pair_words, nwords = (n + 31) >> 5;
     unsigned status = 0;
+    long long tphase = clock64();
+    int nphase = 0;
+    auto phase_mark = [&]() {  // thread 0 only; diagnostic phase durations in the record header
+        if (tid == 0 && nphase < HDR_WORDS - HDR_DIAG) {
+            const long long t = clock64();
+            hdr[HDR_DIAG + nphase] = (int)((t - tphase) >> 4);
+            tphase = t;
+        }
+        nphase++;
+    };
 
     // ---- A: keypoints, row offsets, symmetric alive matrix
     const int* g_row_off = p.row_off + (size_t)b * (p.max_kp + 1);
-    for (int t = tid; t < n; t += blockDim.x) {
-        m.kx[t] = out_of<float>(p, b, p.lay.xun)[t];
-        m.ky[t] = out_of<float>(p, b, p.lay.yun)[t];
-        m.adj_cnt[t] = 0;
-    }
     for (int t = tid; t <= n; t += blockDim.x) m.row_off[t] = g_row_off[t];
     const uint32_t* bits = p.pair_bits + (size_t)b * p.max_kp * words;
     for (int t = tid; t < n * words; t += blockDim.x) {
@@ -781,17 +787,15 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
         npass = p.pair_cap;
         status |= ST_OVF_PAIRS;
     }
-    for (int c = tid; c < npass; c += blockDim.x) {  // transpose: bit i of row j
-        const uint32_t se = T.se[c];
-        const int i = se & 0xffff, j = se >> 16;
-        atomicOr(&m.alive[j * words + (i >> 5)], 1u << (i & 31));
-    }
     if (tid == 0) {
         m.ws[40] = 0;  // blocked count
         m.ws[41] = 0;  // interaction-list overflow
+        m.ws[42] = 0;  // diagnostic: candidates visited by the sequential pass
+        m.ws[43] = 0;  // diagnostic: of those, lists read from the spill pool
     }
     __syncthreads();
 
+    phase_mark();
     // ---- B: sequential pass over the candidates that interact, window by window
     const uint32_t* g_cnt = p.inter_cnt + (size_t)b * p.pair_cap;
     const uint32_t* g_off = p.inter_off + (size_t)b * p.pair_cap;
@@ -810,14 +814,31 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
             if (cnt != 0) {
                 const int k = filled + ex;
                 const uint32_t off = g_off[c];
+                const uint32_t se = T.se[c];
+                const int i = se & 0xffff, j = se >> 16;
                 m.seq_cnt[k] = cnt;
                 m.seq_off[k] = off;
-                m.seq_se[k] = T.se[c];
+                m.seq_se[k] = se;
+                m.seq_own[k] = pack_bit(words, i, j, 0u);
                 if (off == 0xffffffffu) {
+                    // expand the (other endpoint | type) entries into packed alive-bit addresses here, in parallel,
+                    // so that the one-warp sequential pass below is load -> test -> vote -> clear and nothing else
+                    const int ci = cnt & 0xffff, cj = cnt >> 16;
                     const uint4* src = reinterpret_cast<const uint4*>(g_ent + (size_t)c * 2 * INTER_K);
-                    uint4* dst = reinterpret_cast<uint4*>(m.seq_ent + (size_t)k * 2 * INTER_K);
-                    dst[0] = src[0];
-                    dst[1] = src[1];
+                    uint32_t* dst = m.seq_ent + (size_t)k * 2 * INTER_K;
+#pragma unroll
+                    for (int v4 = 0; v4 < 2 * INTER_K * 2 / 16; v4++) {
+                        const uint4 u = src[v4];
+                        const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int h = 0; h < 8; h++) {
+                            const int t = v4 * 8 + h;
+                            const uint32_t e = (wv[h >> 1] >> ((h & 1) * 16)) & 0xffffu;
+                            const int side = t / INTER_K, tt = t % INTER_K;
+                            const bool valid = tt < (side ? cj : ci);
+                            dst[t] = valid ? pack_bit(words, side ? j : i, (int)(e & 0x7fff), e >> 15) : 0xffffffffu;
+                        }
+                    }
                 }
             }
             filled += tot;
@@ -826,54 +847,66 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
         __syncthreads();
         if (tid < 32) {
             // One warp walks the window in candidate order.  Inside one candidate the entries are independent (each
-            // looks only at its own old line), so lanes 0-7 take the list at s and lanes 8-15 the list at e in one
+            // looks only at its own old line), so lanes 0-15 take the list at s and lanes 16-31 the list at e in one
             // step: the kills at s always apply, the list at e is scanned only if no live line at s blocks the
             // candidate (:336-337), and a blocked candidate clears its own bit.
+            // The next candidate's record is fetched while the current one is resolved: the only loop-carried
+            // dependency is alive-bit load -> ballot -> clear.
             const int lane = tid;
-            int blocked = 0, ovf = 0;
+            int blocked = 0, ovf = 0, nspill = 0;
+            uint32_t n_own = 0, n_off = 0, n_e = 0;
+            if (filled > 0) {
+                n_own = m.seq_own[0];
+                n_off = m.seq_off[0];
+                n_e = m.seq_ent[lane];
+            }
             for (int k = 0; k < filled; k++) {
-                const uint32_t se = m.seq_se[k];
-                const int i = se & 0xffff, j = se >> 16;
-                const int ci = m.seq_cnt[k] & 0xffff, cj = m.seq_cnt[k] >> 16;
-                const uint32_t off = m.seq_off[k];
+                const uint32_t own = n_own, off = n_off, e = n_e;
+                if (k + 1 < filled) {
+                    n_own = m.seq_own[k + 1];
+                    n_off = m.seq_off[k + 1];
+                    n_e = m.seq_ent[(size_t)(k + 1) * 2 * INTER_K + lane];
+                }
                 if (off == 0xfffffffeu) {
                     ovf = 1;
                     continue;
                 }
                 bool blk;
                 if (off == 0xffffffffu) {
-                    const int side = lane >> 3, t = lane & (INTER_K - 1);
-                    const bool valid = lane < 2 * INTER_K && t < (side ? cj : ci);
-                    const int e = valid ? m.seq_ent[(size_t)k * 2 * INTER_K + lane] : 0;
-                    const int pt = side ? j : i, q = e & 0x7fff;
-                    const bool al = valid && alive_bit(m, words, pt, q);
-                    const unsigned mb = __ballot_sync(FULL, al && (e >> 15));
-                    const bool blk_i = (mb & 0x00ffu) != 0;
-                    if (al && !(e >> 15) && (side == 0 || !blk_i)) clear_line(m, words, pt, q);
+                    const bool valid = e != 0xffffffffu;
+                    const uint32_t w = (e >> 5) & 0x3ffffffu, bit = e & 31u;
+                    const bool al = valid && ((m.alive[w] >> bit) & 1u);
+                    const unsigned mb = __ballot_sync(FULL, al && (e >> 31));
+                    const bool blk_i = (mb & ((1u << INTER_K) - 1u)) != 0;
+                    if (al && !(e >> 31) && (lane < INTER_K || !blk_i)) atomicAnd(&m.alive[w], ~(1u << bit));
                     blk = mb != 0;  // a block at e only counts when s did not block, and then blk_i is set anyway
                 } else {
+                    nspill++;
+                    const uint32_t se = m.seq_se[k], cnt2 = m.seq_cnt[k];
+                    const int i = se & 0xffff, j = se >> 16;
+                    const int ci = cnt2 & 0xffff, cj = cnt2 >> 16;
                     bool blk_i = false, blk_j = false;
                     for (int t0 = 0; t0 < ci; t0 += 32) {  // scan of adj[s] (:316-335)
                         const int t = t0 + lane;
-                        const int e = t < ci ? g_pool[off + t] : 0;
-                        const int q = e & 0x7fff;
-                        const bool al = t < ci && alive_bit(m, words, i, q);
-                        if (al && !(e >> 15)) clear_line(m, words, i, q);
-                        blk_i |= __any_sync(FULL, al && (e >> 15));
+                        const uint32_t g = t < ci ? g_pool[off + t] : 0u;
+                        const uint32_t pk = pack_bit(words, i, (int)(g & 0x7fff), 0u);
+                        const bool al = t < ci && ((m.alive[pk >> 5] >> (pk & 31u)) & 1u);
+                        if (al && !(g >> 15)) atomicAnd(&m.alive[pk >> 5], ~(1u << (pk & 31u)));
+                        blk_i |= __any_sync(FULL, al && (g >> 15));
                     }
                     if (!blk_i)
                         for (int t0 = 0; t0 < cj; t0 += 32) {  // scan of adj[e] (:338-357)
                             const int t = t0 + lane;
-                            const int e = t < cj ? g_pool[off + ci + t] : 0;
-                            const int q = e & 0x7fff;
-                            const bool al = t < cj && alive_bit(m, words, j, q);
-                            if (al && !(e >> 15)) clear_line(m, words, j, q);
-                            blk_j |= __any_sync(FULL, al && (e >> 15));
+                            const uint32_t g = t < cj ? g_pool[off + ci + t] : 0u;
+                            const uint32_t pk = pack_bit(words, j, (int)(g & 0x7fff), 0u);
+                            const bool al = t < cj && ((m.alive[pk >> 5] >> (pk & 31u)) & 1u);
+                            if (al && !(g >> 15)) atomicAnd(&m.alive[pk >> 5], ~(1u << (pk & 31u)));
+                            blk_j |= __any_sync(FULL, al && (g >> 15));
                         }
                     blk = blk_i || blk_j;
                 }
                 if (blk) {
-                    if (lane == 0) clear_line(m, words, i, j);
+                    if (lane == 0) atomicAnd(&m.alive[own >> 5], ~(1u << (own & 31u)));
                     blocked++;
                 }
                 __syncwarp();
@@ -881,6 +914,8 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
             if (lane == 0) {
                 m.ws[40] += blocked;
                 m.ws[41] |= ovf;
+                m.ws[42] += filled;
+                m.ws[43] += nspill;
             }
         }
         __syncthreads();
@@ -888,46 +923,141 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
     }
     if (m.ws[41]) status |= ST_OVF_DEGREE;
     const int ncreated = npass - m.ws[40];
-
-    // ---- C: line scoring (:367-389)
-    float* lscore = p.l_score + (size_t)b * p.pair_cap;
-    int* ledge = p.l_edge + (size_t)b * p.pair_cap;
-    for (int c = tid; c < npass; c += blockDim.x) {
+    for (int c = tid; c < npass; c += blockDim.x) {  // mirror bits of the surviving lines: bit s of row e
         const uint32_t se = T.se[c];
-        const int s = se & 0xffff, e = se >> 16;
-        if (!alive_bit(m, words, s, e)) continue;
-        const float psx = m.kx[s], psy = m.ky[s], pex = m.kx[e], pey = m.ky[e];
-        const float dist = T.dist[c];
-        int lenLevel = (int)((double)(dist * p.inv_scale) * 4.0);  // :485
-        if (lenLevel > 3) lenLevel = 3;                            // dist == diagonal cannot happen (points >= 1 px inside)
-        if (lenLevel < 0) lenLevel = 0;
-        const int segNum = (int)(dist * c_inv_gap[lenLevel]);      // :486
-        const float step = (float)(1.0 / (double)(float)segNum);   // :487
-        int cnt = 0;
-        float sum = 0.f;
-        for (int i = 1; i < segNum; i++) {
-            const float qx = (psx * step) * (float)i + (pex * step) * (float)(segNum - i);
-            const float qy = (psy * step) * (float)i + (pey * step) * (float)(segNum - i);
-            const int posx = (int)((double)qx + 0.5), posy = (int)((double)qy + 0.5);
-            if (heat[posy * p.W + posx] > p.line_heatmap_thresh) cnt++;
-            sum += bilinear_heat(heat, p.W, qx, qy);
-        }
-        const float rate = __fdiv_rn((float)cnt, (float)(segNum - 1));  // segNum == 1 -> 0/0 = NaN, accepted (:376)
-        bool bad = false;
-        float sh = 0.f;
-        if (rate < p.line_inlier_rate) {
-            bad = true;
-        } else {
-            sh = __fdiv_rn(sum, (float)(segNum - 1));
-            if (sh < p.line_heatmap_thresh) bad = true;
-        }
-        if (bad)
-            lscore[c] = -INFINITY;  // marker; bits are cleared after the barrier (other threads still read them)
-        else
-            lscore[c] = rate * sh;
-        ledge[c] = bad ? -2 : -1;
+        const int i = se & 0xffff, j = se >> 16;
+        if (alive_bit(m, words, i, j)) atomicOr(&m.alive[j * words + (i >> 5)], 1u << (i & 31));
     }
     __syncthreads();
+    phase_mark();
+    uint32_t* alive_g = p.alive_g + (size_t)b * p.max_kp * words;
+    for (int t = tid; t < n * words; t += blockDim.x) alive_g[t] = m.alive[t];
+    if (tid == 0) {
+        hdr[HDR_DIAG + 5] = m.ws[42];
+        hdr[HDR_DIAG + 6] = m.ws[43];
+        hdr[HDR_STATUS] |= (int)status;
+        hdr[HDR_NPASS] = npass_all;
+        hdr[HDR_NLINES] = ncreated;
+    }
+}
+
+// K12a: line scoring (:367-389) for every surviving candidate of every frame -- one warp per candidate, grid-wide
+// (inside the per-frame CTA this phase took 160 k cycles on 16 warps).  The lanes fetch the samples of the segment in
+// parallel, then the values are added in sample order so that the f32 sum is the reference's sequential one.
+__global__ void __launch_bounds__(256) lines_score_kernel(const PostParams p) {
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int n = hdr_of(p, b)[HDR_NKP];
+    if (n == 0) return;
+    const float* heat = p.heat_final + (size_t)b * p.H * p.W;
+    const CandTables T = cand_of(p, b);
+    const int words = p.pair_words;
+    int npass = p.row_off[(size_t)b * (p.max_kp + 1) + n];
+    if (npass > p.pair_cap) npass = p.pair_cap;
+    const uint32_t* alive_g = p.alive_g + (size_t)b * p.max_kp * words;
+    const float* kxg = out_of<float>(p, b, p.lay.xun);
+    const float* kyg = out_of<float>(p, b, p.lay.yun);
+    float* lscore = p.l_score + (size_t)b * p.pair_cap;
+    int* ledge = p.l_edge + (size_t)b * p.pair_cap;
+    {
+        const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+        for (int c = blockIdx.x * nwarps + warp; c < npass; c += gridDim.x * nwarps) {
+            const uint32_t se = T.se[c];
+            const int s = se & 0xffff, e = se >> 16;
+            if (!((alive_g[s * words + (e >> 5)] >> (e & 31)) & 1u)) continue;
+            const float psx = kxg[s], psy = kyg[s], pex = kxg[e], pey = kyg[e];
+            const float dist = T.dist[c];
+            int lenLevel = (int)((double)(dist * p.inv_scale) * 4.0);  // :485
+            if (lenLevel > 3) lenLevel = 3;  // dist == diagonal cannot happen (points >= 1 px inside)
+            if (lenLevel < 0) lenLevel = 0;
+            const int segNum = (int)(dist * c_inv_gap[lenLevel]);     // :486
+            const float step = (float)(1.0 / (double)(float)segNum);  // :487
+            int cnt = 0;
+            float sum = 0.f;
+            // up to SC_CH x 32 samples are fetched before anything is added (one round of load latency per line)
+            constexpr int SC_CH = 4;
+            for (int i00 = 1; i00 < segNum; i00 += 32 * SC_CH) {
+                float v[SC_CH];
+                bool inl[SC_CH];
+#pragma unroll
+                for (int ch = 0; ch < SC_CH; ch++) {
+                    const int i = i00 + ch * 32 + lane;
+                    v[ch] = 0.f;
+                    inl[ch] = false;
+                    if (i < segNum) {
+                        const float qx = (psx * step) * (float)i + (pex * step) * (float)(segNum - i);
+                        const float qy = (psy * step) * (float)i + (pey * step) * (float)(segNum - i);
+                        const int posx = (int)((double)qx + 0.5), posy = (int)((double)qy + 0.5);
+                        inl[ch] = heat[posy * p.W + posx] > p.line_heatmap_thresh;
+                        v[ch] = bilinear_heat(heat, p.W, qx, qy);
+                    }
+                }
+#pragma unroll
+                for (int ch = 0; ch < SC_CH; ch++) {
+                    const int i0 = i00 + ch * 32;
+                    if (i0 < segNum) {
+                        cnt += __popc(__ballot_sync(FULL, inl[ch]));
+                        const int mm = min(32, segNum - i0);
+                        for (int t = 0; t < mm; t++) sum += __shfl_sync(FULL, v[ch], t);
+                    }
+                }
+            }
+            if (lane == 0) {
+                const float rate = __fdiv_rn((float)cnt, (float)(segNum - 1));  // segNum == 1 -> 0/0 = NaN, accepted (:376)
+                bool bad = false;
+                float sh = 0.f;
+                if (rate < p.line_inlier_rate) {
+                    bad = true;
+                } else {
+                    sh = __fdiv_rn(sum, (float)(segNum - 1));
+                    if (sh < p.line_heatmap_thresh) bad = true;
+                }
+                // bad lines: marker only; lines_graph_kernel clears their bits
+                lscore[c] = bad ? -INFINITY : rate * sh;
+                ledge[c] = bad ? -2 : -1;
+            }
+        }
+    }
+}
+
+// K12b: one CTA per frame -- final edges, mvConnected, colinearity.
+__global__ void __launch_bounds__(512) lines_graph_kernel(const PostParams p) {
+    extern __shared__ __align__(16) uint8_t smem_lines[];
+    const LineSmem m = carve_lines(p, smem_lines);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    int* hdr = hdr_of(p, b);
+    const int n = hdr[HDR_NKP];
+    int* conn_off = out_of<int>(p, b, p.lay.conn_off);
+    int* col_off = out_of<int>(p, b, p.lay.col_off);
+    if (n == 0) {  // detectLines returns at :239-240; the record carries no edges
+        if (tid == 0) {
+            conn_off[0] = 0;
+            col_off[0] = 0;
+        }
+        return;
+    }
+    const CandTables T = cand_of(p, b);
+    const int words = p.pair_words, nwords = (n + 31) >> 5;
+    unsigned status = 0;
+    long long tphase = clock64();
+    int nphase = 3;
+    auto phase_mark = [&]() {  // thread 0 only; diagnostic phase durations in the record header
+        if (tid == 0 && nphase < HDR_WORDS - HDR_DIAG) {
+            const long long t = clock64();
+            hdr[HDR_DIAG + nphase] = (int)((t - tphase) >> 4);
+            tphase = t;
+        }
+        nphase++;
+    };
+    const int* g_row_off = p.row_off + (size_t)b * (p.max_kp + 1);
+    for (int t = tid; t < n; t += blockDim.x) m.adj_cnt[t] = 0;
+    for (int t = tid; t <= n; t += blockDim.x) m.row_off[t] = g_row_off[t];
+    const uint32_t* alive_g = p.alive_g + (size_t)b * p.max_kp * words;
+    for (int t = tid; t < n * words; t += blockDim.x) m.alive[t] = alive_g[t];
+    __syncthreads();
+    int npass = m.row_off[n];
+    if (npass > p.pair_cap) npass = p.pair_cap;
+    float* lscore = p.l_score + (size_t)b * p.pair_cap;
+    int* ledge = p.l_edge + (size_t)b * p.pair_cap;
     for (int c = tid; c < npass; c += blockDim.x) {
         const uint32_t se = T.se[c];
         const int s = se & 0xffff, e = se >> 16;
@@ -1005,6 +1135,7 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
     }
     if (tid == 0) conn_off[n] = ccarry;
 
+    phase_mark();
     // ---- E: colinearity (:392-432), in place on the adjacency row; pair k is parked at row[D-2(k+1)..]
     int ncol_mine = 0;
     int colcarry = 0;
@@ -1070,13 +1201,12 @@ __global__ void __launch_bounds__(512) lines_kernel(const PostParams p) {
         colcarry += tot;
     }
     if (colcarry > p.lay.max_col) status |= ST_OVF_COLINE;
+    phase_mark();
     if (tid == 0) {
         col_off[n] = colcarry;
         hdr[HDR_NEDGES] = nedges;
         hdr[HDR_NCOL] = colcarry;
         hdr[HDR_STATUS] |= (int)status;
-        hdr[HDR_NPASS] = npass_all;
-        hdr[HDR_NLINES] = ncreated;
     }
 }
 
@@ -1193,7 +1323,7 @@ void post_plan_nms(PostParams& p) {
 size_t post_lines_fixed_smem(int max_kp, int pair_words) {
     size_t s = (size_t)max_kp * pair_words * 4;                     // alive
     s += (size_t)(max_kp * 4 + 1) * 4 + 48 * 4 + 16;                // adj_cnt, row_off, kx, ky, ws (+ alignment)
-    s += (size_t)SEQ_WIN * (4 + 4 + 4 + 2 * INTER_K * 2);           // seq_se, seq_cnt, seq_off, seq_ent
+    s += (size_t)SEQ_WIN * (4 + 4 + 4 + 4 + 2 * INTER_K * 4);       // seq_se, seq_own, seq_cnt, seq_off, seq_ent
     return align_up(s, 16);
 }
 
@@ -1205,7 +1335,9 @@ cudaError_t post_init_attrs(const PostParams& p) {
     cudaError_t e = cudaFuncSetAttribute(p.nms_smem ? nms_smem_kernel : nms_global_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_nms_smem(p));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(lines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_lines_smem(p));
+    e = cudaFuncSetAttribute(lines_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_lines_smem(p));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(lines_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_lines_smem(p));
 }
 
 cudaError_t post_keypoints_launch(const PostParams& p, cudaStream_t st, long long* launches) {
@@ -1239,8 +1371,10 @@ cudaError_t post_lines_launch(const PostParams& p, cudaStream_t st, long long* l
     pair_test_kernel<<<g, 256, 0, st>>>(p);
     cand_build_kernel<<<g, 256, 0, st>>>(p);
     interact_kernel<<<dim3((p.pair_cap + 7) / 8, p.B), 256, 0, st>>>(p);
-    lines_kernel<<<p.B, 512, post_lines_smem(p), st>>>(p);
-    *launches += 4;
+    lines_filter_kernel<<<p.B, 512, post_lines_smem(p), st>>>(p);
+    lines_score_kernel<<<dim3(16, p.B), 256, 0, st>>>(p);
+    lines_graph_kernel<<<p.B, 512, post_lines_smem(p), st>>>(p);
+    *launches += 6;
     return cudaGetLastError();
 }
 

@@ -25,6 +25,7 @@ enum HdrField {
     HDR_NPASS = 6,
     HDR_NLINES = 7,
     HDR_NMS_ROUNDS = 8,
+    HDR_DIAG = 9,  // .. 15: phase clocks of lines_kernel
     HDR_WORDS = 16
 };
 
@@ -63,11 +64,12 @@ struct PostParams {
     int pair_cap, deg_cap;
     uint32_t* c_se;     // [B][pair_cap] candidate lines: s | e << 16
     float *c_dist, *c_dirf, *c_dirb;
-    uint16_t* inter;    // [B][pair_cap][16] overlap-filter interactions (8 per endpoint)
+    uint16_t* inter;    // [B][pair_cap][32] overlap-filter interactions (16 per endpoint)
     uint32_t* inter_cnt;  // [B][pair_cap] count at s | count at e << 16
     uint32_t* inter_off;  // [B][pair_cap] offset of a spilled list in inter_pool, ~0 = inline
     uint16_t* inter_pool; // [B][pool_cap] spilled lists (s side then e side); counters[b][2] = used
     int pool_cap;
+    uint32_t* alive_g;  // [B][max_kp][pair_words] symmetric matrix of the lines alive after the overlap filter
     float* l_score;     // [B][pair_cap]
     int* l_edge;        // [B][pair_cap]
     uint8_t* out;       // [B][lay.total]

@@ -86,6 +86,8 @@ def main():
         recs = e.download(B, allow_capacity=True)
         rep["b32_records"] = [[r["n_kp"], r["n_edges"], r["n_colines"], r["status"], r["nms_rounds"],
                                r["n_pairs_ok"], r["n_candidate_lines"]] for r in recs]
+        rep["b32_lines_phase_cycles_x16_mean"] = np.mean([r["diag"] for r in recs], axis=0).tolist()
+        rep["b32_lines_phase_cycles_x16_max"] = np.max([r["diag"] for r in recs], axis=0).tolist()
         e.close()
     except Exception:
         rep["b32_error"] = traceback.format_exc()

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Short deterministic workload for ncu: two batch-32 extract steps + association of 2 frames per step."""
+"""Short deterministic workload for ncu: the bench step (batch-32 extract + batched association vs 8192 map rows),
+one warm-up step through the host path and two device-resident steps."""
 import os
 import sys
 
@@ -7,22 +8,21 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from ppg_slam_b200 import cameras, capi, synth  # noqa: E402
+import bench  # noqa: E402
+from ppg_slam_b200 import capi  # noqa: E402
 
 B = int(os.environ.get("PPG_NCU_BATCH", "32"))
-cam = cameras.EUROC
-frames = [synth.frame(s, cam.width, cam.height) for s in range(B)]
-e = capi.Extractor(cam, max_batch=B, max_map_points=8192)
+cam, frames = bench.make_workload(B)
+e = capi.Extractor(cam, max_batch=B, max_map_points=bench.MAP_ROWS)
 recs = e.run(frames)
-r0 = recs[0]
-inp = synth.association_inputs(17, r0["desc"], np.stack([r0["kp_x"], r0["kp_y"]], 1), 8192, cam.width, cam.height)
-e.upload_map(inp["map_desc"])
-e.assoc_stage(np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros((0, 256), np.float32), np.zeros(0, np.uint8),
-              inp["proj_uv"], inp["view_cos"], 10.0, 0.8)
+map_desc, per_frame = bench.make_assoc_inputs(cam, recs, bench.MAP_ROWS)
+e.upload_map(map_desc)
+proj_all = np.stack([uv for uv, _ in per_frame])
+vcos_all = np.stack([vc for _, vc in per_frame])
+e.assoc_stage_batch(proj_all, vcos_all, bench.TH, bench.RATIO)
 for step in range(2):
     e.run_device(B)
-    for f in range(2):
-        e.assoc_run_frame(f)
+    e.assoc_run_batch(B)
 e.sync()
 print("launches", e.launch_count())
 e.close()
