@@ -24,7 +24,8 @@ namespace ppg {
 
 bool make_kmajor_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, bool bf16);
 
-constexpr int A_BM = 128, A_BN = 128, A_STAGES = 6, A_STAGE_BYTES = 32768, A_THREADS = 192, A_TOPK = 4;
+constexpr int A_BM = 128, A_BN = 128, A_STAGES = 4, A_STAGE_BYTES = 32768, A_THREADS = 320, A_TOPK = 4;
+constexpr int A_QCAP = 32;  // per-thread queue of window hits awaiting the exact mask + top-4 insertion
 constexpr unsigned AFULL = 0xffffffffu;
 
 struct RowParam {  // per map point
@@ -208,7 +209,7 @@ struct GemmParams {
     float* guard;
 };
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(A_THREADS, 1)
 assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -220,7 +221,11 @@ assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     uint64_t* tfull = empty + 8;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float4* kp = reinterpret_cast<float4*>(tmem_slot + 4);  // [ncap] x, y, n2, info(bits) of the current frame
+    // keypoint tables of the current frame: (x, y) and (|b|^2, info bits), [ncap] each
+    float2* kxy = reinterpret_cast<float2*>(tmem_slot + 4);
+    float2* kzi = kxy + p.ncap;
+    float2* qbuf = kzi + p.ncap;                              // [A_QCAP][256] (d2, column) hit queues
+    float* mbuf = reinterpret_cast<float*>(qbuf + A_QCAP * 256);  // [9][128] top-4 lists of column half 1
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (p.rows + A_BM - 1) / A_BM;
@@ -235,7 +240,7 @@ assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&tfull[a], 1);
-            ptx::mbar_init(&tempty[a], 4);
+            ptx::mbar_init(&tempty[a], 8);  // 2 column halves x 4 lane quarters
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&mapA);
@@ -300,24 +305,34 @@ assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             }
         }
     } else {
-        const int q = warp & 3;
-        const int rloc = q * 32 + lane, etid = threadIdx.x - 64;
+        // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =====================
+        // One map row per thread and column half.  The first version ran the whole window mask and the top-4
+        // insertion on every (row, keypoint) element and took 0.87 ms per 32 frames (the MMAs need 0.05 ms).  Now an
+        // element costs four compares against a slightly widened window box; the ~2 % that pass are queued (d2,
+        // column) in shared memory and get the exact mask (in_window) and the insertion once per row.  Both halves
+        // keep a top-4 list + guard under the total order (d2, column); half 1 hands its list to half 0, which merges
+        // and stores.  That order makes the result independent of how the columns are split or queued.
+        const int q = warp & 3, grp = (warp - 2) >> 2;
+        const int rloc = q * 32 + lane, etid = threadIdx.x - 64;  // 0..255
         uint32_t lt = 0;
         int cur_f = -1, n = 0;
         for (int t = t0; t < t1; t++) {
             const int f = t / m_tiles, mt = t - f * m_tiles;
-            if (f != cur_f) {  // (re)load the frame's keypoint table; all four epilogue warps take this branch together
+            if (f != cur_f) {  // (re)load the frame's keypoint tables; all eight epilogue warps take this branch together
                 epi_bar();
                 n = min(p.src.n_of(f), p.ncap);
                 const float* kx = p.src.kx_of(f);
                 const float* ky = p.src.ky_of(f);
                 const int ncols = (n + A_BN - 1) / A_BN * A_BN;
-                for (int i = etid; i < ncols; i += 128) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (i < n)
-                        v = make_float4(kx[i], ky[i], p.fn2[(size_t)f * p.ncap + i],
-                                        __uint_as_float(p.kinfo[(size_t)f * p.ncap + i]));
-                    kp[i] = v;
+                for (int i = etid; i < ncols; i += 256) {
+                    // padding columns sit far outside every window box
+                    float2 xy = make_float2(-1e30f, -1e30f), zi = make_float2(0.f, 0.f);
+                    if (i < n) {
+                        xy = make_float2(kx[i], ky[i]);
+                        zi = make_float2(p.fn2[(size_t)f * p.ncap + i], __uint_as_float(p.kinfo[(size_t)f * p.ncap + i]));
+                    }
+                    kxy[i] = xy;
+                    kzi[i] = zi;
                 }
                 epi_bar();
                 cur_f = f;
@@ -328,46 +343,86 @@ assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             rp.u = rp.v = rp.r = rp.na2 = 0.f;
             rp.cells = 0xffffffffu;
             if (row < p.rows) rp = p.rowp[(size_t)f * p.max_rows + row];
+            // conservative box around |x - u| < r, |y - v| < r (0.01 px covers the rounding of x - u for |x| < 2^13)
+            const bool live = rp.cells != 0xffffffffu;
+            const float xlo = live ? rp.u - rp.r - 0.01f : 1e30f, xhi = rp.u + rp.r + 0.01f;
+            const float ylo = rp.v - rp.r - 0.01f, yhi = rp.v + rp.r + 0.01f;
             float bd[A_TOPK];
             int bi[A_TOPK];
 #pragma unroll
             for (int k = 0; k < A_TOPK; k++) {
                 bd[k] = INFINITY;
-                bi[k] = -1;
+                bi[k] = 0x7fffffff;
             }
             float a5 = INFINITY;
-            for (int nt = 0; nt < n_tiles; nt++, lt++) {
+            auto insert = [&](float d2, int col) {
+                if (d2 < bd[A_TOPK - 1] || (d2 == bd[A_TOPK - 1] && col < bi[A_TOPK - 1])) {
+                    a5 = fminf(a5, bd[A_TOPK - 1]);  // the displaced 4th best (min: a5 may be the -inf overflow mark)
+                    float cd = d2;
+                    int ci = col;
+#pragma unroll
+                    for (int k = 0; k < A_TOPK; k++) {
+                        if (cd < bd[k] || (cd == bd[k] && ci < bi[k])) {
+                            const float td = bd[k];
+                            const int ti = bi[k];
+                            bd[k] = cd;
+                            bi[k] = ci;
+                            cd = td;
+                            ci = ti;
+                        }
+                    }
+                } else if (d2 < a5) {
+                    a5 = d2;
+                }
+            };
+            // Hits are queued as (raw accumulator, column) and drained (exact mask + insertion) whenever fewer than 16
+            // slots are left before a 16-column chunk, and at the end of the row.  The scan loop is deliberately NOT
+            // fully unrolled and the drain exists once: the first queue version inlined it 64 times and ran at 0.07
+            // IPC on instruction-cache misses (stall_no_instruction 9.9 per issue in the ncu capture).
+            int qcnt = 0;
+            auto drain = [&]() {
+#pragma unroll 1
+                for (int sidx = 0; sidx < qcnt; sidx++) {
+                    const float2 e = qbuf[sidx * 256 + etid];
+                    const int col = __float_as_int(e.y);
+                    const float2 xy = kxy[col], zi = kzi[col];
+                    if (in_window(rp, __float_as_uint(zi.y), xy.x, xy.y)) insert((rp.na2 + zi.x) - 2.0f * e.x, col);
+                }
+                qcnt = 0;
+            };
+            for (int nt = 0; nt <= n_tiles; nt++) {
+                if (nt == n_tiles) {  // same call site for the final drain: one copy of the code
+                    drain();
+                    break;
+                }
                 const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
+                lt++;
                 ptx::mbar_wait(&tfull[acc], aph);
                 ptx::tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * A_BN;
-                for (int c0 = 0; c0 < A_BN; c0 += 16) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * A_BN + grp * 64;
+                const int cbase = nt * A_BN + grp * 64;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 16) {
                     uint32_t rr[16];
+                    __syncwarp();  // the drain below is per-lane divergent; tcgen05.ld is warp-collective
                     ptx::tmem_ld16(taddr + c0, rr);
                     ptx::tmem_ld_wait();
+                    if (qcnt > A_QCAP - 16) drain();
+                    const float4* xy4 = reinterpret_cast<const float4*>(kxy + cbase + c0);
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const int col = nt * A_BN + c0 + j;
-                        const float4 k4 = kp[col];
-                        if (!in_window(rp, __float_as_uint(k4.w), k4.x, k4.y)) continue;
-                        const float d2 = (rp.na2 + k4.z) - 2.0f * __uint_as_float(rr[j]);
-                        if (d2 < bd[A_TOPK - 1]) {
-                            a5 = bd[A_TOPK - 1];
-                            float cd = d2;
-                            int ci = col;
-#pragma unroll
-                            for (int k = 0; k < A_TOPK; k++) {
-                                if (cd < bd[k]) {
-                                    const float td = bd[k];
-                                    const int ti = bi[k];
-                                    bd[k] = cd;
-                                    bi[k] = ci;
-                                    cd = td;
-                                    ci = ti;
-                                }
-                            }
-                        } else if (d2 < a5) {
-                            a5 = d2;
+                    for (int j2 = 0; j2 < 8; j2++) {
+                        const float4 v = xy4[j2];  // (x, y) of columns cbase + c0 + 2 j2, + 1
+                        const bool h0 = (v.x > xlo) & (v.x < xhi) & (v.y > ylo) & (v.y < yhi);
+                        const bool h1 = (v.z > xlo) & (v.z < xhi) & (v.w > ylo) & (v.w < yhi);
+                        if (h0) {
+                            qbuf[qcnt * 256 + etid] =
+                                make_float2(__uint_as_float(rr[2 * j2]), __int_as_float(cbase + c0 + 2 * j2));
+                            qcnt++;
+                        }
+                        if (h1) {
+                            qbuf[qcnt * 256 + etid] =
+                                make_float2(__uint_as_float(rr[2 * j2 + 1]), __int_as_float(cbase + c0 + 2 * j2 + 1));
+                            qcnt++;
                         }
                     }
                 }
@@ -375,11 +430,32 @@ assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
             }
-            if (row < p.rows) {
-                const size_t o = (size_t)f * p.max_rows + row;
-                *reinterpret_cast<int4*>(p.cand + o * 4) = make_int4(bi[0], bi[1], bi[2], bi[3]);
-                p.guard[o] = a5;
+            // merge the two column halves (half 1 -> half 0)
+            if (grp == 1) {
+#pragma unroll
+                for (int k = 0; k < A_TOPK; k++) {
+                    mbuf[k * 128 + rloc] = bd[k];
+                    mbuf[(A_TOPK + k) * 128 + rloc] = __int_as_float(bi[k]);
+                }
+                mbuf[2 * A_TOPK * 128 + rloc] = a5;
             }
+            epi_bar();
+            if (grp == 0) {
+#pragma unroll
+                for (int k = 0; k < A_TOPK; k++) {
+                    const int ci = __float_as_int(mbuf[(A_TOPK + k) * 128 + rloc]);
+                    if (ci != 0x7fffffff) insert(mbuf[k * 128 + rloc], ci);
+                }
+                a5 = fminf(a5, mbuf[2 * A_TOPK * 128 + rloc]);
+                if (row < p.rows) {
+                    const size_t o = (size_t)f * p.max_rows + row;
+                    *reinterpret_cast<int4*>(p.cand + o * 4) =
+                        make_int4(bi[0] == 0x7fffffff ? -1 : bi[0], bi[1] == 0x7fffffff ? -1 : bi[1],
+                                  bi[2] == 0x7fffffff ? -1 : bi[2], bi[3] == 0x7fffffff ? -1 : bi[3]);
+                    p.guard[o] = a5;
+                }
+            }
+            epi_bar();  // mbuf is free again
         }
     }
     ptx::tc_fence_before();
@@ -503,7 +579,9 @@ cudaError_t dalloc(T** p, size_t count) {
     return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
 }
 
-int gemm_smem(const AssocState* s) { return A_STAGES * A_STAGE_BYTES + 1024 + 20 * 8 + 16 + s->ncap * 16 + 64; }
+int gemm_smem(const AssocState* s) {
+    return A_STAGES * A_STAGE_BYTES + 1024 + 20 * 8 + 16 + s->ncap * 16 + A_QCAP * 256 * 8 + 9 * 128 * 4 + 64;
+}
 
 int ensure_state(ppg_ctx* c) {
     if (c->assoc) return PPG_OK;

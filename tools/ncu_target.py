@@ -24,5 +24,5 @@ for step in range(2):
     e.run_device(B)
     e.assoc_run_batch(B)
 e.sync()
-print("launches", e.launch_count())
+print("launches", e.launch_count(), "assoc fallback rows (last batch)", e.assoc_fallback_rows())
 e.close()
