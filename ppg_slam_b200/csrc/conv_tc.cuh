@@ -67,6 +67,10 @@ constexpr int CONV2_TILE_W = 8, CONV2_TILE_H = 16;
 // Fills stages / tiles / smem size for the given shape. Tensor maps are encoded by the caller (api).
 void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded, int taps, int mode, int relu,
                   const float* bias, void* out, int out_ld);
-cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStream_t st);
+// fuse_gray != nullptr (halo kernel only): the layer's input is conv1a of that u8 image, computed inside the kernel
+// by producer warps (fuse_w [64][9] fp32, fuse_b [64]) instead of being read through mapA.
+cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStream_t st,
+                           const uint8_t* fuse_gray = nullptr, const float* fuse_w = nullptr,
+                           const float* fuse_b = nullptr);
 
 }  // namespace ppg

@@ -65,6 +65,7 @@ struct ppg_ctx {
 
     // profiling
     bool profiling = false;
+    bool fuse_conv1a = false;  // PPG_FUSE_CONV1A=1 -> conv1a computed by producer warps inside conv1b (measured slower)
     std::vector<cudaEvent_t> ev;
     std::vector<const char*> ev_names;
     int n_ev = 0;

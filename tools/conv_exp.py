@@ -41,7 +41,7 @@ def main():
             continue
         d = json.loads(line[0][4:])
         out[f] = d
-        print(f, " ".join("%s=%.3f" % (k, d[k]) for k in ("conv1b", "conv2a", "conv2b", "conv3a", "edge1")), flush=True)
+        print(f, " ".join("%s=%.3f" % (k, d[k]) for k in ("conv1a+conv1b" if "conv1a+conv1b" in d else "conv1b", "conv2a", "conv2b", "conv3a", "edge1")), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "conv_exp.json"), "w"), indent=1)
 
