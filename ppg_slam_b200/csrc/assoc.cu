@@ -75,8 +75,9 @@ struct AssocState {
     float *best_d = nullptr, *second_d = nullptr;
     uint8_t* accept = nullptr;
     int* fallback = nullptr;
-    uint8_t* h_res = nullptr;  // pinned staging for fetch
+    uint8_t* h_res = nullptr;  // pinned staging for fetch: 5 planes [bcap][max_rows] (4 x 4 bytes, 1 x 1 byte)
     size_t h_res_bytes = 0;
+    float* h_stage = nullptr;  // pinned staging for the per-frame projections: [bcap][max_rows] x (2 + 1) floats
 };
 
 namespace {
@@ -618,6 +619,7 @@ int ensure_state(ppg_ctx* c) {
     PPG_CUDA(c, dalloc(&s->fallback, 1));
     s->h_res_bytes = B * R * 17;
     PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&s->h_res), s->h_res_bytes));
+    PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&s->h_stage), B * R * 3 * sizeof(float)));
     if (!make_kmajor_map(&s->mapA, s->map_bf, R, 256, A_BM, true) ||
         !make_kmajor_map(&s->mapB, s->f_bf, B * N, 256, A_BN, true))
         return set_err(c, PPG_ERR_CUDA, "cuTensorMapEncodeTiled failed for the association operands");
@@ -713,28 +715,30 @@ int run_assoc(ppg_ctx* c, const FrameSrc& src, int frames, int force_exact) {
     return PPG_OK;
 }
 
-int fetch_slot(ppg_ctx* c, int slot, ppg_assoc_out* out) {
+// Results of `frames` slots -> pinned planes with ONE strided copy per array (the first version issued 5 copies per
+// frame: 160 driver calls per batch-32 fetch); plane k of slot f starts at h_res + plane_off[k] + f * R * elem.
+int fetch_slots(ppg_ctx* c, int frames) {
     AssocState* s = c->assoc;
-    const size_t R = s->staged_rows, o = (size_t)slot * s->max_rows;
-    uint8_t* h = s->h_res + (size_t)slot * s->max_rows * 17;
-    PPG_CUDA(c, cudaMemcpyAsync(h, s->best_idx + o, R * 4, cudaMemcpyDeviceToHost, c->st));
-    PPG_CUDA(c, cudaMemcpyAsync(h + R * 4, s->second_idx + o, R * 4, cudaMemcpyDeviceToHost, c->st));
-    PPG_CUDA(c, cudaMemcpyAsync(h + R * 8, s->best_d + o, R * 4, cudaMemcpyDeviceToHost, c->st));
-    PPG_CUDA(c, cudaMemcpyAsync(h + R * 12, s->second_d + o, R * 4, cudaMemcpyDeviceToHost, c->st));
-    PPG_CUDA(c, cudaMemcpyAsync(h + R * 16, s->accept + o, R, cudaMemcpyDeviceToHost, c->st));
-    (void)out;
+    const size_t R = s->staged_rows, M = s->max_rows, F = frames, B = s->bcap;
+    uint8_t* h = s->h_res;
+    const void* src[5] = {s->best_idx, s->second_idx, s->best_d, s->second_d, s->accept};
+    for (int k = 0; k < 5; k++) {
+        const size_t es = k < 4 ? 4 : 1;
+        PPG_CUDA(c, cudaMemcpy2DAsync(h + (size_t)k * B * M * 4, R * es, src[k], M * es, R * es, F,
+                                      cudaMemcpyDeviceToHost, c->st));
+    }
     return PPG_OK;
 }
 
 void unpack_slot(ppg_ctx* c, int slot, ppg_assoc_out* out) {
     AssocState* s = c->assoc;
-    const size_t R = s->staged_rows;
-    const uint8_t* h = s->h_res + (size_t)slot * s->max_rows * 17;
-    if (out->best_idx) memcpy(out->best_idx, h, R * 4);
-    if (out->second_idx) memcpy(out->second_idx, h + R * 4, R * 4);
-    if (out->best_dist) memcpy(out->best_dist, h + R * 8, R * 4);
-    if (out->second_dist) memcpy(out->second_dist, h + R * 12, R * 4);
-    if (out->accept) memcpy(out->accept, h + R * 16, R);
+    const size_t R = s->staged_rows, M = s->max_rows, B = s->bcap;
+    const uint8_t* h = s->h_res;
+    if (out->best_idx) memcpy(out->best_idx, h + 0 * B * M * 4 + (size_t)slot * R * 4, R * 4);
+    if (out->second_idx) memcpy(out->second_idx, h + 1 * B * M * 4 + (size_t)slot * R * 4, R * 4);
+    if (out->best_dist) memcpy(out->best_dist, h + 2 * B * M * 4 + (size_t)slot * R * 4, R * 4);
+    if (out->second_dist) memcpy(out->second_dist, h + 3 * B * M * 4 + (size_t)slot * R * 4, R * 4);
+    if (out->accept) memcpy(out->accept, h + 4 * B * M * 4 + (size_t)slot * R, R);
 }
 
 }  // namespace
@@ -748,6 +752,7 @@ void assoc_destroy(ppg_ctx* c) {
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (s->h_res) cudaFreeHost(s->h_res);
+    if (s->h_stage) cudaFreeHost(s->h_stage);
     delete s;
     c->assoc = nullptr;
 }
@@ -780,12 +785,17 @@ static int stage_rows(ppg_ctx* c, int frames, int n_rows, const float* proj_uv, 
     if (n_rows < 1 || n_rows > s->n_rows || !proj_uv || !view_cos)
         return set_err(c, PPG_ERR_ARG, "association: n_rows must be in [1, uploaded rows]");
     if (frames < 1 || frames > s->bcap) return set_err(c, PPG_ERR_ARG, "association: bad frame count");
-    for (int f = 0; f < frames; f++) {
-        PPG_CUDA(c, cudaMemcpyAsync(s->proj + (size_t)f * s->max_rows * 2, proj_uv + (size_t)f * n_rows * 2,
-                                    (size_t)n_rows * 8, cudaMemcpyHostToDevice, c->st));
-        PPG_CUDA(c, cudaMemcpyAsync(s->vcos + (size_t)f * s->max_rows, view_cos + (size_t)f * n_rows,
-                                    (size_t)n_rows * 4, cudaMemcpyHostToDevice, c->st));
-    }
+    // the caller's arrays are pageable: one memcpy into pinned staging and one strided DMA per array instead of two
+    // driver-staged copies per frame.  The previous batch's DMA out of the staging buffer must be done first.
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    float* hp = s->h_stage;
+    float* hv = s->h_stage + (size_t)s->bcap * s->max_rows * 2;
+    memcpy(hp, proj_uv, (size_t)frames * n_rows * 8);
+    memcpy(hv, view_cos, (size_t)frames * n_rows * 4);
+    PPG_CUDA(c, cudaMemcpy2DAsync(s->proj, (size_t)s->max_rows * 8, hp, (size_t)n_rows * 8, (size_t)n_rows * 8, frames,
+                                  cudaMemcpyHostToDevice, c->st));
+    PPG_CUDA(c, cudaMemcpy2DAsync(s->vcos, (size_t)s->max_rows * 4, hv, (size_t)n_rows * 4, (size_t)n_rows * 4, frames,
+                                  cudaMemcpyHostToDevice, c->st));
     s->staged_rows = n_rows;
     s->staged_frames = frames;
     s->th = th;
@@ -849,7 +859,7 @@ int ppg_assoc_run_batch(ppg_ctx* c, int n_frames) {
 int ppg_assoc_fetch(ppg_ctx* c, ppg_assoc_out* out) {
     if (!c || !c->assoc || !out) return set_err(c, PPG_ERR_ARG, "ppg_assoc_fetch: null argument");
     PPG_CUDA(c, cudaSetDevice(c->dev));
-    int rc = fetch_slot(c, 0, out);
+    int rc = fetch_slots(c, 1);
     if (rc != PPG_OK) return rc;
     PPG_CUDA(c, cudaStreamSynchronize(c->st));
     unpack_slot(c, 0, out);
@@ -860,10 +870,8 @@ int ppg_assoc_fetch_batch(ppg_ctx* c, int n_frames, ppg_assoc_out* outs) {
     if (!c || !c->assoc || !outs || n_frames < 1 || n_frames > c->assoc->bcap)
         return set_err(c, PPG_ERR_ARG, "ppg_assoc_fetch_batch: bad arguments");
     PPG_CUDA(c, cudaSetDevice(c->dev));
-    for (int f = 0; f < n_frames; f++) {
-        int rc = fetch_slot(c, f, &outs[f]);
-        if (rc != PPG_OK) return rc;
-    }
+    int rc = fetch_slots(c, n_frames);
+    if (rc != PPG_OK) return rc;
     PPG_CUDA(c, cudaStreamSynchronize(c->st));
     for (int f = 0; f < n_frames; f++) unpack_slot(c, f, &outs[f]);
     return PPG_OK;
