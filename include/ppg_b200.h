@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PPG_API_VERSION 1
+#define PPG_API_VERSION 2
 #define PPG_DESC_DIM 256 /* PPGExtractor::DESC_DIM_SIZE, PPGExtractor.cpp:44 */
 
 typedef enum {
@@ -171,14 +171,29 @@ typedef struct {
     const float* view_cos;   /* M: MapPoint::mTrackViewCos */
     float th;                /* search radius factor (Matcher.cpp:240-244: r = th * (cos>0.998 ? 2.5 : 4)) */
     float ratio;             /* Matcher::mfNNratio */
+    int mode;                /* PPG_SEARCH_EXTEND_MAP (0) or PPG_SEARCH_WINDOW (1), see below */
+    float max_dist;          /* mode 1: accept iff best_dist <= max_dist */
+    double e2_max;           /* mode 1: > 0 -> candidates with ex*ex + ey*ey > e2_max are skipped */
 } ppg_assoc_in;
+
+/* Search rules.  The window walk (Frame/KeyFrame::GetFeaturesInArea), the free mask, DescriptorDistance and the
+ * first-minimum tie rule are shared; radius and acceptance differ:
+ *   PPG_SEARCH_EXTEND_MAP  Matcher::ExtendMapMatches (Matcher.cpp:224-281): r = th * (viewCos > 0.998 ? 2.5 : 4),
+ *                          accept = !(best > TH_HIGH && best > ratio * second)
+ *   PPG_SEARCH_WINDOW      the best-only projection cores: r = th, accept = best <= max_dist
+ *                            SearchByProjection(Cur, Last, th)                  :31-87      max_dist = TH_HIGH
+ *                            SearchByProjection(F, KF, sFound, th, descDist)    :1337-1411  max_dist = descDist
+ *                            Fuse(KF, vpMapPoints, th)                          :897-1036   max_dist = TH_LOW,
+ *                                                                               e2_max = 5.99 (:1000-1005)
+ *                          view_cos is ignored. */
+enum { PPG_SEARCH_EXTEND_MAP = 0, PPG_SEARCH_WINDOW = 1 };
 
 typedef struct {       /* caller-allocated host arrays of n_rows */
     int32_t* best_idx;   /* -1 when the window is empty */
     int32_t* second_idx; /* -1 when fewer than two candidates */
     float* best_dist;    /* DescriptorDistance (MapPoint.cpp:22-29); 1e6 when absent */
     float* second_dist;
-    uint8_t* accept;     /* !(best > TH_HIGH && best > ratio*second), Matcher.cpp:276 */
+    uint8_t* accept;     /* mode 0: !(best > TH_HIGH && best > ratio*second), Matcher.cpp:276; mode 1: best <= max_dist */
 } ppg_assoc_out;
 
 /* Inputs/outputs in host memory; synchronous. */

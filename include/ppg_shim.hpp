@@ -163,7 +163,7 @@ inline SearchResult search_local_points(ppg_ctx* ctx, Frame& F, const std::vecto
     r.best_dist.resize(M);
     r.second_dist.resize(M);
     r.accept.resize(M);
-    ppg_assoc_in in;
+    ppg_assoc_in in{};  // mode = PPG_SEARCH_EXTEND_MAP
     in.n_kp = N;
     in.kp_x = kx.data();
     in.kp_y = ky.data();
@@ -176,6 +176,52 @@ inline SearchResult search_local_points(ppg_ctx* ctx, Frame& F, const std::vecto
     in.ratio = nnratio;
     ppg_assoc_out out{r.best_idx.data(), r.second_idx.data(), r.best_dist.data(), r.second_dist.data(),
                       r.accept.data()};
+    check(ppg_associate(ctx, &in, &out), ctx, "ppg_associate");
+    return r;
+}
+
+// The best-only projection cores share the same primitive with r = th and accept = best <= max_dist
+// (PPG_SEARCH_WINDOW).  The caller keeps its own projection / visibility filters and passes the surviving rows:
+//   Matcher::SearchByProjection(Cur, Last, th)               Matcher.cpp:31-87     max_dist = TH_HIGH,
+//        free_mask[i] = !(Cur.mvpMapPoints[i] && Cur.mvpMapPoints[i]->Observations() > 0)               (:66-68)
+//   Matcher::SearchByProjection(F, pKF, sFound, th, descDist) Matcher.cpp:1337-1411 max_dist = descDist,
+//        free_mask[i] = !F.mvpMapPoints[i]                                                               (:1386)
+//   Matcher::Fuse(pKF, vpMapPoints, th)                       Matcher.cpp:897-1036  max_dist = TH_LOW, e2_max = 5.99,
+//        free_mask all ones (Fuse looks at every keypoint of the window, :994-1013)
+// `FrameLike` is Frame or KeyFrame (mvKeysUn, mDescriptors).  As in search_local_points the sequential consumption
+// (a keypoint taken by an earlier row) is resolved by the caller with the reference's own inner loop.
+template <class FrameLike>
+inline SearchResult search_window(ppg_ctx* ctx, FrameLike& F, const std::vector<MapPoint*>& mps,
+                                  const std::vector<float>& proj_uv, const std::vector<uint8_t>& free_mask, float th,
+                                  float max_dist, double e2_max = 0.0) {
+    const int N = (int)F.mvKeysUn.size(), M = (int)mps.size();
+    std::vector<float> kx(N), ky(N), vc(M, 0.f);
+    for (int i = 0; i < N; i++) {
+        kx[i] = F.mvKeysUn[i].mPos[0];
+        ky[i] = F.mvKeysUn[i].mPos[1];
+    }
+    SearchResult r;
+    r.best_idx.resize(M);
+    r.second_idx.resize(M);
+    r.best_dist.resize(M);
+    r.second_dist.resize(M);
+    r.accept.resize(M);
+    ppg_assoc_in in{};
+    in.n_kp = N;
+    in.kp_x = kx.data();
+    in.kp_y = ky.data();
+    in.frame_desc = F.mDescriptors.template ptr<float>(0);
+    in.free_mask = free_mask.data();
+    in.n_rows = M;
+    in.proj_uv = proj_uv.data();
+    in.view_cos = vc.data();
+    in.th = th;
+    in.mode = PPG_SEARCH_WINDOW;
+    in.max_dist = max_dist;
+    in.e2_max = e2_max;
+    ppg_assoc_out out{r.best_idx.data(), r.second_idx.data(), r.best_dist.data(), r.second_dist.data(),
+                      r.accept.data()};
+    upload_map_descriptors(ctx, mps);
     check(ppg_associate(ctx, &in, &out), ctx, "ppg_associate");
     return r;
 }

@@ -208,9 +208,12 @@ def indexable(cam, kx, ky):
                                             C.byref(px), C.byref(py)) for x, y in zip(kx, ky)], np.uint8)
 
 
-def search_all(cam, kx, ky, frame_desc, free_mask, map_desc, proj_uv, view_cos, th, ratio, th_high=0.8):
-    """Search core of Matcher::ExtendMapMatches (Matcher.cpp:224-281) for every map point, frame
-    state frozen.  -> dict(best_idx, second_idx, best_d, second_d, accept)."""
+def search_all(cam, kx, ky, frame_desc, free_mask, map_desc, proj_uv, view_cos, th, ratio, th_high=0.8, mode=0,
+               max_dist=0.8, e2_max=0.0):
+    """Search core of Matcher::ExtendMapMatches (Matcher.cpp:224-281, mode 0) or of the best-only projection
+    matchers (SearchByProjection :31-87 / :1337-1411, Fuse :897-1036; mode 1: r = th, accept = best <= max_dist,
+    optional e2_max) for every map point, frame state frozen.
+    -> dict(best_idx, second_idx, best_d, second_d, accept)."""
     cfg = make_cfg(cam)
     kx, ky, frame_desc = f32(kx), f32(ky), f32(frame_desc)
     map_desc, proj_uv, view_cos = f32(map_desc), f32(proj_uv), f32(view_cos)
@@ -222,6 +225,6 @@ def search_all(cam, kx, ky, frame_desc, free_mask, map_desc, proj_uv, view_cos, 
     lib().ppgo_search_all(C.byref(cfg), n, _p(kx, C.c_float), _p(ky, C.c_float), _p(frame_desc, C.c_float),
                           _p(free_mask, C.c_uint8), m, _p(map_desc, C.c_float), _p(proj_uv, C.c_float),
                           _p(view_cos, C.c_float), C.c_float(th), C.c_float(ratio), C.c_float(th_high),
-                          _p(bi, C.c_int), _p(si, C.c_int), _p(bd, C.c_float), _p(sd, C.c_float),
+                          C.c_int(mode), C.c_float(max_dist), C.c_double(e2_max), _p(bi, C.c_int), _p(si, C.c_int), _p(bd, C.c_float), _p(sd, C.c_float),
                           _p(acc, C.c_uint8))
     return dict(best_idx=bi, second_idx=si, best_d=bd, second_d=sd, accept=acc)

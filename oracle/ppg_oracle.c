@@ -729,27 +729,41 @@ int ppgo_features_in_area(const ppgo_bounds *b, const int *grid_off, const int *
     return cnt;
 }
 
-/* Search core of Matcher::ExtendMapMatches, matching/src/Matcher.cpp:224-281, for one map point with
- * the frame state frozen (free_mask[idx]!=0 <=> keypoint idx is NOT skipped at :253).  This is the
- * data-parallel contract of ppg_associate(): the sequential consumption (:278-378) stays in the host
- * shim.  Candidate order = GetFeaturesInArea order (cell-major), ties keep the first (strict <).
+/* Search core of the projection matchers for one map point with the frame state frozen
+ * (free_mask[idx]!=0 <=> keypoint idx is NOT skipped).  This is the data-parallel contract of
+ * ppg_associate(): the sequential consumption stays in the host shim.  Candidate order =
+ * GetFeaturesInArea order (cell-major), ties keep the first (strict <).
+ *   mode 0  Matcher::ExtendMapMatches, matching/src/Matcher.cpp:224-281: r = th * (viewCos > 0.998 ? 2.5 : 4),
+ *           accept = !(best > TH_HIGH && best > ratio * second) (:276)
+ *   mode 1  the "best only" cores: SearchByProjection(Cur, Last) :31-87 (max_dist = TH_HIGH),
+ *           SearchByProjection(F, KF, sFound, th, descDist) :1337-1411 (max_dist = descDist), Fuse :897-1036
+ *           (max_dist = TH_LOW, e2_max = 5.99: candidates with ex*ex + ey*ey > 5.99 are skipped, :1000-1005):
+ *           r = th, accept = best <= max_dist.
  * -> accept flag; outputs best/second idx and distances (second_idx=-1, d=1e6 when absent). */
 int ppgo_search_core(const ppgo_bounds *b, const int *grid_off, const int *grid_idx, int n, const float *kx,
                      const float *ky, const float *frame_desc, const uint8_t *free_mask, const float *mp_desc,
-                     float proj_x, float proj_y, float view_cos, float th, float ratio, float th_high,
-                     int *best_idx, int *second_idx, float *best_d, float *second_d) {
+                     float proj_x, float proj_y, float view_cos, float th, float ratio, float th_high, int mode,
+                     float max_dist, double e2_max, int *best_idx, int *second_idx, float *best_d,
+                     float *second_d) {
     float bestDist = 1e6f, bestDist2 = 1e6f;
     int bestIdx = -1, bestIdx2 = -1;
     float r = th;
-    if ((double)view_cos > 0.998) /* :240-244: float compared with a double literal, r *= double */
-        r = (float)((double)r * 2.5);
-    else
-        r = (float)((double)r * 4.0);
+    if (mode == 0) {
+        if ((double)view_cos > 0.998) /* :240-244: float compared with a double literal, r *= double */
+            r = (float)((double)r * 2.5);
+        else
+            r = (float)((double)r * 4.0);
+    }
     int *cand = malloc(sizeof(int) * (n > 0 ? n : 1));
     int nc = ppgo_features_in_area(b, grid_off, grid_idx, kx, ky, proj_x, proj_y, r, cand);
     for (int t = 0; t < nc; t++) {
         int idx = cand[t];
         if (!free_mask[idx]) continue;
+        if (mode == 1 && e2_max > 0.0) { /* Fuse :1000-1005: float e2 compared with the double literal */
+            float ex = proj_x - kx[idx], ey = proj_y - ky[idx];
+            float e2 = ex * ex + ey * ey;
+            if ((double)e2 > e2_max) continue;
+        }
         float dist = ppgo_descriptor_distance(mp_desc, frame_desc + (size_t)idx * 256, 256);
         if (dist < bestDist) {
             bestDist2 = bestDist;
@@ -767,14 +781,16 @@ int ppgo_search_core(const ppgo_bounds *b, const int *grid_off, const int *grid_
     *best_d = bestDist;
     *second_d = bestDist2;
     if (nc == 0 || bestIdx < 0) return 0;
+    if (mode == 1) return bestDist <= max_dist ? 1 : 0; /* :78, :1399, :1016 */
     if (bestDist > th_high && bestDist > ratio * bestDist2) return 0; /* :276 */
     return 1;
 }
 
 void ppgo_search_all(const ppgo_cfg *c, int n, const float *kx, const float *ky, const float *frame_desc,
                      const uint8_t *free_mask, int m, const float *map_desc, const float *proj_uv,
-                     const float *view_cos, float th, float ratio, float th_high, int *best_idx, int *second_idx,
-                     float *best_d, float *second_d, uint8_t *accept) {
+                     const float *view_cos, float th, float ratio, float th_high, int mode, float max_dist,
+                     double e2_max, int *best_idx, int *second_idx, float *best_d, float *second_d,
+                     uint8_t *accept) {
     ppgo_bounds b;
     ppgo_image_bounds(c, &b);
     int *goff = malloc(sizeof(int) * (64 * 48 + 1)), *gidx = malloc(sizeof(int) * (n > 0 ? n : 1));
@@ -782,8 +798,8 @@ void ppgo_search_all(const ppgo_cfg *c, int n, const float *kx, const float *ky,
     for (int j = 0; j < m; j++)
         accept[j] = (uint8_t)ppgo_search_core(&b, goff, gidx, n, kx, ky, frame_desc, free_mask,
                                               map_desc + (size_t)j * 256, proj_uv[2 * j], proj_uv[2 * j + 1],
-                                              view_cos[j], th, ratio, th_high, &best_idx[j], &second_idx[j],
-                                              &best_d[j], &second_d[j]);
+                                              view_cos[j], th, ratio, th_high, mode, max_dist, e2_max, &best_idx[j],
+                                              &second_idx[j], &best_d[j], &second_d[j]);
     free(goff);
     free(gidx);
 }

@@ -49,7 +49,10 @@ class AssocIn(C.Structure):
     _fields_ = [("n_kp", C.c_int), ("kp_x", C.POINTER(C.c_float)), ("kp_y", C.POINTER(C.c_float)),
                 ("frame_desc", C.POINTER(C.c_float)), ("free_mask", C.POINTER(C.c_uint8)), ("n_rows", C.c_int),
                 ("proj_uv", C.POINTER(C.c_float)), ("view_cos", C.POINTER(C.c_float)), ("th", C.c_float),
-                ("ratio", C.c_float)]
+                ("ratio", C.c_float), ("mode", C.c_int), ("max_dist", C.c_float), ("e2_max", C.c_double)]
+
+
+SEARCH_EXTEND_MAP, SEARCH_WINDOW = 0, 1
 
 
 class AssocOut(C.Structure):
@@ -255,7 +258,8 @@ class Extractor:
         self._check(self.lib.ppg_upload_map(self.h, _fp(m), m.shape[0]))
         self._n_rows = m.shape[0]
 
-    def _assoc_in(self, kp_x, kp_y, frame_desc, free_mask, proj_uv, view_cos, th, ratio):
+    def _assoc_in(self, kp_x, kp_y, frame_desc, free_mask, proj_uv, view_cos, th, ratio, mode=0, max_dist=0.0,
+                  e2_max=0.0):
         a = AssocIn()
         keep = [np.ascontiguousarray(kp_x, np.float32), np.ascontiguousarray(kp_y, np.float32),
                 np.ascontiguousarray(frame_desc, np.float32), np.ascontiguousarray(free_mask, np.uint8),
@@ -266,6 +270,7 @@ class Extractor:
         a.n_rows = len(keep[5])
         a.proj_uv, a.view_cos = _fp(keep[4]), _fp(keep[5])
         a.th, a.ratio = th, ratio
+        a.mode, a.max_dist, a.e2_max = mode, max_dist, e2_max
         return a, keep
 
     @staticmethod
@@ -279,8 +284,12 @@ class Extractor:
         o.accept = r["accept"].ctypes.data_as(C.POINTER(C.c_uint8))
         return o, r
 
-    def associate(self, kp_x, kp_y, frame_desc, free_mask, proj_uv, view_cos, th, ratio):
-        a, keep = self._assoc_in(kp_x, kp_y, frame_desc, free_mask, proj_uv, view_cos, th, ratio)
+    def associate(self, kp_x, kp_y, frame_desc, free_mask, proj_uv, view_cos, th, ratio, mode=0, max_dist=0.0,
+                  e2_max=0.0):
+        """mode 0: search core of ExtendMapMatches; mode 1 (SEARCH_WINDOW): best-only cores of SearchByProjection /
+        Fuse -- r = th, accept = best <= max_dist, optional circular limit e2_max (include/ppg_b200.h)."""
+        a, keep = self._assoc_in(kp_x, kp_y, frame_desc, free_mask, proj_uv, view_cos, th, ratio, mode, max_dist,
+                                 e2_max)
         o, r = self._assoc_out(a.n_rows)
         self._check(self.lib.ppg_associate(self.h, C.byref(a), C.byref(o)))
         return r

@@ -67,6 +67,9 @@ struct AssocState {
     float *proj = nullptr, *vcos = nullptr;
     RowParam* rowp = nullptr;
     float th = 0.f, ratio = 0.f;
+    int mode = 0;            // PPG_SEARCH_EXTEND_MAP / PPG_SEARCH_WINDOW
+    float max_dist = 0.f;    // mode 1 acceptance threshold
+    double e2_max = 0.0;     // mode 1 circular limit (Fuse), 0 = none
     int staged_rows = 0, staged_frames = 0;
     // results, [bcap][max_rows]
     int* cand = nullptr;  // x4
@@ -154,19 +157,21 @@ __global__ void __launch_bounds__(256) prep_frame_kernel(const FrameSrc src, int
 // Search window of each map point: r (Matcher.cpp:240-244) and the cell range of GetFeaturesInArea
 // (Frame.cpp:270-292) including its early returns.  grid (rows/256, frames).
 __global__ void prep_rows_kernel(const float* __restrict__ proj, const float* __restrict__ vcos,
-                                 const float* __restrict__ n2, int rows, int max_rows, float th, GridParam g,
-                                 RowParam* __restrict__ rp) {
+                                 const float* __restrict__ n2, int rows, int max_rows, float th, int mode,
+                                 GridParam g, RowParam* __restrict__ rp) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
     if (m >= rows) return;
     const size_t o = (size_t)f * max_rows + m;
     RowParam p;
     p.u = proj[2 * o];
     p.v = proj[2 * o + 1];
-    float r = th;
-    if ((double)vcos[o] > 0.998)
-        r = (float)((double)r * 2.5);
-    else
-        r = (float)((double)r * 4.0);
+    float r = th;  // PPG_SEARCH_WINDOW: r = th (Matcher.cpp:56, :1378, :971)
+    if (mode == 0) {  // ExtendMapMatches :240-244
+        if ((double)vcos[o] > 0.998)
+            r = (float)((double)r * 2.5);
+        else
+            r = (float)((double)r * 4.0);
+    }
     p.r = r;
     p.na2 = n2[m];
     bool empty = false;
@@ -186,12 +191,20 @@ __global__ void prep_rows_kernel(const float* __restrict__ proj, const float* __
     rp[o] = p;
 }
 
-__device__ __forceinline__ bool in_window(const RowParam& p, uint32_t info, float x, float y) {
+// e2_max > 0 (Fuse, Matcher.cpp:1000-1005): candidates farther than sqrt(e2_max) from the projection are skipped;
+// float e2 compared with the double literal, as the reference does.
+__device__ __forceinline__ bool in_window(const RowParam& p, uint32_t info, float x, float y, double e2_max) {
     if (!(info & 0x10000u) || p.cells == 0xffffffffu) return false;
     const uint32_t cx = info & 0xff, cy = (info >> 8) & 0xff;
     if (cx < (p.cells & 0xff) || cx > ((p.cells >> 8) & 0xff) || cy < ((p.cells >> 16) & 0xff) || cy > (p.cells >> 24))
         return false;
-    return fabsf(x - p.u) < p.r && fabsf(y - p.v) < p.r;  // Frame.cpp:305-309
+    if (!(fabsf(x - p.u) < p.r && fabsf(y - p.v) < p.r)) return false;  // Frame.cpp:305-309
+    if (e2_max > 0.0) {
+        const float ex = p.u - x, ey = p.v - y;
+        const float e2 = ex * ex + ey * ey;
+        if ((double)e2 > e2_max) return false;
+    }
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -208,6 +221,7 @@ struct GemmParams {
     const uint32_t* kinfo;
     int* cand;
     float* guard;
+    double e2_max;
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -387,7 +401,8 @@ assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     const float2 e = qbuf[sidx * 256 + etid];
                     const int col = __float_as_int(e.y);
                     const float2 xy = kxy[col], zi = kzi[col];
-                    if (in_window(rp, __float_as_uint(zi.y), xy.x, xy.y)) insert((rp.na2 + zi.x) - 2.0f * e.x, col);
+                    if (in_window(rp, __float_as_uint(zi.y), xy.x, xy.y, p.e2_max))
+                        insert((rp.na2 + zi.x) - 2.0f * e.x, col);
                 }
                 qcnt = 0;
             };
@@ -493,6 +508,9 @@ struct RescoreParams {
     const float* guard;
     const float* nbmax;
     float ratio, th_high;
+    int mode;         // 0: ExtendMapMatches rule, 1: best <= max_dist
+    float max_dist;
+    double e2_max;
     int force_exact;  // 1: ignore the GEMM candidates and score every window exactly (validation)
     int *best_idx, *second_idx;
     float *best_d, *second_d;
@@ -554,7 +572,7 @@ __global__ void __launch_bounds__(256) assoc_rescore_kernel(const RescoreParams 
         for (int c0 = 0; c0 < n; c0 += 32) {
             const int c = c0 + lane;
             bool in = false;
-            if (c < n) in = in_window(rp, kinfo[c], kx[c], ky[c]);
+            if (c < n) in = in_window(rp, kinfo[c], kx[c], ky[c], p.e2_max);
             unsigned mask = __ballot_sync(AFULL, in);
             while (mask) {
                 const int cc = c0 + __ffs(mask) - 1;
@@ -570,7 +588,12 @@ __global__ void __launch_bounds__(256) assoc_rescore_kernel(const RescoreParams 
         p.best_d[o] = b1;
         p.second_d[o] = b2;
         uint8_t acc = 0;
-        if (i1 >= 0) acc = !(b1 > p.th_high && b1 > p.ratio * b2);  // Matcher.cpp:276
+        if (i1 >= 0) {
+            if (p.mode == 1)
+                acc = b1 <= p.max_dist;  // Matcher.cpp:78, :1399, :1016
+            else
+                acc = !(b1 > p.th_high && b1 > p.ratio * b2);  // Matcher.cpp:276
+        }
         p.accept[o] = acc;
     }
 }
@@ -669,7 +692,7 @@ int run_assoc(ppg_ctx* c, const FrameSrc& src, int frames, int force_exact) {
     prep_frame_kernel<<<dim3(s->ncap / 8, frames), 256, 0, c->st>>>(src, s->ncap, g, s->f_bf, s->fn2, s->kinfo,
                                                                     s->korder, s->nbmax);
     prep_rows_kernel<<<dim3((rows + 255) / 256, frames), 256, 0, c->st>>>(s->proj, s->vcos, s->map_n2, rows,
-                                                                          s->max_rows, s->th, g, s->rowp);
+                                                                          s->max_rows, s->th, s->mode, g, s->rowp);
     c->launches += 2;
     if (!force_exact) {
         GemmParams gp;
@@ -683,6 +706,7 @@ int run_assoc(ppg_ctx* c, const FrameSrc& src, int frames, int force_exact) {
         gp.kinfo = s->kinfo;
         gp.cand = s->cand;
         gp.guard = s->guard;
+        gp.e2_max = s->mode == 1 ? s->e2_max : 0.0;
         const int total = (rows + A_BM - 1) / A_BM * frames;
         const int grid = total < c->num_sms ? total : c->num_sms;
         assoc_gemm_kernel<<<grid, A_THREADS, gemm_smem(s), c->st>>>(s->mapA, s->mapB, gp);
@@ -702,6 +726,9 @@ int run_assoc(ppg_ctx* c, const FrameSrc& src, int frames, int force_exact) {
     rp.nbmax = s->nbmax;
     rp.ratio = s->ratio;
     rp.th_high = c->cfg.th_high;
+    rp.mode = s->mode;
+    rp.max_dist = s->max_dist;
+    rp.e2_max = s->mode == 1 ? s->e2_max : 0.0;
     rp.force_exact = force_exact;
     rp.best_idx = s->best_idx;
     rp.second_idx = s->second_idx;
@@ -800,6 +827,9 @@ static int stage_rows(ppg_ctx* c, int frames, int n_rows, const float* proj_uv, 
     s->staged_frames = frames;
     s->th = th;
     s->ratio = ratio;
+    s->mode = 0;  // ppg_assoc_stage overrides from ppg_assoc_in
+    s->max_dist = 0.f;
+    s->e2_max = 0.0;
     return PPG_OK;
 }
 
@@ -810,6 +840,8 @@ int ppg_assoc_stage(ppg_ctx* c, const ppg_assoc_in* in) {
     if (rc != PPG_OK) return rc;
     AssocState* s = c->assoc;
     if (in->n_kp < 0 || in->n_kp > s->ncap) return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage: too many keypoints");
+    if (in->mode == PPG_SEARCH_WINDOW && !in->view_cos)
+        return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage: view_cos must point to n_rows floats (ignored in mode 1)");
     if ((rc = stage_rows(c, 1, in->n_rows, in->proj_uv, in->view_cos, in->th, in->ratio)) != PPG_OK) return rc;
     if (in->n_kp > 0 && in->kp_x && in->kp_y && in->frame_desc) {
         PPG_CUDA(c, cudaMemcpyAsync(s->kx, in->kp_x, (size_t)in->n_kp * 4, cudaMemcpyHostToDevice, c->st));
@@ -822,6 +854,11 @@ int ppg_assoc_stage(ppg_ctx* c, const ppg_assoc_in* in) {
     }
     PPG_CUDA(c, cudaStreamSynchronize(c->st));
     s->staged_n = in->n_kp;
+    if (in->mode != PPG_SEARCH_EXTEND_MAP && in->mode != PPG_SEARCH_WINDOW)
+        return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage: unknown search mode");
+    s->mode = in->mode;
+    s->max_dist = in->max_dist;
+    s->e2_max = in->e2_max;
     return PPG_OK;
 }
 

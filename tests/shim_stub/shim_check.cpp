@@ -8,5 +8,9 @@ int shim_instantiate(GeometricCamera* cam, Frame& F, std::vector<MapPoint*>& mps
     cv::Mat d;
     ex.run(cv::Mat(), a, b, e, d);
     ppg_shim::upload_map_descriptors(ex.context(), mps);
-    return (int)ppg_shim::search_local_points(ex.context(), F, mps, 10.f, 0.8f).accept.size();
+    std::vector<float> uv(2 * mps.size());
+    std::vector<uint8_t> free_mask(F.mvKeysUn.size(), 1);
+    int n = (int)ppg_shim::search_window(ex.context(), F, mps, uv, free_mask, 15.f, 0.8f).accept.size();        // :31-87
+    n += (int)ppg_shim::search_window(ex.context(), F, mps, uv, free_mask, 3.f, 0.7f, 5.99).accept.size();     // Fuse
+    return n + (int)ppg_shim::search_local_points(ex.context(), F, mps, 10.f, 0.8f).accept.size();
 }

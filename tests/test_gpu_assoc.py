@@ -82,6 +82,39 @@ def test_assoc_edge_cases():
         e.close()
 
 
+@pytest.mark.parametrize("name,th,max_dist,e2_max", [("by_projection", 15.0, 0.8, 0.0), ("by_projection_desc", 10.0, 0.75, 0.0),
+                                                      ("fuse", 3.0, 0.7, 5.99)], ids=lambda v: str(v))
+def test_window_search_modes_match_oracle(name, th, max_dist, e2_max):
+    """PPG_SEARCH_WINDOW: the best-only cores of SearchByProjection (Matcher.cpp:31-87, :1337-1411) and Fuse
+    (:897-1036, incl. the e2 > 5.99 skip) -- same kernels, r = th, accept = best <= threshold."""
+    from oracle import post_ref as O
+    from ppg_slam_b200 import capi
+    cam = cameras.EUROC
+    n, m = 420, 6000
+    kx, ky, fdesc = _synthetic_keypoints(21, cam, n)
+    inp = synth.association_inputs(8, fdesc, np.stack([kx, ky], 1), m, cam.width, cam.height, th=th)
+    rs = np.random.RandomState(4)
+    k = min(n, 300)
+    inp["proj_uv"][:k] = np.stack([kx[:k], ky[:k]], 1) + rs.uniform(-2.0, 2.0, (k, 2)).astype(np.float32)
+    free = (rs.rand(n) > 0.15).astype(np.uint8)
+    e = capi.Extractor(cam, max_batch=1, max_map_points=8192)
+    try:
+        e.upload_map(inp["map_desc"])
+        got = e.associate(kx, ky, fdesc, free, inp["proj_uv"], inp["view_cos"], th, 0.8, mode=capi.SEARCH_WINDOW,
+                          max_dist=max_dist, e2_max=e2_max)
+        ref = O.search_all(cam, kx, ky, fdesc, free, inp["map_desc"], inp["proj_uv"], inp["view_cos"], th, 0.8,
+                           mode=1, max_dist=max_dist, e2_max=e2_max)
+        np.testing.assert_array_equal(got["best_idx"], ref["best_idx"])
+        np.testing.assert_array_equal(got["second_idx"], ref["second_idx"])
+        np.testing.assert_array_equal(got["best_d"].view(np.uint32), ref["best_d"].view(np.uint32))
+        np.testing.assert_array_equal(got["accept"], ref["accept"])
+        assert ref["accept"].sum() > 20 and (ref["best_idx"] < 0).sum() > 0
+        # the ExtendMapMatches rule is back after a mode-0 call on the same ctx
+        _check(e, cam, kx, ky, fdesc, free, inp, th, 0.8)
+    finally:
+        e.close()
+
+
 def test_assoc_on_extracted_frame():
     """extract -> associate with the frame's own keypoints/descriptors left on the device."""
     from oracle import post_ref as O

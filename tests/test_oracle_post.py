@@ -232,3 +232,42 @@ def test_search_core_kat():
         if bi >= 0:
             assert abs(ref["best_d"][j] - np.linalg.norm(inp["map_desc"][j] - fd[bi])) < 1e-5
     assert ref["accept"].sum() > 20 and (ref["best_idx"] < 0).sum() > 0
+
+
+@pytest.mark.parametrize("name,th,max_dist,e2_max", [("SearchByProjection(Cur,Last)", 15.0, 0.8, 0.0),
+                                                      ("SearchByProjection(F,KF,descDist)", 10.0, 0.75, 0.0),
+                                                      ("Fuse", 3.0, 0.7, 5.99)], ids=lambda v: str(v))
+def test_window_search_core_kat(name, th, max_dist, e2_max):
+    """The best-only projection cores (Matcher.cpp:31-87, :1337-1411, :897-1036): r = th, strict-< best over the
+    window in GetFeaturesInArea order, Fuse's e2 > 5.99 skip, accept = best <= threshold."""
+    cam = cameras.EUROC
+    rs = np.random.RandomState(5)
+    n, m = 150, 250
+    kx = rs.uniform(20, cam.width - 20, n).astype(np.float32)
+    ky = rs.uniform(20, cam.height - 20, n).astype(np.float32)
+    fd = rs.normal(size=(n, 256)).astype(np.float32)
+    fd /= np.linalg.norm(fd, axis=1, keepdims=True)
+    inp = synth.association_inputs(6, fd, np.stack([kx, ky], 1), m, cam.width, cam.height, th=th)
+    # planted rows project close to their keypoint so that Fuse's 2.45 px circle keeps some of them
+    inp["proj_uv"][:60] = np.stack([kx[:60], ky[:60]], 1) + rs.uniform(-1.5, 1.5, (60, 2)).astype(np.float32)
+    free = (rs.rand(n) > 0.2).astype(np.uint8)
+    ref = O.search_all(cam, kx, ky, fd, free, inp["map_desc"], inp["proj_uv"], inp["view_cos"], th, 0.8, mode=1,
+                       max_dist=max_dist, e2_max=e2_max)
+    for j in range(m):
+        x, y = inp["proj_uv"][j]
+        order = O.features_in_area(cam, kx, ky, x, y, np.float32(th))
+        best, bi = np.float32(1e6), -1
+        for i in order:
+            if not free[i]:
+                continue
+            if e2_max > 0:
+                ex, ey = np.float32(x) - kx[i], np.float32(y) - ky[i]
+                e2 = np.float32(np.float32(ex * ex) + np.float32(ey * ey))
+                if float(e2) > e2_max:
+                    continue
+            d = O.descriptor_distance(inp["map_desc"][j], fd[i])
+            if d < best:
+                best, bi = d, i
+        assert ref["best_idx"][j] == bi, (name, j)
+        assert ref["accept"][j] == int(bi >= 0 and best <= np.float32(max_dist))
+    assert ref["accept"].sum() > 5 and (ref["best_idx"] < 0).sum() > 0
