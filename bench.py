@@ -197,9 +197,10 @@ def run_b200(args, rank, local_rank, world):
     proj_all = np.stack([uv for uv, _ in per_frame])
     vcos_all = np.stack([vc for _, vc in per_frame])
 
-    def device_step():
-        e.run_device(B)
-        e.assoc_run_batch(B)
+    def device_step(x=None):
+        x = x or e
+        x.run_device(B)
+        x.assoc_run_batch(B)
 
     def e2e_step(x=None):
         x = x or e
@@ -210,28 +211,49 @@ def run_b200(args, rank, local_rank, world):
         x.assoc_run_batch(B)
         x.assoc_fetch_batch(B)
 
-    # ---- device-timed arm: frames resident in HBM
-    e.upload(frames)
-    e.assoc_stage_batch(proj_all, vcos_all, TH, RATIO)
-    e.set_profiling(True)
+    # ---- contexts: one per stream in flight.  A ctx is single-stream (like the reference's extractor object);
+    # throughput callers keep several batches in flight on several ctxs of the same GPU, which also fills the SMs
+    # that the latency-bound one-CTA-per-frame kernels (NMS, overlap filter, graph) leave idle.
+    ctxs = [e]
+    for _ in range(max(1, args.dev_streams, args.e2e_streams) - 1):
+        x = capi.Extractor(cam, device=local_rank, max_batch=B, max_map_points=max(args.map_rows, 1024))
+        x.upload_map(map_desc)
+        ctxs.append(x)
+    all_ctxs = list(ctxs)
+    dev = ctxs[:max(1, args.dev_streams)]
+
+    # ---- device-timed arm: frames resident in HBM, K steps dealt round-robin to the device contexts
+    for x in dev:
+        x.upload(frames)
+        x.assoc_stage_batch(proj_all, vcos_all, TH, RATIO)
     clocks = ClockSampler(local_rank)
     t_w = time.perf_counter()
     k = 0
     while k < args.warmup or (time.perf_counter() - t_w < 1.5 and clocks.p is not None):
-        device_step()  # warm-up; keeps the GPU under load until nvidia-smi delivers its first samples
-        e.sync()
+        for x in dev:
+            device_step(x)  # warm-up; keeps the GPU under load until nvidia-smi delivers its first samples
+        for x in dev:
+            x.sync()
         k += 1
     barrier()
-    l0 = e.launch_count()
-    e.timer_start()
-    for _ in range(args.steps):
-        device_step()
-    ms = e.timer_stop()
-    launches = e.launch_count() - l0
+    l0 = sum(x.launch_count() for x in dev)
+    for x in dev:
+        x.timer_start()
+    for i in range(args.steps):
+        device_step(dev[i % len(dev)])
+    ms = max(x.timer_stop() for x in dev)  # CUDA events on every stream; the longest bracket counts
+    launches = sum(x.launch_count() for x in dev) - l0
+    # Per-kernel durations for the roofline: with more than one context in flight an event bracket around a kernel
+    # also covers the other stream's kernels it waits for, so the stage events are taken in a single-stream pass of
+    # the same step (same buffers, same clocks sampling window), right after the timed steps.
+    e.set_profiling(True)
+    for _ in range(3):
+        device_step(e)
+        e.sync()
+    stage = e.stage_times()
+    e.set_profiling(False)
     barrier()
     clk = clocks.stop()
-    stage = e.stage_times()  # last step of the timed region
-    e.set_profiling(False)
     if dist is not None:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -244,11 +266,8 @@ def run_b200(args, rank, local_rank, world):
     # run() is), so a caller that wants copies hidden behind compute keeps `--e2e-streams` contexts in flight, one
     # host thread each (ctypes releases the GIL); every step is still one full batch through ppg_extract + associate.
     keep, fptrs, fstrides, _ = e._frame_ptrs(frames)
-    ctxs = [e]
-    for _ in range(max(1, args.e2e_streams) - 1):
-        x = capi.Extractor(cam, device=local_rank, max_batch=B, max_map_points=max(args.map_rows, 1024))
-        x.upload_map(map_desc)
-        ctxs.append(x)
+    n_dev_ctx = len(dev)
+    ctxs = ctxs[:max(1, args.e2e_streams)]
     for x in ctxs:
         for _ in range(max(1, args.warmup // 2)):
             e2e_step(x)
@@ -274,7 +293,7 @@ def run_b200(args, rank, local_rank, world):
     if errs:
         raise errs[0]
     barrier()
-    for x in ctxs[1:]:
+    for x in all_ctxs[1:]:
         x.close()
     if dist is not None:
         t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
@@ -315,7 +334,8 @@ def run_b200(args, rank, local_rank, world):
                               ("conv1a 1->64 producer + " if fused else ""),
                     "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
                     "peak_source": how + " (sustained bf16 cuBLAS; fp16 runs on the same pipe)",
-                    "ms_per_launch": conv1b_ms, "frames_per_launch": B}
+                    "ms_per_launch": conv1b_ms, "frames_per_launch": B,
+                    "timing": "CUDA events around the launch in a single-stream pass of the same step"}
         conv_ms = sum(v for k, v in stage if k.startswith("conv") and k != "conv1a" or k.startswith("edge0")
                       or k.startswith("edge1"))  # tensor-core layers (the fused launch includes conv1a's 0.42 GFLOP)
         cpu_t, cpu_n = 0.0, 0
@@ -332,7 +352,7 @@ def run_b200(args, rank, local_rank, world):
                 "config": {"workload": "EuRoC 752x480 batch-%d synthetic frames per GPU: extract + point-pair graph "
                                        "+ association of every frame vs %d resident map points" % (B, args.map_rows),
                            "batch_per_gpu": B, "map_rows": args.map_rows, "sharding": "frames (no collective)",
-                           "e2e_contexts_in_flight": len(ctxs),
+                           "device_contexts_in_flight": n_dev_ctx, "e2e_contexts_in_flight": len(ctxs),
                            "l2": "per-step working set ~3.4 GB of activations streams through the 126 MB L2 "
                                  "(inputs larger than L2; no explicit flush)"},
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
@@ -362,7 +382,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--map-rows", type=int, default=MAP_ROWS)
-    ap.add_argument("--e2e-streams", type=int, default=3, help="contexts (host threads) in flight in the e2e arm")
+    ap.add_argument("--dev-streams", type=int, default=2, help="contexts in flight in the device-timed arm")
+    ap.add_argument("--e2e-streams", type=int, default=4, help="contexts (host threads) in flight in the e2e arm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
