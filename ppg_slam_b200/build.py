@@ -20,6 +20,7 @@ SOURCES = {
     "api.cu": [],
     "conv_tc.cu": [],
     "net_direct.cu": [],
+    "conv1a_tc.cu": [],
     "post.cu": ["-fmad=false"],
     "assoc.cu": ["-fmad=false"],
 }

@@ -88,6 +88,12 @@ __global__ void __launch_bounds__(256, 2) conv1a_kernel(const uint8_t* __restric
 // sub-partition, slower than 32 FFMA lanes.  The FMA kernel stays.
 cudaError_t conv1a_launch(const uint8_t* gray, const float* w, const float* bias, __half* out, int B, int H, int W,
                           cudaStream_t st) {
+    static int use_tc = -1;  // tcgen05 version (conv1a_tc.cu) unless PPG_CONV1A_TC=0 (A/B comparison)
+    if (use_tc < 0) {
+        const char* e = getenv("PPG_CONV1A_TC");
+        use_tc = (e && !atoi(e)) ? 0 : 1;
+    }
+    if (use_tc && conv1a_tc_supported(H, W)) return conv1a_tc_launch(gray, w, bias, out, B, H, W, st);
     dim3 grid((W + 31) / 32, (H + 31) / 32, B);
     conv1a_kernel<<<grid, 256, 0, st>>>(gray, w, bias, out, H, W);
     return cudaGetLastError();
