@@ -189,6 +189,171 @@ __global__ void __launch_bounds__(C1_THREADS) conv1a_tc_kernel(const uint8_t* __
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Edge decoder tail on tcgen05: conv3x3 16->16 (BN folded) + ReLU + pixel_shuffle(2) + conv1x1 4->2 + softmax[:,1]
+// (EdgeHeatmap.pt tail, PPGExtractor.cpp:154, :242).  The mma.sync version spent ~40 cycles per legacy HMMA
+// (0.12 ms per 32 frames for 4.3 MB/frame of traffic).  Here one output tile of 8 x 16 low-res pixels is nine
+// M128 N16 K16 instructions whose A operands are windows into ONE halo tile, as in conv_tc2_kernel, but in the
+// no-swizzle layout: the halo is stored as two planes (channels 0-7 / 8-15) of [18 x 10 pixels][16 B], so the 8
+// pixels of an MMA row group are one contiguous 128-byte core matrix for ANY tap offset (start address = 16-byte
+// granular), the next row group is one halo row further (SBO = 160 B) and the second K half one plane further
+// (LBO = 2880 B).  Worker threads load the halo (3 x 16 B each), the MMA warp issues, the workers' epilogue does
+// bias/ReLU/pixel-shuffle/1x1/softmax for their pixel and writes the 2 x 2 full-resolution scores.
+constexpr int ET_THREADS = 160, ET_TW = 8, ET_TH = 16, ET_HP = (ET_TW + 2) * (ET_TH + 2);  // 180 halo pixels
+constexpr int ET_PLANE = ET_HP * 16, ET_A_BYTES = 2 * ET_PLANE;                              // 2880, 5760
+
+__global__ void __launch_bounds__(ET_THREADS) edge_tail_tc_kernel(const __half* __restrict__ in, const float* __restrict__ w3,
+                                                                  const float* __restrict__ b3, const float* __restrict__ w1,
+                                                                  const float* __restrict__ b1, float* __restrict__ heat,
+                                                                  int Hh, int Wh, int tiles_x, int tiles_y, int total_tiles) {
+    extern __shared__ __align__(1024) uint8_t et_smem[];
+    uint8_t* sA = et_smem;                    // 2 stages x 5760 B
+    uint8_t* sB = et_smem + 2 * ET_A_BYTES;   // 9 taps x [2 k-cores][16 rows][16 B] = 9 x 512 B
+    uint64_t* afull = reinterpret_cast<uint64_t*>(sB + 9 * 512);
+    uint64_t* tfull = afull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
+    const int warp = threadIdx.x >> 5, t = threadIdx.x;
+
+    if (t == 0) {
+        for (int s = 0; s < 2; s++) {
+            ptx::mbar_init(&afull[s], 128);
+            ptx::mbar_init(&tfull[s], 1);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 4) {
+        ptx::tmem_alloc(tmem_slot, 32);
+        ptx::tmem_relinquish();
+    }
+    // weights: w3 [16 co][9 taps][16 ci] fp32 -> per tap [k-core][co][8 ci] fp16
+    for (int i = t; i < 9 * 2 * 16; i += ET_THREADS) {
+        const int tap = i / 32, kc = (i >> 4) & 1, co = i & 15;
+        const float* src = w3 + ((size_t)co * 9 + tap) * 16 + kc * 8;
+        *reinterpret_cast<uint4*>(sB + tap * 512 + kc * 256 + co * 16) =
+            make_uint4(pack_h2(src[0], src[1]), pack_h2(src[2], src[3]), pack_h2(src[4], src[5]), pack_h2(src[6], src[7]));
+    }
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto decode = [&](int i, int& n, int& y0, int& x0) {
+        const int tile = blockIdx.x + i * gridDim.x, per = tiles_x * tiles_y;
+        n = tile / per;
+        const int r = tile - n * per, ty = r / tiles_x;
+        y0 = ty * ET_TH;
+        x0 = (r - ty * tiles_x) * ET_TW;
+    };
+
+    if (warp == 4) {
+        const uint32_t idesc = ptx::make_idesc_f16(128, 16, 0);
+        const uint32_t b_addr = ptx::smem_u32(sB);
+        for (int i = 0; i < my_tiles; i++) {
+            const int s = i & 1;
+            ptx::mbar_wait(&afull[s], (i >> 1) & 1);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint32_t a_addr = ptx::smem_u32(sA + s * ET_A_BYTES);
+#pragma unroll
+                for (int tap = 0; tap < 9; tap++) {
+                    const uint64_t adesc =
+                        make_nosw_desc(a_addr + (uint32_t)((tap / 3) * (ET_TW + 2) + tap % 3) * 16u, ET_PLANE, (ET_TW + 2) * 16);
+                    const uint64_t bdesc = make_nosw_desc(b_addr + tap * 512, 256, 128);
+                    ptx::umma_f16(tmem_base + s * 16, adesc, bdesc, idesc, (uint32_t)(tap != 0));
+                }
+                ptx::umma_commit(&tfull[s]);
+            }
+            __syncwarp();
+        }
+    } else {
+        float bias_r[16], s1[8];
+#pragma unroll
+        for (int c = 0; c < 16; c++) bias_r[c] = b3[c];
+#pragma unroll
+        for (int c = 0; c < 8; c++) s1[c] = w1[c];
+        const float sb10 = b1[0], sb11 = b1[1];
+        const int H = Hh * 2, W = Wh * 2;
+        // halo chunks of this thread: c = t, t + 128, t + 256 (< 360): plane c / 180, halo pixel c % 180
+        auto fetch = [&](int i, uint4 (&v)[3]) {
+#pragma unroll
+            for (int e = 0; e < 3; e++) v[e] = make_uint4(0u, 0u, 0u, 0u);
+            if (i >= my_tiles) return;
+            int n, y0, x0;
+            decode(i, n, y0, x0);
+            const __half* src = in + (size_t)n * Hh * Wh * 16;
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                const int c = t + e * 128;
+                if (c < 2 * ET_HP) {
+                    const int plane = c / ET_HP, hp = c - plane * ET_HP;
+                    const int hy = hp / (ET_TW + 2), hx = hp - hy * (ET_TW + 2);
+                    const int y = y0 - 1 + hy, x = x0 - 1 + hx;
+                    if (y >= 0 && y < Hh && x >= 0 && x < Wh)
+                        v[e] = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)y * Wh + x) * 16 + plane * 8));
+                }
+            }
+        };
+        uint4 hv[3];
+        fetch(0, hv);
+        for (int i = 0; i <= my_tiles; i++) {
+            if (i < my_tiles) {
+                const int s = i & 1;
+                uint8_t* a = sA + s * ET_A_BYTES;
+#pragma unroll
+                for (int e = 0; e < 3; e++) {
+                    const int c = t + e * 128;
+                    if (c < 2 * ET_HP) *reinterpret_cast<uint4*>(a + c * 16) = hv[e];  // plane-major = chunk index order
+                }
+                ptx::fence_proxy_async();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&afull[s]);
+                fetch(i + 1, hv);
+            }
+            if (i > 0) {
+                const int j = i - 1, s = j & 1;
+                ptx::mbar_wait(&tfull[s], (j >> 1) & 1);
+                ptx::tc_fence_after();
+                uint32_t r[16];
+                ptx::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + s * 16, r);
+                ptx::tmem_ld_wait();
+                int n, y0, x0;
+                decode(j, n, y0, x0);
+                const int y = y0 + (t >> 3), x = x0 + (t & 7);  // TMEM lane = 8 * row + column of the tile
+                if (y < Hh && x < Wh) {
+                    float* dst = heat + (size_t)n * H * W;
+#pragma unroll
+                    for (int ii = 0; ii < 2; ii++) {
+                        float hvv[2];
+#pragma unroll
+                        for (int jj = 0; jj < 2; jj++) {
+                            // pixel_shuffle(2): full-res channel c at (2y+ii, 2x+jj) = low-res channel 4c + 2ii + jj
+                            float l0 = sb10, l1 = sb11;
+#pragma unroll
+                            for (int c = 0; c < 4; c++) {
+                                const int ch = 4 * c + 2 * ii + jj;
+                                const float v = fmaxf(__uint_as_float(r[ch]) + bias_r[ch], 0.f);
+                                l0 = fmaf(s1[c], v, l0);
+                                l1 = fmaf(s1[4 + c], v, l1);
+                            }
+                            const float m = fmaxf(l0, l1);
+                            const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+                            hvv[jj] = e1 / (e0 + e1);  // softmax(dim=1)[:,1], PPGExtractor.cpp:242
+                        }
+                        *reinterpret_cast<float2*>(dst + (size_t)(2 * y + ii) * W + 2 * x) = make_float2(hvv[0], hvv[1]);
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 32);
+    }
+}
+
 }  // namespace
 
 // -> false when the shape is not covered (the frame must be a whole number of 128-pixel tiles)
@@ -213,6 +378,26 @@ cudaError_t conv1a_tc_launch(const uint8_t* gray, const float* w, const float* b
     const int grid = total < sms * 4 ? total : sms * 4;
     if (grid <= 0) return cudaSuccess;
     conv1a_tc_kernel<<<grid, C1_THREADS, SMEM, st>>>(gray, w, bias, out, H, W, total, swap);
+    return cudaGetLastError();
+}
+
+cudaError_t edge_tail_tc_launch(const __half* in, const float* w3, const float* b3, const float* w1, const float* b1,
+                                float* heat, int B, int Hh, int Wh, cudaStream_t st) {
+    // 28 KB of dynamic shared memory per CTA -> 8 CTAs per SM (32 TMEM columns each)
+    constexpr int SMEM = 28 * 1024;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(edge_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const int tiles_x = (Wh + ET_TW - 1) / ET_TW, tiles_y = (Hh + ET_TH - 1) / ET_TH, total = tiles_x * tiles_y * B;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = total < sms * 8 ? total : sms * 8;
+    if (grid <= 0) return cudaSuccess;
+    edge_tail_tc_kernel<<<grid, ET_THREADS, SMEM, st>>>(in, w3, b3, w1, b1, heat, Hh, Wh, tiles_x, tiles_y, total);
     return cudaGetLastError();
 }
 

@@ -222,6 +222,12 @@ __global__ void __launch_bounds__(128) edge_tail_kernel(const __half* __restrict
 
 cudaError_t edge_tail_launch(const __half* in, const float* w3, const float* b3, const float* w1, const float* b1,
                              float* heat, int B, int Hh, int Wh, cudaStream_t st) {
+    static int use_tc = -1;  // tcgen05 version (conv1a_tc.cu) unless PPG_EDGE_TAIL_TC=0 (A/B comparison)
+    if (use_tc < 0) {
+        const char* e = getenv("PPG_EDGE_TAIL_TC");
+        use_tc = (e && !atoi(e)) ? 0 : 1;
+    }
+    if (use_tc) return edge_tail_tc_launch(in, w3, b3, w1, b1, heat, B, Hh, Wh, st);
     const int tiles_x = (Wh + 15) / 16, tiles_y = (Hh + 7) / 8, total = tiles_x * tiles_y * B;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

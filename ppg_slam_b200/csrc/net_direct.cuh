@@ -10,6 +10,8 @@ cudaError_t conv1a_launch(const uint8_t* gray, const float* w, const float* bias
 bool conv1a_tc_supported(int H, int W);  // conv1a_tc.cu: the tcgen05 version of conv1a
 cudaError_t conv1a_tc_launch(const uint8_t* gray, const float* w, const float* bias, __half* out, int B, int H, int W,
                              cudaStream_t st);
+cudaError_t edge_tail_tc_launch(const __half* in, const float* w3, const float* b3, const float* w1, const float* b1,
+                                float* heat, int B, int Hh, int Wh, cudaStream_t st);  // conv1a_tc.cu
 cudaError_t edge_tail_launch(const __half* in, const float* w3, const float* b3, const float* w1, const float* b1,
                              float* heat, int B, int Hh, int Wh, cudaStream_t st);
 cudaError_t junction_d2s_launch(const float* logits, float* prob, int B, int Hc, int Wc, int ld, cudaStream_t st);
