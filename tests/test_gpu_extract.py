@@ -51,6 +51,29 @@ def test_dense_maps_within_tolerance(ex_euroc, net, seed):
     assert rec["n_kp"] > 50
 
 
+@pytest.mark.parametrize("cam", [cameras.TUMVI, cameras.UMA, cameras.TUMVI1024], ids=lambda c: c.name)
+def test_dense_maps_other_shapes(net, cam):
+    """The BASELINE.json shapes besides EuRoC (TUM-VI 512x512, UMA-VI 1024x768, TUM-VI-1024): the tensor-core
+    networks stay within the same tolerances, and the full path finds a plausible number of keypoints."""
+    from ppg_slam_b200 import capi
+    e = capi.Extractor(cam, max_batch=1)
+    try:
+        g = synth.frame(7, cam.width, cam.height)
+        rec = e.run([g], allow_capacity=True)[0]
+        m = e.get_maps(0)
+        ref = net.forward_u8(g)
+        assert np.abs(m["prob"] - ref["prob"]).max() <= PROB_TOL
+        assert np.abs(m["heat"] - ref["heat"]).max() <= HEAT_TOL
+        a, b = m["desc"].reshape(256, -1), ref["desc"].reshape(256, -1)
+        cos = (a * b).sum(0) / (np.linalg.norm(a, axis=0) * np.linalg.norm(b, axis=0) + 1e-12)
+        assert cos.min() >= COS_MIN
+        assert rec["n_kp"] > 50
+        for name, d, r in e.selftest_conv():
+            assert d <= 2e-2 * max(1.0, r), "%s %s: tcgen05 vs CUDA-core conv differ by %g" % (cam.name, name, d)
+    finally:
+        e.close()
+
+
 @pytest.mark.parametrize("cam,seeds", [(cameras.EUROC, [0, 1, 2, 5]), (cameras.TUMVI, [1, 4]),
                                        (cameras.UMA, [2]), (cameras.TUMVI1024, [0])], ids=lambda v: getattr(v, "name", str(v)))
 def test_post_bit_exact_from_reference_maps(net, cam, seeds):
