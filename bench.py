@@ -91,9 +91,17 @@ class ClockSampler:
         return out
 
 
+CAMERA = "EuRoC"  # --camera: EuRoC (the benchmark configuration), TUM-VI, TUM-VI-1024, UMA-VI (other BASELINE shapes)
+
+
+def _cam():
+    from ppg_slam_b200 import cameras
+    return cameras.ALL[CAMERA]
+
+
 def make_workload(batch, seed0=0):
-    from ppg_slam_b200 import cameras, synth
-    cam = cameras.EUROC
+    from ppg_slam_b200 import synth
+    cam = _cam()
     frames = [synth.frame(seed0 + s, cam.width, cam.height) for s in range(batch)]
     return cam, frames
 
@@ -121,7 +129,7 @@ def cpu_reference_pass(n_frames, seed0, threads, rows=MAP_ROWS):
     from oracle.net_ref import NetRef
     from ppg_slam_b200 import cameras, synth
     torch.set_num_threads(threads)
-    cam = cameras.EUROC
+    cam = _cam()
     net = cpu_reference_pass.net if hasattr(cpu_reference_pass, "net") else NetRef()
     cpu_reference_pass.net = net
     frames = [synth.frame(seed0 + s, cam.width, cam.height) for s in range(n_frames)]
@@ -156,11 +164,11 @@ def run_reference(args, rank, world):
         dt, _ = cpu_reference_pass(sample, 2000 + k * sample, threads)
         t += dt
     fps = args.steps * sample / t
-    line = {"metric": "frames/sec extract+associate at 752x480", "value": fps, "unit": "frames/s",
+    line = {"metric": "frames/sec extract+associate at %dx%d" % (_cam().width, _cam().height), "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": "EuRoC 752x480 synthetic frames, extract + point-pair graph + association vs "
+            "config": {"workload": CAMERA + " synthetic frames, extract + point-pair graph + association vs "
                                    "%d map points (CPU reference path: %d-frame sample per step)" % (MAP_ROWS, sample)},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": "%d frames per step x %d steps; networks torch-CPU fp32 with %d threads, "
@@ -322,16 +330,17 @@ def run_b200(args, rank, local_rank, world):
         fused = "conv1a+conv1b" in sd
         conv1b_ms = sd.get("conv1a+conv1b") or sd.get("conv1b")
         roof = None
+        scale = cam.width * cam.height / (752.0 * 480.0)  # conv FLOPs scale with the pixel count
         if conv1b_ms:
             # algorithmic FLOPs of the launch: conv1b, plus conv1a (2 * 0.21 GMAC) when it is fused into the kernel
-            ach = (CONV1B_GFLOP_PER_FRAME + (0.416 if fused else 0.0)) * B / conv1b_ms  # GFLOP / ms = TFLOP/s
+            ach = (CONV1B_GFLOP_PER_FRAME + (0.416 if fused else 0.0)) * scale * B / conv1b_ms  # GFLOP / ms = TFLOP/s
             traffic = None
             tp = os.path.join(ROOT, "profiles", "conv1b_traffic.json")
             if os.path.exists(tp):
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             roof = {"bound": "tensor",
-                    "kernel": "conv_tc2_kernel[%sconv1b 64->64 3x3 @752x480 + ReLU + 2x2 pool]" %
-                              ("conv1a 1->64 producer + " if fused else ""),
+                    "kernel": "conv_tc2_kernel[%sconv1b 64->64 3x3 @%dx%d + ReLU + 2x2 pool]" %
+                              ("conv1a 1->64 producer + " if fused else "", cam.width, cam.height),
                     "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
                     "peak_source": how + " (sustained bf16 cuBLAS; fp16 runs on the same pipe)",
                     "ms_per_launch": conv1b_ms, "frames_per_launch": B,
@@ -345,12 +354,13 @@ def run_b200(args, rank, local_rank, world):
             dt, n = cpu_reference_pass(4, 3000 + cpu_n, cpu_threads)
             cpu_t += dt
             cpu_n += n
-        line = {"metric": "frames/sec extract+associate at 752x480", "value": fps, "unit": "frames/s",
+        line = {"metric": "frames/sec extract+associate at %dx%d" % (_cam().width, _cam().height), "value": fps, "unit": "frames/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
                 "data": "synthetic",
-                "config": {"workload": "EuRoC 752x480 batch-%d synthetic frames per GPU: extract + point-pair graph "
-                                       "+ association of every frame vs %d resident map points" % (B, args.map_rows),
+                "config": {"workload": "%s %dx%d batch-%d synthetic frames per GPU: extract + point-pair graph "
+                                       "+ association of every frame vs %d resident map points" %
+                                       (CAMERA, cam.width, cam.height, B, args.map_rows),
                            "batch_per_gpu": B, "map_rows": args.map_rows, "sharding": "frames (no collective)",
                            "device_contexts_in_flight": n_dev_ctx, "e2e_contexts_in_flight": len(ctxs),
                            "l2": "per-step working set ~3.4 GB of activations streams through the 126 MB L2 "
@@ -362,7 +372,7 @@ def run_b200(args, rank, local_rank, world):
                 "clocks": clk,
                 "roofline": roof,
                 "stages_ms_per_step": {k: round(v, 4) for k, v in stage},
-                "conv_tflops_all_tc_layers": (GFLOP_PER_FRAME - 0.84) * B / conv_ms if conv_ms else None,
+                "conv_tflops_all_tc_layers": (GFLOP_PER_FRAME - 0.84) * scale * B / conv_ms if conv_ms else None,
                 "cpu_baseline": {"value": cpu_n / cpu_t, "unit": "frames/s", "cores": cpu_threads, "kind": "port",
                                  "sample": "%d frames (same synthetic workload); networks torch-CPU fp32 on %d "
                                            "threads, post-processing + association single-threaded C oracle" %
@@ -384,7 +394,11 @@ def main():
     ap.add_argument("--map-rows", type=int, default=MAP_ROWS)
     ap.add_argument("--dev-streams", type=int, default=2, help="contexts in flight in the device-timed arm")
     ap.add_argument("--e2e-streams", type=int, default=4, help="contexts (host threads) in flight in the e2e arm")
+    ap.add_argument("--camera", default="EuRoC", choices=["EuRoC", "TUM-VI", "TUM-VI-1024", "UMA-VI"],
+                    help="frame shape / calibration; EuRoC 752x480 is the benchmark configuration")
     args = ap.parse_args()
+    global CAMERA
+    CAMERA = args.camera
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
