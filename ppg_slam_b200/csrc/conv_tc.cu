@@ -274,11 +274,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             ptx::mbar_wait(&tfull[acc], aph);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-            for (int c0 = 0; c0 < p.N; c0 += 16) {
-                uint32_t r[16];
-                ptx::tmem_ld16(taddr + c0, r);
-                ptx::tmem_ld_wait();
-                epilogue_store<1, 16>(p, cb, r, c0, t.n, y, x, inb, lane);
+            if ((p.N & 63) == 0) {
+                // 64 columns per tcgen05.ld; the pool is the reduce-scatter of epilogue64 (48 SHFL per 64 channels
+                // instead of 128 -- SHFL shares the shared-memory data pipe with the tensor core's operand reads)
+                for (int c0 = 0; c0 < p.N; c0 += 64) {
+                    uint32_t r[64];
+                    ptx::tmem_ld64(taddr + c0, r);
+                    ptx::tmem_ld_wait();
+                    epilogue64<1, 16>(p, cb, r, c0, t.n, y, x, inb, lane);
+                }
+            } else {
+                for (int c0 = 0; c0 < p.N; c0 += 16) {
+                    uint32_t r[16];
+                    ptx::tmem_ld16(taddr + c0, r);
+                    ptx::tmem_ld_wait();
+                    epilogue_store<1, 16>(p, cb, r, c0, t.n, y, x, inb, lane);
+                }
             }
             ptx::tc_fence_before();
             __syncwarp();
