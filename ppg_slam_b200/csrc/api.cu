@@ -395,7 +395,7 @@ void ppg_destroy(ppg_ctx* c) {
                     c->undist_lut, c->remap_lut, c->d_out, c->post.state, c->post.state2, c->post.cand, c->post.counters,
                     c->post.pair_bits, c->post.row_cnt, c->post.l_score, c->post.l_edge, c->post.row_prefix,
                     c->post.row_off, c->post.c_se, c->post.c_dist, c->post.c_dirf, c->post.c_dirb, c->post.inter,
-                    c->post.inter_cnt, c->post.inter_off, c->post.inter_pool, c->post.alive_g};
+                    c->post.inter_cnt, c->post.inter_off, c->post.inter_pool, c->post.alive_g, c->post.sym_bits};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (c->h_gray) cudaFreeHost(c->h_gray);
@@ -636,6 +636,7 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
     PPG_CUDA(c, dalloc(&p.cand, B * HW));
     PPG_CUDA(c, dalloc(&p.counters, (size_t)B * 8));
     PPG_CUDA(c, dalloc(&p.pair_bits, (size_t)B * p.max_kp * p.pair_words));
+    PPG_CUDA(c, dalloc(&p.sym_bits, (size_t)B * p.max_kp * p.pair_words));
     PPG_CUDA(c, dalloc(&p.row_cnt, (size_t)B * p.max_kp));
     PPG_CUDA(c, dalloc(&p.row_prefix, (size_t)B * p.max_kp * p.pair_words));
     PPG_CUDA(c, dalloc(&p.row_off, (size_t)B * (p.max_kp + 1)));

@@ -485,11 +485,12 @@ assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // DescriptorDistance in the fixed order shared with the oracle (ppgo_descriptor_distance): lane l sums
 // elements l, l+32, ... in order, then an xor butterfly 16,8,4,2,1; every lane ends with the same value.
-__device__ __forceinline__ float exact_distance(const float* __restrict__ a, const float* __restrict__ b, int lane) {
+// `av` = the map row's elements lane, lane + 32, ... held in registers across the candidates of a row.
+__device__ __forceinline__ float exact_distance(const float (&av)[8], const float* __restrict__ b, int lane) {
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const float d = a[lane + 32 * k] - b[lane + 32 * k];
+        const float d = av[k] - b[lane + 32 * k];
         s = s + d * d;
     }
 #pragma unroll
@@ -537,7 +538,9 @@ __global__ void __launch_bounds__(256) assoc_rescore_kernel(const RescoreParams 
     const size_t o = (size_t)f * p.max_rows + row;
     const int n = min(p.src.n_of(f), p.ncap);
     const RowParam rp = p.rowp[o];
-    const float* a = p.map_f32 + (size_t)row * 256;
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = p.map_f32[(size_t)row * 256 + lane + 32 * k];
     const float* fdesc = p.src.desc_of(f);
     const uint32_t* korder = p.korder + (size_t)f * p.ncap;
     float b1 = 1e6f, b2 = 1e6f;  // Matcher.cpp:248-249 initial values
@@ -547,12 +550,19 @@ __global__ void __launch_bounds__(256) assoc_rescore_kernel(const RescoreParams 
     if (!exact_all) {
         const int4 c4 = *reinterpret_cast<const int4*>(p.cand + o * 4);
         const int cs[4] = {c4.x, c4.y, c4.z, c4.w};
+        // the four candidates' rows are fetched and reduced together (independent chains; one at a time the kernel
+        // was bound by 4 dependent rounds of load latency per row), then ranked in order
+        float dk[4];
+        uint32_t ok[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (cs[k] < 0) continue;
-            const float d = exact_distance(a, fdesc + (size_t)cs[k] * 256, lane);
-            top2_update(d, korder[cs[k]], cs[k], b1, o1, i1, b2, o2, i2);
+            const int ck = cs[k] < 0 ? 0 : cs[k];
+            dk[k] = exact_distance(a, fdesc + (size_t)ck * 256, lane);
+            ok[k] = korder[ck];
         }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (cs[k] >= 0) top2_update(dk[k], ok[k], cs[k], b1, o1, i1, b2, o2, i2);
         const float g = p.guard[o];
         if (g < INFINITY) {
             // bf16 operands: |dot_bf16 - dot| <= (2^-8 + 2^-16) |a||b| (+ fp32 accumulation); in squared distance x2

@@ -484,6 +484,7 @@ __global__ void __launch_bounds__(256) pair_test_kernel(const PostParams p) {
     const float* heat = p.heat_final + (size_t)b * p.H * p.W;
     uint32_t* bits = p.pair_bits + ((size_t)b * p.max_kp + i) * p.pair_words;
     uint16_t* prefix = p.row_prefix + ((size_t)b * p.max_kp + i) * p.pair_words;
+    uint32_t* sym = p.sym_bits + ((size_t)b * p.max_kp + i) * p.pair_words;
     const float xi = sx[i], yi = sy[i];
     const bool iout = so[i] != 0;
     const float th = p.line_heatmap_thresh;
@@ -504,6 +505,7 @@ __global__ void __launch_bounds__(256) pair_test_kernel(const PostParams p) {
         const unsigned m = __ballot_sync(FULL, pass);
         if (lane == 0) {
             bits[w] = m;
+            sym[w] = m;  // cand_build_kernel ORs the transposed bits in
             prefix[w] = (uint16_t)total;
         }
         total += __popc(m);
@@ -578,6 +580,7 @@ __global__ void __launch_bounds__(256) cand_build_kernel(const PostParams p) {
                 T.dirf[id] = d;
                 T.dirb[id] = r;
                 T.se[id] = (uint32_t)i | ((uint32_t)j << 16);
+                atomicOr(p.sym_bits + ((size_t)b * p.max_kp + j) * p.pair_words + (i >> 5), 1u << (i & 31));
             }
         }
         pos += __popc(mw);
@@ -611,37 +614,60 @@ __device__ __forceinline__ int interact_one(const PostParams& p, const CandTable
 }
 
 // One pass over the earlier candidates that share an endpoint with candidate (i,j):
-//   side i: old lines (q,i) with q < i (rows above), and (i,q) with i < q < j (same row, earlier columns)
-//   side j: old lines (q,j) with q < i (rows above row i); later rows are not created yet
-// Entries are written in ascending q (= the order of the reference's adjacency lists) while they fit.
+//   side i: old lines (q,i) with q < i (rows above) and (i,q) with i < q < j (same row, earlier columns)
+//           = the neighbours q < j of i in the symmetric pair matrix
+//   side j: old lines (q,j) with q < i (rows above row i; later rows are not created yet) = the neighbours q < i of j
+// Lane l owns word l of the two rows (max_kp <= 1024) and evaluates only the set bits; entries are written in
+// ascending q (= the order of the reference's adjacency lists) while they fit.  (The first version tested all
+// q < j with strided reads of the upper-triangular matrix: 0.11 ms per 32 frames.)
+__device__ __forceinline__ uint32_t bits_below(uint32_t w, int lane, int limit) {  // keep bits whose index < limit
+    const int lo = lane * 32;
+    if (lo >= limit) return 0u;
+    if (limit - lo >= 32) return w;
+    return w & ((1u << (limit - lo)) - 1u);
+}
+
 __device__ __forceinline__ void interact_scan(const PostParams& p, const CandTables& T, int b, const int* row_off,
-                                              const uint32_t* bits, int i, int j, float dirf, float dirb, float dist_new,
-                                              int lane, uint16_t* ent_i, int cap_i, uint16_t* ent_j, int cap_j,
-                                              int* out_cnt_i, int* out_cnt_j) {
-    int cnt_i = 0, cnt_j = 0;
-    for (int q0 = 0; q0 < j; q0 += 32) {
-        const int q = q0 + lane;
-        int ti = -1, tj = -1;
-        if (q < i) {
-            if ((bits[(size_t)q * p.pair_words + (i >> 5)] >> (i & 31)) & 1u) ti = interact_one(p, T, b, row_off, i, q, dirf, dist_new);
-            if ((bits[(size_t)q * p.pair_words + (j >> 5)] >> (j & 31)) & 1u) tj = interact_one(p, T, b, row_off, j, q, dirb, dist_new);
-        } else if (q > i && q < j) {
-            if ((bits[(size_t)i * p.pair_words + (q >> 5)] >> (q & 31)) & 1u) ti = interact_one(p, T, b, row_off, i, q, dirf, dist_new);
-        }
-        const unsigned mi = __ballot_sync(FULL, ti >= 0), mj = __ballot_sync(FULL, tj >= 0);
-        if (ti >= 0) {
-            const int k = cnt_i + __popc(mi & ((1u << lane) - 1u));
-            if (k < cap_i) ent_i[k] = (uint16_t)(q | (ti << 15));
-        }
-        if (tj >= 0) {
-            const int k = cnt_j + __popc(mj & ((1u << lane) - 1u));
-            if (k < cap_j) ent_j[k] = (uint16_t)(q | (tj << 15));
-        }
-        cnt_i += __popc(mi);
-        cnt_j += __popc(mj);
+                                              const uint32_t* sym, int nwords, int i, int j, float dirf, float dirb,
+                                              float dist_new, int lane, uint16_t* ent_i, int cap_i, uint16_t* ent_j,
+                                              int cap_j, int* out_cnt_i, int* out_cnt_j) {
+    uint32_t wi = 0u, wj = 0u;
+    if (lane < nwords) {
+        wi = bits_below(sym[(size_t)i * p.pair_words + lane], lane, j);
+        wj = bits_below(sym[(size_t)j * p.pair_words + lane], lane, i);
     }
-    *out_cnt_i = cnt_i;
-    *out_cnt_j = cnt_j;
+    uint32_t hit_i = 0u, typ_i = 0u, hit_j = 0u, typ_j = 0u;
+    for (uint32_t m = wi; m; m &= m - 1) {
+        const int bit = __ffs(m) - 1;
+        const int ty = interact_one(p, T, b, row_off, i, lane * 32 + bit, dirf, dist_new);
+        if (ty >= 0) {
+            hit_i |= 1u << bit;
+            typ_i |= (uint32_t)ty << bit;
+        }
+    }
+    for (uint32_t m = wj; m; m &= m - 1) {
+        const int bit = __ffs(m) - 1;
+        const int ty = interact_one(p, T, b, row_off, j, lane * 32 + bit, dirb, dist_new);
+        if (ty >= 0) {
+            hit_j |= 1u << bit;
+            typ_j |= (uint32_t)ty << bit;
+        }
+    }
+    __syncwarp();
+    const int ci = __popc(hit_i), cj = __popc(hit_j);
+    const int inc_i = warp_incl_scan(ci, lane), inc_j = warp_incl_scan(cj, lane);
+    int k = inc_i - ci;
+    for (uint32_t m = hit_i; m; m &= m - 1, k++) {
+        const int bit = __ffs(m) - 1;
+        if (k < cap_i) ent_i[k] = (uint16_t)((lane * 32 + bit) | (((typ_i >> bit) & 1u) << 15));
+    }
+    k = inc_j - cj;
+    for (uint32_t m = hit_j; m; m &= m - 1, k++) {
+        const int bit = __ffs(m) - 1;
+        if (k < cap_j) ent_j[k] = (uint16_t)((lane * 32 + bit) | (((typ_j >> bit) & 1u) << 15));
+    }
+    *out_cnt_i = __shfl_sync(FULL, inc_i, 31);
+    *out_cnt_j = __shfl_sync(FULL, inc_j, 31);
 }
 
 // Lists longer than INTER_K per side (dense fans of near-parallel candidates) spill to a per-frame pool: the warp
@@ -660,9 +686,11 @@ __global__ void __launch_bounds__(256) interact_kernel(const PostParams p) {
     const int i = se & 0xffff, j = se >> 16;
     const float dist_new = T.dist[c], dirf = T.dirf[c], dirb = T.dirb[c];
     uint16_t* ent = p.inter + ((size_t)b * p.pair_cap + c) * (2 * INTER_K);
-    const uint32_t* bits = p.pair_bits + (size_t)b * p.max_kp * p.pair_words;
+    const uint32_t* sym = p.sym_bits + (size_t)b * p.max_kp * p.pair_words;
+    const int nwords = (n + 31) >> 5;
     int cnt_i, cnt_j;
-    interact_scan(p, T, b, row_off, bits, i, j, dirf, dirb, dist_new, lane, ent, INTER_K, ent + INTER_K, INTER_K, &cnt_i, &cnt_j);
+    interact_scan(p, T, b, row_off, sym, nwords, i, j, dirf, dirb, dist_new, lane, ent, INTER_K, ent + INTER_K, INTER_K,
+                  &cnt_i, &cnt_j);
     uint32_t off = 0xffffffffu;
     if (cnt_i > INTER_K || cnt_j > INTER_K) {
         int base = 0;
@@ -671,7 +699,8 @@ __global__ void __launch_bounds__(256) interact_kernel(const PostParams p) {
         if (base + cnt_i + cnt_j <= p.pool_cap) {
             uint16_t* pool = p.inter_pool + (size_t)b * p.pool_cap + base;
             int ci2, cj2;
-            interact_scan(p, T, b, row_off, bits, i, j, dirf, dirb, dist_new, lane, pool, cnt_i, pool + cnt_i, cnt_j, &ci2, &cj2);
+            interact_scan(p, T, b, row_off, sym, nwords, i, j, dirf, dirb, dist_new, lane, pool, cnt_i, pool + cnt_i,
+                          cnt_j, &ci2, &cj2);
             off = (uint32_t)base;
         } else {
             off = 0xfffffffeu;  // pool exhausted: reported as ST_OVF_DEGREE by lines_kernel

@@ -58,6 +58,7 @@ struct PostParams {
     int acc_cap;        // NMS survivors that can be ranked (power of two)
     uint32_t* pair_bits;  // [B][max_kp][pair_words] bit j of row i: pair (i,j) passed the 3-point test
     int pair_words;
+    uint32_t* sym_bits;   // [B][max_kp][pair_words] the same matrix made symmetric (both endpoints' rows)
     int* row_cnt;       // [B][max_kp]
     uint16_t* row_prefix;  // [B][max_kp][pair_words] set bits of the row before each word
     int* row_off;       // [B][max_kp + 1] candidate id of the first pair of each row
