@@ -185,6 +185,12 @@ typedef struct {
  *                            SearchByProjection(F, KF, sFound, th, descDist)    :1337-1411  max_dist = descDist
  *                            Fuse(KF, vpMapPoints, th)                          :897-1036   max_dist = TH_LOW,
  *                                                                               e2_max = 5.99 (:1000-1005)
+ *                            SearchByProjection(KF, Scw, vpPoints, vpMatched, th, ratioHamming)
+ *                                                                               :479-568    max_dist = TH_LOW * ratioHamming,
+ *                                                                               free_mask = !vpMatched[idx]
+ *                            Fuse(KF, Scw, vpPoints, th, vpReplacePoint)        :1038-1135  max_dist = TH_LOW
+ *                            SearchBySim3(KF1, KF2, vpMatches12, S12, th)       :1149-1335  both directions,
+ *                                                                               max_dist = TH_HIGH, free_mask all ones
  *                          view_cos is ignored. */
 enum { PPG_SEARCH_EXTEND_MAP = 0, PPG_SEARCH_WINDOW = 1 };
 

@@ -188,6 +188,12 @@ inline SearchResult search_local_points(ppg_ctx* ctx, Frame& F, const std::vecto
 //        free_mask[i] = !F.mvpMapPoints[i]                                                               (:1386)
 //   Matcher::Fuse(pKF, vpMapPoints, th)                       Matcher.cpp:897-1036  max_dist = TH_LOW, e2_max = 5.99,
 //        free_mask all ones (Fuse looks at every keypoint of the window, :994-1013)
+//   Matcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming)   Matcher.cpp:479-568
+//        max_dist = TH_LOW * ratioHamming, free_mask[i] = !vpMatched[i]
+//   Matcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint)     Matcher.cpp:1038-1135 max_dist = TH_LOW, free_mask all ones
+//   Matcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th)   Matcher.cpp:1149-1335 one call per direction (map points of
+//        KF1 against the keypoints of KF2 and vice versa), max_dist = TH_HIGH, free_mask all ones; the mutual-consistency
+//        check (:1316-1330) stays on the host
 // `FrameLike` is Frame or KeyFrame (mvKeysUn, mDescriptors).  As in search_local_points the sequential consumption
 // (a keypoint taken by an earlier row) is resolved by the caller with the reference's own inner loop.
 template <class FrameLike>
