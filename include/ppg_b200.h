@@ -223,6 +223,20 @@ int ppg_assoc_fetch_batch(ppg_ctx* ctx, int n_frames, ppg_assoc_out* outs);
  * over the whole window (diagnostic). */
 int ppg_assoc_fallback_rows(ppg_ctx* ctx, int* n);
 
+/* ---- map-descriptor table from raw observations: MapPoint::ComputeDistinctiveDescriptors ---------
+ * (feature/src/MapPoint.cpp:234-302) for n_points map points at once.  desc = the observation descriptors of
+ * all points packed back to back (rows of 256 floats, each point's rows in the order the caller iterates
+ * mObservations), offsets[n_points + 1] = first row of every point.  best_idx[p] = BestIdx of point p (index
+ * into its own list; 0 when no median distance is below 1.0, as in the reference).  At most
+ * PPG_MAX_OBSERVATIONS rows per point (PPG_ERR_CAPACITY otherwise).
+ * ppg_upload_map_distinctive additionally makes the chosen rows the resident association table (row p = the
+ * representative descriptor of point p), i.e. ppg_upload_map without the host round trip; best_idx may be NULL. */
+#define PPG_MAX_OBSERVATIONS 128
+int ppg_distinctive_descriptors(ppg_ctx* ctx, const float* desc, const int32_t* offsets, int n_points,
+                                int32_t* best_idx);
+int ppg_upload_map_distinctive(ppg_ctx* ctx, const float* desc, const int32_t* offsets, int n_points,
+                               int32_t* best_idx);
+
 /* Device pointers of the staged association results (n_rows each), for the sharded all-gather that
  * the multi-GPU host layer issues through NCCL (ppg_slam_b200/sharded.py). */
 int ppg_assoc_device_results(ppg_ctx* ctx, void** best_idx, void** second_idx, void** best_dist, void** second_dist,

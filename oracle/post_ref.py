@@ -228,3 +228,14 @@ def search_all(cam, kx, ky, frame_desc, free_mask, map_desc, proj_uv, view_cos, 
                           C.c_int(mode), C.c_float(max_dist), C.c_double(e2_max), _p(bi, C.c_int), _p(si, C.c_int), _p(bd, C.c_float), _p(sd, C.c_float),
                           _p(acc, C.c_uint8))
     return dict(best_idx=bi, second_idx=si, best_d=bd, second_d=sd, accept=acc)
+
+
+def distinctive_all(desc, offsets):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cpp:234-302) for a batch of map points: desc (total, 256)
+    packed observation descriptors, offsets (P + 1).  -> BestIdx per map point (index into its own list)."""
+    desc = f32(desc)
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    p = len(offsets) - 1
+    out = np.zeros(p, np.int32)
+    lib().ppgo_distinctive_all(_p(desc, C.c_float), _p(offsets, C.c_int), p, _p(out, C.c_int))
+    return out

@@ -803,3 +803,48 @@ void ppgo_search_all(const ppgo_cfg *c, int n, const float *kx, const float *ky,
     free(goff);
     free(gidx);
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* MapPoint::ComputeDistinctiveDescriptors, feature/src/MapPoint.cpp:234-302: the representative */
+/* descriptor of a map point = the observation with the least median distance to the others.    */
+/* ------------------------------------------------------------------------------------------- */
+static int ppgo_cmp_float(const void *a, const void *b) {
+    float x = *(const float *)a, y = *(const float *)b;
+    return (x > y) - (x < y);
+}
+
+/* desc: n x 256 observation descriptors in the order the caller iterates mObservations.
+ * -> BestIdx (:279-291: BestMedian starts at 1.0f, strict <, so index 0 when no median is below 1). */
+int ppgo_distinctive_one(const float *desc, int n) {
+    if (n <= 0) return -1;
+    float *D = malloc(sizeof(float) * (size_t)n * n), *row = malloc(sizeof(float) * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        D[(size_t)i * n + i] = 0.f; /* :270 */
+        for (int j = i + 1; j < n; j++) {
+            float d = ppgo_descriptor_distance(desc + (size_t)i * 256, desc + (size_t)j * 256, 256);
+            D[(size_t)i * n + j] = d;
+            D[(size_t)j * n + i] = d;
+        }
+    }
+    float best_median = 1.0f;
+    int best = 0;
+    for (int i = 0; i < n; i++) {
+        memcpy(row, D + (size_t)i * n, sizeof(float) * (size_t)n);
+        qsort(row, (size_t)n, sizeof(float), ppgo_cmp_float); /* :284 std::sort */
+        float median = row[(size_t)(0.5 * (double)(n - 1))];  /* :285 vDists[0.5 * (N - 1)] */
+        if (median < best_median) {
+            best_median = median;
+            best = i;
+        }
+    }
+    free(D);
+    free(row);
+    return best;
+}
+
+/* offsets[n_points + 1] into the packed descriptor array */
+void ppgo_distinctive_all(const float *desc, const int *offsets, int n_points, int *best_idx) {
+    for (int p = 0; p < n_points; p++)
+        best_idx[p] = ppgo_distinctive_one(desc + (size_t)offsets[p] * 256, offsets[p + 1] - offsets[p]);
+}
+

@@ -68,7 +68,7 @@ SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", 
            "ppg_timer_stop", "ppg_upload_map", "ppg_associate", "ppg_assoc_stage", "ppg_assoc_run",
            "ppg_assoc_fetch", "ppg_assoc_run_frame", "ppg_assoc_stage_batch", "ppg_assoc_run_batch",
            "ppg_assoc_fetch_batch", "ppg_assoc_fallback_rows", "ppg_assoc_device_results",
-           "ppg_stream"]
+           "ppg_distinctive_descriptors", "ppg_upload_map_distinctive", "ppg_stream"]
 
 _lib = None
 
@@ -93,7 +93,8 @@ def load():
                      "ppg_assoc_stage", "ppg_assoc_run", "ppg_assoc_fetch", "ppg_assoc_run_frame", "ppg_assoc_stage_batch", "ppg_assoc_run_batch",
            "ppg_assoc_fetch_batch",
                      "ppg_assoc_fallback_rows", "ppg_assoc_device_results", "ppg_assoc_stage_batch",
-                     "ppg_assoc_run_batch", "ppg_assoc_fetch_batch"]:
+                     "ppg_assoc_run_batch", "ppg_assoc_fetch_batch", "ppg_distinctive_descriptors",
+                     "ppg_upload_map_distinctive"]:
             getattr(lib, name).restype = C.c_int
         _lib = lib
     return _lib
@@ -334,6 +335,17 @@ class Extractor:
         o, r = self._assoc_out(self._assoc_rows)
         self._check(self.lib.ppg_assoc_fetch(self.h, C.byref(o)))
         return r
+
+    def distinctive_descriptors(self, desc, offsets, to_table=False):
+        """MapPoint::ComputeDistinctiveDescriptors for a batch of map points (packed observation descriptors +
+        offsets) -> BestIdx per point; to_table=True also makes the chosen rows the resident association table."""
+        d = np.ascontiguousarray(desc, np.float32)
+        off = np.ascontiguousarray(offsets, np.int32)
+        out = np.zeros(len(off) - 1, np.int32)
+        fn = self.lib.ppg_upload_map_distinctive if to_table else self.lib.ppg_distinctive_descriptors
+        self._check(fn(self.h, _fp(d), off.ctypes.data_as(C.POINTER(C.c_int32)), len(off) - 1,
+                       out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
 
     def assoc_fallback_rows(self):
         n = C.c_int(0)

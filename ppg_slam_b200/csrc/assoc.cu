@@ -17,6 +17,9 @@
 #include <math.h>
 #include <string.h>
 
+#include <string>
+#include <vector>
+
 #include "ctx.cuh"
 #include "ptx.cuh"
 
@@ -608,6 +611,94 @@ __global__ void __launch_bounds__(256) assoc_rescore_kernel(const RescoreParams 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// MapPoint::ComputeDistinctiveDescriptors (feature/src/MapPoint.cpp:234-302): one CTA per map point.
+//   pairwise DescriptorDistance of its n observations (one warp per pair, the oracle's summation order) -> D in
+//   shared memory; thread i finds the median of row i (the value of rank (int)(0.5 (n-1)), by counting) ; thread 0
+//   takes the first row whose median is below the running best (start 1.0f, strict <, :279-291).
+constexpr int DD_MAX = PPG_MAX_OBSERVATIONS;
+
+__global__ void __launch_bounds__(256) distinctive_kernel(const float* __restrict__ desc, const int* __restrict__ offsets,
+                                                          int n_points, int* __restrict__ best_idx,
+                                                          int* __restrict__ err) {
+    extern __shared__ float dd_smem[];  // D [n][n], then median [n]
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int o0 = offsets[p], n = offsets[p + 1] - o0;
+    if (n <= 0 || n > DD_MAX) {
+        if (tid == 0) {
+            best_idx[p] = n <= 0 ? -1 : 0;
+            if (n > DD_MAX) atomicExch(err, 1);
+        }
+        return;
+    }
+    float* D = dd_smem;
+    float* med = dd_smem + n * n;
+    const float* base = desc + (size_t)o0 * 256;
+    for (int i = tid; i < n; i += blockDim.x) D[i * n + i] = 0.f;  // :270
+    // pair (i, j), i < j, enumerated row-major; one warp per pair
+    const int npairs = n * (n - 1) / 2;
+    for (int q = warp; q < npairs; q += nw) {
+        // row i such that i*(2n-i-1)/2 <= q
+        int i = 0, rem = q;
+        while (rem >= n - 1 - i) {
+            rem -= n - 1 - i;
+            i++;
+        }
+        const int j = i + 1 + rem;
+        float av[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) av[k] = base[(size_t)i * 256 + lane + 32 * k];
+        const float d = exact_distance(av, base + (size_t)j * 256, lane);
+        if (lane == 0) {
+            D[i * n + j] = d;
+            D[j * n + i] = d;
+        }
+    }
+    __syncthreads();
+    const int k = (int)(0.5 * (double)(n - 1));  // :285
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float* row = D + i * n;
+        float m = 0.f;
+        for (int c = 0; c < n; c++) {  // the value v with #(x < v) <= k < #(x <= v) is the element of rank k
+            const float v = row[c];
+            int lt = 0, le = 0;
+            for (int x = 0; x < n; x++) {
+                lt += row[x] < v;
+                le += row[x] <= v;
+            }
+            if (lt <= k && k < le) {
+                m = v;
+                break;
+            }
+        }
+        med[i] = m;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float best_median = 1.0f;
+        int best = 0;
+        for (int i = 0; i < n; i++)
+            if (med[i] < best_median) {
+                best_median = med[i];
+                best = i;
+            }
+        best_idx[p] = best;
+    }
+}
+
+// map_f32[p] = observation offsets[p] + best_idx[p]
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ desc, const int* __restrict__ offsets,
+                                                          const int* __restrict__ best_idx, int n_points,
+                                                          float* __restrict__ dst) {
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (p >= n_points) return;
+    const int b = best_idx[p];
+    const float4* src = reinterpret_cast<const float4*>(desc + (size_t)(offsets[p] + (b < 0 ? 0 : b)) * 256);
+    float4* d = reinterpret_cast<float4*>(dst + (size_t)p * 256);
+    d[lane] = b < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : src[lane];
+    d[lane + 32] = b < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : src[lane + 32];
+}
+
 template <typename T>
 cudaError_t dalloc(T** p, size_t count) {
     return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
@@ -929,6 +1020,72 @@ int ppg_associate(ppg_ctx* c, const ppg_assoc_in* in, ppg_assoc_out* out) {
     if (rc != PPG_OK) return rc;
     if ((rc = ppg_assoc_run(c)) != PPG_OK) return rc;
     return ppg_assoc_fetch(c, out);
+}
+
+static int distinctive_impl(ppg_ctx* c, const float* desc, const int32_t* offsets, int n_points, int32_t* best_idx,
+                            bool to_table) {
+    if (!c || !desc || !offsets || n_points < 1) return set_err(c, PPG_ERR_ARG, "distinctive descriptors: bad arguments");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    int rc = ensure_state(c);
+    if (rc != PPG_OK) return rc;
+    AssocState* s = c->assoc;
+    if (to_table && n_points > s->max_rows)
+        return set_err(c, PPG_ERR_ARG, "ppg_upload_map_distinctive: more points than max_map_points");
+    const size_t total = (size_t)offsets[n_points];
+    if (offsets[0] != 0 || total < 1) return set_err(c, PPG_ERR_ARG, "distinctive descriptors: offsets must start at 0");
+    float* d_desc = nullptr;
+    int *d_off = nullptr, *d_best = nullptr, *d_err = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_desc);
+        cudaFree(d_off);
+        cudaFree(d_best);
+        cudaFree(d_err);
+    };
+    cudaError_t e = dalloc(&d_desc, total * 256);
+    if (e == cudaSuccess) e = dalloc(&d_off, (size_t)n_points + 1);
+    if (e == cudaSuccess) e = dalloc(&d_best, (size_t)n_points);
+    if (e == cudaSuccess) e = dalloc(&d_err, 1);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_desc, desc, total * 1024, cudaMemcpyHostToDevice, c->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, offsets, ((size_t)n_points + 1) * 4, cudaMemcpyHostToDevice, c->st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_err, 0, 4, c->st);
+    if (e == cudaSuccess) {
+        static bool attr = false;
+        const int smem = (DD_MAX * DD_MAX + DD_MAX) * 4;
+        if (!attr) {
+            e = cudaFuncSetAttribute(distinctive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            attr = e == cudaSuccess;
+        }
+        if (e == cudaSuccess) {
+            distinctive_kernel<<<n_points, 256, smem, c->st>>>(d_desc, d_off, n_points, d_best, d_err);
+            c->launches++;
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess && to_table) {
+        gather_rows_kernel<<<(n_points + 7) / 8, 256, 0, c->st>>>(d_desc, d_off, d_best, n_points, s->map_f32);
+        prep_map_kernel<<<(n_points + 7) / 8, 256, 0, c->st>>>(s->map_f32, s->map_bf, s->map_n2, n_points, n_points);
+        c->launches += 2;
+        e = cudaGetLastError();
+    }
+    int h_err = 0;
+    std::vector<int32_t> tmp;
+    if (e == cudaSuccess && best_idx) e = cudaMemcpyAsync(best_idx, d_best, (size_t)n_points * 4, cudaMemcpyDeviceToHost, c->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, c->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+    cleanup();
+    if (e != cudaSuccess) return set_err(c, PPG_ERR_CUDA, std::string("distinctive descriptors: ") + cudaGetErrorString(e));
+    if (h_err) return set_err(c, PPG_ERR_CAPACITY, "a map point has more than PPG_MAX_OBSERVATIONS observations");
+    if (to_table) s->n_rows = n_points;
+    return PPG_OK;
+}
+
+int ppg_distinctive_descriptors(ppg_ctx* c, const float* desc, const int32_t* offsets, int n_points, int32_t* best_idx) {
+    if (!best_idx) return set_err(c, PPG_ERR_ARG, "ppg_distinctive_descriptors: best_idx is null");
+    return distinctive_impl(c, desc, offsets, n_points, best_idx, false);
+}
+
+int ppg_upload_map_distinctive(ppg_ctx* c, const float* desc, const int32_t* offsets, int n_points, int32_t* best_idx) {
+    return distinctive_impl(c, desc, offsets, n_points, best_idx, true);
 }
 
 int ppg_assoc_fallback_rows(ppg_ctx* c, int* n) {

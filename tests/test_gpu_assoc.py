@@ -187,3 +187,46 @@ def test_assoc_batch_equals_oracle_per_frame():
         assert got[0]["accept"].sum() > 100
     finally:
         e.close()
+
+
+def test_distinctive_descriptors_match_oracle():
+    """ppg_distinctive_descriptors / ppg_upload_map_distinctive == MapPoint::ComputeDistinctiveDescriptors
+    (MapPoint.cpp:234-302) restated by the oracle, and the table built on the device gives the same association
+    as uploading the chosen rows from the host."""
+    from oracle import post_ref as O
+    from ppg_slam_b200 import capi
+    cam = cameras.EUROC
+    rs = np.random.RandomState(31)
+    P = 700
+    sizes = rs.randint(1, 40, P)
+    sizes[:6] = [1, 2, 3, 128, 64, 127]
+    centre = _unit(rs.normal(size=(P, 256)))
+    desc = np.concatenate([_unit(centre[k] + rs.normal(size=(n, 256)) * rs.choice([0.05, 0.2, 2.0]))
+                           for k, n in enumerate(sizes)])
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    want = O.distinctive_all(desc, off)
+    e = capi.Extractor(cam, max_batch=1, max_map_points=1024)
+    try:
+        got = e.distinctive_descriptors(desc, off)
+        np.testing.assert_array_equal(got, want)
+        assert len(set(got.tolist())) > 5
+        # device-built table == host upload of the same rows
+        n = 300
+        kx, ky, fdesc = _synthetic_keypoints(3, cam, n)
+        table = desc[off[:-1] + want]
+        inp = synth.association_inputs(2, fdesc, np.stack([kx, ky], 1), P, cam.width, cam.height, th=10.0)
+        free = np.ones(n, np.uint8)
+        e.upload_map(table)
+        a = e.associate(kx, ky, fdesc, free, inp["proj_uv"], inp["view_cos"], 10.0, 0.8)
+        got2 = e.distinctive_descriptors(desc, off, to_table=True)
+        np.testing.assert_array_equal(got2, want)
+        b = e.associate(kx, ky, fdesc, free, inp["proj_uv"], inp["view_cos"], 10.0, 0.8)
+        for k in ("best_idx", "second_idx", "accept"):
+            np.testing.assert_array_equal(a[k], b[k])
+        np.testing.assert_array_equal(a["best_d"].view(np.uint32), b["best_d"].view(np.uint32))
+        # more than PPG_MAX_OBSERVATIONS observations -> capacity error, no crash
+        big = np.concatenate([[0], [129]]).astype(np.int32)
+        with pytest.raises(capi.PpgError):
+            e.distinctive_descriptors(_unit(rs.normal(size=(129, 256))), big)
+    finally:
+        e.close()

@@ -271,3 +271,31 @@ def test_window_search_core_kat(name, th, max_dist, e2_max):
         assert ref["best_idx"][j] == bi, (name, j)
         assert ref["accept"][j] == int(bi >= 0 and best <= np.float32(max_dist))
     assert ref["accept"].sum() > 5 and (ref["best_idx"] < 0).sum() > 0
+
+
+def test_distinctive_descriptor_kat():
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cpp:234-302): least median distance, median =
+    sorted[(int)(0.5 (N-1))] (the self distance 0 is part of every row), BestMedian starts at 1.0, first minimum."""
+    rs = np.random.RandomState(12)
+    sizes = [1, 2, 3, 4, 7, 8, 15, 33, 64, 128, 5, 2]
+    centre = rs.normal(size=(len(sizes), 256)).astype(np.float32)
+    chunks = []
+    for k, n in enumerate(sizes):
+        d = centre[k] + rs.normal(size=(n, 256)).astype(np.float32) * (0.15 if k != 4 else 3.0)  # k == 4: all far apart
+        chunks.append((d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32))
+    desc = np.concatenate(chunks)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    got = O.distinctive_all(desc, off)
+    for k, n in enumerate(sizes):
+        d = chunks[k]
+        D = np.zeros((n, n), np.float32)
+        for i in range(n):
+            for j in range(i + 1, n):
+                D[i, j] = D[j, i] = O.descriptor_distance(d[i], d[j])
+        best, best_med = 0, np.float32(1.0)
+        for i in range(n):
+            med = np.sort(D[i])[int(0.5 * (n - 1))]
+            if med < best_med:
+                best, best_med = i, med
+        assert got[k] == best, (k, n)
+    assert got[1] == 0 and got[0] == 0  # N <= 2: the median is the self distance, index 0 wins
