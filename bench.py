@@ -392,7 +392,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--map-rows", type=int, default=MAP_ROWS)
-    ap.add_argument("--dev-streams", type=int, default=2, help="contexts in flight in the device-timed arm")
+    ap.add_argument("--dev-streams", type=int, default=3, help="contexts in flight in the device-timed arm")
     ap.add_argument("--e2e-streams", type=int, default=4, help="contexts (host threads) in flight in the e2e arm")
     ap.add_argument("--camera", default="EuRoC", choices=["EuRoC", "TUM-VI", "TUM-VI-1024", "UMA-VI"],
                     help="frame shape / calibration; EuRoC 752x480 is the benchmark configuration")

@@ -100,8 +100,9 @@ typedef struct {
     const int32_t* col_off;  /* n_kp + 1 */
     const int32_t* col_pairs;
     const float* desc;       /* n_kp x 256 */
-    int diag[8];             /* SM clock cycles / 16 of the phases of the point-pair graph kernel (diagnostic):
-                                setup, overlap filter, scoring, edges + adjacency, colinearity */
+    int diag[8];             /* diagnostics of the point-pair graph kernels: [0],[1],[3],[4] SM clock cycles / 16 of
+                                setup, overlap filter, edges + adjacency, colinearity; [2] candidates with a block entry,
+                                [5] candidates visited by the sequential pass, [6] of those with spilled lists */
 } ppg_frame_out;
 
 void ppg_default_config(ppg_config* cfg);

@@ -821,6 +821,7 @@ __global__ void __launch_bounds__(512) lines_filter_kernel(const PostParams p) {
         m.ws[41] = 0;  // interaction-list overflow
         m.ws[42] = 0;  // diagnostic: candidates visited by the sequential pass
         m.ws[43] = 0;  // diagnostic: of those, lists read from the spill pool
+        m.ws[44] = 0;  // diagnostic: visited candidates with at least one block entry (inline lists)
     }
     __syncthreads();
 
@@ -855,6 +856,7 @@ __global__ void __launch_bounds__(512) lines_filter_kernel(const PostParams p) {
                     const int ci = cnt & 0xffff, cj = cnt >> 16;
                     const uint4* src = reinterpret_cast<const uint4*>(g_ent + (size_t)c * 2 * INTER_K);
                     uint32_t* dst = m.seq_ent + (size_t)k * 2 * INTER_K;
+                    bool any_block = false;
 #pragma unroll
                     for (int v4 = 0; v4 < 2 * INTER_K * 2 / 16; v4++) {
                         const uint4 u = src[v4];
@@ -866,8 +868,10 @@ __global__ void __launch_bounds__(512) lines_filter_kernel(const PostParams p) {
                             const int side = t / INTER_K, tt = t % INTER_K;
                             const bool valid = tt < (side ? cj : ci);
                             dst[t] = valid ? pack_bit(words, side ? j : i, (int)(e & 0x7fff), e >> 15) : 0xffffffffu;
+                            any_block |= valid && (e >> 15);
                         }
                     }
+                    if (any_block) atomicAdd(&m.ws[44], 1);  // diagnostic: candidates that can be blocked at all
                 }
             }
             filled += tot;
@@ -964,6 +968,7 @@ __global__ void __launch_bounds__(512) lines_filter_kernel(const PostParams p) {
     if (tid == 0) {
         hdr[HDR_DIAG + 5] = m.ws[42];
         hdr[HDR_DIAG + 6] = m.ws[43];
+        hdr[HDR_DIAG + 2] = m.ws[44];
         hdr[HDR_STATUS] |= (int)status;
         hdr[HDR_NPASS] = npass_all;
         hdr[HDR_NLINES] = ncreated;
