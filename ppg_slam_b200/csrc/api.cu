@@ -623,12 +623,13 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
     p.pair_words = (p.max_kp + 31) / 32;
     p.pair_cap = 16384;
     {
-        const size_t budget = 220 * 1024;
+        const size_t budget = 226 * 1024;
         const size_t fixed = post_lines_fixed_smem(p.max_kp, p.pair_words) + 64;
-        int deg = (int)((budget - fixed) / ((size_t)p.max_kp * 2));
+        int deg = fixed < budget ? (int)((budget - fixed) / ((size_t)p.max_kp * 2)) : 0;
         if (deg > 128) deg = 128;
-        if (deg < 8) return set_err(c, PPG_ERR_ARG, "junction_max_num too large for the line-graph kernel");
         p.deg_cap = deg;
+        if (deg < 8 || post_lines_filter_smem(p) > budget)
+            return set_err(c, PPG_ERR_ARG, "junction_max_num too large for the line-graph kernels");
     }
     p.lay = make_out_layout(p.max_kp, cfg->max_edges, cfg->max_colines);
     PPG_CUDA(c, dalloc(&p.state, B * HW));

@@ -758,7 +758,8 @@ __device__ __forceinline__ LineSmem carve_lines(const PostParams& p, uint8_t* s)
     m.seq_cnt = m.seq_own + SEQ_WIN;
     m.seq_off = m.seq_cnt + SEQ_WIN;
     m.seq_ent = m.seq_off + SEQ_WIN;
-    m.adj = reinterpret_cast<uint16_t*>(m.seq_ent + SEQ_WIN * 2 * INTER_K);
+    // the adjacency rows (lines_graph_kernel) share the region of the sequential-pass window (lines_filter_kernel)
+    m.adj = reinterpret_cast<uint16_t*>(m.ws + 48);
     return m;
 }
 
@@ -1354,14 +1355,18 @@ void post_plan_nms(PostParams& p) {
         }
 }
 
+// shared memory both per-frame kernels carve: alive matrix, adj_cnt, row_off, kx, ky, ws
 size_t post_lines_fixed_smem(int max_kp, int pair_words) {
-    size_t s = (size_t)max_kp * pair_words * 4;                     // alive
-    s += (size_t)(max_kp * 4 + 1) * 4 + 48 * 4 + 16;                // adj_cnt, row_off, kx, ky, ws (+ alignment)
-    s += (size_t)SEQ_WIN * (4 + 4 + 4 + 4 + 2 * INTER_K * 4);       // seq_se, seq_own, seq_cnt, seq_off, seq_ent
+    size_t s = (size_t)max_kp * pair_words * 4;
+    s += (size_t)(max_kp * 4 + 1) * 4 + 48 * 4 + 16;
     return align_up(s, 16);
 }
 
-size_t post_lines_smem(const PostParams& p) {
+size_t post_lines_filter_smem(const PostParams& p) {  // + seq_se, seq_own, seq_cnt, seq_off, seq_ent
+    return post_lines_fixed_smem(p.max_kp, p.pair_words) + (size_t)SEQ_WIN * (4 + 4 + 4 + 4 + 2 * INTER_K * 4);
+}
+
+size_t post_lines_smem(const PostParams& p) {  // + adjacency rows
     return align_up(post_lines_fixed_smem(p.max_kp, p.pair_words) + (size_t)p.max_kp * p.deg_cap * 2, 16);
 }
 
@@ -1369,7 +1374,8 @@ cudaError_t post_init_attrs(const PostParams& p) {
     cudaError_t e = cudaFuncSetAttribute(p.nms_smem ? nms_smem_kernel : nms_global_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_nms_smem(p));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(lines_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_lines_smem(p));
+    e = cudaFuncSetAttribute(lines_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)post_lines_filter_smem(p));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(lines_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_lines_smem(p));
 }
@@ -1405,7 +1411,7 @@ cudaError_t post_lines_launch(const PostParams& p, cudaStream_t st, long long* l
     pair_test_kernel<<<g, 256, 0, st>>>(p);
     cand_build_kernel<<<g, 256, 0, st>>>(p);
     interact_kernel<<<dim3((p.pair_cap + 7) / 8, p.B), 256, 0, st>>>(p);
-    lines_filter_kernel<<<p.B, 512, post_lines_smem(p), st>>>(p);
+    lines_filter_kernel<<<p.B, 512, post_lines_filter_smem(p), st>>>(p);
     lines_score_kernel<<<dim3(16, p.B), 256, 0, st>>>(p);
     lines_graph_kernel<<<p.B, 512, post_lines_smem(p), st>>>(p);
     *launches += 6;

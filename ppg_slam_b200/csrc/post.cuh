@@ -79,7 +79,8 @@ struct PostParams {
 
 size_t post_nms_smem(const PostParams& p);
 void post_plan_nms(PostParams& p);  // sets nms_smem and acc_cap from H, W
-size_t post_lines_smem(const PostParams& p);
+size_t post_lines_smem(const PostParams& p);         // lines_graph_kernel
+size_t post_lines_filter_smem(const PostParams& p);  // lines_filter_kernel
 size_t post_lines_fixed_smem(int max_kp, int pair_words);
 cudaError_t post_init_attrs(const PostParams& p);
 // each returns the number of kernels it launched through *launches (added)

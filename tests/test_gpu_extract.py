@@ -130,6 +130,28 @@ def test_edge_cases_from_maps():
         e.close()
 
 
+def test_non_default_tunables_bit_exact(net):
+    """The ten static tunables of PPGExtractor (PPGExtractor.cpp:44-53) travel through ppg_config: a run with
+    JUNCTION_MAX_NUM = 1000 (BASELINE config 4 raises it), a lower junction threshold, NMS radius 3 and other line
+    thresholds stays bit-exact against the oracle given the same overrides."""
+    from ppg_slam_b200 import capi
+    from tests.parity_util import diff_records, oracle_post
+    cam = cameras.UMA
+    over = dict(junction_max_num=1000, junction_thresh=1.0 / 256.0, junction_nms_radius=3, line_valid_ratio=0.25,
+                line_dist_thresh=1.5, line_heatmap_thresh=0.25, line_inlier_rate=0.7)
+    m = net.forward_u8(synth.frame(11, cam.width, cam.height))
+    e = capi.Extractor(cam, max_batch=1, max_edges=8192, max_colines=8192, **over)
+    try:
+        got = e.run_from_maps(m["prob"][None], m["heat"][None], m["desc"][None])[0]
+        ref = oracle_post(cam, m["prob"], m["heat"], m["desc"], **over)
+        assert got["status"] == 0
+        bad = diff_records(got, ref)
+        assert not bad, "; ".join(bad)
+        assert got["n_kp"] > 500, "the raised cap must be exercised (n_kp = %d)" % got["n_kp"]
+    finally:
+        e.close()
+
+
 def test_nms_global_memory_variant(net, monkeypatch):
     """Frames whose 2-bit state map does not fit in shared memory (1024x1024) take nms_global_kernel; force it on an
     EuRoC frame and on the tie / chain cases and require the same bit-exact records."""
