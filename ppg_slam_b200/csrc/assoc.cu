@@ -1049,12 +1049,10 @@ static int distinctive_impl(ppg_ctx* c, const float* desc, const int32_t* offset
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, offsets, ((size_t)n_points + 1) * 4, cudaMemcpyHostToDevice, c->st);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_err, 0, 4, c->st);
     if (e == cudaSuccess) {
-        static bool attr = false;
-        const int smem = (DD_MAX * DD_MAX + DD_MAX) * 4;
-        if (!attr) {
-            e = cudaFuncSetAttribute(distinctive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            attr = e == cudaSuccess;
-        }
+        constexpr int smem = (DD_MAX * DD_MAX + DD_MAX) * 4;
+        static const cudaError_t attr_err =
+            cudaFuncSetAttribute(distinctive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        e = attr_err;
         if (e == cudaSuccess) {
             distinctive_kernel<<<n_points, 256, smem, c->st>>>(d_desc, d_off, n_points, d_best, d_err);
             c->launches++;

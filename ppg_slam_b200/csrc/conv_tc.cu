@@ -645,14 +645,14 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
 
 cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStream_t st, const uint8_t* fuse_gray,
                            const float* fuse_w, const float* fuse_b) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    // one-time kernel attributes; a function-local static initialiser is thread-safe (contexts on several host
+    // threads launch through here concurrently)
+    static const cudaError_t attr_err = [] {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+        return cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    }();
+    if (attr_err != cudaSuccess) return attr_err;
     ConvTcParams p = L.p;
     p.B = batch;
     p.total_tiles = batch * p.tiles_x * p.tiles_y;

@@ -88,11 +88,10 @@ __global__ void __launch_bounds__(256, 2) conv1a_kernel(const uint8_t* __restric
 // sub-partition, slower than 32 FFMA lanes.  The FMA kernel stays.
 cudaError_t conv1a_launch(const uint8_t* gray, const float* w, const float* bias, __half* out, int B, int H, int W,
                           cudaStream_t st) {
-    static int use_tc = -1;  // tcgen05 version (conv1a_tc.cu) unless PPG_CONV1A_TC=0 (A/B comparison)
-    if (use_tc < 0) {
+    static const int use_tc = [] {  // tcgen05 version (conv1a_tc.cu) unless PPG_CONV1A_TC=0 (A/B comparison)
         const char* e = getenv("PPG_CONV1A_TC");
-        use_tc = (e && !atoi(e)) ? 0 : 1;
-    }
+        return (e && !atoi(e)) ? 0 : 1;
+    }();
     if (use_tc && conv1a_tc_supported(H, W)) return conv1a_tc_launch(gray, w, bias, out, B, H, W, st);
     dim3 grid((W + 31) / 32, (H + 31) / 32, B);
     conv1a_kernel<<<grid, 256, 0, st>>>(gray, w, bias, out, H, W);
@@ -222,11 +221,10 @@ __global__ void __launch_bounds__(128) edge_tail_kernel(const __half* __restrict
 
 cudaError_t edge_tail_launch(const __half* in, const float* w3, const float* b3, const float* w1, const float* b1,
                              float* heat, int B, int Hh, int Wh, cudaStream_t st) {
-    static int use_tc = -1;  // tcgen05 version (conv1a_tc.cu) unless PPG_EDGE_TAIL_TC=0 (A/B comparison)
-    if (use_tc < 0) {
+    static const int use_tc = [] {  // tcgen05 version (conv1a_tc.cu) unless PPG_EDGE_TAIL_TC=0 (A/B comparison)
         const char* e = getenv("PPG_EDGE_TAIL_TC");
-        use_tc = (e && !atoi(e)) ? 0 : 1;
-    }
+        return (e && !atoi(e)) ? 0 : 1;
+    }();
     if (use_tc) return edge_tail_tc_launch(in, w3, b3, w1, b1, heat, B, Hh, Wh, st);
     const int tiles_x = (Wh + 15) / 16, tiles_y = (Hh + 7) / 8, total = tiles_x * tiles_y * B;
     int dev = 0, sms = 148;
