@@ -480,7 +480,6 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
     PPG_CUDA(c, dalloc(&c->d1, B * HW / 64 * 256));
     PPG_CUDA(c, dalloc(&c->e1, B * HW / 16 * 64));
     PPG_CUDA(c, dalloc(&c->e2, B * HW / 4 * 16));
-    PPG_CUDA(c, dalloc(&c->jlogits, B * HW / 64 * 80));
     PPG_CUDA(c, dalloc(&c->desc, B * HW / 64 * 256));
     PPG_CUDA(c, dalloc(&c->prob, B * HW));
     PPG_CUDA(c, dalloc(&c->heat_raw, B * HW));
@@ -508,7 +507,8 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
     ADD("conv4a", "backbone.conv4a", "", c->a6, Hc, Wc, EPI_F16, 1, c->a7, 128, 0)
     ADD("conv4b", "backbone.conv4b", "", c->a7, Hc, Wc, EPI_F16, 1, c->feat, 128, 0)
     ADD("convPa", "junction.convPa", "", c->feat, Hc, Wc, EPI_F16, 1, c->p1, 256, 0)
-    ADD("convPb", "junction.convPb", "", c->p1, Hc, Wc, EPI_F32, 0, c->jlogits, 80, 80)
+    // convPb's epilogue is the softmax + depth-to-space: it writes the H x W junction map, not logits
+    ADD("convPb", "junction.convPb", "", c->p1, Hc, Wc, EPI_SOFTMAX_D2S, 0, c->prob, 80, 80)
     ADD("convDa", "descriptor.convDa", "", c->feat, Hc, Wc, EPI_F16, 1, c->d1, 256, 0)
     ADD("convDb", "descriptor.convDb", "", c->d1, Hc, Wc, EPI_F32, 0, c->desc, 256, 0)
     ADD("edge0", "edge.conv_block_lst.0.0", "edge.conv_block_lst.0.1", c->feat, Hc, Wc, EPI_F16_PS2, 1, c->e1, 64, 0)
@@ -728,9 +728,6 @@ int ppg_run(ppg_ctx* c, int n) {
         c->launches++;
         mark(c, fuse1a && &l == &c->tc[0] ? "conv1a+conv1b" : l.name);
     }
-    PPG_CUDA(c, junction_d2s_launch(c->jlogits, c->prob, n, c->Hc, c->Wc, 80, c->st));
-    c->launches++;
-    mark(c, "junction_softmax_d2s");
     PPG_CUDA(c, edge_tail_launch(c->e2, c->we3, c->be3, c->we1, c->be1b, c->heat_raw, n, c->H / 2, c->W / 2, c->st));
     c->launches++;
     mark(c, "edge_tail");
@@ -862,7 +859,21 @@ int ppg_selftest_conv(ppg_ctx* c, int max_layers, const char** names, float* max
             if (!(d <= md)) md = d;  // NaN-propagating max
             if (fabsf(want) > mr) mr = fabsf(want);
         };
-        if (l.mode == EPI_F32) {
+        if (l.mode == EPI_SOFTMAX_D2S) {  // compare the probabilities with the softmax of the reference logits
+            const int Wf = l.W * 8;
+            std::vector<float> o((size_t)l.H * 8 * Wf);
+            PPG_CUDA(c, cudaMemcpy(o.data(), l.out, o.size() * 4, cudaMemcpyDeviceToHost));
+            for (int y = 0; y < l.H; y++)
+                for (int x = 0; x < l.W; x++) {
+                    const float* lg = &r[((size_t)y * l.W + x) * l.N];
+                    float m = lg[0];
+                    for (int ch = 1; ch < 65; ch++) m = fmaxf(m, lg[ch]);
+                    float sum = 0.f;
+                    for (int ch = 0; ch < 65; ch++) sum += expf(lg[ch] - m);
+                    for (int ch = 0; ch < 64; ch++)
+                        acc(o[((size_t)(8 * y + ch / 8)) * Wf + 8 * x + ch % 8], expf(lg[ch] - m) / sum);
+                }
+        } else if (l.mode == EPI_F32) {
             std::vector<float> o(npix * l.out_ld);
             PPG_CUDA(c, cudaMemcpy(o.data(), l.out, o.size() * 4, cudaMemcpyDeviceToHost));
             for (size_t px = 0; px < npix; px++)

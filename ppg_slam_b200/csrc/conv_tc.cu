@@ -274,7 +274,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             ptx::mbar_wait(&tfull[acc], aph);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-            if ((p.N & 63) == 0) {
+            if (p.mode == EPI_SOFTMAX_D2S) {
+                // one thread = one coarse cell: all 65 logits are in its TMEM lane, so the softmax needs no exchange
+                // and the 8 x 8 probabilities go straight to the full-resolution map (no logits round trip, no
+                // separate depth-to-space kernel)
+                uint32_t r[64], r2[16];
+                ptx::tmem_ld64(taddr, r);
+                ptx::tmem_ld16(taddr + 64, r2);
+                ptx::tmem_ld_wait();
+                float v[64];
+                float m = __uint_as_float(r2[0]) + cb.v[64];  // dustbin channel
+                const float dust = m;
+#pragma unroll
+                for (int j = 0; j < 64; j++) {
+                    v[j] = __uint_as_float(r[j]) + cb.v[j];
+                    m = fmaxf(m, v[j]);
+                }
+                float sum = expf(dust - m);
+#pragma unroll
+                for (int j = 0; j < 64; j++) {
+                    v[j] = expf(v[j] - m);
+                    sum += v[j];
+                }
+                if (inb) {
+                    const int Wf = p.W * 8;
+                    float* dst = reinterpret_cast<float*>(p.out) + ((size_t)t.n * p.H * 8 + 8 * y) * Wf + 8 * x;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        float4* o = reinterpret_cast<float4*>(dst + (size_t)i * Wf);
+                        o[0] = make_float4(v[8 * i] / sum, v[8 * i + 1] / sum, v[8 * i + 2] / sum, v[8 * i + 3] / sum);
+                        o[1] = make_float4(v[8 * i + 4] / sum, v[8 * i + 5] / sum, v[8 * i + 6] / sum, v[8 * i + 7] / sum);
+                    }
+                }
+            } else if ((p.N & 63) == 0) {
                 // 64 columns per tcgen05.ld; the pool is the reduce-scatter of epilogue64 (48 SHFL per 64 channels
                 // instead of 128 -- SHFL shares the shared-memory data pipe with the tensor core's operand reads)
                 for (int c0 = 0; c0 < p.N; c0 += 64) {

@@ -25,6 +25,8 @@ enum ConvEpilogue {
     EPI_F16_POOL = 1,  // bias + ReLU + 2x2 max-pool -> NHWC fp16 at half resolution
     EPI_F16_PS2 = 2,   // bias + ReLU + pixel_shuffle(2) -> NHWC fp16, Cout/4 channels at double resolution
     EPI_F32 = 3,       // bias (+ReLU) -> NHWC fp32 (all N padded channels stored)
+    EPI_SOFTMAX_D2S = 4,  // junction head tail (N = 80, 65 valid): bias -> softmax over 65 channels -> drop the dustbin
+                          // -> depth-to-space(8): P[8y+i][8x+j] = softmax[8i+j]  (PPGExtractor.cpp:161-162), fp32
 };
 
 struct ConvTcParams {
