@@ -816,6 +816,30 @@ __global__ void __launch_bounds__(512) lines_filter_kernel(const PostParams p) {
     if (npass > p.pair_cap) {
         npass = p.pair_cap;
         status |= ST_OVF_PAIRS;
+        // Pairs beyond the candidate table have no id: drop their bits, so that nothing downstream (scoring, edge
+        // list, adjacency rows, colinearity) can look up a candidate that was never built.  The record is flagged
+        // and the graph is that of the first pair_cap candidates.
+        for (int t = tid; t < n; t += blockDim.x) {
+            if (m.row_off[t + 1] <= p.pair_cap) continue;
+            int keep = p.pair_cap - m.row_off[t];
+            if (keep < 0) keep = 0;
+            for (int w = 0; w < nwords; w++) {
+                uint32_t v = m.alive[t * words + w];
+                const int cnt = __popc(v);
+                if (cnt <= keep) {
+                    keep -= cnt;
+                    continue;
+                }
+                uint32_t kept = 0u;
+                for (; keep > 0; keep--) {
+                    const uint32_t low = v & (0u - v);
+                    kept |= low;
+                    v ^= low;
+                }
+                m.alive[t * words + w] = kept;
+            }
+        }
+        __syncthreads();
     }
     if (tid == 0) {
         m.ws[40] = 0;  // blocked count

@@ -152,6 +152,56 @@ def test_non_default_tunables_bit_exact(net):
         e.close()
 
 
+def test_dense_graph_stress_and_capacity():
+    """A lattice of keypoints under a mostly-hot heat map: thousands of candidate pairs, long interaction lists (the
+    spill pool of the overlap filter), many colinear triples -- still bit-exact.  With the heat map fully hot every
+    pair passes the 3-point test and the candidate table overflows: that must come back as PPG_ERR_CAPACITY with
+    the overflow bit set, not as a crash or a silently truncated graph."""
+    from ppg_slam_b200 import capi
+    from tests.parity_util import diff_records, oracle_post
+    cam = cameras.EUROC
+    H, W = cam.height, cam.width
+    rs = np.random.RandomState(5)
+    desc = rs.normal(size=(256, H // 8, W // 8)).astype(np.float32)
+    prob = np.zeros((H, W), np.float32)
+    ys, xs = np.meshgrid(np.arange(60, 420, 24), np.arange(80, 680, 40), indexing="ij")
+    prob[ys, xs] = (0.3 + 0.5 * rs.rand(*ys.shape)).astype(np.float32)      # 15 x 15 = 225 keypoints
+    # three quarters of the pixels hot: a fully hot 16 x 16 tile would be zeroed by refineHeatMap (:557-560)
+    yy, xx = np.mgrid[0:H, 0:W]
+    pattern = np.where((yy % 2 == 0) & (xx % 2 == 0), 0.0, 0.9).astype(np.float32)
+    cold = (rs.rand(H // 16, W // 16) < 0.25).repeat(16, 0).repeat(16, 1)   # a quarter of the tiles stay cold
+    heat = np.where(cold, 0.0, pattern).astype(np.float32)
+    e = capi.Extractor(cam, max_batch=1, max_edges=16384, max_colines=16384)
+    try:
+        got = e.run_from_maps(prob[None], heat[None], desc[None], allow_capacity=True)[0]
+        ref = oracle_post(cam, prob, heat, desc)
+        assert got["status"] == 0, "capacity bits %d on the stress case" % got["status"]
+        bad = diff_records(got, ref)
+        assert not bad, "; ".join(bad)
+        assert got["n_pairs_ok"] > 1500 and got["n_edges"] > 50, (got["n_pairs_ok"], got["n_edges"])
+        hot = pattern
+        dense = np.zeros((H, W), np.float32)
+        dense[20:460:10, 20:740:10] = 0.5     # 44 x 72 candidates -> 500 keypoints, ~125 k passing pairs
+        with pytest.raises(capi.PpgError):
+            e.run_from_maps(dense[None], hot[None], desc[None])
+        rec = e.run_from_maps(dense[None], hot[None], desc[None], allow_capacity=True)[0]
+        assert rec["status"] & 2, "ST_OVF_PAIRS expected, status = %d" % rec["status"]
+        # the ctx stays usable after an overflow
+        again = e.run_from_maps(prob[None], heat[None], desc[None])[0]
+        assert not diff_records(again, ref)
+    finally:
+        e.close()
+    # small edge / coline capacities: flagged, no crash, keypoints still exact
+    e = capi.Extractor(cam, max_batch=1, max_edges=64, max_colines=16)
+    try:
+        rec = e.run_from_maps(prob[None], heat[None], desc[None], allow_capacity=True)[0]
+        assert rec["status"] & 8 and rec["status"] & 16, "ST_OVF_EDGES | ST_OVF_COLINE expected, status = %d" % rec["status"]
+        np.testing.assert_array_equal(rec["px"], ref["px"])
+        np.testing.assert_array_equal(rec["py"], ref["py"])
+    finally:
+        e.close()
+
+
 def test_nms_global_memory_variant(net, monkeypatch):
     """Frames whose 2-bit state map does not fit in shared memory (1024x1024) take nms_global_kernel; force it on an
     EuRoC frame and on the tie / chain cases and require the same bit-exact records."""
