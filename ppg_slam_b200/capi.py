@@ -172,7 +172,9 @@ class Extractor:
 
     # ---- PPGExtractor::run
     def _frame_ptrs(self, frames):
-        frames = [np.ascontiguousarray(f, dtype=np.uint8) for f in frames]
+        # rows may be padded (cv::Mat::step > cols): such views are passed as they are, with their row stride
+        frames = [f if (isinstance(f, np.ndarray) and f.dtype == np.uint8 and f.ndim == 2 and f.strides[1] == 1 and
+                        f.strides[0] >= f.shape[1]) else np.ascontiguousarray(f, dtype=np.uint8) for f in frames]
         for f in frames:
             if f.shape != (self.H, self.W):
                 raise ValueError("frame shape %r != (%d, %d)" % (f.shape, self.H, self.W))

@@ -237,6 +237,43 @@ def test_batch_equals_single(ex_euroc):
         np.testing.assert_array_equal(batch[f]["desc"], single["desc"])
 
 
+def test_padded_rows_empty_frames_and_mixed_batch(ex_euroc):
+    """cv::Mat rows may be padded (run() takes data + step); a batch may mix ordinary frames with frames that yield no
+    keypoints at all (detectLines / genPointDescriptor return early, :210, :239-240); the batched association must
+    cope with a frame of zero keypoints."""
+    from oracle import post_ref as O
+    cam = cameras.EUROC
+    g0, g1 = synth.frame(4, 752, 480), synth.frame(6, 752, 480)
+    padded = np.zeros((480, 800), np.uint8)
+    padded[:, :752] = g0
+    view = padded[:, :752]
+    assert view.strides[0] == 800
+    black = np.zeros((480, 752), np.uint8)
+    single0, single1 = ex_euroc.run([g0])[0], ex_euroc.run([g1])[0]
+    batch = ex_euroc.run([view, black, g1])
+    assert batch[1]["n_kp"] == 0 and batch[1]["n_edges"] == 0 and batch[1]["status"] == 0
+    for got, want in ((batch[0], single0), (batch[2], single1)):
+        for k in ("px", "py", "edge_start", "edge_end", "conn_idx", "col_pairs"):
+            np.testing.assert_array_equal(got[k], want[k])
+        np.testing.assert_array_equal(got["desc"], want["desc"])
+    # association of the three frames in one batch: the empty frame has no candidates anywhere
+    M = 2048
+    kp0 = np.stack([single0["kp_x"], single0["kp_y"]], 1)
+    inp = synth.association_inputs(3, single0["desc"], kp0, M, cam.width, cam.height, th=10.0)
+    ex_euroc.upload_map(inp["map_desc"])
+    uv = np.stack([inp["proj_uv"]] * 3)
+    vc = np.stack([inp["view_cos"]] * 3)
+    ex_euroc.assoc_stage_batch(uv, vc, 10.0, 0.8)
+    ex_euroc.assoc_run_batch(3)
+    got = ex_euroc.assoc_fetch_batch(3)
+    assert (got[1]["best_idx"] == -1).all() and not got[1]["accept"].any()
+    for f, r in ((0, single0), (2, single1)):
+        ref = O.search_all(cam, r["kp_x"], r["kp_y"], r["desc"], np.ones(r["n_kp"], np.uint8), inp["map_desc"],
+                           inp["proj_uv"], inp["view_cos"], 10.0, 0.8)
+        np.testing.assert_array_equal(got[f]["best_idx"], ref["best_idx"])
+        np.testing.assert_array_equal(got[f]["accept"], ref["accept"])
+
+
 def test_full_path_agrees_with_oracle_graph(ex_euroc, net):
     """End to end (fp16 tensor-core networks): keypoint sets must overlap the fp32 oracle's almost entirely."""
     from tests.parity_util import oracle_post
