@@ -123,10 +123,54 @@ __global__ void __launch_bounds__(256) scan_kernel(const PostParams p) {
 // truncates the walk, so it is applied afterwards on the ranked survivors.
 // Rank the NMS survivors (bitonic sort of (~score, index) keys = score desc, raster asc), keep the first max_kp
 // (:196-197), undistort them through the LUT and write the keypoint SoA + header of the frame record.
-__device__ void nms_finish(const PostParams& p, int b, unsigned long long* keys, int nacc_all, int ovf, int rounds) {
+// If more survivors than key slots exist (degenerate maps: a uniform map leaves 14 400 survivors at 752x480), the
+// max_kp best are selected exactly first: bitwise search for the max_kp-th smallest key over the accepted
+// candidates (`accepted(idx)` reads the NMS state), then only the keys up to it are gathered -- keys are unique, so
+// exactly max_kp of them.  The record is then NOT flagged: the result is the reference's.
+template <typename AcceptedFn>
+__device__ void nms_finish(const PostParams& p, int b, unsigned long long* keys, int nacc_all, int ovf, int rounds,
+                           int ncand, AcceptedFn accepted) {
     const int tid = threadIdx.x, W = p.W;
     int nacc = nacc_all;
     int* hdr = hdr_of(p, b);
+    if (nacc_all > p.acc_cap && p.max_kp <= p.acc_cap) {
+        __shared__ int s_cnt;
+        const float* prob = p.prob + (size_t)b * p.H * p.W;
+        const uint32_t* cl = p.cand + (size_t)b * p.H * p.W;
+        auto key_of = [&](int idx) {
+            return ((unsigned long long)(~__float_as_uint(__ldg(prob + idx))) << 32) | (unsigned)idx;
+        };
+        unsigned long long kth = 0ull;  // smallest K with #(key <= K) >= max_kp, built from the top bit down
+        for (int bit = 63; bit >= 0; bit--) {
+            const unsigned long long trial = kth | ((1ull << bit) - 1ull);  // all keys with this bit clear (and prefix)
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            int c = 0;
+            for (int t = tid; t < ncand; t += blockDim.x) {
+                const int idx = cl[t];
+                if (accepted(idx) && key_of(idx) <= trial) c++;
+            }
+            if (c) atomicAdd(&s_cnt, c);
+            __syncthreads();
+            if (s_cnt < p.max_kp) kth |= 1ull << bit;
+            __syncthreads();
+        }
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        for (int t = tid; t < ncand; t += blockDim.x) {
+            const int idx = cl[t];
+            if (!accepted(idx)) continue;
+            const unsigned long long k = key_of(idx);
+            if (k <= kth) {
+                const int slot = atomicAdd(&s_cnt, 1);
+                if (slot < p.acc_cap) keys[slot] = k;
+            }
+        }
+        __syncthreads();
+        nacc = s_cnt < p.acc_cap ? s_cnt : p.acc_cap;
+        ovf = 0;
+        __syncthreads();
+    }
     if (nacc > p.acc_cap) nacc = p.acc_cap;
     // bitonic sort of the survivors' keys (ascending = score desc, index asc)
     int P = 1;
@@ -252,7 +296,7 @@ __global__ void __launch_bounds__(1024) nms_global_kernel(const PostParams p) {
         __syncthreads();
         if (rem == 0 || rounds > n + 1) break;
     }
-    nms_finish(p, b, keys, s_nacc, s_ovf, rounds);
+    nms_finish(p, b, keys, s_nacc, s_ovf, rounds, n, [&](int idx) { return state[idx] == 2; });
 }
 
 // Same fixed point with the per-pixel state held in SHARED memory as 2 bits per pixel (90 KB at 752x480): the
@@ -332,7 +376,8 @@ __global__ void __launch_bounds__(1024) nms_smem_kernel(const PostParams p) {
         __syncthreads();
         if (rem == 0 || rounds > n + 1) break;
     }
-    nms_finish(p, b, keys, s_nacc, s_ovf, rounds);
+    nms_finish(p, b, keys, s_nacc, s_ovf, rounds, n,
+               [&](int idx) { return ((st2[idx >> 4] >> ((idx & 15) * 2)) & 3u) == 2u; });
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -120,6 +120,10 @@ def test_edge_cases_from_maps():
         ramp = np.zeros((H, W), np.float32)
         ramp[100, 50:700] = np.linspace(0.1, 0.9, 650).astype(np.float32)  # long suppression chain
         cases["ramp_chain"] = ramp
+        # degenerate maps: every pixel is a candidate and more survivors (14 400 / ~9 000) than ranking slots exist --
+        # the 500 best must still be exactly the reference's (hundreds of NMS rounds on the uniform map)
+        cases["uniform_all_candidates"] = np.full((H, W), 0.5, np.float32)
+        cases["dense_noise"] = (rs.rand(H, W) * 0.9 + 0.05).astype(np.float32)
         for name, prob in cases.items():
             got = e.run_from_maps(prob[None], heat[None], desc[None])[0]
             ref = oracle_post(cam, prob, heat, desc)
