@@ -115,6 +115,28 @@ def test_window_search_modes_match_oracle(name, th, max_dist, e2_max):
         e.close()
 
 
+def test_assoc_stress_huge_windows_and_global_ties():
+    """Windows that cover the whole image (every keypoint is a candidate of every row: the hit queues drain on
+    every chunk and most rows need the exact window scan), and a frame whose descriptors are all identical (every
+    distance ties: the reference keeps the first keypoint in GetFeaturesInArea order)."""
+    from ppg_slam_b200 import capi
+    cam = cameras.EUROC
+    n, m = 357, 1500
+    kx, ky, fdesc = _synthetic_keypoints(17, cam, n)
+    inp = synth.association_inputs(13, fdesc, np.stack([kx, ky], 1), m, cam.width, cam.height, th=10.0)
+    free = np.ones(n, np.uint8)
+    e = capi.Extractor(cam, max_batch=1, max_map_points=2048)
+    try:
+        e.upload_map(inp["map_desc"])
+        _check(e, cam, kx, ky, fdesc, free, inp, 250.0, 0.8)       # r = 625 / 1000 px
+        same = np.repeat(fdesc[:1], n, 0)
+        got, ref = _check(e, cam, kx, ky, same, free, inp, 10.0, 0.8)
+        assert (got["best_idx"] >= 0).sum() > 100
+        _check(e, cam, kx, ky, same, free, inp, 250.0, 0.9)
+    finally:
+        e.close()
+
+
 def test_assoc_on_extracted_frame():
     """extract -> associate with the frame's own keypoints/descriptors left on the device."""
     from oracle import post_ref as O
