@@ -1416,6 +1416,7 @@ void post_plan_nms(PostParams& p) {
     p.nms_smem = 0;
     p.acc_cap = 8192;
     if ((p.H * p.W) % 16 != 0) return;
+    if (2 * p.nms_radius + 1 > 16) return;  // a window row must fit the 32-bit field the kernel extracts
     for (int cap = 8192; cap >= 2048; cap >>= 1)
         if (bitmap + (size_t)cap * 8 <= budget) {
             p.nms_smem = 1;

@@ -134,6 +134,24 @@ def test_edge_cases_from_maps():
         e.close()
 
 
+def test_widest_nms_radius_bit_exact(net):
+    """junction_nms_radius = 8 (17-pixel window rows: handled by the global-memory NMS variant) and = 7 (the widest
+    the shared-memory bitmap variant takes)."""
+    from ppg_slam_b200 import capi
+    from tests.parity_util import diff_records, oracle_post
+    cam = cameras.EUROC
+    m = net.forward_u8(synth.frame(2, cam.width, cam.height))
+    for R in (7, 8):
+        e = capi.Extractor(cam, max_batch=1, junction_nms_radius=R)
+        try:
+            got = e.run_from_maps(m["prob"][None], m["heat"][None], m["desc"][None])[0]
+            ref = oracle_post(cam, m["prob"], m["heat"], m["desc"], junction_nms_radius=R)
+            bad = diff_records(got, ref)
+            assert not bad, "R = %d: %s" % (R, "; ".join(bad))
+        finally:
+            e.close()
+
+
 def test_non_default_tunables_bit_exact(net):
     """The ten static tunables of PPGExtractor (PPGExtractor.cpp:44-53) travel through ppg_config: a run with
     JUNCTION_MAX_NUM = 1000 (BASELINE config 4 raises it), a lower junction threshold, NMS radius 3 and other line
