@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "ctx.cuh"
+#include "once.cuh"
 #include "ptx.cuh"
 
 namespace ppg {
@@ -747,7 +748,7 @@ int ensure_state(ppg_ctx* c) {
     if (!make_kmajor_map(&s->mapA, s->map_bf, R, 256, A_BM, true) ||
         !make_kmajor_map(&s->mapB, s->f_bf, B * N, 256, A_BN, true))
         return set_err(c, PPG_ERR_CUDA, "cuTensorMapEncodeTiled failed for the association operands");
-    PPG_CUDA(c, cudaFuncSetAttribute(assoc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(s)));
+    PPG_CUDA(c, cudaFuncSetAttribute(assoc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     return PPG_OK;
 }
 
@@ -1050,9 +1051,11 @@ static int distinctive_impl(ppg_ctx* c, const float* desc, const int32_t* offset
     if (e == cudaSuccess) e = cudaMemsetAsync(d_err, 0, 4, c->st);
     if (e == cudaSuccess) {
         constexpr int smem = (DD_MAX * DD_MAX + DD_MAX) * 4;
-        static const cudaError_t attr_err =
-            cudaFuncSetAttribute(distinctive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        e = attr_err;
+        static bool attr_done[64];
+        static std::mutex attr_mu;
+        e = once_per_device(attr_done, attr_mu, [] {
+            return cudaFuncSetAttribute(distinctive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        });
         if (e == cudaSuccess) {
             distinctive_kernel<<<n_points, 256, smem, c->st>>>(d_desc, d_off, n_points, d_best, d_err);
             c->launches++;

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "net_direct.cuh"
+#include "once.cuh"
 #include "ptx.cuh"
 
 namespace ppg {
@@ -363,8 +364,11 @@ cudaError_t conv1a_tc_launch(const uint8_t* gray, const float* w, const float* b
                              cudaStream_t st) {
     // 56 KB of dynamic shared memory per CTA caps the residency at 4 CTAs per SM = 4 x 128 TMEM columns
     constexpr int SMEM = 56 * 1024;
-    static const cudaError_t attr_err =
-        cudaFuncSetAttribute(conv1a_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    static bool attr_done[64];
+    static std::mutex attr_mu;
+    const cudaError_t attr_err = once_per_device(attr_done, attr_mu, [] {
+        return cudaFuncSetAttribute(conv1a_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    });
     if (attr_err != cudaSuccess) return attr_err;
     static const int swap = [] {  // PPG_C1_SWAP=1: LBO / SBO exchanged (descriptor experiment; gives wrong results)
         const char* s = getenv("PPG_C1_SWAP");
@@ -384,8 +388,11 @@ cudaError_t edge_tail_tc_launch(const __half* in, const float* w3, const float* 
                                 float* heat, int B, int Hh, int Wh, cudaStream_t st) {
     // 28 KB of dynamic shared memory per CTA -> 8 CTAs per SM (32 TMEM columns each)
     constexpr int SMEM = 28 * 1024;
-    static const cudaError_t attr_err =
-        cudaFuncSetAttribute(edge_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    static bool attr_done[64];
+    static std::mutex attr_mu;
+    const cudaError_t attr_err = once_per_device(attr_done, attr_mu, [] {
+        return cudaFuncSetAttribute(edge_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    });
     if (attr_err != cudaSuccess) return attr_err;
     const int tiles_x = (Wh + ET_TW - 1) / ET_TW, tiles_y = (Hh + ET_TH - 1) / ET_TH, total = tiles_x * tiles_y * B;
     int dev = 0, sms = 148;

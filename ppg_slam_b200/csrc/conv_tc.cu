@@ -1,5 +1,6 @@
 // tcgen05 implicit-GEMM convolution kernel -- see conv_tc.cuh for the design.
 #include "conv_tc.cuh"
+#include "once.cuh"
 #include "ptx.cuh"
 
 #include <stdlib.h>
@@ -679,11 +680,13 @@ cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStrea
                            const float* fuse_w, const float* fuse_b) {
     // one-time kernel attributes; a function-local static initialiser is thread-safe (contexts on several host
     // threads launch through here concurrently)
-    static const cudaError_t attr_err = [] {
+    static bool attr_done[64];
+    static std::mutex attr_mu;
+    const cudaError_t attr_err = once_per_device(attr_done, attr_mu, [] {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    }();
+    });
     if (attr_err != cudaSuccess) return attr_err;
     ConvTcParams p = L.p;
     p.B = batch;

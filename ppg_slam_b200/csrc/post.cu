@@ -1441,13 +1441,17 @@ size_t post_lines_smem(const PostParams& p) {  // + adjacency rows
 }
 
 cudaError_t post_init_attrs(const PostParams& p) {
-    cudaError_t e = cudaFuncSetAttribute(p.nms_smem ? nms_smem_kernel : nms_global_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_nms_smem(p));
+    // The attribute belongs to the function, not to the ctx: contexts with different frame shapes share it, so it is
+    // set to the opt-in maximum rather than to this ctx's size.
+    (void)p;
+    const int kMax = 226 * 1024;  // opt-in maximum minus room for the kernels' few static __shared__ words
+    cudaError_t e = cudaFuncSetAttribute(nms_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(lines_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)post_lines_filter_smem(p));
+    e = cudaFuncSetAttribute(nms_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(lines_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_lines_smem(p));
+    e = cudaFuncSetAttribute(lines_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(lines_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
 }
 
 cudaError_t post_keypoints_launch(const PostParams& p, cudaStream_t st, long long* launches) {

@@ -313,3 +313,24 @@ def test_full_path_agrees_with_oracle_graph(ex_euroc, net):
     da = got["desc"][[ia[p] for p in common]]
     db = ref["desc"][[ib[p] for p in common]]
     assert (da * db).sum(1).min() >= COS_MIN
+
+
+def test_contexts_of_different_shapes_coexist(net):
+    """Two contexts with different frame shapes (and so different shared-memory footprints of the per-frame kernels)
+    alive in one process, used alternately."""
+    from ppg_slam_b200 import capi
+    from tests.parity_util import diff_records, oracle_post
+    big, small = cameras.UMA, cameras.TUMVI
+    mb = net.forward_u8(synth.frame(3, big.width, big.height))
+    ms = net.forward_u8(synth.frame(3, small.width, small.height))
+    eb = capi.Extractor(big, max_batch=1)
+    es = capi.Extractor(small, max_batch=1)   # created second: must not shrink what the first one needs
+    try:
+        for _ in range(2):
+            gb = eb.run_from_maps(mb["prob"][None], mb["heat"][None], mb["desc"][None])[0]
+            gs = es.run_from_maps(ms["prob"][None], ms["heat"][None], ms["desc"][None])[0]
+        assert not diff_records(gb, oracle_post(big, mb["prob"], mb["heat"], mb["desc"]))
+        assert not diff_records(gs, oracle_post(small, ms["prob"], ms["heat"], ms["desc"]))
+    finally:
+        eb.close()
+        es.close()
