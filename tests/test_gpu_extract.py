@@ -334,3 +334,37 @@ def test_contexts_of_different_shapes_coexist(net):
     finally:
         eb.close()
         es.close()
+
+
+def test_two_contexts_on_two_threads(ex_euroc):
+    """Different contexts are independent: two host threads driving one ctx each (the pipelined e2e arm of bench.py)
+    get the records a single-threaded run gets."""
+    import threading
+    from ppg_slam_b200 import capi
+    frames = [synth.frame(s, 752, 480) for s in (10, 11, 12, 13)]
+    want = ex_euroc.run(frames)
+    other = capi.Extractor(cameras.EUROC, max_batch=4)
+    res, errs = {}, []
+
+    def work(tag, e, fr):
+        try:
+            for _ in range(4):
+                res[tag] = e.run(fr)
+        except Exception as ex:  # noqa: BLE001
+            errs.append(ex)
+
+    try:
+        th = [threading.Thread(target=work, args=("a", ex_euroc, frames)),
+              threading.Thread(target=work, args=("b", other, frames[::-1]))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errs, errs
+        for f in range(4):
+            for got in (res["a"][f], res["b"][3 - f]):
+                for k in ("px", "py", "edge_start", "edge_end", "col_pairs"):
+                    np.testing.assert_array_equal(got[k], want[f][k])
+                np.testing.assert_array_equal(got["desc"], want[f]["desc"])
+    finally:
+        other.close()
