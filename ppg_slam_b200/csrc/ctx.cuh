@@ -1,5 +1,6 @@
 // Internal context of libppg_b200.so (shared by api.cu and assoc.cu).
 #pragma once
+#include <map>
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -65,6 +66,12 @@ struct ppg_ctx {
 
     // profiling
     bool profiling = false;
+    // CUDA graphs of the launch sequence of ppg_run, one per batch size (captured on the second call with that size;
+    // PPG_GRAPH=0 disables).  Profiling runs bypass them (the stage events are not part of the graph).
+    bool use_graph = true;
+    std::map<int, cudaGraphExec_t> graphs;
+    std::map<int, int> graph_launches;  // kernels per replay, for launch_count
+    std::map<int, int> run_calls;
     bool fuse_conv1a = false;  // PPG_FUSE_CONV1A=1 -> conv1a computed by producer warps inside conv1b (measured slower)
     std::vector<cudaEvent_t> ev;
     std::vector<const char*> ev_names;
