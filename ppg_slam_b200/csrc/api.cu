@@ -384,6 +384,10 @@ void ppg_destroy(ppg_ctx* c) {
     cudaSetDevice(c->dev);
     if (c->st) cudaStreamSynchronize(c->st);
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.second);
+    for (cudaEvent_t e : {c->ev_feat, c->ev_heat, c->ev_dmap, c->ev_kp, c->ev_desc})
+        if (e) cudaEventDestroy(e);
+    if (c->st2) cudaStreamDestroy(c->st2);
+    if (c->st3) cudaStreamDestroy(c->st3);
     assoc_destroy(c);
     for (auto& l : c->tc) {
         cudaFree(l.w);
@@ -463,6 +467,11 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
     const int B = c->maxB, Hc = c->Hc, Wc = c->Wc;
     PPG_CUDA(c, cudaSetDevice(c->dev));
     PPG_CUDA(c, cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    PPG_CUDA(c, cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
+    PPG_CUDA(c, cudaStreamCreateWithFlags(&c->st3, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&c->ev_feat, &c->ev_heat, &c->ev_dmap, &c->ev_kp, &c->ev_desc})
+        PPG_CUDA(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    if (const char* e = getenv("PPG_FORK")) c->use_fork = atoi(e) != 0;
     PPG_CUDA(c, cudaEventCreate(&c->t0));
     PPG_CUDA(c, cudaEventCreate(&c->t1));
 
@@ -765,20 +774,67 @@ static int enqueue_run(ppg_ctx* c, int n) {
         c->launches++;
         mark(c, "conv1a");
     }
-    bool first = true;
+    // Small batches leave most of the GPU idle inside every kernel, so the branches of the network and of the
+    // post-processing that do not depend on one another are forked onto side streams:
+    //   st : backbone -> junction head -> keypoints (scan, NMS)   ...join heat... -> point-pair graph  ...join desc
+    //   st2: (after the backbone) edge head -> edge tail -> refine / remap
+    //   st3: (after the backbone) descriptor head; (after the keypoints) descriptor sampling
+    // Large batches fill the GPU by themselves and stay on one stream (as do profiling runs: stage events).
+    const bool fork = c->use_fork && !c->profiling && n <= 8 && c->st2 && c->st3;
+    auto stream_of = [&](const char* name) {
+        if (!fork) return c->st;
+        if (!strncmp(name, "edge", 4)) return c->st2;
+        if (!strncmp(name, "convD", 5)) return c->st3;
+        return c->st;
+    };
+    bool first = true, forked = false;
     for (auto& l : c->tc) {
+        cudaStream_t s = stream_of(l.name);
+        const bool head = !strncmp(l.name, "convP", 5) || !strncmp(l.name, "convD", 5) || !strncmp(l.name, "edge", 4);
+        if (fork && !forked && head) {  // first head layer: the backbone (feature map) is complete here
+            PPG_CUDA(c, cudaEventRecord(c->ev_feat, c->st));
+            PPG_CUDA(c, cudaStreamWaitEvent(c->st2, c->ev_feat, 0));
+            PPG_CUDA(c, cudaStreamWaitEvent(c->st3, c->ev_feat, 0));
+            forked = true;
+        }
         if (first && fuse1a)
-            PPG_CUDA(c, conv_tc_launch(l.L, n, c->num_sms, c->st, c->gray, c->w1a, c->b1a));
+            PPG_CUDA(c, conv_tc_launch(l.L, n, c->num_sms, s, c->gray, c->w1a, c->b1a));
         else
-            PPG_CUDA(c, conv_tc_launch(l.L, n, c->num_sms, c->st));
+            PPG_CUDA(c, conv_tc_launch(l.L, n, c->num_sms, s));
         first = false;
         c->launches++;
         mark(c, fuse1a && &l == &c->tc[0] ? "conv1a+conv1b" : l.name);
     }
-    PPG_CUDA(c, edge_tail_launch(c->e2, c->we3, c->be3, c->we1, c->be1b, c->heat_raw, n, c->H / 2, c->W / 2, c->st));
+    if (fork && !forked) {  // no head layer ran on a side stream (cannot happen with the shipped networks)
+        PPG_CUDA(c, cudaEventRecord(c->ev_feat, c->st));
+        PPG_CUDA(c, cudaStreamWaitEvent(c->st2, c->ev_feat, 0));
+        PPG_CUDA(c, cudaStreamWaitEvent(c->st3, c->ev_feat, 0));
+    }
+    PostParams p = c->post;
+    p.B = n;
+    cudaStream_t s_heat = fork ? c->st2 : c->st, s_desc = fork ? c->st3 : c->st;
+    PPG_CUDA(c, edge_tail_launch(c->e2, c->we3, c->be3, c->we1, c->be1b, c->heat_raw, n, c->H / 2, c->W / 2, s_heat));
     c->launches++;
     mark(c, "edge_tail");
-    return run_post(c, n);
+    PPG_CUDA(c, post_keypoints_launch(p, c->st, &c->launches));
+    mark(c, "post.keypoints(scan+nms+topk)");
+    PPG_CUDA(c, post_heat_launch(p, s_heat, &c->launches));
+    mark(c, "post.heat(refine+remap)");
+    if (fork) {
+        PPG_CUDA(c, cudaEventRecord(c->ev_heat, c->st2));
+        PPG_CUDA(c, cudaEventRecord(c->ev_kp, c->st));
+        PPG_CUDA(c, cudaStreamWaitEvent(c->st, c->ev_heat, 0));   // the graph needs keypoints + heat map
+        PPG_CUDA(c, cudaStreamWaitEvent(c->st3, c->ev_kp, 0));    // the sampling needs keypoints + descriptor map
+    }
+    PPG_CUDA(c, post_lines_launch(p, c->st, &c->launches));
+    mark(c, "post.lines(pairs+graph)");
+    PPG_CUDA(c, post_desc_launch(p, s_desc, &c->launches));
+    mark(c, "post.descriptors");
+    if (fork) {
+        PPG_CUDA(c, cudaEventRecord(c->ev_desc, c->st3));
+        PPG_CUDA(c, cudaStreamWaitEvent(c->st, c->ev_desc, 0));   // join: everything is ordered on st again
+    }
+    return PPG_OK;
 }
 
 int ppg_sync(ppg_ctx* c) {

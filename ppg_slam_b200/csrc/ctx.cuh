@@ -35,6 +35,11 @@ struct ppg_ctx {
     mutable std::string err;
     int dev = 0, num_sms = 0;
     cudaStream_t st = nullptr;
+    // small batches: the three heads and the post-processing branches that do not depend on one another run on side
+    // streams (fork / join with events, captured into the CUDA graph as parallel branches)
+    cudaStream_t st2 = nullptr, st3 = nullptr;
+    cudaEvent_t ev_feat = nullptr, ev_heat = nullptr, ev_dmap = nullptr, ev_kp = nullptr, ev_desc = nullptr;
+    bool use_fork = true;  // PPG_FORK=0 disables
     int H = 0, W = 0, Hc = 0, Wc = 0, maxB = 0;
     long long launches = 0;
     int last_batch = 0;
