@@ -18,8 +18,8 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile
     t.n = tile / per;
     int r = tile - t.n * per;
     int ty = r / p.tiles_x;
-    t.y0 = ty * CONV_TILE_H;
-    t.x0 = (r - ty * p.tiles_x) * CONV_TILE_W;
+    t.y0 = ty * (128 >> p.tile_w_log2);
+    t.x0 = (r - ty * p.tiles_x) << p.tile_w_log2;
     return t;
 }
 
@@ -264,7 +264,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ld -> bias -> pool -> store chain at low IPC, and with a single group that chain, not the MMAs, set the
         // tile period (tensor pipe 37 % active in the ncu capture).
         const int q = warp & 3, grp = (warp - 2) >> 2;
-        const int row = q * 32 + lane, h = row >> 4, w = row & 15;
+        const int row = q * 32 + lane, h = row >> p.tile_w_log2, w = row & ((1 << p.tile_w_log2) - 1);
         uint32_t lt = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, lt++) {
             uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
@@ -639,6 +639,7 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
     p.out_ld = out_ld;
     L.cin = cin;
     L.cout = cout_padded;
+    p.tile_w_log2 = 4;
     // PPG_CONV_V2=0 forces the generic kernel everywhere (A/B comparison); default = halo kernel where it applies.
     // Measured on B200 (tools/conv_variants.py): UMMA applies the 128-byte swizzle XOR on absolute shared-memory
     // address bits, so a descriptor may start at any 128-byte row of a swizzled tile with base_offset = 0.
@@ -664,10 +665,18 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
     }
     L.halo_pitch = 0;
     L.flags = 0;
-    L.box_w = CONV_TILE_W;
-    L.box_h = CONV_TILE_H;
-    p.tiles_x = (W + CONV_TILE_W - 1) / CONV_TILE_W;
-    p.tiles_y = (H + CONV_TILE_H - 1) / CONV_TILE_H;
+    // Tile shape: 16 x 8 (the fused 2x2 pool needs both neighbours inside one warp), or 32 x 4 when that covers the
+    // map with fewer tiles (60 x 94 coarse map: 45 instead of 48 tiles per frame, 10 instead of 11 tile rounds per SM
+    // at batch 32).
+    p.tile_w_log2 = 4;
+    if (mode != EPI_F16_POOL) {
+        const long t16 = (long)((W + 15) / 16) * ((H + 7) / 8), t32 = (long)((W + 31) / 32) * ((H + 3) / 4);
+        if (t32 < t16) p.tile_w_log2 = 5;
+    }
+    L.box_w = 1 << p.tile_w_log2;
+    L.box_h = 128 >> p.tile_w_log2;
+    p.tiles_x = (W + L.box_w - 1) / L.box_w;
+    p.tiles_y = (H + L.box_h - 1) / L.box_h;
     p.total_tiles = maxB * p.tiles_x * p.tiles_y;
     const int stage_bytes = CONV_A_BYTES + cout_padded * 128;
     int S = (200 * 1024) / stage_bytes;

@@ -37,6 +37,7 @@ struct ConvTcParams {
     int mode, relu;
     int stages;
     int tiles_x, tiles_y, total_tiles;
+    int tile_w_log2;   // generic kernel: output tile = (1 << tile_w_log2) x (128 >> tile_w_log2) pixels (16 x 8 or 32 x 4)
     const float* bias; // [N]
     void* out;
     int out_ld;        // channels per output pixel in the destination tensor

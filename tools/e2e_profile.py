@@ -11,10 +11,11 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from ppg_slam_b200 import capi  # noqa: E402
 
-B = 32
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 cam, frames = bench.make_workload(B)
 e = capi.Extractor(cam, max_batch=B, max_map_points=bench.MAP_ROWS)
 recs = e.run(frames)
+e.run(frames)
 map_desc, per_frame = bench.make_assoc_inputs(cam, recs, bench.MAP_ROWS)
 e.upload_map(map_desc)
 proj_all = np.stack([uv for uv, _ in per_frame])
