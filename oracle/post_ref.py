@@ -239,3 +239,34 @@ def distinctive_all(desc, offsets):
     out = np.zeros(p, np.int32)
     lib().ppgo_distinctive_all(_p(desc, C.c_float), _p(offsets, C.c_int), p, _p(out, C.c_int))
     return out
+
+
+def extend_map_matches(cam, map_desc, candidate, observed, bad, edge_off, edge_other, edge_ok, proj_uv, view_cos,
+                       tracked, kx, ky, frame_desc, kp_mp, kedge_start, kedge_end, conn_off, conn_idx, kedge_me=None,
+                       th=10.0, ratio=0.8, th_high=0.8):
+    """Matcher::ExtendMapMatches (Matcher.cpp:203-381) in POD form, whole function (sequential walk + seed
+    growing); argument meaning in oracle/ppg_oracle.c::ppgo_extend_map_matches.
+    -> dict(nmatches, kp_mp, kedge_me, tracked) (inputs are not modified)."""
+    cfg = make_cfg(cam)
+    map_desc, proj_uv, view_cos = f32(map_desc), f32(proj_uv), f32(view_cos)
+    kx, ky, frame_desc = f32(kx), f32(ky), f32(frame_desc)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    candidate, observed, bad, edge_ok = u8(candidate), u8(observed), u8(bad), u8(edge_ok)
+    edge_off, edge_other = i32(edge_off), i32(edge_other)
+    kedge_start, kedge_end, conn_off, conn_idx = i32(kedge_start), i32(kedge_end), i32(conn_off), i32(conn_idx)
+    tracked = u8(tracked).copy()
+    kp_mp = i32(kp_mp).copy()
+    ne = len(kedge_start)
+    kedge_me = np.full(max(ne, 1), -1, np.int32) if kedge_me is None else i32(kedge_me).copy()
+    pad = lambda a, t: a if a.size else np.zeros(1, t)
+    nm = lib().ppgo_extend_map_matches(
+        C.byref(cfg), len(map_desc), _p(map_desc, C.c_float), _p(candidate, C.c_uint8), _p(observed, C.c_uint8),
+        _p(bad, C.c_uint8), _p(edge_off, C.c_int), _p(pad(edge_other, np.int32), C.c_int),
+        _p(pad(edge_ok, np.uint8), C.c_uint8), _p(proj_uv, C.c_float), _p(view_cos, C.c_float),
+        _p(tracked, C.c_uint8), len(kx), _p(pad(kx, np.float32), C.c_float), _p(pad(ky, np.float32), C.c_float),
+        _p(pad(frame_desc, np.float32), C.c_float), _p(pad(kp_mp, np.int32), C.c_int),
+        _p(pad(kedge_start, np.int32), C.c_int), _p(pad(kedge_end, np.int32), C.c_int), _p(conn_off, C.c_int),
+        _p(pad(conn_idx, np.int32), C.c_int), _p(kedge_me, C.c_int), C.c_float(th), C.c_float(ratio),
+        C.c_float(th_high))
+    return dict(nmatches=int(nm), kp_mp=kp_mp, kedge_me=kedge_me[:ne], tracked=tracked)

@@ -848,3 +848,159 @@ void ppgo_distinctive_all(const float *desc, const int *offsets, int n_points, i
         best_idx[p] = ppgo_distinctive_one(desc + (size_t)offsets[p] * 256, offsets[p + 1] - offsets[p]);
 }
 
+
+/* ------------------------------------------------------------------------------------------- */
+/* Matcher::ExtendMapMatches, matching/src/Matcher.cpp:203-381, whole function: the sequential  */
+/* walk over the candidate map points (search core above with the LIVE frame state) and the    */
+/* seed growing over (map edges of pMP) x (key edges of the matched keypoint).                 */
+/*                                                                                             */
+/* POD form of the pointer graph.  The table has P rows = the candidate map points AND every   */
+/* map point reachable as theOtherPt of one of their edges (its descriptor is read at :330):   */
+/*   candidate[p]   !isBad() && mbTrackInView (:210-215)                                       */
+/*   observed[p]    Observations() > 0 (:253)             bad[p]  isBad() (:227, :364)         */
+/*   edge_off/edge_other/edge_ok   CSR of MapPoint::getEdges() in vector order: the row of     */
+/*                  theOtherPt(pMP) (-1 = nullptr) and !isBad() && mbValid of each edge (:311)  */
+/*   tracked[p]     in/out: mnTrackedbyFrame == F.mnId                                         */
+/* Frame: keypoints (mvKeysUn[i].mPos), descriptors, key edges (mvKeyEdges start/end), CSR of  */
+/*   mvConnected; kp_mp[i] in/out = F.mvpMapPoints[i] as a table row, -1 = nullptr, -2 = a map */
+/*   point outside the table that has observations; kedge_me[e] in/out = F.mvpMapEdges[e] as   */
+/*   the CSR position of the map edge (-1 = nullptr).                                          */
+/* std::sort by getEdges().size() descending is unstable (:223-224): ties keep table order here */
+/* (same documented divergence as the other sorts).  Requires ratio < 1 (with ratio >= 1 the    */
+/* reference writes mvpMapPoints[-1] when every keypoint of a window is taken).                */
+/* -> nmatches as the reference counts it (two increments per accepted map point, :281, :378). */
+/* ------------------------------------------------------------------------------------------- */
+static int emm_occupied(const int *kp_mp, const uint8_t *observed, int idx) {
+    int r = kp_mp[idx];
+    return r >= 0 ? (observed[r] != 0) : (r == -2); /* :253 */
+}
+
+typedef struct {
+    int row, deg, pos;
+} emm_key;
+
+static int emm_cmp(const void *a, const void *b) {
+    const emm_key *x = a, *y = b;
+    if (x->deg != y->deg) return x->deg > y->deg ? -1 : 1;
+    return x->pos < y->pos ? -1 : (x->pos > y->pos ? 1 : 0);
+}
+
+int ppgo_extend_map_matches(const ppgo_cfg *c, int P, const float *map_desc, const uint8_t *candidate,
+                            const uint8_t *observed, const uint8_t *bad, const int *edge_off, const int *edge_other,
+                            const uint8_t *edge_ok, const float *proj_uv, const float *view_cos, uint8_t *tracked,
+                            int n, const float *kx, const float *ky, const float *frame_desc, int *kp_mp,
+                            const int *kedge_start, const int *kedge_end, const int *conn_off, const int *conn_idx,
+                            int *kedge_me, float th, float ratio, float th_high) {
+    int nmatches = 0;
+    ppgo_bounds b;
+    ppgo_image_bounds(c, &b);
+    int *goff = malloc(sizeof(int) * (64 * 48 + 1)), *gidx = malloc(sizeof(int) * (n > 0 ? n : 1));
+    ppgo_grid_build(&b, n, kx, ky, goff, gidx);
+    emm_key *order = malloc(sizeof(emm_key) * (P > 0 ? P : 1));
+    int nc = 0;
+    for (int p = 0; p < P; p++) /* :210-215 */
+        if (candidate[p] && !bad[p]) {
+            order[nc].row = p;
+            order[nc].deg = edge_off[p + 1] - edge_off[p];
+            order[nc].pos = nc;
+            nc++;
+        }
+    qsort(order, nc, sizeof(emm_key), emm_cmp); /* :223-224 */
+    int *win = malloc(sizeof(int) * (n > 0 ? n : 1));
+    int *queue = malloc(sizeof(int) * ((size_t)P + 2)); /* every push marks a new map point tracked */
+    for (int t = 0; t < nc; t++) {
+        const int p = order[t].row;
+        if (tracked[p] || bad[p]) continue; /* :229 */
+        const float *dmp = map_desc + (size_t)p * 256;
+        float bestDist = 1e6f, bestDist2 = 1e6f;
+        int bestIdx = -1;
+        float r = th;
+        if ((double)view_cos[p] > 0.998) /* :240-244 */
+            r = (float)((double)r * 2.5);
+        else
+            r = (float)((double)r * 4.0);
+        int nw = ppgo_features_in_area(&b, goff, gidx, kx, ky, proj_uv[2 * p], proj_uv[2 * p + 1], r, win);
+        if (nw == 0) continue; /* :247-248 */
+        for (int k = 0; k < nw; k++) {
+            int idx = win[k];
+            if (emm_occupied(kp_mp, observed, idx)) continue; /* :253 */
+            float dist = ppgo_descriptor_distance(dmp, frame_desc + (size_t)idx * 256, 256);
+            if (dist < bestDist) {
+                bestDist2 = bestDist;
+                bestDist = dist;
+                bestIdx = idx;
+            } else if (dist < bestDist2)
+                bestDist2 = dist;
+        }
+        if (bestDist > th_high && bestDist > ratio * bestDist2) continue; /* :276 */
+        if (bestIdx < 0) continue; /* unreachable for ratio < 1 (see header) */
+        kp_mp[bestIdx] = p; /* :279 */
+        tracked[p] = 1;
+        nmatches++;
+        /* seed growing, :287-377 */
+        int qh = 0, qt = 0, qcap = P + 2;
+        queue[qt++] = bestIdx;
+        const int me0 = edge_off[p], nme = edge_off[p + 1] - edge_off[p];
+        while (qh < qt) {
+            const int keyID = queue[qh++];
+            const int ke0 = conn_off[keyID], nke = conn_off[keyID + 1] - conn_off[keyID];
+            if (nme == 0 || nke == 0) continue; /* :300-301 */
+            float *weight = malloc(sizeof(float) * (size_t)nme * nke);
+            for (int i = 0; i < nme * nke; i++) weight[i] = 1e6f; /* :308 */
+            int *lx = malloc(sizeof(int) * nme), *ly = malloc(sizeof(int) * nke);
+            int nlx = 0, nly = 0;
+            for (int i = 0; i < nme; i++) { /* :312-318 */
+                if (!edge_ok[me0 + i] || edge_other[me0 + i] < 0) continue;
+                lx[nlx++] = i;
+            }
+            for (int j = 0; j < nke; j++) ly[nly++] = j; /* :321-322 */
+            for (int a = 0; a < nlx; a++)
+                for (int j = 0; j < nke; j++) { /* :324-340 */
+                    const int i = lx[a];
+                    const int po = edge_other[me0 + i];
+                    const int e = conn_idx[ke0 + j];
+                    const int ko = kedge_start[e] == keyID ? kedge_end[e] : kedge_start[e];
+                    if (po == kp_mp[ko])
+                        weight[i * nke + j] = -1.f;
+                    else
+                        weight[i * nke + j] =
+                            ppgo_descriptor_distance(map_desc + (size_t)po * 256, frame_desc + (size_t)ko * 256, 256);
+                }
+            while (nlx > 0 && nly > 0) { /* :342-374 */
+                int minlx = 0, minly = 0;
+                float minWeight = 1e6f;
+                for (int a = 0; a < nlx; a++)
+                    for (int bb = 0; bb < nly; bb++)
+                        if (weight[lx[a] * nke + ly[bb]] < minWeight) {
+                            minWeight = weight[lx[a] * nke + ly[bb]];
+                            minlx = a;
+                            minly = bb;
+                        }
+                if (minWeight > th_high) break;
+                const int mi = lx[minlx], kj = ly[minly];
+                memmove(lx + minlx, lx + minlx + 1, sizeof(int) * (nlx - minlx - 1));
+                nlx--;
+                memmove(ly + minly, ly + minly + 1, sizeof(int) * (nly - minly - 1));
+                nly--;
+                const int po = edge_other[me0 + mi];
+                const int e = conn_idx[ke0 + kj];
+                const int ko = kedge_start[e] == keyID ? kedge_end[e] : kedge_start[e];
+                if (po < 0 || bad[po] || tracked[po]) continue; /* :364-365 */
+                kp_mp[ko] = po; /* :366 */
+                kedge_me[e] = me0 + mi;
+                tracked[po] = 1;
+                if (qt < qcap) queue[qt++] = ko;
+            }
+            free(weight);
+            free(lx);
+            free(ly);
+        }
+        nmatches++; /* :378 */
+    }
+    free(queue);
+    free(win);
+    free(order);
+    free(goff);
+    free(gidx);
+    return nmatches;
+}

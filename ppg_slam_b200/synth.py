@@ -74,3 +74,66 @@ def association_inputs(seed, frame_desc, kp_xy, n_map, width, height, th=10.0, p
     n_edges = rs.randint(0, 6, M).astype(np.int32)
     return dict(map_desc=d.astype(np.float32), proj_uv=uv.astype(np.float32),
                 view_cos=view_cos, n_edges=n_edges)
+
+
+def extend_inputs(seed, frame_desc, kp_xy, kedge_start, kedge_end, n_map, width, height, th=10.0, planted_frac=0.5,
+                  clean=False):
+    """Map-side inputs for the whole Matcher::ExtendMapMatches (Matcher.cpp:203-381): association_inputs plus a map
+    graph.  Planted rows copy a keypoint (descriptor + noise, projection near it); for every key edge of the frame
+    whose two endpoints have planted rows, those rows are joined by a map edge (so seed growing has something to
+    grow along), plus random edges between arbitrary rows.  Unless `clean`, the state a running system would have
+    is mixed in: non-candidate rows, bad rows, unobserved rows, invalid / dangling edges, rows already tracked and
+    keypoints that already hold a map point.
+    -> dict(map_desc, proj_uv, view_cos, candidate, observed, bad, edge_off, edge_other, edge_ok, tracked, kp_mp,
+            planted_rows, planted_src)"""
+    rs = np.random.RandomState(seed)
+    N, M = frame_desc.shape[0], n_map
+    d = rs.normal(size=(M, 256)).astype(np.float32)
+    uv = np.stack([rs.uniform(0, width, M), rs.uniform(0, height, M)], 1).astype(np.float32)
+    view_cos = rs.uniform(0.9, 1.0, M).astype(np.float32)
+    rows = np.zeros(0, np.int64)
+    src = np.zeros(0, np.int64)
+    if N > 0:
+        n_pl = min(int(M * planted_frac), M)
+        rows = rs.choice(M, n_pl, replace=False)
+        src = rs.randint(0, N, n_pl)
+        d[rows] = frame_desc[src] + rs.normal(0, 0.05, size=(n_pl, 256)).astype(np.float32)
+        r = np.where(view_cos[rows] > 0.998, 2.5, 4.0) * th
+        uv[rows] = kp_xy[src] + (rs.uniform(-0.5, 0.5, size=(n_pl, 2)) * r[:, None]).astype(np.float32)
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-12)
+    first_row = {}
+    for rw, s in zip(rows.tolist(), src.tolist()):
+        first_row.setdefault(s, rw)
+    adj = [[] for _ in range(M)]  # (other, ok)
+    for a, b in zip(np.asarray(kedge_start).tolist(), np.asarray(kedge_end).tolist()):
+        if a in first_row and b in first_row and rs.rand() < 0.85:
+            ra, rb = first_row[a], first_row[b]
+            ok = 1 if (clean or rs.rand() < 0.93) else 0
+            adj[ra].append((rb, ok))
+            adj[rb].append((ra, ok))
+    for _ in range(0 if clean else M // 4):
+        ra, rb = rs.randint(0, M, 2)
+        if ra == rb:
+            continue
+        ok = 1 if rs.rand() < 0.9 else 0
+        adj[ra].append((rb if rs.rand() < 0.95 else -1, ok))  # -1: theOtherPt() == nullptr
+        adj[rb].append((ra, ok))
+    edge_off = np.zeros(M + 1, np.int32)
+    edge_off[1:] = np.cumsum([len(a) for a in adj])
+    edge_other = np.array([o for a in adj for o, _ in a], np.int32)
+    edge_ok = np.array([k for a in adj for _, k in a], np.uint8)
+    if clean:
+        candidate, observed, bad = np.ones(M, np.uint8), np.ones(M, np.uint8), np.zeros(M, np.uint8)
+        tracked, kp_mp = np.zeros(M, np.uint8), np.full(N, -1, np.int32)
+    else:
+        candidate = (rs.rand(M) < 0.9).astype(np.uint8)
+        observed = (rs.rand(M) < 0.95).astype(np.uint8)
+        bad = ((rs.rand(M) < 0.03) & (candidate == 0)).astype(np.uint8)
+        tracked = (rs.rand(M) < 0.02).astype(np.uint8)
+        kp_mp = np.full(N, -1, np.int32)
+        pre = rs.rand(N) < 0.08
+        kp_mp[pre] = rs.randint(0, M, int(pre.sum()))
+        kp_mp[rs.rand(N) < 0.03] = -2
+    return dict(map_desc=d.astype(np.float32), proj_uv=uv.astype(np.float32), view_cos=view_cos, candidate=candidate,
+                observed=observed, bad=bad, edge_off=edge_off, edge_other=edge_other, edge_ok=edge_ok, tracked=tracked,
+                kp_mp=kp_mp, planted_rows=rows.astype(np.int32), planted_src=src.astype(np.int32))
