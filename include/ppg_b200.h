@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PPG_API_VERSION 2
+#define PPG_API_VERSION 3
 #define PPG_DESC_DIM 256 /* PPGExtractor::DESC_DIM_SIZE, PPGExtractor.cpp:44 */
 
 typedef enum {
@@ -237,6 +237,75 @@ int ppg_distinctive_descriptors(ppg_ctx* ctx, const float* desc, const int32_t* 
                                 int32_t* best_idx);
 int ppg_upload_map_distinctive(ppg_ctx* ctx, const float* desc, const int32_t* offsets, int n_points,
                                int32_t* best_idx);
+
+/* ---- the whole Matcher::ExtendMapMatches (matching/src/Matcher.cpp:203-381) on the GPU ---------------
+ * Search core as above PLUS the sequential part: the walk over the candidate map points in the order of
+ * getEdges().size() (descending; ties keep table order), the live "keypoint already holds an observed map point"
+ * test (:253), the assignment (:279-281) and the seed growing over (map edges of pMP) x (key edges of the matched
+ * keypoint) with its greedy minimum-weight assignment (:287-377).  Nothing of it runs on the host.
+ *
+ * The pointer graph is passed in POD form.  The resident table (ppg_upload_map / ppg_upload_map_distinctive) holds
+ * n_points rows: the candidate map points AND every map point reachable as theOtherPt() of one of their edges (its
+ * descriptor is read at :330).  Per row:
+ *   candidate  !isBad() && mbTrackInView (:210-215)        observed  Observations() > 0 (:253)
+ *   bad        isBad() (:227, :364)
+ *   edge_off[n_points + 1], edge_other[], edge_ok[]  CSR of MapPoint::getEdges() in vector order: the row of
+ *              theOtherPt(pMP) (-1 = nullptr) and !isBad() && mbValid (:311) of every edge.  A map edge is named by
+ *              its CSR position in the results.
+ * Capacities: at most PPG_EXTEND_MAX_DEGREE edges per map point and key edges per keypoint, and (valid map edges) x
+ * (key edges) <= PPG_EXTEND_MAX_WEIGHTS per seed; beyond that the frame's status gets PPG_EXTEND_OVF and the call
+ * returns PPG_ERR_CAPACITY.  Requires ratio < 1 (with ratio >= 1 the reference itself writes mvpMapPoints[-1]). */
+#define PPG_EXTEND_MAX_DEGREE 128
+#define PPG_EXTEND_MAX_WEIGHTS 4096
+#define PPG_EXTEND_OVF 1u
+typedef struct {
+    int n_points;
+    const uint8_t* candidate;
+    const uint8_t* observed;
+    const uint8_t* bad;
+    const int32_t* edge_off;
+    const int32_t* edge_other;
+    const uint8_t* edge_ok;
+} ppg_map_graph;
+int ppg_upload_map_graph(ppg_ctx* ctx, const ppg_map_graph* graph);
+
+typedef struct {
+    int n_kp;                 /* Frame::N */
+    const float* kp_x;        /* mvKeysUn[i].mPos */
+    const float* kp_y;
+    const float* frame_desc;  /* N x 256 */
+    const int32_t* kp_mp;     /* N: F.mvpMapPoints[i] as a table row, -1 = nullptr, -2 = a map point outside the table
+                                 that has observations; NULL = all -1 */
+    int n_edges;              /* F.mvKeyEdges.size() (<= ppg_config.max_edges) */
+    const int32_t* edge_start;/* KeyEdge::startIdx / endIdx */
+    const int32_t* edge_end;
+    const int32_t* conn_off;  /* n_kp + 1: CSR of mvKeysUn[i].mvConnected */
+    const int32_t* conn_idx;
+    const int32_t* kedge_me;  /* n_edges: F.mvpMapEdges[e] as a CSR position, -1 = nullptr; NULL = all -1 */
+    const float* proj_uv;     /* n_points x 2: mTrackProjX/Y (read for candidate rows only) */
+    const float* view_cos;    /* n_points */
+    const uint8_t* tracked;   /* n_points: mnTrackedbyFrame == F.mnId; NULL = none */
+    float th, ratio;
+} ppg_extend_in;
+
+typedef struct {        /* caller-allocated */
+    int32_t* kp_mp;     /* n_kp: F.mvpMapPoints after the call (batch form: room for junction_max_num) */
+    int32_t* kedge_me;  /* n_edges: F.mvpMapEdges after the call (batch form: room for max_edges) */
+    uint8_t* tracked;   /* n_points, may be NULL */
+    int nmatches;       /* the reference's return value (two increments per accepted map point, :281 and :378) */
+    uint32_t status;    /* 0 or PPG_EXTEND_OVF */
+    int n_kp, n_edges;  /* entries written to kp_mp / kedge_me */
+    int n_accepted;     /* map points accepted by the window search (diagnostic) */
+    int n_grown;        /* map points matched by seed growing (diagnostic) */
+    int n_rescans;      /* rows whose stored candidate list had to be rebuilt from the whole window (diagnostic) */
+} ppg_extend_out;
+
+/* One frame, everything in host memory; synchronous. */
+int ppg_extend_map_matches(ppg_ctx* ctx, const ppg_extend_in* in, ppg_extend_out* out);
+/* Every frame of the last extraction batch (keypoints, descriptors and point-pair graph still on the device, no map
+ * point assigned yet) against the projections staged with ppg_assoc_stage_batch (n_rows = n_points); asynchronous. */
+int ppg_extend_run_batch(ppg_ctx* ctx, int n_frames);
+int ppg_extend_fetch_batch(ppg_ctx* ctx, int n_frames, ppg_extend_out* outs);
 
 /* Device pointers of the staged association results (n_rows each), for the sharded all-gather that
  * the multi-GPU host layer issues through NCCL (ppg_slam_b200/sharded.py). */

@@ -61,6 +61,29 @@ class AssocOut(C.Structure):
                 ("accept", C.POINTER(C.c_uint8))]
 
 
+class MapGraph(C.Structure):
+    _fields_ = [("n_points", C.c_int), ("candidate", C.POINTER(C.c_uint8)), ("observed", C.POINTER(C.c_uint8)),
+                ("bad", C.POINTER(C.c_uint8)), ("edge_off", C.POINTER(C.c_int32)),
+                ("edge_other", C.POINTER(C.c_int32)), ("edge_ok", C.POINTER(C.c_uint8))]
+
+
+class ExtendIn(C.Structure):
+    _fields_ = [("n_kp", C.c_int), ("kp_x", C.POINTER(C.c_float)), ("kp_y", C.POINTER(C.c_float)),
+                ("frame_desc", C.POINTER(C.c_float)), ("kp_mp", C.POINTER(C.c_int32)), ("n_edges", C.c_int),
+                ("edge_start", C.POINTER(C.c_int32)), ("edge_end", C.POINTER(C.c_int32)),
+                ("conn_off", C.POINTER(C.c_int32)), ("conn_idx", C.POINTER(C.c_int32)),
+                ("kedge_me", C.POINTER(C.c_int32)), ("proj_uv", C.POINTER(C.c_float)),
+                ("view_cos", C.POINTER(C.c_float)), ("tracked", C.POINTER(C.c_uint8)), ("th", C.c_float),
+                ("ratio", C.c_float)]
+
+
+class ExtendOut(C.Structure):
+    _fields_ = [("kp_mp", C.POINTER(C.c_int32)), ("kedge_me", C.POINTER(C.c_int32)),
+                ("tracked", C.POINTER(C.c_uint8)), ("nmatches", C.c_int), ("status", C.c_uint32),
+                ("n_kp", C.c_int), ("n_edges", C.c_int), ("n_accepted", C.c_int), ("n_grown", C.c_int),
+                ("n_rescans", C.c_int)]
+
+
 # every symbol include/ppg_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", "ppg_api_version", "ppg_extract",
            "ppg_upload_frames", "ppg_run", "ppg_download", "ppg_sync", "ppg_extract_from_maps", "ppg_get_maps",
@@ -68,7 +91,8 @@ SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", 
            "ppg_timer_stop", "ppg_upload_map", "ppg_associate", "ppg_assoc_stage", "ppg_assoc_run",
            "ppg_assoc_fetch", "ppg_assoc_run_frame", "ppg_assoc_stage_batch", "ppg_assoc_run_batch",
            "ppg_assoc_fetch_batch", "ppg_assoc_fallback_rows", "ppg_assoc_device_results",
-           "ppg_distinctive_descriptors", "ppg_upload_map_distinctive", "ppg_stream"]
+           "ppg_distinctive_descriptors", "ppg_upload_map_distinctive", "ppg_stream", "ppg_upload_map_graph",
+           "ppg_extend_map_matches", "ppg_extend_run_batch", "ppg_extend_fetch_batch"]
 
 _lib = None
 
@@ -94,7 +118,8 @@ def load():
            "ppg_assoc_fetch_batch",
                      "ppg_assoc_fallback_rows", "ppg_assoc_device_results", "ppg_assoc_stage_batch",
                      "ppg_assoc_run_batch", "ppg_assoc_fetch_batch", "ppg_distinctive_descriptors",
-                     "ppg_upload_map_distinctive"]:
+                     "ppg_upload_map_distinctive", "ppg_upload_map_graph", "ppg_extend_map_matches",
+                     "ppg_extend_run_batch", "ppg_extend_fetch_batch"]:
             getattr(lib, name).restype = C.c_int
         _lib = lib
     return _lib
@@ -337,6 +362,88 @@ class Extractor:
         o, r = self._assoc_out(self._assoc_rows)
         self._check(self.lib.ppg_assoc_fetch(self.h, C.byref(o)))
         return r
+
+    # ---- the whole Matcher::ExtendMapMatches (matching/src/Matcher.cpp:203-381): search + sequential walk + seed growing
+    def upload_map_graph(self, candidate, observed, bad, edge_off, edge_other, edge_ok):
+        """POD form of the map-point graph for the rows of the resident table (include/ppg_b200.h, ppg_map_graph)."""
+        u8p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
+        keep = [np.ascontiguousarray(candidate, np.uint8), np.ascontiguousarray(observed, np.uint8),
+                np.ascontiguousarray(bad, np.uint8), np.ascontiguousarray(edge_off, np.int32),
+                np.ascontiguousarray(edge_other, np.int32), np.ascontiguousarray(edge_ok, np.uint8)]
+        g = MapGraph()
+        g.n_points = len(keep[0])
+        g.candidate, g.observed, g.bad = (k.ctypes.data_as(u8p) for k in keep[:3])
+        g.edge_off = keep[3].ctypes.data_as(i32p)
+        g.edge_other = keep[4].ctypes.data_as(i32p) if keep[4].size else None
+        g.edge_ok = keep[5].ctypes.data_as(u8p) if keep[5].size else None
+        self._check(self.lib.ppg_upload_map_graph(self.h, C.byref(g)))
+        self._graph_points = g.n_points
+
+    @staticmethod
+    def _extend_out(n_kp, n_edges, n_points):
+        r = dict(kp_mp=np.zeros(max(n_kp, 1), np.int32), kedge_me=np.zeros(max(n_edges, 1), np.int32),
+                 tracked=np.zeros(max(n_points, 1), np.uint8))
+        o = ExtendOut()
+        o.kp_mp = r["kp_mp"].ctypes.data_as(C.POINTER(C.c_int32))
+        o.kedge_me = r["kedge_me"].ctypes.data_as(C.POINTER(C.c_int32))
+        o.tracked = r["tracked"].ctypes.data_as(C.POINTER(C.c_uint8))
+        return o, r
+
+    @staticmethod
+    def _extend_result(o, r, n_points):
+        return dict(nmatches=o.nmatches, status=int(o.status), kp_mp=r["kp_mp"][:o.n_kp].copy(),
+                    kedge_me=r["kedge_me"][:o.n_edges].copy(), tracked=r["tracked"][:n_points].copy(),
+                    n_accepted=o.n_accepted, n_grown=o.n_grown, n_rescans=o.n_rescans)
+
+    def extend_map_matches(self, kp_x, kp_y, frame_desc, kp_mp, edge_start, edge_end, conn_off, conn_idx, proj_uv,
+                           view_cos, tracked, th, ratio, kedge_me=None):
+        """Matcher::ExtendMapMatches for one frame given in host memory (ppg_extend_in).  -> dict(nmatches, kp_mp,
+        kedge_me, tracked, ...)."""
+        i32p, u8p = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+        f32a = lambda a: np.ascontiguousarray(a, np.float32)
+        i32a = lambda a: np.ascontiguousarray(a, np.int32)
+        kx, ky, fd, uv, vc = f32a(kp_x), f32a(kp_y), f32a(frame_desc), f32a(proj_uv), f32a(view_cos)
+        es, ee, coff, cidx = i32a(edge_start), i32a(edge_end), i32a(conn_off), i32a(conn_idx)
+        a = ExtendIn()
+        a.n_kp, a.n_edges = len(kx), len(es)
+        a.kp_x, a.kp_y, a.frame_desc = _fp(kx), _fp(ky), _fp(fd)
+        keep = [kx, ky, fd, uv, vc, es, ee, coff, cidx]
+        if kp_mp is not None:
+            k = i32a(kp_mp)
+            keep.append(k)
+            a.kp_mp = k.ctypes.data_as(i32p)
+        a.edge_start, a.edge_end = es.ctypes.data_as(i32p), ee.ctypes.data_as(i32p)
+        a.conn_off, a.conn_idx = coff.ctypes.data_as(i32p), cidx.ctypes.data_as(i32p)
+        if kedge_me is not None:
+            k = i32a(kedge_me)
+            keep.append(k)
+            a.kedge_me = k.ctypes.data_as(i32p)
+        a.proj_uv, a.view_cos = _fp(uv), _fp(vc)
+        if tracked is not None:
+            t = np.ascontiguousarray(tracked, np.uint8)
+            keep.append(t)
+            a.tracked = t.ctypes.data_as(u8p)
+        a.th, a.ratio = th, ratio
+        o, r = self._extend_out(a.n_kp, a.n_edges, self._graph_points)
+        self._check(self.lib.ppg_extend_map_matches(self.h, C.byref(a), C.byref(o)))
+        return self._extend_result(o, r, self._graph_points)
+
+    def extend_run_batch(self, n_frames):
+        """Every frame of the last extraction batch against the projections staged with assoc_stage_batch."""
+        self._check(self.lib.ppg_extend_run_batch(self.h, n_frames))
+
+    def extend_fetch_batch(self, n_frames):
+        if getattr(self, "_xbatch_out", None) is None or len(self._xbatch_out[1]) != n_frames:
+            outs = (ExtendOut * n_frames)()
+            res = []
+            for f in range(n_frames):
+                o, r = self._extend_out(self.cfg.junction_max_num, self.cfg.max_edges, self._graph_points)
+                outs[f] = o
+                res.append(r)
+            self._xbatch_out = (outs, res)
+        outs, res = self._xbatch_out
+        self._check(self.lib.ppg_extend_fetch_batch(self.h, n_frames, outs))
+        return [self._extend_result(outs[f], res[f], self._graph_points) for f in range(n_frames)]
 
     def distinctive_descriptors(self, desc, offsets, to_table=False):
         """MapPoint::ComputeDistinctiveDescriptors for a batch of map points (packed observation descriptors +

@@ -20,73 +20,12 @@
 #include <string>
 #include <vector>
 
+#include "assoc.cuh"
 #include "ctx.cuh"
 #include "once.cuh"
 #include "ptx.cuh"
 
 namespace ppg {
-
-bool make_kmajor_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, bool bf16);
-
-constexpr int A_BM = 128, A_BN = 128, A_STAGES = 4, A_STAGE_BYTES = 32768, A_THREADS = 320, A_TOPK = 4;
-constexpr int A_QCAP = 32;  // per-thread queue of window hits awaiting the exact mask + top-4 insertion
-constexpr unsigned AFULL = 0xffffffffu;
-
-struct RowParam {  // per map point
-    float u, v, r, na2;
-    uint32_t cells;  // minCx | maxCx << 8 | minCy << 16 | maxCy << 24 ; 0xffffffff = empty window
-};
-
-// Where the keypoints / descriptors of frame f live: staged arrays (one frame) or the extraction output blocks
-// of the last batch (byte stride = one output block).
-struct FrameSrc {
-    const uint8_t *kx, *ky, *desc, *free_mask, *n;
-    size_t stride, free_stride;
-    int n_val;  // used when n == nullptr
-    __host__ __device__ const float* kx_of(int f) const { return reinterpret_cast<const float*>(kx + f * stride); }
-    __host__ __device__ const float* ky_of(int f) const { return reinterpret_cast<const float*>(ky + f * stride); }
-    __host__ __device__ const float* desc_of(int f) const { return reinterpret_cast<const float*>(desc + f * stride); }
-    __host__ __device__ const uint8_t* free_of(int f) const { return free_mask + f * free_stride; }
-    __device__ int n_of(int f) const { return n ? *reinterpret_cast<const int*>(n + f * stride) : n_val; }
-};
-
-struct AssocState {
-    int max_rows = 0, n_rows = 0, ncap = 0;  // ncap: keypoint capacity per frame (multiple of 128)
-    int bcap = 1;                            // frames per batched call
-    // map side (shared by all frames)
-    float* map_f32 = nullptr;
-    __nv_bfloat16* map_bf = nullptr;
-    float* map_n2 = nullptr;
-    CUtensorMap mapA, mapB;
-    // frame side: staged single frame, or the extraction output blocks of the last batch
-    float *kx = nullptr, *ky = nullptr, *fdesc = nullptr;
-    uint8_t *free_mask = nullptr, *ones = nullptr;
-    float* fn2 = nullptr;            // [bcap][ncap]
-    __nv_bfloat16* f_bf = nullptr;   // [bcap][ncap][256]
-    uint32_t* kinfo = nullptr;       // [bcap][ncap]  cx | cy << 8 | ok << 16
-    uint32_t* korder = nullptr;      // [bcap][ncap]  (cx*48+cy) << 16 | i : GetFeaturesInArea visiting order
-    float* nbmax = nullptr;          // [bcap] max squared norm of the frame descriptors (float bits, atomicMax)
-    int staged_n = 0;
-    // row side, [bcap][max_rows]
-    float *proj = nullptr, *vcos = nullptr;
-    RowParam* rowp = nullptr;
-    float th = 0.f, ratio = 0.f;
-    int mode = 0;            // PPG_SEARCH_EXTEND_MAP / PPG_SEARCH_WINDOW
-    float max_dist = 0.f;    // mode 1 acceptance threshold
-    double e2_max = 0.0;     // mode 1 circular limit (Fuse), 0 = none
-    int staged_rows = 0, staged_frames = 0;
-    // results, [bcap][max_rows]
-    int* cand = nullptr;  // x4
-    float* guard = nullptr;
-    int *best_idx = nullptr, *second_idx = nullptr;
-    float *best_d = nullptr, *second_d = nullptr;
-    uint8_t* accept = nullptr;
-    int* fallback = nullptr;
-    uint8_t* h_res = nullptr;  // pinned staging for fetch: 5 planes [bcap][max_rows] (4 x 4 bytes, 1 x 1 byte)
-    size_t h_res_bytes = 0;
-    float* h_stage = nullptr;  // pinned staging for the per-frame projections: [bcap][max_rows] x (2 + 1) floats
-};
-
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -125,10 +64,6 @@ __global__ void __launch_bounds__(256) prep_map_kernel(const float* __restrict__
     prep_row(src, dst, n2, row, n, threadIdx.x & 31, nullptr);
 }
 
-struct GridParam {
-    int minX, minY;
-    float wInv, hInv;
-};
 
 // Frame side of one call, grid (ncap/8, frames): descriptors -> bf16 + norms; Frame::PosInGrid
 // (Frame.cpp:317-327) of every keypoint + the free mask (Matcher.cpp:253).
@@ -193,22 +128,6 @@ __global__ void prep_rows_kernel(const float* __restrict__ proj, const float* __
     if (y1 < 0) empty = true;
     p.cells = empty ? 0xffffffffu : ((uint32_t)x0 | ((uint32_t)x1 << 8) | ((uint32_t)y0 << 16) | ((uint32_t)y1 << 24));
     rp[o] = p;
-}
-
-// e2_max > 0 (Fuse, Matcher.cpp:1000-1005): candidates farther than sqrt(e2_max) from the projection are skipped;
-// float e2 compared with the double literal, as the reference does.
-__device__ __forceinline__ bool in_window(const RowParam& p, uint32_t info, float x, float y, double e2_max) {
-    if (!(info & 0x10000u) || p.cells == 0xffffffffu) return false;
-    const uint32_t cx = info & 0xff, cy = (info >> 8) & 0xff;
-    if (cx < (p.cells & 0xff) || cx > ((p.cells >> 8) & 0xff) || cy < ((p.cells >> 16) & 0xff) || cy > (p.cells >> 24))
-        return false;
-    if (!(fabsf(x - p.u) < p.r && fabsf(y - p.v) < p.r)) return false;  // Frame.cpp:305-309
-    if (e2_max > 0.0) {
-        const float ex = p.u - x, ey = p.v - y;
-        const float e2 = ex * ex + ey * ey;
-        if ((double)e2 > e2_max) return false;
-    }
-    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -487,21 +406,6 @@ assoc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
-// DescriptorDistance in the fixed order shared with the oracle (ppgo_descriptor_distance): lane l sums
-// elements l, l+32, ... in order, then an xor butterfly 16,8,4,2,1; every lane ends with the same value.
-// `av` = the map row's elements lane, lane + 32, ... held in registers across the candidates of a row.
-__device__ __forceinline__ float exact_distance(const float (&av)[8], const float* __restrict__ b, int lane) {
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const float d = av[k] - b[lane + 32 * k];
-        s = s + d * d;
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) s = s + __shfl_xor_sync(AFULL, s, m);
-    return sqrtf(s);
-}
-
 struct RescoreParams {
     int rows, max_rows, ncap;
     FrameSrc src;
@@ -522,18 +426,6 @@ struct RescoreParams {
     uint8_t* accept;
     int* fallback;
 };
-
-// best = first minimum, second = first minimum of the rest, both in GetFeaturesInArea order
-// (equivalent to the strict-< update at Matcher.cpp:262-271).
-__device__ __forceinline__ void top2_update(float d, uint32_t ord, int idx, float& b1, uint32_t& o1, int& i1, float& b2,
-                                            uint32_t& o2, int& i2) {
-    if (d < b1 || (d == b1 && ord < o1)) {
-        b2 = b1; o2 = o1; i2 = i1;
-        b1 = d; o1 = ord; i1 = idx;
-    } else if (d < b2 || (d == b2 && ord < o2)) {
-        b2 = d; o2 = ord; i2 = idx;
-    }
-}
 
 __global__ void __launch_bounds__(256) assoc_rescore_kernel(const RescoreParams p) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -700,16 +592,13 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
     d[lane + 32] = b < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : src[lane + 32];
 }
 
-template <typename T>
-cudaError_t dalloc(T** p, size_t count) {
-    return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
-}
-
 int gemm_smem(const AssocState* s) {
     return A_STAGES * A_STAGE_BYTES + 1024 + 20 * 8 + 16 + s->ncap * 16 + A_QCAP * 256 * 8 + 9 * 128 * 4 + 64;
 }
 
-int ensure_state(ppg_ctx* c) {
+}  // namespace
+
+int assoc_ensure_state(ppg_ctx* c) {
     if (c->assoc) return PPG_OK;
     AssocState* s = new AssocState();
     c->assoc = s;
@@ -752,7 +641,7 @@ int ensure_state(ppg_ctx* c) {
     return PPG_OK;
 }
 
-FrameSrc staged_src(const AssocState* s) {
+FrameSrc assoc_staged_src(const AssocState* s) {
     FrameSrc f;
     f.kx = reinterpret_cast<const uint8_t*>(s->kx);
     f.ky = reinterpret_cast<const uint8_t*>(s->ky);
@@ -767,7 +656,7 @@ FrameSrc staged_src(const AssocState* s) {
 
 // Frames first..first+frames-1 of the last extraction batch: mvKeysUn[i].mPos as run() returns it (kp_x, kp_y)
 // and the descriptors, still on the device.
-FrameSrc extracted_src(const ppg_ctx* c, int first) {
+FrameSrc assoc_extracted_src(const ppg_ctx* c, int first) {
     const OutLayout& L = c->post.lay;
     const uint8_t* blk = c->d_out + (size_t)first * L.total;
     FrameSrc f;
@@ -782,20 +671,31 @@ FrameSrc extracted_src(const ppg_ctx* c, int first) {
     return f;
 }
 
+int assoc_prep(ppg_ctx* c, const FrameSrc& src, int frames) {
+    AssocState* s = c->assoc;
+    const int rows = s->staged_rows;
+    GridParam g{c->minX, c->minY, c->wInv, c->hInv};
+    PPG_CUDA(c, cudaMemsetAsync(s->nbmax, 0, 4 * frames, c->st));
+    prep_frame_kernel<<<dim3(s->ncap / 8, frames), 256, 0, c->st>>>(src, s->ncap, g, s->f_bf, s->fn2, s->kinfo,
+                                                                    s->korder, s->nbmax);
+    prep_rows_kernel<<<dim3((rows + 255) / 256, frames), 256, 0, c->st>>>(s->proj, s->vcos, s->map_n2, rows,
+                                                                          s->max_rows, s->th, s->mode, g, s->rowp);
+    c->launches += 2;
+    PPG_CUDA(c, cudaGetLastError());
+    return PPG_OK;
+}
+
+namespace {
+
 // prep + gemm + rescore on the ctx stream for `frames` frames; results land in slots 0..frames-1.
 int run_assoc(ppg_ctx* c, const FrameSrc& src, int frames, int force_exact) {
     AssocState* s = c->assoc;
     const int rows = s->staged_rows;
     if (rows < 1 || rows > s->n_rows) return set_err(c, PPG_ERR_ARG, "association: stage rows first (<= uploaded rows)");
     if (frames < 1 || frames > s->bcap) return set_err(c, PPG_ERR_ARG, "association: bad frame count");
-    GridParam g{c->minX, c->minY, c->wInv, c->hInv};
-    PPG_CUDA(c, cudaMemsetAsync(s->nbmax, 0, 4 * frames, c->st));
     PPG_CUDA(c, cudaMemsetAsync(s->fallback, 0, 4, c->st));
-    prep_frame_kernel<<<dim3(s->ncap / 8, frames), 256, 0, c->st>>>(src, s->ncap, g, s->f_bf, s->fn2, s->kinfo,
-                                                                    s->korder, s->nbmax);
-    prep_rows_kernel<<<dim3((rows + 255) / 256, frames), 256, 0, c->st>>>(s->proj, s->vcos, s->map_n2, rows,
-                                                                          s->max_rows, s->th, s->mode, g, s->rowp);
-    c->launches += 2;
+    int rc = assoc_prep(c, src, frames);
+    if (rc != PPG_OK) return rc;
     if (!force_exact) {
         GemmParams gp;
         gp.rows = rows;
@@ -880,35 +780,14 @@ void assoc_destroy(ppg_ctx* c) {
                     s->best_idx, s->second_idx, s->best_d, s->second_d, s->accept, s->fallback};
     for (void* b : bufs)
         if (b) cudaFree(b);
+    extend_destroy(s);
     if (s->h_res) cudaFreeHost(s->h_res);
     if (s->h_stage) cudaFreeHost(s->h_stage);
     delete s;
     c->assoc = nullptr;
 }
 
-}  // namespace ppg
-
-using namespace ppg;
-
-extern "C" {
-
-int ppg_upload_map(ppg_ctx* c, const float* map_desc, int n_rows) {
-    if (!c || !map_desc || n_rows < 1) return set_err(c, PPG_ERR_ARG, "ppg_upload_map: bad arguments");
-    PPG_CUDA(c, cudaSetDevice(c->dev));
-    int rc = ensure_state(c);
-    if (rc != PPG_OK) return rc;
-    AssocState* s = c->assoc;
-    if (n_rows > s->max_rows) return set_err(c, PPG_ERR_ARG, "ppg_upload_map: more rows than max_map_points");
-    PPG_CUDA(c, cudaMemcpyAsync(s->map_f32, map_desc, (size_t)n_rows * 1024, cudaMemcpyHostToDevice, c->st));
-    prep_map_kernel<<<(n_rows + 7) / 8, 256, 0, c->st>>>(s->map_f32, s->map_bf, s->map_n2, n_rows, n_rows);
-    c->launches++;
-    PPG_CUDA(c, cudaGetLastError());
-    PPG_CUDA(c, cudaStreamSynchronize(c->st));
-    s->n_rows = n_rows;
-    return PPG_OK;
-}
-
-static int stage_rows(ppg_ctx* c, int frames, int n_rows, const float* proj_uv, const float* view_cos, float th,
+int assoc_stage_rows(ppg_ctx* c, int frames, int n_rows, const float* proj_uv, const float* view_cos, float th,
                       float ratio) {
     AssocState* s = c->assoc;
     if (n_rows < 1 || n_rows > s->n_rows || !proj_uv || !view_cos)
@@ -935,16 +814,38 @@ static int stage_rows(ppg_ctx* c, int frames, int n_rows, const float* proj_uv, 
     return PPG_OK;
 }
 
+}  // namespace ppg
+
+using namespace ppg;
+
+extern "C" {
+
+int ppg_upload_map(ppg_ctx* c, const float* map_desc, int n_rows) {
+    if (!c || !map_desc || n_rows < 1) return set_err(c, PPG_ERR_ARG, "ppg_upload_map: bad arguments");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    int rc = assoc_ensure_state(c);
+    if (rc != PPG_OK) return rc;
+    AssocState* s = c->assoc;
+    if (n_rows > s->max_rows) return set_err(c, PPG_ERR_ARG, "ppg_upload_map: more rows than max_map_points");
+    PPG_CUDA(c, cudaMemcpyAsync(s->map_f32, map_desc, (size_t)n_rows * 1024, cudaMemcpyHostToDevice, c->st));
+    prep_map_kernel<<<(n_rows + 7) / 8, 256, 0, c->st>>>(s->map_f32, s->map_bf, s->map_n2, n_rows, n_rows);
+    c->launches++;
+    PPG_CUDA(c, cudaGetLastError());
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    s->n_rows = n_rows;
+    return PPG_OK;
+}
+
 int ppg_assoc_stage(ppg_ctx* c, const ppg_assoc_in* in) {
     if (!c || !in) return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage: null argument");
     PPG_CUDA(c, cudaSetDevice(c->dev));
-    int rc = ensure_state(c);
+    int rc = assoc_ensure_state(c);
     if (rc != PPG_OK) return rc;
     AssocState* s = c->assoc;
     if (in->n_kp < 0 || in->n_kp > s->ncap) return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage: too many keypoints");
     if (in->mode == PPG_SEARCH_WINDOW && !in->view_cos)
         return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage: view_cos must point to n_rows floats (ignored in mode 1)");
-    if ((rc = stage_rows(c, 1, in->n_rows, in->proj_uv, in->view_cos, in->th, in->ratio)) != PPG_OK) return rc;
+    if ((rc = assoc_stage_rows(c, 1, in->n_rows, in->proj_uv, in->view_cos, in->th, in->ratio)) != PPG_OK) return rc;
     if (in->n_kp > 0 && in->kp_x && in->kp_y && in->frame_desc) {
         PPG_CUDA(c, cudaMemcpyAsync(s->kx, in->kp_x, (size_t)in->n_kp * 4, cudaMemcpyHostToDevice, c->st));
         PPG_CUDA(c, cudaMemcpyAsync(s->ky, in->kp_y, (size_t)in->n_kp * 4, cudaMemcpyHostToDevice, c->st));
@@ -968,9 +869,9 @@ int ppg_assoc_stage_batch(ppg_ctx* c, int n_frames, int n_rows, const float* pro
                           float ratio) {
     if (!c) return PPG_ERR_ARG;
     PPG_CUDA(c, cudaSetDevice(c->dev));
-    int rc = ensure_state(c);
+    int rc = assoc_ensure_state(c);
     if (rc != PPG_OK) return rc;
-    if ((rc = stage_rows(c, n_frames, n_rows, proj_uv, view_cos, th, ratio)) != PPG_OK) return rc;
+    if ((rc = assoc_stage_rows(c, n_frames, n_rows, proj_uv, view_cos, th, ratio)) != PPG_OK) return rc;
     PPG_CUDA(c, cudaStreamSynchronize(c->st));
     return PPG_OK;
 }
@@ -978,21 +879,21 @@ int ppg_assoc_stage_batch(ppg_ctx* c, int n_frames, int n_rows, const float* pro
 int ppg_assoc_run(ppg_ctx* c) {
     if (!c || !c->assoc) return set_err(c, PPG_ERR_ARG, "ppg_assoc_run: nothing staged");
     PPG_CUDA(c, cudaSetDevice(c->dev));
-    return run_assoc(c, staged_src(c->assoc), 1, 0);
+    return run_assoc(c, assoc_staged_src(c->assoc), 1, 0);
 }
 
 int ppg_assoc_run_frame(ppg_ctx* c, int frame) {
     if (!c || !c->assoc || frame < 0 || frame >= c->maxB)
         return set_err(c, PPG_ERR_ARG, "ppg_assoc_run_frame: bad frame or nothing staged");
     PPG_CUDA(c, cudaSetDevice(c->dev));
-    return run_assoc(c, extracted_src(c, frame), 1, 0);
+    return run_assoc(c, assoc_extracted_src(c, frame), 1, 0);
 }
 
 int ppg_assoc_run_batch(ppg_ctx* c, int n_frames) {
     if (!c || !c->assoc || n_frames < 1 || n_frames > c->maxB || n_frames > c->assoc->staged_frames)
         return set_err(c, PPG_ERR_ARG, "ppg_assoc_run_batch: stage projections for every frame first");
     PPG_CUDA(c, cudaSetDevice(c->dev));
-    return run_assoc(c, extracted_src(c, 0), n_frames, 0);
+    return run_assoc(c, assoc_extracted_src(c, 0), n_frames, 0);
 }
 
 int ppg_assoc_fetch(ppg_ctx* c, ppg_assoc_out* out) {
@@ -1027,7 +928,7 @@ static int distinctive_impl(ppg_ctx* c, const float* desc, const int32_t* offset
                             bool to_table) {
     if (!c || !desc || !offsets || n_points < 1) return set_err(c, PPG_ERR_ARG, "distinctive descriptors: bad arguments");
     PPG_CUDA(c, cudaSetDevice(c->dev));
-    int rc = ensure_state(c);
+    int rc = assoc_ensure_state(c);
     if (rc != PPG_OK) return rc;
     AssocState* s = c->assoc;
     if (to_table && n_points > s->max_rows)

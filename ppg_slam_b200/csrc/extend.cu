@@ -1,0 +1,818 @@
+// The whole Matcher::ExtendMapMatches (matching/src/Matcher.cpp:203-381) on the GPU.
+//
+// The reference walks the candidate map points one after the other because every accepted match changes what
+// the later ones may take (Matcher.cpp:253) and seed growing assigns further keypoints on the way (:287-377).
+// Split used here:
+//
+//   X1 extend_lists_kernel (grid-wide, one warp per candidate map point and frame)
+//        everything that does NOT depend on the walk: the keypoints of the search window (Frame::GetFeaturesInArea,
+//        Frame.cpp:262-315) with their exact DescriptorDistance, sorted by (distance, visiting order) -- the first
+//        X_LIST of them are stored.  Whatever the walk has taken by the time it reaches a row, that row's best /
+//        second best are the first two FREE entries of its list (strict-< update at :262-271 = first minimum in
+//        visiting order), so the walk never computes a window distance again (unless fewer than two free entries
+//        are left of a list that was cut, which falls back to a CTA-wide rescan of the window).
+//   X2 extend_walk_kernel (one CTA per frame)
+//        the sequential part.  256 threads hold 256 consecutive rows of the sorted order and evaluate them against
+//        the live occupancy in shared memory; the first row that is ACCEPTED is an event (rows that are rejected or
+//        empty change nothing and cost nothing), processed by the whole CTA: assignment, then seed growing -- the
+//        weight matrix (:324-340) is computed by 8 warps, one exact distance each, the greedy minimum-weight
+//        assignment (:342-374) by one warp.  The rows after the event are re-evaluated and so on.
+//
+// Results are bit-identical to the CPU restatement of the reference function (tests/test_gpu_extend.py).
+// Built with -fmad=false.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "assoc.cuh"
+#include "ctx.cuh"
+#include "once.cuh"
+
+namespace ppg {
+
+constexpr int X_LIST = 16;                           // window candidates stored per row
+constexpr int X_LCAP = PPG_EXTEND_MAX_DEGREE;        // map edges per map point / key edges per keypoint
+constexpr int X_WCAP = PPG_EXTEND_MAX_WEIGHTS;       // weight-matrix entries per seed
+constexpr int X_THREADS = 256, X_WARPS = X_THREADS / 32;
+constexpr int X_NOEVENT = 1 << 20;
+
+// Where the point-pair graph of frame f lives: staged arrays (one frame) or the extraction output blocks.
+struct FrameGraphSrc {
+    const uint8_t *es, *ee, *coff, *cidx, *ne;
+    size_t stride;
+    int ne_val;
+    __device__ const int* es_of(int f) const { return reinterpret_cast<const int*>(es + f * stride); }
+    __device__ const int* ee_of(int f) const { return reinterpret_cast<const int*>(ee + f * stride); }
+    __device__ const int* coff_of(int f) const { return reinterpret_cast<const int*>(coff + f * stride); }
+    __device__ const int* cidx_of(int f) const { return reinterpret_cast<const int*>(cidx + f * stride); }
+    __device__ int ne_of(int f) const { return ne ? *reinterpret_cast<const int*>(ne + f * stride) : ne_val; }
+};
+
+enum { XR_NMATCHES = 0, XR_STATUS, XR_ACCEPTED, XR_GROWN, XR_RESCANS, XR_NKP, XR_NEDGES, XR_WORDS = 8 };
+
+struct ExtendState {
+    // map graph (shared by all frames)
+    int P = 0, nc = 0, edge_cap = 0;
+    uint8_t *observed = nullptr, *bad = nullptr, *edge_ok = nullptr;
+    int *edge_off = nullptr, *edge_other = nullptr, *order = nullptr;
+    // per-row candidate lists, indexed by position in the sorted order: [bcap][max_rows][X_LIST]
+    uint16_t* l_idx = nullptr;
+    float* l_d = nullptr;
+    uint8_t* l_cnt = nullptr;  // [bcap][max_rows] window size, saturated at 255
+    // per-frame state
+    uint8_t* tracked = nullptr;  // [bcap][max_rows]
+    int* kp_mp = nullptr;        // [bcap][ncap]
+    int* kedge_me = nullptr;     // [bcap][ecap]
+    int* result = nullptr;       // [bcap][XR_WORDS]
+    int ecap = 0;
+    // staged point-pair graph of one frame (ppg_extend_map_matches)
+    int *g_es = nullptr, *g_ee = nullptr, *g_coff = nullptr, *g_cidx = nullptr;
+    // pinned mirrors for the fetch
+    int *h_kp_mp = nullptr, *h_kedge_me = nullptr, *h_result = nullptr;
+    uint8_t* h_tracked = nullptr;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+struct ListParams {
+    int nc, max_rows, ncap;
+    FrameSrc src;
+    const int* order;
+    const RowParam* rowp;
+    const float* map_f32;
+    const uint32_t* kinfo;
+    const uint32_t* korder;
+    uint16_t* l_idx;
+    float* l_d;
+    uint8_t* l_cnt;
+};
+
+__global__ void __launch_bounds__(256) extend_lists_kernel(const ListParams p) {
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int f = blockIdx.y;
+    if (q >= p.nc) return;
+    const int row = p.order[q];
+    const size_t o = (size_t)f * p.max_rows + row, ol = (size_t)f * p.max_rows + q;
+    const int n = min(p.src.n_of(f), p.ncap);
+    const RowParam rp = p.rowp[o];
+    // the sorted list lives across the warp: lane k holds its k-th entry (empty = +inf)
+    float ld = INFINITY;
+    uint32_t lo = 0xffffffffu;
+    int li = -1;
+    int cnt = 0;
+    if (rp.cells != 0xffffffffu) {
+        float a[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = p.map_f32[(size_t)row * 256 + lane + 32 * k];
+        const float* fdesc = p.src.desc_of(f);
+        const float* kx = p.src.kx_of(f);
+        const float* ky = p.src.ky_of(f);
+        const uint32_t* kinfo = p.kinfo + (size_t)f * p.ncap;
+        const uint32_t* korder = p.korder + (size_t)f * p.ncap;
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int c = c0 + lane;
+            bool in = false;
+            if (c < n) in = in_window(rp, kinfo[c], kx[c], ky[c], 0.0);
+            unsigned mask = __ballot_sync(AFULL, in);
+            while (mask) {
+                const int cc = c0 + __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float d = exact_distance(a, fdesc + (size_t)cc * 256, lane);
+                const uint32_t ord = korder[cc];
+                // entries that stay in front of the new one form a prefix of the lanes
+                const bool before = ld < d || (ld == d && lo < ord);
+                const int pos = __popc(__ballot_sync(AFULL, before));
+                const float ud = __shfl_up_sync(AFULL, ld, 1);
+                const uint32_t uo = __shfl_up_sync(AFULL, lo, 1);
+                const int ui = __shfl_up_sync(AFULL, li, 1);
+                if (lane == pos) {
+                    ld = d; lo = ord; li = cc;
+                } else if (lane > pos) {
+                    ld = ud; lo = uo; li = ui;
+                }
+                cnt++;
+            }
+        }
+    }
+    if (lane < X_LIST) {
+        p.l_idx[ol * X_LIST + lane] = li < 0 ? (uint16_t)0xffff : (uint16_t)li;
+        p.l_d[ol * X_LIST + lane] = ld;
+    }
+    if (lane == 0) p.l_cnt[ol] = (uint8_t)min(cnt, 255);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct WalkParams {
+    int nc, P, max_rows, ncap, ecap;
+    FrameSrc src;
+    FrameGraphSrc gsrc;
+    const int* order;
+    const RowParam* rowp;
+    const float* map_f32;
+    const uint32_t* kinfo;
+    const uint32_t* korder;
+    const uint16_t* l_idx;
+    const float* l_d;
+    const uint8_t* l_cnt;
+    const uint8_t *observed, *bad, *edge_ok;
+    const int *edge_off, *edge_other;
+    uint8_t* tracked;  // in (when has_state) / out
+    int* kp_mp;        // in (when has_state) / out
+    int* kedge_me;     // in / out (initialised by the host side)
+    int* result;
+    float ratio, th_high;
+    int has_state;
+};
+
+struct WalkShared {
+    int kpmp[1024];      // F.mvpMapPoints as table rows
+    uint8_t occ[1024];   // mvpMapPoints[i] && Observations() > 0   (Matcher.cpp:253)
+    float w[X_WCAP];     // weight matrix of the current seed, [lx position][key edge]
+    int po[X_LCAP];      // other map point of the valid map edges of pMP (lx)
+    int lxi[X_LCAP];     // their position in getEdges()
+    int ko[X_LCAP];      // other keypoint of every key edge of the seed
+    int ke[X_LCAP];      // the key edge ids
+    int clx[X_LCAP], cly[X_LCAP];  // lx / ly while the greedy assignment erases from them
+    int queue[X_LCAP + 2];         // matchSeed: every push marks one more endpoint of pMP tracked
+    uint16_t cl[1024];   // window of a rescanned row
+    float t2d[X_WARPS][2];
+    uint32_t t2o[X_WARPS][2];
+    int t2i[X_WARPS][2];
+    int wfirst[X_WARPS];
+    int ev[4];           // row, act, best idx
+    int cln, nlx, qn;
+    int res[XR_WORDS];
+};
+
+__device__ __forceinline__ bool trk_get(const uint32_t* trk, int r) { return (trk[r >> 5] >> (r & 31)) & 1u; }
+__device__ __forceinline__ void trk_set(uint32_t* trk, int r) { trk[r >> 5] |= 1u << (r & 31); }
+
+__global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkParams p) {
+    extern __shared__ __align__(16) uint8_t xsm[];
+    WalkShared& S = *reinterpret_cast<WalkShared*>(xsm);
+    uint32_t* trk = reinterpret_cast<uint32_t*>(xsm + ((sizeof(WalkShared) + 15) & ~size_t(15)));
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = min(p.src.n_of(f), p.ncap);
+    const int ne = min(p.gsrc.ne_of(f), p.ecap);
+    const float* fdesc = p.src.desc_of(f);
+    const int* es = p.gsrc.es_of(f);
+    const int* ee = p.gsrc.ee_of(f);
+    const int* coff = p.gsrc.coff_of(f);
+    const int* cidx = p.gsrc.cidx_of(f);
+    int* kedge_me = p.kedge_me + (size_t)f * p.ecap;
+    uint8_t* tracked_g = p.tracked + (size_t)f * p.max_rows;
+    int* kpmp_g = p.kp_mp + (size_t)f * p.ncap;
+
+    // ---- initial state
+    for (int i = tid; i < p.ncap; i += X_THREADS) {
+        int r = -1;
+        if (p.has_state && i < n) r = kpmp_g[i];
+        S.kpmp[i] = r;
+        S.occ[i] = r >= 0 ? (p.observed[r] != 0) : (r == -2);
+    }
+    const int tw = (p.P + 31) >> 5;
+    for (int w = tid; w < tw; w += X_THREADS) {
+        uint32_t bits = 0;
+        if (p.has_state)
+            for (int b = 0; b < 32; b++) {
+                const int r = w * 32 + b;
+                if (r < p.P && tracked_g[r]) bits |= 1u << b;
+            }
+        trk[w] = bits;
+    }
+    if (tid < XR_WORDS) S.res[tid] = 0;
+    __syncthreads();
+
+    for (int base = 0; base < p.nc; base += X_THREADS) {
+        // ---- static part of the 256 rows of this chunk: the stored window lists
+        const int pos = base + tid;
+        int row = -1, cnt = 0;
+        uint16_t idx[X_LIST];
+        float d[X_LIST];
+        if (pos < p.nc) {
+            row = p.order[pos];
+            const size_t ol = (size_t)f * p.max_rows + pos;
+            cnt = p.l_cnt[ol];
+            const uint4* pi = reinterpret_cast<const uint4*>(p.l_idx + ol * X_LIST);
+            const uint4 i0 = pi[0], i1 = pi[1];
+            const uint32_t iw[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                idx[2 * k] = (uint16_t)(iw[k] & 0xffff);
+                idx[2 * k + 1] = (uint16_t)(iw[k] >> 16);
+            }
+            const float4* pd = reinterpret_cast<const float4*>(p.l_d + ol * X_LIST);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float4 v = pd[k];
+                d[4 * k] = v.x; d[4 * k + 1] = v.y; d[4 * k + 2] = v.z; d[4 * k + 3] = v.w;
+            }
+        }
+        const int stored = cnt < X_LIST ? cnt : X_LIST;
+        int cursor = 0;
+        while (true) {
+            // ---- what would the reference do with my row in the current state?  (Matcher.cpp:229-277)
+            int act = 0, bidx = -1;
+            if (row >= 0 && tid >= cursor && cnt > 0 && !trk_get(trk, row)) {
+                float b1 = 1e6f, b2 = 1e6f;
+                int nfree = 0;
+#pragma unroll
+                for (int k = 0; k < X_LIST; k++) {
+                    if (k < stored && !S.occ[idx[k]]) {
+                        if (nfree == 0) {
+                            b1 = d[k];
+                            bidx = idx[k];
+                        } else if (nfree == 1) {
+                            b2 = d[k];
+                        }
+                        nfree++;
+                    }
+                }
+                if (nfree >= 2 || (cnt <= X_LIST && nfree == 1))
+                    act = !(b1 > p.th_high && b1 > p.ratio * b2) ? 1 : 0;  // :276
+                else if (cnt > X_LIST)
+                    act = 2;  // the list was cut and fewer than two free entries are left of it: rescan the window
+                // nfree == 0 with the whole window stored: bestIdx stays -1, the row is rejected (ratio < 1)
+            }
+            const unsigned m = __ballot_sync(AFULL, act != 0);
+            if (lane == 0) S.wfirst[warp] = m ? warp * 32 + __ffs(m) - 1 : X_NOEVENT;
+            __syncthreads();
+            int first = X_NOEVENT;
+#pragma unroll
+            for (int w = 0; w < X_WARPS; w++) first = min(first, S.wfirst[w]);
+            if (first == X_NOEVENT) {
+                __syncthreads();
+                break;
+            }
+            if (tid == first) {
+                S.ev[0] = row;
+                S.ev[1] = act;
+                S.ev[2] = bidx;
+            }
+            __syncthreads();
+            const int erow = S.ev[0];
+            // ---- a cut list ran dry: best / second best over the whole window with the live occupancy
+            if (S.ev[1] == 2) {
+                if (tid == 0) S.cln = 0;
+                __syncthreads();
+                const RowParam rp = p.rowp[(size_t)f * p.max_rows + erow];
+                const float* kx = p.src.kx_of(f);
+                const float* ky = p.src.ky_of(f);
+                const uint32_t* kinfo = p.kinfo + (size_t)f * p.ncap;
+                const uint32_t* korder = p.korder + (size_t)f * p.ncap;
+                for (int c = tid; c < n; c += X_THREADS)
+                    if (in_window(rp, kinfo[c], kx[c], ky[c], 0.0) && !S.occ[c]) S.cl[atomicAdd(&S.cln, 1)] = (uint16_t)c;
+                __syncthreads();
+                float a[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) a[k] = p.map_f32[(size_t)erow * 256 + lane + 32 * k];
+                float b1 = 1e6f, b2 = 1e6f;
+                uint32_t o1 = 0xffffffffu, o2 = 0xffffffffu;
+                int i1 = -1, i2 = -1;
+                const int ncl = S.cln;
+                for (int k = warp; k < ncl; k += X_WARPS) {
+                    const int cc = S.cl[k];
+                    const float dd = exact_distance(a, fdesc + (size_t)cc * 256, lane);
+                    top2_update(dd, korder[cc], cc, b1, o1, i1, b2, o2, i2);
+                }
+                if (lane == 0) {
+                    S.t2d[warp][0] = b1; S.t2o[warp][0] = o1; S.t2i[warp][0] = i1;
+                    S.t2d[warp][1] = b2; S.t2o[warp][1] = o2; S.t2i[warp][1] = i2;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    b1 = b2 = 1e6f;
+                    o1 = o2 = 0xffffffffu;
+                    i1 = i2 = -1;
+                    for (int w = 0; w < X_WARPS; w++)
+                        for (int k = 0; k < 2; k++)
+                            if (S.t2i[w][k] >= 0) top2_update(S.t2d[w][k], S.t2o[w][k], S.t2i[w][k], b1, o1, i1, b2, o2, i2);
+                    S.ev[1] = (i1 >= 0 && !(b1 > p.th_high && b1 > p.ratio * b2)) ? 1 : 0;
+                    S.ev[2] = i1;
+                    S.res[XR_RESCANS]++;
+                }
+                __syncthreads();
+            }
+            if (S.ev[1] == 1) {
+                // ---- accepted: F.mvpMapPoints[bestIdx] = pMP (:279-281), then seed growing (:287-377)
+                const int bestIdx = S.ev[2];
+                const int me0 = p.edge_off[erow], nme = p.edge_off[erow + 1] - me0;
+                const bool deg_ok = nme <= X_LCAP;
+                if (tid == 0) {
+                    S.kpmp[bestIdx] = erow;
+                    S.occ[bestIdx] = p.observed[erow] != 0;
+                    trk_set(trk, erow);
+                    S.res[XR_NMATCHES] += 2;  // :281 and :378
+                    S.res[XR_ACCEPTED]++;
+                    S.queue[0] = bestIdx;
+                    S.qn = 1;
+                    S.nlx = 0;
+                    if (!deg_ok) S.res[XR_STATUS] |= PPG_EXTEND_OVF;
+                }
+                // lx: the valid map edges of pMP (:312-318); mapEdge_set is pMP's for every seed of the event
+                if (warp == 0 && deg_ok) {
+                    int nlx = 0;
+                    for (int i0 = 0; i0 < nme; i0 += 32) {
+                        const int i = i0 + lane;
+                        int other = -1;
+                        bool ok = false;
+                        if (i < nme) {
+                            other = p.edge_other[me0 + i];
+                            ok = p.edge_ok[me0 + i] != 0 && other >= 0;
+                        }
+                        const unsigned mk = __ballot_sync(AFULL, ok);
+                        if (ok) {
+                            const int k = nlx + __popc(mk & ((1u << lane) - 1u));
+                            S.po[k] = other;
+                            S.lxi[k] = i;
+                        }
+                        nlx += __popc(mk);
+                    }
+                    if (lane == 0) S.nlx = nlx;
+                }
+                __syncthreads();
+                const int nlx0 = S.nlx;
+                int qh = 0;
+                while (deg_ok && nme > 0) {
+                    if (qh >= S.qn) break;
+                    const int keyID = S.queue[qh++];
+                    const int ke0 = coff[keyID], nke = coff[keyID + 1] - ke0;
+                    if (nke == 0) continue;  // :300-301
+                    if (nke > X_LCAP || nlx0 * nke > X_WCAP) {
+                        if (tid == 0) S.res[XR_STATUS] |= PPG_EXTEND_OVF;
+                        continue;
+                    }
+                    if (nlx0 == 0) continue;  // lx empty: the assignment loop does not run (:342)
+                    for (int j = tid; j < nke; j += X_THREADS) {
+                        const int e = cidx[ke0 + j];
+                        const int s0 = es[e], e0 = ee[e];
+                        S.ke[j] = e;
+                        S.ko[j] = s0 == keyID ? e0 : s0;  // KeyEdge::theOtherPid
+                        S.cly[j] = j;
+                    }
+                    for (int i = tid; i < nlx0; i += X_THREADS) S.clx[i] = i;
+                    __syncthreads();
+                    // weight matrix (:324-340), one warp per entry
+                    for (int q = warp; q < nlx0 * nke; q += X_WARPS) {
+                        const int i = q / nke, j = q - i * nke;
+                        const int po = S.po[i], ko = S.ko[j];
+                        float w;
+                        if (po == S.kpmp[ko]) {
+                            w = -1.f;
+                        } else {
+                            float a[8];
+#pragma unroll
+                            for (int k = 0; k < 8; k++) a[k] = p.map_f32[(size_t)po * 256 + lane + 32 * k];
+                            w = exact_distance(a, fdesc + (size_t)ko * 256, lane);
+                        }
+                        if (lane == 0) S.w[q] = w;
+                    }
+                    __syncthreads();
+                    // greedy minimum-weight assignment (:342-374), one warp
+                    if (warp == 0) {
+                        int nlx = nlx0, nly = nke;
+                        while (nlx > 0 && nly > 0) {
+                            float bw = 1e6f;
+                            int bq = 0x7fffffff;
+                            for (int q = lane; q < nlx * nly; q += 32) {
+                                const int a = q / nly, b = q - a * nly;
+                                const float w = S.w[S.clx[a] * nke + S.cly[b]];
+                                if (w < bw) {  // strict <: the first minimum in (a, b) order wins
+                                    bw = w;
+                                    bq = q;
+                                }
+                            }
+#pragma unroll
+                            for (int mm = 16; mm >= 1; mm >>= 1) {
+                                const float ow = __shfl_xor_sync(AFULL, bw, mm);
+                                const int oq = __shfl_xor_sync(AFULL, bq, mm);
+                                if (ow < bw || (ow == bw && oq < bq)) {
+                                    bw = ow;
+                                    bq = oq;
+                                }
+                            }
+                            if (bq == 0x7fffffff || bw > p.th_high) break;  // :357-358
+                            const int a = bq / nly, b = bq - a * nly;
+                            const int mi = S.clx[a], kj = S.cly[b];
+                            // lx.erase / ly.erase keep the order of the rest
+                            int tx[X_LCAP / 32], ty[X_LCAP / 32];
+#pragma unroll
+                            for (int k = 0; k < X_LCAP / 32; k++) {
+                                const int t = lane + 32 * k;
+                                tx[k] = (t >= a && t + 1 < nlx) ? S.clx[t + 1] : (t < nlx ? S.clx[t] : 0);
+                                ty[k] = (t >= b && t + 1 < nly) ? S.cly[t + 1] : (t < nly ? S.cly[t] : 0);
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int k = 0; k < X_LCAP / 32; k++) {
+                                const int t = lane + 32 * k;
+                                if (t < nlx) S.clx[t] = tx[k];
+                                if (t < nly) S.cly[t] = ty[k];
+                            }
+                            nlx--;
+                            nly--;
+                            if (lane == 0) {
+                                const int po = S.po[mi], ko = S.ko[kj];
+                                if (!(p.bad[po] || trk_get(trk, po))) {  // :364-365
+                                    S.kpmp[ko] = po;                     // :366
+                                    S.occ[ko] = p.observed[po] != 0;
+                                    kedge_me[S.ke[kj]] = me0 + S.lxi[mi];
+                                    trk_set(trk, po);
+                                    S.res[XR_GROWN]++;
+                                    if (S.qn < X_LCAP + 2) S.queue[S.qn++] = ko;
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            cursor = first + 1;
+            __syncthreads();
+        }
+    }
+
+    // ---- results
+    for (int i = tid; i < p.ncap; i += X_THREADS) kpmp_g[i] = S.kpmp[i];
+    for (int r = tid; r < p.P; r += X_THREADS) tracked_g[r] = trk_get(trk, r) ? 1 : 0;
+    if (tid == 0) {
+        S.res[XR_NKP] = n;
+        S.res[XR_NEDGES] = ne;
+    }
+    __syncthreads();
+    if (tid < XR_WORDS) p.result[f * XR_WORDS + tid] = S.res[tid];
+}
+
+size_t walk_smem(int P) { return ((sizeof(WalkShared) + 15) & ~size_t(15)) + (size_t)((P + 31) / 32) * 4 + 16; }
+
+int ensure_extend(ppg_ctx* c) {
+    int rc = assoc_ensure_state(c);
+    if (rc != PPG_OK) return rc;
+    AssocState* s = c->assoc;
+    if (s->ext) return PPG_OK;
+    if (s->ncap > 1024) return set_err(c, PPG_ERR_ARG, "extend: keypoint capacity above 1024");
+    ExtendState* x = new ExtendState();
+    s->ext = x;
+    const size_t R = s->max_rows, N = s->ncap, B = s->bcap;
+    x->ecap = c->post.lay.max_edges;
+    const size_t E = x->ecap;
+    PPG_CUDA(c, dalloc(&x->observed, R));
+    PPG_CUDA(c, dalloc(&x->bad, R));
+    PPG_CUDA(c, dalloc(&x->edge_off, R + 1));
+    PPG_CUDA(c, dalloc(&x->order, R));
+    PPG_CUDA(c, dalloc(&x->l_idx, B * R * X_LIST));
+    PPG_CUDA(c, dalloc(&x->l_d, B * R * X_LIST));
+    PPG_CUDA(c, dalloc(&x->l_cnt, B * R));
+    PPG_CUDA(c, dalloc(&x->tracked, B * R));
+    PPG_CUDA(c, dalloc(&x->kp_mp, B * N));
+    PPG_CUDA(c, dalloc(&x->kedge_me, B * E));
+    PPG_CUDA(c, dalloc(&x->result, B * XR_WORDS));
+    PPG_CUDA(c, dalloc(&x->g_es, E));
+    PPG_CUDA(c, dalloc(&x->g_ee, E));
+    PPG_CUDA(c, dalloc(&x->g_coff, N + 1));
+    PPG_CUDA(c, dalloc(&x->g_cidx, 2 * E));
+    PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&x->h_kp_mp), B * N * 4));
+    PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&x->h_kedge_me), B * E * 4));
+    PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&x->h_result), B * XR_WORDS * 4));
+    PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&x->h_tracked), B * R));
+    static bool attr_done[64];
+    static std::mutex attr_mu;
+    PPG_CUDA(c, once_per_device(attr_done, attr_mu, [] {
+                 return cudaFuncSetAttribute(extend_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+             }));
+    return PPG_OK;
+}
+
+FrameGraphSrc staged_graph(const ExtendState* x, int ne) {
+    FrameGraphSrc g;
+    g.es = reinterpret_cast<const uint8_t*>(x->g_es);
+    g.ee = reinterpret_cast<const uint8_t*>(x->g_ee);
+    g.coff = reinterpret_cast<const uint8_t*>(x->g_coff);
+    g.cidx = reinterpret_cast<const uint8_t*>(x->g_cidx);
+    g.ne = nullptr;
+    g.stride = 0;
+    g.ne_val = ne;
+    return g;
+}
+
+FrameGraphSrc extracted_graph(const ppg_ctx* c) {
+    const OutLayout& L = c->post.lay;
+    const uint8_t* blk = c->d_out;
+    FrameGraphSrc g;
+    g.es = blk + L.edge_s;
+    g.ee = blk + L.edge_e;
+    g.coff = blk + L.conn_off;
+    g.cidx = blk + L.conn_idx;
+    g.ne = blk + L.hdr + HDR_NEDGES * sizeof(int);
+    g.stride = L.total;
+    g.ne_val = 0;
+    return g;
+}
+
+// prep + lists + walk on the ctx stream
+int run_extend(ppg_ctx* c, const FrameSrc& src, const FrameGraphSrc& gsrc, int frames, int has_state) {
+    AssocState* s = c->assoc;
+    ExtendState* x = s->ext;
+    int rc = assoc_prep(c, src, frames);
+    if (rc != PPG_OK) return rc;
+    if (x->nc > 0) {
+        ListParams lp;
+        lp.nc = x->nc;
+        lp.max_rows = s->max_rows;
+        lp.ncap = s->ncap;
+        lp.src = src;
+        lp.order = x->order;
+        lp.rowp = s->rowp;
+        lp.map_f32 = s->map_f32;
+        lp.kinfo = s->kinfo;
+        lp.korder = s->korder;
+        lp.l_idx = x->l_idx;
+        lp.l_d = x->l_d;
+        lp.l_cnt = x->l_cnt;
+        extend_lists_kernel<<<dim3((x->nc + 7) / 8, frames), 256, 0, c->st>>>(lp);
+        c->launches++;
+    }
+    WalkParams wp;
+    wp.nc = x->nc;
+    wp.P = x->P;
+    wp.max_rows = s->max_rows;
+    wp.ncap = s->ncap;
+    wp.ecap = x->ecap;
+    wp.src = src;
+    wp.gsrc = gsrc;
+    wp.order = x->order;
+    wp.rowp = s->rowp;
+    wp.map_f32 = s->map_f32;
+    wp.kinfo = s->kinfo;
+    wp.korder = s->korder;
+    wp.l_idx = x->l_idx;
+    wp.l_d = x->l_d;
+    wp.l_cnt = x->l_cnt;
+    wp.observed = x->observed;
+    wp.bad = x->bad;
+    wp.edge_ok = x->edge_ok;
+    wp.edge_off = x->edge_off;
+    wp.edge_other = x->edge_other;
+    wp.tracked = x->tracked;
+    wp.kp_mp = x->kp_mp;
+    wp.kedge_me = x->kedge_me;
+    wp.result = x->result;
+    wp.ratio = s->ratio;
+    wp.th_high = c->cfg.th_high;
+    wp.has_state = has_state;
+    extend_walk_kernel<<<frames, X_THREADS, walk_smem(x->P), c->st>>>(wp);
+    c->launches++;
+    PPG_CUDA(c, cudaGetLastError());
+    return PPG_OK;
+}
+
+int check_status(ppg_ctx* c, const int* res, int frames) {
+    for (int f = 0; f < frames; f++)
+        if (res[f * XR_WORDS + XR_STATUS] & PPG_EXTEND_OVF)
+            return set_err(c, PPG_ERR_CAPACITY,
+                           "ExtendMapMatches: a map point / keypoint has more edges than PPG_EXTEND_MAX_DEGREE or a "
+                           "seed's weight matrix exceeds PPG_EXTEND_MAX_WEIGHTS (frame " + std::to_string(f) + ")");
+    return PPG_OK;
+}
+
+void fill_out(const ExtendState* x, const AssocState* s, int f, ppg_extend_out* o) {
+    const int* r = x->h_result + f * XR_WORDS;
+    o->nmatches = r[XR_NMATCHES];
+    o->status = (uint32_t)r[XR_STATUS];
+    o->n_kp = r[XR_NKP];
+    o->n_edges = r[XR_NEDGES];
+    o->n_accepted = r[XR_ACCEPTED];
+    o->n_grown = r[XR_GROWN];
+    o->n_rescans = r[XR_RESCANS];
+    if (o->kp_mp) memcpy(o->kp_mp, x->h_kp_mp + (size_t)f * s->ncap, (size_t)o->n_kp * 4);
+    if (o->kedge_me) memcpy(o->kedge_me, x->h_kedge_me + (size_t)f * x->ecap, (size_t)o->n_edges * 4);
+    if (o->tracked) memcpy(o->tracked, x->h_tracked + (size_t)f * x->P, (size_t)x->P);
+}
+
+int fetch_extend(ppg_ctx* c, int frames) {
+    AssocState* s = c->assoc;
+    ExtendState* x = s->ext;
+    PPG_CUDA(c, cudaMemcpyAsync(x->h_result, x->result, (size_t)frames * XR_WORDS * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(x->h_kp_mp, x->kp_mp, (size_t)frames * s->ncap * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(x->h_kedge_me, x->kedge_me, (size_t)frames * x->ecap * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaMemcpy2DAsync(x->h_tracked, (size_t)x->P, x->tracked, (size_t)s->max_rows, (size_t)x->P, frames,
+                                  cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    return PPG_OK;
+}
+
+}  // namespace
+
+void extend_destroy(AssocState* s) {
+    ExtendState* x = s->ext;
+    if (!x) return;
+    void* bufs[] = {x->observed, x->bad, x->edge_ok, x->edge_off, x->edge_other, x->order, x->l_idx, x->l_d, x->l_cnt,
+                    x->tracked, x->kp_mp, x->kedge_me, x->result, x->g_es, x->g_ee, x->g_coff, x->g_cidx};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    void* hbufs[] = {x->h_kp_mp, x->h_kedge_me, x->h_result, x->h_tracked};
+    for (void* b : hbufs)
+        if (b) cudaFreeHost(b);
+    delete x;
+    s->ext = nullptr;
+}
+
+}  // namespace ppg
+
+using namespace ppg;
+
+extern "C" {
+
+int ppg_upload_map_graph(ppg_ctx* c, const ppg_map_graph* g) {
+    if (!c || !g || g->n_points < 1 || !g->candidate || !g->observed || !g->bad || !g->edge_off)
+        return set_err(c, PPG_ERR_ARG, "ppg_upload_map_graph: bad arguments");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    int rc = ensure_extend(c);
+    if (rc != PPG_OK) return rc;
+    AssocState* s = c->assoc;
+    ExtendState* x = s->ext;
+    const int P = g->n_points;
+    if (P > s->n_rows) return set_err(c, PPG_ERR_ARG, "ppg_upload_map_graph: upload the descriptors of all n_points rows first");
+    const int ne = g->edge_off[P];
+    if (g->edge_off[0] != 0 || ne < 0 || (ne > 0 && (!g->edge_other || !g->edge_ok)))
+        return set_err(c, PPG_ERR_ARG, "ppg_upload_map_graph: malformed edge CSR");
+    for (int p = 0; p < P; p++)
+        if (g->edge_off[p + 1] < g->edge_off[p]) return set_err(c, PPG_ERR_ARG, "ppg_upload_map_graph: malformed edge CSR");
+    for (int k = 0; k < ne; k++)
+        if (g->edge_other[k] >= P) return set_err(c, PPG_ERR_ARG, "ppg_upload_map_graph: edge endpoint outside the table");
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    if (ne > x->edge_cap) {
+        if (x->edge_other) cudaFree(x->edge_other);
+        if (x->edge_ok) cudaFree(x->edge_ok);
+        x->edge_other = nullptr;
+        x->edge_ok = nullptr;
+        x->edge_cap = 0;
+        const size_t cap = (size_t)ne + ne / 2 + 1024;
+        PPG_CUDA(c, dalloc(&x->edge_other, cap));
+        PPG_CUDA(c, dalloc(&x->edge_ok, cap));
+        x->edge_cap = (int)cap;
+    }
+    // std::sort by getEdges().size() descending over the trackable points (Matcher.cpp:210-224); ties keep table order
+    std::vector<int> order;
+    order.reserve(P);
+    for (int p = 0; p < P; p++)
+        if (g->candidate[p] && !g->bad[p]) order.push_back(p);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return g->edge_off[a + 1] - g->edge_off[a] > g->edge_off[b + 1] - g->edge_off[b];
+    });
+    PPG_CUDA(c, cudaMemcpyAsync(x->observed, g->observed, (size_t)P, cudaMemcpyHostToDevice, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(x->bad, g->bad, (size_t)P, cudaMemcpyHostToDevice, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(x->edge_off, g->edge_off, ((size_t)P + 1) * 4, cudaMemcpyHostToDevice, c->st));
+    if (ne > 0) {
+        PPG_CUDA(c, cudaMemcpyAsync(x->edge_other, g->edge_other, (size_t)ne * 4, cudaMemcpyHostToDevice, c->st));
+        PPG_CUDA(c, cudaMemcpyAsync(x->edge_ok, g->edge_ok, (size_t)ne, cudaMemcpyHostToDevice, c->st));
+    }
+    if (!order.empty())
+        PPG_CUDA(c, cudaMemcpyAsync(x->order, order.data(), order.size() * 4, cudaMemcpyHostToDevice, c->st));
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    x->P = P;
+    x->nc = (int)order.size();
+    return PPG_OK;
+}
+
+int ppg_extend_map_matches(ppg_ctx* c, const ppg_extend_in* in, ppg_extend_out* out) {
+    if (!c || !in || !out) return set_err(c, PPG_ERR_ARG, "ppg_extend_map_matches: null argument");
+    if (!c->assoc || !c->assoc->ext || c->assoc->ext->P < 1)
+        return set_err(c, PPG_ERR_ARG, "ppg_extend_map_matches: upload the map graph first");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    AssocState* s = c->assoc;
+    ExtendState* x = s->ext;
+    const int N = in->n_kp, E = in->n_edges, P = x->P;
+    if (N < 0 || N > s->ncap || E < 0 || E > x->ecap)
+        return set_err(c, PPG_ERR_ARG, "ppg_extend_map_matches: too many keypoints / key edges");
+    if (!(in->ratio < 1.0f)) return set_err(c, PPG_ERR_ARG, "ppg_extend_map_matches: ratio must be below 1");
+    if (N > 0 && (!in->kp_x || !in->kp_y || !in->frame_desc || !in->conn_off))
+        return set_err(c, PPG_ERR_ARG, "ppg_extend_map_matches: null frame arrays");
+    if (E > 0 && (!in->edge_start || !in->edge_end || !in->conn_idx))
+        return set_err(c, PPG_ERR_ARG, "ppg_extend_map_matches: null key-edge arrays");
+    if (N > 0) {
+        if (in->conn_off[0] != 0 || in->conn_off[N] < 0 || in->conn_off[N] > 2 * x->ecap)
+            return set_err(c, PPG_ERR_ARG, "ppg_extend_map_matches: malformed mvConnected CSR");
+        for (int i = 0; i < N; i++)
+            if (in->conn_off[i + 1] < in->conn_off[i])
+                return set_err(c, PPG_ERR_ARG, "ppg_extend_map_matches: malformed mvConnected CSR");
+        for (int k = 0; k < in->conn_off[N]; k++) {
+            const int e = in->conn_idx[k];
+            if (e < 0 || e >= E) return set_err(c, PPG_ERR_ARG, "ppg_extend_map_matches: mvConnected names a missing edge");
+        }
+        for (int e = 0; e < E; e++)
+            if (in->edge_start[e] < 0 || in->edge_start[e] >= N || in->edge_end[e] < 0 || in->edge_end[e] >= N)
+                return set_err(c, PPG_ERR_ARG, "ppg_extend_map_matches: key edge endpoint out of range");
+        if (in->kp_mp)
+            for (int i = 0; i < N; i++)
+                if (in->kp_mp[i] < -2 || in->kp_mp[i] >= P)
+                    return set_err(c, PPG_ERR_ARG, "ppg_extend_map_matches: kp_mp row out of range");
+    }
+    int rc = assoc_stage_rows(c, 1, P, in->proj_uv, in->view_cos, in->th, in->ratio);
+    if (rc != PPG_OK) return rc;
+    if (N > 0) {
+        PPG_CUDA(c, cudaMemcpyAsync(s->kx, in->kp_x, (size_t)N * 4, cudaMemcpyHostToDevice, c->st));
+        PPG_CUDA(c, cudaMemcpyAsync(s->ky, in->kp_y, (size_t)N * 4, cudaMemcpyHostToDevice, c->st));
+        PPG_CUDA(c, cudaMemcpyAsync(s->fdesc, in->frame_desc, (size_t)N * 1024, cudaMemcpyHostToDevice, c->st));
+        PPG_CUDA(c, cudaMemcpyAsync(x->g_coff, in->conn_off, ((size_t)N + 1) * 4, cudaMemcpyHostToDevice, c->st));
+        if (in->conn_off[N] > 0)
+            PPG_CUDA(c, cudaMemcpyAsync(x->g_cidx, in->conn_idx, (size_t)in->conn_off[N] * 4, cudaMemcpyHostToDevice, c->st));
+        if (in->kp_mp)
+            PPG_CUDA(c, cudaMemcpyAsync(x->kp_mp, in->kp_mp, (size_t)N * 4, cudaMemcpyHostToDevice, c->st));
+        else
+            PPG_CUDA(c, cudaMemsetAsync(x->kp_mp, 0xff, (size_t)N * 4, c->st));
+    }
+    if (E > 0) {
+        PPG_CUDA(c, cudaMemcpyAsync(x->g_es, in->edge_start, (size_t)E * 4, cudaMemcpyHostToDevice, c->st));
+        PPG_CUDA(c, cudaMemcpyAsync(x->g_ee, in->edge_end, (size_t)E * 4, cudaMemcpyHostToDevice, c->st));
+        if (in->kedge_me)
+            PPG_CUDA(c, cudaMemcpyAsync(x->kedge_me, in->kedge_me, (size_t)E * 4, cudaMemcpyHostToDevice, c->st));
+        else
+            PPG_CUDA(c, cudaMemsetAsync(x->kedge_me, 0xff, (size_t)E * 4, c->st));
+    }
+    if (in->tracked)
+        PPG_CUDA(c, cudaMemcpyAsync(x->tracked, in->tracked, (size_t)P, cudaMemcpyHostToDevice, c->st));
+    else
+        PPG_CUDA(c, cudaMemsetAsync(x->tracked, 0, (size_t)P, c->st));
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));  // the caller's arrays are pageable
+    s->staged_n = N;
+    FrameSrc src = assoc_staged_src(s);
+    src.free_mask = s->ones;  // the lists hold every indexable keypoint of the window; occupancy is live in the walk
+    if ((rc = run_extend(c, src, staged_graph(x, E), 1, 1)) != PPG_OK) return rc;
+    if ((rc = fetch_extend(c, 1)) != PPG_OK) return rc;
+    fill_out(x, s, 0, out);
+    return check_status(c, x->h_result, 1);
+}
+
+int ppg_extend_run_batch(ppg_ctx* c, int n_frames) {
+    if (!c || !c->assoc || !c->assoc->ext || c->assoc->ext->P < 1)
+        return set_err(c, PPG_ERR_ARG, "ppg_extend_run_batch: upload the map graph first");
+    AssocState* s = c->assoc;
+    ExtendState* x = s->ext;
+    if (n_frames < 1 || n_frames > c->maxB || n_frames > s->staged_frames || s->staged_rows != x->P)
+        return set_err(c, PPG_ERR_ARG, "ppg_extend_run_batch: stage projections of all n_points rows for every frame first");
+    if (!(s->ratio < 1.0f)) return set_err(c, PPG_ERR_ARG, "ppg_extend_run_batch: ratio must be below 1");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    PPG_CUDA(c, cudaMemsetAsync(x->kedge_me, 0xff, (size_t)n_frames * x->ecap * 4, c->st));
+    s->mode = 0;
+    return run_extend(c, assoc_extracted_src(c, 0), extracted_graph(c), n_frames, 0);
+}
+
+int ppg_extend_fetch_batch(ppg_ctx* c, int n_frames, ppg_extend_out* outs) {
+    if (!c || !c->assoc || !c->assoc->ext || !outs || n_frames < 1 || n_frames > c->assoc->bcap)
+        return set_err(c, PPG_ERR_ARG, "ppg_extend_fetch_batch: bad arguments");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    int rc = fetch_extend(c, n_frames);
+    if (rc != PPG_OK) return rc;
+    for (int f = 0; f < n_frames; f++) fill_out(c->assoc->ext, c->assoc, f, &outs[f]);
+    return check_status(c, c->assoc->ext->h_result, n_frames);
+}
+
+}  // extern "C"

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libppg_b200.so does not export %s" % name
     assert sorted(capi.SYMBOLS) == declared, "capi.SYMBOLS is out of sync with include/ppg_b200.h"
-    assert lib.ppg_api_version() == 2
+    assert lib.ppg_api_version() == 3
 
 
 def test_struct_layouts_match_header():
@@ -49,6 +49,9 @@ def test_struct_layouts_match_header():
     assert fields("ppg_frame_out") == [f[0] for f in capi.FrameOut._fields_]
     assert fields("ppg_assoc_in") == [f[0] for f in capi.AssocIn._fields_]
     assert fields("ppg_assoc_out") == [f[0] for f in capi.AssocOut._fields_]
+    assert fields("ppg_map_graph") == [f[0] for f in capi.MapGraph._fields_]
+    assert fields("ppg_extend_in") == [f[0] for f in capi.ExtendIn._fields_]
+    assert fields("ppg_extend_out") == [f[0] for f in capi.ExtendOut._fields_]
 
 
 def test_no_cpu_fallback():
