@@ -107,23 +107,31 @@ def make_workload(batch, seed0=0):
 
 
 def make_assoc_inputs(cam, recs, rows):
-    """Per-frame projections of the SAME resident map table: planted around frame 0's keypoints."""
+    """Per-frame projections of the SAME resident map: descriptors / projections planted around frame 0's keypoints,
+    map edges mirroring frame 0's point-pair graph (synth.extend_inputs)."""
     from ppg_slam_b200 import synth
     r0 = recs[0]
     kp = np.stack([r0["kp_x"], r0["kp_y"]], 1)
-    base = synth.association_inputs(17, r0["desc"], kp, rows, cam.width, cam.height, th=TH)
+    base = synth.extend_inputs(17, r0["desc"], kp, r0["edge_start"], r0["edge_end"], rows, cam.width, cam.height,
+                               th=TH, clean=True)
     per_frame = []
     for f, r in enumerate(recs):
         rs = np.random.RandomState(100 + f)
         uv = base["proj_uv"] + rs.uniform(-2, 2, base["proj_uv"].shape).astype(np.float32)
         per_frame.append((uv, base["view_cos"]))
-    return base["map_desc"], per_frame
+    return base, per_frame
+
+
+def upload_map(x, base):
+    x.upload_map(base["map_desc"])
+    x.upload_map_graph(base["candidate"], base["observed"], base["bad"], base["edge_off"], base["edge_other"],
+                       base["edge_ok"])
 
 
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_pass(n_frames, seed0, threads, rows=MAP_ROWS):
     """The reference path restated on the CPU (oracle): LibTorch-CPU fp32 networks, single-threaded C
-    post-processing and windowed association.  -> (seconds, frames)."""
+    post-processing and Matcher::ExtendMapMatches (window search + seed growing).  -> (seconds, frames)."""
     import torch
     from oracle import post_ref as O
     from oracle.net_ref import NetRef
@@ -143,12 +151,15 @@ def cpu_reference_pass(n_frames, seed0, threads, rows=MAP_ROWS):
         if not hasattr(cpu_reference_pass, "assoc"):
             from ppg_slam_b200 import synth as S
             kp = np.stack([rec["kp_x"], rec["kp_y"]], 1)
-            cpu_reference_pass.assoc = S.association_inputs(17, rec["desc"], kp, rows, cam.width, cam.height, th=TH)
+            cpu_reference_pass.assoc = S.extend_inputs(17, rec["desc"], kp, rec["edge_start"], rec["edge_end"], rows,
+                                                       cam.width, cam.height, th=TH, clean=True)
         a = cpu_reference_pass.assoc
         n = rec["n_kp"]
-        if n > 0:
-            O.search_all(cam, rec["kp_x"], rec["kp_y"], rec["desc"], np.ones(n, np.uint8), a["map_desc"],
-                         a["proj_uv"], a["view_cos"], TH, RATIO)
+        if n > 0:  # Matcher::ExtendMapMatches, whole function (window search + assignment + seed growing)
+            O.extend_map_matches(cam, a["map_desc"], a["candidate"], a["observed"], a["bad"], a["edge_off"],
+                                 a["edge_other"], a["edge_ok"], a["proj_uv"], a["view_cos"], a["tracked"],
+                                 rec["kp_x"], rec["kp_y"], rec["desc"], np.full(n, -1, np.int32), rec["edge_start"],
+                                 rec["edge_end"], rec["conn_off"], rec["conn_idx"], th=TH, ratio=RATIO)
     return time.perf_counter() - t0, n_frames
 
 
@@ -210,8 +221,9 @@ def run_b200(args, rank, local_rank, world):
     cam, frames = make_workload(B, seed0=rank * B)
     e = capi.Extractor(cam, device=local_rank, max_batch=B, max_map_points=max(args.map_rows, 1024))
     recs = e.run(frames)
-    map_desc, per_frame = make_assoc_inputs(cam, recs, args.map_rows)
-    e.upload_map(map_desc)
+    base, per_frame = make_assoc_inputs(cam, recs, args.map_rows)
+    upload_map(e, base)
+    core_only = args.assoc == "core"  # search core of ExtendMapMatches only (the round-1 step), for comparison
     empty = (np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros((0, 256), np.float32), np.zeros(0, np.uint8))
 
     proj_all = np.stack([uv for uv, _ in per_frame])
@@ -220,7 +232,10 @@ def run_b200(args, rank, local_rank, world):
     def device_step(x=None):
         x = x or e
         x.run_device(B)
-        x.assoc_run_batch(B)
+        if core_only:
+            x.assoc_run_batch(B)
+        else:
+            x.extend_run_batch(B)
 
     def e2e_step(x=None):
         x = x or e
@@ -228,8 +243,12 @@ def run_b200(args, rank, local_rank, world):
         if rc not in (0, capi.PPG_ERR_CAPACITY):
             raise capi.PpgError(rc, x.lib.ppg_last_error(x.h).decode())
         x.assoc_stage_batch(proj_all, vcos_all, TH, RATIO)
-        x.assoc_run_batch(B)
-        x.assoc_fetch_batch(B)
+        if core_only:
+            x.assoc_run_batch(B)
+            x.assoc_fetch_batch(B)
+        else:
+            x.extend_run_batch(B)
+            x.extend_fetch_batch(B)
 
     # ---- contexts: one per stream in flight.  A ctx is single-stream (like the reference's extractor object);
     # throughput callers keep several batches in flight on several ctxs of the same GPU, which also fills the SMs
@@ -237,7 +256,7 @@ def run_b200(args, rank, local_rank, world):
     ctxs = [e]
     for _ in range(max(1, args.dev_streams, args.e2e_streams) - 1):
         x = capi.Extractor(cam, device=local_rank, max_batch=B, max_map_points=max(args.map_rows, 1024))
-        x.upload_map(map_desc)
+        upload_map(x, base)
         ctxs.append(x)
     all_ctxs = list(ctxs)
     dev = ctxs[:max(1, args.dev_streams)]
@@ -323,16 +342,25 @@ def run_b200(args, rank, local_rank, world):
     recs = [capi._frame_to_dict(e._outs[i]) for i in range(B)]
     lay_small = 64 + sum(r["n_kp"] * 29 + r["n_edges"] * 20 + r["n_colines"] * 8 + (r["n_kp"] + 1) * 8 for r in recs)
     h2d = B * cam.width * cam.height + B * args.map_rows * 12
-    d2h = int(lay_small + sum(r["n_kp"] for r in recs) * 1024 + B * args.map_rows * 17)
+    if core_only:
+        d2h_assoc = B * args.map_rows * 17
+    else:  # F.mvpMapPoints, F.mvpMapEdges, tracked flags and the counters of every frame
+        d2h_assoc = B * (1024 * 4 + e.cfg.max_edges * 4 + args.map_rows + 32)
+    d2h = int(lay_small + sum(r["n_kp"] for r in recs) * 1024 + d2h_assoc)
 
     # ---- batch-1 latency (p50 ms/frame), host in -> host out
     lat = []
     for k in range(12):
         t0 = time.perf_counter()
         e.lib.ppg_extract(e.h, fptrs, fstrides, 1, e._outs)
-        e.assoc_stage(*empty, per_frame[0][0], per_frame[0][1], TH, RATIO)
-        e.assoc_run_frame(0)
-        e.assoc_fetch()
+        if core_only:
+            e.assoc_stage(*empty, per_frame[0][0], per_frame[0][1], TH, RATIO)
+            e.assoc_run_frame(0)
+            e.assoc_fetch()
+        else:
+            e.assoc_stage_batch(per_frame[0][0][None], per_frame[0][1][None], TH, RATIO)
+            e.extend_run_batch(1)
+            xres = e.extend_fetch_batch(1)
         lat.append((time.perf_counter() - t0) * 1e3)
     p50 = float(np.median(lat[2:]))
 
@@ -372,8 +400,11 @@ def run_b200(args, rank, local_rank, world):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
                 "data": "synthetic",
                 "config": {"workload": "%s %dx%d batch-%d synthetic frames per GPU: extract + point-pair graph "
-                                       "+ association of every frame vs %d resident map points" %
-                                       (CAMERA, cam.width, cam.height, B, args.map_rows),
+                                       "+ %s of every frame vs %d resident map points" %
+                                       (CAMERA, cam.width, cam.height, B,
+                                        "association search core" if core_only else
+                                        "Matcher::ExtendMapMatches (window search + assignment + seed growing)",
+                                        args.map_rows),
                            "batch_per_gpu": B, "map_rows": args.map_rows, "sharding": "frames (no collective)",
                            "device_contexts_in_flight": n_dev_ctx, "e2e_contexts_in_flight": len(ctxs),
                            "l2": "per-step working set ~3.4 GB of activations streams through the 126 MB L2 "
@@ -381,6 +412,11 @@ def run_b200(args, rank, local_rank, world):
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": d2h},
                 "latency": {"p50_ms_per_frame_batch1": p50},
+                "association": (None if core_only else
+                                {"frame0_keypoints": int(recs[0]["n_kp"]), "frame0_accepted": xres[0]["n_accepted"],
+                                 "frame0_grown_along_edges": xres[0]["n_grown"],
+                                 "frame0_matched_keypoints": int((xres[0]["kp_mp"] >= 0).sum()),
+                                 "frame0_window_rescans": xres[0]["n_rescans"]}),
                 "gpu_launches": int(launches),
                 "clocks": clk,
                 "roofline": roof,
@@ -407,6 +443,8 @@ def main():
     ap.add_argument("--map-rows", type=int, default=MAP_ROWS)
     ap.add_argument("--dev-streams", type=int, default=3, help="contexts in flight in the device-timed arm")
     ap.add_argument("--e2e-streams", type=int, default=4, help="contexts (host threads) in flight in the e2e arm")
+    ap.add_argument("--assoc", default="extend", choices=["extend", "core"],
+                    help="extend: the whole Matcher::ExtendMapMatches on the GPU (default); core: its search core only")
     ap.add_argument("--camera", default="EuRoC", choices=["EuRoC", "TUM-VI", "TUM-VI-1024", "UMA-VI"],
                     help="frame shape / calibration; EuRoC 752x480 is the benchmark configuration")
     args = ap.parse_args()

@@ -287,7 +287,7 @@ static int add_tc_layer(ppg_ctx* c, const Blob& blob, const char* name, const st
     return PPG_OK;
 }
 
-static void mark(ppg_ctx* c, const char* name) {
+void stage_mark(ppg_ctx* c, const char* name) {
     if (!c->profiling) return;
     if (c->n_ev >= (int)c->ev.size()) {
         cudaEvent_t e;
@@ -341,13 +341,13 @@ static int run_post(ppg_ctx* c, int n) {
         p.desc = c->desc_in;
     }
     PPG_CUDA(c, post_keypoints_launch(p, c->st, &c->launches));
-    mark(c, "post.keypoints(scan+nms+topk)");
+    stage_mark(c, "post.keypoints(scan+nms+topk)");
     PPG_CUDA(c, post_heat_launch(p, c->st, &c->launches));
-    mark(c, "post.heat(refine+remap)");
+    stage_mark(c, "post.heat(refine+remap)");
     PPG_CUDA(c, post_lines_launch(p, c->st, &c->launches));
-    mark(c, "post.lines(pairs+graph)");
+    stage_mark(c, "post.lines(pairs+graph)");
     PPG_CUDA(c, post_desc_launch(p, c->st, &c->launches));
-    mark(c, "post.descriptors");
+    stage_mark(c, "post.descriptors");
     return PPG_OK;
 }
 
@@ -764,7 +764,7 @@ int ppg_run(ppg_ctx* c, int n) {
 }
 
 static int enqueue_run(ppg_ctx* c, int n) {
-    mark(c, "start");
+    stage_mark(c, "start");
     // PPG_FUSE_CONV1A=1: conv1a is computed inside conv1b's kernel by producer warps (no 64-channel full-resolution
     // map in HBM).  Measured on B200: 1.87 ms vs 0.93 + conv1a for the two kernels -- four producer warps cannot keep
     // up with the tile rate and their mma.sync traffic competes with the tcgen05 MMAs -- so it is off by default.
@@ -772,7 +772,7 @@ static int enqueue_run(ppg_ctx* c, int n) {
     if (!fuse1a) {
         PPG_CUDA(c, conv1a_launch(c->gray, c->w1a, c->b1a, c->a1, n, c->H, c->W, c->st));
         c->launches++;
-        mark(c, "conv1a");
+        stage_mark(c, "conv1a");
     }
     // Small batches leave most of the GPU idle inside every kernel, so the branches of the network and of the
     // post-processing that do not depend on one another are forked onto side streams:
@@ -803,7 +803,7 @@ static int enqueue_run(ppg_ctx* c, int n) {
             PPG_CUDA(c, conv_tc_launch(l.L, n, c->num_sms, s));
         first = false;
         c->launches++;
-        mark(c, fuse1a && &l == &c->tc[0] ? "conv1a+conv1b" : l.name);
+        stage_mark(c, fuse1a && &l == &c->tc[0] ? "conv1a+conv1b" : l.name);
     }
     if (fork && !forked) {  // no head layer ran on a side stream (cannot happen with the shipped networks)
         PPG_CUDA(c, cudaEventRecord(c->ev_feat, c->st));
@@ -815,11 +815,11 @@ static int enqueue_run(ppg_ctx* c, int n) {
     cudaStream_t s_heat = fork ? c->st2 : c->st, s_desc = fork ? c->st3 : c->st;
     PPG_CUDA(c, edge_tail_launch(c->e2, c->we3, c->be3, c->we1, c->be1b, c->heat_raw, n, c->H / 2, c->W / 2, s_heat));
     c->launches++;
-    mark(c, "edge_tail");
+    stage_mark(c, "edge_tail");
     PPG_CUDA(c, post_keypoints_launch(p, c->st, &c->launches));
-    mark(c, "post.keypoints(scan+nms+topk)");
+    stage_mark(c, "post.keypoints(scan+nms+topk)");
     PPG_CUDA(c, post_heat_launch(p, s_heat, &c->launches));
-    mark(c, "post.heat(refine+remap)");
+    stage_mark(c, "post.heat(refine+remap)");
     if (fork) {
         PPG_CUDA(c, cudaEventRecord(c->ev_heat, c->st2));
         PPG_CUDA(c, cudaEventRecord(c->ev_kp, c->st));
@@ -827,9 +827,9 @@ static int enqueue_run(ppg_ctx* c, int n) {
         PPG_CUDA(c, cudaStreamWaitEvent(c->st3, c->ev_kp, 0));    // the sampling needs keypoints + descriptor map
     }
     PPG_CUDA(c, post_lines_launch(p, c->st, &c->launches));
-    mark(c, "post.lines(pairs+graph)");
+    stage_mark(c, "post.lines(pairs+graph)");
     PPG_CUDA(c, post_desc_launch(p, s_desc, &c->launches));
-    mark(c, "post.descriptors");
+    stage_mark(c, "post.descriptors");
     if (fork) {
         PPG_CUDA(c, cudaEventRecord(c->ev_desc, c->st3));
         PPG_CUDA(c, cudaStreamWaitEvent(c->st, c->ev_desc, 0));   // join: everything is ordered on st again
@@ -901,7 +901,7 @@ int ppg_extract_from_maps(ppg_ctx* c, const float* prob, const float* heat, cons
     c->maps_from_caller = true;
     c->last_batch = n;
     c->n_ev = 0;
-    mark(c, "start");
+    stage_mark(c, "start");
     int rc = run_post(c, n);
     if (rc != PPG_OK) return rc;
     return ppg_download(c, n, out);

@@ -682,6 +682,7 @@ int assoc_prep(ppg_ctx* c, const FrameSrc& src, int frames) {
                                                                           s->max_rows, s->th, s->mode, g, s->rowp);
     c->launches += 2;
     PPG_CUDA(c, cudaGetLastError());
+    stage_mark(c, "assoc.prep");
     return PPG_OK;
 }
 
@@ -713,6 +714,7 @@ int run_assoc(ppg_ctx* c, const FrameSrc& src, int frames, int force_exact) {
         const int grid = total < c->num_sms ? total : c->num_sms;
         assoc_gemm_kernel<<<grid, A_THREADS, gemm_smem(s), c->st>>>(s->mapA, s->mapB, gp);
         c->launches++;
+        stage_mark(c, "assoc.gemm(top4)");
     }
     RescoreParams rp;
     rp.rows = rows;
@@ -740,6 +742,7 @@ int run_assoc(ppg_ctx* c, const FrameSrc& src, int frames, int force_exact) {
     rp.fallback = s->fallback;
     assoc_rescore_kernel<<<dim3((rows + 7) / 8, frames), 256, 0, c->st>>>(rp);
     c->launches++;
+    stage_mark(c, "assoc.rescore");
     PPG_CUDA(c, cudaGetLastError());
     return PPG_OK;
 }

@@ -90,6 +90,8 @@ namespace ppg {
 int set_err(const ppg_ctx* c, int code, const std::string& msg);
 int cuda_fail(const ppg_ctx* c, cudaError_t e, const char* what);
 void assoc_destroy(ppg_ctx* c);
+// profiling runs: records a CUDA event named after the stage that just ended on the ctx stream (api.cu)
+void stage_mark(ppg_ctx* c, const char* name);
 }  // namespace ppg
 
 #define PPG_CUDA(c, call)                                               \

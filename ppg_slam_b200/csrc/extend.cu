@@ -176,8 +176,6 @@ struct WalkShared {
     float w[X_WCAP];     // weight matrix of the current seed, [lx position][key edge]
     int po[X_LCAP];      // other map point of the valid map edges of pMP (lx)
     int lxi[X_LCAP];     // their position in getEdges()
-    int ko[X_LCAP];      // other keypoint of every key edge of the seed
-    int ke[X_LCAP];      // the key edge ids
     int clx[X_LCAP], cly[X_LCAP];  // lx / ly while the greedy assignment erases from them
     int queue[X_LCAP + 2];         // matchSeed: every push marks one more endpoint of pMP tracked
     uint16_t cl[1024];   // window of a rescanned row
@@ -185,7 +183,7 @@ struct WalkShared {
     uint32_t t2o[X_WARPS][2];
     int t2i[X_WARPS][2];
     int wfirst[X_WARPS];
-    int ev[4];           // row, act, best idx
+    int ev[8];           // row, act, best idx, first map edge, map edges
     int cln, nlx, qn;
     int res[XR_WORDS];
 };
@@ -196,47 +194,72 @@ __device__ __forceinline__ void trk_set(uint32_t* trk, int r) { trk[r >> 5] |= 1
 __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkParams p) {
     extern __shared__ __align__(16) uint8_t xsm[];
     WalkShared& S = *reinterpret_cast<WalkShared*>(xsm);
+    const int tw = (p.P + 31) >> 5;
     uint32_t* trk = reinterpret_cast<uint32_t*>(xsm + ((sizeof(WalkShared) + 15) & ~size_t(15)));
+    uint32_t* obs = trk + tw;   // Observations() > 0 of every table row
+    uint32_t* badb = obs + tw;  // isBad()
+    uint16_t* s_coff = reinterpret_cast<uint16_t*>(badb + tw);  // [ncap + 1] CSR of mvConnected
+    uint16_t* s_cko = s_coff + p.ncap + 2;                      // [2 ecap] other keypoint of every CSR entry
+    uint16_t* s_cke = s_cko + 2 * p.ecap;                       // [2 ecap] its key edge
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = min(p.src.n_of(f), p.ncap);
     const int ne = min(p.gsrc.ne_of(f), p.ecap);
     const float* fdesc = p.src.desc_of(f);
-    const int* es = p.gsrc.es_of(f);
-    const int* ee = p.gsrc.ee_of(f);
-    const int* coff = p.gsrc.coff_of(f);
-    const int* cidx = p.gsrc.cidx_of(f);
     int* kedge_me = p.kedge_me + (size_t)f * p.ecap;
     uint8_t* tracked_g = p.tracked + (size_t)f * p.max_rows;
     int* kpmp_g = p.kp_mp + (size_t)f * p.ncap;
 
     // ---- initial state
+    for (int w = tid; w < tw; w += X_THREADS) {
+        uint32_t tb = 0, ob = 0, bb = 0;
+        for (int b = 0; b < 32; b++) {
+            const int r = w * 32 + b;
+            if (r < p.P) {
+                if (p.has_state && tracked_g[r]) tb |= 1u << b;
+                if (p.observed[r]) ob |= 1u << b;
+                if (p.bad[r]) bb |= 1u << b;
+            }
+        }
+        trk[w] = tb;
+        obs[w] = ob;
+        badb[w] = bb;
+    }
+    {   // the frame's point-pair graph: every mvConnected entry with KeyEdge::theOtherPid resolved
+        const int* es = p.gsrc.es_of(f);
+        const int* ee = p.gsrc.ee_of(f);
+        const int* coff = p.gsrc.coff_of(f);
+        const int* cidx = p.gsrc.cidx_of(f);
+        for (int i = tid; i <= n && n > 0; i += X_THREADS) s_coff[i] = (uint16_t)min(coff[i], 2 * p.ecap);
+        for (int i = tid; i < n; i += X_THREADS) {
+            const int k0 = coff[i], k1 = min(coff[i + 1], 2 * p.ecap);
+            for (int k = k0; k < k1; k++) {
+                const int e = cidx[k];
+                const int s0 = es[e], e0 = ee[e];
+                s_cko[k] = (uint16_t)(s0 == i ? e0 : s0);
+                s_cke[k] = (uint16_t)e;
+            }
+        }
+    }
+    if (tid < XR_WORDS) S.res[tid] = 0;
+    __syncthreads();
     for (int i = tid; i < p.ncap; i += X_THREADS) {
         int r = -1;
         if (p.has_state && i < n) r = kpmp_g[i];
         S.kpmp[i] = r;
-        S.occ[i] = r >= 0 ? (p.observed[r] != 0) : (r == -2);
+        S.occ[i] = r >= 0 ? trk_get(obs, r) : (r == -2);
     }
-    const int tw = (p.P + 31) >> 5;
-    for (int w = tid; w < tw; w += X_THREADS) {
-        uint32_t bits = 0;
-        if (p.has_state)
-            for (int b = 0; b < 32; b++) {
-                const int r = w * 32 + b;
-                if (r < p.P && tracked_g[r]) bits |= 1u << b;
-            }
-        trk[w] = bits;
-    }
-    if (tid < XR_WORDS) S.res[tid] = 0;
     __syncthreads();
 
     for (int base = 0; base < p.nc; base += X_THREADS) {
         // ---- static part of the 256 rows of this chunk: the stored window lists
         const int pos = base + tid;
-        int row = -1, cnt = 0;
+        int row = -1, cnt = 0, my_me0 = 0, my_nme = 0;
         uint16_t idx[X_LIST];
         float d[X_LIST];
         if (pos < p.nc) {
             row = p.order[pos];
+            my_me0 = p.edge_off[row];
+            my_nme = p.edge_off[row + 1] - my_me0;
             const size_t ol = (size_t)f * p.max_rows + pos;
             cnt = p.l_cnt[ol];
             const uint4* pi = reinterpret_cast<const uint4*>(p.l_idx + ol * X_LIST);
@@ -294,6 +317,8 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                 S.ev[0] = row;
                 S.ev[1] = act;
                 S.ev[2] = bidx;
+                S.ev[3] = my_me0;
+                S.ev[4] = my_nme;
             }
             __syncthreads();
             const int erow = S.ev[0];
@@ -342,11 +367,11 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
             if (S.ev[1] == 1) {
                 // ---- accepted: F.mvpMapPoints[bestIdx] = pMP (:279-281), then seed growing (:287-377)
                 const int bestIdx = S.ev[2];
-                const int me0 = p.edge_off[erow], nme = p.edge_off[erow + 1] - me0;
+                const int me0 = S.ev[3], nme = S.ev[4];
                 const bool deg_ok = nme <= X_LCAP;
                 if (tid == 0) {
                     S.kpmp[bestIdx] = erow;
-                    S.occ[bestIdx] = p.observed[erow] != 0;
+                    S.occ[bestIdx] = trk_get(obs, erow);
                     trk_set(trk, erow);
                     S.res[XR_NMATCHES] += 2;  // :281 and :378
                     S.res[XR_ACCEPTED]++;
@@ -355,123 +380,118 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                     S.nlx = 0;
                     if (!deg_ok) S.res[XR_STATUS] |= PPG_EXTEND_OVF;
                 }
-                // lx: the valid map edges of pMP (:312-318); mapEdge_set is pMP's for every seed of the event
-                if (warp == 0 && deg_ok) {
-                    int nlx = 0;
-                    for (int i0 = 0; i0 < nme; i0 += 32) {
-                        const int i = i0 + lane;
-                        int other = -1;
-                        bool ok = false;
-                        if (i < nme) {
-                            other = p.edge_other[me0 + i];
-                            ok = p.edge_ok[me0 + i] != 0 && other >= 0;
-                        }
-                        const unsigned mk = __ballot_sync(AFULL, ok);
-                        if (ok) {
-                            const int k = nlx + __popc(mk & ((1u << lane) - 1u));
-                            S.po[k] = other;
-                            S.lxi[k] = i;
-                        }
-                        nlx += __popc(mk);
-                    }
-                    if (lane == 0) S.nlx = nlx;
-                }
-                __syncthreads();
-                const int nlx0 = S.nlx;
-                int qh = 0;
-                while (deg_ok && nme > 0) {
-                    if (qh >= S.qn) break;
-                    const int keyID = S.queue[qh++];
-                    const int ke0 = coff[keyID], nke = coff[keyID + 1] - ke0;
-                    if (nke == 0) continue;  // :300-301
-                    if (nke > X_LCAP || nlx0 * nke > X_WCAP) {
-                        if (tid == 0) S.res[XR_STATUS] |= PPG_EXTEND_OVF;
-                        continue;
-                    }
-                    if (nlx0 == 0) continue;  // lx empty: the assignment loop does not run (:342)
-                    for (int j = tid; j < nke; j += X_THREADS) {
-                        const int e = cidx[ke0 + j];
-                        const int s0 = es[e], e0 = ee[e];
-                        S.ke[j] = e;
-                        S.ko[j] = s0 == keyID ? e0 : s0;  // KeyEdge::theOtherPid
-                        S.cly[j] = j;
-                    }
-                    for (int i = tid; i < nlx0; i += X_THREADS) S.clx[i] = i;
-                    __syncthreads();
-                    // weight matrix (:324-340), one warp per entry
-                    for (int q = warp; q < nlx0 * nke; q += X_WARPS) {
-                        const int i = q / nke, j = q - i * nke;
-                        const int po = S.po[i], ko = S.ko[j];
-                        float w;
-                        if (po == S.kpmp[ko]) {
-                            w = -1.f;
-                        } else {
-                            float a[8];
-#pragma unroll
-                            for (int k = 0; k < 8; k++) a[k] = p.map_f32[(size_t)po * 256 + lane + 32 * k];
-                            w = exact_distance(a, fdesc + (size_t)ko * 256, lane);
-                        }
-                        if (lane == 0) S.w[q] = w;
-                    }
-                    __syncthreads();
-                    // greedy minimum-weight assignment (:342-374), one warp
+                // without map edges every seed is skipped at :300-301
+                if (deg_ok && nme > 0) {
+                    // lx: the valid map edges of pMP (:312-318); mapEdge_set is pMP's for every seed of the event
                     if (warp == 0) {
-                        int nlx = nlx0, nly = nke;
-                        while (nlx > 0 && nly > 0) {
-                            float bw = 1e6f;
-                            int bq = 0x7fffffff;
-                            for (int q = lane; q < nlx * nly; q += 32) {
-                                const int a = q / nly, b = q - a * nly;
-                                const float w = S.w[S.clx[a] * nke + S.cly[b]];
-                                if (w < bw) {  // strict <: the first minimum in (a, b) order wins
-                                    bw = w;
-                                    bq = q;
-                                }
+                        int nlx = 0;
+                        for (int i0 = 0; i0 < nme; i0 += 32) {
+                            const int i = i0 + lane;
+                            int other = -1;
+                            bool ok = false;
+                            if (i < nme) {
+                                other = p.edge_other[me0 + i];
+                                ok = p.edge_ok[me0 + i] != 0 && other >= 0;
                             }
-#pragma unroll
-                            for (int mm = 16; mm >= 1; mm >>= 1) {
-                                const float ow = __shfl_xor_sync(AFULL, bw, mm);
-                                const int oq = __shfl_xor_sync(AFULL, bq, mm);
-                                if (ow < bw || (ow == bw && oq < bq)) {
-                                    bw = ow;
-                                    bq = oq;
-                                }
+                            const unsigned mk = __ballot_sync(AFULL, ok);
+                            if (ok) {
+                                const int k = nlx + __popc(mk & ((1u << lane) - 1u));
+                                S.po[k] = other;
+                                S.lxi[k] = i;
                             }
-                            if (bq == 0x7fffffff || bw > p.th_high) break;  // :357-358
-                            const int a = bq / nly, b = bq - a * nly;
-                            const int mi = S.clx[a], kj = S.cly[b];
-                            // lx.erase / ly.erase keep the order of the rest
-                            int tx[X_LCAP / 32], ty[X_LCAP / 32];
-#pragma unroll
-                            for (int k = 0; k < X_LCAP / 32; k++) {
-                                const int t = lane + 32 * k;
-                                tx[k] = (t >= a && t + 1 < nlx) ? S.clx[t + 1] : (t < nlx ? S.clx[t] : 0);
-                                ty[k] = (t >= b && t + 1 < nly) ? S.cly[t + 1] : (t < nly ? S.cly[t] : 0);
-                            }
-                            __syncwarp();
-#pragma unroll
-                            for (int k = 0; k < X_LCAP / 32; k++) {
-                                const int t = lane + 32 * k;
-                                if (t < nlx) S.clx[t] = tx[k];
-                                if (t < nly) S.cly[t] = ty[k];
-                            }
-                            nlx--;
-                            nly--;
-                            if (lane == 0) {
-                                const int po = S.po[mi], ko = S.ko[kj];
-                                if (!(p.bad[po] || trk_get(trk, po))) {  // :364-365
-                                    S.kpmp[ko] = po;                     // :366
-                                    S.occ[ko] = p.observed[po] != 0;
-                                    kedge_me[S.ke[kj]] = me0 + S.lxi[mi];
-                                    trk_set(trk, po);
-                                    S.res[XR_GROWN]++;
-                                    if (S.qn < X_LCAP + 2) S.queue[S.qn++] = ko;
-                                }
-                            }
-                            __syncwarp();
+                            nlx += __popc(mk);
                         }
+                        if (lane == 0) S.nlx = nlx;
                     }
                     __syncthreads();
+                    const int nlx0 = S.nlx;
+                    int qh = 0;
+                    while (nlx0 > 0) {  // lx empty: the assignment loop never runs (:342)
+                        if (qh >= S.qn) break;
+                        const int keyID = S.queue[qh++];
+                        const int ke0 = s_coff[keyID], nke = s_coff[keyID + 1] - ke0;
+                        if (nke == 0) continue;  // :300-301
+                        if (nke > X_LCAP || nlx0 * nke > X_WCAP) {
+                            if (tid == 0) S.res[XR_STATUS] |= PPG_EXTEND_OVF;
+                            continue;
+                        }
+                        // weight matrix (:324-340), one warp per entry
+                        for (int q = warp; q < nlx0 * nke; q += X_WARPS) {
+                            const int i = q / nke, j = q - i * nke;
+                            const int po = S.po[i], ko = s_cko[ke0 + j];
+                            float w;
+                            if (po == S.kpmp[ko]) {
+                                w = -1.f;
+                            } else {
+                                float a[8];
+#pragma unroll
+                                for (int k = 0; k < 8; k++) a[k] = p.map_f32[(size_t)po * 256 + lane + 32 * k];
+                                w = exact_distance(a, fdesc + (size_t)ko * 256, lane);
+                            }
+                            if (lane == 0) S.w[q] = w;
+                        }
+                        for (int j = tid; j < nke; j += X_THREADS) S.cly[j] = j;
+                        for (int i = tid; i < nlx0; i += X_THREADS) S.clx[i] = i;
+                        __syncthreads();
+                        // greedy minimum-weight assignment (:342-374), one warp
+                        if (warp == 0) {
+                            int nlx = nlx0, nly = nke;
+                            while (nlx > 0 && nly > 0) {
+                                float bw = 1e6f;
+                                int bq = 0x7fffffff;
+                                for (int q = lane; q < nlx * nly; q += 32) {
+                                    const int a = q / nly, b = q - a * nly;
+                                    const float w = S.w[S.clx[a] * nke + S.cly[b]];
+                                    if (w < bw) {  // strict <: the first minimum in (a, b) order wins
+                                        bw = w;
+                                        bq = q;
+                                    }
+                                }
+#pragma unroll
+                                for (int mm = 16; mm >= 1; mm >>= 1) {
+                                    const float ow = __shfl_xor_sync(AFULL, bw, mm);
+                                    const int oq = __shfl_xor_sync(AFULL, bq, mm);
+                                    if (ow < bw || (ow == bw && oq < bq)) {
+                                        bw = ow;
+                                        bq = oq;
+                                    }
+                                }
+                                if (bq == 0x7fffffff || bw > p.th_high) break;  // :357-358
+                                const int a = bq / nly, b = bq - a * nly;
+                                const int mi = S.clx[a], kj = S.cly[b];
+                                // lx.erase / ly.erase keep the order of the rest
+                                int tx[X_LCAP / 32], ty[X_LCAP / 32];
+#pragma unroll
+                                for (int k = 0; k < X_LCAP / 32; k++) {
+                                    const int t = lane + 32 * k;
+                                    tx[k] = (t >= a && t + 1 < nlx) ? S.clx[t + 1] : (t < nlx ? S.clx[t] : 0);
+                                    ty[k] = (t >= b && t + 1 < nly) ? S.cly[t + 1] : (t < nly ? S.cly[t] : 0);
+                                }
+                                __syncwarp();
+#pragma unroll
+                                for (int k = 0; k < X_LCAP / 32; k++) {
+                                    const int t = lane + 32 * k;
+                                    if (t < nlx) S.clx[t] = tx[k];
+                                    if (t < nly) S.cly[t] = ty[k];
+                                }
+                                nlx--;
+                                nly--;
+                                if (lane == 0) {
+                                    const int po = S.po[mi], ko = s_cko[ke0 + kj];
+                                    if (!(trk_get(badb, po) || trk_get(trk, po))) {  // :364-365
+                                        S.kpmp[ko] = po;                             // :366
+                                        S.occ[ko] = trk_get(obs, po);
+                                        kedge_me[s_cke[ke0 + kj]] = me0 + S.lxi[mi];
+                                        trk_set(trk, po);
+                                        S.res[XR_GROWN]++;
+                                        if (S.qn < X_LCAP + 2) S.queue[S.qn++] = ko;
+                                    }
+                                }
+                                __syncwarp();
+                            }
+                        }
+                        __syncthreads();
+                    }
                 }
             }
             cursor = first + 1;
@@ -490,7 +510,10 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
     if (tid < XR_WORDS) p.result[f * XR_WORDS + tid] = S.res[tid];
 }
 
-size_t walk_smem(int P) { return ((sizeof(WalkShared) + 15) & ~size_t(15)) + (size_t)((P + 31) / 32) * 4 + 16; }
+size_t walk_smem(int P, int ncap, int ecap) {
+    return ((sizeof(WalkShared) + 15) & ~size_t(15)) + (size_t)((P + 31) / 32) * 12 + (size_t)(ncap + 2) * 2 +
+           (size_t)ecap * 8 + 16;
+}
 
 int ensure_extend(ppg_ctx* c) {
     int rc = assoc_ensure_state(c);
@@ -502,6 +525,8 @@ int ensure_extend(ppg_ctx* c) {
     s->ext = x;
     const size_t R = s->max_rows, N = s->ncap, B = s->bcap;
     x->ecap = c->post.lay.max_edges;
+    if (x->ecap > 32767 || walk_smem(s->max_rows, s->ncap, x->ecap) > 200 * 1024)
+        return set_err(c, PPG_ERR_ARG, "extend: max_edges / max_map_points too large for the walk kernel's shared memory");
     const size_t E = x->ecap;
     PPG_CUDA(c, dalloc(&x->observed, R));
     PPG_CUDA(c, dalloc(&x->bad, R));
@@ -578,6 +603,7 @@ int run_extend(ppg_ctx* c, const FrameSrc& src, const FrameGraphSrc& gsrc, int f
         lp.l_cnt = x->l_cnt;
         extend_lists_kernel<<<dim3((x->nc + 7) / 8, frames), 256, 0, c->st>>>(lp);
         c->launches++;
+        stage_mark(c, "extend.lists");
     }
     WalkParams wp;
     wp.nc = x->nc;
@@ -607,8 +633,9 @@ int run_extend(ppg_ctx* c, const FrameSrc& src, const FrameGraphSrc& gsrc, int f
     wp.ratio = s->ratio;
     wp.th_high = c->cfg.th_high;
     wp.has_state = has_state;
-    extend_walk_kernel<<<frames, X_THREADS, walk_smem(x->P), c->st>>>(wp);
+    extend_walk_kernel<<<frames, X_THREADS, walk_smem(x->P, s->ncap, x->ecap), c->st>>>(wp);
     c->launches++;
+    stage_mark(c, "extend.walk");
     PPG_CUDA(c, cudaGetLastError());
     return PPG_OK;
 }
