@@ -35,7 +35,9 @@
 
 namespace ppg {
 
-constexpr int X_LIST = 16;                           // window candidates stored per row
+constexpr int X_LIST = 32;                           // window candidates stored per row
+constexpr int X_LI_STRIDE = 258, X_LD_STRIDE = 257;  // entry-major list tiles in shared memory, conflict-free
+constexpr int X_PRE = 4;                             // map edges of a row preloaded with its chunk
 constexpr int X_LCAP = PPG_EXTEND_MAX_DEGREE;        // map edges per map point / key edges per keypoint
 constexpr int X_WCAP = PPG_EXTEND_MAX_WEIGHTS;       // weight-matrix entries per seed
 constexpr int X_THREADS = 256, X_WARPS = X_THREADS / 32;
@@ -93,58 +95,103 @@ struct ListParams {
     uint8_t* l_cnt;
 };
 
-__global__ void __launch_bounds__(256) extend_lists_kernel(const ListParams p) {
-    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    const int f = blockIdx.y;
-    if (q >= p.nc) return;
-    const int row = p.order[q];
-    const size_t o = (size_t)f * p.max_rows + row, ol = (size_t)f * p.max_rows + q;
-    const int n = min(p.src.n_of(f), p.ncap);
-    const RowParam rp = p.rowp[o];
-    // the sorted list lives across the warp: lane k holds its k-th entry (empty = +inf)
-    float ld = INFINITY;
-    uint32_t lo = 0xffffffffu;
-    int li = -1;
-    int cnt = 0;
-    if (rp.cells != 0xffffffffu) {
-        float a[8];
+// DescriptorDistance with both rows already in registers (same operation order as exact_distance).
+__device__ __forceinline__ float exact_distance_rr(const float (&av)[8], const float (&bv)[8]) {
+    float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; k++) a[k] = p.map_f32[(size_t)row * 256 + lane + 32 * k];
-        const float* fdesc = p.src.desc_of(f);
+    for (int k = 0; k < 8; k++) {
+        const float d = av[k] - bv[k];
+        s = s + d * d;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) s = s + __shfl_xor_sync(AFULL, s, m);
+    return sqrtf(s);
+}
+
+constexpr int XL_ROWS = 64;  // rows per CTA (8 per warp): the frame's keypoint table is staged once for all of them
+
+// grid (ceil(nc / XL_ROWS), frames).  The window scan reads the keypoint table from shared memory; the hits of a row
+// are collected first and their descriptor rows are then fetched four at a time (the first version took one
+// dependent round of global loads per 32 keypoints scanned and one per hit: 0.39 ms per 32 frames x 8192 rows).
+__global__ void __launch_bounds__(256) extend_lists_kernel(const ListParams p) {
+    __shared__ float s_kx[1024], s_ky[1024];
+    __shared__ uint32_t s_info[1024], s_ord[1024];
+    __shared__ uint16_t s_hit[8][1024];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, f = blockIdx.y;
+    const int n = min(p.src.n_of(f), p.ncap);
+    {
         const float* kx = p.src.kx_of(f);
         const float* ky = p.src.ky_of(f);
         const uint32_t* kinfo = p.kinfo + (size_t)f * p.ncap;
         const uint32_t* korder = p.korder + (size_t)f * p.ncap;
-        for (int c0 = 0; c0 < n; c0 += 32) {
-            const int c = c0 + lane;
-            bool in = false;
-            if (c < n) in = in_window(rp, kinfo[c], kx[c], ky[c], 0.0);
-            unsigned mask = __ballot_sync(AFULL, in);
-            while (mask) {
-                const int cc = c0 + __ffs(mask) - 1;
-                mask &= mask - 1;
-                const float d = exact_distance(a, fdesc + (size_t)cc * 256, lane);
-                const uint32_t ord = korder[cc];
-                // entries that stay in front of the new one form a prefix of the lanes
-                const bool before = ld < d || (ld == d && lo < ord);
-                const int pos = __popc(__ballot_sync(AFULL, before));
-                const float ud = __shfl_up_sync(AFULL, ld, 1);
-                const uint32_t uo = __shfl_up_sync(AFULL, lo, 1);
-                const int ui = __shfl_up_sync(AFULL, li, 1);
-                if (lane == pos) {
-                    ld = d; lo = ord; li = cc;
-                } else if (lane > pos) {
-                    ld = ud; lo = uo; li = ui;
-                }
-                cnt++;
-            }
+        for (int i = threadIdx.x; i < n; i += 256) {
+            s_kx[i] = kx[i];
+            s_ky[i] = ky[i];
+            s_info[i] = kinfo[i];
+            s_ord[i] = korder[i];
         }
     }
-    if (lane < X_LIST) {
-        p.l_idx[ol * X_LIST + lane] = li < 0 ? (uint16_t)0xffff : (uint16_t)li;
-        p.l_d[ol * X_LIST + lane] = ld;
+    __syncthreads();
+    const float* fdesc = p.src.desc_of(f);
+    for (int r = 0; r < XL_ROWS / 8; r++) {
+        const int q = blockIdx.x * XL_ROWS + r * 8 + warp;
+        if (q >= p.nc) break;
+        const int row = p.order[q];
+        const size_t o = (size_t)f * p.max_rows + row, ol = (size_t)f * p.max_rows + q;
+        const RowParam rp = p.rowp[o];
+        // the sorted list lives across the warp: lane k holds its k-th entry (empty = +inf)
+        float ld = INFINITY;
+        uint32_t lo = 0xffffffffu;
+        int li = -1;
+        int nh = 0;
+        if (rp.cells != 0xffffffffu) {
+            float a[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) a[k] = p.map_f32[(size_t)row * 256 + lane + 32 * k];
+            for (int c0 = 0; c0 < n; c0 += 32) {
+                const int c = c0 + lane;
+                bool in = false;
+                if (c < n) in = in_window(rp, s_info[c], s_kx[c], s_ky[c], 0.0);
+                const unsigned mask = __ballot_sync(AFULL, in);
+                if (in) s_hit[warp][nh + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)c;
+                nh += __popc(mask);
+            }
+            __syncwarp();
+            for (int h0 = 0; h0 < nh; h0 += 4) {
+                int cc[4];
+                float b[4][8];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    cc[u] = s_hit[warp][min(h0 + u, nh - 1)];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) b[u][k] = fdesc[(size_t)cc[u] * 256 + lane + 32 * k];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (h0 + u >= nh) break;  // warp-uniform
+                    const float d = exact_distance_rr(a, b[u]);
+                    const uint32_t ord = s_ord[cc[u]];
+                    // entries that stay in front of the new one form a prefix of the lanes
+                    const bool before = ld < d || (ld == d && lo < ord);
+                    const int pos = __popc(__ballot_sync(AFULL, before));
+                    const float ud = __shfl_up_sync(AFULL, ld, 1);
+                    const uint32_t uo = __shfl_up_sync(AFULL, lo, 1);
+                    const int ui = __shfl_up_sync(AFULL, li, 1);
+                    if (lane == pos) {
+                        ld = d; lo = ord; li = cc[u];
+                    } else if (lane > pos) {
+                        ld = ud; lo = uo; li = ui;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        {
+            p.l_idx[ol * X_LIST + lane] = li < 0 ? (uint16_t)0xffff : (uint16_t)li;
+            p.l_d[ol * X_LIST + lane] = ld;
+        }
+        if (lane == 0) p.l_cnt[ol] = (uint8_t)min(nh, 255);
     }
-    if (lane == 0) p.l_cnt[ol] = (uint8_t)min(cnt, 255);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -171,6 +218,8 @@ struct WalkParams {
 };
 
 struct WalkShared {
+    uint16_t lidx[X_LIST * X_LI_STRIDE];  // window lists of the 256 rows of the chunk: keypoint ...
+    float ld[X_LIST * X_LD_STRIDE];       // ... and exact distance, [entry][row]
     int kpmp[1024];      // F.mvpMapPoints as table rows
     uint8_t occ[1024];   // mvpMapPoints[i] && Observations() > 0   (Matcher.cpp:253)
     float w[X_WCAP];     // weight matrix of the current seed, [lx position][key edge]
@@ -251,53 +300,54 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
     __syncthreads();
 
     for (int base = 0; base < p.nc; base += X_THREADS) {
-        // ---- static part of the 256 rows of this chunk: the stored window lists
+        // ---- static part of the 256 rows of this chunk: the stored window lists (shared memory, entry-major so
+        // that a thread walking its own list is conflict-free) and the first map edges of each row (registers)
+        for (int e = tid; e < X_THREADS * X_LIST; e += X_THREADS) {
+            const int r = e / X_LIST, k = e - r * X_LIST;
+            if (base + r < p.nc) {
+                const size_t g = ((size_t)f * p.max_rows + base + r) * X_LIST + k;
+                S.lidx[k * X_LI_STRIDE + r] = p.l_idx[g];
+                S.ld[k * X_LD_STRIDE + r] = p.l_d[g];
+            }
+        }
         const int pos = base + tid;
         int row = -1, cnt = 0, my_me0 = 0, my_nme = 0;
-        uint16_t idx[X_LIST];
-        float d[X_LIST];
+        int pe[X_PRE];  // theOtherPt row of my first map edges, -1 when the edge is not usable (:312-318)
+#pragma unroll
+        for (int k = 0; k < X_PRE; k++) pe[k] = -1;
         if (pos < p.nc) {
             row = p.order[pos];
             my_me0 = p.edge_off[row];
             my_nme = p.edge_off[row + 1] - my_me0;
-            const size_t ol = (size_t)f * p.max_rows + pos;
-            cnt = p.l_cnt[ol];
-            const uint4* pi = reinterpret_cast<const uint4*>(p.l_idx + ol * X_LIST);
-            const uint4 i0 = pi[0], i1 = pi[1];
-            const uint32_t iw[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+            cnt = p.l_cnt[(size_t)f * p.max_rows + pos];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                idx[2 * k] = (uint16_t)(iw[k] & 0xffff);
-                idx[2 * k + 1] = (uint16_t)(iw[k] >> 16);
-            }
-            const float4* pd = reinterpret_cast<const float4*>(p.l_d + ol * X_LIST);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float4 v = pd[k];
-                d[4 * k] = v.x; d[4 * k + 1] = v.y; d[4 * k + 2] = v.z; d[4 * k + 3] = v.w;
-            }
+            for (int k = 0; k < X_PRE; k++)
+                if (k < my_nme) pe[k] = p.edge_ok[my_me0 + k] ? p.edge_other[my_me0 + k] : -1;
         }
         const int stored = cnt < X_LIST ? cnt : X_LIST;
         int cursor = 0;
+        __syncthreads();
         while (true) {
             // ---- what would the reference do with my row in the current state?  (Matcher.cpp:229-277)
             int act = 0, bidx = -1;
             if (row >= 0 && tid >= cursor && cnt > 0 && !trk_get(trk, row)) {
                 float b1 = 1e6f, b2 = 1e6f;
                 int nfree = 0;
-#pragma unroll
-                for (int k = 0; k < X_LIST; k++) {
-                    if (k < stored && !S.occ[idx[k]]) {
+                for (int k = 0; k < stored; k++) {
+                    const int ki = S.lidx[k * X_LI_STRIDE + tid];
+                    if (!S.occ[ki]) {
                         if (nfree == 0) {
-                            b1 = d[k];
-                            bidx = idx[k];
-                        } else if (nfree == 1) {
-                            b2 = d[k];
+                            b1 = S.ld[k * X_LD_STRIDE + tid];
+                            bidx = ki;
+                            nfree = 1;
+                        } else {
+                            b2 = S.ld[k * X_LD_STRIDE + tid];
+                            nfree = 2;
+                            break;
                         }
-                        nfree++;
                     }
                 }
-                if (nfree >= 2 || (cnt <= X_LIST && nfree == 1))
+                if (nfree == 2 || (cnt <= X_LIST && nfree == 1))
                     act = !(b1 > p.th_high && b1 > p.ratio * b2) ? 1 : 0;  // :276
                 else if (cnt > X_LIST)
                     act = 2;  // the list was cut and fewer than two free entries are left of it: rescan the window
@@ -310,15 +360,38 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
 #pragma unroll
             for (int w = 0; w < X_WARPS; w++) first = min(first, S.wfirst[w]);
             if (first == X_NOEVENT) {
-                __syncthreads();
+                __syncthreads();  // the next chunk overwrites the lists
                 break;
             }
             if (tid == first) {
+                // every thread is past its evaluation (barrier above): the state may change now
                 S.ev[0] = row;
                 S.ev[1] = act;
                 S.ev[2] = bidx;
                 S.ev[3] = my_me0;
                 S.ev[4] = my_nme;
+                // lx: the valid map edges of pMP (:312-318); mapEdge_set is pMP's for every seed of the event
+                int nlx = -1;
+                if (my_nme <= X_PRE) {
+                    nlx = 0;
+#pragma unroll
+                    for (int k = 0; k < X_PRE; k++)
+                        if (pe[k] >= 0) {
+                            S.po[nlx] = pe[k];
+                            S.lxi[nlx] = k;
+                            nlx++;
+                        }
+                }
+                S.nlx = nlx;  // -1: more edges than were preloaded, built from global memory below
+                if (act == 1) {  // F.mvpMapPoints[bestIdx] = pMP (:279-281)
+                    S.kpmp[bidx] = row;
+                    S.occ[bidx] = trk_get(obs, row);
+                    trk_set(trk, row);
+                    S.res[XR_NMATCHES] += 2;  // :281 and :378
+                    S.res[XR_ACCEPTED]++;
+                    S.queue[0] = bidx;
+                    S.qn = 1;
+                }
             }
             __syncthreads();
             const int erow = S.ev[0];
@@ -358,52 +431,52 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                     for (int w = 0; w < X_WARPS; w++)
                         for (int k = 0; k < 2; k++)
                             if (S.t2i[w][k] >= 0) top2_update(S.t2d[w][k], S.t2o[w][k], S.t2i[w][k], b1, o1, i1, b2, o2, i2);
-                    S.ev[1] = (i1 >= 0 && !(b1 > p.th_high && b1 > p.ratio * b2)) ? 1 : 0;
+                    const bool acc = i1 >= 0 && !(b1 > p.th_high && b1 > p.ratio * b2);
+                    S.ev[1] = acc ? 1 : 0;
                     S.ev[2] = i1;
                     S.res[XR_RESCANS]++;
+                    if (acc) {
+                        S.kpmp[i1] = erow;
+                        S.occ[i1] = trk_get(obs, erow);
+                        trk_set(trk, erow);
+                        S.res[XR_NMATCHES] += 2;
+                        S.res[XR_ACCEPTED]++;
+                        S.queue[0] = i1;
+                        S.qn = 1;
+                    }
                 }
                 __syncthreads();
             }
-            if (S.ev[1] == 1) {
-                // ---- accepted: F.mvpMapPoints[bestIdx] = pMP (:279-281), then seed growing (:287-377)
-                const int bestIdx = S.ev[2];
-                const int me0 = S.ev[3], nme = S.ev[4];
-                const bool deg_ok = nme <= X_LCAP;
-                if (tid == 0) {
-                    S.kpmp[bestIdx] = erow;
-                    S.occ[bestIdx] = trk_get(obs, erow);
-                    trk_set(trk, erow);
-                    S.res[XR_NMATCHES] += 2;  // :281 and :378
-                    S.res[XR_ACCEPTED]++;
-                    S.queue[0] = bestIdx;
-                    S.qn = 1;
-                    S.nlx = 0;
-                    if (!deg_ok) S.res[XR_STATUS] |= PPG_EXTEND_OVF;
-                }
-                // without map edges every seed is skipped at :300-301
-                if (deg_ok && nme > 0) {
-                    // lx: the valid map edges of pMP (:312-318); mapEdge_set is pMP's for every seed of the event
-                    if (warp == 0) {
-                        int nlx = 0;
-                        for (int i0 = 0; i0 < nme; i0 += 32) {
-                            const int i = i0 + lane;
-                            int other = -1;
-                            bool ok = false;
-                            if (i < nme) {
-                                other = p.edge_other[me0 + i];
-                                ok = p.edge_ok[me0 + i] != 0 && other >= 0;
+            // ---- accepted: seed growing (:287-377).  Without map edges every seed is skipped at :300-301.
+            const int me0 = S.ev[3], nme = S.ev[4];
+            if (S.ev[1] == 1 && nme > 0) {
+                if (nme > X_LCAP) {
+                    if (tid == 0) S.res[XR_STATUS] |= PPG_EXTEND_OVF;
+                } else {
+                    if (S.nlx < 0) {  // uniform: S.nlx is rewritten only behind the barrier below
+                        __syncthreads();
+                        if (warp == 0) {
+                            int nlx = 0;
+                            for (int i0 = 0; i0 < nme; i0 += 32) {
+                                const int i = i0 + lane;
+                                int other = -1;
+                                bool ok = false;
+                                if (i < nme) {
+                                    other = p.edge_other[me0 + i];
+                                    ok = p.edge_ok[me0 + i] != 0 && other >= 0;
+                                }
+                                const unsigned mk = __ballot_sync(AFULL, ok);
+                                if (ok) {
+                                    const int k = nlx + __popc(mk & ((1u << lane) - 1u));
+                                    S.po[k] = other;
+                                    S.lxi[k] = i;
+                                }
+                                nlx += __popc(mk);
                             }
-                            const unsigned mk = __ballot_sync(AFULL, ok);
-                            if (ok) {
-                                const int k = nlx + __popc(mk & ((1u << lane) - 1u));
-                                S.po[k] = other;
-                                S.lxi[k] = i;
-                            }
-                            nlx += __popc(mk);
+                            if (lane == 0) S.nlx = nlx;
                         }
-                        if (lane == 0) S.nlx = nlx;
+                        __syncthreads();
                     }
-                    __syncthreads();
                     const int nlx0 = S.nlx;
                     int qh = 0;
                     while (nlx0 > 0) {  // lx empty: the assignment loop never runs (:342)
@@ -415,20 +488,35 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                             if (tid == 0) S.res[XR_STATUS] |= PPG_EXTEND_OVF;
                             continue;
                         }
-                        // weight matrix (:324-340), one warp per entry
-                        for (int q = warp; q < nlx0 * nke; q += X_WARPS) {
-                            const int i = q / nke, j = q - i * nke;
-                            const int po = S.po[i], ko = s_cko[ke0 + j];
-                            float w;
-                            if (po == S.kpmp[ko]) {
-                                w = -1.f;
-                            } else {
-                                float a[8];
+                        // weight matrix (:324-340): one warp per entry, four entries of a warp in flight
+                        const int tot = nlx0 * nke;
+                        for (int q0 = warp; q0 < tot; q0 += 4 * X_WARPS) {
+                            float av[4][8], bv[4][8];
+                            bool same[4];
 #pragma unroll
-                                for (int k = 0; k < 8; k++) a[k] = p.map_f32[(size_t)po * 256 + lane + 32 * k];
-                                w = exact_distance(a, fdesc + (size_t)ko * 256, lane);
+                            for (int u = 0; u < 4; u++) {
+                                const int q = min(q0 + u * X_WARPS, tot - 1);
+                                const int i = q / nke, j = q - i * nke;
+                                const int po = S.po[i], ko = s_cko[ke0 + j];
+                                same[u] = po == S.kpmp[ko];
+                                if (!same[u]) {
+#pragma unroll
+                                    for (int k = 0; k < 8; k++) {
+                                        av[u][k] = p.map_f32[(size_t)po * 256 + lane + 32 * k];
+                                        bv[u][k] = fdesc[(size_t)ko * 256 + lane + 32 * k];
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < 8; k++) av[u][k] = bv[u][k] = 0.f;
+                                }
                             }
-                            if (lane == 0) S.w[q] = w;
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int q = q0 + u * X_WARPS;
+                                if (q >= tot) break;  // warp-uniform
+                                const float w = same[u] ? -1.f : exact_distance_rr(av[u], bv[u]);
+                                if (lane == 0) S.w[q] = w;
+                            }
                         }
                         for (int j = tid; j < nke; j += X_THREADS) S.cly[j] = j;
                         for (int i = tid; i < nlx0; i += X_THREADS) S.clx[i] = i;
@@ -495,7 +583,8 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                 }
             }
             cursor = first + 1;
-            __syncthreads();
+            // no barrier here: whatever changed the state above is followed by one, and the next writes to wfirst / ev
+            // come after the next iteration's barrier, which every thread reaches only after its reads of this one
         }
     }
 
@@ -601,7 +690,7 @@ int run_extend(ppg_ctx* c, const FrameSrc& src, const FrameGraphSrc& gsrc, int f
         lp.l_idx = x->l_idx;
         lp.l_d = x->l_d;
         lp.l_cnt = x->l_cnt;
-        extend_lists_kernel<<<dim3((x->nc + 7) / 8, frames), 256, 0, c->st>>>(lp);
+        extend_lists_kernel<<<dim3((x->nc + XL_ROWS - 1) / XL_ROWS, frames), 256, 0, c->st>>>(lp);
         c->launches++;
         stage_mark(c, "extend.lists");
     }
