@@ -81,7 +81,7 @@ class ExtendOut(C.Structure):
     _fields_ = [("kp_mp", C.POINTER(C.c_int32)), ("kedge_me", C.POINTER(C.c_int32)),
                 ("tracked", C.POINTER(C.c_uint8)), ("nmatches", C.c_int), ("status", C.c_uint32),
                 ("n_kp", C.c_int), ("n_edges", C.c_int), ("n_accepted", C.c_int), ("n_grown", C.c_int),
-                ("n_rescans", C.c_int)]
+                ("n_rescans", C.c_int), ("diag", C.c_int * 8)]
 
 
 # every symbol include/ppg_b200.h declares (tests/test_abi.py checks the header against this list)
@@ -393,7 +393,8 @@ class Extractor:
     def _extend_result(o, r, n_points):
         return dict(nmatches=o.nmatches, status=int(o.status), kp_mp=r["kp_mp"][:o.n_kp].copy(),
                     kedge_me=r["kedge_me"][:o.n_edges].copy(), tracked=r["tracked"][:n_points].copy(),
-                    n_accepted=o.n_accepted, n_grown=o.n_grown, n_rescans=o.n_rescans)
+                    n_accepted=o.n_accepted, n_grown=o.n_grown, n_rescans=o.n_rescans,
+                    diag=[int(v) for v in o.diag])
 
     def extend_map_matches(self, kp_x, kp_y, frame_desc, kp_mp, edge_start, edge_end, conn_off, conn_idx, proj_uv,
                            view_cos, tracked, th, ratio, kedge_me=None):

@@ -36,7 +36,6 @@
 namespace ppg {
 
 constexpr int X_LIST = 32;                           // window candidates stored per row
-constexpr int X_LI_STRIDE = 258, X_LD_STRIDE = 257;  // entry-major list tiles in shared memory, conflict-free
 constexpr int X_PRE = 4;                             // map edges of a row preloaded with its chunk
 constexpr int X_LCAP = PPG_EXTEND_MAX_DEGREE;        // map edges per map point / key edges per keypoint
 constexpr int X_WCAP = PPG_EXTEND_MAX_WEIGHTS;       // weight-matrix entries per seed
@@ -55,7 +54,8 @@ struct FrameGraphSrc {
     __device__ int ne_of(int f) const { return ne ? *reinterpret_cast<const int*>(ne + f * stride) : ne_val; }
 };
 
-enum { XR_NMATCHES = 0, XR_STATUS, XR_ACCEPTED, XR_GROWN, XR_RESCANS, XR_NKP, XR_NEDGES, XR_WORDS = 8 };
+enum { XR_NMATCHES = 0, XR_STATUS, XR_ACCEPTED, XR_GROWN, XR_RESCANS, XR_NKP, XR_NEDGES, XR_ROUNDS,
+       XR_T_SETUP, XR_T_CHUNK, XR_T_EVAL, XR_T_EVENT, XR_T_SEED, XR_SEEDS, XR_WORDS = 16 };  // XR_T_*: SM cycles / 16
 
 struct ExtendState {
     // map graph (shared by all frames)
@@ -218,22 +218,20 @@ struct WalkParams {
 };
 
 struct WalkShared {
-    uint16_t lidx[X_LIST * X_LI_STRIDE];  // window lists of the 256 rows of the chunk: keypoint ...
-    float ld[X_LIST * X_LD_STRIDE];       // ... and exact distance, [entry][row]
     int kpmp[1024];      // F.mvpMapPoints as table rows
     uint8_t occ[1024];   // mvpMapPoints[i] && Observations() > 0   (Matcher.cpp:253)
     float w[X_WCAP];     // weight matrix of the current seed, [lx position][key edge]
     int po[X_LCAP];      // other map point of the valid map edges of pMP (lx)
     int lxi[X_LCAP];     // their position in getEdges()
-    int clx[X_LCAP], cly[X_LCAP];  // lx / ly while the greedy assignment erases from them
+    uint16_t taken[X_LCAP + 2];    // keypoints that became occupied during the last event
     int queue[X_LCAP + 2];         // matchSeed: every push marks one more endpoint of pMP tracked
     uint16_t cl[1024];   // window of a rescanned row
     float t2d[X_WARPS][2];
     uint32_t t2o[X_WARPS][2];
     int t2i[X_WARPS][2];
-    int wfirst[X_WARPS];
+    int wfirst[2][X_WARPS];  // double-buffered by iteration parity: one barrier per evaluation round is enough
     int ev[8];           // row, act, best idx, first map edge, map edges
-    int cln, nlx, qn;
+    int cln, nlx, qn, freed, ntaken;
     int res[XR_WORDS];
 };
 
@@ -251,6 +249,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
     uint16_t* s_cko = s_coff + p.ncap + 2;                      // [2 ecap] other keypoint of every CSR entry
     uint16_t* s_cke = s_cko + 2 * p.ecap;                       // [2 ecap] its key edge
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long t_begin = clock64();
     const int n = min(p.src.n_of(f), p.ncap);
     const int ne = min(p.gsrc.ne_of(f), p.ecap);
     const float* fdesc = p.src.desc_of(f);
@@ -261,12 +260,14 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
     // ---- initial state
     for (int w = tid; w < tw; w += X_THREADS) {
         uint32_t tb = 0, ob = 0, bb = 0;
-        for (int b = 0; b < 32; b++) {
-            const int r = w * 32 + b;
-            if (r < p.P) {
-                if (p.has_state && tracked_g[r]) tb |= 1u << b;
-                if (p.observed[r]) ob |= 1u << b;
-                if (p.bad[r]) bb |= 1u << b;
+#pragma unroll
+        for (int b = 0; b < 32; b++) {  // unconditional loads (clamped) so that all of them are in flight together
+            const int r = min(w * 32 + b, p.P - 1);
+            const uint32_t t = tracked_g[r], o = p.observed[r], d = p.bad[r];
+            if (w * 32 + b < p.P) {
+                if (p.has_state && t) tb |= 1u << b;
+                if (o) ob |= 1u << b;
+                if (d) bb |= 1u << b;
             }
         }
         trk[w] = tb;
@@ -290,6 +291,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
         }
     }
     if (tid < XR_WORDS) S.res[tid] = 0;
+    if (tid == 0) S.freed = S.ntaken = 0;
     __syncthreads();
     for (int i = tid; i < p.ncap; i += X_THREADS) {
         int r = -1;
@@ -299,68 +301,127 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
     }
     __syncthreads();
 
+    int round = 0;
+    long long tc = clock64(), t_chunk = 0, t_eval = 0, t_event = 0, t_seed = 0;
+    if (tid == 0) S.res[XR_T_SETUP] = (int)((tc - t_begin) >> 4);
     for (int base = 0; base < p.nc; base += X_THREADS) {
-        // ---- static part of the 256 rows of this chunk: the stored window lists (shared memory, entry-major so
-        // that a thread walking its own list is conflict-free) and the first map edges of each row (registers)
-        for (int e = tid; e < X_THREADS * X_LIST; e += X_THREADS) {
-            const int r = e / X_LIST, k = e - r * X_LIST;
-            if (base + r < p.nc) {
-                const size_t g = ((size_t)f * p.max_rows + base + r) * X_LIST + k;
-                S.lidx[k * X_LI_STRIDE + r] = p.l_idx[g];
-                S.ld[k * X_LD_STRIDE + r] = p.l_d[g];
-            }
-        }
+        // ---- static part of the 256 rows of this chunk: my row's stored window list (thread-local, indexed
+        // dynamically: L1-resident local memory) and its first map edges (registers)
         const int pos = base + tid;
         int row = -1, cnt = 0, my_me0 = 0, my_nme = 0;
+        uint32_t li[X_LIST / 2];  // keypoints of my list, two per word: registers (only unrolled, static indexing)
+        uint32_t lim[X_LIST / 2];  // the same for the dynamic look-up of the best entry: thread-local memory
+        float ld[X_LIST];          // exact distances, thread-local memory
         int pe[X_PRE];  // theOtherPt row of my first map edges, -1 when the edge is not usable (:312-318)
 #pragma unroll
         for (int k = 0; k < X_PRE; k++) pe[k] = -1;
+#pragma unroll
+        for (int k = 0; k < X_LIST / 2; k++) li[k] = 0xffffffffu;
         if (pos < p.nc) {
             row = p.order[pos];
+            const size_t ol = (size_t)f * p.max_rows + pos;
+            const uint4* pi = reinterpret_cast<const uint4*>(p.l_idx + ol * X_LIST);
+            const float4* pd = reinterpret_cast<const float4*>(p.l_d + ol * X_LIST);
+            uint4 iv[X_LIST / 8];
+            float4 dv[X_LIST / 4];
+#pragma unroll
+            for (int k = 0; k < X_LIST / 8; k++) iv[k] = pi[k];
+#pragma unroll
+            for (int k = 0; k < X_LIST / 4; k++) dv[k] = pd[k];
             my_me0 = p.edge_off[row];
             my_nme = p.edge_off[row + 1] - my_me0;
-            cnt = p.l_cnt[(size_t)f * p.max_rows + pos];
+            cnt = p.l_cnt[ol];
 #pragma unroll
             for (int k = 0; k < X_PRE; k++)
                 if (k < my_nme) pe[k] = p.edge_ok[my_me0 + k] ? p.edge_other[my_me0 + k] : -1;
+#pragma unroll
+            for (int k = 0; k < X_LIST / 8; k++) {
+                li[4 * k] = iv[k].x; li[4 * k + 1] = iv[k].y; li[4 * k + 2] = iv[k].z; li[4 * k + 3] = iv[k].w;
+            }
+#pragma unroll
+            for (int k = 0; k < X_LIST / 4; k++) {
+                ld[4 * k] = dv[k].x; ld[4 * k + 1] = dv[k].y; ld[4 * k + 2] = dv[k].z; ld[4 * k + 3] = dv[k].w;
+            }
+            if (base + X_THREADS + tid < p.nc) {  // the next chunk's list on its way to L2 while this one is walked
+                const size_t nl = ol + X_THREADS;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.l_idx + nl * X_LIST));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.l_d + nl * X_LIST));
+            }
         }
+#pragma unroll
+        for (int k = 0; k < X_LIST / 2; k++) lim[k] = li[k];
         const int stored = cnt < X_LIST ? cnt : X_LIST;
+        const uint32_t valid = stored >= 32 ? AFULL : (1u << stored) - 1u;
+        // fm: which entries of my list are FREE keypoints.  Built once per chunk from the occupancy table; after that
+        // every event publishes the keypoints it took (S.taken) and each thread strikes them out of its mask with
+        // register compares -- no walk over the list, no dependent shared-memory look-ups per evaluation round.
+        // S.freed counts the rare opposite case (an unobserved map point written over an observed one): rebuild.
+        auto build_mask = [&]() -> uint32_t {
+            uint32_t fm = 0;
+#pragma unroll
+            for (int k = 0; k < X_LIST / 2; k++) {
+                const uint32_t w = li[k];
+                if (2 * k < stored && !S.occ[w & 0xffffu]) fm |= 1u << (2 * k);
+                if (2 * k + 1 < stored && !S.occ[w >> 16]) fm |= 1u << (2 * k + 1);
+            }
+            return fm;
+        };
+        int my_freed = S.freed;
+        uint32_t fm = build_mask();
+        bool fresh = true;  // fm was built from the table in this round: S.taken is already in it
         int cursor = 0;
-        __syncthreads();
+        {
+            const long long t = clock64();
+            t_chunk += t - tc;
+            tc = t;
+        }
         while (true) {
             // ---- what would the reference do with my row in the current state?  (Matcher.cpp:229-277)
             int act = 0, bidx = -1;
             if (row >= 0 && tid >= cursor && cnt > 0 && !trk_get(trk, row)) {
-                float b1 = 1e6f, b2 = 1e6f;
-                int nfree = 0;
-                for (int k = 0; k < stored; k++) {
-                    const int ki = S.lidx[k * X_LI_STRIDE + tid];
-                    if (!S.occ[ki]) {
-                        if (nfree == 0) {
-                            b1 = S.ld[k * X_LD_STRIDE + tid];
-                            bidx = ki;
-                            nfree = 1;
-                        } else {
-                            b2 = S.ld[k * X_LD_STRIDE + tid];
-                            nfree = 2;
-                            break;
+                const int fr = S.freed;
+                if (fr != my_freed) {
+                    my_freed = fr;
+                    fm = build_mask();
+                } else if (!fresh) {
+                    const int nt = S.ntaken;
+                    for (int t = 0; t < nt; t++) {
+                        const uint32_t kp = S.taken[t], kp2 = kp | (kp << 16);
+#pragma unroll
+                        for (int k = 0; k < X_LIST / 2; k++) {
+                            const uint32_t x = li[k] ^ kp2;
+                            if ((x & 0xffffu) == 0) fm &= ~(1u << (2 * k));
+                            if ((x >> 16) == 0) fm &= ~(1u << (2 * k + 1));
                         }
                     }
                 }
-                if (nfree == 2 || (cnt <= X_LIST && nfree == 1))
+                fm &= valid;
+                const int nfree = __popc(fm);
+                if (nfree >= 2 || (cnt <= X_LIST && nfree == 1)) {
+                    const int k1 = __ffs(fm) - 1;
+                    const uint32_t rest = fm & (fm - 1);
+                    const float b1 = ld[k1], b2 = rest ? ld[__ffs(rest) - 1] : 1e6f;
+                    bidx = (int)((lim[k1 >> 1] >> ((k1 & 1) * 16)) & 0xffffu);
                     act = !(b1 > p.th_high && b1 > p.ratio * b2) ? 1 : 0;  // :276
-                else if (cnt > X_LIST)
+                } else if (cnt > X_LIST) {
                     act = 2;  // the list was cut and fewer than two free entries are left of it: rescan the window
+                }
                 // nfree == 0 with the whole window stored: bestIdx stays -1, the row is rejected (ratio < 1)
             }
+            fresh = false;
             const unsigned m = __ballot_sync(AFULL, act != 0);
-            if (lane == 0) S.wfirst[warp] = m ? warp * 32 + __ffs(m) - 1 : X_NOEVENT;
+            if (lane == 0) S.wfirst[round & 1][warp] = m ? warp * 32 + __ffs(m) - 1 : X_NOEVENT;
             __syncthreads();
             int first = X_NOEVENT;
 #pragma unroll
-            for (int w = 0; w < X_WARPS; w++) first = min(first, S.wfirst[w]);
+            for (int w = 0; w < X_WARPS; w++) first = min(first, S.wfirst[round & 1][w]);
+            round++;
+            {
+                const long long t = clock64();
+                t_eval += t - tc;
+                tc = t;
+            }
             if (first == X_NOEVENT) {
-                __syncthreads();  // the next chunk overwrites the lists
                 break;
             }
             if (tid == first) {
@@ -383,9 +444,11 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                         }
                 }
                 S.nlx = nlx;  // -1: more edges than were preloaded, built from global memory below
-                if (act == 1) {  // F.mvpMapPoints[bestIdx] = pMP (:279-281)
+                S.ntaken = 0;
+                if (act == 1) {  // F.mvpMapPoints[bestIdx] = pMP (:279-281); bestIdx was free
                     S.kpmp[bidx] = row;
                     S.occ[bidx] = trk_get(obs, row);
+                    if (S.occ[bidx]) S.taken[S.ntaken++] = (uint16_t)bidx;
                     trk_set(trk, row);
                     S.res[XR_NMATCHES] += 2;  // :281 and :378
                     S.res[XR_ACCEPTED]++;
@@ -438,6 +501,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                     if (acc) {
                         S.kpmp[i1] = erow;
                         S.occ[i1] = trk_get(obs, erow);
+                        if (S.occ[i1]) S.taken[S.ntaken++] = (uint16_t)i1;
                         trk_set(trk, erow);
                         S.res[XR_NMATCHES] += 2;
                         S.res[XR_ACCEPTED]++;
@@ -446,6 +510,11 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                     }
                 }
                 __syncthreads();
+            }
+            {
+                const long long t = clock64();
+                t_event += t - tc;
+                tc = t;
             }
             // ---- accepted: seed growing (:287-377).  Without map edges every seed is skipped at :300-301.
             const int me0 = S.ev[3], nme = S.ev[4];
@@ -482,6 +551,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                     while (nlx0 > 0) {  // lx empty: the assignment loop never runs (:342)
                         if (qh >= S.qn) break;
                         const int keyID = S.queue[qh++];
+                        if (tid == 0) S.res[XR_SEEDS]++;
                         const int ke0 = s_coff[keyID], nke = s_coff[keyID + 1] - ke0;
                         if (nke == 0) continue;  // :300-301
                         if (nke > X_LCAP || nlx0 * nke > X_WCAP) {
@@ -518,21 +588,50 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                                 if (lane == 0) S.w[q] = w;
                             }
                         }
-                        for (int j = tid; j < nke; j += X_THREADS) S.cly[j] = j;
-                        for (int i = tid; i < nlx0; i += X_THREADS) S.clx[i] = i;
                         __syncthreads();
-                        // greedy minimum-weight assignment (:342-374), one warp
+                        // greedy minimum-weight assignment (:342-374), one warp.  lx.erase / ly.erase keep the order of
+                        // the remaining entries, so "first minimum over the current lx x ly" = the alive entry with the
+                        // least (weight, original i, original j): no list is rebuilt, rows / columns are just struck out.
                         if (warp == 0) {
+                            uint32_t ra[X_LCAP / 32], ca[X_LCAP / 32];  // alive map edges (lx) / key edges (ly)
+#pragma unroll
+                            for (int k = 0; k < X_LCAP / 32; k++) {
+                                ra[k] = nlx0 >= 32 * (k + 1) ? AFULL : (nlx0 > 32 * k ? (1u << (nlx0 - 32 * k)) - 1u : 0u);
+                                ca[k] = nke >= 32 * (k + 1) ? AFULL : (nke > 32 * k ? (1u << (nke - 32 * k)) - 1u : 0u);
+                            }
+                            auto alive = [&](const uint32_t(&m)[X_LCAP / 32], int i) -> bool {
+                                uint32_t w = m[0];
+#pragma unroll
+                                for (int k = 1; k < X_LCAP / 32; k++) w = (i >> 5) == k ? m[k] : w;
+                                return (w >> (i & 31)) & 1u;
+                            };
+                            auto strike = [&](uint32_t(&m)[X_LCAP / 32], int i) {
+#pragma unroll
+                                for (int k = 0; k < X_LCAP / 32; k++)
+                                    if ((i >> 5) == k) m[k] &= ~(1u << (i & 31));
+                            };
+                            // the at-sign snapshot of :327-331: pMP_o == F.mvpMapPoints[keyID_o] is part of the weights above
+                            const bool small = tot <= 32;
+                            const int my_i = lane / nke, my_j = lane - my_i * nke;
+                            const float my_w = (small && lane < tot) ? S.w[lane] : 1e6f;
                             int nlx = nlx0, nly = nke;
                             while (nlx > 0 && nly > 0) {
                                 float bw = 1e6f;
                                 int bq = 0x7fffffff;
-                                for (int q = lane; q < nlx * nly; q += 32) {
-                                    const int a = q / nly, b = q - a * nly;
-                                    const float w = S.w[S.clx[a] * nke + S.cly[b]];
-                                    if (w < bw) {  // strict <: the first minimum in (a, b) order wins
-                                        bw = w;
-                                        bq = q;
+                                if (small) {
+                                    if (lane < tot && alive(ra, my_i) && alive(ca, my_j) && my_w < bw) {
+                                        bw = my_w;
+                                        bq = lane;
+                                    }
+                                } else {
+                                    for (int q = lane; q < tot; q += 32) {
+                                        const int i = q / nke, j = q - i * nke;
+                                        if (!alive(ra, i) || !alive(ca, j)) continue;
+                                        const float w = S.w[q];
+                                        if (w < bw) {  // strict <: the first minimum in (i, j) order wins
+                                            bw = w;
+                                            bq = q;
+                                        }
                                     }
                                 }
 #pragma unroll
@@ -545,37 +644,25 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                                     }
                                 }
                                 if (bq == 0x7fffffff || bw > p.th_high) break;  // :357-358
-                                const int a = bq / nly, b = bq - a * nly;
-                                const int mi = S.clx[a], kj = S.cly[b];
-                                // lx.erase / ly.erase keep the order of the rest
-                                int tx[X_LCAP / 32], ty[X_LCAP / 32];
-#pragma unroll
-                                for (int k = 0; k < X_LCAP / 32; k++) {
-                                    const int t = lane + 32 * k;
-                                    tx[k] = (t >= a && t + 1 < nlx) ? S.clx[t + 1] : (t < nlx ? S.clx[t] : 0);
-                                    ty[k] = (t >= b && t + 1 < nly) ? S.cly[t + 1] : (t < nly ? S.cly[t] : 0);
-                                }
-                                __syncwarp();
-#pragma unroll
-                                for (int k = 0; k < X_LCAP / 32; k++) {
-                                    const int t = lane + 32 * k;
-                                    if (t < nlx) S.clx[t] = tx[k];
-                                    if (t < nly) S.cly[t] = ty[k];
-                                }
+                                const int mi = bq / nke, kj = bq - mi * nke;
+                                strike(ra, mi);
+                                strike(ca, kj);
                                 nlx--;
                                 nly--;
                                 if (lane == 0) {
                                     const int po = S.po[mi], ko = s_cko[ke0 + kj];
                                     if (!(trk_get(badb, po) || trk_get(trk, po))) {  // :364-365
                                         S.kpmp[ko] = po;                             // :366
-                                        S.occ[ko] = trk_get(obs, po);
+                                        const bool nocc = trk_get(obs, po);
+                                        if (S.occ[ko] && !nocc) S.freed++;  // an observed map point was overwritten
+                                        if (!S.occ[ko] && nocc && S.ntaken < X_LCAP + 2) S.taken[S.ntaken++] = (uint16_t)ko;
+                                        S.occ[ko] = nocc;
                                         kedge_me[s_cke[ke0 + kj]] = me0 + S.lxi[mi];
                                         trk_set(trk, po);
                                         S.res[XR_GROWN]++;
                                         if (S.qn < X_LCAP + 2) S.queue[S.qn++] = ko;
                                     }
                                 }
-                                __syncwarp();
                             }
                         }
                         __syncthreads();
@@ -583,6 +670,11 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                 }
             }
             cursor = first + 1;
+            {
+                const long long t = clock64();
+                t_seed += t - tc;
+                tc = t;
+            }
             // no barrier here: whatever changed the state above is followed by one, and the next writes to wfirst / ev
             // come after the next iteration's barrier, which every thread reaches only after its reads of this one
         }
@@ -594,6 +686,11 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
     if (tid == 0) {
         S.res[XR_NKP] = n;
         S.res[XR_NEDGES] = ne;
+        S.res[XR_ROUNDS] = round;
+        S.res[XR_T_CHUNK] = (int)(t_chunk >> 4);
+        S.res[XR_T_EVAL] = (int)(t_eval >> 4);
+        S.res[XR_T_EVENT] = (int)(t_event >> 4);
+        S.res[XR_T_SEED] = (int)(t_seed >> 4);
     }
     __syncthreads();
     if (tid < XR_WORDS) p.result[f * XR_WORDS + tid] = S.res[tid];
@@ -747,6 +844,7 @@ void fill_out(const ExtendState* x, const AssocState* s, int f, ppg_extend_out* 
     o->n_accepted = r[XR_ACCEPTED];
     o->n_grown = r[XR_GROWN];
     o->n_rescans = r[XR_RESCANS];
+    for (int k = 0; k < 8; k++) o->diag[k] = r[XR_ROUNDS + k];
     if (o->kp_mp) memcpy(o->kp_mp, x->h_kp_mp + (size_t)f * s->ncap, (size_t)o->n_kp * 4);
     if (o->kedge_me) memcpy(o->kedge_me, x->h_kedge_me + (size_t)f * x->ecap, (size_t)o->n_edges * 4);
     if (o->tracked) memcpy(o->tracked, x->h_tracked + (size_t)f * x->P, (size_t)x->P);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Short deterministic workload for ncu: the bench step (batch-32 extract + batched association vs 8192 map rows),
-one warm-up step through the host path and two device-resident steps."""
+"""Short deterministic workload for ncu: the bench step (batch-32 extract + Matcher::ExtendMapMatches vs 8192 map rows),
+one warm-up step through the host path and two device-resident steps (PPG_NCU_ASSOC=core: search core only)."""
 import os
 import sys
 
@@ -15,14 +15,17 @@ B = int(os.environ.get("PPG_NCU_BATCH", "32"))
 cam, frames = bench.make_workload(B)
 e = capi.Extractor(cam, max_batch=B, max_map_points=bench.MAP_ROWS)
 recs = e.run(frames)
-map_desc, per_frame = bench.make_assoc_inputs(cam, recs, bench.MAP_ROWS)
-e.upload_map(map_desc)
+base, per_frame = bench.make_assoc_inputs(cam, recs, bench.MAP_ROWS)
+bench.upload_map(e, base)
 proj_all = np.stack([uv for uv, _ in per_frame])
 vcos_all = np.stack([vc for _, vc in per_frame])
 e.assoc_stage_batch(proj_all, vcos_all, bench.TH, bench.RATIO)
 for step in range(2):
     e.run_device(B)
-    e.assoc_run_batch(B)
+    if os.environ.get("PPG_NCU_ASSOC", "extend") == "core":
+        e.assoc_run_batch(B)
+    else:
+        e.extend_run_batch(B)
 e.sync()
-print("launches", e.launch_count(), "assoc fallback rows (last batch)", e.assoc_fallback_rows())
+print("launches", e.launch_count())
 e.close()
