@@ -3,13 +3,15 @@
 // Compile this INSIDE the PPG-SLAM tree in place of feature/src/PPGExtractor.cpp and of
 // Matcher::ExtendMapMatches (matching/src/Matcher.cpp:203-381): it includes the reference's own headers for
 // GeometricCamera / KeyPointEx / KeyEdge / Frame / MapPoint and needs OpenCV + Eigen exactly as they do.  It
-// holds no numerical logic of its own besides translating containers <-> POD and the sequential consumption
-// of the matches, which SURVEY.md s.8b keeps on the host.  (tests/test_shim_compiles.py builds it against tiny
+// holds no numerical logic of its own: it translates containers / the pointer graph <-> POD.  ExtendMapMatches runs
+// whole on the GPU (extend_map_matches below); search_local_points / search_window expose the frozen-state search
+// core for the matchers that keep their own sequential loops.  (tests/test_shim_compiles.py builds it against tiny
 // stand-in headers to keep it syntactically honest in a container without OpenCV/Eigen.)
 #pragma once
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "ppg_b200.h"
@@ -230,6 +232,114 @@ inline SearchResult search_window(ppg_ctx* ctx, FrameLike& F, const std::vector<
     upload_map_descriptors(ctx, mps);
     check(ppg_associate(ctx, &in, &out), ctx, "ppg_associate");
     return r;
+}
+
+// The whole Matcher::ExtendMapMatches (matching/src/Matcher.cpp:203-381) in one GPU call: window search with the live
+// frame state, assignment and seed growing all run in ppg_extend_map_matches; this function only flattens the
+// pointer graph into the POD form of include/ppg_b200.h and writes the result back into the Frame:
+//   table rows = the trackable map points (:210-215) in vpMapPoints order, then every map point reachable as
+//   theOtherPt() of one of their edges (its descriptor is read at :330), then the map points the frame already holds
+//   (needed for the pMP_o == F.mvpMapPoints[keyID_o] test at :327).
+// Drop-in body:  int Matcher::ExtendMapMatches(Frame& F, const vector<MapPoint*>& v, const float th)
+//                { return ppg_shim::extend_map_matches(ctx, F, v, th, mfNNratio); }
+inline int extend_map_matches(ppg_ctx* ctx, Frame& F, const std::vector<MapPoint*>& vpMapPoints, float th,
+                              float nnratio) {
+    std::vector<MapPoint*> rows;
+    std::unordered_map<MapPoint*, int32_t> row_of;
+    std::vector<uint8_t> candidate;
+    auto add_row = [&](MapPoint* p, bool cand) -> int32_t {
+        auto it = row_of.find(p);
+        if (it != row_of.end()) return it->second;
+        const int32_t r = (int32_t)rows.size();
+        row_of.emplace(p, r);
+        rows.push_back(p);
+        candidate.push_back(cand ? 1 : 0);
+        return r;
+    };
+    for (MapPoint* pMP : vpMapPoints)
+        if (!(pMP->isBad() || !pMP->mbTrackInView)) add_row(pMP, true);  // :210-215
+    const size_t n_cand = rows.size();
+    std::vector<std::vector<MapEdge*>> edges(n_cand);
+    for (size_t r = 0; r < n_cand; r++) {
+        edges[r] = rows[r]->getEdges();
+        for (MapEdge* e : edges[r])
+            if (MapPoint* o = e->theOtherPt(rows[r])) add_row(o, false);
+    }
+    const int N = (int)F.mvKeysUn.size();
+    std::vector<int32_t> kp_mp(N, -1);
+    for (int i = 0; i < N; i++)
+        if (MapPoint* q = F.mvpMapPoints[i]) kp_mp[i] = add_row(q, false);
+    const int P = (int)rows.size();
+    std::vector<uint8_t> observed(P), bad(P), tracked(P), edge_ok;
+    std::vector<int32_t> edge_off(P + 1, 0), edge_other;
+    std::vector<MapEdge*> edge_ptr;
+    std::vector<float> uv(2 * (size_t)P, 0.f), vc(P, 0.f);
+    for (int r = 0; r < P; r++) {
+        MapPoint* p = rows[r];
+        observed[r] = p->Observations() > 0;                 // :253
+        bad[r] = p->isBad();                                 // :227, :364
+        tracked[r] = p->mnTrackedbyFrame == F.mnId;          // :227, :364
+        uv[2 * r] = p->mTrackProjX;
+        uv[2 * r + 1] = p->mTrackProjY;
+        vc[r] = p->mTrackViewCos;
+        if ((size_t)r < n_cand)
+            for (MapEdge* e : edges[r]) {
+                MapPoint* o = e->theOtherPt(p);
+                edge_other.push_back(o ? row_of[o] : -1);
+                edge_ok.push_back(!(e->isBad() || !e->mbValid));  // :311
+                edge_ptr.push_back(e);
+            }
+        edge_off[r + 1] = (int32_t)edge_other.size();
+    }
+    upload_map_descriptors(ctx, rows);
+    ppg_map_graph g{P, candidate.data(), observed.data(), bad.data(), edge_off.data(), edge_other.data(),
+                    edge_ok.data()};
+    check(ppg_upload_map_graph(ctx, &g), ctx, "ppg_upload_map_graph");
+    const int E = (int)F.mvKeyEdges.size();
+    std::vector<float> kx(N), ky(N);
+    std::vector<int32_t> es(E), ee(E), conn_off(N + 1, 0), conn_idx, kedge_me(E, -1);
+    for (int i = 0; i < N; i++) {
+        kx[i] = F.mvKeysUn[i].mPos[0];
+        ky[i] = F.mvKeysUn[i].mPos[1];
+        for (unsigned int e : F.mvKeysUn[i].mvConnected) conn_idx.push_back((int32_t)e);
+        conn_off[i + 1] = (int32_t)conn_idx.size();
+    }
+    for (int e = 0; e < E; e++) {
+        es[e] = (int32_t)F.mvKeyEdges[e].startIdx;
+        ee[e] = (int32_t)F.mvKeyEdges[e].endIdx;
+    }
+    ppg_extend_in in{};
+    in.n_kp = N;
+    in.kp_x = kx.data();
+    in.kp_y = ky.data();
+    in.frame_desc = F.mDescriptors.ptr<float>(0);
+    in.kp_mp = kp_mp.data();
+    in.n_edges = E;
+    in.edge_start = es.data();
+    in.edge_end = ee.data();
+    in.conn_off = conn_off.data();
+    in.conn_idx = conn_idx.data();
+    in.kedge_me = nullptr;  // only written, never read, by the reference (:367)
+    in.proj_uv = uv.data();
+    in.view_cos = vc.data();
+    in.tracked = tracked.data();
+    in.th = th;
+    in.ratio = nnratio;
+    std::vector<int32_t> out_kp(N > 0 ? N : 1), out_ke(E > 0 ? E : 1);
+    std::vector<uint8_t> out_tr(P);
+    ppg_extend_out out{};
+    out.kp_mp = out_kp.data();
+    out.kedge_me = out_ke.data();
+    out.tracked = out_tr.data();
+    int rc = ppg_extend_map_matches(ctx, &in, &out);
+    if (rc != PPG_OK) throw std::runtime_error(std::string("ppg_extend_map_matches: ") + ppg_last_error(ctx));
+    for (int i = 0; i < N; i++)
+        if (out_kp[i] != kp_mp[i]) F.mvpMapPoints[i] = rows[out_kp[i]];          // :279, :366
+    for (int e = 0; e < E; e++)
+        if (out_ke[e] >= 0) F.mvpMapEdges[e] = edge_ptr[out_ke[e]];              // :367
+    for (int r = 0; r < P; r++)
+        if (out_tr[r] && !tracked[r]) rows[r]->mnTrackedbyFrame = F.mnId;        // :280, :368
+    return out.nmatches;
 }
 
 }  // namespace ppg_shim

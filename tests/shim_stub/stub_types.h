@@ -49,13 +49,27 @@ struct GeometricCamera {
     virtual int imHeight() = 0;
     unsigned int mnType;
 };
+struct MapPoint;
+struct MapEdge {
+    MapPoint *mpMPs, *mpMPe;
+    bool mbBad, mbValid;
+    MapPoint* theOtherPt(MapPoint* p) { return p == mpMPs ? mpMPe : (p == mpMPe ? mpMPs : nullptr); }
+    bool isBad() { return mbBad; }
+};
 struct MapPoint {
     float mTrackProjX, mTrackProjY, mTrackViewCos;
+    bool mbTrackInView;
+    long unsigned int mnTrackedbyFrame;
     int Observations() { return 0; }
+    bool isBad() { return false; }
+    std::vector<MapEdge*> getEdges() { return {}; }
     cv::Mat GetDescriptor() { return cv::Mat(); }
 };
 struct Frame {
+    long unsigned int mnId;
     std::vector<KeyPointEx> mvKeysUn;
+    std::vector<KeyEdge> mvKeyEdges;
     std::vector<MapPoint*> mvpMapPoints;
+    std::vector<MapEdge*> mvpMapEdges;
     cv::Mat mDescriptors;
 };
