@@ -122,7 +122,29 @@ def make_assoc_inputs(cam, recs, rows):
     return base, per_frame
 
 
+def make_geometry(cam, base, n_frames):
+    """--frustum: world points that project (identity pose) where the synthetic projections are, and one slightly
+    perturbed pose per frame, so that Frame::CheckInFrustum runs on the device instead of staging projections."""
+    from ppg_slam_b200 import synth
+    M = len(base["view_cos"])
+    rs = np.random.RandomState(5)
+    z = rs.uniform(2.0, 9.0, M).astype(np.float32)
+    fx, fy, cx, cy = cam.K[0], cam.K[4], cam.K[2], cam.K[5]
+    uv = base["proj_uv"]
+    P = np.stack([(uv[:, 0] - cx) / fx * z, (uv[:, 1] - cy) / fy * z, z], 1).astype(np.float32)
+    nrm = (P / np.linalg.norm(P, axis=1, keepdims=True)).astype(np.float32)
+    d = np.linalg.norm(P, axis=1)
+    g = synth.frustum_inputs(3, cam, 8, n_frames=n_frames)
+    Rcw, tcw = g["Rcw"], (g["tcw"] * 0.05).astype(np.float32)
+    Ow = np.stack([-(Rcw[f].T @ tcw[f]) for f in range(n_frames)]).astype(np.float32)
+    return dict(world_pos=P, normal=nrm, min_dist=(0.5 * d).astype(np.float32), max_dist=(2.0 * d).astype(np.float32),
+                Rcw=Rcw, tcw=tcw, Ow=Ow)
+
+
 def upload_map(x, base):
+    if "geometry" in base:
+        g = base["geometry"]
+        x.upload_map_geometry(g["world_pos"], g["normal"], g["min_dist"], g["max_dist"])
     x.upload_map(base["map_desc"])
     x.upload_map_graph(base["candidate"], base["observed"], base["bad"], base["edge_off"], base["edge_other"],
                        base["edge_ok"])
@@ -222,6 +244,9 @@ def run_b200(args, rank, local_rank, world):
     e = capi.Extractor(cam, device=local_rank, max_batch=B, max_map_points=max(args.map_rows, 1024))
     recs = e.run(frames)
     base, per_frame = make_assoc_inputs(cam, recs, args.map_rows)
+    if args.frustum:
+        base["geometry"] = make_geometry(cam, base, B)
+    geo = base.get("geometry")
     upload_map(e, base)
     core_only = args.assoc == "core"  # search core of ExtendMapMatches only (the round-1 step), for comparison
     empty = (np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros((0, 256), np.float32), np.zeros(0, np.uint8))
@@ -229,9 +254,17 @@ def run_b200(args, rank, local_rank, world):
     proj_all = np.stack([uv for uv, _ in per_frame])
     vcos_all = np.stack([vc for _, vc in per_frame])
 
+    def stage(x):
+        if geo is not None:  # Frame::CheckInFrustum on the device: 15 floats per frame cross the bus
+            x.assoc_stage_poses(geo["Rcw"], geo["tcw"], geo["Ow"], args.map_rows, 0.5, TH, RATIO)
+        else:
+            x.assoc_stage_batch(proj_all, vcos_all, TH, RATIO)
+
     def device_step(x=None):
         x = x or e
         x.run_device(B)
+        if geo is not None:
+            stage(x)
         if core_only:
             x.assoc_run_batch(B)
         else:
@@ -242,7 +275,7 @@ def run_b200(args, rank, local_rank, world):
         rc = x.lib.ppg_extract(x.h, fptrs, fstrides, B, x._outs)
         if rc not in (0, capi.PPG_ERR_CAPACITY):
             raise capi.PpgError(rc, x.lib.ppg_last_error(x.h).decode())
-        x.assoc_stage_batch(proj_all, vcos_all, TH, RATIO)
+        stage(x)
         if core_only:
             x.assoc_run_batch(B)
             x.assoc_fetch_batch(B)
@@ -264,7 +297,7 @@ def run_b200(args, rank, local_rank, world):
     # ---- device-timed arm: frames resident in HBM, K steps dealt round-robin to the device contexts
     for x in dev:
         x.upload(frames)
-        x.assoc_stage_batch(proj_all, vcos_all, TH, RATIO)
+        stage(x)
     clocks = ClockSampler(local_rank)
     t_w = time.perf_counter()
     k = 0
@@ -341,7 +374,7 @@ def run_b200(args, rank, local_rank, world):
     fps_e2e = world * B * args.steps / t_e2e
     recs = [capi._frame_to_dict(e._outs[i]) for i in range(B)]
     lay_small = 64 + sum(r["n_kp"] * 29 + r["n_edges"] * 20 + r["n_colines"] * 8 + (r["n_kp"] + 1) * 8 for r in recs)
-    h2d = B * cam.width * cam.height + B * args.map_rows * 12
+    h2d = B * cam.width * cam.height + (B * 64 if geo is not None else B * args.map_rows * 12)
     if core_only:
         d2h_assoc = B * args.map_rows * 17
     else:  # F.mvpMapPoints, F.mvpMapEdges, tracked flags and the counters of every frame
@@ -406,6 +439,7 @@ def run_b200(args, rank, local_rank, world):
                                         "Matcher::ExtendMapMatches (window search + assignment + seed growing)",
                                         args.map_rows),
                            "batch_per_gpu": B, "map_rows": args.map_rows, "sharding": "frames (no collective)",
+                           "projections": "Frame::CheckInFrustum on the device" if geo is not None else "staged by the host",
                            "device_contexts_in_flight": n_dev_ctx, "e2e_contexts_in_flight": len(ctxs),
                            "l2": "per-step working set ~3.4 GB of activations streams through the 126 MB L2 "
                                  "(inputs larger than L2; no explicit flush)"},
@@ -445,6 +479,8 @@ def main():
     ap.add_argument("--e2e-streams", type=int, default=4, help="contexts (host threads) in flight in the e2e arm")
     ap.add_argument("--assoc", default="extend", choices=["extend", "core"],
                     help="extend: the whole Matcher::ExtendMapMatches on the GPU (default); core: its search core only")
+    ap.add_argument("--frustum", action="store_true",
+                    help="project the map points on the device (Frame::CheckInFrustum) instead of staging projections")
     ap.add_argument("--camera", default="EuRoC", choices=["EuRoC", "TUM-VI", "TUM-VI-1024", "UMA-VI"],
                     help="frame shape / calibration; EuRoC 752x480 is the benchmark configuration")
     args = ap.parse_args()

@@ -238,6 +238,23 @@ int ppg_distinctive_descriptors(ppg_ctx* ctx, const float* desc, const int32_t* 
 int ppg_upload_map_distinctive(ppg_ctx* ctx, const float* desc, const int32_t* offsets, int n_points,
                                int32_t* best_idx);
 
+/* ---- Frame::CheckInFrustum (map/src/Frame.cpp:223-260) on the device ----------------------------------
+ * The projections that ExtendMapMatches consumes (mbTrackInView, mTrackProjX/Y, mTrackDepth, mTrackViewCos) computed
+ * from the map geometry and the frame poses, so that per frame only a 15-float pose crosses the bus instead of 12 bytes
+ * per map point.  Geometry per resident row: MapPoint::GetWorldPos, GetNormal, GetMinDistanceInvariance,
+ * GetMaxDistanceInvariance.  Pose per frame: Frame::mRcw (row major), mtcw, mOw.  Projection =
+ * GeometricCamera::project of the ctx's camera (Pinhole.cpp:32-38 / KannalaBrandt8.cpp:44-59), image test =
+ * GeometricCamera::IsInImage (GeometricCamera.cpp:21-24).  ppg_assoc_stage_poses replaces ppg_assoc_stage_batch:
+ * rows that are not in view get no search window (Matcher.cpp:212).  MapPoint::IncreaseVisible (:259) stays with
+ * the caller (ppg_frustum_fetch returns the flags). */
+int ppg_upload_map_geometry(ppg_ctx* ctx, const float* world_pos, const float* normal, const float* min_dist,
+                            const float* max_dist, int n_rows);
+int ppg_assoc_stage_poses(ppg_ctx* ctx, int n_frames, int n_rows, const float* Rcw, const float* tcw, const float* Ow,
+                          float cos_limit, float th, float ratio);
+/* n_frames x n_rows each (any pointer may be NULL): mbTrackInView, mTrackProjX/Y (-1 when not in view), mTrackDepth
+ * (-1), mTrackViewCos (0). */
+int ppg_frustum_fetch(ppg_ctx* ctx, int n_frames, uint8_t* in_view, float* proj_uv, float* depth, float* view_cos);
+
 /* ---- the whole Matcher::ExtendMapMatches (matching/src/Matcher.cpp:203-381) on the GPU ---------------
  * Search core as above PLUS the sequential part: the walk over the candidate map points in the order of
  * getEdges().size() (descending; ties keep table order), the live "keypoint already holds an observed map point"

@@ -270,3 +270,19 @@ def extend_map_matches(cam, map_desc, candidate, observed, bad, edge_off, edge_o
         _p(pad(conn_idx, np.int32), C.c_int), _p(kedge_me, C.c_int), C.c_float(th), C.c_float(ratio),
         C.c_float(th_high))
     return dict(nmatches=int(nm), kp_mp=kp_mp, kedge_me=kedge_me[:ne], tracked=tracked)
+
+
+def check_in_frustum(cam, Rcw, tcw, Ow, world_pos, normal, min_dist, max_dist, cos_limit=0.5, variant=""):
+    """Frame::CheckInFrustum (map/src/Frame.cpp:223-260) for every map point under one pose.
+    -> dict(in_view u8, proj_uv (M,2), depth, view_cos)."""
+    cfg = make_cfg(cam)
+    Rcw, tcw, Ow = f32(Rcw).reshape(9), f32(tcw).reshape(3), f32(Ow).reshape(3)
+    wp, nr, mn, mx = f32(world_pos), f32(normal), f32(min_dist), f32(max_dist)
+    m = len(mn)
+    iv, uv = np.zeros(m, np.uint8), np.zeros((m, 2), np.float32)
+    dp, vc = np.zeros(m, np.float32), np.zeros(m, np.float32)
+    lib(variant).ppgo_check_in_frustum_all(C.byref(cfg), _p(Rcw, C.c_float), _p(tcw, C.c_float), _p(Ow, C.c_float), m,
+                                           _p(wp, C.c_float), _p(nr, C.c_float), _p(mn, C.c_float), _p(mx, C.c_float),
+                                           C.c_float(cos_limit), _p(iv, C.c_uint8), _p(uv, C.c_float),
+                                           _p(dp, C.c_float), _p(vc, C.c_float))
+    return dict(in_view=iv, proj_uv=uv, depth=dp, view_cos=vc)

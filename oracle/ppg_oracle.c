@@ -1004,3 +1004,80 @@ int ppgo_extend_map_matches(const ppgo_cfg *c, int P, const float *map_desc, con
     free(gidx);
     return nmatches;
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* Frame::CheckInFrustum, map/src/Frame.cpp:223-260, with Pinhole::project (sensors/src/        */
+/* Pinhole.cpp:32-38) / KannalaBrandt8::project (sensors/src/KannalaBrandt8.cpp:44-59) and      */
+/* GeometricCamera::IsInImage (sensors/src/GeometricCamera.cpp:21-24).  It produces the inputs  */
+/* of ExtendMapMatches: mbTrackInView, mTrackProjX/Y, mTrackDepth, mTrackViewCos.               */
+/* Eigen's evaluation order for the 3-vectors is taken as: a row of a 3x3 product and a dot /   */
+/* squared norm are (a0*b0 + a1*b1) + a2*b2 (unrolled redux of a fixed-size expression), the    */
+/* translation is added afterwards; no FMA (baseline x86-64).  Eigen is not available here, so   */
+/* this order is an assumption shared with the CUDA path ("parity unpinned" for this function). */
+/* KannalaBrandt8: atan2f as o_atan2f; `cos(psi)` / `sin(psi)` are unqualified calls on a float  */
+/* -> double routine, the product is carried in double and rounded once on assignment            */
+/* (PPGO_LIBM_FLOAT=1: cosf / sinf in float).                                                   */
+/* out = {u, v, depth, viewCos}; returns mbTrackInView.  Not-in-view rows keep the reference's  */
+/* reset values (-1, -1, -1) and viewCos 0.                                                      */
+/* ------------------------------------------------------------------------------------------- */
+static float o_dot3(const float *a, const float *b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+
+int ppgo_check_in_frustum(const ppgo_cfg *c, const ppgo_bounds *b, const float *Rcw, const float *tcw,
+                          const float *Ow, const float *P, const float *Pn, float minD, float maxD, float cos_limit,
+                          float *out) {
+    out[0] = -1.f; /* :226-228 */
+    out[1] = -1.f;
+    out[2] = -1.f;
+    out[3] = 0.f;
+    float Pc[3];
+    for (int i = 0; i < 3; i++) Pc[i] = o_dot3(Rcw + 3 * i, P) + tcw[i]; /* :232 */
+    if (Pc[2] < 0.0f) return 0;                                         /* :234 */
+    const float fx = c->K[0], fy = c->K[4], cx = c->K[2], cy = c->K[5];
+    float u, v;
+    if (!c->fisheye) { /* Pinhole.cpp:35-36 */
+        u = fx * Pc[0] / Pc[2] + cx;
+        v = fy * Pc[1] / Pc[2] + cy;
+    } else { /* KannalaBrandt8.cpp:46-58 */
+        const float x2y2 = Pc[0] * Pc[0] + Pc[1] * Pc[1];
+        const float theta = o_atan2f(sqrtf(x2y2), Pc[2]);
+        const float psi = o_atan2f(Pc[1], Pc[0]);
+        const float theta2 = theta * theta, theta3 = theta * theta2, theta5 = theta3 * theta2;
+        const float theta7 = theta5 * theta2, theta9 = theta7 * theta2;
+        const float r = theta + c->D[0] * theta3 + c->D[1] * theta5 + c->D[2] * theta7 + c->D[3] * theta9;
+#if PPGO_LIBM_FLOAT
+        u = fx * r * cosf(psi) + cx;
+        v = fy * r * sinf(psi) + cy;
+#else
+        u = (float)((double)(fx * r) * cos((double)psi) + (double)cx);
+        v = (float)((double)(fy * r) * sin((double)psi) + (double)cy);
+#endif
+    }
+    if (!(u >= (float)b->minX && u < (float)b->maxX && v >= (float)b->minY && v < (float)b->maxY)) return 0; /* :238 */
+    float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]}; /* :243 */
+    const float dist = sqrtf(o_dot3(PO, PO));                  /* :244 */
+    if (dist < minD || dist > maxD) return 0;                  /* :245 */
+    const float viewCos = o_dot3(PO, Pn) / dist;               /* :249 */
+    if (viewCos < cos_limit) return 0;                         /* :250 */
+    out[0] = u;
+    out[1] = v;
+    out[2] = dist;
+    out[3] = viewCos;
+    return 1;
+}
+
+void ppgo_check_in_frustum_all(const ppgo_cfg *c, const float *Rcw, const float *tcw, const float *Ow, int m,
+                               const float *world_pos, const float *normal, const float *min_dist,
+                               const float *max_dist, float cos_limit, uint8_t *in_view, float *proj_uv,
+                               float *depth, float *view_cos) {
+    ppgo_bounds b;
+    ppgo_image_bounds(c, &b);
+    for (int j = 0; j < m; j++) {
+        float o[4];
+        in_view[j] = (uint8_t)ppgo_check_in_frustum(c, &b, Rcw, tcw, Ow, world_pos + 3 * j, normal + 3 * j,
+                                                    min_dist[j], max_dist[j], cos_limit, o);
+        proj_uv[2 * j] = o[0];
+        proj_uv[2 * j + 1] = o[1];
+        depth[j] = o[2];
+        view_cos[j] = o[3];
+    }
+}

@@ -92,7 +92,8 @@ SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", 
            "ppg_assoc_fetch", "ppg_assoc_run_frame", "ppg_assoc_stage_batch", "ppg_assoc_run_batch",
            "ppg_assoc_fetch_batch", "ppg_assoc_fallback_rows", "ppg_assoc_device_results",
            "ppg_distinctive_descriptors", "ppg_upload_map_distinctive", "ppg_stream", "ppg_upload_map_graph",
-           "ppg_extend_map_matches", "ppg_extend_run_batch", "ppg_extend_fetch_batch"]
+           "ppg_extend_map_matches", "ppg_extend_run_batch", "ppg_extend_fetch_batch", "ppg_upload_map_geometry",
+           "ppg_assoc_stage_poses", "ppg_frustum_fetch"]
 
 _lib = None
 
@@ -119,7 +120,8 @@ def load():
                      "ppg_assoc_fallback_rows", "ppg_assoc_device_results", "ppg_assoc_stage_batch",
                      "ppg_assoc_run_batch", "ppg_assoc_fetch_batch", "ppg_distinctive_descriptors",
                      "ppg_upload_map_distinctive", "ppg_upload_map_graph", "ppg_extend_map_matches",
-                     "ppg_extend_run_batch", "ppg_extend_fetch_batch"]:
+                     "ppg_extend_run_batch", "ppg_extend_fetch_batch", "ppg_upload_map_geometry",
+                     "ppg_assoc_stage_poses", "ppg_frustum_fetch"]:
             getattr(lib, name).restype = C.c_int
         _lib = lib
     return _lib
@@ -445,6 +447,29 @@ class Extractor:
         outs, res = self._xbatch_out
         self._check(self.lib.ppg_extend_fetch_batch(self.h, n_frames, outs))
         return [self._extend_result(outs[f], res[f], self._graph_points) for f in range(n_frames)]
+
+    # ---- Frame::CheckInFrustum on the device (map/src/Frame.cpp:223-260)
+    def upload_map_geometry(self, world_pos, normal, min_dist, max_dist):
+        a = [np.ascontiguousarray(x, np.float32) for x in (world_pos, normal, min_dist, max_dist)]
+        self._check(self.lib.ppg_upload_map_geometry(self.h, _fp(a[0]), _fp(a[1]), _fp(a[2]), _fp(a[3]), len(a[2])))
+
+    def assoc_stage_poses(self, Rcw, tcw, Ow, n_rows, cos_limit, th, ratio):
+        """Rcw (F,3,3), tcw (F,3), Ow (F,3): projects the resident map points into every frame on the device and
+        stages the result for assoc_run_batch / extend_run_batch."""
+        R, t, o = (np.ascontiguousarray(x, np.float32) for x in (Rcw, tcw, Ow))
+        F = t.reshape(-1, 3).shape[0]
+        self._check(self.lib.ppg_assoc_stage_poses(self.h, F, n_rows, _fp(R), _fp(t), _fp(o), C.c_float(cos_limit),
+                                                   C.c_float(th), C.c_float(ratio)))
+        self._assoc_rows, self._assoc_frames = n_rows, F
+        self._batch_out = None
+
+    def frustum_fetch(self, n_frames):
+        M = self._assoc_rows
+        iv, uv = np.zeros((n_frames, M), np.uint8), np.zeros((n_frames, M, 2), np.float32)
+        dp, vc = np.zeros((n_frames, M), np.float32), np.zeros((n_frames, M), np.float32)
+        self._check(self.lib.ppg_frustum_fetch(self.h, n_frames, iv.ctypes.data_as(C.POINTER(C.c_uint8)), _fp(uv),
+                                               _fp(dp), _fp(vc)))
+        return dict(in_view=iv, proj_uv=uv, depth=dp, view_cos=vc)
 
     def distinctive_descriptors(self, desc, offsets, to_table=False):
         """MapPoint::ComputeDistinctiveDescriptors for a batch of map points (packed observation descriptors +

@@ -93,11 +93,77 @@ __global__ void __launch_bounds__(256) prep_frame_kernel(const FrameSrc src, int
     }
 }
 
+// Frame::CheckInFrustum (map/src/Frame.cpp:223-260) of every resident map point under the pose of every frame, with
+// Pinhole::project (sensors/src/Pinhole.cpp:32-38) / KannalaBrandt8::project (KannalaBrandt8.cpp:44-59) and
+// GeometricCamera::IsInImage (GeometricCamera.cpp:21-24).  grid (rows/256, frames).  The arithmetic order is the one the
+// CPU restatement fixes: (a0*b0 + a1*b1) + a2*b2 for the rows of Rcw * P and the dot products, no FMA (-fmad=false);
+// KB8: atan2f / cos / sin through the double routines, rounded once.
+struct FrustumParam {
+    float fx, fy, cx, cy, k0, k1, k2, k3;
+    float minX, maxX, minY, maxY;
+    int fisheye;
+    float cos_limit;
+};
+__device__ __forceinline__ float dot3(const float* a, float b0, float b1, float b2) {
+    return (a[0] * b0 + a[1] * b1) + a[2] * b2;
+}
+__global__ void frustum_kernel(const float* __restrict__ wpos, const float* __restrict__ nrm,
+                               const float* __restrict__ dmin, const float* __restrict__ dmax,
+                               const float* __restrict__ poses, int rows, int max_rows, FrustumParam fp,
+                               float* __restrict__ proj, float* __restrict__ vcos, float* __restrict__ depth,
+                               uint8_t* __restrict__ in_view) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+    if (m >= rows) return;
+    const size_t o = (size_t)f * max_rows + m;
+    const float* T = poses + f * 16;
+    const float P0 = wpos[3 * m], P1 = wpos[3 * m + 1], P2 = wpos[3 * m + 2];
+    float u = -1.f, v = -1.f, dep = -1.f, vc = 0.f;  // :226-228
+    bool ok = false;
+    const float Pc0 = dot3(T, P0, P1, P2) + T[9];
+    const float Pc1 = dot3(T + 3, P0, P1, P2) + T[10];
+    const float Pc2 = dot3(T + 6, P0, P1, P2) + T[11];
+    if (!(Pc2 < 0.0f)) {  // :234
+        float pu, pv;
+        if (!fp.fisheye) {
+            pu = fp.fx * Pc0 / Pc2 + fp.cx;
+            pv = fp.fy * Pc1 / Pc2 + fp.cy;
+        } else {
+            const float x2y2 = Pc0 * Pc0 + Pc1 * Pc1;
+            const float theta = (float)atan2((double)sqrtf(x2y2), (double)Pc2);
+            const float psi = (float)atan2((double)Pc1, (double)Pc0);
+            const float theta2 = theta * theta, theta3 = theta * theta2, theta5 = theta3 * theta2;
+            const float theta7 = theta5 * theta2, theta9 = theta7 * theta2;
+            const float r = theta + fp.k0 * theta3 + fp.k1 * theta5 + fp.k2 * theta7 + fp.k3 * theta9;
+            pu = (float)((double)(fp.fx * r) * cos((double)psi) + (double)fp.cx);
+            pv = (float)((double)(fp.fy * r) * sin((double)psi) + (double)fp.cy);
+        }
+        if (pu >= fp.minX && pu < fp.maxX && pv >= fp.minY && pv < fp.maxY) {  // :238
+            const float PO0 = P0 - T[12], PO1 = P1 - T[13], PO2 = P2 - T[14];
+            const float dist = sqrtf((PO0 * PO0 + PO1 * PO1) + PO2 * PO2);
+            if (!(dist < dmin[m] || dist > dmax[m])) {  // :245
+                const float c = ((PO0 * nrm[3 * m] + PO1 * nrm[3 * m + 1]) + PO2 * nrm[3 * m + 2]) / dist;
+                if (!(c < fp.cos_limit)) {  // :250
+                    ok = true;
+                    u = pu;
+                    v = pv;
+                    dep = dist;
+                    vc = c;
+                }
+            }
+        }
+    }
+    proj[2 * o] = u;
+    proj[2 * o + 1] = v;
+    vcos[o] = vc;
+    depth[o] = dep;
+    in_view[o] = ok ? 1 : 0;
+}
+
 // Search window of each map point: r (Matcher.cpp:240-244) and the cell range of GetFeaturesInArea
 // (Frame.cpp:270-292) including its early returns.  grid (rows/256, frames).
 __global__ void prep_rows_kernel(const float* __restrict__ proj, const float* __restrict__ vcos,
                                  const float* __restrict__ n2, int rows, int max_rows, float th, int mode,
-                                 GridParam g, RowParam* __restrict__ rp) {
+                                 GridParam g, RowParam* __restrict__ rp, const uint8_t* __restrict__ in_view) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
     if (m >= rows) return;
     const size_t o = (size_t)f * max_rows + m;
@@ -113,7 +179,7 @@ __global__ void prep_rows_kernel(const float* __restrict__ proj, const float* __
     }
     p.r = r;
     p.na2 = n2[m];
-    bool empty = false;
+    bool empty = in_view != nullptr && !in_view[o];  // !mbTrackInView: not a candidate (Matcher.cpp:212)
     int x0 = (int)floorf((p.u - (float)g.minX - r) * g.wInv);
     if (x0 < 0) x0 = 0;
     if (x0 >= 64) empty = true;
@@ -631,6 +697,13 @@ int assoc_ensure_state(ppg_ctx* c) {
     PPG_CUDA(c, dalloc(&s->second_d, B * R));
     PPG_CUDA(c, dalloc(&s->accept, B * R));
     PPG_CUDA(c, dalloc(&s->fallback, 1));
+    PPG_CUDA(c, dalloc(&s->wpos, R * 3));
+    PPG_CUDA(c, dalloc(&s->nrm, R * 3));
+    PPG_CUDA(c, dalloc(&s->dmin, R));
+    PPG_CUDA(c, dalloc(&s->dmax, R));
+    PPG_CUDA(c, dalloc(&s->poses, B * 16));
+    PPG_CUDA(c, dalloc(&s->in_view, B * R));
+    PPG_CUDA(c, dalloc(&s->depth, B * R));
     s->h_res_bytes = B * R * 17;
     PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&s->h_res), s->h_res_bytes));
     PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&s->h_stage), B * R * 3 * sizeof(float)));
@@ -679,7 +752,8 @@ int assoc_prep(ppg_ctx* c, const FrameSrc& src, int frames) {
     prep_frame_kernel<<<dim3(s->ncap / 8, frames), 256, 0, c->st>>>(src, s->ncap, g, s->f_bf, s->fn2, s->kinfo,
                                                                     s->korder, s->nbmax);
     prep_rows_kernel<<<dim3((rows + 255) / 256, frames), 256, 0, c->st>>>(s->proj, s->vcos, s->map_n2, rows,
-                                                                          s->max_rows, s->th, s->mode, g, s->rowp);
+                                                                          s->max_rows, s->th, s->mode, g, s->rowp,
+                                                                          s->use_in_view ? s->in_view : nullptr);
     c->launches += 2;
     PPG_CUDA(c, cudaGetLastError());
     stage_mark(c, "assoc.prep");
@@ -780,7 +854,8 @@ void assoc_destroy(ppg_ctx* c) {
     if (!s) return;
     void* bufs[] = {s->map_f32, s->map_bf, s->map_n2, s->kx, s->ky, s->fdesc, s->fn2, s->free_mask, s->ones, s->f_bf,
                     s->kinfo, s->korder, s->nbmax, s->proj, s->vcos, s->rowp, s->cand, s->guard,
-                    s->best_idx, s->second_idx, s->best_d, s->second_d, s->accept, s->fallback};
+                    s->best_idx, s->second_idx, s->best_d, s->second_d, s->accept, s->fallback,
+                    s->wpos, s->nrm, s->dmin, s->dmax, s->poses, s->in_view, s->depth};
     for (void* b : bufs)
         if (b) cudaFree(b);
     extend_destroy(s);
@@ -814,6 +889,7 @@ int assoc_stage_rows(ppg_ctx* c, int frames, int n_rows, const float* proj_uv, c
     s->mode = 0;  // ppg_assoc_stage overrides from ppg_assoc_in
     s->max_dist = 0.f;
     s->e2_max = 0.0;
+    s->use_in_view = false;
     return PPG_OK;
 }
 
@@ -836,6 +912,88 @@ int ppg_upload_map(ppg_ctx* c, const float* map_desc, int n_rows) {
     PPG_CUDA(c, cudaGetLastError());
     PPG_CUDA(c, cudaStreamSynchronize(c->st));
     s->n_rows = n_rows;
+    return PPG_OK;
+}
+
+int ppg_upload_map_geometry(ppg_ctx* c, const float* world_pos, const float* normal, const float* min_dist,
+                            const float* max_dist, int n_rows) {
+    if (!c || !world_pos || !normal || !min_dist || !max_dist || n_rows < 1)
+        return set_err(c, PPG_ERR_ARG, "ppg_upload_map_geometry: bad arguments");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    int rc = assoc_ensure_state(c);
+    if (rc != PPG_OK) return rc;
+    AssocState* s = c->assoc;
+    if (n_rows > s->max_rows) return set_err(c, PPG_ERR_ARG, "ppg_upload_map_geometry: more rows than max_map_points");
+    PPG_CUDA(c, cudaMemcpyAsync(s->wpos, world_pos, (size_t)n_rows * 12, cudaMemcpyHostToDevice, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(s->nrm, normal, (size_t)n_rows * 12, cudaMemcpyHostToDevice, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(s->dmin, min_dist, (size_t)n_rows * 4, cudaMemcpyHostToDevice, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(s->dmax, max_dist, (size_t)n_rows * 4, cudaMemcpyHostToDevice, c->st));
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    s->geo_rows = n_rows;
+    return PPG_OK;
+}
+
+int ppg_assoc_stage_poses(ppg_ctx* c, int n_frames, int n_rows, const float* Rcw, const float* tcw, const float* Ow,
+                          float cos_limit, float th, float ratio) {
+    if (!c || !c->assoc || !Rcw || !tcw || !Ow) return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage_poses: null argument");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    AssocState* s = c->assoc;
+    if (n_rows < 1 || n_rows > s->n_rows || n_rows > s->geo_rows)
+        return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage_poses: upload descriptors and geometry of all n_rows rows first");
+    if (n_frames < 1 || n_frames > s->bcap) return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage_poses: bad frame count");
+    // 64 bytes per frame from pageable memory: the driver stages such a copy before it returns, so no pinned buffer
+    // (and no synchronisation with the previous batch) is needed
+    std::vector<float> hv((size_t)n_frames * 16, 0.f);
+    float* h = hv.data();
+    for (int f = 0; f < n_frames; f++) {
+        memcpy(h + 16 * f, Rcw + 9 * f, 36);
+        memcpy(h + 16 * f + 9, tcw + 3 * f, 12);
+        memcpy(h + 16 * f + 12, Ow + 3 * f, 12);
+    }
+    PPG_CUDA(c, cudaMemcpyAsync(s->poses, h, (size_t)n_frames * 64, cudaMemcpyHostToDevice, c->st));
+    FrustumParam fp;
+    fp.fx = c->cfg.K[0];
+    fp.fy = c->cfg.K[4];
+    fp.cx = c->cfg.K[2];
+    fp.cy = c->cfg.K[5];
+    fp.k0 = c->cfg.D[0];
+    fp.k1 = c->cfg.D[1];
+    fp.k2 = c->cfg.D[2];
+    fp.k3 = c->cfg.D[3];
+    fp.minX = (float)c->minX;
+    fp.maxX = (float)c->maxX;
+    fp.minY = (float)c->minY;
+    fp.maxY = (float)c->maxY;
+    fp.fisheye = c->cfg.fisheye;
+    fp.cos_limit = cos_limit;
+    frustum_kernel<<<dim3((n_rows + 255) / 256, n_frames), 256, 0, c->st>>>(s->wpos, s->nrm, s->dmin, s->dmax, s->poses,
+                                                                             n_rows, s->max_rows, fp, s->proj, s->vcos,
+                                                                             s->depth, s->in_view);
+    c->launches++;
+    PPG_CUDA(c, cudaGetLastError());
+    stage_mark(c, "assoc.frustum");
+    s->staged_rows = n_rows;
+    s->staged_frames = n_frames;
+    s->th = th;
+    s->ratio = ratio;
+    s->mode = 0;
+    s->max_dist = 0.f;
+    s->e2_max = 0.0;
+    s->use_in_view = true;
+    return PPG_OK;
+}
+
+int ppg_frustum_fetch(ppg_ctx* c, int n_frames, uint8_t* in_view, float* proj_uv, float* depth, float* view_cos) {
+    if (!c || !c->assoc || n_frames < 1 || n_frames > c->assoc->staged_frames || !c->assoc->use_in_view)
+        return set_err(c, PPG_ERR_ARG, "ppg_frustum_fetch: stage poses first");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    AssocState* s = c->assoc;
+    const size_t R = s->staged_rows, M = s->max_rows, F = n_frames;
+    if (in_view) PPG_CUDA(c, cudaMemcpy2DAsync(in_view, R, s->in_view, M, R, F, cudaMemcpyDeviceToHost, c->st));
+    if (proj_uv) PPG_CUDA(c, cudaMemcpy2DAsync(proj_uv, R * 8, s->proj, M * 8, R * 8, F, cudaMemcpyDeviceToHost, c->st));
+    if (depth) PPG_CUDA(c, cudaMemcpy2DAsync(depth, R * 4, s->depth, M * 4, R * 4, F, cudaMemcpyDeviceToHost, c->st));
+    if (view_cos) PPG_CUDA(c, cudaMemcpy2DAsync(view_cos, R * 4, s->vcos, M * 4, R * 4, F, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
     return PPG_OK;
 }
 

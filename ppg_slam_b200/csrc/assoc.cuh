@@ -70,6 +70,14 @@ struct AssocState {
     int* fallback = nullptr;
     uint8_t* h_res = nullptr;  // pinned staging for fetch: 5 planes [bcap][max_rows] (4 x 4 bytes, 1 x 1 byte)
     size_t h_res_bytes = 0;
+    // Frame::CheckInFrustum on the device (ppg_upload_map_geometry / ppg_assoc_stage_poses): map geometry, poses,
+    // mbTrackInView / mTrackDepth per (frame, row); proj and vcos above are then written by frustum_kernel
+    float *wpos = nullptr, *nrm = nullptr, *dmin = nullptr, *dmax = nullptr;  // [max_rows] x 3, 3, 1, 1
+    float* poses = nullptr;                                                   // [bcap][16]: Rcw 9, tcw 3, Ow 3
+    uint8_t* in_view = nullptr;                                               // [bcap][max_rows]
+    float* depth = nullptr;                                                   // [bcap][max_rows]
+    int geo_rows = 0;
+    bool use_in_view = false;  // rows staged through poses: out-of-view rows have no search window
     ExtendState* ext = nullptr;  // whole ExtendMapMatches (extend.cu), allocated on first use
     float* h_stage = nullptr;  // pinned staging for the per-frame projections: [bcap][max_rows] x (2 + 1) floats
 };

@@ -137,3 +137,36 @@ def extend_inputs(seed, frame_desc, kp_xy, kedge_start, kedge_end, n_map, width,
     return dict(map_desc=d.astype(np.float32), proj_uv=uv.astype(np.float32), view_cos=view_cos, candidate=candidate,
                 observed=observed, bad=bad, edge_off=edge_off, edge_other=edge_other, edge_ok=edge_ok, tracked=tracked,
                 kp_mp=kp_mp, planted_rows=rows.astype(np.int32), planted_src=src.astype(np.int32))
+
+
+def frustum_inputs(seed, cam, n_points, n_frames=1):
+    """Map geometry + camera poses for Frame::CheckInFrustum: points scattered in front of (and partly behind /
+    beside) a camera near the origin, mean viewing directions (MapPoint::GetNormal) roughly along the ray, scale-invariance distance bands, and small random
+    rigid motions per frame.  -> dict(world_pos, normal, min_dist, max_dist, Rcw (F,3,3), tcw (F,3), Ow (F,3))"""
+    rs = np.random.RandomState(seed)
+    fx, fy, cx, cy = cam.K[0], cam.K[4], cam.K[2], cam.K[5]
+    z = rs.uniform(1.0, 12.0, n_points)
+    u = rs.uniform(-0.3 * cam.width, 1.3 * cam.width, n_points)
+    v = rs.uniform(-0.3 * cam.height, 1.3 * cam.height, n_points)
+    P = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    behind = rs.rand(n_points) < 0.05
+    P[behind, 2] *= -1
+    n = P / np.linalg.norm(P, axis=1, keepdims=True) + rs.normal(0, 0.6, P.shape)  # mean viewing direction
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    d = np.linalg.norm(P, axis=1)
+    min_d = d * rs.uniform(0.3, 1.05, n_points)
+    max_d = d * rs.uniform(0.95, 3.0, n_points)
+    Rs, ts, Os = [], [], []
+    for _ in range(n_frames):
+        w = rs.normal(0, 0.03, 3)
+        th = np.linalg.norm(w)
+        k = w / th
+        K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        R = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+        t = rs.normal(0, 0.1, 3)
+        Rs.append(R)
+        ts.append(t)
+        Os.append(-R.T @ t)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    return dict(world_pos=f(P), normal=f(n), min_dist=f(min_d), max_dist=f(max_d), Rcw=f(np.stack(Rs)),
+                tcw=f(np.stack(ts)), Ow=f(np.stack(Os)))

@@ -205,3 +205,79 @@ def test_extend_batch_on_extracted_frames():
         assert got[0]["n_accepted"] > 50 and got[0]["n_grown"] > 50
     finally:
         e.close()
+
+
+@pytest.mark.parametrize("cam", [cameras.EUROC, cameras.TUMVI, cameras.UMA], ids=lambda c: c.name)
+def test_check_in_frustum_equals_oracle(cam):
+    """Frame::CheckInFrustum on the device (ppg_assoc_stage_poses) == the CPU restatement, bit for bit: flags,
+    projections, depth and viewing cosine of every map point under three poses (pinhole and KannalaBrandt8)."""
+    from oracle import post_ref as O
+    from ppg_slam_b200 import capi
+    M, F = 5000, 3
+    g = synth.frustum_inputs(8, cam, M, n_frames=F)
+    rs = np.random.RandomState(0)
+    desc = rs.normal(size=(M, 256)).astype(np.float32)
+    e = capi.Extractor(cam, max_batch=F, max_map_points=8192)
+    try:
+        e.upload_map(desc)
+        e.upload_map_geometry(g["world_pos"], g["normal"], g["min_dist"], g["max_dist"])
+        e.assoc_stage_poses(g["Rcw"], g["tcw"], g["Ow"], M, 0.5, 10.0, 0.8)
+        got = e.frustum_fetch(F)
+        for f in range(F):
+            ref = O.check_in_frustum(cam, g["Rcw"][f], g["tcw"][f], g["Ow"][f], g["world_pos"], g["normal"],
+                                     g["min_dist"], g["max_dist"], 0.5)
+            np.testing.assert_array_equal(got["in_view"][f], ref["in_view"])
+            for k in ("proj_uv", "depth", "view_cos"):
+                np.testing.assert_array_equal(got[k][f].view(np.uint32), ref[k].view(np.uint32), err_msg=k)
+            assert 0.1 * M < ref["in_view"].sum() < 0.9 * M
+    finally:
+        e.close()
+
+
+def test_extend_batch_with_device_projection():
+    """The tracking step end to end on the device: extract -> CheckInFrustum of the resident map under each frame's
+    pose -> ExtendMapMatches.  Oracle: CheckInFrustum restatement, then ExtendMapMatches with mbTrackInView folded
+    into the candidate flags (Matcher.cpp:212)."""
+    from oracle import post_ref as O
+    from ppg_slam_b200 import capi
+    cam = cameras.EUROC
+    Bn, M = 3, 4096
+    e = capi.Extractor(cam, max_batch=Bn, max_map_points=M)
+    try:
+        recs = e.run([synth.frame(s, cam.width, cam.height) for s in range(Bn)])
+        r0 = recs[0]
+        inp = synth.extend_inputs(6, r0["desc"], np.stack([r0["kp_x"], r0["kp_y"]], 1), r0["edge_start"], r0["edge_end"],
+                                  M, cam.width, cam.height, th=10.0, clean=False)
+        # world points that project (under the identity pose) where extend_inputs put the projections
+        rs = np.random.RandomState(2)
+        z = rs.uniform(2.0, 9.0, M).astype(np.float32)
+        fx, fy, cx, cy = cam.K[0], cam.K[4], cam.K[2], cam.K[5]
+        P = np.stack([(inp["proj_uv"][:, 0] - cx) / fx * z, (inp["proj_uv"][:, 1] - cy) / fy * z, z], 1).astype(np.float32)
+        nrm = (P / np.linalg.norm(P, axis=1, keepdims=True) + rs.normal(0, 0.3, P.shape)).astype(np.float32)
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        d = np.linalg.norm(P, axis=1)
+        dmin, dmax = (d * rs.uniform(0.4, 1.02, M)).astype(np.float32), (d * rs.uniform(0.98, 2.5, M)).astype(np.float32)
+        g = synth.frustum_inputs(3, cam, 8, n_frames=Bn)  # poses only
+        Rcw, tcw, Ow = g["Rcw"], g["tcw"] * 0.1, None
+        Ow = np.stack([-(Rcw[f].T @ tcw[f]) for f in range(Bn)]).astype(np.float32)
+        e.upload_map(inp["map_desc"])
+        e.upload_map_graph(inp["candidate"], inp["observed"], inp["bad"], inp["edge_off"], inp["edge_other"],
+                           inp["edge_ok"])
+        e.upload_map_geometry(P, nrm, dmin, dmax)
+        e.assoc_stage_poses(Rcw, tcw, Ow, M, 0.5, 10.0, 0.8)
+        e.extend_run_batch(Bn)
+        got = e.extend_fetch_batch(Bn)
+        n_acc = 0
+        for f in range(Bn):
+            r = recs[f]
+            fr = O.check_in_frustum(cam, Rcw[f], tcw[f], Ow[f], P, nrm, dmin, dmax, 0.5)
+            fi = dict(inp, proj_uv=fr["proj_uv"], view_cos=fr["view_cos"], candidate=inp["candidate"] & fr["in_view"],
+                      kp_mp=np.full(r["n_kp"], -1, np.int32), tracked=np.zeros(M, np.uint8))
+            ref = _oracle(cam, fi, r["kp_x"], r["kp_y"], r["desc"], r["edge_start"], r["edge_end"], r["conn_off"],
+                          r["conn_idx"], 10.0, 0.8)
+            _same(got[f], ref)
+            n_acc += got[f]["n_accepted"]
+            assert 0.2 * M < fr["in_view"].sum() < M
+        assert n_acc > 100
+    finally:
+        e.close()

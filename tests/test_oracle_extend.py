@@ -191,3 +191,51 @@ def test_extend_map_matches_kat(seed, clean):
     assert (got["kedge_me"] >= 0).sum() >= 5
     if not clean:
         assert (inp["kp_mp"] != got["kp_mp"]).sum() >= 10
+
+
+@pytest.mark.parametrize("cam", [cameras.EUROC, cameras.TUMVI], ids=lambda c: c.name)
+def test_check_in_frustum_kat(cam):
+    """Frame::CheckInFrustum (map/src/Frame.cpp:223-260) restated with numpy float32 scalars, statement by statement."""
+    import math
+    f = np.float32
+    g = synth.frustum_inputs(3, cam, 600)
+    R, t, Ow = g["Rcw"][0], g["tcw"][0], g["Ow"][0]
+    got = O.check_in_frustum(cam, R, t, Ow, g["world_pos"], g["normal"], g["min_dist"], g["max_dist"], 0.5)
+    b = O.image_bounds(cam)
+    fx, fy, cx, cy = f(cam.K[0]), f(cam.K[4]), f(cam.K[2]), f(cam.K[5])
+    n_in = 0
+    for j in range(len(g["min_dist"])):
+        P, Pn = g["world_pos"][j], g["normal"][j]
+        dot3 = lambda a, c: f(f(f(a[0] * c[0]) + f(a[1] * c[1])) + f(a[2] * c[2]))
+        Pc = [f(dot3(R[i], P) + t[i]) for i in range(3)]
+        want = (0, -1.0, -1.0, -1.0, 0.0)
+        if not Pc[2] < 0:
+            with np.errstate(all="ignore"):
+                if not cam.fisheye:
+                    u = f(f(f(fx * Pc[0]) / Pc[2]) + cx)
+                    v = f(f(f(fy * Pc[1]) / Pc[2]) + cy)
+                else:
+                    x2y2 = f(f(Pc[0] * Pc[0]) + f(Pc[1] * Pc[1]))
+                    theta = f(math.atan2(float(np.sqrt(x2y2)), float(Pc[2])))
+                    psi = f(math.atan2(float(Pc[1]), float(Pc[0])))
+                    t2 = f(theta * theta)
+                    t3 = f(theta * t2)
+                    t5 = f(t3 * t2)
+                    t7 = f(t5 * t2)
+                    t9 = f(t7 * t2)
+                    D = [f(x) for x in cam.D]
+                    r = f(f(f(f(theta + f(D[0] * t3)) + f(D[1] * t5)) + f(D[2] * t7)) + f(D[3] * t9))
+                    u = f(float(f(fx * r)) * math.cos(float(psi)) + float(cx))
+                    v = f(float(f(fy * r)) * math.sin(float(psi)) + float(cy))
+            if u >= f(b.minX) and u < f(b.maxX) and v >= f(b.minY) and v < f(b.maxY):
+                PO = [f(P[i] - Ow[i]) for i in range(3)]
+                dist = f(np.sqrt(dot3(PO, PO)))
+                if not (dist < g["min_dist"][j] or dist > g["max_dist"][j]):
+                    vc = f(dot3(PO, Pn) / dist)
+                    if not vc < f(0.5):
+                        want = (1, u, v, dist, vc)
+        assert got["in_view"][j] == want[0]
+        for a, w in zip((got["proj_uv"][j, 0], got["proj_uv"][j, 1], got["depth"][j], got["view_cos"][j]), want[1:]):
+            assert f(a).view(np.uint32) == f(w).view(np.uint32), (j, a, w)
+        n_in += want[0]
+    assert 60 < n_in < 500  # every exit of the function is taken by some point
