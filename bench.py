@@ -254,7 +254,7 @@ def run_b200(args, rank, local_rank, world):
     proj_all = np.stack([uv for uv, _ in per_frame])
     vcos_all = np.stack([vc for _, vc in per_frame])
 
-    def stage(x):
+    def stage_proj(x):
         if geo is not None:  # Frame::CheckInFrustum on the device: 15 floats per frame cross the bus
             x.assoc_stage_poses(geo["Rcw"], geo["tcw"], geo["Ow"], args.map_rows, 0.5, TH, RATIO)
         else:
@@ -264,7 +264,7 @@ def run_b200(args, rank, local_rank, world):
         x = x or e
         x.run_device(B)
         if geo is not None:
-            stage(x)
+            stage_proj(x)
         if core_only:
             x.assoc_run_batch(B)
         else:
@@ -275,7 +275,7 @@ def run_b200(args, rank, local_rank, world):
         rc = x.lib.ppg_extract(x.h, fptrs, fstrides, B, x._outs)
         if rc not in (0, capi.PPG_ERR_CAPACITY):
             raise capi.PpgError(rc, x.lib.ppg_last_error(x.h).decode())
-        stage(x)
+        stage_proj(x)
         if core_only:
             x.assoc_run_batch(B)
             x.assoc_fetch_batch(B)
@@ -297,7 +297,7 @@ def run_b200(args, rank, local_rank, world):
     # ---- device-timed arm: frames resident in HBM, K steps dealt round-robin to the device contexts
     for x in dev:
         x.upload(frames)
-        stage(x)
+        stage_proj(x)
     clocks = ClockSampler(local_rank)
     t_w = time.perf_counter()
     k = 0
