@@ -326,6 +326,40 @@ int ppg_extend_map_matches(ppg_ctx* ctx, const ppg_extend_in* in, ppg_extend_out
 int ppg_extend_run_batch(ppg_ctx* ctx, int n_frames);
 int ppg_extend_fetch_batch(ppg_ctx* ctx, int n_frames, ppg_extend_out* outs);
 
+/* ---- bag of words: DBoW3::Vocabulary::transform (Frame::ComputeBoW, map/src/Frame.cpp:331-340) --------
+ * The vocabulary is the k-ary tree of the reference's Vocabulary/voc_*_9x3.gz (DBoW3 binary; tools/export_vocabulary.py
+ * converts it to these flat arrays): children[n_nodes][k] in DBoW3's visiting order (-1 padded, leaves all -1),
+ * word_id[n_nodes] (-1 for inner nodes), weight[n_nodes] (the leaf's idf), desc[n_nodes][256].  transform:
+ *   per feature: descend from the root taking at every level the FIRST child with the least DescManip::distance
+ *   (sum of float (a_i - b_i)^2 accumulated in double in index order); word / weight = the leaf's; FeatureVector node =
+ *   the node reached at level L - levelsup, the root when that is <= 0 (the reference: L = 3, levelsup = 4);
+ *   BowVector = the weights of the features with weight > 0 summed per word in feature order, then divided by their
+ *   L2 norm (scoring 1), L1 norm (0, 2, 3, 4) or, for DOT_PRODUCT (5), by the number of words.
+ * Weighting must be TF_IDF (0) or TF (1). */
+typedef struct {
+    int k, L, scoring, weighting, n_nodes, dim;
+    const int32_t* children;
+    const int32_t* word_id;
+    const double* weight;
+    const float* desc;
+} ppg_vocabulary;
+int ppg_upload_vocabulary(ppg_ctx* ctx, const ppg_vocabulary* voc);
+
+typedef struct {          /* caller-allocated (any pointer may be NULL) */
+    int n_features;       /* out: features transformed */
+    int n_bow;            /* out: entries of the BowVector */
+    int32_t* word_id;     /* n_features: WordId of every feature */
+    double* word_weight;  /* n_features: its weight */
+    int32_t* node_id;     /* n_features: FeatureVector node of the feature, -1 when its weight is <= 0 (not listed) */
+    int32_t* bow_word;    /* n_bow: BowVector keys, ascending */
+    double* bow_value;    /* n_bow: BowVector values */
+} ppg_bow_out;
+/* One frame, descriptors (n_features x 256) in host memory; synchronous. */
+int ppg_bow_transform(ppg_ctx* ctx, const float* desc, int n_features, int levelsup, ppg_bow_out* out);
+/* Every frame of the last extraction batch (descriptors still on the device); asynchronous + fetch. */
+int ppg_bow_run_batch(ppg_ctx* ctx, int n_frames, int levelsup);
+int ppg_bow_fetch_batch(ppg_ctx* ctx, int n_frames, ppg_bow_out* outs);
+
 /* Device pointers of the staged association results (n_rows each), for the sharded all-gather that
  * the multi-GPU host layer issues through NCCL (ppg_slam_b200/sharded.py). */
 int ppg_assoc_device_results(ppg_ctx* ctx, void** best_idx, void** second_idx, void** best_dist, void** second_dist,

@@ -286,3 +286,22 @@ def check_in_frustum(cam, Rcw, tcw, Ow, world_pos, normal, min_dist, max_dist, c
                                            C.c_float(cos_limit), _p(iv, C.c_uint8), _p(uv, C.c_float),
                                            _p(dp, C.c_float), _p(vc, C.c_float))
     return dict(in_view=iv, proj_uv=uv, depth=dp, view_cos=vc)
+
+
+def bow_transform(voc, feat, levelsup=4):
+    """DBoW3::Vocabulary::transform as the reference calls it (map/src/Frame.cpp:331-340).  voc: object with k, L,
+    scoring, child_table(), weight, word_id, desc (ppg_slam_b200.vocabulary.Vocabulary or a synthetic stand-in).
+    -> dict(word, weight, node per feature; bow_word, bow_value sorted by word)."""
+    feat = f32(feat)
+    n = feat.shape[0]
+    ch = np.ascontiguousarray(voc.child_table(), np.int32)
+    w = np.ascontiguousarray(voc.weight, np.float64)
+    wid = np.ascontiguousarray(voc.word_id, np.int32)
+    nd = f32(voc.desc)
+    fw, fwt, fn = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64), np.zeros(max(n, 1), np.int32)
+    bw, bv = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64)
+    nb = lib().ppgo_bow_transform(voc.k, voc.L, voc.scoring, _p(ch, C.c_int), _p(w, C.c_double), _p(wid, C.c_int),
+                                  _p(nd, C.c_float), nd.shape[1], n, _p(feat if n else np.zeros(1, np.float32), C.c_float),
+                                  levelsup, _p(fw, C.c_int), _p(fwt, C.c_double), _p(fn, C.c_int), _p(bw, C.c_int),
+                                  _p(bv, C.c_double))
+    return dict(word=fw[:n], weight=fwt[:n], node=fn[:n], bow_word=bw[:nb].copy(), bow_value=bv[:nb].copy())

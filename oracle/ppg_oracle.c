@@ -1081,3 +1081,84 @@ void ppgo_check_in_frustum_all(const ppgo_cfg *c, const float *Rcw, const float 
         view_cos[j] = o[3];
     }
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* DBoW3::Vocabulary::transform(features, BowVector&, FeatureVector&, levelsup) as called from  */
+/* Frame::ComputeBoW (map/src/Frame.cpp:331-340, levelsup = 4) and KeyFrame construction        */
+/* (:127-131).  DBoW3 is a third-party dependency (find_package(DBoW3), CMakeLists.txt:18,      */
+/* unpinned, not under /root/reference); this restates its published algorithm:                  */
+/*   per feature: descend from the root, at every level take the child with the least           */
+/*     DescManip::distance = sum_i (float)((a_i - b_i) * (a_i - b_i)) accumulated in double in   */
+/*     index order, strict < so the first child wins ties; word = leaf's word id, weight = leaf's */
+/*     weight; node for the FeatureVector = the node reached at level L - levelsup, or the root   */
+/*     (0) when that level is <= 0 (the reference: L = 3, levelsup = 4 -> always the root);        */
+/*   BowVector: features with weight > 0 add their weight to their word (std::map, accumulated in */
+/*     feature order), then normalize: L1 (scoring 0, 2, 3, 4), L2 (scoring 1) over the words in  */
+/*     ascending id, or no norm (scoring 5, DOT_PRODUCT): every value divided by the word count.  */
+/* Weighting TF_IDF (0) / TF (1) only (IDF / BINARY use addIfNotExist).  "Parity unpinned": no    */
+/* DBoW3 here; the reference's own vocabulary files pin the file format (ppg_slam_b200/            */
+/* vocabulary.py).  Outputs: per feature word / weight / node (-1 when weight <= 0), BowVector    */
+/* as sorted (word, value) pairs -> returns their number.                                         */
+/* ------------------------------------------------------------------------------------------- */
+static double bow_distance(const float *a, const float *b, int dim) {
+    double sqd = 0.;
+    for (int i = 0; i < dim; i++) sqd += (a[i] - b[i]) * (a[i] - b[i]); /* float product, double sum */
+    return sqd;
+}
+
+int ppgo_bow_transform(int k, int L, int scoring, const int *children, const double *node_weight,
+                       const int *node_word, const float *node_desc, int dim, int n, const float *feat, int levelsup,
+                       int *f_word, double *f_weight, int *f_node, int *bow_word, double *bow_value) {
+    const int nid_level = L - levelsup;
+    int nb = 0;
+    for (int i = 0; i < n; i++) {
+        int final_id = 0, current_level = 0, nid = 0;
+        do {
+            ++current_level;
+            double best_d = 1.7976931348623157e308;
+            const int *ch = children + (size_t)final_id * k;
+            int next = final_id;
+            for (int c = 0; c < k && ch[c] >= 0; c++) {
+                double d = bow_distance(feat + (size_t)i * dim, node_desc + (size_t)ch[c] * dim, dim);
+                if (d < best_d) {
+                    best_d = d;
+                    next = ch[c];
+                }
+            }
+            final_id = next;
+            if (current_level == nid_level) nid = final_id;
+        } while (children[(size_t)final_id * k] >= 0);
+        f_word[i] = node_word[final_id];
+        f_weight[i] = node_weight[final_id];
+        f_node[i] = f_weight[i] > 0 ? nid : -1;
+        if (f_weight[i] > 0) { /* v.addWeight(id, w) */
+            int lo = 0;
+            while (lo < nb && bow_word[lo] < f_word[i]) lo++;
+            if (lo < nb && bow_word[lo] == f_word[i])
+                bow_value[lo] += f_weight[i];
+            else {
+                memmove(bow_word + lo + 1, bow_word + lo, sizeof(int) * (nb - lo));
+                memmove(bow_value + lo + 1, bow_value + lo, sizeof(double) * (nb - lo));
+                bow_word[lo] = f_word[i];
+                bow_value[lo] = f_weight[i];
+                nb++;
+            }
+        }
+    }
+    if (nb > 0) {
+        if (scoring == 5) { /* !mustNormalize */
+            const double nd = (double)nb;
+            for (int j = 0; j < nb; j++) bow_value[j] /= nd;
+        } else {
+            double norm = 0.0;
+            if (scoring == 1) {
+                for (int j = 0; j < nb; j++) norm += bow_value[j] * bow_value[j];
+                norm = sqrt(norm);
+            } else
+                for (int j = 0; j < nb; j++) norm += fabs(bow_value[j]);
+            if (norm > 0.0)
+                for (int j = 0; j < nb; j++) bow_value[j] /= norm;
+        }
+    }
+    return nb;
+}

@@ -84,6 +84,18 @@ class ExtendOut(C.Structure):
                 ("n_rescans", C.c_int), ("diag", C.c_int * 8)]
 
 
+class VocabularyPod(C.Structure):
+    _fields_ = [("k", C.c_int), ("L", C.c_int), ("scoring", C.c_int), ("weighting", C.c_int), ("n_nodes", C.c_int),
+                ("dim", C.c_int), ("children", C.POINTER(C.c_int32)), ("word_id", C.POINTER(C.c_int32)),
+                ("weight", C.POINTER(C.c_double)), ("desc", C.POINTER(C.c_float))]
+
+
+class BowOut(C.Structure):
+    _fields_ = [("n_features", C.c_int), ("n_bow", C.c_int), ("word_id", C.POINTER(C.c_int32)),
+                ("word_weight", C.POINTER(C.c_double)), ("node_id", C.POINTER(C.c_int32)),
+                ("bow_word", C.POINTER(C.c_int32)), ("bow_value", C.POINTER(C.c_double))]
+
+
 # every symbol include/ppg_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", "ppg_api_version", "ppg_extract",
            "ppg_upload_frames", "ppg_run", "ppg_download", "ppg_sync", "ppg_extract_from_maps", "ppg_get_maps",
@@ -93,7 +105,8 @@ SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", 
            "ppg_assoc_fetch_batch", "ppg_assoc_fallback_rows", "ppg_assoc_device_results",
            "ppg_distinctive_descriptors", "ppg_upload_map_distinctive", "ppg_stream", "ppg_upload_map_graph",
            "ppg_extend_map_matches", "ppg_extend_run_batch", "ppg_extend_fetch_batch", "ppg_upload_map_geometry",
-           "ppg_assoc_stage_poses", "ppg_frustum_fetch"]
+           "ppg_assoc_stage_poses", "ppg_frustum_fetch", "ppg_upload_vocabulary", "ppg_bow_transform",
+           "ppg_bow_run_batch", "ppg_bow_fetch_batch"]
 
 _lib = None
 
@@ -121,7 +134,8 @@ def load():
                      "ppg_assoc_run_batch", "ppg_assoc_fetch_batch", "ppg_distinctive_descriptors",
                      "ppg_upload_map_distinctive", "ppg_upload_map_graph", "ppg_extend_map_matches",
                      "ppg_extend_run_batch", "ppg_extend_fetch_batch", "ppg_upload_map_geometry",
-                     "ppg_assoc_stage_poses", "ppg_frustum_fetch"]:
+                     "ppg_assoc_stage_poses", "ppg_frustum_fetch", "ppg_upload_vocabulary", "ppg_bow_transform",
+                     "ppg_bow_run_batch", "ppg_bow_fetch_batch"]:
             getattr(lib, name).restype = C.c_int
         _lib = lib
     return _lib
@@ -470,6 +484,58 @@ class Extractor:
         self._check(self.lib.ppg_frustum_fetch(self.h, n_frames, iv.ctypes.data_as(C.POINTER(C.c_uint8)), _fp(uv),
                                                _fp(dp), _fp(vc)))
         return dict(in_view=iv, proj_uv=uv, depth=dp, view_cos=vc)
+
+    # ---- bag of words: DBoW3::Vocabulary::transform (Frame::ComputeBoW, map/src/Frame.cpp:331-340)
+    def upload_vocabulary(self, voc):
+        """voc: ppg_slam_b200.vocabulary.PodVocabulary / Vocabulary (k, L, scoring, weighting, child_table(), ...)."""
+        ch = np.ascontiguousarray(voc.child_table(), np.int32)
+        wid = np.ascontiguousarray(voc.word_id, np.int32)
+        w = np.ascontiguousarray(voc.weight, np.float64)
+        d = np.ascontiguousarray(voc.desc, np.float32)
+        v = VocabularyPod()
+        v.k, v.L, v.scoring, v.weighting, v.n_nodes, v.dim = voc.k, voc.L, voc.scoring, voc.weighting, ch.shape[0], d.shape[1]
+        v.children = ch.ctypes.data_as(C.POINTER(C.c_int32))
+        v.word_id = wid.ctypes.data_as(C.POINTER(C.c_int32))
+        v.weight = w.ctypes.data_as(C.POINTER(C.c_double))
+        v.desc = _fp(d)
+        self._check(self.lib.ppg_upload_vocabulary(self.h, C.byref(v)))
+
+    @staticmethod
+    def _bow_out(cap):
+        r = dict(word=np.zeros(cap, np.int32), weight=np.zeros(cap, np.float64), node=np.zeros(cap, np.int32),
+                 bow_word=np.zeros(cap, np.int32), bow_value=np.zeros(cap, np.float64))
+        o = BowOut()
+        o.word_id = r["word"].ctypes.data_as(C.POINTER(C.c_int32))
+        o.word_weight = r["weight"].ctypes.data_as(C.POINTER(C.c_double))
+        o.node_id = r["node"].ctypes.data_as(C.POINTER(C.c_int32))
+        o.bow_word = r["bow_word"].ctypes.data_as(C.POINTER(C.c_int32))
+        o.bow_value = r["bow_value"].ctypes.data_as(C.POINTER(C.c_double))
+        return o, r
+
+    @staticmethod
+    def _bow_result(o, r):
+        n, nb = o.n_features, o.n_bow
+        return dict(word=r["word"][:n].copy(), weight=r["weight"][:n].copy(), node=r["node"][:n].copy(),
+                    bow_word=r["bow_word"][:nb].copy(), bow_value=r["bow_value"][:nb].copy())
+
+    def bow_transform(self, desc, levelsup=4):
+        d = np.ascontiguousarray(desc, np.float32).reshape(-1, 256)
+        o, r = self._bow_out(max(len(d), 1))
+        self._check(self.lib.ppg_bow_transform(self.h, _fp(d), len(d), levelsup, C.byref(o)))
+        return self._bow_result(o, r)
+
+    def bow_run_batch(self, n_frames, levelsup=4):
+        self._check(self.lib.ppg_bow_run_batch(self.h, n_frames, levelsup))
+
+    def bow_fetch_batch(self, n_frames):
+        outs = (BowOut * n_frames)()
+        res = []
+        for f in range(n_frames):
+            o, r = self._bow_out(1024)
+            outs[f] = o
+            res.append(r)
+        self._check(self.lib.ppg_bow_fetch_batch(self.h, n_frames, outs))
+        return [self._bow_result(outs[f], res[f]) for f in range(n_frames)]
 
     def distinctive_descriptors(self, desc, offsets, to_table=False):
         """MapPoint::ComputeDistinctiveDescriptors for a batch of map points (packed observation descriptors +

@@ -389,6 +389,7 @@ void ppg_destroy(ppg_ctx* c) {
     if (c->st2) cudaStreamDestroy(c->st2);
     if (c->st3) cudaStreamDestroy(c->st3);
     assoc_destroy(c);
+    bow_destroy(c);
     for (auto& l : c->tc) {
         cudaFree(l.w);
         cudaFree(l.bias);

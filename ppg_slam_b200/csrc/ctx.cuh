@@ -26,6 +26,7 @@ struct TcLayerInfo {
 };
 
 struct AssocState;  // assoc.cu
+struct BowState;    // bow.cu
 
 }  // namespace ppg
 
@@ -84,12 +85,14 @@ struct ppg_ctx {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
 
     ppg::AssocState* assoc = nullptr;
+    ppg::BowState* bow = nullptr;
 };
 
 namespace ppg {
 int set_err(const ppg_ctx* c, int code, const std::string& msg);
 int cuda_fail(const ppg_ctx* c, cudaError_t e, const char* what);
 void assoc_destroy(ppg_ctx* c);
+void bow_destroy(ppg_ctx* c);
 // profiling runs: records a CUDA event named after the stage that just ended on the ctx stream (api.cu)
 void stage_mark(ppg_ctx* c, const char* name);
 }  // namespace ppg

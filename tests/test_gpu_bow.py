@@ -1,0 +1,74 @@
+"""GPU parity of the bag-of-words transform (DBoW3::Vocabulary::transform as Frame::ComputeBoW calls it,
+map/src/Frame.cpp:331-340) against the CPU restatement: word / weight / FeatureVector node of every feature and the
+BowVector (keys and double values) bit for bit -- on the reference's own EuRoC vocabulary and on synthetic trees."""
+import os
+
+import numpy as np
+import pytest
+
+from ppg_slam_b200 import cameras, synth, vocabulary
+
+pytestmark = pytest.mark.gpu
+WEIGHTS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ppg_slam_b200", "weights")
+
+
+def _same(got, ref):
+    np.testing.assert_array_equal(got["word"], ref["word"])
+    np.testing.assert_array_equal(got["weight"].view(np.uint64), ref["weight"].view(np.uint64))
+    np.testing.assert_array_equal(got["node"], ref["node"])
+    np.testing.assert_array_equal(got["bow_word"], ref["bow_word"])
+    np.testing.assert_array_equal(got["bow_value"].view(np.uint64), ref["bow_value"].view(np.uint64))
+
+
+@pytest.mark.parametrize("name,levelsup,n", [("euroc", 4, 500), ("tum", 4, 357), ("euroc", 2, 500), ("k4L2-l1", 1, 200),
+                                              ("k3L4-dot", 2, 1000), ("k32L1", 0, 64)])
+def test_bow_transform_equals_oracle(name, levelsup, n):
+    from oracle import post_ref as O
+    from ppg_slam_b200 import capi
+    if name in ("euroc", "tum"):
+        voc = vocabulary.load_blob(os.path.join(WEIGHTS, "voc_%s_9x3.bin" % name))
+    elif name == "k4L2-l1":
+        voc = vocabulary.random_vocabulary(1, 4, 2, scoring=0, zero_weight_frac=0.3)
+    elif name == "k3L4-dot":
+        voc = vocabulary.random_vocabulary(2, 3, 4, scoring=5, zero_weight_frac=0.3)
+    else:
+        voc = vocabulary.random_vocabulary(3, 32, 1, scoring=1, zero_weight_frac=0.2)
+    rs = np.random.RandomState(7)
+    # descriptors near the vocabulary's own nodes (so that many words are hit) plus pure noise
+    leaves = np.nonzero(voc.word_id >= 0)[0]
+    feats = voc.desc[leaves[rs.randint(0, len(leaves), n)]] + rs.normal(0, 0.03, (n, 256)).astype(np.float32)
+    feats[::7] = rs.normal(size=(len(feats[::7]), 256))
+    feats = (feats / np.linalg.norm(feats, axis=1, keepdims=True)).astype(np.float32)
+    feats[3] = feats[2]
+    ref = O.bow_transform(voc, feats, levelsup)
+    e = capi.Extractor(cameras.EUROC, max_batch=1, junction_max_num=1000)
+    try:
+        e.upload_vocabulary(voc)
+        got = e.bow_transform(feats, levelsup)
+        _same(got, ref)
+        assert len(ref["bow_word"]) > 3 and len(ref["bow_word"]) < n  # words are shared, weights accumulate
+        got = e.bow_transform(feats[:0], levelsup)
+        assert len(got["word"]) == 0 and len(got["bow_word"]) == 0
+    finally:
+        e.close()
+
+
+def test_bow_batch_on_extracted_frames():
+    """Frame::ComputeBoW for every frame of an extraction batch with the descriptors left on the device."""
+    from oracle import post_ref as O
+    from ppg_slam_b200 import capi
+    cam = cameras.EUROC
+    voc = vocabulary.load_blob(os.path.join(WEIGHTS, "voc_euroc_9x3.bin"))
+    Bn = 3
+    e = capi.Extractor(cam, max_batch=Bn)
+    try:
+        recs = e.run([synth.frame(s, cam.width, cam.height) for s in range(Bn)])
+        e.upload_vocabulary(voc)
+        e.bow_run_batch(Bn, 4)
+        got = e.bow_fetch_batch(Bn)
+        for f in range(Bn):
+            ref = O.bow_transform(voc, recs[f]["desc"], 4)
+            _same(got[f], ref)
+            assert len(got[f]["word"]) == recs[f]["n_kp"] and len(ref["bow_word"]) > 20
+    finally:
+        e.close()

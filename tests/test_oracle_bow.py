@@ -1,0 +1,113 @@
+"""Known-answer tests of the bag-of-words path: the vocabulary reader against the reference's own files (when the
+reference tree is present) and against the committed blobs, and the transform oracle (oracle/ppg_oracle.c::
+ppgo_bow_transform) against a restatement of DBoW3::Vocabulary::transform written the way DBoW3 is (std::map ->
+dict kept sorted, per-feature descent, BowVector::normalize)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import post_ref as O
+from ppg_slam_b200 import vocabulary
+
+WEIGHTS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ppg_slam_b200", "weights")
+REF_VOC = "/root/reference/Vocabulary"
+
+
+def py_transform(voc, feats, levelsup):
+    ch = voc.child_table()
+    nid_level = voc.L - levelsup
+    bow, fv = {}, {}
+    words, weights = [], []
+    for i, f in enumerate(feats):
+        final_id, level, nid = 0, 0, 0
+        while True:
+            level += 1
+            best = float("inf")
+            nodes = [c for c in ch[final_id] if c >= 0]
+            for c in nodes:
+                diff = (f - voc.desc[c]).astype(np.float32)
+                sq = (diff * diff).astype(np.float32)
+                d = 0.0
+                for x in sq:  # double accumulation in index order
+                    d += float(x)
+                if d < best:
+                    best, final_id = d, c
+            if level == nid_level:
+                nid = final_id
+            if ch[final_id][0] < 0:
+                break
+        w = float(voc.weight[final_id])
+        words.append(int(voc.word_id[final_id]))
+        weights.append(w)
+        if w > 0:
+            bow[words[-1]] = bow.get(words[-1], 0.0) + w
+            fv.setdefault(nid, []).append(i)
+    keys = sorted(bow)
+    vals = [bow[k] for k in keys]
+    if keys:
+        if voc.scoring == 5:
+            vals = [v / float(len(keys)) for v in vals]
+        else:
+            norm = 0.0
+            if voc.scoring == 1:
+                for v in vals:
+                    norm += v * v
+                norm = math.sqrt(norm)
+            else:
+                for v in vals:
+                    norm += abs(v)
+            if norm > 0:
+                vals = [v / norm for v in vals]
+    return words, weights, keys, vals, fv
+
+
+@pytest.mark.parametrize("k,L,scoring,levelsup", [(9, 3, 1, 4), (4, 2, 0, 1), (3, 4, 5, 2), (9, 3, 1, 2)])
+def test_bow_transform_kat(k, L, scoring, levelsup):
+    voc = vocabulary.random_vocabulary(k * 10 + L, k, L, scoring=scoring)
+    rs = np.random.RandomState(1)
+    feats = rs.normal(size=(70, 256)).astype(np.float32)
+    feats /= np.linalg.norm(feats, axis=1, keepdims=True)
+    feats[5] = feats[4]  # two features in the same word: weights accumulate
+    got = O.bow_transform(voc, feats, levelsup)
+    words, weights, keys, vals, fv = py_transform(voc, feats, levelsup)
+    assert got["word"].tolist() == words
+    assert got["weight"].tolist() == weights
+    assert got["bow_word"].tolist() == keys
+    assert got["bow_value"].tolist() == vals  # bit-exact doubles
+    want_node = np.full(len(feats), -1)
+    for nid, idx in fv.items():
+        want_node[idx] = nid
+    assert got["node"].tolist() == want_node.tolist()
+    assert len(keys) >= 2 and len(set(words)) < len(words)  # shared words accumulate
+
+
+def test_committed_vocabulary_blobs_are_the_reference_files():
+    for name in ("voc_euroc_9x3", "voc_tum_9x3"):
+        b = vocabulary.load_blob(os.path.join(WEIGHTS, name + ".bin"))
+        assert (b.k, b.L, b.scoring, b.weighting, b.n_nodes, b.n_words) == (9, 3, 1, 0, 820, 729)
+        nch = (b.children >= 0).sum(1)
+        assert sorted(set(nch.tolist())) == [0, 9] and (nch == 9).sum() == 91
+        assert sorted(b.word_id[b.word_id >= 0].tolist()) == list(range(729))
+        assert ((b.word_id >= 0) == (nch == 0)).all()  # words are exactly the leaves
+        src = os.path.join(REF_VOC, name + ".gz")
+        if os.path.exists(src):  # in the build container: the blob is a faithful export of the reference file
+            v = vocabulary.Vocabulary(src)
+            np.testing.assert_array_equal(v.child_table(), b.children)
+            np.testing.assert_array_equal(v.word_id, b.word_id)
+            np.testing.assert_array_equal(v.weight, b.weight)
+            np.testing.assert_array_equal(v.desc, b.desc)
+
+
+def test_real_vocabulary_transform_is_consistent():
+    """On the reference's EuRoC vocabulary: every feature lands on a leaf, levelsup = 4 puts all features with a
+    positive weight under the root (L = 3), the BowVector has unit L2 norm."""
+    voc = vocabulary.load_blob(os.path.join(WEIGHTS, "voc_euroc_9x3.bin"))
+    rs = np.random.RandomState(3)
+    feats = voc.desc[rs.randint(91, 820, 200)] + rs.normal(0, 0.02, (200, 256)).astype(np.float32)
+    got = O.bow_transform(voc, feats.astype(np.float32), 4)
+    assert (got["word"] >= 0).all() and (got["word"] < 729).all()
+    assert set(got["node"].tolist()) <= {0, -1}
+    assert abs(np.sqrt((got["bow_value"] ** 2).sum()) - 1.0) < 1e-12
+    assert (np.diff(got["bow_word"]) > 0).all()
