@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PPG_API_VERSION 3
+#define PPG_API_VERSION 4
 #define PPG_DESC_DIM 256 /* PPGExtractor::DESC_DIM_SIZE, PPGExtractor.cpp:44 */
 
 typedef enum {
@@ -175,6 +175,8 @@ typedef struct {
     int mode;                /* PPG_SEARCH_EXTEND_MAP (0) or PPG_SEARCH_WINDOW (1), see below */
     float max_dist;          /* mode 1: accept iff best_dist <= max_dist */
     double e2_max;           /* mode 1: > 0 -> candidates with ex*ex + ey*ey > e2_max are skipped */
+    const int32_t* row_node; /* mode 2: M, FeatureVector node of every row's feature (-1 = not listed) */
+    const int32_t* kp_node;  /* mode 2: N, FeatureVector node of every frame feature (ppg_bow_out.node_id) */
 } ppg_assoc_in;
 
 /* Search rules.  The window walk (Frame/KeyFrame::GetFeaturesInArea), the free mask, DescriptorDistance and the
@@ -192,8 +194,16 @@ typedef struct {
  *                            Fuse(KF, Scw, vpPoints, th, vpReplacePoint)        :1038-1135  max_dist = TH_LOW
  *                            SearchBySim3(KF1, KF2, vpMatches12, S12, th)       :1149-1335  both directions,
  *                                                                               max_dist = TH_HIGH, free_mask all ones
- *                          view_cos is ignored. */
-enum { PPG_SEARCH_EXTEND_MAP = 0, PPG_SEARCH_WINDOW = 1 };
+ *                          view_cos is ignored.
+ *   PPG_SEARCH_NODE        the bag-of-words matchers: candidates = the frame features of the row's vocabulary node
+ *                          (FeatureVector, ppg_bow_transform) in ascending index, no window (proj_uv / view_cos / th
+ *                          unused, kp_x / kp_y may be zeros), accept = best <= max_dist && best < ratio * second
+ *                            SearchByBoW(KF, F, vpMapPointMatches)              :393-477    rows = the keyframe's features
+ *                                                                               that hold a good map point, max_dist = TH_LOW,
+ *                                                                               free_mask = !vpMapPointMatches[idx]
+ *                            SearchByBoW(KF1, KF2, vpMatches12)                 :663-754    max_dist = TH_LOW,
+ *                                                                               free_mask = !vbMatched2[idx] && map point good */
+enum { PPG_SEARCH_EXTEND_MAP = 0, PPG_SEARCH_WINDOW = 1, PPG_SEARCH_NODE = 2 };
 
 typedef struct {       /* caller-allocated host arrays of n_rows */
     int32_t* best_idx;   /* -1 when the window is empty */

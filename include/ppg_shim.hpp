@@ -10,6 +10,7 @@
 #pragma once
 #include <cstring>
 #include <stdexcept>
+#include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -232,6 +233,27 @@ inline SearchResult search_window(ppg_ctx* ctx, FrameLike& F, const std::vector<
     upload_map_descriptors(ctx, mps);
     check(ppg_associate(ctx, &in, &out), ctx, "ppg_associate");
     return r;
+}
+
+// Frame::ComputeBoW (map/src/Frame.cpp:331-340): mpVoc->transform(descriptors, mBowVec, mFeatVec, 4) on the GPU.  The
+// vocabulary is uploaded once (ppg_upload_vocabulary, from the blob tools/export_vocabulary.py writes next to the .gz).
+// `FrameLike` is Frame or KeyFrame (mDescriptors, mBowVec, mFeatVec).
+template <class FrameLike>
+inline void compute_bow(ppg_ctx* ctx, FrameLike& F, int levelsup = 4) {
+    if (!F.mBowVec.empty()) return;
+    const int N = F.mDescriptors.rows;
+    std::vector<int32_t> word(N > 0 ? N : 1), node(N > 0 ? N : 1), bword(N > 0 ? N : 1);
+    std::vector<double> weight(N > 0 ? N : 1), bval(N > 0 ? N : 1);
+    ppg_bow_out out{};
+    out.word_id = word.data();
+    out.word_weight = weight.data();
+    out.node_id = node.data();
+    out.bow_word = bword.data();
+    out.bow_value = bval.data();
+    check(ppg_bow_transform(ctx, F.mDescriptors.template ptr<float>(0), N, levelsup, &out), ctx, "ppg_bow_transform");
+    for (int j = 0; j < out.n_bow; j++) F.mBowVec[(unsigned int)bword[j]] = bval[j];          // BowVector = map<WordId, WordValue>
+    for (int i = 0; i < out.n_features; i++)
+        if (node[i] >= 0) F.mFeatVec[(unsigned int)node[i]].push_back((unsigned int)i);       // FeatureVector::addFeature
 }
 
 // The whole Matcher::ExtendMapMatches (matching/src/Matcher.cpp:203-381) in one GPU call: window search with the live

@@ -305,3 +305,19 @@ def bow_transform(voc, feat, levelsup=4):
                                   levelsup, _p(fw, C.c_int), _p(fwt, C.c_double), _p(fn, C.c_int), _p(bw, C.c_int),
                                   _p(bv, C.c_double))
     return dict(word=fw[:n], weight=fwt[:n], node=fn[:n], bow_word=bw[:nb].copy(), bow_value=bv[:nb].copy())
+
+
+def search_node_all(frame_desc, free_mask, kp_node, row_desc, row_node, ratio, max_dist):
+    """Frozen-state search core of Matcher::SearchByBoW (Matcher.cpp:421-461 / :700-740): candidates = frame
+    features of the row's FeatureVector node.  -> dict(best_idx, second_idx, best_d, second_d, accept)."""
+    frame_desc, row_desc = f32(frame_desc), f32(row_desc)
+    free_mask = np.ascontiguousarray(free_mask, np.uint8)
+    kp_node, row_node = np.ascontiguousarray(kp_node, np.int32), np.ascontiguousarray(row_node, np.int32)
+    n, m = len(kp_node), len(row_node)
+    bi, si = np.zeros(m, np.int32), np.zeros(m, np.int32)
+    bd, sd = np.zeros(m, np.float32), np.zeros(m, np.float32)
+    acc = np.zeros(m, np.uint8)
+    lib().ppgo_search_node_all(n, _p(frame_desc, C.c_float), _p(free_mask, C.c_uint8), _p(kp_node, C.c_int), m,
+                               _p(row_desc, C.c_float), _p(row_node, C.c_int), C.c_float(ratio), C.c_float(max_dist),
+                               _p(bi, C.c_int), _p(si, C.c_int), _p(bd, C.c_float), _p(sd, C.c_float), _p(acc, C.c_uint8))
+    return dict(best_idx=bi, second_idx=si, best_d=bd, second_d=sd, accept=acc)

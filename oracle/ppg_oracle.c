@@ -1162,3 +1162,44 @@ int ppgo_bow_transform(int k, int L, int scoring, const int *children, const dou
     }
     return nb;
 }
+
+/* Search core of the bag-of-words matchers for one keyframe feature with the frame state frozen:
+ * Matcher::SearchByBoW(KF, F, ...) matching/src/Matcher.cpp:393-477 (inner loop :421-461) and SearchByBoW(KF1, KF2)
+ * :663-754.  Candidates = the frame features listed under the same FeatureVector node, in ascending index (vIndicesF
+ * is filled in feature order), skipped when free_mask[idx] == 0 (:434 / :707-711); best / second by strict <;
+ * accept = best <= max_dist && best < ratio * second (:456-458). */
+int ppgo_search_node_core(int n, const float *frame_desc, const uint8_t *free_mask, const int *kp_node,
+                          const float *row_desc, int row_node, float ratio, float max_dist, int *best_idx,
+                          int *second_idx, float *best_d, float *second_d) {
+    float bestDist1 = 1e6f, bestDist2 = 1e6f;
+    int bestIdxF = -1, bestIdx2 = -1;
+    if (row_node >= 0)
+        for (int idx = 0; idx < n; idx++) {
+            if (kp_node[idx] != row_node || !free_mask[idx]) continue;
+            float dist = ppgo_descriptor_distance(row_desc, frame_desc + (size_t)idx * 256, 256);
+            if (dist < bestDist1) {
+                bestDist2 = bestDist1;
+                bestIdx2 = bestIdxF;
+                bestDist1 = dist;
+                bestIdxF = idx;
+            } else if (dist < bestDist2) {
+                bestDist2 = dist;
+                bestIdx2 = idx;
+            }
+        }
+    *best_idx = bestIdxF;
+    *second_idx = bestIdx2;
+    *best_d = bestDist1;
+    *second_d = bestDist2;
+    if (bestIdxF < 0) return 0;
+    return (bestDist1 <= max_dist && bestDist1 < ratio * bestDist2) ? 1 : 0;
+}
+
+void ppgo_search_node_all(int n, const float *frame_desc, const uint8_t *free_mask, const int *kp_node, int m,
+                          const float *row_desc, const int *row_node, float ratio, float max_dist, int *best_idx,
+                          int *second_idx, float *best_d, float *second_d, uint8_t *accept) {
+    for (int j = 0; j < m; j++)
+        accept[j] = (uint8_t)ppgo_search_node_core(n, frame_desc, free_mask, kp_node, row_desc + (size_t)j * 256,
+                                                   row_node[j], ratio, max_dist, &best_idx[j], &second_idx[j],
+                                                   &best_d[j], &second_d[j]);
+}

@@ -49,10 +49,11 @@ class AssocIn(C.Structure):
     _fields_ = [("n_kp", C.c_int), ("kp_x", C.POINTER(C.c_float)), ("kp_y", C.POINTER(C.c_float)),
                 ("frame_desc", C.POINTER(C.c_float)), ("free_mask", C.POINTER(C.c_uint8)), ("n_rows", C.c_int),
                 ("proj_uv", C.POINTER(C.c_float)), ("view_cos", C.POINTER(C.c_float)), ("th", C.c_float),
-                ("ratio", C.c_float), ("mode", C.c_int), ("max_dist", C.c_float), ("e2_max", C.c_double)]
+                ("ratio", C.c_float), ("mode", C.c_int), ("max_dist", C.c_float), ("e2_max", C.c_double),
+                ("row_node", C.POINTER(C.c_int32)), ("kp_node", C.POINTER(C.c_int32))]
 
 
-SEARCH_EXTEND_MAP, SEARCH_WINDOW = 0, 1
+SEARCH_EXTEND_MAP, SEARCH_WINDOW, SEARCH_NODE = 0, 1, 2
 
 
 class AssocOut(C.Structure):
@@ -303,7 +304,7 @@ class Extractor:
         self._n_rows = m.shape[0]
 
     def _assoc_in(self, kp_x, kp_y, frame_desc, free_mask, proj_uv, view_cos, th, ratio, mode=0, max_dist=0.0,
-                  e2_max=0.0):
+                  e2_max=0.0, row_node=None, kp_node=None):
         a = AssocIn()
         keep = [np.ascontiguousarray(kp_x, np.float32), np.ascontiguousarray(kp_y, np.float32),
                 np.ascontiguousarray(frame_desc, np.float32), np.ascontiguousarray(free_mask, np.uint8),
@@ -315,6 +316,10 @@ class Extractor:
         a.proj_uv, a.view_cos = _fp(keep[4]), _fp(keep[5])
         a.th, a.ratio = th, ratio
         a.mode, a.max_dist, a.e2_max = mode, max_dist, e2_max
+        if row_node is not None:
+            keep += [np.ascontiguousarray(row_node, np.int32), np.ascontiguousarray(kp_node, np.int32)]
+            a.row_node = keep[-2].ctypes.data_as(C.POINTER(C.c_int32))
+            a.kp_node = keep[-1].ctypes.data_as(C.POINTER(C.c_int32))
         return a, keep
 
     @staticmethod
@@ -329,11 +334,11 @@ class Extractor:
         return o, r
 
     def associate(self, kp_x, kp_y, frame_desc, free_mask, proj_uv, view_cos, th, ratio, mode=0, max_dist=0.0,
-                  e2_max=0.0):
+                  e2_max=0.0, row_node=None, kp_node=None):
         """mode 0: search core of ExtendMapMatches; mode 1 (SEARCH_WINDOW): best-only cores of SearchByProjection /
         Fuse -- r = th, accept = best <= max_dist, optional circular limit e2_max (include/ppg_b200.h)."""
         a, keep = self._assoc_in(kp_x, kp_y, frame_desc, free_mask, proj_uv, view_cos, th, ratio, mode, max_dist,
-                                 e2_max)
+                                 e2_max, row_node, kp_node)
         o, r = self._assoc_out(a.n_rows)
         self._check(self.lib.ppg_associate(self.h, C.byref(a), C.byref(o)))
         return r

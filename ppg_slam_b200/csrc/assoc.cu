@@ -486,7 +486,9 @@ struct RescoreParams {
     int mode;         // 0: ExtendMapMatches rule, 1: best <= max_dist
     float max_dist;
     double e2_max;
-    int force_exact;  // 1: ignore the GEMM candidates and score every window exactly (validation)
+    int force_exact;  // 1: ignore the GEMM candidates and score every window exactly (validation, node mode)
+    const int* row_node;  // mode 2 (SearchByBoW): vocabulary node of every row / keypoint, candidates = same node
+    const int* kp_node;
     int *best_idx, *second_idx;
     float *best_d, *second_d;
     uint8_t* accept;
@@ -541,16 +543,23 @@ __global__ void __launch_bounds__(256) assoc_rescore_kernel(const RescoreParams 
         const float* kx = p.src.kx_of(f);
         const float* ky = p.src.ky_of(f);
         const uint32_t* kinfo = p.kinfo + (size_t)f * p.ncap;
+        const int my_node = p.mode == 2 ? p.row_node[row] : -1;
+        const uint8_t* freem = p.src.free_of(f);
         for (int c0 = 0; c0 < n; c0 += 32) {
             const int c = c0 + lane;
             bool in = false;
-            if (c < n) in = in_window(rp, kinfo[c], kx[c], ky[c], p.e2_max);
+            if (c < n) {
+                if (p.mode == 2)  // features of the same vocabulary node, in vIndicesF order (Matcher.cpp:432-437)
+                    in = my_node >= 0 && p.kp_node[c] == my_node && freem[c] != 0;
+                else
+                    in = in_window(rp, kinfo[c], kx[c], ky[c], p.e2_max);
+            }
             unsigned mask = __ballot_sync(AFULL, in);
             while (mask) {
                 const int cc = c0 + __ffs(mask) - 1;
                 mask &= mask - 1;
                 const float d = exact_distance(a, fdesc + (size_t)cc * 256, lane);
-                top2_update(d, korder[cc], cc, b1, o1, i1, b2, o2, i2);
+                top2_update(d, p.mode == 2 ? (uint32_t)cc : korder[cc], cc, b1, o1, i1, b2, o2, i2);
             }
         }
     }
@@ -561,7 +570,9 @@ __global__ void __launch_bounds__(256) assoc_rescore_kernel(const RescoreParams 
         p.second_d[o] = b2;
         uint8_t acc = 0;
         if (i1 >= 0) {
-            if (p.mode == 1)
+            if (p.mode == 2)
+                acc = b1 <= p.max_dist && b1 < p.ratio * b2;  // Matcher.cpp:456-458, :733-735
+            else if (p.mode == 1)
                 acc = b1 <= p.max_dist;  // Matcher.cpp:78, :1399, :1016
             else
                 acc = !(b1 > p.th_high && b1 > p.ratio * b2);  // Matcher.cpp:276
@@ -697,6 +708,8 @@ int assoc_ensure_state(ppg_ctx* c) {
     PPG_CUDA(c, dalloc(&s->second_d, B * R));
     PPG_CUDA(c, dalloc(&s->accept, B * R));
     PPG_CUDA(c, dalloc(&s->fallback, 1));
+    PPG_CUDA(c, dalloc(&s->row_node, R));
+    PPG_CUDA(c, dalloc(&s->kp_node, N));
     PPG_CUDA(c, dalloc(&s->wpos, R * 3));
     PPG_CUDA(c, dalloc(&s->nrm, R * 3));
     PPG_CUDA(c, dalloc(&s->dmin, R));
@@ -771,7 +784,7 @@ int run_assoc(ppg_ctx* c, const FrameSrc& src, int frames, int force_exact) {
     PPG_CUDA(c, cudaMemsetAsync(s->fallback, 0, 4, c->st));
     int rc = assoc_prep(c, src, frames);
     if (rc != PPG_OK) return rc;
-    if (!force_exact) {
+    if (!force_exact && s->mode != 2) {
         GemmParams gp;
         gp.rows = rows;
         gp.max_rows = s->max_rows;
@@ -807,7 +820,9 @@ int run_assoc(ppg_ctx* c, const FrameSrc& src, int frames, int force_exact) {
     rp.mode = s->mode;
     rp.max_dist = s->max_dist;
     rp.e2_max = s->mode == 1 ? s->e2_max : 0.0;
-    rp.force_exact = force_exact;
+    rp.force_exact = (force_exact || s->mode == 2) ? 1 : 0;
+    rp.row_node = s->row_node;
+    rp.kp_node = s->kp_node;
     rp.best_idx = s->best_idx;
     rp.second_idx = s->second_idx;
     rp.best_d = s->best_d;
@@ -855,7 +870,7 @@ void assoc_destroy(ppg_ctx* c) {
     void* bufs[] = {s->map_f32, s->map_bf, s->map_n2, s->kx, s->ky, s->fdesc, s->fn2, s->free_mask, s->ones, s->f_bf,
                     s->kinfo, s->korder, s->nbmax, s->proj, s->vcos, s->rowp, s->cand, s->guard,
                     s->best_idx, s->second_idx, s->best_d, s->second_d, s->accept, s->fallback,
-                    s->wpos, s->nrm, s->dmin, s->dmax, s->poses, s->in_view, s->depth};
+                    s->wpos, s->nrm, s->dmin, s->dmax, s->poses, s->in_view, s->depth, s->row_node, s->kp_node};
     for (void* b : bufs)
         if (b) cudaFree(b);
     extend_destroy(s);
@@ -1006,7 +1021,17 @@ int ppg_assoc_stage(ppg_ctx* c, const ppg_assoc_in* in) {
     if (in->n_kp < 0 || in->n_kp > s->ncap) return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage: too many keypoints");
     if (in->mode == PPG_SEARCH_WINDOW && !in->view_cos)
         return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage: view_cos must point to n_rows floats (ignored in mode 1)");
-    if ((rc = assoc_stage_rows(c, 1, in->n_rows, in->proj_uv, in->view_cos, in->th, in->ratio)) != PPG_OK) return rc;
+    if (in->mode == PPG_SEARCH_NODE) {
+        if (!in->row_node || (in->n_kp > 0 && !in->kp_node) || in->n_rows < 1 || in->n_rows > s->n_rows)
+            return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage: node mode needs row_node, kp_node and 1 <= n_rows <= uploaded rows");
+        // no projections in this mode: the row parameters are prepared from zeros and never used
+        std::vector<float> zeros((size_t)in->n_rows * 2, 0.f);
+        if ((rc = assoc_stage_rows(c, 1, in->n_rows, zeros.data(), zeros.data(), in->th, in->ratio)) != PPG_OK) return rc;
+        PPG_CUDA(c, cudaMemcpyAsync(s->row_node, in->row_node, (size_t)in->n_rows * 4, cudaMemcpyHostToDevice, c->st));
+        if (in->n_kp > 0)
+            PPG_CUDA(c, cudaMemcpyAsync(s->kp_node, in->kp_node, (size_t)in->n_kp * 4, cudaMemcpyHostToDevice, c->st));
+    } else if ((rc = assoc_stage_rows(c, 1, in->n_rows, in->proj_uv, in->view_cos, in->th, in->ratio)) != PPG_OK)
+        return rc;
     if (in->n_kp > 0 && in->kp_x && in->kp_y && in->frame_desc) {
         PPG_CUDA(c, cudaMemcpyAsync(s->kx, in->kp_x, (size_t)in->n_kp * 4, cudaMemcpyHostToDevice, c->st));
         PPG_CUDA(c, cudaMemcpyAsync(s->ky, in->kp_y, (size_t)in->n_kp * 4, cudaMemcpyHostToDevice, c->st));
@@ -1018,7 +1043,7 @@ int ppg_assoc_stage(ppg_ctx* c, const ppg_assoc_in* in) {
     }
     PPG_CUDA(c, cudaStreamSynchronize(c->st));
     s->staged_n = in->n_kp;
-    if (in->mode != PPG_SEARCH_EXTEND_MAP && in->mode != PPG_SEARCH_WINDOW)
+    if (in->mode != PPG_SEARCH_EXTEND_MAP && in->mode != PPG_SEARCH_WINDOW && in->mode != PPG_SEARCH_NODE)
         return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage: unknown search mode");
     s->mode = in->mode;
     s->max_dist = in->max_dist;

@@ -72,6 +72,7 @@ struct AssocState {
     size_t h_res_bytes = 0;
     // Frame::CheckInFrustum on the device (ppg_upload_map_geometry / ppg_assoc_stage_poses): map geometry, poses,
     // mbTrackInView / mTrackDepth per (frame, row); proj and vcos above are then written by frustum_kernel
+    int *row_node = nullptr, *kp_node = nullptr;  // PPG_SEARCH_NODE: vocabulary node of every row / keypoint
     float *wpos = nullptr, *nrm = nullptr, *dmin = nullptr, *dmax = nullptr;  // [max_rows] x 3, 3, 1, 1
     float* poses = nullptr;                                                   // [bcap][16]: Rcw 9, tcw 3, Ow 3
     uint8_t* in_view = nullptr;                                               // [bcap][max_rows]

@@ -3,6 +3,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <map>
 #include <utility>
 #include <vector>
 #define CV_32FC1 5
@@ -66,6 +67,8 @@ struct MapPoint {
     cv::Mat GetDescriptor() { return cv::Mat(); }
 };
 struct Frame {
+    std::map<unsigned int, double> mBowVec;                      // DBoW3::BowVector
+    std::map<unsigned int, std::vector<unsigned int>> mFeatVec;  // DBoW3::FeatureVector
     long unsigned int mnId;
     std::vector<KeyPointEx> mvKeysUn;
     std::vector<KeyEdge> mvKeyEdges;

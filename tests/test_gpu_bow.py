@@ -72,3 +72,38 @@ def test_bow_batch_on_extracted_frames():
             assert len(got[f]["word"]) == recs[f]["n_kp"] and len(ref["bow_word"]) > 20
     finally:
         e.close()
+
+
+def test_search_by_bow_core_equals_oracle():
+    """PPG_SEARCH_NODE: the frozen-state core of Matcher::SearchByBoW (Matcher.cpp:393-477) with the FeatureVector
+    nodes the GPU transform produced for both the keyframe's and the frame's descriptors."""
+    from oracle import post_ref as O
+    from ppg_slam_b200 import capi
+    voc = vocabulary.load_blob(os.path.join(WEIGHTS, "voc_euroc_9x3.bin"))
+    rs = np.random.RandomState(11)
+    n, m = 480, 400
+    leaves = np.nonzero(voc.word_id >= 0)[0]
+    fd = voc.desc[leaves[rs.randint(0, len(leaves), n)]] + rs.normal(0, 0.05, (n, 256)).astype(np.float32)
+    fd = (fd / np.linalg.norm(fd, axis=1, keepdims=True)).astype(np.float32)
+    kd = fd[rs.randint(0, n, m)] + rs.normal(0, 0.02, (m, 256)).astype(np.float32)
+    kd = (kd / np.linalg.norm(kd, axis=1, keepdims=True)).astype(np.float32)
+    free = (rs.rand(n) > 0.1).astype(np.uint8)
+    e = capi.Extractor(cameras.EUROC, max_batch=1, max_map_points=1024)
+    try:
+        e.upload_vocabulary(voc)
+        for levelsup in (4, 2):  # 4: everything under the root (the reference's setting), 2: level-1 nodes
+            kp_node = e.bow_transform(fd, levelsup)["node"]
+            row_node = e.bow_transform(kd, levelsup)["node"]
+            e.upload_map(kd)
+            z = np.zeros(n, np.float32)
+            got = e.associate(z, z, fd, free, np.zeros((m, 2), np.float32), np.zeros(m, np.float32), 0.0, 0.8,
+                              mode=capi.SEARCH_NODE, max_dist=0.7, row_node=row_node, kp_node=kp_node)
+            ref = O.search_node_all(fd, free, kp_node, kd, row_node, 0.8, 0.7)
+            np.testing.assert_array_equal(got["best_idx"], ref["best_idx"])
+            np.testing.assert_array_equal(got["second_idx"], ref["second_idx"])
+            np.testing.assert_array_equal(got["best_d"].view(np.uint32), ref["best_d"].view(np.uint32))
+            np.testing.assert_array_equal(got["second_d"].view(np.uint32), ref["second_d"].view(np.uint32))
+            np.testing.assert_array_equal(got["accept"], ref["accept"])
+            assert ref["accept"].sum() > 50
+    finally:
+        e.close()

@@ -111,3 +111,38 @@ def test_real_vocabulary_transform_is_consistent():
     assert set(got["node"].tolist()) <= {0, -1}
     assert abs(np.sqrt((got["bow_value"] ** 2).sum()) - 1.0) < 1e-12
     assert (np.diff(got["bow_word"]) > 0).all()
+
+
+def test_search_by_bow_core_kat():
+    """Inner loop of Matcher::SearchByBoW(KF, F) (Matcher.cpp:421-461) restated with the FeatureVector as a dict."""
+    rs = np.random.RandomState(5)
+    n, m = 150, 120
+    fd = rs.normal(size=(n, 256)).astype(np.float32)
+    fd /= np.linalg.norm(fd, axis=1, keepdims=True)
+    kd = fd[rs.randint(0, n, m)] + rs.normal(0, 0.03, (m, 256)).astype(np.float32)
+    kd = (kd / np.linalg.norm(kd, axis=1, keepdims=True)).astype(np.float32)
+    kp_node = rs.choice([-1, 0, 0, 0, 4, 7], n).astype(np.int32)
+    row_node = rs.choice([-1, 0, 0, 4, 7, 9], m).astype(np.int32)
+    free = (rs.rand(n) > 0.15).astype(np.uint8)
+    got = O.search_node_all(fd, free, kp_node, kd, row_node, 0.8, 0.7)
+    fv = {}
+    for i, nd in enumerate(kp_node.tolist()):
+        if nd >= 0:
+            fv.setdefault(nd, []).append(i)
+    n_acc = 0
+    for j in range(m):
+        best1, best2, bi = 1e6, 1e6, -1
+        for idx in fv.get(int(row_node[j]), []) if row_node[j] >= 0 else []:
+            if not free[idx]:
+                continue
+            d = O.descriptor_distance(kd[j], fd[idx])
+            if d < best1:
+                best2, best1, bi = best1, d, idx
+            elif d < best2:
+                best2 = d
+        acc = int(bi >= 0 and best1 <= np.float32(0.7) and best1 < float(np.float32(np.float32(0.8) * np.float32(best2))))
+        assert got["best_idx"][j] == bi and got["accept"][j] == acc
+        if bi >= 0:
+            assert got["best_d"][j] == np.float32(best1) and got["second_d"][j] == np.float32(best2)
+        n_acc += acc
+    assert n_acc > 20 and (got["best_idx"] < 0).sum() > 5

@@ -33,6 +33,17 @@ for name, fn in (("search_core_ms", e.assoc_run_batch), ("extend_map_matches_ms"
     for _ in range(10):
         fn(B)
     out[name] = e.timer_stop() / 10
+import os as _os
+from ppg_slam_b200 import vocabulary as _voc
+e.upload_vocabulary(_voc.load_blob(_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))),
+                                                  "ppg_slam_b200", "weights", "voc_euroc_9x3.bin")))
+for _ in range(3):
+    e.bow_run_batch(B, 4)
+e.sync()
+e.timer_start()
+for _ in range(10):
+    e.bow_run_batch(B, 4)
+out["bow_transform_ms"] = e.timer_stop() / 10
 got = e.extend_fetch_batch(B)
 out["accepted_per_frame"] = float(np.mean([g["n_accepted"] for g in got]))
 out["grown_per_frame"] = float(np.mean([g["n_grown"] for g in got]))
