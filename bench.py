@@ -475,8 +475,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--map-rows", type=int, default=MAP_ROWS)
-    ap.add_argument("--dev-streams", type=int, default=3, help="contexts in flight in the device-timed arm")
-    ap.add_argument("--e2e-streams", type=int, default=4, help="contexts (host threads) in flight in the e2e arm")
+    ap.add_argument("--dev-streams", type=int, default=4, help="contexts in flight in the device-timed arm")
+    ap.add_argument("--e2e-streams", type=int, default=5, help="contexts (host threads) in flight in the e2e arm")
     ap.add_argument("--assoc", default="extend", choices=["extend", "core"],
                     help="extend: the whole Matcher::ExtendMapMatches on the GPU (default); core: its search core only")
     ap.add_argument("--frustum", action="store_true",

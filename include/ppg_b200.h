@@ -326,7 +326,8 @@ typedef struct {        /* caller-allocated */
     int n_grown;        /* map points matched by seed growing (diagnostic) */
     int n_rescans;      /* rows whose stored candidate list had to be rebuilt from the whole window (diagnostic) */
     int diag[8];        /* walk kernel: [0] evaluation rounds, [1..5] SM clock cycles / 16 of setup, chunk loads,
-                           evaluation, event handling, seed growing; [6] seeds popped */
+                           evaluation, event handling, seed growing; [6] seeds popped; [7] cycles / 16 of the weight matrices
+                           (part of seed growing) */
 } ppg_extend_out;
 
 /* One frame, everything in host memory; synchronous. */

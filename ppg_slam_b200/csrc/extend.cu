@@ -36,7 +36,7 @@
 namespace ppg {
 
 constexpr int X_LIST = 32;                           // window candidates stored per row
-constexpr int X_PRE = 4;                             // map edges of a row preloaded with its chunk
+constexpr int X_PRE = 8;                             // map edges of a row preloaded with its chunk
 constexpr int X_LCAP = PPG_EXTEND_MAX_DEGREE;        // map edges per map point / key edges per keypoint
 constexpr int X_WCAP = PPG_EXTEND_MAX_WEIGHTS;       // weight-matrix entries per seed
 constexpr int X_THREADS = 256, X_WARPS = X_THREADS / 32;
@@ -55,7 +55,7 @@ struct FrameGraphSrc {
 };
 
 enum { XR_NMATCHES = 0, XR_STATUS, XR_ACCEPTED, XR_GROWN, XR_RESCANS, XR_NKP, XR_NEDGES, XR_ROUNDS,
-       XR_T_SETUP, XR_T_CHUNK, XR_T_EVAL, XR_T_EVENT, XR_T_SEED, XR_SEEDS, XR_WORDS = 16 };  // XR_T_*: SM cycles / 16
+       XR_T_SETUP, XR_T_CHUNK, XR_T_EVAL, XR_T_EVENT, XR_T_SEED, XR_SEEDS, XR_T_WEIGHTS, XR_WORDS = 16 };  // XR_T_*: SM cycles / 16
 
 struct ExtendState {
     // map graph (shared by all frames)
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
     __syncthreads();
 
     int round = 0;
-    long long tc = clock64(), t_chunk = 0, t_eval = 0, t_event = 0, t_seed = 0;
+    long long tc = clock64(), t_chunk = 0, t_eval = 0, t_event = 0, t_seed = 0, t_weights = 0;
     if (tid == 0) S.res[XR_T_SETUP] = (int)((tc - t_begin) >> 4);
     for (int base = 0; base < p.nc; base += X_THREADS) {
         // ---- static part of the 256 rows of this chunk: my row's stored window list (thread-local, indexed
@@ -560,6 +560,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                         }
                         // weight matrix (:324-340): one warp per entry, four entries of a warp in flight
                         const int tot = nlx0 * nke;
+                        const long long tw0 = clock64();
                         for (int q0 = warp; q0 < tot; q0 += 4 * X_WARPS) {
                             float av[4][8], bv[4][8];
                             bool same[4];
@@ -589,6 +590,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                             }
                         }
                         __syncthreads();
+                        t_weights += clock64() - tw0;
                         // greedy minimum-weight assignment (:342-374), one warp.  lx.erase / ly.erase keep the order of
                         // the remaining entries, so "first minimum over the current lx x ly" = the alive entry with the
                         // least (weight, original i, original j): no list is rebuilt, rows / columns are just struck out.
@@ -615,6 +617,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                             const int my_i = lane / nke, my_j = lane - my_i * nke;
                             const float my_w = (small && lane < tot) ? S.w[lane] : 1e6f;
                             int nlx = nlx0, nly = nke;
+                            int qn_r = S.qn, nt_r = S.ntaken, freed_r = S.freed, grown_r = S.res[XR_GROWN];
                             while (nlx > 0 && nly > 0) {
                                 float bw = 1e6f;
                                 int bq = 0x7fffffff;
@@ -634,16 +637,15 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                                         }
                                     }
                                 }
-#pragma unroll
-                                for (int mm = 16; mm >= 1; mm >>= 1) {
-                                    const float ow = __shfl_xor_sync(AFULL, bw, mm);
-                                    const int oq = __shfl_xor_sync(AFULL, bq, mm);
-                                    if (ow < bw || (ow == bw && oq < bq)) {
-                                        bw = ow;
-                                        bq = oq;
-                                    }
-                                }
-                                if (bq == 0x7fffffff || bw > p.th_high) break;  // :357-358
+                                // warp argmin of (weight, q) with two hardware reductions: weights are -1 or >= 0, so
+                                // their bit patterns (shifted by one, -1 -> 0) order like the values
+                                const uint32_t wkey = bq == 0x7fffffff ? 0xffffffffu
+                                                                       : (bw < 0.f ? 0u : __float_as_uint(bw) + 1u);
+                                const uint32_t mkey = __reduce_min_sync(AFULL, wkey);
+                                if (mkey == 0xffffffffu) break;
+                                bw = mkey == 0u ? -1.f : __uint_as_float(mkey - 1u);
+                                if (bw > p.th_high) break;  // :357-358
+                                bq = (int)__reduce_min_sync(AFULL, wkey == mkey ? (uint32_t)bq : 0xffffffffu);
                                 const int mi = bq / nke, kj = bq - mi * nke;
                                 strike(ra, mi);
                                 strike(ca, kj);
@@ -653,16 +655,22 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                                     const int po = S.po[mi], ko = s_cko[ke0 + kj];
                                     if (!(trk_get(badb, po) || trk_get(trk, po))) {  // :364-365
                                         S.kpmp[ko] = po;                             // :366
-                                        const bool nocc = trk_get(obs, po);
-                                        if (S.occ[ko] && !nocc) S.freed++;  // an observed map point was overwritten
-                                        if (!S.occ[ko] && nocc && S.ntaken < X_LCAP + 2) S.taken[S.ntaken++] = (uint16_t)ko;
+                                        const bool nocc = trk_get(obs, po), wocc = S.occ[ko] != 0;
+                                        if (wocc && !nocc) freed_r++;  // an observed map point was overwritten
+                                        if (!wocc && nocc && nt_r < X_LCAP + 2) S.taken[nt_r++] = (uint16_t)ko;
                                         S.occ[ko] = nocc;
                                         kedge_me[s_cke[ke0 + kj]] = me0 + S.lxi[mi];
                                         trk_set(trk, po);
-                                        S.res[XR_GROWN]++;
-                                        if (S.qn < X_LCAP + 2) S.queue[S.qn++] = ko;
+                                        grown_r++;
+                                        if (qn_r < X_LCAP + 2) S.queue[qn_r++] = ko;
                                     }
                                 }
+                            }
+                            if (lane == 0) {  // counters kept in registers over the picks of the seed
+                                S.qn = qn_r;
+                                S.ntaken = nt_r;
+                                S.freed = freed_r;
+                                S.res[XR_GROWN] = grown_r;
                             }
                         }
                         __syncthreads();
@@ -691,6 +699,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
         S.res[XR_T_EVAL] = (int)(t_eval >> 4);
         S.res[XR_T_EVENT] = (int)(t_event >> 4);
         S.res[XR_T_SEED] = (int)(t_seed >> 4);
+        S.res[XR_T_WEIGHTS] = (int)(t_weights >> 4);
     }
     __syncthreads();
     if (tid < XR_WORDS) p.result[f * XR_WORDS + tid] = S.res[tid];
