@@ -325,9 +325,9 @@ typedef struct {        /* caller-allocated */
     int n_accepted;     /* map points accepted by the window search (diagnostic) */
     int n_grown;        /* map points matched by seed growing (diagnostic) */
     int n_rescans;      /* rows whose stored candidate list had to be rebuilt from the whole window (diagnostic) */
-    int diag[8];        /* walk kernel: [0] evaluation rounds, [1..5] SM clock cycles / 16 of setup, chunk loads,
+    int diag[9];        /* walk kernel: [0] evaluation rounds, [1..5] SM clock cycles / 16 of setup, chunk loads,
                            evaluation, event handling, seed growing; [6] seeds popped; [7] cycles / 16 of the weight matrices
-                           (part of seed growing) */
+                           (part of seed growing); [8] seeds skipped because no other endpoint of pMP was left to match */
 } ppg_extend_out;
 
 /* One frame, everything in host memory; synchronous. */

@@ -82,7 +82,7 @@ class ExtendOut(C.Structure):
     _fields_ = [("kp_mp", C.POINTER(C.c_int32)), ("kedge_me", C.POINTER(C.c_int32)),
                 ("tracked", C.POINTER(C.c_uint8)), ("nmatches", C.c_int), ("status", C.c_uint32),
                 ("n_kp", C.c_int), ("n_edges", C.c_int), ("n_accepted", C.c_int), ("n_grown", C.c_int),
-                ("n_rescans", C.c_int), ("diag", C.c_int * 8)]
+                ("n_rescans", C.c_int), ("diag", C.c_int * 9)]
 
 
 class VocabularyPod(C.Structure):

@@ -55,7 +55,8 @@ struct FrameGraphSrc {
 };
 
 enum { XR_NMATCHES = 0, XR_STATUS, XR_ACCEPTED, XR_GROWN, XR_RESCANS, XR_NKP, XR_NEDGES, XR_ROUNDS,
-       XR_T_SETUP, XR_T_CHUNK, XR_T_EVAL, XR_T_EVENT, XR_T_SEED, XR_SEEDS, XR_T_WEIGHTS, XR_WORDS = 16 };  // XR_T_*: SM cycles / 16
+       XR_T_SETUP, XR_T_CHUNK, XR_T_EVAL, XR_T_EVENT, XR_T_SEED, XR_SEEDS, XR_T_WEIGHTS, XR_SEEDS_SKIPPED,
+       XR_WORDS = 16 };  // XR_T_*: SM cycles / 16
 
 struct ExtendState {
     // map graph (shared by all frames)
@@ -554,6 +555,27 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                         if (tid == 0) S.res[XR_SEEDS]++;
                         const int ke0 = s_coff[keyID], nke = s_coff[keyID + 1] - ke0;
                         if (nke == 0) continue;  // :300-301
+                        // The assignment loop changes the frame only through map points that are neither bad nor
+                        // tracked (:364-365); once every other endpoint of pMP's edges is tracked -- the usual state
+                        // after the first seed of an event -- a seed can only strike pairs out of its own lists, so
+                        // its weight matrix and its loop are skipped altogether.  Every warp evaluates the same
+                        // shared-memory state: the decision is uniform without a barrier.
+                        {
+                            bool live = false;
+                            for (int i0 = 0; i0 < nlx0; i0 += 32) {
+                                const int i = i0 + lane;
+                                bool l = false;
+                                if (i < nlx0) {
+                                    const int po = S.po[i];
+                                    l = !(trk_get(badb, po) || trk_get(trk, po));
+                                }
+                                live |= __ballot_sync(AFULL, l) != 0u;
+                            }
+                            if (!live) {
+                                if (tid == 0) S.res[XR_SEEDS_SKIPPED]++;
+                                continue;
+                            }
+                        }
                         if (nke > X_LCAP || nlx0 * nke > X_WCAP) {
                             if (tid == 0) S.res[XR_STATUS] |= PPG_EXTEND_OVF;
                             continue;
@@ -853,7 +875,7 @@ void fill_out(const ExtendState* x, const AssocState* s, int f, ppg_extend_out* 
     o->n_accepted = r[XR_ACCEPTED];
     o->n_grown = r[XR_GROWN];
     o->n_rescans = r[XR_RESCANS];
-    for (int k = 0; k < 8; k++) o->diag[k] = r[XR_ROUNDS + k];
+    for (int k = 0; k < 9; k++) o->diag[k] = r[XR_ROUNDS + k];
     if (o->kp_mp) memcpy(o->kp_mp, x->h_kp_mp + (size_t)f * s->ncap, (size_t)o->n_kp * 4);
     if (o->kedge_me) memcpy(o->kedge_me, x->h_kedge_me + (size_t)f * x->ecap, (size_t)o->n_edges * 4);
     if (o->tracked) memcpy(o->tracked, x->h_tracked + (size_t)f * x->P, (size_t)x->P);

@@ -50,6 +50,6 @@ out["grown_per_frame"] = float(np.mean([g["n_grown"] for g in got]))
 out["rescans_per_frame"] = float(np.mean([g["n_rescans"] for g in got]))
 out["matched_keypoints_per_frame"] = float(np.mean([(g["kp_mp"] >= 0).sum() for g in got]))
 out["n_kp_frame0"] = int(r0["n_kp"])
-out["walk_diag_mean(rounds,setup,chunk,eval,event,seed cycles/16,seeds,weights cycles/16)"] = np.mean([g["diag"] for g in got], 0).round(0).tolist()
+out["walk_diag_mean(rounds,setup,chunk,eval,event,seed cycles/16,seeds,weights cycles/16,seeds skipped)"] = np.mean([g["diag"] for g in got], 0).round(0).tolist()
 out["walk_diag_frame0"] = got[0]["diag"]
 print(json.dumps(out))
