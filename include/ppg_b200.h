@@ -371,6 +371,30 @@ int ppg_bow_transform(ppg_ctx* ctx, const float* desc, int n_features, int level
 int ppg_bow_run_batch(ppg_ctx* ctx, int n_frames, int levelsup);
 int ppg_bow_fetch_batch(ppg_ctx* ctx, int n_frames, ppg_bow_out* outs);
 
+/* ---- the whole Matcher::SearchByBoW on the GPU (matching/src/Matcher.cpp:393-477 and :663-754) ------------
+ * The keyframe features that hold a good map point are the rows (their descriptors uploaded with ppg_upload_map, in
+ * the reference's visiting order: FeatureVector node ascending, then feature index -- with the reference's
+ * levelsup = 4 every feature is under the root, i.e. plain feature order); the frame / second keyframe gives its
+ * descriptors and the node of every feature (ppg_bow_out.node_id; -1 = not listed, or for SearchByBoW(KF1, KF2) a
+ * feature without a good map point, :707-711).  A row's candidates are the features of its node that no earlier row
+ * has taken (vpMapPointMatches[idx] / vbMatched2[idx], live); accept = best <= max_dist (strict = 0, :456) or
+ * best < max_dist (strict = 1, :733), and best < ratio * second.  kp_row[i] = the row matched to feature i or -1. */
+typedef struct {
+    int n_rows;
+    const int32_t* row_node;
+    int n_kp;
+    const float* frame_desc;
+    const int32_t* kp_node;
+    float ratio, max_dist;
+    int strict;
+} ppg_bow_match_in;
+typedef struct {
+    int32_t* kp_row; /* n_kp, caller-allocated */
+    int nmatches;    /* the reference's return value */
+    int n_rescans;   /* diagnostic, as in ppg_extend_out */
+} ppg_bow_match_out;
+int ppg_search_by_bow(ppg_ctx* ctx, const ppg_bow_match_in* in, ppg_bow_match_out* out);
+
 /* Device pointers of the staged association results (n_rows each), for the sharded all-gather that
  * the multi-GPU host layer issues through NCCL (ppg_slam_b200/sharded.py). */
 int ppg_assoc_device_results(ppg_ctx* ctx, void** best_idx, void** second_idx, void** best_dist, void** second_dist,

@@ -321,3 +321,14 @@ def search_node_all(frame_desc, free_mask, kp_node, row_desc, row_node, ratio, m
                                _p(row_desc, C.c_float), _p(row_node, C.c_int), C.c_float(ratio), C.c_float(max_dist),
                                _p(bi, C.c_int), _p(si, C.c_int), _p(bd, C.c_float), _p(sd, C.c_float), _p(acc, C.c_uint8))
     return dict(best_idx=bi, second_idx=si, best_d=bd, second_d=sd, accept=acc)
+
+
+def search_by_bow(frame_desc, kp_node, row_desc, row_node, ratio, max_dist, strict=False):
+    """Matcher::SearchByBoW whole (Matcher.cpp:393-477, :663-754).  -> dict(kp_row, nmatches)."""
+    frame_desc, row_desc = f32(frame_desc), f32(row_desc)
+    kp_node, row_node = np.ascontiguousarray(kp_node, np.int32), np.ascontiguousarray(row_node, np.int32)
+    kr = np.zeros(max(len(kp_node), 1), np.int32)
+    nm = lib().ppgo_search_by_bow(len(kp_node), _p(frame_desc, C.c_float), _p(kp_node, C.c_int), len(row_node),
+                                  _p(row_desc, C.c_float), _p(row_node, C.c_int), C.c_float(ratio),
+                                  C.c_float(max_dist), int(strict), _p(kr, C.c_int))
+    return dict(kp_row=kr[:len(kp_node)].copy(), nmatches=int(nm))

@@ -1203,3 +1203,43 @@ void ppgo_search_node_all(int n, const float *frame_desc, const uint8_t *free_ma
                                                    row_node[j], ratio, max_dist, &best_idx[j], &second_idx[j],
                                                    &best_d[j], &second_d[j]);
 }
+
+/* Matcher::SearchByBoW whole, matching/src/Matcher.cpp:393-477 (KF vs Frame: strict = 0, `bestDist1 <= TH_LOW`) and
+ * :663-754 (KF1 vs KF2: strict = 1, `bestDist1 < TH_LOW`).  Rows = the keyframe features that hold a good map point
+ * (the callers' `if (!pMP) continue; if (pMP->isBad()) continue;`), listed in the order the reference visits them;
+ * kp_node = FeatureVector node of every feature of the other side (-1: not listed / no good map point).  The two
+ * FeatureVector maps are walked in ascending node id; kp_row[idx] = the row matched to feature idx (vpMapPointMatches /
+ * vbMatched2), -1 otherwise.  -> nmatches. */
+int ppgo_search_by_bow(int n, const float *frame_desc, const int *kp_node, int m, const float *row_desc,
+                       const int *row_node, float ratio, float max_dist, int strict, int *kp_row) {
+    int nmatches = 0;
+    for (int i = 0; i < n; i++) kp_row[i] = -1;
+    int max_node = -1;
+    for (int j = 0; j < m; j++)
+        if (row_node[j] > max_node) max_node = row_node[j];
+    for (int node = 0; node <= max_node; node++) { /* KFit->first == Fit->first, ascending */
+        for (int j = 0; j < m; j++) {
+            if (row_node[j] != node) continue;
+            const float *dKF = row_desc + (size_t)j * 256;
+            float bestDist1 = 1e6f, bestDist2 = 1e6f;
+            int bestIdxF = -1;
+            for (int idx = 0; idx < n; idx++) {
+                if (kp_node[idx] != node) continue;
+                if (kp_row[idx] >= 0) continue; /* :434 / :707 */
+                float dist = ppgo_descriptor_distance(dKF, frame_desc + (size_t)idx * 256, 256);
+                if (dist < bestDist1) {
+                    bestDist2 = bestDist1;
+                    bestDist1 = dist;
+                    bestIdxF = idx;
+                } else if (dist < bestDist2)
+                    bestDist2 = dist;
+            }
+            if (strict ? bestDist1 < max_dist : bestDist1 <= max_dist) /* :733 / :456 */
+                if (bestDist1 < ratio * bestDist2) {
+                    kp_row[bestIdxF] = j;
+                    nmatches++;
+                }
+        }
+    }
+    return nmatches;
+}

@@ -97,6 +97,16 @@ class BowOut(C.Structure):
                 ("bow_word", C.POINTER(C.c_int32)), ("bow_value", C.POINTER(C.c_double))]
 
 
+class BowMatchIn(C.Structure):
+    _fields_ = [("n_rows", C.c_int), ("row_node", C.POINTER(C.c_int32)), ("n_kp", C.c_int),
+                ("frame_desc", C.POINTER(C.c_float)), ("kp_node", C.POINTER(C.c_int32)), ("ratio", C.c_float),
+                ("max_dist", C.c_float), ("strict", C.c_int)]
+
+
+class BowMatchOut(C.Structure):
+    _fields_ = [("kp_row", C.POINTER(C.c_int32)), ("nmatches", C.c_int), ("n_rescans", C.c_int)]
+
+
 # every symbol include/ppg_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", "ppg_api_version", "ppg_extract",
            "ppg_upload_frames", "ppg_run", "ppg_download", "ppg_sync", "ppg_extract_from_maps", "ppg_get_maps",
@@ -107,7 +117,7 @@ SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", 
            "ppg_distinctive_descriptors", "ppg_upload_map_distinctive", "ppg_stream", "ppg_upload_map_graph",
            "ppg_extend_map_matches", "ppg_extend_run_batch", "ppg_extend_fetch_batch", "ppg_upload_map_geometry",
            "ppg_assoc_stage_poses", "ppg_frustum_fetch", "ppg_upload_vocabulary", "ppg_bow_transform",
-           "ppg_bow_run_batch", "ppg_bow_fetch_batch"]
+           "ppg_bow_run_batch", "ppg_bow_fetch_batch", "ppg_search_by_bow"]
 
 _lib = None
 
@@ -136,7 +146,7 @@ def load():
                      "ppg_upload_map_distinctive", "ppg_upload_map_graph", "ppg_extend_map_matches",
                      "ppg_extend_run_batch", "ppg_extend_fetch_batch", "ppg_upload_map_geometry",
                      "ppg_assoc_stage_poses", "ppg_frustum_fetch", "ppg_upload_vocabulary", "ppg_bow_transform",
-                     "ppg_bow_run_batch", "ppg_bow_fetch_batch"]:
+                     "ppg_bow_run_batch", "ppg_bow_fetch_batch", "ppg_search_by_bow"]:
             getattr(lib, name).restype = C.c_int
         _lib = lib
     return _lib
@@ -541,6 +551,23 @@ class Extractor:
             res.append(r)
         self._check(self.lib.ppg_bow_fetch_batch(self.h, n_frames, outs))
         return [self._bow_result(outs[f], res[f]) for f in range(n_frames)]
+
+    def search_by_bow(self, row_node, frame_desc, kp_node, ratio, max_dist, strict=False):
+        """Matcher::SearchByBoW whole (rows = the table uploaded with upload_map, in visiting order).
+        -> dict(kp_row, nmatches, n_rescans)."""
+        rn = np.ascontiguousarray(row_node, np.int32)
+        fd = np.ascontiguousarray(frame_desc, np.float32).reshape(-1, 256)
+        kn = np.ascontiguousarray(kp_node, np.int32)
+        a = BowMatchIn()
+        a.n_rows, a.n_kp = len(rn), len(kn)
+        a.row_node = rn.ctypes.data_as(C.POINTER(C.c_int32))
+        a.frame_desc, a.kp_node = _fp(fd), kn.ctypes.data_as(C.POINTER(C.c_int32))
+        a.ratio, a.max_dist, a.strict = ratio, max_dist, int(strict)
+        kr = np.full(max(len(kn), 1), -1, np.int32)
+        o = BowMatchOut()
+        o.kp_row = kr.ctypes.data_as(C.POINTER(C.c_int32))
+        self._check(self.lib.ppg_search_by_bow(self.h, C.byref(a), C.byref(o)))
+        return dict(kp_row=kr[:len(kn)].copy(), nmatches=o.nmatches, n_rescans=o.n_rescans)
 
     def distinctive_descriptors(self, desc, offsets, to_table=False):
         """MapPoint::ComputeDistinctiveDescriptors for a batch of map points (packed observation descriptors +

@@ -75,6 +75,9 @@ struct ExtendState {
     int ecap = 0;
     // staged point-pair graph of one frame (ppg_extend_map_matches)
     int *g_es = nullptr, *g_ee = nullptr, *g_coff = nullptr, *g_cidx = nullptr;
+    // node mode (SearchByBoW): no map graph -> zero CSR / flags, identity order, every row "observed"
+    int *zero_i = nullptr, *ident = nullptr, *row_node = nullptr, *kp_node = nullptr;
+    uint8_t* ones_u8 = nullptr;
     // pinned mirrors for the fetch
     int *h_kp_mp = nullptr, *h_kedge_me = nullptr, *h_result = nullptr;
     uint8_t* h_tracked = nullptr;
@@ -94,6 +97,11 @@ struct ListParams {
     uint16_t* l_idx;
     float* l_d;
     uint8_t* l_cnt;
+    // node mode (Matcher::SearchByBoW): the "window" of a row = the frame features of its FeatureVector node, in
+    // ascending index; no geometry
+    int node_mode;
+    const int* row_node;
+    const int* kp_node;
 };
 
 // DescriptorDistance with both rows already in registers (same operation order as exact_distance).
@@ -120,7 +128,12 @@ __global__ void __launch_bounds__(256) extend_lists_kernel(const ListParams p) {
     __shared__ uint16_t s_hit[8][1024];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, f = blockIdx.y;
     const int n = min(p.src.n_of(f), p.ncap);
-    {
+    if (p.node_mode) {
+        for (int i = threadIdx.x; i < n; i += 256) {
+            s_info[i] = (uint32_t)p.kp_node[i];
+            s_ord[i] = (uint32_t)i;  // vIndicesF is filled in feature order
+        }
+    } else {
         const float* kx = p.src.kx_of(f);
         const float* ky = p.src.ky_of(f);
         const uint32_t* kinfo = p.kinfo + (size_t)f * p.ncap;
@@ -139,7 +152,15 @@ __global__ void __launch_bounds__(256) extend_lists_kernel(const ListParams p) {
         if (q >= p.nc) break;
         const int row = p.order[q];
         const size_t o = (size_t)f * p.max_rows + row, ol = (size_t)f * p.max_rows + q;
-        const RowParam rp = p.rowp[o];
+        RowParam rp;
+        rp.cells = 0;
+        int my_node = -1;
+        if (p.node_mode) {
+            my_node = p.row_node[row];
+            if (my_node < 0) rp.cells = 0xffffffffu;
+        } else {
+            rp = p.rowp[o];
+        }
         // the sorted list lives across the warp: lane k holds its k-th entry (empty = +inf)
         float ld = INFINITY;
         uint32_t lo = 0xffffffffu;
@@ -154,8 +175,13 @@ __global__ void __launch_bounds__(256) extend_lists_kernel(const ListParams p) {
                 // the distance test of Frame.cpp:305-309 first: two subtractions reject ~98 % of the keypoints, the
                 // literal cell-range / indexable test (in_window) runs only for the few that pass (the kernel is
                 // issue-bound; the full test on every keypoint was 40 % of its instructions)
-                bool in = c < n && fabsf(s_kx[c] - rp.u) < rp.r && fabsf(s_ky[c] - rp.v) < rp.r;
-                if (in) in = in_window(rp, s_info[c], s_kx[c], s_ky[c], 0.0);
+                bool in;
+                if (p.node_mode) {
+                    in = c < n && (int)s_info[c] == my_node;  // Matcher.cpp:417-418
+                } else {
+                    in = c < n && fabsf(s_kx[c] - rp.u) < rp.r && fabsf(s_ky[c] - rp.v) < rp.r;
+                    if (in) in = in_window(rp, s_info[c], s_kx[c], s_ky[c], 0.0);
+                }
                 const unsigned mask = __ballot_sync(AFULL, in);
                 if (in) s_hit[warp][nh + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)c;
                 nh += __popc(mask);
@@ -219,6 +245,12 @@ struct WalkParams {
     int* result;
     float ratio, th_high;
     int has_state;
+    // node mode (Matcher::SearchByBoW, Matcher.cpp:393-477 / :663-754): accept = best <= (or <) max_dist && best <
+    // ratio * second; every matched feature is taken (vpMapPointMatches / vbMatched2), no map edges
+    int node_mode, strict;
+    float max_dist;
+    const int* row_node;
+    const int* kp_node;
 };
 
 struct WalkShared {
@@ -406,7 +438,10 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                     const uint32_t rest = fm & (fm - 1);
                     const float b1 = ld[k1], b2 = rest ? ld[__ffs(rest) - 1] : 1e6f;
                     bidx = (int)((lim[k1 >> 1] >> ((k1 & 1) * 16)) & 0xffffu);
-                    act = !(b1 > p.th_high && b1 > p.ratio * b2) ? 1 : 0;  // :276
+                    if (p.node_mode)
+                        act = ((p.strict ? b1 < p.max_dist : b1 <= p.max_dist) && b1 < p.ratio * b2) ? 1 : 0;  // :456-458
+                    else
+                        act = !(b1 > p.th_high && b1 > p.ratio * b2) ? 1 : 0;  // :276
                 } else if (cnt > X_LIST) {
                     act = 2;  // the list was cut and fewer than two free entries are left of it: rescan the window
                 }
@@ -466,13 +501,20 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
             if (S.ev[1] == 2) {
                 if (tid == 0) S.cln = 0;
                 __syncthreads();
-                const RowParam rp = p.rowp[(size_t)f * p.max_rows + erow];
-                const float* kx = p.src.kx_of(f);
-                const float* ky = p.src.ky_of(f);
-                const uint32_t* kinfo = p.kinfo + (size_t)f * p.ncap;
                 const uint32_t* korder = p.korder + (size_t)f * p.ncap;
-                for (int c = tid; c < n; c += X_THREADS)
-                    if (in_window(rp, kinfo[c], kx[c], ky[c], 0.0) && !S.occ[c]) S.cl[atomicAdd(&S.cln, 1)] = (uint16_t)c;
+                if (p.node_mode) {
+                    const int my_node = p.row_node[erow];
+                    for (int c = tid; c < n; c += X_THREADS)
+                        if (p.kp_node[c] == my_node && !S.occ[c]) S.cl[atomicAdd(&S.cln, 1)] = (uint16_t)c;
+                } else {
+                    const RowParam rp = p.rowp[(size_t)f * p.max_rows + erow];
+                    const float* kx = p.src.kx_of(f);
+                    const float* ky = p.src.ky_of(f);
+                    const uint32_t* kinfo = p.kinfo + (size_t)f * p.ncap;
+                    for (int c = tid; c < n; c += X_THREADS)
+                        if (in_window(rp, kinfo[c], kx[c], ky[c], 0.0) && !S.occ[c])
+                            S.cl[atomicAdd(&S.cln, 1)] = (uint16_t)c;
+                }
                 __syncthreads();
                 float a[8];
 #pragma unroll
@@ -484,7 +526,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                 for (int k = warp; k < ncl; k += X_WARPS) {
                     const int cc = S.cl[k];
                     const float dd = exact_distance(a, fdesc + (size_t)cc * 256, lane);
-                    top2_update(dd, korder[cc], cc, b1, o1, i1, b2, o2, i2);
+                    top2_update(dd, p.node_mode ? (uint32_t)cc : korder[cc], cc, b1, o1, i1, b2, o2, i2);
                 }
                 if (lane == 0) {
                     S.t2d[warp][0] = b1; S.t2o[warp][0] = o1; S.t2i[warp][0] = i1;
@@ -498,7 +540,9 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                     for (int w = 0; w < X_WARPS; w++)
                         for (int k = 0; k < 2; k++)
                             if (S.t2i[w][k] >= 0) top2_update(S.t2d[w][k], S.t2o[w][k], S.t2i[w][k], b1, o1, i1, b2, o2, i2);
-                    const bool acc = i1 >= 0 && !(b1 > p.th_high && b1 > p.ratio * b2);
+                    const bool acc = i1 >= 0 && (p.node_mode ? ((p.strict ? b1 < p.max_dist : b1 <= p.max_dist) &&
+                                                                b1 < p.ratio * b2)
+                                                             : !(b1 > p.th_high && b1 > p.ratio * b2));
                     S.ev[1] = acc ? 1 : 0;
                     S.ev[2] = i1;
                     S.res[XR_RESCANS]++;
@@ -763,6 +807,18 @@ int ensure_extend(ppg_ctx* c) {
     PPG_CUDA(c, dalloc(&x->g_ee, E));
     PPG_CUDA(c, dalloc(&x->g_coff, N + 1));
     PPG_CUDA(c, dalloc(&x->g_cidx, 2 * E));
+    PPG_CUDA(c, dalloc(&x->zero_i, R + N + 2));
+    PPG_CUDA(c, cudaMemset(x->zero_i, 0, (R + N + 2) * 4));
+    PPG_CUDA(c, dalloc(&x->ones_u8, R));
+    PPG_CUDA(c, cudaMemset(x->ones_u8, 1, R));
+    PPG_CUDA(c, dalloc(&x->row_node, R));
+    PPG_CUDA(c, dalloc(&x->kp_node, N));
+    PPG_CUDA(c, dalloc(&x->ident, R));
+    {
+        std::vector<int> id(R);
+        std::iota(id.begin(), id.end(), 0);
+        PPG_CUDA(c, cudaMemcpy(x->ident, id.data(), R * 4, cudaMemcpyHostToDevice));
+    }
     PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&x->h_kp_mp), B * N * 4));
     PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&x->h_kedge_me), B * E * 4));
     PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&x->h_result), B * XR_WORDS * 4));
@@ -821,6 +877,8 @@ int run_extend(ppg_ctx* c, const FrameSrc& src, const FrameGraphSrc& gsrc, int f
         lp.l_idx = x->l_idx;
         lp.l_d = x->l_d;
         lp.l_cnt = x->l_cnt;
+        lp.node_mode = 0;
+        lp.row_node = lp.kp_node = nullptr;
         extend_lists_kernel<<<dim3((x->nc + XL_ROWS - 1) / XL_ROWS, frames), 256, 0, c->st>>>(lp);
         c->launches++;
         stage_mark(c, "extend.lists");
@@ -853,6 +911,10 @@ int run_extend(ppg_ctx* c, const FrameSrc& src, const FrameGraphSrc& gsrc, int f
     wp.ratio = s->ratio;
     wp.th_high = c->cfg.th_high;
     wp.has_state = has_state;
+    wp.node_mode = 0;
+    wp.strict = 0;
+    wp.max_dist = 0.f;
+    wp.row_node = wp.kp_node = nullptr;
     extend_walk_kernel<<<frames, X_THREADS, walk_smem(x->P, s->ncap, x->ecap), c->st>>>(wp);
     c->launches++;
     stage_mark(c, "extend.walk");
@@ -902,7 +964,8 @@ void extend_destroy(AssocState* s) {
     ExtendState* x = s->ext;
     if (!x) return;
     void* bufs[] = {x->observed, x->bad, x->edge_ok, x->edge_off, x->edge_other, x->order, x->l_idx, x->l_d, x->l_cnt,
-                    x->tracked, x->kp_mp, x->kedge_me, x->result, x->g_es, x->g_ee, x->g_coff, x->g_cidx};
+                    x->tracked, x->kp_mp, x->kedge_me, x->result, x->g_es, x->g_ee, x->g_coff, x->g_cidx,
+                    x->zero_i, x->ident, x->row_node, x->kp_node, x->ones_u8};
     for (void* b : bufs)
         if (b) cudaFree(b);
     void* hbufs[] = {x->h_kp_mp, x->h_kedge_me, x->h_result, x->h_tracked};
@@ -1061,6 +1124,97 @@ int ppg_extend_fetch_batch(ppg_ctx* c, int n_frames, ppg_extend_out* outs) {
     if (rc != PPG_OK) return rc;
     for (int f = 0; f < n_frames; f++) fill_out(c->assoc->ext, c->assoc, f, &outs[f]);
     return check_status(c, c->assoc->ext->h_result, n_frames);
+}
+
+// Matcher::SearchByBoW whole (Matcher.cpp:393-477 / :663-754) through the same two kernels: lists over the features of
+// the row's vocabulary node, walk with the live vpMapPointMatches / vbMatched2 state, no map graph.
+int ppg_search_by_bow(ppg_ctx* c, const ppg_bow_match_in* in, ppg_bow_match_out* out) {
+    if (!c || !in || !out || !in->row_node) return set_err(c, PPG_ERR_ARG, "ppg_search_by_bow: null argument");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    int rc = ensure_extend(c);
+    if (rc != PPG_OK) return rc;
+    AssocState* s = c->assoc;
+    ExtendState* x = s->ext;
+    const int M = in->n_rows, N = in->n_kp;
+    if (M < 1 || M > s->n_rows) return set_err(c, PPG_ERR_ARG, "ppg_search_by_bow: upload the n_rows descriptors first");
+    if (N < 0 || N > s->ncap || (N > 0 && (!in->frame_desc || !in->kp_node)))
+        return set_err(c, PPG_ERR_ARG, "ppg_search_by_bow: bad frame arrays");
+    int last = -1;
+    for (int m = 0; m < M; m++) {  // the reference walks the FeatureVector nodes in ascending order
+        if (in->row_node[m] < 0) continue;
+        if (in->row_node[m] < last) return set_err(c, PPG_ERR_ARG, "ppg_search_by_bow: rows must be ordered by node");
+        last = in->row_node[m];
+    }
+    PPG_CUDA(c, cudaMemcpyAsync(x->row_node, in->row_node, (size_t)M * 4, cudaMemcpyHostToDevice, c->st));
+    if (N > 0) {
+        PPG_CUDA(c, cudaMemcpyAsync(x->kp_node, in->kp_node, (size_t)N * 4, cudaMemcpyHostToDevice, c->st));
+        PPG_CUDA(c, cudaMemcpyAsync(s->fdesc, in->frame_desc, (size_t)N * 1024, cudaMemcpyHostToDevice, c->st));
+    }
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));  // pageable sources
+    s->staged_n = N;
+    FrameSrc src = assoc_staged_src(s);
+    src.free_mask = s->ones;
+    ListParams lp{};
+    lp.nc = M;
+    lp.max_rows = s->max_rows;
+    lp.ncap = s->ncap;
+    lp.src = src;
+    lp.order = x->ident;
+    lp.map_f32 = s->map_f32;
+    lp.l_idx = x->l_idx;
+    lp.l_d = x->l_d;
+    lp.l_cnt = x->l_cnt;
+    lp.node_mode = 1;
+    lp.row_node = x->row_node;
+    lp.kp_node = x->kp_node;
+    extend_lists_kernel<<<dim3((M + XL_ROWS - 1) / XL_ROWS, 1), 256, 0, c->st>>>(lp);
+    stage_mark(c, "bow_match.lists");
+    WalkParams wp{};
+    wp.nc = M;
+    wp.P = M;
+    wp.max_rows = s->max_rows;
+    wp.ncap = s->ncap;
+    wp.ecap = x->ecap;
+    wp.src = src;
+    FrameGraphSrc g{};
+    g.coff = reinterpret_cast<const uint8_t*>(x->zero_i);  // no key edges
+    g.es = g.ee = g.cidx = g.coff;
+    g.ne_val = 0;
+    wp.gsrc = g;
+    wp.order = x->ident;
+    wp.map_f32 = s->map_f32;
+    wp.korder = s->korder;
+    wp.l_idx = x->l_idx;
+    wp.l_d = x->l_d;
+    wp.l_cnt = x->l_cnt;
+    wp.observed = x->ones_u8;
+    wp.bad = reinterpret_cast<const uint8_t*>(x->zero_i);
+    wp.edge_ok = reinterpret_cast<const uint8_t*>(x->zero_i);
+    wp.edge_off = x->zero_i;
+    wp.edge_other = x->zero_i;
+    wp.tracked = x->tracked;
+    wp.kp_mp = x->kp_mp;
+    wp.kedge_me = x->kedge_me;
+    wp.result = x->result;
+    wp.ratio = in->ratio;
+    wp.th_high = c->cfg.th_high;
+    wp.has_state = 0;
+    wp.node_mode = 1;
+    wp.strict = in->strict;
+    wp.max_dist = in->max_dist;
+    wp.row_node = x->row_node;
+    wp.kp_node = x->kp_node;
+    extend_walk_kernel<<<1, X_THREADS, walk_smem(M, s->ncap, x->ecap), c->st>>>(wp);
+    stage_mark(c, "bow_match.walk");
+    c->launches += 2;
+    PPG_CUDA(c, cudaGetLastError());
+    PPG_CUDA(c, cudaMemcpyAsync(x->h_result, x->result, XR_WORDS * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(x->h_kp_mp, x->kp_mp, (size_t)s->ncap * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    out->nmatches = x->h_result[XR_ACCEPTED];
+    out->n_rescans = x->h_result[XR_RESCANS];
+    if (out->kp_row && N > 0) memcpy(out->kp_row, x->h_kp_mp, (size_t)N * 4);
+    return PPG_OK;
 }
 
 }  // extern "C"

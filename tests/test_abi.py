@@ -54,6 +54,8 @@ def test_struct_layouts_match_header():
     assert fields("ppg_extend_out") == [f[0] for f in capi.ExtendOut._fields_]
     assert fields("ppg_vocabulary") == [f[0] for f in capi.VocabularyPod._fields_]
     assert fields("ppg_bow_out") == [f[0] for f in capi.BowOut._fields_]
+    assert fields("ppg_bow_match_in") == [f[0] for f in capi.BowMatchIn._fields_]
+    assert fields("ppg_bow_match_out") == [f[0] for f in capi.BowMatchOut._fields_]
 
 
 def test_no_cpu_fallback():

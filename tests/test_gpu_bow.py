@@ -107,3 +107,38 @@ def test_search_by_bow_core_equals_oracle():
             assert ref["accept"].sum() > 50
     finally:
         e.close()
+
+
+@pytest.mark.parametrize("strict,n,m,levelsup", [(False, 480, 400, 4), (True, 480, 400, 4), (False, 1000, 900, 2),
+                                                  (False, 60, 0, 4)])
+def test_search_by_bow_whole_equals_oracle(strict, n, m, levelsup):
+    """ppg_search_by_bow: the whole Matcher::SearchByBoW (live vpMapPointMatches) on the GPU == the oracle."""
+    from oracle import post_ref as O
+    from ppg_slam_b200 import capi
+    voc = vocabulary.load_blob(os.path.join(WEIGHTS, "voc_euroc_9x3.bin"))
+    rs = np.random.RandomState(13)
+    leaves = np.nonzero(voc.word_id >= 0)[0]
+    fd = voc.desc[leaves[rs.randint(0, len(leaves), n)]] + rs.normal(0, 0.05, (n, 256)).astype(np.float32)
+    fd = (fd / np.linalg.norm(fd, axis=1, keepdims=True)).astype(np.float32)
+    mm = max(m, 1)
+    # three keyframe features per frame feature on average: the later ones find their best taken
+    kd = fd[rs.randint(0, max(n // 3, 1), mm)] + rs.normal(0, 0.03, (mm, 256)).astype(np.float32)
+    kd = (kd / np.linalg.norm(kd, axis=1, keepdims=True)).astype(np.float32)
+    e = capi.Extractor(cameras.EUROC, max_batch=1, max_map_points=1024, junction_max_num=1000)
+    try:
+        e.upload_vocabulary(voc)
+        kp_node = e.bow_transform(fd, levelsup)["node"]
+        row_node = e.bow_transform(kd, levelsup)["node"]
+        order = np.argsort(np.where(row_node < 0, 1 << 30, row_node), kind="stable")  # visiting order: node, then index
+        kd, row_node = kd[order], row_node[order]
+        if m == 0:
+            row_node[:] = -1  # no keyframe feature holds a map point
+        e.upload_map(kd)
+        got = e.search_by_bow(row_node, fd, kp_node, 0.8, 0.7, strict)
+        ref = O.search_by_bow(fd, kp_node, kd, row_node, 0.8, 0.7, strict)
+        assert got["nmatches"] == ref["nmatches"]
+        np.testing.assert_array_equal(got["kp_row"], ref["kp_row"])
+        if m:
+            assert ref["nmatches"] > 50
+    finally:
+        e.close()

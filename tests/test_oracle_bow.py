@@ -146,3 +146,51 @@ def test_search_by_bow_core_kat():
             assert got["best_d"][j] == np.float32(best1) and got["second_d"][j] == np.float32(best2)
         n_acc += acc
     assert n_acc > 20 and (got["best_idx"] < 0).sum() > 5
+
+
+def _bow_match_case(seed, n=160, m=130, nodes=(0,)):
+    rs = np.random.RandomState(seed)
+    fd = rs.normal(size=(n, 256)).astype(np.float32)
+    fd /= np.linalg.norm(fd, axis=1, keepdims=True)
+    # several keyframe features near the same frame feature: later rows must take their second choice or fail
+    kd = fd[rs.randint(0, n // 3, m)] + rs.normal(0, 0.04, (m, 256)).astype(np.float32)
+    kd = (kd / np.linalg.norm(kd, axis=1, keepdims=True)).astype(np.float32)
+    kp_node = rs.choice(list(nodes) + [-1], n).astype(np.int32)
+    row_node = np.sort(rs.choice(list(nodes), m)).astype(np.int32)
+    row_node[rs.rand(m) < 0.05] = -1
+    return fd, kp_node, kd, row_node
+
+
+@pytest.mark.parametrize("strict,nodes", [(False, (0,)), (True, (0,)), (False, (3, 5, 9))])
+def test_search_by_bow_whole_kat(strict, nodes):
+    """Matcher::SearchByBoW (Matcher.cpp:393-477 / :663-754) with the FeatureVectors as ordered dicts and the live
+    vpMapPointMatches vector, statement by statement."""
+    fd, kp_node, kd, row_node = _bow_match_case(4, nodes=nodes)
+    got = O.search_by_bow(fd, kp_node, kd, row_node, 0.8, 0.7, strict)
+    fvF, fvK = {}, {}
+    for i, nd in enumerate(kp_node.tolist()):
+        if nd >= 0:
+            fvF.setdefault(nd, []).append(i)
+    for j, nd in enumerate(row_node.tolist()):
+        if nd >= 0:
+            fvK.setdefault(nd, []).append(j)
+    matches = [None] * len(kp_node)
+    nm = 0
+    for node in sorted(set(fvF) & set(fvK)):
+        for j in fvK[node]:
+            best1, best2, bi = 1e6, 1e6, -1
+            for idx in fvF[node]:
+                if matches[idx] is not None:
+                    continue
+                d = O.descriptor_distance(kd[j], fd[idx])
+                if d < best1:
+                    best2, best1, bi = best1, d, idx
+                elif d < best2:
+                    best2 = d
+            ok = best1 < np.float32(0.7) if strict else best1 <= np.float32(0.7)
+            if ok and best1 < float(np.float32(np.float32(0.8) * np.float32(best2))):
+                matches[bi] = j
+                nm += 1
+    assert got["nmatches"] == nm
+    assert got["kp_row"].tolist() == [(-1 if x is None else x) for x in matches]
+    assert nm > 15
