@@ -256,6 +256,50 @@ inline void compute_bow(ppg_ctx* ctx, FrameLike& F, int levelsup = 4) {
         if (node[i] >= 0) F.mFeatVec[(unsigned int)node[i]].push_back((unsigned int)i);       // FeatureVector::addFeature
 }
 
+// Matcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (matching/src/Matcher.cpp:393-477) whole on the GPU
+// (ppg_search_by_bow): rows = the keyframe features that hold a good map point, in the order the reference visits them
+// (FeatureVector node ascending, then feature index); the frame side gives its descriptors and the node of every
+// listed feature.  `KeyFrameLike` needs GetMapPointMatches(), mFeatVec, mDescriptors.
+template <class KeyFrameLike>
+inline int search_by_bow(ppg_ctx* ctx, KeyFrameLike* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches,
+                         float nnratio, float th_low) {
+    const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+    const int N = (int)F.mvKeysUn.size();
+    vpMapPointMatches = std::vector<MapPoint*>(N, static_cast<MapPoint*>(nullptr));  // :396
+    std::vector<int32_t> row_node, kp_node(N, -1);
+    std::vector<MapPoint*> row_mp;
+    std::vector<float> table;
+    for (const auto& nf : pKF->mFeatVec)  // std::map: ascending node id
+        for (unsigned int idx : nf.second) {
+            MapPoint* pMP = vpMapPointsKF[idx];
+            if (!pMP || pMP->isBad()) continue;  // :423-427
+            row_node.push_back((int32_t)nf.first);
+            row_mp.push_back(pMP);
+            const float* d = pKF->mDescriptors.template ptr<float>((int)idx);
+            table.insert(table.end(), d, d + PPG_DESC_DIM);
+        }
+    if (row_node.empty()) return 0;
+    for (const auto& nf : F.mFeatVec)
+        for (unsigned int idx : nf.second) kp_node[idx] = (int32_t)nf.first;
+    check(ppg_upload_map(ctx, table.data(), (int)row_node.size()), ctx, "ppg_upload_map");
+    std::vector<int32_t> kp_row(N > 0 ? N : 1, -1);
+    ppg_bow_match_in in{};
+    in.n_rows = (int)row_node.size();
+    in.row_node = row_node.data();
+    in.n_kp = N;
+    in.frame_desc = F.mDescriptors.template ptr<float>(0);
+    in.kp_node = kp_node.data();
+    in.ratio = nnratio;
+    in.max_dist = th_low;
+    in.strict = 0;  // :456 `<=`; SearchByBoW(KF1, KF2) :733 uses `<` (strict = 1)
+    ppg_bow_match_out out{};
+    out.kp_row = kp_row.data();
+    check(ppg_search_by_bow(ctx, &in, &out), ctx, "ppg_search_by_bow");
+    for (int i = 0; i < N; i++)
+        if (kp_row[i] >= 0) vpMapPointMatches[i] = row_mp[kp_row[i]];  // :460
+    return out.nmatches;
+}
+
 // The whole Matcher::ExtendMapMatches (matching/src/Matcher.cpp:203-381) in one GPU call: window search with the live
 // frame state, assignment and seed growing all run in ppg_extend_map_matches; this function only flattens the
 // pointer graph into the POD form of include/ppg_b200.h and writes the result back into the Frame:

@@ -13,6 +13,9 @@ int shim_instantiate(GeometricCamera* cam, Frame& F, std::vector<MapPoint*>& mps
     int n = (int)ppg_shim::search_window(ex.context(), F, mps, uv, free_mask, 15.f, 0.8f).accept.size();        // :31-87
     n += (int)ppg_shim::search_window(ex.context(), F, mps, uv, free_mask, 3.f, 0.7f, 5.99).accept.size();     // Fuse
     ppg_shim::compute_bow(ex.context(), F);  // Frame.cpp:331-340
+    KeyFrame kf;
+    std::vector<MapPoint*> bowm;
+    n += ppg_shim::search_by_bow(ex.context(), &kf, F, bowm, 0.8f, 0.7f);  // Matcher.cpp:393-477
     n += ppg_shim::extend_map_matches(ex.context(), F, mps, 10.f, 0.8f);  // Matcher.cpp:203-381
     return n + (int)ppg_shim::search_local_points(ex.context(), F, mps, 10.f, 0.8f).accept.size();
 }

@@ -66,6 +66,11 @@ struct MapPoint {
     std::vector<MapEdge*> getEdges() { return {}; }
     cv::Mat GetDescriptor() { return cv::Mat(); }
 };
+struct KeyFrame {
+    std::map<unsigned int, std::vector<unsigned int>> mFeatVec;
+    cv::Mat mDescriptors;
+    std::vector<MapPoint*> GetMapPointMatches() { return {}; }
+};
 struct Frame {
     std::map<unsigned int, double> mBowVec;                      // DBoW3::BowVector
     std::map<unsigned int, std::vector<unsigned int>> mFeatVec;  // DBoW3::FeatureVector
