@@ -356,6 +356,15 @@ typedef struct {
 } ppg_vocabulary;
 int ppg_upload_vocabulary(ppg_ctx* ctx, const ppg_vocabulary* voc);
 
+/* Host-side reader (no GPU needed): the reference's Vocabulary/voc_*_9x3.gz as System loads them with
+ * DBoW3::Vocabulary::load (DBoW3 binary stream, QuickLZ level-1 chunks) or the flat blob of tools/export_vocabulary.py.
+ * `view` points into memory owned by the handle until ppg_vocabulary_close.  ppg_load_vocabulary = open + upload. */
+typedef struct ppg_voc_file ppg_voc_file;
+int ppg_vocabulary_open(const char* path, ppg_voc_file** out, ppg_vocabulary* view);
+void ppg_vocabulary_close(ppg_voc_file* voc);
+const char* ppg_vocabulary_error(void); /* why the last ppg_vocabulary_open on this thread failed */
+int ppg_load_vocabulary(ppg_ctx* ctx, const char* path);
+
 typedef struct {          /* caller-allocated (any pointer may be NULL) */
     int n_features;       /* out: features transformed */
     int n_bow;            /* out: entries of the BowVector */

@@ -731,7 +731,8 @@ int ppgo_features_in_area(const ppgo_bounds *b, const int *grid_off, const int *
 
 /* Search core of the projection matchers for one map point with the frame state frozen
  * (free_mask[idx]!=0 <=> keypoint idx is NOT skipped).  This is the data-parallel contract of
- * ppg_associate(): the sequential consumption stays in the host shim.  Candidate order =
+ * ppg_associate(); the whole function (sequential consumption + seed growing) is ppgo_extend_map_matches below.
+ * Candidate order =
  * GetFeaturesInArea order (cell-major), ties keep the first (strict <).
  *   mode 0  Matcher::ExtendMapMatches, matching/src/Matcher.cpp:224-281: r = th * (viewCos > 0.998 ? 2.5 : 4),
  *           accept = !(best > TH_HIGH && best > ratio * second) (:276)

@@ -25,6 +25,7 @@ SOURCES = {
     "assoc.cu": ["-fmad=false"],
     "extend.cu": ["-fmad=false"],
     "bow.cu": ["-fmad=false"],
+    "voc_io.cu": [],
 }
 
 

@@ -117,7 +117,8 @@ SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", 
            "ppg_distinctive_descriptors", "ppg_upload_map_distinctive", "ppg_stream", "ppg_upload_map_graph",
            "ppg_extend_map_matches", "ppg_extend_run_batch", "ppg_extend_fetch_batch", "ppg_upload_map_geometry",
            "ppg_assoc_stage_poses", "ppg_frustum_fetch", "ppg_upload_vocabulary", "ppg_bow_transform",
-           "ppg_bow_run_batch", "ppg_bow_fetch_batch", "ppg_search_by_bow"]
+           "ppg_bow_run_batch", "ppg_bow_fetch_batch", "ppg_search_by_bow", "ppg_vocabulary_open",
+           "ppg_vocabulary_close", "ppg_vocabulary_error", "ppg_load_vocabulary"]
 
 _lib = None
 
@@ -134,6 +135,9 @@ def load():
         lib.ppg_destroy.restype = None
         lib.ppg_launch_count.restype = C.c_longlong
         lib.ppg_launch_count.argtypes = [C.c_void_p]
+        lib.ppg_vocabulary_error.restype = C.c_char_p
+        lib.ppg_vocabulary_close.restype = None
+        lib.ppg_vocabulary_close.argtypes = [C.c_void_p]
         lib.ppg_stream.restype = C.c_void_p
         lib.ppg_stream.argtypes = [C.c_void_p]
         for name in ["ppg_extract", "ppg_upload_frames", "ppg_run", "ppg_download", "ppg_sync",
@@ -146,7 +150,8 @@ def load():
                      "ppg_upload_map_distinctive", "ppg_upload_map_graph", "ppg_extend_map_matches",
                      "ppg_extend_run_batch", "ppg_extend_fetch_batch", "ppg_upload_map_geometry",
                      "ppg_assoc_stage_poses", "ppg_frustum_fetch", "ppg_upload_vocabulary", "ppg_bow_transform",
-                     "ppg_bow_run_batch", "ppg_bow_fetch_batch", "ppg_search_by_bow"]:
+                     "ppg_bow_run_batch", "ppg_bow_fetch_batch", "ppg_search_by_bow", "ppg_vocabulary_open",
+                     "ppg_load_vocabulary"]:
             getattr(lib, name).restype = C.c_int
         _lib = lib
     return _lib
@@ -154,6 +159,25 @@ def load():
 
 def _fp(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def read_vocabulary(path):
+    """The library's own host-side reader (ppg_vocabulary_open: DBoW3 binary + QuickLZ, or the PVOC blob).
+    -> ppg_slam_b200.vocabulary.PodVocabulary.  No GPU involved."""
+    from . import vocabulary
+    lib = load()
+    h, v = C.c_void_p(), VocabularyPod()
+    rc = lib.ppg_vocabulary_open(os.fsencode(path), C.byref(h), C.byref(v))
+    if rc != PPG_OK:
+        raise PpgError(rc, lib.ppg_vocabulary_error().decode())
+    try:
+        n, k, dim = v.n_nodes, v.k, v.dim
+        return vocabulary.PodVocabulary(
+            k, v.L, v.scoring, v.weighting, np.ctypeslib.as_array(v.children, shape=(n, k)).copy(),
+            np.ctypeslib.as_array(v.word_id, shape=(n,)).copy(), np.ctypeslib.as_array(v.weight, shape=(n,)).copy(),
+            np.ctypeslib.as_array(v.desc, shape=(n, dim)).copy())
+    finally:
+        lib.ppg_vocabulary_close(h)
 
 
 def _frame_to_dict(o):
@@ -501,6 +525,10 @@ class Extractor:
         return dict(in_view=iv, proj_uv=uv, depth=dp, view_cos=vc)
 
     # ---- bag of words: DBoW3::Vocabulary::transform (Frame::ComputeBoW, map/src/Frame.cpp:331-340)
+    def load_vocabulary(self, path):
+        """ppg_load_vocabulary: the reference's Vocabulary/voc_*.gz (or the exported blob) straight into the ctx."""
+        self._check(self.lib.ppg_load_vocabulary(self.h, os.fsencode(path)))
+
     def upload_vocabulary(self, voc):
         """voc: ppg_slam_b200.vocabulary.PodVocabulary / Vocabulary (k, L, scoring, weighting, child_table(), ...)."""
         ch = np.ascontiguousarray(voc.child_table(), np.int32)

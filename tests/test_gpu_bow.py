@@ -63,7 +63,7 @@ def test_bow_batch_on_extracted_frames():
     e = capi.Extractor(cam, max_batch=Bn)
     try:
         recs = e.run([synth.frame(s, cam.width, cam.height) for s in range(Bn)])
-        e.upload_vocabulary(voc)
+        e.load_vocabulary(os.path.join(WEIGHTS, "voc_euroc_9x3.bin"))  # the library's own reader (ppg_load_vocabulary)
         e.bow_run_batch(Bn, 4)
         got = e.bow_fetch_batch(Bn)
         for f in range(Bn):

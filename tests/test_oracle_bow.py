@@ -194,3 +194,47 @@ def test_search_by_bow_whole_kat(strict, nodes):
     assert got["nmatches"] == nm
     assert got["kp_row"].tolist() == [(-1 if x is None else x) for x in matches]
     assert nm > 15
+
+
+def test_library_vocabulary_reader_matches_python_reader(tmp_path):
+    """ppg_vocabulary_open (C++ host code of libppg_b200.so, no GPU): the committed blob, an uncompressed DBoW3 stream
+    written here, and -- in the build container -- the reference's own QuickLZ-compressed files."""
+    import struct
+    from ppg_slam_b200 import capi
+    blob = vocabulary.load_blob(os.path.join(WEIGHTS, "voc_euroc_9x3.bin"))
+
+    def same(a, b):
+        assert (a.k, a.L, a.scoring, a.weighting, a.n_nodes) == (b.k, b.L, b.scoring, b.weighting, b.n_nodes)
+        np.testing.assert_array_equal(a.child_table(), b.child_table())
+        np.testing.assert_array_equal(a.word_id, b.word_id)
+        np.testing.assert_array_equal(a.weight, b.weight)
+        np.testing.assert_array_equal(a.desc[1:], b.desc[1:])  # the root has no descriptor in the file
+
+    same(capi.read_vocabulary(os.path.join(WEIGHTS, "voc_euroc_9x3.bin")), blob)
+    # DBoW3 stream, uncompressed: depth-first node records in the order Vocabulary::toStream writes them
+    v = vocabulary.random_vocabulary(5, 3, 2)
+    out = struct.pack("<QBI", vocabulary.SIGNATURE, 0, v.n_nodes) + struct.pack("<iiii", v.k, v.L, v.scoring, v.weighting)
+    parents = [0]
+    while parents:
+        pid = parents.pop()
+        for c in v.children[pid]:
+            if c < 0:
+                continue
+            out += struct.pack("<IId", c, pid, v.weight[c]) + struct.pack("<iii", 256, 1, 5) + v.desc[c].tobytes()
+            if v.children[c][0] >= 0:
+                parents.append(c)
+    words = np.nonzero(v.word_id >= 0)[0]
+    out += struct.pack("<I", len(words)) + b"".join(struct.pack("<II", int(v.word_id[n]), int(n)) for n in words)
+    path = tmp_path / "voc_raw.bin"
+    path.write_bytes(out)
+    got = capi.read_vocabulary(str(path))
+    same(got, v)
+    same(vocabulary.Vocabulary(str(path)), v)  # the Python reader agrees
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(out[:-3])
+    with pytest.raises(capi.PpgError):
+        capi.read_vocabulary(str(bad))
+    for name in ("voc_euroc_9x3", "voc_tum_9x3"):
+        src = os.path.join(REF_VOC, name + ".gz")
+        if os.path.exists(src):
+            same(capi.read_vocabulary(src), vocabulary.load_blob(os.path.join(WEIGHTS, name + ".bin")))
