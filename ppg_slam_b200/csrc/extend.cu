@@ -36,7 +36,7 @@
 namespace ppg {
 
 constexpr int X_LIST = 32;                           // window candidates stored per row
-constexpr int X_PRE = 8;                             // map edges of a row preloaded with its chunk
+constexpr int X_PRE = 8;                             // map edges of a row preloaded with its chunk (row header layout)
 constexpr int X_LCAP = PPG_EXTEND_MAX_DEGREE;        // map edges per map point / key edges per keypoint
 constexpr int X_WCAP = PPG_EXTEND_MAX_WEIGHTS;       // weight-matrix entries per seed
 constexpr int X_THREADS = 256, X_WARPS = X_THREADS / 32;
@@ -63,6 +63,7 @@ struct ExtendState {
     int P = 0, nc = 0, edge_cap = 0;
     uint8_t *observed = nullptr, *bad = nullptr, *edge_ok = nullptr;
     int *edge_off = nullptr, *edge_other = nullptr, *order = nullptr;
+    int4* row_hdr = nullptr;  // [max_rows][3]
     // per-row candidate lists, indexed by position in the sorted order: [bcap][max_rows][X_LIST]
     uint16_t* l_idx = nullptr;
     float* l_d = nullptr;
@@ -230,6 +231,7 @@ struct WalkParams {
     FrameSrc src;
     FrameGraphSrc gsrc;
     const int* order;
+    const int4* row_hdr;  // [nc][3] or null (then order / edge_off / edge_other / edge_ok are read per row)
     const RowParam* rowp;
     const float* map_f32;
     const uint32_t* kinfo;
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
 #pragma unroll
         for (int k = 0; k < X_LIST / 2; k++) li[k] = 0xffffffffu;
         if (pos < p.nc) {
-            row = p.order[pos];
+            if (!p.row_hdr) row = p.order[pos];
             const size_t ol = (size_t)f * p.max_rows + pos;
             const uint4* pi = reinterpret_cast<const uint4*>(p.l_idx + ol * X_LIST);
             const float4* pd = reinterpret_cast<const float4*>(p.l_d + ol * X_LIST);
@@ -364,12 +366,25 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
             for (int k = 0; k < X_LIST / 8; k++) iv[k] = pi[k];
 #pragma unroll
             for (int k = 0; k < X_LIST / 4; k++) dv[k] = pd[k];
-            my_me0 = p.edge_off[row];
-            my_nme = p.edge_off[row + 1] - my_me0;
             cnt = p.l_cnt[ol];
+            if (p.row_hdr) {
+                // row, first map edge, edge count and the first eight usable other endpoints in one 48-byte record
+                // per sorted position (built when the map graph is uploaded): one round trip instead of three
+                // dependent ones (order -> edge_off -> edge_other / edge_ok)
+                const int4* hp = p.row_hdr + (size_t)pos * 3;
+                const int4 h0 = hp[0], h1 = hp[1], h2 = hp[2];
+                row = h0.x;
+                my_me0 = h0.y;
+                my_nme = h0.z;
+                pe[0] = h0.w; pe[1] = h1.x; pe[2] = h1.y; pe[3] = h1.z;
+                pe[4] = h1.w; pe[5] = h2.x; pe[6] = h2.y; pe[7] = h2.z;
+            } else {
+                my_me0 = p.edge_off[row];
+                my_nme = p.edge_off[row + 1] - my_me0;
 #pragma unroll
-            for (int k = 0; k < X_PRE; k++)
-                if (k < my_nme) pe[k] = p.edge_ok[my_me0 + k] ? p.edge_other[my_me0 + k] : -1;
+                for (int k = 0; k < X_PRE; k++)
+                    if (k < my_nme) pe[k] = p.edge_ok[my_me0 + k] ? p.edge_other[my_me0 + k] : -1;
+            }
 #pragma unroll
             for (int k = 0; k < X_LIST / 8; k++) {
                 li[4 * k] = iv[k].x; li[4 * k + 1] = iv[k].y; li[4 * k + 2] = iv[k].z; li[4 * k + 3] = iv[k].w;
@@ -387,6 +402,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
 #pragma unroll
         for (int k = 0; k < X_LIST / 2; k++) lim[k] = li[k];
         const int stored = cnt < X_LIST ? cnt : X_LIST;
+        const int wmax = __reduce_max_sync(AFULL, stored);  // longest list of the warp: the unrolled loops stop there
         const uint32_t valid = stored >= 32 ? AFULL : (1u << stored) - 1u;
         // fm: which entries of my list are FREE keypoints.  Built once per chunk from the occupancy table; after that
         // every event publishes the keypoints it took (S.taken) and each thread strikes them out of its mask with
@@ -396,6 +412,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
             uint32_t fm = 0;
 #pragma unroll
             for (int k = 0; k < X_LIST / 2; k++) {
+                if (2 * k >= wmax) break;
                 const uint32_t w = li[k];
                 if (2 * k < stored && !S.occ[w & 0xffffu]) fm |= 1u << (2 * k);
                 if (2 * k + 1 < stored && !S.occ[w >> 16]) fm |= 1u << (2 * k + 1);
@@ -425,6 +442,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                         const uint32_t kp = S.taken[t], kp2 = kp | (kp << 16);
 #pragma unroll
                         for (int k = 0; k < X_LIST / 2; k++) {
+                            if (2 * k >= wmax) break;
                             const uint32_t x = li[k] ^ kp2;
                             if ((x & 0xffffu) == 0) fm &= ~(1u << (2 * k));
                             if ((x >> 16) == 0) fm &= ~(1u << (2 * k + 1));
@@ -796,6 +814,7 @@ int ensure_extend(ppg_ctx* c) {
     PPG_CUDA(c, dalloc(&x->bad, R));
     PPG_CUDA(c, dalloc(&x->edge_off, R + 1));
     PPG_CUDA(c, dalloc(&x->order, R));
+    PPG_CUDA(c, dalloc(&x->row_hdr, R * 3));
     PPG_CUDA(c, dalloc(&x->l_idx, B * R * X_LIST));
     PPG_CUDA(c, dalloc(&x->l_d, B * R * X_LIST));
     PPG_CUDA(c, dalloc(&x->l_cnt, B * R));
@@ -892,6 +911,7 @@ int run_extend(ppg_ctx* c, const FrameSrc& src, const FrameGraphSrc& gsrc, int f
     wp.src = src;
     wp.gsrc = gsrc;
     wp.order = x->order;
+    wp.row_hdr = x->row_hdr;
     wp.rowp = s->rowp;
     wp.map_f32 = s->map_f32;
     wp.kinfo = s->kinfo;
@@ -963,7 +983,7 @@ int fetch_extend(ppg_ctx* c, int frames) {
 void extend_destroy(AssocState* s) {
     ExtendState* x = s->ext;
     if (!x) return;
-    void* bufs[] = {x->observed, x->bad, x->edge_ok, x->edge_off, x->edge_other, x->order, x->l_idx, x->l_d, x->l_cnt,
+    void* bufs[] = {x->row_hdr, x->observed, x->bad, x->edge_ok, x->edge_off, x->edge_other, x->order, x->l_idx, x->l_d, x->l_cnt,
                     x->tracked, x->kp_mp, x->kedge_me, x->result, x->g_es, x->g_ee, x->g_coff, x->g_cidx,
                     x->zero_i, x->ident, x->row_node, x->kp_node, x->ones_u8};
     for (void* b : bufs)
@@ -1025,8 +1045,19 @@ int ppg_upload_map_graph(ppg_ctx* c, const ppg_map_graph* g) {
         PPG_CUDA(c, cudaMemcpyAsync(x->edge_other, g->edge_other, (size_t)ne * 4, cudaMemcpyHostToDevice, c->st));
         PPG_CUDA(c, cudaMemcpyAsync(x->edge_ok, g->edge_ok, (size_t)ne, cudaMemcpyHostToDevice, c->st));
     }
-    if (!order.empty())
+    std::vector<int32_t> hdr(order.size() * 12, -1);
+    for (size_t q = 0; q < order.size(); q++) {
+        const int r = order[q], e0 = g->edge_off[r], ne_r = g->edge_off[r + 1] - e0;
+        int32_t* hq = &hdr[q * 12];
+        hq[0] = r;
+        hq[1] = e0;
+        hq[2] = ne_r;
+        for (int k = 0; k < X_PRE && k < ne_r; k++) hq[3 + k] = g->edge_ok[e0 + k] ? g->edge_other[e0 + k] : -1;
+    }
+    if (!order.empty()) {
         PPG_CUDA(c, cudaMemcpyAsync(x->order, order.data(), order.size() * 4, cudaMemcpyHostToDevice, c->st));
+        PPG_CUDA(c, cudaMemcpyAsync(x->row_hdr, hdr.data(), hdr.size() * 4, cudaMemcpyHostToDevice, c->st));
+    }
     PPG_CUDA(c, cudaStreamSynchronize(c->st));
     x->P = P;
     x->nc = (int)order.size();
