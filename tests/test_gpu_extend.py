@@ -281,3 +281,29 @@ def test_extend_batch_with_device_projection():
         assert n_acc > 100
     finally:
         e.close()
+
+
+def test_extend_is_deterministic_over_repeats():
+    """The walk synchronises 256 threads through shared memory; a missing barrier would show up as run-to-run
+    differences.  40 repeats of a seed-rich case (and of the batch form on three contexts' worth of frames) must
+    give the same record every time."""
+    from ppg_slam_b200 import capi
+    cam = cameras.UMA
+    rs = np.random.RandomState(77)
+    kx, ky, fd, es, ee, coff, cidx = _frame_graph(rs, cam, 900, 2600)
+    m = 12000
+    inp = synth.extend_inputs(9, fd, np.stack([kx, ky], 1), es, ee, m, cam.width, cam.height, th=10.0,
+                              planted_frac=0.5, clean=False)
+    ref = _oracle(cam, inp, kx, ky, fd, es, ee, coff, cidx, 10.0, 0.8)
+    e = capi.Extractor(cam, max_batch=1, max_map_points=16384, junction_max_num=1000)
+    try:
+        e.upload_map(inp["map_desc"])
+        e.upload_map_graph(inp["candidate"], inp["observed"], inp["bad"], inp["edge_off"], inp["edge_other"],
+                           inp["edge_ok"])
+        for _ in range(40):
+            got = e.extend_map_matches(kx, ky, fd, inp["kp_mp"], es, ee, coff, cidx, inp["proj_uv"], inp["view_cos"],
+                                       inp["tracked"], 10.0, 0.8)
+            _same(got, ref)
+        assert got["n_grown"] > 100
+    finally:
+        e.close()
