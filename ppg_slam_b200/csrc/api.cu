@@ -670,6 +670,22 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
     PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_out), (size_t)B * p.lay.total));
     memset(c->h_out, 0, (size_t)B * p.lay.total);
     p.out = c->d_out;
+    p.scan_fused = 0;
+    // The junction head's epilogue (convPb: softmax + depth-to-space) also does the threshold scan of detectKeyPoint:
+    // candidate list, NMS state map and counters come out of the same registers that hold the probabilities.
+    // PPG_FUSE_SCAN=0 keeps the separate scan kernel (A/B comparison; ppg_extract_from_maps always uses it).
+    c->fuse_scan = true;
+    if (const char* e = getenv("PPG_FUSE_SCAN")) c->fuse_scan = atoi(e) != 0;
+    if (c->fuse_scan)
+        for (auto& l : c->tc)
+            if (l.L.p.mode == EPI_SOFTMAX_D2S) {
+                l.L.p.scan_cand = p.cand;
+                l.L.p.scan_counters = p.counters;
+                l.L.p.scan_state2 = p.nms_smem ? p.state2 : nullptr;
+                l.L.p.scan_state = p.nms_smem ? nullptr : p.state;
+                l.L.p.scan_thresh = p.junction_thresh;
+                l.L.p.scan_radius = p.nms_radius;
+            }
     PPG_CUDA(c, post_init_attrs(p));
     PPG_CUDA(c, cudaDeviceSynchronize());
     guard.ok = true;
@@ -789,6 +805,8 @@ static int enqueue_run(ppg_ctx* c, int n) {
         return c->st;
     };
     bool first = true, forked = false;
+    if (c->fuse_scan)  // the junction head's epilogue appends candidates: counters start at zero
+        PPG_CUDA(c, cudaMemsetAsync(c->post.counters, 0, sizeof(int) * 8 * n, c->st));
     for (auto& l : c->tc) {
         cudaStream_t s = stream_of(l.name);
         const bool head = !strncmp(l.name, "convP", 5) || !strncmp(l.name, "convD", 5) || !strncmp(l.name, "edge", 4);
@@ -813,6 +831,7 @@ static int enqueue_run(ppg_ctx* c, int n) {
     }
     PostParams p = c->post;
     p.B = n;
+    p.scan_fused = c->fuse_scan ? 1 : 0;
     cudaStream_t s_heat = fork ? c->st2 : c->st, s_desc = fork ? c->st3 : c->st;
     PPG_CUDA(c, edge_tail_launch(c->e2, c->we3, c->be3, c->we1, c->be1b, c->heat_raw, n, c->H / 2, c->W / 2, s_heat));
     c->launches++;

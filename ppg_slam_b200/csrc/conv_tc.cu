@@ -297,14 +297,81 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     v[j] = expf(v[j] - m);
                     sum += v[j];
                 }
+#pragma unroll
+                for (int j = 0; j < 64; j++) v[j] = v[j] / sum;
+                const int Wf = p.W * 8, Hf = p.H * 8;
                 if (inb) {
-                    const int Wf = p.W * 8;
-                    float* dst = reinterpret_cast<float*>(p.out) + ((size_t)t.n * p.H * 8 + 8 * y) * Wf + 8 * x;
+                    float* dst = reinterpret_cast<float*>(p.out) + ((size_t)t.n * Hf + 8 * y) * Wf + 8 * x;
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         float4* o = reinterpret_cast<float4*>(dst + (size_t)i * Wf);
-                        o[0] = make_float4(v[8 * i] / sum, v[8 * i + 1] / sum, v[8 * i + 2] / sum, v[8 * i + 3] / sum);
-                        o[1] = make_float4(v[8 * i + 4] / sum, v[8 * i + 5] / sum, v[8 * i + 6] / sum, v[8 * i + 7] / sum);
+                        o[0] = make_float4(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3]);
+                        o[1] = make_float4(v[8 * i + 4], v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
+                    }
+                }
+                if (p.scan_cand) {
+                    // threshold scan (PPGExtractor.cpp:168-176): `!(score < thresh)` as the reference's `continue`
+                    // on `<`; pixels closer than R to the border can never be accepted nor suppress (:190-193)
+                    const int R = p.scan_radius;
+                    const size_t HWf = (size_t)Hf * Wf;
+                    int c = 0, call = 0;
+                    if (inb) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int py = 8 * y + i;
+                            const bool yin = py >= R && py <= Hf - R - 1;
+                            uint32_t bits = 0;  // 2 bits per pixel of the row
+                            uint32_t b_lo = 0, b_hi = 0;  // one byte per pixel
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const int px = 8 * x + j;
+                                const bool pass = !(v[8 * i + j] < p.scan_thresh);
+                                const bool keep = pass && yin && px >= R && px <= Wf - R - 1;
+                                call += pass;
+                                c += keep;
+                                if (keep) {
+                                    bits |= 1u << (2 * j);
+                                    if (j < 4) b_lo |= 1u << (8 * j); else b_hi |= 1u << (8 * (j - 4));
+                                }
+                            }
+                            const size_t pix0 = (size_t)py * Wf + 8 * x;
+                            if (p.scan_state2)
+                                *reinterpret_cast<uint16_t*>(p.scan_state2 + (size_t)t.n * (HWf / 4) + pix0 / 4) = (uint16_t)bits;
+                            else
+                                *reinterpret_cast<uint2*>(p.scan_state + (size_t)t.n * HWf + pix0) = make_uint2(b_lo, b_hi);
+                        }
+                    }
+                    // warp-aggregated append (the whole warp is here: the mode test is uniform)
+                    int inc = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+                        if (lane >= d) inc += o;
+                    }
+                    const int tot = __shfl_sync(0xffffffffu, inc, 31);
+                    int call_w = call;
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) call_w += __shfl_xor_sync(0xffffffffu, call_w, d);
+                    int base = 0;
+                    if (lane == 0) {
+                        if (tot) base = atomicAdd(&p.scan_counters[t.n * 8 + 0], tot);
+                        if (call_w) atomicAdd(&p.scan_counters[t.n * 8 + 1], call_w);
+                    }
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (c) {
+                        uint32_t* cl = p.scan_cand + (size_t)t.n * HWf + base + inc - c;
+                        const int R2 = R;
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int py = 8 * y + i;
+                            const bool yin = py >= R2 && py <= Hf - R2 - 1;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const int px = 8 * x + j;
+                                if (!(v[8 * i + j] < p.scan_thresh) && yin && px >= R2 && px <= Wf - R2 - 1)
+                                    *cl++ = (uint32_t)(py * Wf + px);
+                            }
+                        }
                     }
                 }
             } else if ((p.N & 63) == 0) {
@@ -637,6 +704,12 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
     p.bias = bias;
     p.out = out;
     p.out_ld = out_ld;
+    p.scan_cand = nullptr;
+    p.scan_counters = nullptr;
+    p.scan_state2 = nullptr;
+    p.scan_state = nullptr;
+    p.scan_thresh = 0.f;
+    p.scan_radius = 0;
     L.cin = cin;
     L.cout = cout_padded;
     p.tile_w_log2 = 4;

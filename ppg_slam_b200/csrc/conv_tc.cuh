@@ -41,6 +41,15 @@ struct ConvTcParams {
     const float* bias; // [N]
     void* out;
     int out_ld;        // channels per output pixel in the destination tensor
+    // EPI_SOFTMAX_D2S only: the threshold scan of detectKeyPoint (PPGExtractor.cpp:168-176) fused into the epilogue --
+    // every thread has the 64 probabilities of its coarse cell in registers, so the candidate list and the NMS state
+    // map are written here and the H x W map is not read again for it (scan_cand == nullptr: not fused)
+    uint32_t* scan_cand;    // [B][H*W*64] pixel indices of the in-border candidates (unordered)
+    int* scan_counters;     // [B][8]: 0 in-border candidates, 1 pixels >= threshold
+    uint8_t* scan_state2;   // [B][H*W*16] 2 bits per pixel (shared-memory NMS), or
+    uint8_t* scan_state;    // [B][H*W*64] one byte per pixel (global-memory NMS)
+    float scan_thresh;
+    int scan_radius;
 };
 
 // Bias of one layer, passed BY VALUE as a __grid_constant__ kernel parameter: the epilogue then reads it from the

@@ -1456,15 +1456,18 @@ cudaError_t post_init_attrs(const PostParams& p) {
 
 cudaError_t post_keypoints_launch(const PostParams& p, cudaStream_t st, long long* launches) {
     const int HW = p.H * p.W;
-    cudaError_t e = cudaMemsetAsync(p.counters, 0, sizeof(int) * 8 * p.B, st);
-    if (e != cudaSuccess) return e;
-    dim3 g((HW / 4 + 255) / 256, p.B);
-    scan_kernel<<<g, 256, 0, st>>>(p);
+    if (!p.scan_fused) {
+        cudaError_t e = cudaMemsetAsync(p.counters, 0, sizeof(int) * 8 * p.B, st);
+        if (e != cudaSuccess) return e;
+        dim3 g((HW / 4 + 255) / 256, p.B);
+        scan_kernel<<<g, 256, 0, st>>>(p);
+        *launches += 1;
+    }
     if (p.nms_smem)
         nms_smem_kernel<<<p.B, 1024, post_nms_smem(p), st>>>(p);
     else
         nms_global_kernel<<<p.B, 1024, post_nms_smem(p), st>>>(p);
-    *launches += 2;
+    *launches += 1;
     return cudaGetLastError();
 }
 

@@ -53,6 +53,7 @@ struct PostParams {
     uint8_t* state;     // [B][H*W]   0 none, 1 undecided candidate, 2 accepted, 3 suppressed
     uint8_t* state2;    // [B][H*W/4] the same, 2 bits per pixel (shared-memory NMS variant)
     int nms_smem;       // 1: state2 + nms_smem_kernel, 0: state + nms_global_kernel
+    int scan_fused;     // 1: candidates / state / counters were written by the junction head's epilogue (conv_tc.cu)
     uint32_t* cand;     // [B][H*W]   pixel indices of in-border candidates (unordered)
     int* counters;      // [B][8]     0: candidates in border, 1: pixels >= threshold, 2: inter_pool entries used
     int acc_cap;        // NMS survivors that can be ranked (power of two)

@@ -368,3 +368,34 @@ def test_two_contexts_on_two_threads(ex_euroc):
                 np.testing.assert_array_equal(got["desc"], want[f]["desc"])
     finally:
         other.close()
+
+
+@pytest.mark.parametrize("variant", ["fused-scan", "scan-kernel", "fused-scan-global-nms"])
+def test_full_path_equals_post_processing_of_its_own_maps(variant, monkeypatch):
+    """The threshold scan fused into the junction head's epilogue (candidates, NMS state map, counters written by
+    convPb) must give exactly the record the stand-alone post-processing gives on the SAME dense maps -- the path that
+    is bit-exact against the oracle (ppg_extract_from_maps); PPG_FUSE_SCAN=0 keeps the separate scan kernel."""
+    from ppg_slam_b200 import capi
+    if variant == "scan-kernel":
+        monkeypatch.setenv("PPG_FUSE_SCAN", "0")
+    if variant == "fused-scan-global-nms":
+        monkeypatch.setenv("PPG_NMS_GLOBAL", "1")
+    cam = cameras.EUROC
+    frames = [synth.frame(s, cam.width, cam.height) for s in (0, 5, 9)]
+    frames.append(np.full((cam.height, cam.width), 90, np.uint8))  # flat frame: no keypoints
+    e = capi.Extractor(cam, max_batch=4)
+    try:
+        full = e.run(frames)
+        maps = [e.get_maps(f) for f in range(4)]
+        again = e.run_from_maps(np.stack([m["prob"] for m in maps]), np.stack([m["heat"] for m in maps]),
+                                np.stack([m["desc"] for m in maps]))
+        for f in range(4):
+            a, b = full[f], again[f]
+            assert a["n_kp"] == b["n_kp"] and a["n_edges"] == b["n_edges"] and a["n_cand"] == b["n_cand"]
+            for k in ("px", "py", "out", "edge_start", "edge_end", "conn_off", "conn_idx", "col_off", "col_pairs"):
+                np.testing.assert_array_equal(a[k], b[k], err_msg="%s frame %d" % (k, f))
+            np.testing.assert_array_equal(a["score"].view(np.uint32), b["score"].view(np.uint32))
+            np.testing.assert_array_equal(a["desc"].view(np.uint32), b["desc"].view(np.uint32))
+        assert full[0]["n_kp"] > 200 and full[3]["n_kp"] == 0
+    finally:
+        e.close()
