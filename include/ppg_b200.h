@@ -310,7 +310,8 @@ typedef struct {
     const int32_t* conn_idx;
     const int32_t* kedge_me;  /* n_edges: F.mvpMapEdges[e] as a CSR position, -1 = nullptr; NULL = all -1 */
     const float* proj_uv;     /* n_points x 2: mTrackProjX/Y (read for candidate rows only) */
-    const float* view_cos;    /* n_points */
+    const float* view_cos;    /* n_points.  Both NULL: use the projections ppg_assoc_stage_poses left on the device
+                                 (Frame::CheckInFrustum there; rows not in view are no candidates) */
     const uint8_t* tracked;   /* n_points: mnTrackedbyFrame == F.mnId; NULL = none */
     float th, ratio;
 } ppg_extend_in;

@@ -235,6 +235,54 @@ inline SearchResult search_window(ppg_ctx* ctx, FrameLike& F, const std::vector<
     return r;
 }
 
+// MSTracking::SearchLocalPoints (system/src/Tracking.cpp:978-1008) = Frame::CheckInFrustum over the local map +
+// ExtendMapMatches.  The first half on the GPU: map geometry uploaded once per local-map update, one pose per frame.
+// Writes mbTrackInView / mTrackProjX / mTrackProjY / mTrackDepth / mTrackViewCos back and calls IncreaseVisible()
+// (map/src/Frame.cpp:252-259) so that code reading those members keeps working.  `rows` = the map points of the
+// resident table, in table order.
+inline void upload_map_geometry(ppg_ctx* ctx, const std::vector<MapPoint*>& rows) {
+    const size_t M = rows.size();
+    std::vector<float> P(3 * M), Nn(3 * M), dmin(M), dmax(M);
+    for (size_t m = 0; m < M; m++) {
+        const auto p = rows[m]->GetWorldPos();
+        const auto n = rows[m]->GetNormal();
+        for (int k = 0; k < 3; k++) {
+            P[3 * m + k] = p[k];
+            Nn[3 * m + k] = n[k];
+        }
+        dmin[m] = rows[m]->GetMinDistanceInvariance();
+        dmax[m] = rows[m]->GetMaxDistanceInvariance();
+    }
+    check(ppg_upload_map_geometry(ctx, P.data(), Nn.data(), dmin.data(), dmax.data(), (int)M), ctx,
+          "ppg_upload_map_geometry");
+}
+
+inline void check_in_frustum(ppg_ctx* ctx, Frame& F, const std::vector<MapPoint*>& rows, float viewingCosLimit,
+                             float th, float nnratio) {
+    float R[9], t[3], O[3];
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) R[3 * r + c] = F.mRcw(r, c);
+        t[r] = F.mtcw[r];
+        O[r] = F.mOw[r];
+    }
+    const int M = (int)rows.size();
+    check(ppg_assoc_stage_poses(ctx, 1, M, R, t, O, viewingCosLimit, th, nnratio), ctx, "ppg_assoc_stage_poses");
+    std::vector<uint8_t> in_view(M);
+    std::vector<float> uv(2 * (size_t)M), depth(M), vc(M);
+    check(ppg_frustum_fetch(ctx, 1, in_view.data(), uv.data(), depth.data(), vc.data()), ctx, "ppg_frustum_fetch");
+    for (int m = 0; m < M; m++) {
+        MapPoint* p = rows[m];
+        p->mbTrackInView = in_view[m] != 0;
+        p->mTrackProjX = uv[2 * m];
+        p->mTrackProjY = uv[2 * m + 1];
+        p->mTrackDepth = depth[m];
+        if (in_view[m]) {
+            p->mTrackViewCos = vc[m];
+            p->IncreaseVisible();
+        }
+    }
+}
+
 // Frame::ComputeBoW (map/src/Frame.cpp:331-340): mpVoc->transform(descriptors, mBowVec, mFeatVec, 4) on the GPU.  The
 // vocabulary is uploaded once (ppg_upload_vocabulary, from the blob tools/export_vocabulary.py writes next to the .gz).
 // `FrameLike` is Frame or KeyFrame (mDescriptors, mBowVec, mFeatVec).

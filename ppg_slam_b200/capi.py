@@ -458,7 +458,8 @@ class Extractor:
         i32p, u8p = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
         f32a = lambda a: np.ascontiguousarray(a, np.float32)
         i32a = lambda a: np.ascontiguousarray(a, np.int32)
-        kx, ky, fd, uv, vc = f32a(kp_x), f32a(kp_y), f32a(frame_desc), f32a(proj_uv), f32a(view_cos)
+        kx, ky, fd = f32a(kp_x), f32a(kp_y), f32a(frame_desc)
+        uv, vc = (f32a(proj_uv), f32a(view_cos)) if proj_uv is not None else (None, None)
         es, ee, coff, cidx = i32a(edge_start), i32a(edge_end), i32a(conn_off), i32a(conn_idx)
         a = ExtendIn()
         a.n_kp, a.n_edges = len(kx), len(es)
@@ -474,7 +475,8 @@ class Extractor:
             k = i32a(kedge_me)
             keep.append(k)
             a.kedge_me = k.ctypes.data_as(i32p)
-        a.proj_uv, a.view_cos = _fp(uv), _fp(vc)
+        if uv is not None:  # else: projections staged on the device by assoc_stage_poses
+            a.proj_uv, a.view_cos = _fp(uv), _fp(vc)
         if tracked is not None:
             t = np.ascontiguousarray(tracked, np.uint8)
             keep.append(t)

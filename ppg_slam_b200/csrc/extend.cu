@@ -1097,8 +1097,19 @@ int ppg_extend_map_matches(ppg_ctx* c, const ppg_extend_in* in, ppg_extend_out* 
                 if (in->kp_mp[i] < -2 || in->kp_mp[i] >= P)
                     return set_err(c, PPG_ERR_ARG, "ppg_extend_map_matches: kp_mp row out of range");
     }
-    int rc = assoc_stage_rows(c, 1, P, in->proj_uv, in->view_cos, in->th, in->ratio);
-    if (rc != PPG_OK) return rc;
+    int rc;
+    if (!in->proj_uv && !in->view_cos) {
+        // projections already on the device: Frame::CheckInFrustum ran there (ppg_assoc_stage_poses, one frame)
+        if (!s->use_in_view || s->staged_rows != P || s->staged_frames < 1)
+            return set_err(c, PPG_ERR_ARG,
+                           "ppg_extend_map_matches: proj_uv / view_cos are null but no poses were staged for the "
+                           "n_points rows (ppg_assoc_stage_poses)");
+        s->th = in->th;
+        s->ratio = in->ratio;
+        s->mode = 0;
+    } else if ((rc = assoc_stage_rows(c, 1, P, in->proj_uv, in->view_cos, in->th, in->ratio)) != PPG_OK) {
+        return rc;
+    }
     if (N > 0) {
         PPG_CUDA(c, cudaMemcpyAsync(s->kx, in->kp_x, (size_t)N * 4, cudaMemcpyHostToDevice, c->st));
         PPG_CUDA(c, cudaMemcpyAsync(s->ky, in->kp_y, (size_t)N * 4, cudaMemcpyHostToDevice, c->st));

@@ -12,6 +12,8 @@ int shim_instantiate(GeometricCamera* cam, Frame& F, std::vector<MapPoint*>& mps
     std::vector<uint8_t> free_mask(F.mvKeysUn.size(), 1);
     int n = (int)ppg_shim::search_window(ex.context(), F, mps, uv, free_mask, 15.f, 0.8f).accept.size();        // :31-87
     n += (int)ppg_shim::search_window(ex.context(), F, mps, uv, free_mask, 3.f, 0.7f, 5.99).accept.size();     // Fuse
+    ppg_shim::upload_map_geometry(ex.context(), mps);
+    ppg_shim::check_in_frustum(ex.context(), F, mps, 0.5f, 10.f, 0.8f);  // Frame.cpp:223-260
     ppg_shim::compute_bow(ex.context(), F);  // Frame.cpp:331-340
     KeyFrame kf;
     std::vector<MapPoint*> bowm;

@@ -57,8 +57,21 @@ struct MapEdge {
     MapPoint* theOtherPt(MapPoint* p) { return p == mpMPs ? mpMPe : (p == mpMPe ? mpMPs : nullptr); }
     bool isBad() { return mbBad; }
 };
+struct Vec3f {
+    float v[3];
+    float operator[](int i) const { return v[i]; }
+};
+struct Mat3f {
+    float m[9];
+    float operator()(int r, int c) const { return m[3 * r + c]; }
+};
 struct MapPoint {
-    float mTrackProjX, mTrackProjY, mTrackViewCos;
+    float mTrackProjX, mTrackProjY, mTrackViewCos, mTrackDepth;
+    Vec3f GetWorldPos() { return Vec3f(); }
+    Vec3f GetNormal() { return Vec3f(); }
+    float GetMinDistanceInvariance() { return 0.f; }
+    float GetMaxDistanceInvariance() { return 0.f; }
+    void IncreaseVisible(int = 1) {}
     bool mbTrackInView;
     long unsigned int mnTrackedbyFrame;
     int Observations() { return 0; }
@@ -72,6 +85,8 @@ struct KeyFrame {
     std::vector<MapPoint*> GetMapPointMatches() { return {}; }
 };
 struct Frame {
+    Mat3f mRcw;
+    Vec3f mtcw, mOw;
     std::map<unsigned int, double> mBowVec;                      // DBoW3::BowVector
     std::map<unsigned int, std::vector<unsigned int>> mFeatVec;  // DBoW3::FeatureVector
     long unsigned int mnId;

@@ -307,3 +307,41 @@ def test_extend_is_deterministic_over_repeats():
         assert got["n_grown"] > 100
     finally:
         e.close()
+
+
+def test_extend_single_frame_with_staged_poses():
+    """ppg_extend_map_matches with proj_uv = view_cos = NULL consumes the projections Frame::CheckInFrustum left on the
+    device (ppg_assoc_stage_poses) -- the SearchLocalPoints sequence of the shim."""
+    from oracle import post_ref as O
+    from ppg_slam_b200 import capi
+    cam = cameras.EUROC
+    rs = np.random.RandomState(21)
+    kx, ky, fd, es, ee, coff, cidx = _frame_graph(rs, cam, 300, 600)
+    M = 5000
+    inp = synth.extend_inputs(8, fd, np.stack([kx, ky], 1), es, ee, M, cam.width, cam.height, th=10.0, clean=False)
+    z = rs.uniform(2.0, 9.0, M).astype(np.float32)
+    fx, fy, cx, cy = cam.K[0], cam.K[4], cam.K[2], cam.K[5]
+    P = np.stack([(inp["proj_uv"][:, 0] - cx) / fx * z, (inp["proj_uv"][:, 1] - cy) / fy * z, z], 1).astype(np.float32)
+    nrm = (P / np.linalg.norm(P, axis=1, keepdims=True)).astype(np.float32)
+    d = np.linalg.norm(P, axis=1)
+    dmin, dmax = (0.5 * d).astype(np.float32), (2.0 * d).astype(np.float32)
+    g = synth.frustum_inputs(5, cam, 8, n_frames=1)
+    Rcw, tcw = g["Rcw"], (g["tcw"] * 0.1).astype(np.float32)
+    Ow = np.stack([-(Rcw[0].T @ tcw[0])]).astype(np.float32)
+    fr = O.check_in_frustum(cam, Rcw[0], tcw[0], Ow[0], P, nrm, dmin, dmax, 0.5)
+    fi = dict(inp, proj_uv=fr["proj_uv"], view_cos=fr["view_cos"], candidate=inp["candidate"] & fr["in_view"])
+    ref = _oracle(cam, fi, kx, ky, fd, es, ee, coff, cidx, 10.0, 0.8)
+    e = capi.Extractor(cam, max_batch=1, max_map_points=8192)
+    try:
+        e.upload_map(inp["map_desc"])
+        e.upload_map_graph(inp["candidate"], inp["observed"], inp["bad"], inp["edge_off"], inp["edge_other"],
+                           inp["edge_ok"])
+        e.upload_map_geometry(P, nrm, dmin, dmax)
+        with pytest.raises(capi.PpgError):  # nothing staged yet
+            e.extend_map_matches(kx, ky, fd, inp["kp_mp"], es, ee, coff, cidx, None, None, inp["tracked"], 10.0, 0.8)
+        e.assoc_stage_poses(Rcw, tcw, Ow, M, 0.5, 10.0, 0.8)
+        got = e.extend_map_matches(kx, ky, fd, inp["kp_mp"], es, ee, coff, cidx, None, None, inp["tracked"], 10.0, 0.8)
+        _same(got, ref)
+        assert got["n_accepted"] > 50
+    finally:
+        e.close()
