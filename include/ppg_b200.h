@@ -51,7 +51,7 @@ typedef struct {
     float K[9];               /* GeometricCamera::toK(), row major */
     float D[4];               /* GeometricCamera::toD(): pinhole k1 k2 p1 p2, KB8 k0..k3 */
     int fisheye;              /* mnType == CAM_FISHEYE */
-    const char* weights_path; /* flat export of net/*.pt (tools/export_weights.py) */
+    const char* weights_path; /* flat export of the net .pt files (tools/export_weights.py) */
     float junction_thresh;    /* JUNCTION_THRESH 1/128 */
     int junction_nms_radius;  /* JUNCTION_NMS_RADIUS 4 (<= 8) */
     int junction_max_num;     /* JUNCTION_MAX_NUM 500 */

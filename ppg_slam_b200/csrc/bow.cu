@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) bow_vector_kernel(FrameSrc src, int ncap,
                                                          int* __restrict__ nb_out) {
     __shared__ unsigned long long key[BOW_NCAP];
     __shared__ int s_start[BOW_NCAP + 1];
-    __shared__ int s_cnt, s_nb;
+    __shared__ int s_nb;
     __shared__ double s_norm;
     const int f = blockIdx.x, tid = threadIdx.x;
     const int n = min(src.n_of(f), ncap);
@@ -134,7 +134,6 @@ __global__ void __launch_bounds__(256) bow_vector_kernel(FrameSrc src, int ncap,
             cnt++;
         }
         s_start[nbv] = cnt;
-        s_cnt = cnt;
         s_nb = nbv;
     }
     __syncthreads();
