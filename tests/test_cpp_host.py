@@ -11,8 +11,7 @@ PKG = os.path.join(ROOT, "ppg_slam_b200")
 
 
 def _build(tmp_path):
-    from ppg_slam_b200 import build
-    build.build()
+    assert os.path.exists(os.path.join(PKG, "libppg_b200.so")), "build the library first (python __graft_entry__.py)"
     exe = str(tmp_path / "abi_host")
     cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
            os.path.join(ROOT, "tests", "cpp", "abi_host.cpp"), "-o", exe, "-L", PKG, "-lppg_b200",
