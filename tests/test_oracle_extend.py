@@ -239,3 +239,44 @@ def test_check_in_frustum_kat(cam):
             assert f(a).view(np.uint32) == f(w).view(np.uint32), (j, a, w)
         n_in += want[0]
     assert 60 < n_in < 500  # every exit of the function is taken by some point
+
+
+@pytest.mark.parametrize("seed", list(range(20)))
+def test_extend_map_matches_random_small_graphs(seed):
+    """A sweep over small random configurations (sizes, edge densities, duplicate and dangling map edges, keypoints
+    without key edges, thresholds): oracle == pointer-graph restatement, plus invariants of the function itself."""
+    cam = cameras.EUROC
+    rs = np.random.RandomState(1000 + seed)
+    n = int(rs.randint(3, 45))
+    M = int(rs.randint(5, 140))
+    ne = int(rs.randint(0, min(3 * n, n * (n - 1) // 2) + 1))
+    kx, ky, fd, es, ee, coff, cidx, conn = random_frame_graph(rs, cam, n, ne)
+    if seed % 3 == 0:  # a tight cluster of keypoints: windows overlap, rows compete for the same keypoints
+        kx = (300 + rs.uniform(0, 60, n)).astype(np.float32)
+        ky = (200 + rs.uniform(0, 40, n)).astype(np.float32)
+    th = float(rs.choice([3.0, 10.0, 15.0]))
+    inp = synth.extend_inputs(seed, fd, np.stack([kx, ky], 1), es, ee, M, cam.width, cam.height, th=th,
+                              planted_frac=float(rs.uniform(0.2, 0.9)), clean=bool(seed % 4 == 1))
+    if seed % 5 == 2 and len(inp["edge_other"]) > 4:  # duplicate map edges (two edges to the same other point)
+        inp["edge_other"][1::7] = inp["edge_other"][0::7][:len(inp["edge_other"][1::7])]
+    ratio = float(rs.choice([0.6, 0.8, 0.95]))
+    got = O.extend_map_matches(cam, inp["map_desc"], inp["candidate"], inp["observed"], inp["bad"], inp["edge_off"],
+                               inp["edge_other"], inp["edge_ok"], inp["proj_uv"], inp["view_cos"], inp["tracked"],
+                               kx, ky, fd, inp["kp_mp"], es, ee, coff, cidx, th=th, ratio=ratio)
+    mps, outside = build_pointer_graph(inp)
+    F = dict(mnId=7, kx=kx, ky=ky, desc=fd, mvKeyEdges=list(zip(es.tolist(), ee.tolist())), mvConnected=conn,
+             mvpMapPoints=[mps[r] if r >= 0 else (outside if r == -2 else None) for r in inp["kp_mp"]],
+             mvpMapEdges=[None] * len(es))
+    want_n = py_extend(cam, F, mps, th, ratio)
+    assert got["nmatches"] == want_n
+    want_kp = [(-1 if q is None else q.row) for q in F["mvpMapPoints"]]
+    assert got["kp_mp"].tolist() == want_kp
+    assert got["kedge_me"].tolist() == [(-1 if e is None else e.uid) for e in F["mvpMapEdges"]]
+    assert got["tracked"].tolist() == [int(p.mnTrackedbyFrame == 7) for p in mps]
+    # invariants: tracking only grows; every newly assigned map point is tracked, not bad, and assigned once
+    assert (got["tracked"] >= inp["tracked"]).all()
+    new = got["kp_mp"][got["kp_mp"] != inp["kp_mp"]]
+    assert (new >= 0).all() and got["tracked"][new].all() and not inp["bad"][new].any()
+    assert got["nmatches"] % 2 == 0 and got["nmatches"] <= 2 * int(inp["candidate"].sum())
+    newly_tracked = np.nonzero(got["tracked"] > inp["tracked"])[0]
+    assert len(newly_tracked) >= got["nmatches"] // 2
