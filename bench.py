@@ -7,10 +7,12 @@ at 752x480 on 1/2/4/8 B200).
   torchrun --nproc-per-node N ... bench.py --gpus N ...     # N>1: one rank per GPU, frames sharded, no collective
 
 One step = one batch of 32 synthetic EuRoC-shaped frames per GPU through the whole path:
-networks (tcgen05 convolutions) -> keypoints -> point-pair graph -> descriptors -> association of every
-frame against a resident table of M map-point descriptors (search core of ExtendMapMatches).
+networks (tcgen05 convolutions) -> keypoints -> point-pair graph -> descriptors -> the whole
+Matcher::ExtendMapMatches of every frame against a resident map of M points + its edge graph (window search with
+the live frame state, assignment, seed growing; --assoc core: the frozen-state search core only; --frustum:
+Frame::CheckInFrustum on the device instead of staged projections).
 `value` times the device work with the frames already in HBM; `e2e` goes through the host-facing calls
-(ppg_extract with HOST frames, ppg_assoc_stage_batch / run_batch / fetch_batch) including all copies.
+(ppg_extract with HOST frames, ppg_assoc_stage_batch + ppg_extend_run_batch / fetch_batch) including all copies.
 Prints ONE JSON line on rank 0.
 """
 import argparse
