@@ -19,6 +19,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=o
 SOURCES = {
     "api.cu": [],
     "conv_tc.cu": [],
+    "conv_t64.cu": [],
     "net_direct.cu": [],
     "conv1a_tc.cu": [],
     "post.cu": ["-fmad=false"],

@@ -278,6 +278,7 @@ static int add_tc_layer(ppg_ctx* c, const Blob& blob, const char* name, const st
     PPG_CUDA(c, cudaMemcpy(li.w, hw.data(), hw.size() * sizeof(__half), cudaMemcpyHostToDevice));
     PPG_CUDA(c, cudaMemcpy(li.bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
     conv_tc_plan(li.L, c->maxB, H, W, cin, N, taps, mode, relu, li.bias, out, out_ld);
+    li.L.wgt = li.w;
     memset(&li.L.hb, 0, sizeof(li.L.hb));
     memcpy(li.L.hb.v, hb.data(), hb.size() * sizeof(float));
     if (!make_act_map(&li.L.mapA, in, c->maxB, H, W, cin, li.L.box_w, li.L.box_h) ||
@@ -459,7 +460,6 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
     c->dev = cfg->device;
     c->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("PPG_GRAPH")) c->use_graph = atoi(e) != 0;
-    if (const char* e = getenv("PPG_FUSE_CONV1A")) c->fuse_conv1a = atoi(e) != 0;
     c->H = H;
     c->W = W;
     c->Hc = H / 8;
@@ -783,15 +783,9 @@ int ppg_run(ppg_ctx* c, int n) {
 
 static int enqueue_run(ppg_ctx* c, int n) {
     stage_mark(c, "start");
-    // PPG_FUSE_CONV1A=1: conv1a is computed inside conv1b's kernel by producer warps (no 64-channel full-resolution
-    // map in HBM).  Measured on B200: 1.87 ms vs 0.93 + conv1a for the two kernels -- four producer warps cannot keep
-    // up with the tile rate and their mma.sync traffic competes with the tcgen05 MMAs -- so it is off by default.
-    const bool fuse1a = c->fuse_conv1a && !c->tc.empty() && c->tc[0].L.v2;
-    if (!fuse1a) {
-        PPG_CUDA(c, conv1a_launch(c->gray, c->w1a, c->b1a, c->a1, n, c->H, c->W, c->st));
-        c->launches++;
-        stage_mark(c, "conv1a");
-    }
+    PPG_CUDA(c, conv1a_tc_launch(c->gray, c->w1a, c->b1a, c->a1, n, c->H, c->W, c->st));
+    c->launches++;
+    stage_mark(c, "conv1a");
     // Small batches leave most of the GPU idle inside every kernel, so the branches of the network and of the
     // post-processing that do not depend on one another are forked onto side streams:
     //   st : backbone -> junction head -> keypoints (scan, NMS)   ...join heat... -> point-pair graph  ...join desc
@@ -805,7 +799,7 @@ static int enqueue_run(ppg_ctx* c, int n) {
         if (!strncmp(name, "convD", 5)) return c->st3;
         return c->st;
     };
-    bool first = true, forked = false;
+    bool forked = false;
     if (c->fuse_scan)  // the junction head's epilogue appends candidates: counters start at zero
         PPG_CUDA(c, cudaMemsetAsync(c->post.counters, 0, sizeof(int) * 8 * n, c->st));
     for (auto& l : c->tc) {
@@ -817,13 +811,9 @@ static int enqueue_run(ppg_ctx* c, int n) {
             PPG_CUDA(c, cudaStreamWaitEvent(c->st3, c->ev_feat, 0));
             forked = true;
         }
-        if (first && fuse1a)
-            PPG_CUDA(c, conv_tc_launch(l.L, n, c->num_sms, s, c->gray, c->w1a, c->b1a));
-        else
-            PPG_CUDA(c, conv_tc_launch(l.L, n, c->num_sms, s));
-        first = false;
+        PPG_CUDA(c, conv_tc_launch(l.L, n, c->num_sms, s));
         c->launches++;
-        stage_mark(c, fuse1a && &l == &c->tc[0] ? "conv1a+conv1b" : l.name);
+        stage_mark(c, l.name);
     }
     if (fork && !forked) {  // no head layer ran on a side stream (cannot happen with the shipped networks)
         PPG_CUDA(c, cudaEventRecord(c->ev_feat, c->st));
@@ -834,7 +824,7 @@ static int enqueue_run(ppg_ctx* c, int n) {
     p.B = n;
     p.scan_fused = c->fuse_scan ? 1 : 0;
     cudaStream_t s_heat = fork ? c->st2 : c->st, s_desc = fork ? c->st3 : c->st;
-    PPG_CUDA(c, edge_tail_launch(c->e2, c->we3, c->be3, c->we1, c->be1b, c->heat_raw, n, c->H / 2, c->W / 2, s_heat));
+    PPG_CUDA(c, edge_tail_tc_launch(c->e2, c->we3, c->be3, c->we1, c->be1b, c->heat_raw, n, c->H / 2, c->W / 2, s_heat));
     c->launches++;
     stage_mark(c, "edge_tail");
     PPG_CUDA(c, post_keypoints_launch(p, c->st, &c->launches));
@@ -962,10 +952,6 @@ int ppg_selftest_conv(ppg_ctx* c, int max_layers, const char** names, float* max
     PPG_CUDA(c, cudaSetDevice(c->dev));
     PPG_CUDA(c, cudaStreamSynchronize(c->st));
     int nl = 0;
-    // the fused path never materialises conv1a's output: produce it with the standalone kernel for frame 0 so that
-    // conv1b can be checked like every other layer
-    PPG_CUDA(c, conv1a_launch(c->gray, c->w1a, c->b1a, c->a1, 1, c->H, c->W, c->st));
-    c->launches++;
     for (auto& l : c->tc) {
         if (nl >= max_layers) break;
         const size_t npix = (size_t)l.H * l.W;

@@ -44,7 +44,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 __global__ void __launch_bounds__(C1_THREADS) conv1a_tc_kernel(const uint8_t* __restrict__ gray, const float* __restrict__ w,
                                                                const float* __restrict__ bias, __half* __restrict__ out,
-                                                               int H, int W, int total_tiles, int swap_lbo_sbo) {
+                                                               int H, int W, int total_tiles) {
     extern __shared__ __align__(1024) uint8_t c1_smem[];
     uint8_t* sA = c1_smem;                       // 2 stages
     uint8_t* sBhi = c1_smem + 2 * C1_A_BYTES;
@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(C1_THREADS) conv1a_tc_kernel(const uint8_t* __
     if (warp == 4) {
         // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
         const uint32_t idesc = ptx::make_idesc_f16(128, 64, 0);
-        const uint32_t a_lbo = swap_lbo_sbo ? 128u : 2048u, a_sbo = swap_lbo_sbo ? 2048u : 128u;
-        const uint32_t b_lbo = swap_lbo_sbo ? 128u : 1024u, b_sbo = swap_lbo_sbo ? 1024u : 128u;
+        const uint32_t a_lbo = 2048u, a_sbo = 128u;
+        const uint32_t b_lbo = 1024u, b_sbo = 128u;
         const uint64_t bhi = make_nosw_desc(ptx::smem_u32(sBhi), b_lbo, b_sbo);
         const uint64_t blo = make_nosw_desc(ptx::smem_u32(sBlo), b_lbo, b_sbo);
         for (int i = 0; i < my_tiles; i++) {
@@ -357,9 +357,6 @@ __global__ void __launch_bounds__(ET_THREADS) edge_tail_tc_kernel(const __half* 
 
 }  // namespace
 
-// -> false when the shape is not covered (the frame must be a whole number of 128-pixel tiles)
-bool conv1a_tc_supported(int H, int W) { return ((long long)H * W) % 128 == 0; }
-
 cudaError_t conv1a_tc_launch(const uint8_t* gray, const float* w, const float* bias, __half* out, int B, int H, int W,
                              cudaStream_t st) {
     // 56 KB of dynamic shared memory per CTA caps the residency at 4 CTAs per SM = 4 x 128 TMEM columns
@@ -370,17 +367,14 @@ cudaError_t conv1a_tc_launch(const uint8_t* gray, const float* w, const float* b
         return cudaFuncSetAttribute(conv1a_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     });
     if (attr_err != cudaSuccess) return attr_err;
-    static const int swap = [] {  // PPG_C1_SWAP=1: LBO / SBO exchanged (descriptor experiment; gives wrong results)
-        const char* s = getenv("PPG_C1_SWAP");
-        return s ? atoi(s) : 0;
-    }();
+    if (((long long)H * W) % 128 != 0) return cudaErrorInvalidValue;  // whole 128-pixel tiles (W, H multiples of 16)
     const int total = (int)((long long)B * H * W / 128);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = total < sms * 4 ? total : sms * 4;
     if (grid <= 0) return cudaSuccess;
-    conv1a_tc_kernel<<<grid, C1_THREADS, SMEM, st>>>(gray, w, bias, out, H, W, total, swap);
+    conv1a_tc_kernel<<<grid, C1_THREADS, SMEM, st>>>(gray, w, bias, out, H, W, total);
     return cudaGetLastError();
 }
 

@@ -421,28 +421,11 @@ struct Conv2Smem {
     float* sbias;
 };
 
-// Fused conv1a producer (flags bit 1): instead of a TMA box of a materialised 64-channel activation map, four warps
-// compute the halo tile of conv1a (u8 -> x/255 -> conv3x3 1->64 + bias + ReLU, PPGExtractor.cpp:151-152) themselves
-// and write it as fp16 into the 128B-swizzled stage the UMMA descriptors expect.  This removes the 46 MB/frame
-// round trip of the conv1a output through HBM and the separate conv1a kernel (0.44 ms per 32 frames).
-//   * fp32 FMAs with the 72 weights of a thread's 8 channels in registers (weights pre-divided by 255, the pixel
-//     goes in as the exact u8 value): one (halo pixel, 8 channels) item = 9 LDS + 72 FFMA + one 16-byte store.
-//     (A mma.sync producer was tried first: 192 legacy HMMAs per tile at ~50 cycles each made the producer the
-//     bottleneck, 1.87 ms for the fused launch.)
-//   * halo pixels outside the image are conv1b's zero padding: zeros, not relu(bias).
-struct Conv1aFuse {
-    const uint8_t* gray;  // [B][H][W]
-    const float* w;       // [64][9]
-    const float* bias;    // [64]
-};
-
-// flags: bit 0 = issue the MMAs of two consecutive tiles interleaved (independent accumulators back to back);
-// bit 1 = fused conv1a producer (warps 6-9 produce the halo, warps 2-5 are the only epilogue group);
-// bits 8.. = timing experiments only (wrong results): 0x100 no halo TMA, 0x200 no epilogue work, 0x400 one tap.
+// flags: bit 0 = issue the MMAs of two consecutive tiles interleaved (independent accumulators back to back).
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const ConvTcParams p, const __grid_constant__ ConvBias cb, const int halo_pitch,
-                const int halo_stage_bytes, const int flags, const Conv1aFuse fuse) {
+                const int halo_stage_bytes, const int flags) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     const int S = p.stages;
@@ -458,8 +441,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tmem_cols = p.N <= 64 ? 256u : 512u;  // four accumulators of N columns
-    const bool pair_mode = (flags & 1) != 0, fused = (flags & 2) != 0;
-    uint8_t* upatch = reinterpret_cast<uint8_t*>(tmem_slot + 4);  // [2][256] fp32 pixel patches of the fused producer
+    const bool pair_mode = (flags & 1) != 0;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < S; i++) {
@@ -507,15 +489,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             int n, y0, x0;
             decode(blockIdx.x + it * gridDim.x, n, y0, x0);
             const uint32_t s = it % S, ph = (it / S) & 1;
-            if (fused) break;  // the halo stages are produced by warps 6-9
             ptx::mbar_wait(&empty[s], ph ^ 1);
             if (ptx::elect_one()) {
-                if ((flags & 0x100) && it >= S) {
-                    ptx::mbar_arrive(&full[s]);
-                } else {
-                    ptx::mbar_expect_tx(&full[s], halo_bytes);
-                    ptx::tma_load_4d(shalo + (size_t)s * halo_stage_bytes, &mapA, &full[s], 0, x0 - 1, y0 - 1, n);
-                }
+                ptx::mbar_expect_tx(&full[s], halo_bytes);
+                ptx::tma_load_4d(shalo + (size_t)s * halo_stage_bytes, &mapA, &full[s], 0, x0 - 1, y0 - 1, n);
             }
             __syncwarp();
         }
@@ -525,7 +502,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             ptx::mbar_wait(wbar, 0);
             ptx::tc_fence_after();
             const uint32_t w_addr = ptx::smem_u32(sw);
-            const int ntaps = (flags & 0x400) ? 1 : 9;
+            const int ntaps = 9;
             const int step = pair_mode ? 2 : 1;
             for (int it = 0; it < my_tiles; it += step) {
                 const int cnt = (pair_mode && it + 1 < my_tiles) ? 2 : 1;
@@ -568,98 +545,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 __syncwarp();
             }
         }
-    } else if (fused && warp >= 6) {
-        // ===================== fused conv1a producer: 4 warps, 128 threads =====================
-        const int ptid = threadIdx.x - 192, pw = warp - 6;
-        const int cg = ptid & 7, pcol = ptid >> 3;  // 8 channels 8 cg .. 8 cg + 7 of halo pixels pcol + 16 i
-        float wr[8][9], br[8];
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            br[c] = fuse.bias[cg * 8 + c];
-#pragma unroll
-            for (int k = 0; k < 9; k++) wr[c][k] = fuse.w[(cg * 8 + c) * 9 + k] * (1.0f / 255.0f);
-        }
-        constexpr int PW_ = CONV2_TILE_W + 4, PH_ = CONV2_TILE_H + 4;  // u8 patch 12 x 20 around the halo
-        float* upf = reinterpret_cast<float*>(upatch);                  // [2][256] patches as fp32
-        auto load_patch = [&](int it, uint32_t (&v)[2]) {
-            v[0] = v[1] = 0u;
-            if (it >= my_tiles) return;
-            int n, y0, x0;
-            decode(blockIdx.x + it * gridDim.x, n, y0, x0);
-            const uint8_t* gimg = fuse.gray + (size_t)n * p.H * p.W;
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int i = ptid + e * 128;
-                if (i < PW_ * PH_) {
-                    const int py = i / PW_, px = i - py * PW_;
-                    const int iy = y0 - 2 + py, ix = x0 - 2 + px;
-                    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v[e] = gimg[(size_t)iy * p.W + ix];
-                }
-            }
-        };
-        uint32_t cur[2];
-        load_patch(0, cur);
-        for (int it = 0; it < my_tiles; it++) {
-            int n, y0, x0;
-            decode(blockIdx.x + it * gridDim.x, n, y0, x0);
-            const uint32_t s = it % S, ph = (it / S) & 1;
-            float* up = upf + (it & 1) * 256;
-            up[ptid] = (float)cur[0];
-            if (ptid + 128 < PW_ * PH_) up[ptid + 128] = (float)cur[1];
-            load_patch(it + 1, cur);  // in flight while this tile is computed
-            ptx::mbar_wait(&empty[s], ph ^ 1);
-            asm volatile("bar.sync 2, 128;" ::: "memory");  // patch visible, stage free for everybody
-            uint8_t* stage = shalo + (size_t)s * halo_stage_bytes;
-            // two halo pixels per iteration: 16 independent FMA chains hide the FFMA / LDS latency of the single
-            // producer warp per scheduler
-#pragma unroll 1
-            for (int hpb = pcol; hpb < 180; hpb += 32) {  // halo pixel hp = 10 hy + hx
-                float u[2][9];
-                bool inside[2];
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int hp = hpb + 16 * e;
-                    const int hy = hp / 10, hx = hp - hy * 10;
-                    const int iy = y0 - 1 + hy, ix = x0 - 1 + hx;
-                    inside[e] = hp < 180 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                    const int base = hp < 180 ? hy * PW_ + hx : 0;
-#pragma unroll
-                    for (int k = 0; k < 9; k++) u[e][k] = up[base + (k / 3) * PW_ + k % 3];
-                }
-                float a[2][8];
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    a[0][c] = br[c];
-                    a[1][c] = br[c];
-                }
-#pragma unroll
-                for (int k = 0; k < 9; k++)
-#pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        a[0][c] = fmaf(u[0][k], wr[c][k], a[0][c]);
-                        a[1][c] = fmaf(u[1][k], wr[c][k], a[1][c]);
-                    }
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int hp = hpb + 16 * e;
-                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                    if (inside[e])
-                        o = make_uint4(pack_half2(fmaxf(a[e][0], 0.f), fmaxf(a[e][1], 0.f)),
-                                       pack_half2(fmaxf(a[e][2], 0.f), fmaxf(a[e][3], 0.f)),
-                                       pack_half2(fmaxf(a[e][4], 0.f), fmaxf(a[e][5], 0.f)),
-                                       pack_half2(fmaxf(a[e][6], 0.f), fmaxf(a[e][7], 0.f)));
-                    // channels 8 cg .. 8 cg + 7 = 16-byte chunk cg of the pixel's 128-byte row, swizzled by (row & 7)
-                    if (hp < 180) *reinterpret_cast<uint4*>(stage + hp * 128 + ((cg ^ (hp & 7)) << 4)) = o;
-                }
-            }
-            ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (ptid == 0) ptx::mbar_arrive(&full[s]);
-        }
     } else {
         const int q = warp & 3, grp = (warp - 2) >> 2;  // two epilogue groups, see conv_tc_kernel
         const int row = q * 32 + lane, h = row >> 3, w = row & 7;
-        for (int it = grp; it < my_tiles; it += fused ? 1 : 2) {
+        for (int it = grp; it < my_tiles; it += 2) {
             const uint32_t acc = it & 3, aph = (it >> 2) & 1;
             int n, y0, x0;
             decode(blockIdx.x + it * gridDim.x, n, y0, x0);
@@ -668,13 +557,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             ptx::mbar_wait(&tfull[acc], aph);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.N;
-            if (!(flags & 0x200))
-                for (int c0 = 0; c0 < p.N; c0 += 64) {
-                    uint32_t r[64];
-                    ptx::tmem_ld64(taddr + c0, r);
-                    ptx::tmem_ld_wait();
-                    epilogue64<1, 8>(p, cb, r, c0, n, y, x, inb, lane);
-                }
+            for (int c0 = 0; c0 < p.N; c0 += 64) {
+                uint32_t r[64];
+                ptx::tmem_ld64(taddr + c0, r);
+                ptx::tmem_ld_wait();
+                epilogue64<1, 8>(p, cb, r, c0, n, y, x, inb, lane);
+            }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
@@ -713,16 +601,23 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
     L.cin = cin;
     L.cout = cout_padded;
     p.tile_w_log2 = 4;
-    // PPG_CONV_V2=0 forces the generic kernel everywhere (A/B comparison); default = halo kernel where it applies.
+    L.v3 = 0;
+    L.wgt = nullptr;
+    // Kernel choice.  PPG_CONV_KERNEL (A/B comparison only; every setting gives the same results):
+    //   unset / 3: transposed kernel (conv_t64.cu) for the 3x3 64 -> 64 layers, halo kernel for the other Cin = 64 layers
+    //   2: halo kernel for every Cin = 64 layer (the round-1 configuration);  1: generic kernel everywhere.
     // Measured on B200 (tools/conv_variants.py): UMMA applies the 128-byte swizzle XOR on absolute shared-memory
     // address bits, so a descriptor may start at any 128-byte row of a swizzled tile with base_offset = 0.
-    int v2mode = 1;
-    if (const char* e = getenv("PPG_CONV_V2")) v2mode = atoi(e);
-    L.v2 = (v2mode != 0 && taps == 9 && cin == 64 && cout_padded <= 128 && cout_padded % 64 == 0) ? 1 : 0;
+    int kmode = 3;
+    if (const char* e = getenv("PPG_CONV_KERNEL")) kmode = atoi(e);
+    if (kmode >= 3 && conv_t64_applies(cin, cout_padded, taps, mode)) {
+        conv_t64_plan(L, maxB, H, W);
+        return;
+    }
+    L.v2 = (kmode >= 2 && taps == 9 && cin == 64 && cout_padded <= 128 && cout_padded % 64 == 0) ? 1 : 0;
     if (L.v2) {
         L.halo_pitch = CONV2_TILE_W + 2;
         L.flags = 1;  // interleaved tile pairs
-        if (const char* e = getenv("PPG_CONV_FLAGS")) L.flags = (int)strtol(e, nullptr, 0);
         L.box_w = L.halo_pitch;
         L.box_h = CONV2_TILE_H + 2;
         p.tiles_x = (W + CONV2_TILE_W - 1) / CONV2_TILE_W;
@@ -758,8 +653,8 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
     L.smem_bytes = S * stage_bytes + 1024 /*align*/ + 20 * 8 + 16 + 256 * 4 + 64;
 }
 
-cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStream_t st, const uint8_t* fuse_gray,
-                           const float* fuse_w, const float* fuse_b) {
+cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStream_t st) {
+    if (L.v3) return conv_t64_launch(L, L.wgt, batch, num_sms, st);
     // one-time kernel attributes; a function-local static initialiser is thread-safe (contexts on several host
     // threads launch through here concurrently)
     static bool attr_done[64];
@@ -777,13 +672,7 @@ cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStrea
     if (grid <= 0) return cudaSuccess;
     if (L.v2) {
         const int stage = (L.halo_pitch * L.box_h * 128 + 1023) / 1024 * 1024;
-        Conv1aFuse fz;
-        fz.gray = fuse_gray;
-        fz.w = fuse_w;
-        fz.bias = fuse_b;
-        const int flags = fuse_gray ? (L.flags | 2) : (L.flags & ~2);
-        conv_tc2_kernel<<<grid, CONV_THREADS, L.smem_bytes, st>>>(L.mapA, L.mapB, p, L.hb, L.halo_pitch, stage, flags,
-                                                                  fz);
+        conv_tc2_kernel<<<grid, CONV_THREADS, L.smem_bytes, st>>>(L.mapA, L.mapB, p, L.hb, L.halo_pitch, stage, L.flags);
     } else {
         conv_tc_kernel<<<grid, CONV_THREADS, L.smem_bytes, st>>>(L.mapA, L.mapB, p, L.hb);
     }

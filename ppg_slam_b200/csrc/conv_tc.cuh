@@ -70,19 +70,24 @@ struct ConvLayer {
     int v2;             // 0 = generic kernel, 1 = halo kernel
     int box_w, box_h;   // TMA box of the activation map (pixels): generic 16 x 8, halo (8+2 | 16) x 18
     int halo_pitch;     // pixels per halo row in shared memory (= box_w)
-    int flags;          // conv_tc2_kernel flags: bit 0 = interleaved tile pairs; 0x100.. timing experiments
+    int flags;          // conv_tc2_kernel flags: bit 0 = interleaved tile pairs
+    // v3 ("transposed") kernel, conv_t64.cu: 3x3, Cin = Cout = 64, weights as the A operand in tensor memory
+    int v3;
+    const __half* wgt;  // [tap][Cout][Cin] fp16 (the transposed kernel loads its A operand from here)
 };
 
 constexpr int CONV_TILE_W = 16, CONV_TILE_H = 8, CONV_A_BYTES = 16384, CONV_THREADS = 320;
 constexpr int CONV2_TILE_W = 8, CONV2_TILE_H = 16;
+constexpr int CONVT_TILE_W = 38, CONVT_TILE_H = 4;  // transposed kernel: output tile, halo 40 x 6
 
 // Fills stages / tiles / smem size for the given shape. Tensor maps are encoded by the caller (api).
 void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded, int taps, int mode, int relu,
                   const float* bias, void* out, int out_ld);
-// fuse_gray != nullptr (halo kernel only): the layer's input is conv1a of that u8 image, computed inside the kernel
-// by producer warps (fuse_w [64][9] fp32, fuse_b [64]) instead of being read through mapA.
-cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStream_t st,
-                           const uint8_t* fuse_gray = nullptr, const float* fuse_w = nullptr,
-                           const float* fuse_b = nullptr);
+cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStream_t st);
+
+// Transposed kernel (conv_t64.cu).
+bool conv_t64_applies(int cin, int cout_padded, int taps, int mode);
+void conv_t64_plan(ConvLayer& L, int maxB, int H, int W);
+cudaError_t conv_t64_launch(const ConvLayer& L, const __half* wgt, int batch, int num_sms, cudaStream_t st);
 
 }  // namespace ppg

@@ -79,7 +79,6 @@ struct ppg_ctx {
     std::map<int, int> graph_launches;  // kernels per replay, for launch_count
     std::map<int, int> run_calls;
     bool fuse_scan = false;   // PPG_FUSE_SCAN=1: threshold scan inside convPb's epilogue (measured: no gain)
-    bool fuse_conv1a = false;  // PPG_FUSE_CONV1A=1 -> conv1a computed by producer warps inside conv1b (measured slower)
     std::vector<cudaEvent_t> ev;
     std::vector<const char*> ev_names;
     int n_ev = 0;

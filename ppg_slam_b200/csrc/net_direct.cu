@@ -1,271 +1,10 @@
-// CUDA-core pieces of the networks: the layers that are not GEMM-shaped (SURVEY.md s.7 K1/K4c/K3a tail).
-//   conv1a_kernel      u8 -> x/255 -> conv3x3 1->64 + ReLU (fp32; |w| reaches 197) -> NHWC fp16
-//   edge_tail_kernel   conv3x3 16->16 (BN folded) + ReLU + pixel_shuffle(2) + conv1x1 4->2 + softmax[:,1]
-//   junction_d2s_kernel softmax over 65 channels, drop dustbin, depth-to-space(8) -> H x W prob map
-//   conv_ref_kernel    plain fp32 direct convolution over NHWC fp16 (debug/validation of conv_tc only)
-// Reference call sites: feature/src/PPGExtractor.cpp:151-154 (inference), :161-162, :242.
+// Validation-only CUDA-core convolution (ppg_selftest_conv): plain fp32 direct convolution over the same NHWC fp16
+// operands the tensor-core kernels consume.  The network itself runs on tcgen05 only (conv_tc.cu, conv_t64.cu,
+// conv1a_tc.cu); the CUDA-core / mma.sync versions of conv1a, the edge-decoder tail and the junction softmax that round 1
+// superseded are gone.
 #include "net_direct.cuh"
 
-#include <stdlib.h>
-
 namespace ppg {
-
-// ------------------------------------------------------------------------------------------------
-// conv1a: 8 threads per pixel column, each owns 8 output channels whose 72 weights live in REGISTERS (the
-// first version read every weight from shared memory: one LDS per FMA, LSU-bound at 4x the FMA time).  A
-// thread walks down TY rows with a sliding 3x3 window, so a pixel costs 3 shared-memory loads and 72 FMAs.
-// One 16-byte store per pixel and thread; a warp writes 4 pixels x 128 B = 512 contiguous bytes.
-// Input tile (+1 halo) staged in shared memory as fp32 already divided by 255.
-__global__ void __launch_bounds__(256, 2) conv1a_kernel(const uint8_t* __restrict__ gray, const float* __restrict__ w,
-                                                        const float* __restrict__ bias, __half* __restrict__ out,
-                                                        int H, int W) {
-    constexpr int TX = 32, TY = 32;
-    __shared__ float tile[TY + 2][TX + 2];
-    const int n = blockIdx.z, x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-    const uint8_t* g = gray + (size_t)n * H * W;
-    for (int i = threadIdx.x; i < (TY + 2) * (TX + 2); i += blockDim.x) {
-        int ty = i / (TX + 2), tx = i - ty * (TX + 2);
-        int y = y0 + ty - 1, x = x0 + tx - 1;
-        float v = 0.f;
-        if (y >= 0 && y < H && x >= 0 && x < W) v = __fdiv_rn((float)g[(size_t)y * W + x], 255.0f);  // :151
-        tile[ty][tx] = v;
-    }
-    const int grp = threadIdx.x & 7, px = threadIdx.x >> 3;
-    // channel pairs (2c, 2c + 1) share one packed FFMA2 (fma.rn.f32x2, new on sm_100): half the issue slots of the
-    // scalar FFMA version, which was FMA-issue bound (ncu: 322 M warp instructions, two thirds FFMA, IPC 0.64)
-    float2 wr[4][9], br[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        br[c] = make_float2(bias[grp * 8 + 2 * c], bias[grp * 8 + 2 * c + 1]);
-#pragma unroll
-        for (int k = 0; k < 9; k++)
-            wr[c][k] = make_float2(w[(grp * 8 + 2 * c) * 9 + k], w[(grp * 8 + 2 * c + 1) * 9 + k]);
-    }
-    __syncthreads();
-    const int x = x0 + px;
-    float r0[3], r1[3], r2[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        r0[k] = tile[0][px + k];
-        r1[k] = tile[1][px + k];
-    }
-    __half* o = out + (((size_t)n * H + y0) * W + x) * 64 + grp * 8;
-#pragma unroll 4
-    for (int py = 0; py < TY; py++) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) r2[k] = tile[py + 2][px + k];
-        float acc[8];
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            // same summation order as the scalar version: bias, then taps in (ky, kx) raster order
-            float2 a = br[c];
-#pragma unroll
-            for (int k = 0; k < 3; k++) a = __ffma2_rn(make_float2(r0[k], r0[k]), wr[c][k], a);
-#pragma unroll
-            for (int k = 0; k < 3; k++) a = __ffma2_rn(make_float2(r1[k], r1[k]), wr[c][3 + k], a);
-#pragma unroll
-            for (int k = 0; k < 3; k++) a = __ffma2_rn(make_float2(r2[k], r2[k]), wr[c][6 + k], a);
-            acc[2 * c] = fmaxf(a.x, 0.f);
-            acc[2 * c + 1] = fmaxf(a.y, 0.f);
-        }
-        if (y0 + py < H && x < W) {
-            __half2 h0 = __floats2half2_rn(acc[0], acc[1]), h1 = __floats2half2_rn(acc[2], acc[3]);
-            __half2 h2 = __floats2half2_rn(acc[4], acc[5]), h3 = __floats2half2_rn(acc[6], acc[7]);
-            uint4 u = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                                 *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-            *reinterpret_cast<uint4*>(o + (size_t)py * W * 64) = u;
-        }
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            r0[k] = r1[k];
-            r1[k] = r2[k];
-        }
-    }
-}
-
-// A warp-level mma.sync version of this layer (exact u8 operands, hi/lo fp16 weights) was measured at 0.58 ms per 32
-// frames against 0.44 ms for the FMA kernel: on B200 the legacy HMMA path issues one m16n8k16 per ~40-56 cycles and
-// sub-partition, slower than 32 FFMA lanes.  The FMA kernel stays.
-cudaError_t conv1a_launch(const uint8_t* gray, const float* w, const float* bias, __half* out, int B, int H, int W,
-                          cudaStream_t st) {
-    static const int use_tc = [] {  // tcgen05 version (conv1a_tc.cu) unless PPG_CONV1A_TC=0 (A/B comparison)
-        const char* e = getenv("PPG_CONV1A_TC");
-        return (e && !atoi(e)) ? 0 : 1;
-    }();
-    if (use_tc && conv1a_tc_supported(H, W)) return conv1a_tc_launch(gray, w, bias, out, B, H, W, st);
-    dim3 grid((W + 31) / 32, (H + 31) / 32, B);
-    conv1a_kernel<<<grid, 256, 0, st>>>(gray, w, bias, out, H, W);
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------------
-// Edge decoder tail.  in: NHWC fp16, 16 channels at (Hh x Wh) = (H/2 x W/2).
-// conv3x3 16->16 is 9 taps of a (16 pixels x 16 ci) x (16 ci x 16 co) product: warp-level mma.sync m16n8k16
-// (fp16 operands, fp32 accumulate) with the A fragments ldmatrix'ed straight out of the fp16 halo tile.  The
-// layer is 0.2 GMAC with N = 16 -- far too small for a tcgen05 tile -- and with the MMAs it is bound by its
-// 4.3 MB/frame of HBM traffic.  The first version (fp32 FMAs, one shared-memory load per FMA) took 0.51 ms per
-// 32 frames.
-// The output-channel order of B is permuted so that thread t = lane%4 of the C fragment holds the four
-// channels {t, 4+t, 8+t, 12+t} = pixel_shuffle(2) sub-pixel (i = t/2, j = t%2); the 4->2 1x1 conv and the
-// 2-way softmax then need no exchange.  w3: [16 out][3][3][16 in] fp32, BN folded.
-__device__ __forceinline__ uint32_t edge_pack_h2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-
-__global__ void __launch_bounds__(128) edge_tail_kernel(const __half* __restrict__ in, const float* __restrict__ w3,
-                                                        const float* __restrict__ b3, const float* __restrict__ w1,
-                                                        const float* __restrict__ b1, float* __restrict__ heat,
-                                                        int Hh, int Wh, int tiles_x, int tiles_y,
-                                                        int total_tiles) {
-    constexpr int TX = 16, TY = 8, PW = TX + 2;
-    // pixel p of the halo tile = 32 bytes; its two 16-byte halves are swapped when (p >> 2) & 1 so that the 8
-    // rows of an ldmatrix 8x8 block (8 consecutive pixels) fall into 8 different 16-byte bank groups
-    __shared__ __align__(16) uint8_t tile[(TY + 2) * PW * 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // B fragments (all 9 taps, both 8-column halves) in registers; column nn of half nh <-> channel
-    // co = 4 * (2 * nh + (nn & 1)) + (nn >> 1)
-    const int t = lane & 3, g = lane >> 2;
-    uint32_t bf[9][2][2];
-    float cb[2][2];
-#pragma unroll
-    for (int nh = 0; nh < 2; nh++) {
-        const int co = 4 * (2 * nh + (g & 1)) + (g >> 1);  // B column index = g
-        const float* wc = w3 + (size_t)co * 9 * 16;
-#pragma unroll
-        for (int tap = 0; tap < 9; tap++) {
-            bf[tap][nh][0] = edge_pack_h2(wc[tap * 16 + 2 * t], wc[tap * 16 + 2 * t + 1]);
-            bf[tap][nh][1] = edge_pack_h2(wc[tap * 16 + 8 + 2 * t], wc[tap * 16 + 8 + 2 * t + 1]);
-        }
-        // C columns of this thread: nn = 2t, 2t+1 -> channels 4*(2nh) + t and 4*(2nh+1) + t
-        cb[nh][0] = b3[4 * (2 * nh) + t];
-        cb[nh][1] = b3[4 * (2 * nh + 1) + t];
-    }
-    float s1[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) s1[k] = w1[k];
-    const float sb10 = b1[0], sb11 = b1[1];
-    const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(tile);
-    const int H = Hh * 2, W = Wh * 2;
-    // persistent blocks: the 36 B-fragment registers are built once and reused for every tile of the block
-    for (int tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
-    const int n = tl / (tiles_x * tiles_y), trem = tl - n * tiles_x * tiles_y;
-    const int y0 = (trem / tiles_x) * TY, x0 = (trem % tiles_x) * TX;
-    const __half* src = in + (size_t)n * Hh * Wh * 16;
-    __syncthreads();  // the previous tile's ldmatrix reads are done
-    for (int i = threadIdx.x; i < (TY + 2) * PW * 2; i += blockDim.x) {
-        const int half8 = i & 1, pi = i >> 1;
-        const int ty = pi / PW, tx = pi - ty * PW;
-        const int y = y0 + ty - 1, x = x0 + tx - 1;
-        uint4 u = make_uint4(0, 0, 0, 0);
-        if (y >= 0 && y < Hh && x >= 0 && x < Wh)
-            u = *reinterpret_cast<const uint4*>(src + ((size_t)y * Wh + x) * 16 + half8 * 8);
-        *reinterpret_cast<uint4*>(tile + pi * 32 + ((half8 ^ ((pi >> 2) & 1)) << 4)) = u;
-    }
-    __syncthreads();
-    float* dst = heat + (size_t)n * H * W;
-    // ldmatrix.x4: lane l supplies row (l & 7) of matrix (l >> 3); matrices 0/1 = pixels 0-7 / 8-15 of the
-    // channel half 0, matrices 2/3 = the same pixels of channel half 1
-    const int lm_px = ((lane >> 3) & 1) * 8 + (lane & 7), lm_half = lane >> 4;
-#pragma unroll
-    for (int mt = 0; mt < 2; mt++) {
-        const int py = warp * 2 + mt;
-        float acc[2][4];
-#pragma unroll
-        for (int nh = 0; nh < 2; nh++) {
-            acc[nh][0] = cb[nh][0];
-            acc[nh][1] = cb[nh][1];
-            acc[nh][2] = cb[nh][0];
-            acc[nh][3] = cb[nh][1];
-        }
-#pragma unroll
-        for (int tap = 0; tap < 9; tap++) {
-            const int pi = (py + tap / 3) * PW + lm_px + tap % 3;
-            const uint32_t addr = tile_addr + pi * 32 + ((lm_half ^ ((pi >> 2) & 1)) << 4);
-            uint32_t a0, a1, a2, a3;
-            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
-                         : "r"(addr));
-#pragma unroll
-            for (int nh = 0; nh < 2; nh++)
-                asm volatile(
-                    "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-                    "{%0,%1,%2,%3};"
-                    : "+f"(acc[nh][0]), "+f"(acc[nh][1]), "+f"(acc[nh][2]), "+f"(acc[nh][3])
-                    : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf[tap][nh][0]), "r"(bf[tap][nh][1]));
-        }
-        const int y = y0 + py;
-#pragma unroll
-        for (int r = 0; r < 2; r++) {  // C rows g and g + 8
-            const int x = x0 + g + 8 * r;
-            // channels 4c + t for c = 0..3
-            const float v0 = fmaxf(acc[0][2 * r], 0.f), v1 = fmaxf(acc[0][2 * r + 1], 0.f);
-            const float v2 = fmaxf(acc[1][2 * r], 0.f), v3 = fmaxf(acc[1][2 * r + 1], 0.f);
-            float l0 = sb10, l1 = sb11;
-            l0 = fmaf(s1[0], v0, l0);
-            l1 = fmaf(s1[4], v0, l1);
-            l0 = fmaf(s1[1], v1, l0);
-            l1 = fmaf(s1[5], v1, l1);
-            l0 = fmaf(s1[2], v2, l0);
-            l1 = fmaf(s1[6], v2, l1);
-            l0 = fmaf(s1[3], v3, l0);
-            l1 = fmaf(s1[7], v3, l1);
-            const float m = fmaxf(l0, l1);
-            const float e0 = expf(l0 - m), e1 = expf(l1 - m);
-            // pixel_shuffle(2): sub-pixel (i, j) = (t >> 1, t & 1); softmax(dim=1)[:,1], PPGExtractor.cpp:242
-            if (y < Hh && x < Wh) dst[(size_t)(2 * y + (t >> 1)) * W + 2 * x + (t & 1)] = e1 / (e0 + e1);
-        }
-    }
-    }
-}
-
-cudaError_t edge_tail_launch(const __half* in, const float* w3, const float* b3, const float* w1, const float* b1,
-                             float* heat, int B, int Hh, int Wh, cudaStream_t st) {
-    static const int use_tc = [] {  // tcgen05 version (conv1a_tc.cu) unless PPG_EDGE_TAIL_TC=0 (A/B comparison)
-        const char* e = getenv("PPG_EDGE_TAIL_TC");
-        return (e && !atoi(e)) ? 0 : 1;
-    }();
-    if (use_tc) return edge_tail_tc_launch(in, w3, b3, w1, b1, heat, B, Hh, Wh, st);
-    const int tiles_x = (Wh + 15) / 16, tiles_y = (Hh + 7) / 8, total = tiles_x * tiles_y * B;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = total < sms * 5 ? total : sms * 5;
-    if (grid <= 0) return cudaSuccess;
-    edge_tail_kernel<<<grid, 128, 0, st>>>(in, w3, b3, w1, b1, heat, Hh, Wh, tiles_x, tiles_y, total);
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------------
-// Junction head tail: logits NHWC fp32 [B][Hc][Wc][ld] (65 valid) -> prob [B][8Hc][8Wc].
-// One warp per coarse cell.  P[8h+i][8w+j] = softmax(logits)[8i+j]  (PPGExtractor.cpp:161-162).
-__global__ void __launch_bounds__(256) junction_d2s_kernel(const float* __restrict__ logits, float* __restrict__ prob,
-                                                           int cells_total, int Hc, int Wc, int ld) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= cells_total) return;
-    const int n = warp / (Hc * Wc), r = warp - n * Hc * Wc, hc = r / Wc, wc = r - hc * Wc;
-    const float* l = logits + (size_t)warp * ld;
-    float a = l[lane], b = l[lane + 32], c = (lane == 0) ? l[64] : -INFINITY;
-    float m = fmaxf(fmaxf(a, b), c);
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
-    float ea = expf(a - m), eb = expf(b - m), ec = (lane == 0) ? expf(c - m) : 0.f;
-    float sum = ea + eb + ec;
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
-    const int W = Wc * 8, H = Hc * 8;
-    float* dst = prob + (size_t)n * H * W;
-    // channel ch -> (i = ch/8, j = ch%8)
-    dst[(size_t)(8 * hc + (lane >> 3)) * W + 8 * wc + (lane & 7)] = ea / sum;
-    dst[(size_t)(8 * hc + 4 + (lane >> 3)) * W + 8 * wc + (lane & 7)] = eb / sum;
-}
-
-cudaError_t junction_d2s_launch(const float* logits, float* prob, int B, int Hc, int Wc, int ld, cudaStream_t st) {
-    int cells = B * Hc * Wc;
-    int blocks = (cells * 32 + 255) / 256;
-    junction_d2s_kernel<<<blocks, 256, 0, st>>>(logits, prob, cells, Hc, Wc, ld);
-    return cudaGetLastError();
-}
 
 // ------------------------------------------------------------------------------------------------
 // Validation-only direct convolution (fp32 accumulate over the same fp16 operands conv_tc consumes).

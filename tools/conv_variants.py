@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Tries the halo-convolution descriptor variants (PPG_CONV_V2=0..4) and reports self-test errors + timings."""
+"""A/B of the convolution kernel choice (PPG_CONV_KERNEL = 1 generic, 2 halo, 3 transposed for the 64 -> 64 layers):
+self-test errors against the CUDA-core reference convolution + per-layer timings at batch 32."""
 import json
 import os
 import sys
@@ -14,8 +15,8 @@ cam = cameras.EUROC
 B = 32
 frames = [synth.frame(s, cam.width, cam.height) for s in range(B)]
 out = {}
-for v in sys.argv[1:] or ["0", "1", "2", "3", "4"]:
-    os.environ["PPG_CONV_V2"] = v
+for v in sys.argv[1:] or ["2", "3"]:
+    os.environ["PPG_CONV_KERNEL"] = v
     try:
         e = capi.Extractor(cam, max_batch=B)
         e.upload(frames)
@@ -36,3 +37,5 @@ for v in sys.argv[1:] or ["0", "1", "2", "3", "4"]:
     except Exception as ex:  # noqa: BLE001
         out[v] = dict(error=str(ex))
     print(v, json.dumps(out[v]), flush=True)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "conv_variants.json"), "w"), indent=1)
