@@ -14,13 +14,14 @@
 #ifndef PPG_B200_H
 #define PPG_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define PPG_API_VERSION 4
+#define PPG_API_VERSION 5
 #define PPG_DESC_DIM 256 /* PPGExtractor::DESC_DIM_SIZE, PPGExtractor.cpp:44 */
 
 typedef enum {
@@ -128,6 +129,23 @@ int ppg_run(ppg_ctx* ctx, int n_frames);
 int ppg_download(ppg_ctx* ctx, int n_frames, ppg_frame_out* out);
 int ppg_sync(ppg_ctx* ctx);
 
+/* ---- pipelined form (one host thread keeps several contexts busy) -----------------------------------------------
+ * The reference's run() blocks on the GPU (PPGExtractor.cpp:125 `torch::cuda::synchronize`); a throughput caller wants
+ * the copies of batch k + 1 behind the kernels of batch k instead.  ppg_extract_async enqueues host -> device copy,
+ * networks, post-processing and the device -> host copy of the records on the ctx stream and returns at once;
+ * ppg_extract_wait blocks until they are done and fills `out` (same records, same return codes as ppg_extract).
+ * Frames that lie in pinned host memory (ppg_host_alloc, or the caller's own buffers after ppg_host_register, e.g. the
+ * cv::Mat data of a camera ring buffer) are DMA'd from where they are; pageable frames still go through the ctx's
+ * staging buffer, which costs a memcpy and a wait for the previous batch's DMA.  The frames must stay valid until
+ * ppg_extract_wait / ppg_sync returns.  One batch in flight per ctx: the records live in the ctx's pinned mirror. */
+int ppg_extract_async(ppg_ctx* ctx, const uint8_t* const* gray, const int* stride, int n_frames);
+int ppg_extract_wait(ppg_ctx* ctx, int n_frames, ppg_frame_out* out);
+long long ppg_record_bytes(const ppg_ctx* ctx); /* bytes of one frame's record block (what ppg_extract_async copies back) */
+void* ppg_host_alloc(size_t bytes); /* pinned, portable across devices; NULL on failure */
+void ppg_host_free(void* p);
+int ppg_host_register(void* p, size_t bytes);
+int ppg_host_unregister(void* p);
+
 /* ---- parity / debug entry points ----------------------------------------------------------------
  * ppg_extract_from_maps: PPGExtractor::run minus the networks (detectKeyPoint, detectLines,
  * genPointDescriptor; PPGExtractor.cpp:126-146) fed with caller-supplied dense maps (host fp32):
@@ -230,6 +248,10 @@ int ppg_assoc_stage_batch(ppg_ctx* ctx, int n_frames, int n_rows, const float* p
                           float ratio);
 int ppg_assoc_run_batch(ppg_ctx* ctx, int n_frames);
 int ppg_assoc_fetch_batch(ppg_ctx* ctx, int n_frames, ppg_assoc_out* outs);
+/* ppg_assoc_stage_batch without the host round trip: proj_uv / view_cos must lie in pinned host memory and stay valid
+ * until the ctx is synchronised (PPG_ERR_ARG for pageable pointers); nothing is waited for. */
+int ppg_assoc_stage_batch_async(ppg_ctx* ctx, int n_frames, int n_rows, const float* proj_uv, const float* view_cos,
+                                float th, float ratio);
 /* Rows whose tensor-core candidate filter could not guarantee the exact top-2 and were re-scored
  * over the whole window (diagnostic). */
 int ppg_assoc_fallback_rows(ppg_ctx* ctx, int* n);
@@ -337,6 +359,10 @@ int ppg_extend_map_matches(ppg_ctx* ctx, const ppg_extend_in* in, ppg_extend_out
  * point assigned yet) against the projections staged with ppg_assoc_stage_batch (n_rows = n_points); asynchronous. */
 int ppg_extend_run_batch(ppg_ctx* ctx, int n_frames);
 int ppg_extend_fetch_batch(ppg_ctx* ctx, int n_frames, ppg_extend_out* outs);
+/* The fetch split for pipelined callers: ..._async enqueues the device -> pinned-host copies of the results behind the
+ * kernels; after ppg_extract_wait / ppg_sync, ppg_extend_collect hands them out (no CUDA call, no wait). */
+int ppg_extend_fetch_batch_async(ppg_ctx* ctx, int n_frames);
+int ppg_extend_collect(ppg_ctx* ctx, int n_frames, ppg_extend_out* outs);
 
 /* ---- bag of words: DBoW3::Vocabulary::transform (Frame::ComputeBoW, map/src/Frame.cpp:331-340) --------
  * The vocabulary is the k-ary tree of the reference's Vocabulary/voc_*_9x3.gz (DBoW3 binary; tools/export_vocabulary.py
@@ -410,6 +436,22 @@ int ppg_search_by_bow(ppg_ctx* ctx, const ppg_bow_match_in* in, ppg_bow_match_ou
 int ppg_assoc_device_results(ppg_ctx* ctx, void** best_idx, void** second_idx, void** best_dist, void** second_dist,
                              void** accept);
 void* ppg_stream(ppg_ctx* ctx); /* cudaStream_t of the ctx */
+
+/* ---- row-sharded association over the GPUs of one box (BASELINE.json config 5) -------------------------------------
+ * Every rank holds M / world rows of the map table (ppg_upload_map of its rows) and the whole frame; after
+ * ppg_assoc_stage + ppg_assoc_run (or ppg_assoc_run_frame) on its rows, ppg_assoc_allgather packs the per-row records
+ * {best_idx, second_idx, best_dist bits, second_dist bits, accept} (5 x int32) and enqueues ONE ncclAllGather of them
+ * on the ctx stream behind the kernels -- no host synchronisation in between.  rows_per_rank is the send count common
+ * to all ranks (>= n_local; the records past n_local are {-1, -1, 0, 0, 0}).  ppg_assoc_allgather_fetch waits and
+ * returns the [world][rows_per_rank][5] table and the device time of the collective.
+ * The communicator: rank 0 calls ppg_comm_unique_id and hands the 128 bytes to the other ranks by whatever means the
+ * host program has (bench.py: torch.distributed broadcast), then every rank calls ppg_comm_init.  NCCL is loaded at
+ * run time (libnccl.so.2); PPG_ERR_NCCL if it is missing or a call fails. */
+int ppg_comm_unique_id(void* id128);
+int ppg_comm_init(ppg_ctx* ctx, const void* id128, int rank, int world);
+int ppg_comm_destroy(ppg_ctx* ctx);
+int ppg_assoc_allgather(ppg_ctx* ctx, int n_local, int rows_per_rank);
+int ppg_assoc_allgather_fetch(ppg_ctx* ctx, int32_t* records, float* gather_us);
 
 #ifdef __cplusplus
 }

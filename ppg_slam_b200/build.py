@@ -27,6 +27,7 @@ SOURCES = {
     "extend.cu": ["-fmad=false"],
     "bow.cu": ["-fmad=false"],
     "voc_io.cu": [],
+    "comm.cu": [],
 }
 
 
@@ -65,7 +66,7 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=5) as ex:
         list(ex.map(run, jobs))
     if jobs or force or _stale(LIB, objs):
-        run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs)
+        run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl"])
     return LIB
 
 

@@ -118,7 +118,11 @@ SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", 
            "ppg_extend_map_matches", "ppg_extend_run_batch", "ppg_extend_fetch_batch", "ppg_upload_map_geometry",
            "ppg_assoc_stage_poses", "ppg_frustum_fetch", "ppg_upload_vocabulary", "ppg_bow_transform",
            "ppg_bow_run_batch", "ppg_bow_fetch_batch", "ppg_search_by_bow", "ppg_vocabulary_open",
-           "ppg_vocabulary_close", "ppg_vocabulary_error", "ppg_load_vocabulary"]
+           "ppg_vocabulary_close", "ppg_vocabulary_error", "ppg_load_vocabulary", "ppg_extract_async",
+           "ppg_extract_wait", "ppg_host_alloc", "ppg_host_free", "ppg_host_register", "ppg_host_unregister",
+           "ppg_assoc_stage_batch_async", "ppg_extend_fetch_batch_async", "ppg_extend_collect",
+           "ppg_comm_unique_id", "ppg_comm_init", "ppg_comm_destroy", "ppg_assoc_allgather",
+           "ppg_assoc_allgather_fetch", "ppg_record_bytes"]
 
 _lib = None
 
@@ -151,10 +155,67 @@ def load():
                      "ppg_extend_run_batch", "ppg_extend_fetch_batch", "ppg_upload_map_geometry",
                      "ppg_assoc_stage_poses", "ppg_frustum_fetch", "ppg_upload_vocabulary", "ppg_bow_transform",
                      "ppg_bow_run_batch", "ppg_bow_fetch_batch", "ppg_search_by_bow", "ppg_vocabulary_open",
-                     "ppg_load_vocabulary"]:
+                     "ppg_load_vocabulary", "ppg_extract_async", "ppg_extract_wait", "ppg_host_register",
+                     "ppg_host_unregister", "ppg_assoc_stage_batch_async", "ppg_extend_fetch_batch_async",
+                     "ppg_extend_collect", "ppg_comm_unique_id", "ppg_comm_init", "ppg_comm_destroy",
+                     "ppg_assoc_allgather", "ppg_assoc_allgather_fetch"]:
             getattr(lib, name).restype = C.c_int
+        lib.ppg_record_bytes.restype = C.c_longlong
+        lib.ppg_record_bytes.argtypes = [C.c_void_p]
+        lib.ppg_host_alloc.restype = C.c_void_p
+        lib.ppg_host_alloc.argtypes = [C.c_size_t]
+        lib.ppg_host_free.restype = None
+        lib.ppg_host_free.argtypes = [C.c_void_p]
+        lib.ppg_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        lib.ppg_host_unregister.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
+
+
+class _Pinned:
+    """Owner of one ppg_host_alloc block; the numpy views keep it alive."""
+
+    def __init__(self, nbytes):
+        self.lib = load()
+        self.ptr = self.lib.ppg_host_alloc(max(int(nbytes), 1))
+        if not self.ptr:
+            raise MemoryError("ppg_host_alloc(%d) failed" % nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.ppg_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_array(shape, dtype):
+    """numpy array in page-locked host memory (cudaHostAlloc through the C ABI): the source / destination of the
+    asynchronous copies of the pipelined calls."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    blk = _Pinned(n)
+    buf = (C.c_uint8 * max(n, 1)).from_address(blk.ptr)
+    a = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    _PINNED_KEEP[id(buf)] = blk  # the block must outlive every view; freed at interpreter exit or by drop_pinned()
+    return a
+
+
+_PINNED_KEEP = {}
+
+
+def drop_pinned():
+    _PINNED_KEEP.clear()
+
+
+def comm_unique_id():
+    """128 bytes for ppg_comm_init, generated on one rank and handed to the others by the host program."""
+    buf = (C.c_uint8 * 128)()
+    rc = load().ppg_comm_unique_id(buf)
+    if rc != PPG_OK:
+        raise PpgError(rc, "ppg_comm_unique_id failed (libnccl.so.2 missing?)")
+    return bytes(buf)
 
 
 def _fp(a):
@@ -264,6 +325,40 @@ class Extractor:
         keep, ptrs, strides, n = self._frame_ptrs(frames)
         self._check(self.lib.ppg_extract(self.h, ptrs, strides, n, self._outs), allow_capacity)
         return [_frame_to_dict(self._outs[i]) for i in range(n)]
+
+    # ---- pipelined form: enqueue, do something else (another ctx), wait
+    def extract_async(self, frames):
+        """frames should be views of pinned memory (capi.pinned_array) and must stay alive until extract_wait."""
+        keep, ptrs, strides, n = self._frame_ptrs(frames)
+        self._async_keep = (keep, ptrs, strides)
+        self._check(self.lib.ppg_extract_async(self.h, ptrs, strides, n))
+        return n
+
+    def extract_wait(self, n, allow_capacity=False, as_dicts=True):
+        self._check(self.lib.ppg_extract_wait(self.h, n, self._outs), allow_capacity)
+        return [_frame_to_dict(self._outs[i]) for i in range(n)] if as_dicts else None
+
+    def assoc_stage_batch_async(self, proj_uv, view_cos, th, ratio):
+        """proj_uv (F, M, 2) / view_cos (F, M) float32 C-contiguous arrays in pinned memory (capi.pinned_array)."""
+        F, M = view_cos.shape
+        self._check(self.lib.ppg_assoc_stage_batch_async(self.h, F, M, _fp(proj_uv), _fp(view_cos), C.c_float(th),
+                                                         C.c_float(ratio)))
+        self._assoc_rows, self._assoc_frames = M, F
+        self._batch_out = None
+
+    def extend_fetch_batch_async(self, n_frames):
+        self._check(self.lib.ppg_extend_fetch_batch_async(self.h, n_frames))
+
+    def extend_collect(self, n_frames, as_dicts=True):
+        """After extract_wait / sync: the results of the last extend_fetch_batch_async (no CUDA call)."""
+        outs, res = self._extend_outs(n_frames)
+        self._check(self.lib.ppg_extend_collect(self.h, n_frames, outs))
+        if not as_dicts:
+            return outs
+        return [self._extend_result(outs[f], res[f], self._graph_points) for f in range(n_frames)]
+
+    def record_bytes(self):
+        return int(self.lib.ppg_record_bytes(self.h))
 
     def upload(self, frames):
         keep, ptrs, strides, n = self._frame_ptrs(frames)
@@ -490,7 +585,7 @@ class Extractor:
         """Every frame of the last extraction batch against the projections staged with assoc_stage_batch."""
         self._check(self.lib.ppg_extend_run_batch(self.h, n_frames))
 
-    def extend_fetch_batch(self, n_frames):
+    def _extend_outs(self, n_frames):
         if getattr(self, "_xbatch_out", None) is None or len(self._xbatch_out[1]) != n_frames:
             outs = (ExtendOut * n_frames)()
             res = []
@@ -499,7 +594,10 @@ class Extractor:
                 outs[f] = o
                 res.append(r)
             self._xbatch_out = (outs, res)
-        outs, res = self._xbatch_out
+        return self._xbatch_out
+
+    def extend_fetch_batch(self, n_frames):
+        outs, res = self._extend_outs(n_frames)
         self._check(self.lib.ppg_extend_fetch_batch(self.h, n_frames, outs))
         return [self._extend_result(outs[f], res[f], self._graph_points) for f in range(n_frames)]
 
@@ -609,6 +707,27 @@ class Extractor:
         self._check(fn(self.h, _fp(d), off.ctypes.data_as(C.POINTER(C.c_int32)), len(off) - 1,
                        out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out
+
+    # ---- row-sharded association: NCCL all-gather of the per-row records on the ctx stream (comm.cu)
+    def comm_init(self, unique_id, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self.lib.ppg_comm_init(self.h, buf, rank, world))
+        self._comm_world = world
+
+    def comm_destroy(self):
+        self._check(self.lib.ppg_comm_destroy(self.h))
+
+    def assoc_allgather(self, n_local, rows_per_rank):
+        self._check(self.lib.ppg_assoc_allgather(self.h, n_local, rows_per_rank))
+        self._gather_rows = rows_per_rank
+
+    def assoc_allgather_fetch(self, records=True):
+        """-> ((world, rows_per_rank, 5) int32 or None, device microseconds of the all-gather)."""
+        us = C.c_float(0)
+        rec = np.zeros((self._comm_world, self._gather_rows, 5), np.int32) if records else None
+        self._check(self.lib.ppg_assoc_allgather_fetch(
+            self.h, rec.ctypes.data_as(C.POINTER(C.c_int32)) if records else None, C.byref(us)))
+        return rec, us.value
 
     def assoc_fallback_rows(self):
         n = C.c_int(0)

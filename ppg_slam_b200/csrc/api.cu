@@ -5,7 +5,6 @@
 #include <string.h>
 
 #include <map>
-#include <thread>
 
 #include "ctx.cuh"
 #include "net_direct.cuh"
@@ -332,6 +331,13 @@ static void fill_out(const ppg_ctx* c, int f, ppg_frame_out* o) {
     for (int k = 0; k < 8; k++) o->diag[k] = k < HDR_WORDS - HDR_DIAG ? hdr[HDR_DIAG + k] : 0;
 }
 
+static PostMark post_mark(ppg_ctx* c) {
+    PostMark m;
+    m.fn = [](void* user, const char* name) { stage_mark(static_cast<ppg_ctx*>(user), name); };
+    m.user = c;
+    return m;
+}
+
 // Post-processing launches shared by ppg_run and ppg_extract_from_maps.
 static int run_post(ppg_ctx* c, int n) {
     PostParams p = c->post;
@@ -341,14 +347,11 @@ static int run_post(ppg_ctx* c, int n) {
         p.heat_raw = c->heat_in;
         p.desc = c->desc_in;
     }
-    PPG_CUDA(c, post_keypoints_launch(p, c->st, &c->launches));
-    stage_mark(c, "post.keypoints(scan+nms+topk)");
-    PPG_CUDA(c, post_heat_launch(p, c->st, &c->launches));
-    stage_mark(c, "post.heat(refine+remap)");
-    PPG_CUDA(c, post_lines_launch(p, c->st, &c->launches));
-    stage_mark(c, "post.lines(pairs+graph)");
-    PPG_CUDA(c, post_desc_launch(p, c->st, &c->launches));
-    stage_mark(c, "post.descriptors");
+    const PostMark mk = post_mark(c);
+    PPG_CUDA(c, post_keypoints_launch(p, c->st, &c->launches, mk));
+    PPG_CUDA(c, post_heat_launch(p, c->st, &c->launches, mk));
+    PPG_CUDA(c, post_lines_launch(p, c->st, &c->launches, mk));
+    PPG_CUDA(c, post_desc_launch(p, c->st, &c->launches, mk));
     return PPG_OK;
 }
 
@@ -389,6 +392,7 @@ void ppg_destroy(ppg_ctx* c) {
         if (e) cudaEventDestroy(e);
     if (c->st2) cudaStreamDestroy(c->st2);
     if (c->st3) cudaStreamDestroy(c->st3);
+    comm_destroy(c);
     assoc_destroy(c);
     bow_destroy(c);
     for (auto& l : c->tc) {
@@ -695,37 +699,47 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
 }
 
 // -------------------------------------------------------------------------------------------------
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int ppg_upload_frames(ppg_ctx* c, const uint8_t* const* gray, const int* stride, int n) {
     if (!c || !gray || n < 1 || n > c->maxB) return set_err(c, PPG_ERR_ARG, "ppg_upload_frames: bad arguments");
     PPG_CUDA(c, cudaSetDevice(c->dev));
     const size_t HW = (size_t)c->H * c->W;
+    bool pinned = true, packed = true;
     for (int f = 0; f < n; f++) {
         if (!gray[f]) return set_err(c, PPG_ERR_ARG, "null frame pointer");
         const int s = stride ? stride[f] : c->W;
         if (s < c->W) return set_err(c, PPG_ERR_ARG, "row stride smaller than the image width");
+        pinned = pinned && is_pinned(gray[f]);
+        packed = packed && s == c->W && (f == 0 || gray[f] == gray[f - 1] + HW);
     }
-    // the previous batch's DMA out of the pinned staging buffer must be done before it is overwritten
-    PPG_CUDA(c, cudaStreamSynchronize(c->st));
-    // pageable -> pinned staging; a single thread copies at ~9 GB/s (1.3 ms for 32 EuRoC frames), so large batches
-    // are split over a few threads, and each thread's share goes to the GPU as soon as it is staged
-    auto stage = [&](int f0, int f1) {
-        for (int f = f0; f < f1; f++) {
-            const int s = stride ? stride[f] : c->W;
-            uint8_t* dst = c->h_gray + f * HW;
-            if (s == c->W)
-                memcpy(dst, gray[f], HW);
-            else
-                for (int y = 0; y < c->H; y++) memcpy(dst + (size_t)y * c->W, gray[f] + (size_t)y * s, c->W);
+    if (pinned) {
+        // the caller's buffers are page-locked: DMA from where they are, nothing to wait for
+        if (packed) {
+            PPG_CUDA(c, cudaMemcpyAsync(c->gray, gray[0], n * HW, cudaMemcpyHostToDevice, c->st));
+        } else {
+            for (int f = 0; f < n; f++)
+                PPG_CUDA(c, cudaMemcpy2DAsync(c->gray + f * HW, c->W, gray[f], stride ? stride[f] : c->W, c->W, c->H,
+                                              cudaMemcpyHostToDevice, c->st));
         }
-    };
-    const int nth = n >= 8 ? 4 : 1;
-    if (nth == 1) {
-        stage(0, n);
-    } else {
-        std::vector<std::thread> th;
-        for (int t = 1; t < nth; t++) th.emplace_back(stage, n * t / nth, n * (t + 1) / nth);
-        stage(0, n / nth);
-        for (auto& t : th) t.join();
+        return PPG_OK;
+    }
+    // pageable frames: through the pinned staging buffer; the previous batch's DMA out of it must be done first
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    for (int f = 0; f < n; f++) {
+        const int s = stride ? stride[f] : c->W;
+        uint8_t* dst = c->h_gray + f * HW;
+        if (s == c->W)
+            memcpy(dst, gray[f], HW);
+        else
+            for (int y = 0; y < c->H; y++) memcpy(dst + (size_t)y * c->W, gray[f] + (size_t)y * s, c->W);
     }
     PPG_CUDA(c, cudaMemcpyAsync(c->gray, c->h_gray, n * HW, cudaMemcpyHostToDevice, c->st));
     return PPG_OK;
@@ -827,20 +841,17 @@ static int enqueue_run(ppg_ctx* c, int n) {
     PPG_CUDA(c, edge_tail_tc_launch(c->e2, c->we3, c->be3, c->we1, c->be1b, c->heat_raw, n, c->H / 2, c->W / 2, s_heat));
     c->launches++;
     stage_mark(c, "edge_tail");
-    PPG_CUDA(c, post_keypoints_launch(p, c->st, &c->launches));
-    stage_mark(c, "post.keypoints(scan+nms+topk)");
-    PPG_CUDA(c, post_heat_launch(p, s_heat, &c->launches));
-    stage_mark(c, "post.heat(refine+remap)");
+    const PostMark mk = post_mark(c);  // profiling runs are single-stream: every mark lands on c->st
+    PPG_CUDA(c, post_keypoints_launch(p, c->st, &c->launches, mk));
+    PPG_CUDA(c, post_heat_launch(p, s_heat, &c->launches, mk));
     if (fork) {
         PPG_CUDA(c, cudaEventRecord(c->ev_heat, c->st2));
         PPG_CUDA(c, cudaEventRecord(c->ev_kp, c->st));
         PPG_CUDA(c, cudaStreamWaitEvent(c->st, c->ev_heat, 0));   // the graph needs keypoints + heat map
         PPG_CUDA(c, cudaStreamWaitEvent(c->st3, c->ev_kp, 0));    // the sampling needs keypoints + descriptor map
     }
-    PPG_CUDA(c, post_lines_launch(p, c->st, &c->launches));
-    stage_mark(c, "post.lines(pairs+graph)");
-    PPG_CUDA(c, post_desc_launch(p, s_desc, &c->launches));
-    stage_mark(c, "post.descriptors");
+    PPG_CUDA(c, post_lines_launch(p, c->st, &c->launches, mk));
+    PPG_CUDA(c, post_desc_launch(p, s_desc, &c->launches, mk));
     if (fork) {
         PPG_CUDA(c, cudaEventRecord(c->ev_desc, c->st3));
         PPG_CUDA(c, cudaStreamWaitEvent(c->st, c->ev_desc, 0));   // join: everything is ordered on st again
@@ -878,6 +889,58 @@ int ppg_download(ppg_ctx* c, int n, ppg_frame_out* out) {
     }
     if (rc != PPG_OK) set_err(c, rc, "a per-frame capacity was exceeded (see ppg_frame_out.status)");
     return rc;
+}
+
+int ppg_extract_async(ppg_ctx* c, const uint8_t* const* gray, const int* stride, int n) {
+    int rc = ppg_upload_frames(c, gray, stride, n);
+    if (rc != PPG_OK) return rc;
+    if ((rc = ppg_run(c, n)) != PPG_OK) return rc;
+    // the whole record of every frame (descriptor area included) in one strided copy: the live descriptor rows are only
+    // known once the header is on the host, and a host round trip in the middle is what this entry point avoids
+    const OutLayout& L = c->post.lay;
+    PPG_CUDA(c, cudaMemcpy2DAsync(c->h_out, L.total, c->d_out, L.total, L.total, n, cudaMemcpyDeviceToHost, c->st));
+    return PPG_OK;
+}
+
+int ppg_extract_wait(ppg_ctx* c, int n, ppg_frame_out* out) {
+    if (!c || !out || n < 1 || n > c->maxB) return set_err(c, PPG_ERR_ARG, "ppg_extract_wait: bad arguments");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    int rc = PPG_OK;
+    for (int f = 0; f < n; f++) {
+        fill_out(c, f, &out[f]);
+        if (out[f].status) rc = PPG_ERR_CAPACITY;
+    }
+    if (rc != PPG_OK) set_err(c, rc, "a per-frame capacity was exceeded (see ppg_frame_out.status)");
+    return rc;
+}
+
+long long ppg_record_bytes(const ppg_ctx* c) { return c ? (long long)c->post.lay.total : 0; }
+
+void* ppg_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void ppg_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+int ppg_host_register(void* p, size_t bytes) {
+    if (!p || cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return PPG_ERR_CUDA;
+    }
+    return PPG_OK;
+}
+int ppg_host_unregister(void* p) {
+    if (!p || cudaHostUnregister(p) != cudaSuccess) {
+        cudaGetLastError();
+        return PPG_ERR_CUDA;
+    }
+    return PPG_OK;
 }
 
 int ppg_extract(ppg_ctx* c, const uint8_t* const* gray, const int* stride, int n, ppg_frame_out* out) {

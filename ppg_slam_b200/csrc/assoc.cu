@@ -881,18 +881,24 @@ void assoc_destroy(ppg_ctx* c) {
 }
 
 int assoc_stage_rows(ppg_ctx* c, int frames, int n_rows, const float* proj_uv, const float* view_cos, float th,
-                      float ratio) {
+                      float ratio, bool pinned_src) {
     AssocState* s = c->assoc;
     if (n_rows < 1 || n_rows > s->n_rows || !proj_uv || !view_cos)
         return set_err(c, PPG_ERR_ARG, "association: n_rows must be in [1, uploaded rows]");
     if (frames < 1 || frames > s->bcap) return set_err(c, PPG_ERR_ARG, "association: bad frame count");
-    // the caller's arrays are pageable: one memcpy into pinned staging and one strided DMA per array instead of two
-    // driver-staged copies per frame.  The previous batch's DMA out of the staging buffer must be done first.
-    PPG_CUDA(c, cudaStreamSynchronize(c->st));
-    float* hp = s->h_stage;
-    float* hv = s->h_stage + (size_t)s->bcap * s->max_rows * 2;
-    memcpy(hp, proj_uv, (size_t)frames * n_rows * 8);
-    memcpy(hv, view_cos, (size_t)frames * n_rows * 4);
+    const float* hp = proj_uv;
+    const float* hv = view_cos;
+    if (!pinned_src) {
+        // the caller's arrays are pageable: one memcpy into pinned staging and one strided DMA per array instead of two
+        // driver-staged copies per frame.  The previous batch's DMA out of the staging buffer must be done first.
+        PPG_CUDA(c, cudaStreamSynchronize(c->st));
+        float* sp = s->h_stage;
+        float* sv = s->h_stage + (size_t)s->bcap * s->max_rows * 2;
+        memcpy(sp, proj_uv, (size_t)frames * n_rows * 8);
+        memcpy(sv, view_cos, (size_t)frames * n_rows * 4);
+        hp = sp;
+        hv = sv;
+    }
     PPG_CUDA(c, cudaMemcpy2DAsync(s->proj, (size_t)s->max_rows * 8, hp, (size_t)n_rows * 8, (size_t)n_rows * 8, frames,
                                   cudaMemcpyHostToDevice, c->st));
     PPG_CUDA(c, cudaMemcpy2DAsync(s->vcos, (size_t)s->max_rows * 4, hv, (size_t)n_rows * 4, (size_t)n_rows * 4, frames,
@@ -1057,9 +1063,25 @@ int ppg_assoc_stage_batch(ppg_ctx* c, int n_frames, int n_rows, const float* pro
     PPG_CUDA(c, cudaSetDevice(c->dev));
     int rc = assoc_ensure_state(c);
     if (rc != PPG_OK) return rc;
-    if ((rc = assoc_stage_rows(c, n_frames, n_rows, proj_uv, view_cos, th, ratio)) != PPG_OK) return rc;
+    if ((rc = assoc_stage_rows(c, n_frames, n_rows, proj_uv, view_cos, th, ratio, false)) != PPG_OK) return rc;
     PPG_CUDA(c, cudaStreamSynchronize(c->st));
     return PPG_OK;
+}
+
+int ppg_assoc_stage_batch_async(ppg_ctx* c, int n_frames, int n_rows, const float* proj_uv, const float* view_cos,
+                                float th, float ratio) {
+    if (!c) return PPG_ERR_ARG;
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    int rc = assoc_ensure_state(c);
+    if (rc != PPG_OK) return rc;
+    cudaPointerAttributes a, b;
+    if (!proj_uv || !view_cos || cudaPointerGetAttributes(&a, proj_uv) != cudaSuccess ||
+        cudaPointerGetAttributes(&b, view_cos) != cudaSuccess || a.type != cudaMemoryTypeHost ||
+        b.type != cudaMemoryTypeHost) {
+        cudaGetLastError();
+        return set_err(c, PPG_ERR_ARG, "ppg_assoc_stage_batch_async: projections must lie in pinned host memory");
+    }
+    return assoc_stage_rows(c, n_frames, n_rows, proj_uv, view_cos, th, ratio, true);
 }
 
 int ppg_assoc_run(ppg_ctx* c) {

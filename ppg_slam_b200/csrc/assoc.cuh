@@ -141,7 +141,7 @@ int assoc_ensure_state(ppg_ctx* c);
 FrameSrc assoc_staged_src(const AssocState* s);
 FrameSrc assoc_extracted_src(const ppg_ctx* c, int first);
 int assoc_stage_rows(ppg_ctx* c, int frames, int n_rows, const float* proj_uv, const float* view_cos, float th,
-                     float ratio);
+                      float ratio, bool pinned_src = false);
 // prep_frame_kernel + prep_rows_kernel for `frames` frames on the ctx stream (kinfo / korder / rowp)
 int assoc_prep(ppg_ctx* c, const FrameSrc& src, int frames);
 void extend_destroy(AssocState* s);  // extend.cu

@@ -219,32 +219,37 @@ conv_t64_kernel(const __grid_constant__ CUtensorMap mapA, const __half* __restri
                     }
                 }
             } else {  // EPI_F16
+                const int odd = lane & 1;
 #pragma unroll 1
-                for (int oy = 0; oy < T_TH; oy++) {
-                    uint32_t ra[32], rb[8];
-                    ptx::tmem_ld32(tq + oy * T_HW, ra);
-                    ptx::tmem_ld8(tq + oy * T_HW + 32, rb);
+                for (int rp = 0; rp < T_TH / 2; rp++) {
+                    uint32_t ra[64], rb[16];
+                    ptx::tmem_ld64(tq + rp * 2 * T_HW, ra);
+                    ptx::tmem_ld16(tq + rp * 2 * T_HW + 64, rb);
                     ptx::tmem_ld_wait();
-                    auto V = [&](int i) { return __uint_as_float(i < 32 ? ra[i] : rb[(i < 40 ? i : 39) - 32]); };
-                    const int y = y0 + oy;
-                    __half* orow = outp + ((size_t)(n * p.H + y) * p.W + x0) * 64 + ch;
+                    auto V = [&](int i) { return __uint_as_float(i < 64 ? ra[i] : rb[(i < 80 ? i : 79) - 64]); };
 #pragma unroll
-                    for (int i = 0; i < T_HW / 4; i++) {
-                        const int b = 4 * i;
-                        const float k0 = hi ? V(b + 3) : V(b), k1 = hi ? V(b + 4) : V(b + 1);
-                        const float s0 = hi ? V(b + 1) : V(b + 2), s1 = hi ? V(b + 2) : V(b + 3);
-                        float o0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16) + bias;
-                        float o1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16) + bias;
-                        if (p.relu) {
-                            o0 = fmaxf(o0, 0.f);
-                            o1 = fmaxf(o1, 0.f);
-                        }
-                        const int ox = 4 * i + 2 * hi;
-                        if (y < p.H) {
-                            if (ox < T_TW && x0 + ox < p.W)
-                                *reinterpret_cast<uint16_t*>(orow + (size_t)ox * 64) = half_bits(o0);
-                            if (ox + 1 < T_TW && x0 + ox + 1 < p.W)
-                                *reinterpret_cast<uint16_t*>(orow + (size_t)(ox + 1) * 64) = half_bits(o1);
+                    for (int rr = 0; rr < 2; rr++) {
+                        const int y = y0 + 2 * rp + rr;
+                        // the lane pair (r, r ^ 1) holds channels (c, c + 1) of the same two pixels: one exchange lets the
+                        // even lane store both channels of the first pixel and the odd lane both of the second (4-byte
+                        // stores, 8 lanes = one 32-byte sector per pixel)
+                        __half* orow = outp + ((size_t)(n * p.H + y) * p.W + x0) * 64 + (ch & ~1);
+#pragma unroll
+                        for (int i = 0; i < T_HW / 4; i++) {
+                            const int b = rr * T_HW + 4 * i;
+                            const float k0 = hi ? V(b + 3) : V(b), k1 = hi ? V(b + 4) : V(b + 1);
+                            const float s0 = hi ? V(b + 1) : V(b + 2), s1 = hi ? V(b + 2) : V(b + 3);
+                            float o0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16) + bias;
+                            float o1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16) + bias;
+                            if (p.relu) {
+                                o0 = fmaxf(o0, 0.f);
+                                o1 = fmaxf(o1, 0.f);
+                            }
+                            const float got = __shfl_xor_sync(0xffffffffu, odd ? o0 : o1, 1);
+                            const __half2 h2 = odd ? __floats2half2_rn(got, o1) : __floats2half2_rn(o0, got);
+                            const int ox = 4 * i + 2 * hi + odd;
+                            if (ox < T_TW && x0 + ox < p.W && y < p.H)
+                                *reinterpret_cast<__half2*>(orow + (size_t)ox * 64) = h2;
                         }
                     }
                 }

@@ -27,6 +27,7 @@ struct TcLayerInfo {
 
 struct AssocState;  // assoc.cu
 struct BowState;    // bow.cu
+struct CommState;   // comm.cu
 
 }  // namespace ppg
 
@@ -86,6 +87,7 @@ struct ppg_ctx {
 
     ppg::AssocState* assoc = nullptr;
     ppg::BowState* bow = nullptr;
+    ppg::CommState* comm = nullptr;  // NCCL communicator of the row-sharded association (comm.cu)
 };
 
 namespace ppg {
@@ -93,6 +95,7 @@ int set_err(const ppg_ctx* c, int code, const std::string& msg);
 int cuda_fail(const ppg_ctx* c, cudaError_t e, const char* what);
 void assoc_destroy(ppg_ctx* c);
 void bow_destroy(ppg_ctx* c);
+void comm_destroy(ppg_ctx* c);
 // profiling runs: records a CUDA event named after the stage that just ended on the ctx stream (api.cu)
 void stage_mark(ppg_ctx* c, const char* name);
 }  // namespace ppg

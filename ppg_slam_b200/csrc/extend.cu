@@ -982,7 +982,7 @@ void fill_out(const ExtendState* x, const AssocState* s, int f, ppg_extend_out* 
     if (o->tracked) memcpy(o->tracked, x->h_tracked + (size_t)f * x->P, (size_t)x->P);
 }
 
-int fetch_extend(ppg_ctx* c, int frames) {
+int fetch_extend_async(ppg_ctx* c, int frames) {
     AssocState* s = c->assoc;
     ExtendState* x = s->ext;
     PPG_CUDA(c, cudaMemcpyAsync(x->h_result, x->result, (size_t)frames * XR_WORDS * 4, cudaMemcpyDeviceToHost, c->st));
@@ -990,6 +990,12 @@ int fetch_extend(ppg_ctx* c, int frames) {
     PPG_CUDA(c, cudaMemcpyAsync(x->h_kedge_me, x->kedge_me, (size_t)frames * x->ecap * 4, cudaMemcpyDeviceToHost, c->st));
     PPG_CUDA(c, cudaMemcpy2DAsync(x->h_tracked, (size_t)x->P, x->tracked, (size_t)s->max_rows, (size_t)x->P, frames,
                                   cudaMemcpyDeviceToHost, c->st));
+    return PPG_OK;
+}
+
+int fetch_extend(ppg_ctx* c, int frames) {
+    const int rc = fetch_extend_async(c, frames);
+    if (rc != PPG_OK) return rc;
     PPG_CUDA(c, cudaStreamSynchronize(c->st));
     return PPG_OK;
 }
@@ -1180,6 +1186,20 @@ int ppg_extend_fetch_batch(ppg_ctx* c, int n_frames, ppg_extend_out* outs) {
     PPG_CUDA(c, cudaSetDevice(c->dev));
     int rc = fetch_extend(c, n_frames);
     if (rc != PPG_OK) return rc;
+    for (int f = 0; f < n_frames; f++) fill_out(c->assoc->ext, c->assoc, f, &outs[f]);
+    return check_status(c, c->assoc->ext->h_result, n_frames);
+}
+
+int ppg_extend_fetch_batch_async(ppg_ctx* c, int n_frames) {
+    if (!c || !c->assoc || !c->assoc->ext || n_frames < 1 || n_frames > c->assoc->bcap)
+        return set_err(c, PPG_ERR_ARG, "ppg_extend_fetch_batch_async: bad arguments");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    return fetch_extend_async(c, n_frames);
+}
+
+int ppg_extend_collect(ppg_ctx* c, int n_frames, ppg_extend_out* outs) {
+    if (!c || !c->assoc || !c->assoc->ext || !outs || n_frames < 1 || n_frames > c->assoc->bcap)
+        return set_err(c, PPG_ERR_ARG, "ppg_extend_collect: bad arguments");
     for (int f = 0; f < n_frames; f++) fill_out(c->assoc->ext, c->assoc, f, &outs[f]);
     return check_status(c, c->assoc->ext->h_result, n_frames);
 }

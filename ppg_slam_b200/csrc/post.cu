@@ -1454,7 +1454,7 @@ cudaError_t post_init_attrs(const PostParams& p) {
     return cudaFuncSetAttribute(lines_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
 }
 
-cudaError_t post_keypoints_launch(const PostParams& p, cudaStream_t st, long long* launches) {
+cudaError_t post_keypoints_launch(const PostParams& p, cudaStream_t st, long long* launches, PostMark mark) {
     const int HW = p.H * p.W;
     if (!p.scan_fused) {
         cudaError_t e = cudaMemsetAsync(p.counters, 0, sizeof(int) * 8 * p.B, st);
@@ -1462,43 +1462,54 @@ cudaError_t post_keypoints_launch(const PostParams& p, cudaStream_t st, long lon
         dim3 g((HW / 4 + 255) / 256, p.B);
         scan_kernel<<<g, 256, 0, st>>>(p);
         *launches += 1;
+        mark("post.scan");
     }
     if (p.nms_smem)
         nms_smem_kernel<<<p.B, 1024, post_nms_smem(p), st>>>(p);
     else
         nms_global_kernel<<<p.B, 1024, post_nms_smem(p), st>>>(p);
     *launches += 1;
+    mark("post.nms+topk");
     return cudaGetLastError();
 }
 
-cudaError_t post_heat_launch(const PostParams& p, cudaStream_t st, long long* launches) {
+cudaError_t post_heat_launch(const PostParams& p, cudaStream_t st, long long* launches, PostMark mark) {
     const int tiles = (p.W >> 4) * (p.H >> 4) * p.B;
     refine_kernel<<<(tiles + 7) / 8, 256, 0, st>>>(p, p.do_remap ? p.heat_ref : p.heat_final);
     *launches += 1;
+    mark("post.refine");
     if (p.do_remap) {
         dim3 g((p.H * p.W / 4 + 255) / 256, p.B);
         remap_kernel<<<g, 256, 0, st>>>(p);
         *launches += 1;
+        mark("post.remap");
     }
     return cudaGetLastError();
 }
 
-cudaError_t post_lines_launch(const PostParams& p, cudaStream_t st, long long* launches) {
+cudaError_t post_lines_launch(const PostParams& p, cudaStream_t st, long long* launches, PostMark mark) {
     dim3 g((p.max_kp + 7) / 8, p.B);
     pair_test_kernel<<<g, 256, 0, st>>>(p);
+    mark("post.pair_test");
     cand_build_kernel<<<g, 256, 0, st>>>(p);
+    mark("post.cand_build");
     interact_kernel<<<dim3((p.pair_cap + 7) / 8, p.B), 256, 0, st>>>(p);
+    mark("post.interact");
     lines_filter_kernel<<<p.B, 512, post_lines_filter_smem(p), st>>>(p);
+    mark("post.lines_filter");
     lines_score_kernel<<<dim3(16, p.B), 256, 0, st>>>(p);
+    mark("post.lines_score");
     lines_graph_kernel<<<p.B, 512, post_lines_smem(p), st>>>(p);
+    mark("post.lines_graph");
     *launches += 6;
     return cudaGetLastError();
 }
 
-cudaError_t post_desc_launch(const PostParams& p, cudaStream_t st, long long* launches) {
+cudaError_t post_desc_launch(const PostParams& p, cudaStream_t st, long long* launches, PostMark mark) {
     dim3 g((p.max_kp + 7) / 8, p.B);
     desc_kernel<<<g, 256, 0, st>>>(p);
     *launches += 1;
+    mark("post.descriptors");
     return cudaGetLastError();
 }
 

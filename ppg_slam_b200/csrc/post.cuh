@@ -84,10 +84,18 @@ size_t post_lines_smem(const PostParams& p);         // lines_graph_kernel
 size_t post_lines_filter_smem(const PostParams& p);  // lines_filter_kernel
 size_t post_lines_fixed_smem(int max_kp, int pair_words);
 cudaError_t post_init_attrs(const PostParams& p);
+// Optional per-kernel stage marks of a profiling run (api.cu records a CUDA event after each named kernel).
+struct PostMark {
+    void (*fn)(void* user, const char* name) = nullptr;
+    void* user = nullptr;
+    void operator()(const char* name) const {
+        if (fn) fn(user, name);
+    }
+};
 // each returns the number of kernels it launched through *launches (added)
-cudaError_t post_keypoints_launch(const PostParams& p, cudaStream_t st, long long* launches);  // scan + NMS + top-k
-cudaError_t post_heat_launch(const PostParams& p, cudaStream_t st, long long* launches);       // refine (+ remap)
-cudaError_t post_lines_launch(const PostParams& p, cudaStream_t st, long long* launches);      // point-pair graph
-cudaError_t post_desc_launch(const PostParams& p, cudaStream_t st, long long* launches);       // sampling + L2 norm
+cudaError_t post_keypoints_launch(const PostParams& p, cudaStream_t st, long long* launches, PostMark mark = {});  // scan + NMS + top-k
+cudaError_t post_heat_launch(const PostParams& p, cudaStream_t st, long long* launches, PostMark mark = {});       // refine (+ remap)
+cudaError_t post_lines_launch(const PostParams& p, cudaStream_t st, long long* launches, PostMark mark = {});      // point-pair graph
+cudaError_t post_desc_launch(const PostParams& p, cudaStream_t st, long long* launches, PostMark mark = {});       // sampling + L2 norm
 
 }  // namespace ppg

@@ -3,8 +3,10 @@ ranks, every rank scores its rows against the (replicated) frame, and ONE all-ga
 records rebuilds the full answer.  Rows are independent, so the gather is a concatenation.
 
 The frame path itself (extract + graph + descriptors) is sharded by frame with no communication; this module
-is the only place a collective exists.  `torch.distributed` provides the plumbing: NCCL over NVLink on the
-GPU box (device tensors wrapping the ctx result buffers), gloo in the CPU tests of the host logic.
+is the only place a collective exists.  On the GPU box the exchange is the library's own: ppg_assoc_allgather
+(csrc/comm.cu) packs the records and enqueues one ncclAllGather on the ctx stream right behind the scoring kernels,
+no host synchronisation in between; `torch.distributed` only carries the NCCL unique id to the ranks.  The CPU tests
+of the host logic (gloo) pass a `compute` callable and gather through torch.distributed.
 """
 import numpy as np
 import torch
@@ -81,27 +83,31 @@ class ShardedAssociator:
 
     @classmethod
     def from_extractor(cls, ex, map_desc_full, proj_uv_full, view_cos_full, th, ratio, device, group=None):
-        """GPU path: uploads this rank's rows of the table once; run() then calls frame_inputs-free scoring of
-        the frame staged with `stage_frame` and packs the ctx's device result buffers without a host copy."""
+        """GPU path: uploads this rank's rows of the table once and creates the library's NCCL communicator; run()
+        then scores the frame staged with `stage_frame` and all-gathers the records on the ctx stream (comm.cu)."""
+        from . import capi
         n_rows = len(map_desc_full)
         self = cls(n_rows, None, device=device, group=group)
         r0, k = self.row0, self.rows
-        ex.upload_map(map_desc_full[r0:r0 + k])
+        uid = [capi.comm_unique_id() if self.rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0, group=group)
+        ex.comm_init(uid[0], self.rank, self.world)
+        if k > 0:  # a rank without rows (fewer rows than ranks) uploads nothing and only takes part in the gather
+            ex.upload_map(map_desc_full[r0:r0 + k])
         self._ex, self._proj, self._vcos, self._th, self._ratio = ex, proj_uv_full[r0:r0 + k], view_cos_full[r0:r0 + k], th, ratio
+        self.gather_us = None
 
-        def compute(row0, rows):
-            ex.assoc_run()
-            ex.sync()
-            bi, si, bd, sd, ac = ex.assoc_device_results()
-            t = [torch.as_tensor(_DevArray(bi, rows, "<i4"), device=device),
-                 torch.as_tensor(_DevArray(si, rows, "<i4"), device=device),
-                 torch.as_tensor(_DevArray(bd, rows, "<i4"), device=device),
-                 torch.as_tensor(_DevArray(sd, rows, "<i4"), device=device),
-                 torch.as_tensor(_DevArray(ac, rows, "|u1"), device=device).to(torch.int32)]
-            return torch.stack(t, 1)
+        def run():
+            if self.rows > 0:
+                ex.assoc_run()
+            ex.assoc_allgather(self.rows, self.max_rows)
+            rec, self.gather_us = ex.assoc_allgather_fetch()
+            parts = [rec[r, :kk] for r, (_, kk) in enumerate(self.shards)]
+            return unpack_records(np.concatenate(parts, 0))
 
-        self.compute = compute
+        self.run = run
         return self
 
     def stage_frame(self, kp_x, kp_y, frame_desc, free_mask):
-        self._ex.assoc_stage(kp_x, kp_y, frame_desc, free_mask, self._proj, self._vcos, self._th, self._ratio)
+        if self.rows > 0:
+            self._ex.assoc_stage(kp_x, kp_y, frame_desc, free_mask, self._proj, self._vcos, self._th, self._ratio)

@@ -139,6 +139,58 @@ def extend_inputs(seed, frame_desc, kp_xy, kedge_start, kedge_end, n_map, width,
                 kp_mp=kp_mp, planted_rows=rows.astype(np.int32), planted_src=src.astype(np.int32))
 
 
+def extend_inputs_multi(seed, recs, n_map, width, height, th=10.0, rows_per_frame=None, n_slices=None):
+    """ONE resident map for a batch of frames, every frame with its own local map: the table is cut into slices,
+    slice f holds map points planted around the keypoints of frame f (descriptor + noise, map edges mirroring the
+    frame's point-pair graph, as extend_inputs does for a single frame), and in frame f's projections those rows land
+    near their keypoints while all other rows project somewhere else in the image.  Every frame's
+    Matcher::ExtendMapMatches walk then accepts and grows a few hundred matches -- what a SLAM run looks like, where
+    every frame matches its local map -- instead of only the first one.  `recs`: per-frame dicts with kp_x, kp_y, desc,
+    edge_start, edge_end.  n_slices (default len(recs)) fixes the slice size when fewer frames than slices are given
+    (the CPU arm of bench.py processes a sample of the batch against a table of the same shape).
+    -> dict like extend_inputs (clean state) + proj_all (F, M, 2), vcos_all (F, M), slices [(row0, rows)]"""
+    rs = np.random.RandomState(seed)
+    F, M = len(recs), n_map
+    n_slices = n_slices or F
+    per = rows_per_frame or M // n_slices
+    d = rs.normal(size=(M, 256)).astype(np.float32)
+    view_cos = rs.uniform(0.9, 1.0, M).astype(np.float32)
+    proj_all = np.stack([np.stack([rs.uniform(0, width, M), rs.uniform(0, height, M)], 1) for _ in range(F)]).astype(
+        np.float32)
+    adj = [[] for _ in range(M)]
+    slices = []
+    for f, r in enumerate(recs):
+        r0 = f * per
+        slices.append((r0, per))
+        N = len(r["kp_x"])
+        if N == 0:
+            continue
+        kp_xy = np.stack([r["kp_x"], r["kp_y"]], 1)
+        src = rs.permutation(N)[:per] if N >= per else rs.randint(0, N, per)
+        rows = r0 + np.arange(len(src))
+        d[rows] = r["desc"][src] + rs.normal(0, 0.05, size=(len(src), 256)).astype(np.float32)
+        rad = np.where(view_cos[rows] > 0.998, 2.5, 4.0) * th
+        proj_all[f, rows] = kp_xy[src] + (rs.uniform(-0.5, 0.5, size=(len(src), 2)) * rad[:, None]).astype(np.float32)
+        first_row = {}
+        for rw, sidx in zip(rows.tolist(), src.tolist()):
+            first_row.setdefault(sidx, rw)
+        for a, b in zip(np.asarray(r["edge_start"]).tolist(), np.asarray(r["edge_end"]).tolist()):
+            if a in first_row and b in first_row and rs.rand() < 0.85:
+                ra, rb = first_row[a], first_row[b]
+                adj[ra].append((rb, 1))
+                adj[rb].append((ra, 1))
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-12)
+    edge_off = np.zeros(M + 1, np.int32)
+    edge_off[1:] = np.cumsum([len(a) for a in adj])
+    edge_other = np.array([o for a in adj for o, _ in a], np.int32)
+    edge_ok = np.array([k for a in adj for _, k in a], np.uint8)
+    vcos_all = np.ascontiguousarray(np.broadcast_to(view_cos, (F, M)), np.float32)
+    return dict(map_desc=d.astype(np.float32), proj_uv=proj_all[0].copy(), view_cos=view_cos,
+                candidate=np.ones(M, np.uint8), observed=np.ones(M, np.uint8), bad=np.zeros(M, np.uint8),
+                edge_off=edge_off, edge_other=edge_other, edge_ok=edge_ok, tracked=np.zeros(M, np.uint8),
+                proj_all=proj_all, vcos_all=vcos_all, slices=slices)
+
+
 def frustum_inputs(seed, cam, n_points, n_frames=1):
     """Map geometry + camera poses for Frame::CheckInFrustum: points scattered in front of (and partly behind /
     beside) a camera near the origin, mean viewing directions (MapPoint::GetNormal) roughly along the ray, scale-invariance distance bands, and small random

@@ -180,6 +180,40 @@ def test_sharded_association_nccl_two_gpus():
     assert '"parity_vs_oracle": true' in r.stdout
 
 
+def test_allgather_of_records_single_rank_nccl():
+    """The library's own exchange step (csrc/comm.cu: pack kernel + ncclAllGather on the ctx stream) on ONE GPU: a
+    world of one rank, the records gathered equal the per-row results fetched the ordinary way, padding rows are empty."""
+    from ppg_slam_b200 import capi
+    cam = cameras.EUROC
+    rs = np.random.RandomState(21)
+    n, m = 300, 3000
+    kx = rs.uniform(8, cam.width - 8, n).astype(np.float32)
+    ky = rs.uniform(8, cam.height - 8, n).astype(np.float32)
+    fd = rs.normal(size=(n, 256)).astype(np.float32)
+    fd /= np.linalg.norm(fd, axis=1, keepdims=True)
+    inp = synth.association_inputs(6, fd, np.stack([kx, ky], 1), m, cam.width, cam.height)
+    e = capi.Extractor(cam, max_batch=1, max_map_points=4096)
+    try:
+        e.comm_init(capi.comm_unique_id(), 0, 1)
+        e.upload_map(inp["map_desc"])
+        e.assoc_stage(kx, ky, fd, np.ones(n, np.uint8), inp["proj_uv"], inp["view_cos"], 10.0, 0.8)
+        e.assoc_run()
+        e.assoc_allgather(m, m + 7)  # common send count larger than the shard
+        rec, us = e.assoc_allgather_fetch()
+        want = e.assoc_fetch()
+        assert rec.shape == (1, m + 7, 5) and us >= 0
+        np.testing.assert_array_equal(rec[0, :m, 0], want["best_idx"])
+        np.testing.assert_array_equal(rec[0, :m, 1], want["second_idx"])
+        np.testing.assert_array_equal(rec[0, :m, 2], want["best_d"].view(np.int32))
+        np.testing.assert_array_equal(rec[0, :m, 3], want["second_d"].view(np.int32))
+        np.testing.assert_array_equal(rec[0, :m, 4].astype(np.uint8), want["accept"])
+        assert (rec[0, m:, 0] == -1).all() and (rec[0, m:, 4] == 0).all()
+        assert want["accept"].sum() > 50
+        e.comm_destroy()
+    finally:
+        e.close()
+
+
 def test_assoc_batch_equals_oracle_per_frame():
     """Throughput form: all frames of an extraction batch against the resident table in one set of launches."""
     from oracle import post_ref as O

@@ -389,3 +389,51 @@ def test_extend_map_matches_random_small_graphs_sweep():
     finally:
         e.close()
     assert not bad, "mismatching (seed, n, M, edges, th, ratio): %s" % bad
+
+
+def test_pipelined_extend_equals_synchronous_fetch():
+    """ppg_assoc_stage_batch_async (pinned projections) + ppg_extend_run_batch + ppg_extend_fetch_batch_async +
+    ppg_extend_collect == ppg_assoc_stage_batch + ppg_extend_run_batch + ppg_extend_fetch_batch, on a batch in which every
+    frame has its local map (synth.extend_inputs_multi: the benchmark workload)."""
+    from ppg_slam_b200 import capi
+    cam = cameras.EUROC
+    Bn, M = 4, 2048
+    e = capi.Extractor(cam, max_batch=Bn, max_map_points=M)
+    try:
+        frames = [synth.frame(s, cam.width, cam.height) for s in range(Bn)]
+        recs = e.run(frames)
+        base = synth.extend_inputs_multi(17, recs, M, cam.width, cam.height, th=10.0)
+        e.upload_map(base["map_desc"])
+        e.upload_map_graph(base["candidate"], base["observed"], base["bad"], base["edge_off"], base["edge_other"],
+                           base["edge_ok"])
+        e.assoc_stage_batch(base["proj_all"], base["vcos_all"], 10.0, 0.8)
+        e.extend_run_batch(Bn)
+        want = e.extend_fetch_batch(Bn)
+        assert min(w["n_accepted"] for w in want) > 100  # every frame matches its own slice of the table
+        for f in range(Bn):  # and equals the oracle
+            r = recs[f]
+            ref = _oracle(cam, dict(base, proj_uv=base["proj_all"][f], view_cos=base["vcos_all"][f],
+                                    kp_mp=np.full(r["n_kp"], -1, np.int32)),
+                          r["kp_x"], r["kp_y"], r["desc"], r["edge_start"], r["edge_end"], r["conn_off"], r["conn_idx"],
+                          10.0, 0.8)
+            _same(want[f], ref)
+        pu = capi.pinned_array(base["proj_all"].shape, np.float32)
+        pv = capi.pinned_array(base["vcos_all"].shape, np.float32)
+        pu[...] = base["proj_all"]
+        pv[...] = base["vcos_all"]
+        pf = capi.pinned_array((Bn, cam.height, cam.width), np.uint8)
+        for i, g in enumerate(frames):
+            pf[i] = g
+        e.extract_async([pf[i] for i in range(Bn)])
+        e.assoc_stage_batch_async(pu, pv, 10.0, 0.8)
+        e.extend_run_batch(Bn)
+        e.extend_fetch_batch_async(Bn)
+        e.extract_wait(Bn)
+        got = e.extend_collect(Bn)
+        for f in range(Bn):
+            _same(got[f], want[f])
+        with pytest.raises(capi.PpgError):  # pageable projections are refused by the asynchronous call
+            e.assoc_stage_batch_async(base["proj_all"], base["vcos_all"], 10.0, 0.8)
+    finally:
+        e.close()
+        capi.drop_pinned()

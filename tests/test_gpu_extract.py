@@ -336,6 +336,35 @@ def test_contexts_of_different_shapes_coexist(net):
         es.close()
 
 
+def test_pipelined_calls_equal_synchronous_calls(ex_euroc):
+    """ppg_extract_async / ppg_extract_wait with frames in pinned memory (and with pageable frames, which go through the
+    staging buffer) return the records ppg_extract returns; two contexts driven as a ring from one thread."""
+    from ppg_slam_b200 import capi
+    frames = [synth.frame(s, 752, 480) for s in (20, 21, 22)]
+    want = ex_euroc.run(frames)
+    pf = capi.pinned_array((3, 480, 752), np.uint8)
+    for i, g in enumerate(frames):
+        pf[i] = g
+    other = capi.Extractor(cameras.EUROC, max_batch=4)
+    try:
+        ring = [ex_euroc, other]
+        got = {}
+        for step in range(6):
+            x = ring[step % 2]
+            if step >= 2:
+                got[step - 2] = x.extract_wait(3)
+            if step < 4:
+                x.extract_async([pf[i] for i in range(3)] if step != 1 else frames)  # step 1: pageable frames
+        for k in range(4):
+            for f in range(3):
+                for key in ("px", "py", "edge_start", "edge_end", "col_pairs", "conn_idx"):
+                    np.testing.assert_array_equal(got[k][f][key], want[f][key])
+                np.testing.assert_array_equal(got[k][f]["desc"], want[f]["desc"])
+    finally:
+        other.close()
+        capi.drop_pinned()
+
+
 def test_two_contexts_on_two_threads(ex_euroc):
     """Different contexts are independent: two host threads driving one ctx each (the pipelined e2e arm of bench.py)
     get the records a single-threaded run gets."""

@@ -15,11 +15,9 @@ B = int(os.environ.get("PPG_NCU_BATCH", "32"))
 cam, frames = bench.make_workload(B)
 e = capi.Extractor(cam, max_batch=B, max_map_points=bench.MAP_ROWS)
 recs = e.run(frames)
-base, per_frame = bench.make_assoc_inputs(cam, recs, bench.MAP_ROWS)
+base = bench.make_assoc_inputs(cam, recs, bench.MAP_ROWS)
 bench.upload_map(e, base)
-proj_all = np.stack([uv for uv, _ in per_frame])
-vcos_all = np.stack([vc for _, vc in per_frame])
-e.assoc_stage_batch(proj_all, vcos_all, bench.TH, bench.RATIO)
+e.assoc_stage_batch(base["proj_all"], base["vcos_all"], bench.TH, bench.RATIO)
 for step in range(2):
     e.run_device(B)
     if os.environ.get("PPG_NCU_ASSOC", "extend") == "core":
