@@ -96,3 +96,120 @@ class RefExtractor:
                    col_pairs=col_pairs[:nl], desc=nd[:n])
         maps = dict(prob=prob, heat_raw=heat_raw, heat_ref=heat_ref, heat_final=heat_final, desc=desc)
         return rec, maps
+
+
+# ---------------------------------------------------------------- matcher (matching/src/Matcher.cpp)
+def matcher_available():
+    return ref_build.available() and os.path.exists(ref_build.lib_path("matcher"))
+
+
+def _cam_params(cam):
+    return np.array([cam.K[0], cam.K[4], cam.K[2], cam.K[5]] + list(cam.D), np.float32)
+
+
+def consistent_edge_ok(bad, edge_off, edge_other, edge_ok):
+    """What `!pME->isBad() && pME->mbValid` gives for every CSR entry: MapEdge::isBad (PPGGraph.cpp:90-94) is also true when
+    an end point is bad, so a flattening of real objects never has edge_ok = 1 next to a bad end point."""
+    ok = np.array(edge_ok, np.uint8).copy()
+    for p in range(len(bad)):
+        for k in range(edge_off[p], edge_off[p + 1]):
+            q = edge_other[k]
+            if bad[p] or (q >= 0 and bad[q]):
+                ok[k] = 0
+    return ok
+
+
+def extend_map_matches(cam, map_desc, candidate, observed, bad, edge_off, edge_other, edge_ok, proj_uv, view_cos, tracked,
+                       kp_x, kp_y, frame_desc, kp_mp, edge_start, edge_end, conn_off, conn_idx, th, ratio, kedge_me=None):
+    """The reference's own Matcher::ExtendMapMatches on a pointer graph rebuilt from the flat arrays; same arguments and
+    result as oracle.post_ref.extend_map_matches."""
+    lib = _lib("matcher")
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    md, cd, ob, bd = f32(map_desc), u8(candidate), u8(observed), u8(bad)
+    eo, et, ek = i32(edge_off), i32(edge_other), u8(edge_ok)
+    uv, vc = f32(proj_uv), f32(view_cos)
+    tr = u8(tracked).copy()
+    kx, ky, fd = f32(kp_x), f32(kp_y), f32(frame_desc)
+    km = i32(kp_mp).copy()
+    es, ee, co, ci = i32(edge_start), i32(edge_end), i32(conn_off), i32(conn_idx)
+    ne = len(es)
+    me = np.full(max(ne, 1), -1, np.int32) if kedge_me is None else i32(kedge_me).copy()
+    if len(et) == 0:
+        et, ek = np.zeros(1, np.int32), np.zeros(1, np.uint8)
+    if len(ci) == 0:
+        ci = np.zeros(1, np.int32)
+    if ne == 0:
+        es, ee = np.zeros(1, np.int32), np.zeros(1, np.int32)
+    params = _cam_params(cam)
+    u8p, i32p = C.c_uint8, C.c_int
+    nm = lib.ref_extend_map_matches(_p(params), cam.width, cam.height, int(cam.fisheye), len(cd), _p(md), _p(cd, u8p),
+                                    _p(ob, u8p), _p(bd, u8p), _p(eo, i32p), _p(et, i32p), _p(ek, u8p), _p(uv), _p(vc),
+                                    _p(tr, u8p), len(kx), _p(kx), _p(ky), _p(fd), _p(km, i32p), ne, _p(es, i32p),
+                                    _p(ee, i32p), _p(co, i32p), _p(ci, i32p), _p(me, i32p), C.c_float(th),
+                                    C.c_float(ratio))
+    if nm < 0:
+        raise RuntimeError("reference ExtendMapMatches failed")
+    return dict(nmatches=nm, kp_mp=km, kedge_me=me[:ne], tracked=tr)
+
+
+def features_in_area(cam, kx, ky, x, y, r):
+    lib = _lib("matcher")
+    kx, ky = np.ascontiguousarray(kx, np.float32), np.ascontiguousarray(ky, np.float32)
+    out = np.zeros(max(len(kx), 1), np.int32)
+    n = lib.ref_features_in_area(_p(_cam_params(cam)), cam.width, cam.height, int(cam.fisheye), len(kx), _p(kx), _p(ky),
+                                 C.c_float(x), C.c_float(y), C.c_float(r), _p(out, C.c_int))
+    return out[:n].copy()
+
+
+def descriptor_distance(a, b):
+    lib = _lib("matcher")
+    lib.ref_descriptor_distance.restype = C.c_float
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    return float(lib.ref_descriptor_distance(_p(a), _p(b)))
+
+
+def candidate_order(candidate, bad, edge_off):
+    """Rows in the order the reference's ExtendMapMatches walks them (its unstable std::sort included)."""
+    lib = _lib("matcher")
+    cd, bd, eo = np.ascontiguousarray(candidate, np.uint8), np.ascontiguousarray(bad, np.uint8), np.ascontiguousarray(edge_off, np.int32)
+    out = np.zeros(max(len(cd), 1), np.int32)
+    n = lib.ref_candidate_order(len(cd), _p(cd, C.c_uint8), _p(bd, C.c_uint8), _p(eo, C.c_int), _p(out, C.c_int))
+    return out[:n].copy()
+
+
+def permute_table(perm, map_desc, candidate, observed, bad, edge_off, edge_other, edge_ok, proj_uv, view_cos, tracked,
+                  kp_mp):
+    """The same map with its rows renumbered: new row i = old row perm[i] (perm covers every row).  -> dict of the
+    renumbered arrays + `old_of_new` / `new_of_old` to translate results back."""
+    perm = np.asarray(perm, np.int64)
+    P = len(candidate)
+    new_of_old = np.empty(P, np.int64)
+    new_of_old[perm] = np.arange(P)
+    deg = np.diff(edge_off)
+    off = np.zeros(P + 1, np.int32)
+    off[1:] = np.cumsum(deg[perm])
+    other = np.zeros(len(edge_other), np.int32)
+    ok = np.zeros(len(edge_ok), np.uint8)
+    pos_new_of_old = np.zeros(max(len(edge_other), 1), np.int64)  # CSR position translation (kedge_me)
+    for i, p in enumerate(perm):
+        a, b = edge_off[p], edge_off[p + 1]
+        o = np.asarray(edge_other[a:b], np.int64)
+        other[off[i]:off[i + 1]] = np.where(o >= 0, new_of_old[np.maximum(o, 0)], -1)
+        ok[off[i]:off[i + 1]] = edge_ok[a:b]
+        pos_new_of_old[a:b] = np.arange(off[i], off[i + 1])
+    km = np.asarray(kp_mp, np.int64)
+    return dict(map_desc=np.ascontiguousarray(map_desc[perm]), candidate=np.asarray(candidate)[perm],
+                observed=np.asarray(observed)[perm], bad=np.asarray(bad)[perm], edge_off=off, edge_other=other,
+                edge_ok=ok, proj_uv=np.ascontiguousarray(proj_uv[perm]), view_cos=np.asarray(view_cos)[perm],
+                tracked=np.asarray(tracked)[perm],
+                kp_mp=np.where(km >= 0, new_of_old[np.maximum(km, 0)], km).astype(np.int32), old_of_new=perm,
+                new_of_old=new_of_old, pos_new_of_old=pos_new_of_old)
+
+
+def walk_order_permutation(candidate, bad, edge_off):
+    """perm for permute_table: the candidates in the reference's walk order first, then all other rows."""
+    order = candidate_order(candidate, bad, edge_off)
+    rest = np.setdiff1d(np.arange(len(candidate)), order)
+    return np.concatenate([order, rest]).astype(np.int64)

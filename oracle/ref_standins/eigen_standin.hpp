@@ -144,6 +144,10 @@ class Matrix {
         for (int i = 0; i < size(); i++) st.data()[i] = S();
         return *this;
     }
+    Matrix& setConstant(S v) {
+        for (int i = 0; i < size(); i++) st.data()[i] = v;
+        return *this;
+    }
     Matrix& setIdentity() {
         *this = Identity();
         return *this;
@@ -151,6 +155,10 @@ class Matrix {
     CommaInit<Matrix> operator<<(S v) {
         (*this)(0, 0) = v;
         return CommaInit<Matrix>{*this, 1};
+    }
+    CommaInit<Matrix> operator<<(const Matrix& o) {  // `a << b` with a whole matrix: plain assignment
+        *this = o;
+        return CommaInit<Matrix>{*this, size()};
     }
 
     Matrix operator+(const Matrix& o) const {

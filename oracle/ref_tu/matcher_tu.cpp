@@ -1,0 +1,226 @@
+// Reference-pinning harness, part 2: the reference's OWN matcher and map sources compiled as they lie under
+// /root/reference (matching/src/Matcher.cpp, feature/src/MapPoint.cpp, map/src/Frame.cpp, feature/src/PPGGraph.cpp,
+// sensors/src/GeometricCamera.cpp) against the stand-ins of oracle/ref_standins.  TEST INFRASTRUCTURE ONLY.
+//
+// ref_extend_map_matches builds the pointer graph the reference works on -- MapPoint / MapEdge / Frame / KeyPointEx /
+// KeyEdge OBJECTS -- from the flat arrays the C ABI and the oracle use (the inverse of the flattening in
+// include/ppg_shim.hpp), calls the real Matcher::ExtendMapMatches (Matcher.cpp:203-381), which in turn calls the real
+// Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea (Frame.cpp:138-156, 262-327), MapPoint::isBad / getEdges /
+// GetDescriptor / Observations, MapEdge::isBad / theOtherPt, KeyEdge::theOtherPid and DescriptorDistance
+// (MapPoint.cpp:22-29), and reads F.mvpMapPoints / F.mvpMapEdges / mnTrackedbyFrame back.
+// `private -> public` lets the harness fill the members a running system would have filled; no source is modified.
+#include <algorithm>
+#include <atomic>
+#include <cassert>
+#include <chrono>
+#include <deque>
+#include <iostream>
+#include <list>
+#include <map>
+#include <mutex>
+#include <numeric>
+#include <set>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+#include <unistd.h>
+
+#include <torch/script.h>
+#include <torch/torch.h>
+
+#include "cv_eigen_standin.hpp"
+#include "DBoW3/DBoW3.h"
+
+#define private public
+#define protected public
+#include REF_FILE(matching/src/Matcher.cpp)
+#include REF_FILE(feature/src/MapPoint.cpp)
+#include REF_FILE(map/src/Frame.cpp)
+#include REF_FILE(feature/src/PPGGraph.cpp)
+#include REF_FILE(sensors/src/GeometricCamera.cpp)
+#undef protected
+#undef private
+
+namespace {
+
+class HarnessCamera : public GeometricCamera {
+   public:
+    HarnessCamera(const std::vector<float>& p, int w, int h, bool fisheye) : GeometricCamera(p, w, h, 20.f) {
+        mnId = 0;
+        mnType = fisheye ? CAM_FISHEYE : CAM_PINHOLE;
+        InitializeImageBounds();
+    }
+    Eigen::Vector2d project(const Eigen::Vector3d&) override { return Eigen::Vector2d(); }
+    Eigen::Vector2f project(const Eigen::Vector3f&) override { return Eigen::Vector2f(); }
+    Eigen::Vector3f unproject(const Eigen::Vector2f&) override { return Eigen::Vector3f(); }
+    Eigen::Matrix<double, 2, 3> projectJac(const Eigen::Vector3d&) override { return Eigen::Matrix<double, 2, 3>(); }
+    cv::Mat toK() override {  // sensors/src/Pinhole.cpp:68-72
+        cv::Mat K = cv::Mat::zeros(3, 3, CV_32F);
+        K.at<float>(0, 0) = mvParameters[0];
+        K.at<float>(0, 2) = mvParameters[2];
+        K.at<float>(1, 1) = mvParameters[1];
+        K.at<float>(1, 2) = mvParameters[3];
+        K.at<float>(2, 2) = 1.f;
+        return K;
+    }
+    cv::Mat toD() override {  // :74-78
+        cv::Mat D(4, 1, CV_32F);
+        for (int i = 0; i < 4; i++) D.at<float>(i, 0) = mvParameters[4 + i];
+        return D;
+    }
+    Eigen::Matrix3f toK_() override { return Eigen::Matrix3f(); }
+    int imWidth() override { return mnWidth; }
+    int imHeight() override { return mnHeight; }
+    bool ReconstructWithTwoViews(const std::vector<KeyPointEx>&, const std::vector<KeyPointEx>&, const std::vector<int>&,
+                                 SE3f&, std::vector<cv::Point3f>&, std::vector<bool>&) override {
+        return false;
+    }
+    bool epipolarConstrain(const KeyPointEx&, const KeyPointEx&, const Eigen::Matrix3f&, const Eigen::Vector3f&) override {
+        return false;
+    }
+};
+
+MapPoint* make_point(KeyFrame* kf, const float* desc, bool bad, bool in_view, bool observed, float u, float v, float vcos,
+                     bool tracked, unsigned long frame_id) {
+    MapPoint* mp = new MapPoint(Eigen::Vector3f(0.f, 0.f, 1.f), kf);  // the real constructor
+    mp->mbBad = bad;
+    mp->mbTrackInView = in_view;
+    mp->nObs = observed ? 1 : 0;
+    mp->mTrackProjX = u;
+    mp->mTrackProjY = v;
+    mp->mTrackViewCos = vcos;
+    mp->mnTrackedbyFrame = tracked ? frame_id : 0;
+    mp->mDescriptor = cv::Mat(1, 256, CV_32F);
+    if (desc) memcpy(mp->mDescriptor.data, desc, 1024);
+    return mp;
+}
+
+}  // namespace
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+// Arguments as oracle/ppg_oracle.c::ppgo_extend_map_matches documents them (tracked / kp_mp / kedge_me in and out);
+// params8 = fx fy cx cy d0..d3.  The caller must pass edge_ok consistent with MapEdge::isBad (an edge with a bad end
+// point is bad) -- the flattening of include/ppg_shim.hpp guarantees that.  Returns nmatches, or -1.
+REF_API int ref_extend_map_matches(const float* params8, int width, int height, int fisheye, int P, const float* map_desc,
+                                   const unsigned char* candidate, const unsigned char* observed,
+                                   const unsigned char* bad, const int* edge_off, const int* edge_other,
+                                   const unsigned char* edge_ok, const float* proj_uv, const float* view_cos,
+                                   unsigned char* tracked, int n, const float* kx, const float* ky, const float* frame_desc,
+                                   int* kp_mp, int n_kedges, const int* kes, const int* kee, const int* conn_off,
+                                   const int* conn_idx, int* kedge_me, float th, float ratio) {
+    try {
+        HarnessCamera cam(std::vector<float>(params8, params8 + 8), width, height, fisheye != 0);
+        const unsigned long FID = 7;
+        KeyFrame* kf = static_cast<KeyFrame*>(calloc(1, sizeof(KeyFrame)));  // the MapPoint constructor reads two ids of it
+        std::vector<MapPoint*> pts(P);
+        for (int p = 0; p < P; p++)
+            pts[p] = make_point(kf, map_desc + (size_t)p * 256, bad[p] != 0, candidate[p] != 0, observed[p] != 0,
+                                proj_uv[2 * p], proj_uv[2 * p + 1], view_cos[p], tracked[p] != 0, FID);
+        // a point outside the table: the far end of edges whose theOtherPt(pMP) is nullptr, and the holder of
+        // keypoints that are taken by a map point the caller did not list (kp_mp == -2)
+        MapPoint* outsideA = make_point(kf, nullptr, false, false, true, 0, 0, 0, false, FID);
+        MapPoint* outsideB = make_point(kf, nullptr, false, false, true, 0, 0, 0, false, FID);
+        const int E = edge_off[P];
+        std::vector<MapEdge*> edges(E);
+        std::map<MapEdge*, int> edge_pos;
+        for (int p = 0; p < P; p++)
+            for (int k = edge_off[p]; k < edge_off[p + 1]; k++) {
+                const int q = edge_other[k];
+                MapEdge* e = q >= 0 ? new MapEdge(pts[p], pts[q]) : new MapEdge(outsideA, outsideB);  // real constructor
+                e->mbValid = edge_ok[k] != 0;
+                edges[k] = e;
+                edge_pos[e] = k;
+            }
+        // getEdges() order = the CSR order (the constructor above appended every edge to both end points)
+        for (int p = 0; p < P; p++) pts[p]->mvEdges.assign(edges.begin() + edge_off[p], edges.begin() + edge_off[p + 1]);
+
+        Frame F;  // Frame::Frame()
+        F.mnId = FID;
+        F.N = n;
+        F.mpCamera = &cam;
+        F.mvKeysUn.resize(n);
+        for (int i = 0; i < n; i++) {
+            KeyPointEx k(kx[i], ky[i], 1.f);
+            k.mPosUn = k.mPos;
+            k.mbOut = false;
+            for (int c = conn_off[i]; c < conn_off[i + 1]; c++) k.mvConnected.push_back((unsigned int)conn_idx[c]);
+            F.mvKeysUn[i] = k;
+        }
+        F.mvKeys = F.mvKeysUn;
+        for (int e = 0; e < n_kedges; e++) F.mvKeyEdges.emplace_back((unsigned int)kes[e], (unsigned int)kee[e]);
+        F.mDescriptors = cv::Mat(std::max(n, 1), 256, CV_32F);
+        if (n > 0) memcpy(F.mDescriptors.data, frame_desc, (size_t)n * 1024);
+        F.mvpMapPoints.assign(n, nullptr);
+        for (int i = 0; i < n; i++) F.mvpMapPoints[i] = kp_mp[i] >= 0 ? pts[kp_mp[i]] : (kp_mp[i] == -2 ? outsideA : nullptr);
+        F.mvpMapEdges.assign(n_kedges, nullptr);
+        for (int e = 0; e < n_kedges; e++) F.mvpMapEdges[e] = kedge_me[e] >= 0 ? edges[kedge_me[e]] : nullptr;
+        F.AssignFeaturesToGrid();
+
+        Matcher matcher(&cam, ratio);
+        const int nm = matcher.ExtendMapMatches(F, pts, th);
+
+        std::map<MapPoint*, int> row_of;
+        for (int p = 0; p < P; p++) row_of[pts[p]] = p;
+        for (int i = 0; i < n; i++) {
+            MapPoint* m = F.mvpMapPoints[i];
+            kp_mp[i] = !m ? -1 : (row_of.count(m) ? row_of[m] : -2);
+        }
+        for (int e = 0; e < n_kedges; e++) kedge_me[e] = F.mvpMapEdges[e] ? edge_pos[F.mvpMapEdges[e]] : -1;
+        for (int p = 0; p < P; p++) tracked[p] = pts[p]->mnTrackedbyFrame == FID ? 1 : 0;
+        for (MapEdge* e : edges) delete e;
+        for (MapPoint* p : pts) delete p;
+        delete outsideA;
+        delete outsideB;
+        free(kf);
+        return nm;
+    } catch (const std::exception& e) {
+        std::cerr << "ref_extend_map_matches: " << e.what() << std::endl;
+        return -1;
+    }
+}
+
+// The order in which ExtendMapMatches walks the candidates: Matcher.cpp:206-224 filters `!isBad() && mbTrackInView` in
+// vpMapPoints order and std::sorts by getEdges().size() descending -- an UNSTABLE sort, so the order of equal degrees is
+// whatever this libstdc++'s introsort makes of that initial sequence.  The same call on the same sequence of degrees
+// gives the same permutation; the tests use it to hand the oracle (whose documented tie rule is table order) a table
+// that is already in the reference's walk order.  Returns the number of candidates.
+REF_API int ref_candidate_order(int P, const unsigned char* candidate, const unsigned char* bad, const int* edge_off,
+                                int* order) {
+    std::vector<std::pair<int, size_t>> c;  // (row, getEdges().size())
+    c.reserve(P);
+    for (int p = 0; p < P; p++) {
+        if (bad[p] || !candidate[p]) continue;
+        c.emplace_back(p, (size_t)(edge_off[p + 1] - edge_off[p]));
+    }
+    std::sort(c.begin(), c.end(),
+              [](const std::pair<int, size_t>& a, const std::pair<int, size_t>& b) { return a.second > b.second; });
+    for (size_t i = 0; i < c.size(); i++) order[i] = c[i].first;
+    return (int)c.size();
+}
+
+// Frame::GetFeaturesInArea alone (the window query every matcher uses): indices in the reference's visiting order.
+REF_API int ref_features_in_area(const float* params8, int width, int height, int fisheye, int n, const float* kx,
+                                 const float* ky, float x, float y, float r, int* out) {
+    HarnessCamera cam(std::vector<float>(params8, params8 + 8), width, height, fisheye != 0);
+    Frame F;
+    F.N = n;
+    F.mpCamera = &cam;
+    F.mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) {
+        KeyPointEx k(kx[i], ky[i], 1.f);
+        F.mvKeysUn[i] = k;
+    }
+    F.AssignFeaturesToGrid();
+    const std::vector<size_t> v = F.GetFeaturesInArea(x, y, r);
+    for (size_t i = 0; i < v.size(); i++) out[i] = (int)v[i];
+    return (int)v.size();
+}
+
+// DescriptorDistance (feature/src/MapPoint.cpp:22-29) on two 1 x 256 rows.
+REF_API float ref_descriptor_distance(const float* a, const float* b) {
+    cv::Mat A(1, 256, CV_32F, const_cast<float*>(a)), B(1, 256, CV_32F, const_cast<float*>(b));
+    return DescriptorDistance(A, B);
+}

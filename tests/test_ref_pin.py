@@ -134,3 +134,112 @@ def test_full_cuda_path_stays_close_to_the_reference(case):
     mine = {(int(x), int(y)) for x, y in zip(got["px"], got["py"])}
     common = len(ref & mine)
     assert common >= 0.85 * len(ref) and len(mine) <= 1.15 * len(ref) + 2, (common, len(ref), len(mine))
+
+
+# ------------------------------------------------------------------------------------------------ Matcher (L2)
+def _l2():
+    return np.load(os.path.join(GOLD, "ref_l2.npz"))
+
+
+def _l2_cases():
+    z = _l2()
+    return sorted({k.split("/")[0] for k in z.files if k.startswith("case")})
+
+
+_L2_CAMS = [cameras.EUROC, cameras.TUMVI]
+
+
+def _l2_case(name):
+    z = _l2()
+    d = {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "/")}
+    cam = _L2_CAMS[int(d["meta"][0])]
+    return cam, float(d["meta"][1]), float(d["meta"][2]), d
+
+
+def _same_as_reference(got, d):
+    assert int(got["nmatches"]) == int(d["ref_nmatches"][0])
+    np.testing.assert_array_equal(got["kp_mp"], d["ref_kp_mp"])       # F.mvpMapPoints
+    np.testing.assert_array_equal(got["kedge_me"], d["ref_kedge_me"])  # F.mvpMapEdges
+    np.testing.assert_array_equal(got["tracked"], d["ref_tracked"])    # mnTrackedbyFrame == F.mnId
+
+
+@pytest.mark.parametrize("name", _l2_cases())
+def test_oracle_reproduces_the_reference_extend_map_matches(name):
+    """Matcher::ExtendMapMatches as the reference's own C++ ran it on MapPoint / MapEdge / Frame objects (non-candidate,
+    bad, unobserved and already-tracked rows, invalid and dangling map edges, keypoints that hold a map point): the
+    oracle reproduces F.mvpMapPoints, F.mvpMapEdges, the tracked flags and the count."""
+    from oracle import post_ref as O
+    cam, th, ratio, d = _l2_case(name)
+    got = O.extend_map_matches(cam, d["map_desc"], d["candidate"], d["observed"], d["bad"], d["edge_off"], d["edge_other"],
+                               d["edge_ok"], d["proj_uv"], d["view_cos"], d["tracked"], d["kp_x"], d["kp_y"],
+                               d["frame_desc"], d["kp_mp"], d["edge_start"], d["edge_end"], d["conn_off"], d["conn_idx"],
+                               th=th, ratio=ratio)
+    _same_as_reference(got, d)
+
+
+@pytest.mark.parametrize("cname,cam", [("EuRoC", cameras.EUROC), ("TUM-VI", cameras.TUMVI)])
+def test_oracle_reproduces_the_reference_get_features_in_area(cname, cam):
+    """Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea of the reference (keypoints outside the image bounds
+    included): same indices in the same visiting order."""
+    from oracle import post_ref as O
+    z = _l2()
+    kx, ky, q = z["area_%s/kx" % cname], z["area_%s/ky" % cname], z["area_%s/queries" % cname]
+    ans, off = z["area_%s/ans" % cname], z["area_%s/off" % cname]
+    for i, (x, y, r) in enumerate(q):
+        got = O.features_in_area(cam, kx, ky, float(x), float(y), float(r))
+        np.testing.assert_array_equal(got, ans[off[i]:off[i + 1]])
+    assert off[-1] > 100
+
+
+def test_oracle_equals_reference_extend_live():
+    """60 random configurations through the reference's own Matcher::ExtendMapMatches (here) and the oracle."""
+    from oracle import post_ref as O, ref_harness as R
+    if not R.matcher_available():
+        pytest.skip("reference harness not built (no /root/reference on this host)")
+    from tests.test_oracle_extend import random_frame_graph
+    cam = cameras.EUROC
+    for seed in range(60):
+        rs = np.random.RandomState(1000 + seed)
+        n, M = int(rs.randint(3, 45)), int(rs.randint(5, 140))
+        ne = int(rs.randint(0, min(3 * n, n * (n - 1) // 2) + 1))
+        kx, ky, fd, es, ee, coff, cidx, _ = random_frame_graph(rs, cam, n, ne)
+        if seed % 3 == 0:
+            kx = (300 + rs.uniform(0, 60, n)).astype(np.float32)
+            ky = (200 + rs.uniform(0, 40, n)).astype(np.float32)
+        th = float(rs.choice([3.0, 10.0, 15.0]))
+        inp = synth.extend_inputs(seed, fd, np.stack([kx, ky], 1), es, ee, M, cam.width, cam.height, th=th,
+                                  planted_frac=float(rs.uniform(0.2, 0.9)), clean=bool(seed % 4 == 1))
+        ok = R.consistent_edge_ok(inp["bad"], inp["edge_off"], inp["edge_other"], inp["edge_ok"])
+        ratio = float(rs.choice([0.6, 0.8, 0.95]))
+        ref = R.extend_map_matches(cam, inp["map_desc"], inp["candidate"], inp["observed"], inp["bad"], inp["edge_off"],
+                                   inp["edge_other"], ok, inp["proj_uv"], inp["view_cos"], inp["tracked"], kx, ky, fd,
+                                   inp["kp_mp"], es, ee, coff, cidx, th, ratio)
+        perm = R.walk_order_permutation(inp["candidate"], inp["bad"], inp["edge_off"])
+        t = R.permute_table(perm, inp["map_desc"], inp["candidate"], inp["observed"], inp["bad"], inp["edge_off"],
+                            inp["edge_other"], ok, inp["proj_uv"], inp["view_cos"], inp["tracked"], inp["kp_mp"])
+        got = O.extend_map_matches(cam, t["map_desc"], t["candidate"], t["observed"], t["bad"], t["edge_off"],
+                                   t["edge_other"], t["edge_ok"], t["proj_uv"], t["view_cos"], t["tracked"], kx, ky, fd,
+                                   t["kp_mp"], es, ee, coff, cidx, th=th, ratio=ratio)
+        km = np.where(ref["kp_mp"] >= 0, t["new_of_old"][np.maximum(ref["kp_mp"], 0)], ref["kp_mp"])
+        me = np.where(ref["kedge_me"] >= 0, t["pos_new_of_old"][np.maximum(ref["kedge_me"], 0)], -1)
+        assert got["nmatches"] == ref["nmatches"], seed
+        np.testing.assert_array_equal(got["kp_mp"], km)
+        np.testing.assert_array_equal(got["kedge_me"], me)
+        np.testing.assert_array_equal(got["tracked"], ref["tracked"][t["old_of_new"]])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _l2_cases())
+def test_cuda_extend_map_matches_reproduces_the_reference(name):
+    """ppg_extend_map_matches against what the reference's C++ produced -- no oracle in between."""
+    from ppg_slam_b200 import capi
+    cam, th, ratio, d = _l2_case(name)
+    e = capi.Extractor(cam, max_batch=1, max_map_points=1024)
+    try:
+        e.upload_map(d["map_desc"])
+        e.upload_map_graph(d["candidate"], d["observed"], d["bad"], d["edge_off"], d["edge_other"], d["edge_ok"])
+        got = e.extend_map_matches(d["kp_x"], d["kp_y"], d["frame_desc"], d["kp_mp"], d["edge_start"], d["edge_end"],
+                                   d["conn_off"], d["conn_idx"], d["proj_uv"], d["view_cos"], d["tracked"], th, ratio)
+    finally:
+        e.close()
+    _same_as_reference(got, d)
