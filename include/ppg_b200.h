@@ -431,6 +431,30 @@ typedef struct {
 } ppg_bow_match_out;
 int ppg_search_by_bow(ppg_ctx* ctx, const ppg_bow_match_in* in, ppg_bow_match_out* out);
 
+/* ---- the whole Matcher::SearchForInitialization on the GPU (matching/src/Matcher.cpp:582-651; called from
+ * system/src/Tracking.cpp:525 with windowSize 50).  The n1 descriptors of F1 are the resident table (ppg_upload_map);
+ * for every F1 feature in index order: the radius-`window` box around prev_matched[i1] in F2
+ * (Frame::GetFeaturesInArea), best / second best DescriptorDistance over the features not matched yet, accept iff
+ * best <= th_low && best < ratio * second (the reference's vector<int> vMatchedDistance makes a matched F2 feature
+ * unavailable for good, see oracle/ppg_oracle.c).  Needs no map graph. */
+typedef struct {
+    int n1;                    /* F1.mvKeysUn.size() = rows uploaded with ppg_upload_map (F1.mDescriptors) */
+    const float* prev_matched; /* n1 x 2: vbPrevMatched */
+    int n2;
+    const float* kp2_x;        /* n2: F2.mvKeysUn[i].mPos */
+    const float* kp2_y;
+    const float* desc2;        /* n2 x 256: F2.mDescriptors */
+    int window;                /* windowSize */
+    float ratio;               /* Matcher::mfNNratio */
+} ppg_init_match_in;
+typedef struct {
+    int32_t* matches12;  /* n1: vnMatches12 (index in F2 or -1), or NULL */
+    float* prev_matched; /* n1 x 2: vbPrevMatched after the update of :644-647 (may alias the input), or NULL */
+    int nmatches;
+    int n_rescans;
+} ppg_init_match_out;
+int ppg_search_for_initialization(ppg_ctx* ctx, const ppg_init_match_in* in, ppg_init_match_out* out);
+
 /* Device pointers of the staged association results (n_rows each), for the sharded all-gather that
  * the multi-GPU host layer issues through NCCL (ppg_slam_b200/sharded.py). */
 int ppg_assoc_device_results(ppg_ctx* ctx, void** best_idx, void** second_idx, void** best_dist, void** second_dist,

@@ -8,7 +8,9 @@
 // core for the matchers that keep their own sequential loops.  (tests/test_shim_compiles.py builds it against tiny
 // stand-in headers to keep it syntactically honest in a container without OpenCV/Eigen.)
 #pragma once
+#include <cstdio>
 #include <cstring>
+#include <functional>
 #include <stdexcept>
 #include <map>
 #include <string>
@@ -22,13 +24,16 @@
 #include "GeometricCamera.h"  // sensors/include: KeyPointEx, GeometricCamera
 #include "MapPoint.h"         // feature/include
 #include "PPGGraph.h"         // feature/include: KeyEdge
+#include "Matcher.h"          // matching/include: the base of ppg_shim::Matcher (host-side matchers stay there)
 #endif
 
 namespace ppg_shim {
 
+// Every C-ABI failure throws -- PPG_ERR_CAPACITY included: a truncated result must never reach the SLAM caller
+// silently.  The two places where a capacity overflow has a defined meaning handle the code themselves:
+// PPGExtractor::run (records a frame status) and extend_map_matches (falls back to the caller's CPU loop).
 inline void check(int rc, ppg_ctx* ctx, const char* what) {
-    if (rc != PPG_OK && rc != PPG_ERR_CAPACITY)
-        throw std::runtime_error(std::string(what) + ": " + ppg_last_error(ctx));
+    if (rc != PPG_OK) throw std::runtime_error(std::string(what) + ": " + ppg_last_error(ctx));
 }
 
 // Replaces class PPGExtractor (feature/include/PPGExtractor.h:34-148).  Same constructor arguments, same run()
@@ -71,7 +76,18 @@ public:
         const uint8_t* ptr = srcMat.data;
         const int stride = (int)srcMat.step;
         ppg_frame_out o;
-        check(ppg_extract(mCtx, &ptr, &stride, 1, &o), mCtx, "ppg_extract");
+        const int rc = ppg_extract(mCtx, &ptr, &stride, 1, &o);
+        if (rc != PPG_ERR_CAPACITY) check(rc, mCtx, "ppg_extract");
+        // The reference has no capacities.  When one of the library's was exceeded (o.status: PPG_STATUS_* bits --
+        // accepted candidates, candidate pairs, per-keypoint degree, max_edges, max_colines) the record is a truncated
+        // graph: it is still handed out (a subset of the reference's edges), the status is kept for the caller to
+        // inspect, and the first occurrence is reported.  Raise the ppg_config capacities if it ever shows up.
+        mLastStatus = o.status;
+        if (o.status && !mWarned) {
+            std::fprintf(stderr, "ppg_shim::PPGExtractor::run: frame capacity exceeded (status 0x%x): %s\n", o.status,
+                         ppg_last_error(mCtx));
+            mWarned = true;
+        }
         mvKeyPoints.clear();
         mvKeyPoints.reserve(o.n_kp);
         for (int i = 0; i < o.n_kp; i++) {
@@ -103,6 +119,7 @@ public:
     const std::vector<KeyPointEx>& getKeyPoints() const { return mvKeyPoints; }
     const std::vector<KeyEdge>& getKeyEdges() const { return mvKeyEdges; }
     ppg_ctx* context() { return mCtx; }
+    unsigned lastStatus() const { return mLastStatus; }  // ppg_frame_out.status of the last run(): 0 = nothing truncated
 
 public:
     std::vector<KeyPointEx> mvKeyPoints;
@@ -122,6 +139,8 @@ public:
 private:
     ppg_ctx* mCtx = nullptr;
     std::string mWeights;
+    unsigned mLastStatus = 0;
+    bool mWarned = false;
 };
 
 // The data-parallel part of Matcher::ExtendMapMatches (Matcher.cpp:224-281): best / second-best keypoint of
@@ -354,10 +373,12 @@ inline int search_by_bow(ppg_ctx* ctx, KeyFrameLike* pKF, Frame& F, std::vector<
 //   table rows = the trackable map points (:210-215) in vpMapPoints order, then every map point reachable as
 //   theOtherPt() of one of their edges (its descriptor is read at :330), then the map points the frame already holds
 //   (needed for the pMP_o == F.mvpMapPoints[keyID_o] test at :327).
-// Drop-in body:  int Matcher::ExtendMapMatches(Frame& F, const vector<MapPoint*>& v, const float th)
-//                { return ppg_shim::extend_map_matches(ctx, F, v, th, mfNNratio); }
-inline int extend_map_matches(ppg_ctx* ctx, Frame& F, const std::vector<MapPoint*>& vpMapPoints, float th,
-                              float nnratio) {
+// `cpu_fallback` (optional) is the reference's own loop: it runs instead when the frame exceeds a device capacity (a map
+// point / keypoint with more than PPG_EXTEND_MAX_DEGREE edges, a seed needing more than PPG_EXTEND_MAX_WEIGHTS
+// weights) -- nothing has been written into F at that point; without it such a frame throws.
+// ppg_shim::Matcher::ExtendMapMatches below passes ::Matcher::ExtendMapMatches.
+inline int extend_map_matches(ppg_ctx* ctx, Frame& F, const std::vector<MapPoint*>& vpMapPoints, float th, float nnratio,
+                              const std::function<int()>& cpu_fallback = nullptr) {
     std::vector<MapPoint*> rows;
     std::unordered_map<MapPoint*, int32_t> row_of;
     std::vector<uint8_t> candidate;
@@ -373,6 +394,7 @@ inline int extend_map_matches(ppg_ctx* ctx, Frame& F, const std::vector<MapPoint
     for (MapPoint* pMP : vpMapPoints)
         if (!(pMP->isBad() || !pMP->mbTrackInView)) add_row(pMP, true);  // :210-215
     const size_t n_cand = rows.size();
+    if (n_cand == 0) return 0;  // no trackable map point: the reference's loop body never runs (Matcher.cpp:226)
     std::vector<std::vector<MapEdge*>> edges(n_cand);
     for (size_t r = 0; r < n_cand; r++) {
         edges[r] = rows[r]->getEdges();
@@ -445,8 +467,9 @@ inline int extend_map_matches(ppg_ctx* ctx, Frame& F, const std::vector<MapPoint
     out.kp_mp = out_kp.data();
     out.kedge_me = out_ke.data();
     out.tracked = out_tr.data();
-    int rc = ppg_extend_map_matches(ctx, &in, &out);
-    if (rc != PPG_OK) throw std::runtime_error(std::string("ppg_extend_map_matches: ") + ppg_last_error(ctx));
+    const int rc = ppg_extend_map_matches(ctx, &in, &out);
+    if (rc == PPG_ERR_CAPACITY && cpu_fallback) return cpu_fallback();  // F untouched so far
+    check(rc, ctx, "ppg_extend_map_matches");
     for (int i = 0; i < N; i++)
         if (out_kp[i] != kp_mp[i]) F.mvpMapPoints[i] = rows[out_kp[i]];          // :279, :366
     for (int e = 0; e < E; e++)
@@ -455,5 +478,80 @@ inline int extend_map_matches(ppg_ctx* ctx, Frame& F, const std::vector<MapPoint
         if (out_tr[r] && !tracked[r]) rows[r]->mnTrackedbyFrame = F.mnId;        // :280, :368
     return out.nmatches;
 }
+
+// Matcher::SearchForInitialization (matching/src/Matcher.cpp:582-651) whole on the GPU (ppg_search_for_initialization).
+inline int search_for_initialization(ppg_ctx* ctx, Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched,
+                                     std::vector<int>& vnMatches12, int windowSize, float nnratio) {
+    const int n1 = (int)F1.mvKeysUn.size(), n2 = (int)F2.mvKeysUn.size();
+    vnMatches12 = std::vector<int>(n1, -1);  // :585
+    if (n1 == 0 || n2 == 0) return 0;
+    check(ppg_upload_map(ctx, F1.mDescriptors.ptr<float>(0), n1), ctx, "ppg_upload_map");
+    std::vector<float> prev(2 * (size_t)n1), kx(n2), ky(n2);
+    for (int i = 0; i < n1; i++) {
+        prev[2 * i] = vbPrevMatched[i].x;
+        prev[2 * i + 1] = vbPrevMatched[i].y;
+    }
+    for (int i = 0; i < n2; i++) {
+        kx[i] = F2.mvKeysUn[i].mPos[0];
+        ky[i] = F2.mvKeysUn[i].mPos[1];
+    }
+    std::vector<int32_t> m12(n1, -1);
+    ppg_init_match_in in{};
+    in.n1 = n1;
+    in.prev_matched = prev.data();
+    in.n2 = n2;
+    in.kp2_x = kx.data();
+    in.kp2_y = ky.data();
+    in.desc2 = F2.mDescriptors.ptr<float>(0);
+    in.window = windowSize;
+    in.ratio = nnratio;
+    ppg_init_match_out out{};
+    out.matches12 = m12.data();
+    out.prev_matched = prev.data();
+    check(ppg_search_for_initialization(ctx, &in, &out), ctx, "ppg_search_for_initialization");
+    for (int i = 0; i < n1; i++) {
+        vnMatches12[i] = m12[i];
+        if (m12[i] >= 0) vbPrevMatched[i] = cv::Point2f(prev[2 * i], prev[2 * i + 1]);  // :644-647
+    }
+    return out.nmatches;
+}
+
+#ifndef PPG_SHIM_NO_MATCHER_CLASS
+// Replaces class Matcher (matching/include/Matcher.h:20-64) for its callers: the same twelve signatures, constants and
+// public members.  The three matchers on the front-end path run on the GPU --
+//   ExtendMapMatches          image <-> map association of MSTracking::SearchLocalPoints (system/src/Tracking.cpp:1007)
+//   SearchByBoW(KF, F)        relocalisation / reference-keyframe tracking
+//   SearchForInitialization   monocular initialisation (Tracking.cpp:525)
+// -- and the other nine (SearchByProjection x 4, SearchByBoW(KF, KF), SearchForTriangulation, SearchBySim3, Fuse x 2)
+// are the reference's own host code, inherited unchanged from ::Matcher (their window-search cores are available as
+// search_window above for callers that want them on the device; SearchForTriangulation's acceptance is the camera
+// model's virtual epipolarConstrain -- for KannalaBrandt8 a triangulation -- and stays on the host).
+// The ctx is the one the frame's PPGExtractor owns (PPGExtractor::context()).
+class Matcher : public ::Matcher {
+public:
+    Matcher(ppg_ctx* ctx, GeometricCamera* pCam, float nnratio = 0.6) : ::Matcher(pCam, nnratio), mCtx(ctx) {}
+
+    int ExtendMapMatches(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th) {
+        return extend_map_matches(mCtx, F, vpMapPoints, th, mfNNratio,
+                                  [&]() { return ::Matcher::ExtendMapMatches(F, vpMapPoints, th); });
+    }
+    int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches) {
+        return search_by_bow(mCtx, pKF, F, vpMapPointMatches, mfNNratio, TH_LOW);
+    }
+    int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched,
+                                std::vector<int>& vnMatches12, int windowSize = 10) {
+        return search_for_initialization(mCtx, F1, F2, vbPrevMatched, vnMatches12, windowSize, mfNNratio);
+    }
+    // host-side matchers of the reference, unchanged
+    using ::Matcher::Fuse;
+    using ::Matcher::SearchByBoW;  // (KeyFrame*, KeyFrame*, ...); the (KeyFrame*, Frame&, ...) overload above hides the base's
+    using ::Matcher::SearchByProjection;
+    using ::Matcher::SearchBySim3;
+    using ::Matcher::SearchForTriangulation;
+
+private:
+    ppg_ctx* mCtx;
+};
+#endif
 
 }  // namespace ppg_shim

@@ -332,3 +332,19 @@ def search_by_bow(frame_desc, kp_node, row_desc, row_node, ratio, max_dist, stri
                                   _p(row_desc, C.c_float), _p(row_node, C.c_int), C.c_float(ratio),
                                   C.c_float(max_dist), int(strict), _p(kr, C.c_int))
     return dict(kp_row=kr[:len(kp_node)].copy(), nmatches=int(nm))
+
+
+def search_for_initialization(cam, desc1, prev_matched, kx2, ky2, desc2, window=50, ratio=0.9, th_low=0.7):
+    """Matcher::SearchForInitialization (Matcher.cpp:582-651).  -> dict(nmatches, matches12, prev_matched)."""
+    L = lib()
+    cfg = make_cfg(cam)
+    d1, d2 = f32(desc1), f32(desc2)
+    prev = f32(prev_matched).copy()
+    kx2, ky2 = f32(kx2), f32(ky2)
+    n1 = len(d1)
+    m12 = np.full(max(n1, 1), -1, np.int32)
+    L.ppgo_search_for_initialization.restype = C.c_int
+    nm = L.ppgo_search_for_initialization(C.byref(cfg), n1, _p(d1, C.c_float), _p(prev, C.c_float), len(kx2),
+                                          _p(kx2, C.c_float), _p(ky2, C.c_float), _p(d2, C.c_float), int(window),
+                                          C.c_float(ratio), C.c_float(th_low), _p(m12, C.c_int))
+    return dict(nmatches=int(nm), matches12=m12[:n1], prev_matched=prev)

@@ -1244,3 +1244,74 @@ int ppgo_search_by_bow(int n, const float *frame_desc, const int *kp_node, int m
     }
     return nmatches;
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* Matcher::SearchForInitialization, matching/src/Matcher.cpp:582-651 (called from               */
+/* system/src/Tracking.cpp:525 with windowSize = 50).  For every feature i1 of F1 in index order:   */
+/* window of radius windowSize around vbPrevMatched[i1] in F2 (Frame::GetFeaturesInArea), best /     */
+/* second best DescriptorDistance over the window features that are not yet matched, accept iff       */
+/* best <= TH_LOW && best < ratio * second.                                                           */
+/* Quirk kept: vMatchedDistance is a vector<int> -- the stored distance of a matched F2 feature        */
+/* truncates to 0 (every accepted distance is <= TH_LOW < 1), so `vMatchedDistance[i2] <= dist` (:613)  */
+/* is true for every later candidate: a matched F2 feature is never offered again, and the             */
+/* "steal the match back" branch (:634-638) is unreachable.  INT_MAX <= dist (unmatched) is false.      */
+/* matches12[i1] = index in F2 or -1; prev (n1 x 2, in/out) gets the matched feature's position (:646). */
+/* -> nmatches.                                                                                          */
+/* ------------------------------------------------------------------------------------------- */
+int ppgo_search_for_initialization(const ppgo_cfg *c, int n1, const float *desc1, float *prev, int n2,
+                                   const float *kx2, const float *ky2, const float *desc2, int window, float ratio,
+                                   float th_low, int *matches12) {
+    ppgo_bounds b;
+    ppgo_image_bounds(c, &b);
+    int *goff = malloc(sizeof(int) * (64 * 48 + 1)), *gidx = malloc(sizeof(int) * (n2 > 0 ? n2 : 1));
+    ppgo_grid_build(&b, n2, kx2, ky2, goff, gidx);
+    int *win = malloc(sizeof(int) * (n2 > 0 ? n2 : 1));
+    int *matched_dist = malloc(sizeof(int) * (n2 > 0 ? n2 : 1)); /* vMatchedDistance: vector<int> */
+    int *matches21 = malloc(sizeof(int) * (n2 > 0 ? n2 : 1));
+    for (int i = 0; i < n2; i++) {
+        matched_dist[i] = 2147483647;
+        matches21[i] = -1;
+    }
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    int nmatches = 0;
+    for (int i1 = 0; i1 < n1; i1++) {
+        const int nw = ppgo_features_in_area(&b, goff, gidx, kx2, ky2, prev[2 * i1], prev[2 * i1 + 1], (float)window, win);
+        if (nw == 0) continue;
+        float bestDist = 1e6f, bestDist2 = 1e6f;
+        int bestIdx2 = -1;
+        for (int k = 0; k < nw; k++) {
+            const int i2 = win[k];
+            const float dist = ppgo_descriptor_distance(desc1 + (size_t)i1 * 256, desc2 + (size_t)i2 * 256, 256);
+            if ((float)matched_dist[i2] <= dist) continue; /* :613, int -> float */
+            if (dist < bestDist) {
+                bestDist2 = bestDist;
+                bestDist = dist;
+                bestIdx2 = i2;
+            } else if (dist < bestDist2)
+                bestDist2 = dist;
+        }
+        if (bestDist <= th_low) {
+            if (bestDist < bestDist2 * ratio) {
+                if (matches21[bestIdx2] >= 0) { /* unreachable, see header */
+                    matches12[matches21[bestIdx2]] = -1;
+                    nmatches--;
+                }
+                matches12[i1] = bestIdx2;
+                matches21[bestIdx2] = i1;
+                matched_dist[bestIdx2] = (int)bestDist;
+                nmatches++;
+            }
+        }
+    }
+    for (int i1 = 0; i1 < n1; i1++)
+        if (matches12[i1] >= 0) {
+            prev[2 * i1] = kx2[matches12[i1]];
+            prev[2 * i1 + 1] = ky2[matches12[i1]];
+        }
+    free(goff);
+    free(gidx);
+    free(win);
+    free(matched_dist);
+    free(matches21);
+    return nmatches;
+}

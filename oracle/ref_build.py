@@ -61,13 +61,22 @@ def build(force=False, verbose=False):
         subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-c",
                                os.path.join(HERE, "ppg_oracle.c"), "-o", oracle_o])
     built = {}
-    for name in ("extractor", "matcher"):
+    repo = os.path.dirname(HERE)
+    product = os.path.join(repo, "ppg_slam_b200", "libppg_b200.so")
+    for name in ("extractor", "matcher", "shim"):
         tu = os.path.join(HERE, "ref_tu", name + "_tu.cpp")
         if not os.path.exists(tu):
             continue
+        extra, extra_deps = [], []
+        if name == "shim":  # include/ppg_shim.hpp executed on the reference's objects: links the product library
+            if not os.path.exists(product):
+                continue
+            extra = ["-I" + os.path.join(repo, "include"), "-L" + os.path.dirname(product), "-lppg_b200",
+                     "-Wl,-rpath," + os.path.dirname(product)]
+            extra_deps = [os.path.join(repo, "include", "ppg_shim.hpp"), os.path.join(repo, "include", "ppg_b200.h")]
         out = lib_path(name)
-        if force or _stale(out, [tu, oracle_o] + deps):
-            cmd = ["g++"] + common + ["-shared", tu, oracle_o, "-o", out, "-Wl,--gc-sections", "-lm"] + lib
+        if force or _stale(out, [tu, oracle_o] + deps + extra_deps):
+            cmd = ["g++"] + common + ["-shared", tu, oracle_o, "-o", out, "-Wl,--gc-sections", "-lm"] + lib + extra
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError("reference harness %s failed to build:\n%s" % (name, r.stderr[-6000:]))

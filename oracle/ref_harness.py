@@ -213,3 +213,78 @@ def walk_order_permutation(candidate, bad, edge_off):
     order = candidate_order(candidate, bad, edge_off)
     rest = np.setdiff1d(np.arange(len(candidate)), order)
     return np.concatenate([order, rest]).astype(np.int64)
+
+
+def search_for_initialization(cam, kx1, ky1, desc1, prev_matched, kx2, ky2, desc2, window=50, ratio=0.9):
+    """The reference's own Matcher::SearchForInitialization on two Frames rebuilt from the flat arrays."""
+    lib = _lib("matcher")
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    kx1, ky1, d1, kx2, ky2, d2 = f32(kx1), f32(ky1), f32(desc1), f32(kx2), f32(ky2), f32(desc2)
+    prev = f32(prev_matched).copy()
+    n1 = len(kx1)
+    m12 = np.full(max(n1, 1), -1, np.int32)
+    nm = lib.ref_search_for_initialization(_p(_cam_params(cam)), cam.width, cam.height, int(cam.fisheye), n1, _p(kx1),
+                                           _p(ky1), _p(d1), _p(prev), len(kx2), _p(kx2), _p(ky2), _p(d2), int(window),
+                                           C.c_float(ratio), _p(m12, C.c_int))
+    return dict(nmatches=int(nm), matches12=m12[:n1], prev_matched=prev)
+
+
+# ---------------------------------------------------------------- include/ppg_shim.hpp executed on the reference's objects
+def shim_available():
+    return os.path.exists(ref_build.lib_path("shim")) and os.path.exists(ref_build.lib_path("matcher"))
+
+
+def _weights_dir():
+    return os.path.join(os.path.dirname(ref_build.HERE), "ppg_slam_b200", "weights")
+
+
+def shim_extend_both(cam, map_desc, candidate, observed, bad, edge_off, edge_other, edge_ok, proj_uv, view_cos, tracked,
+                     kp_x, kp_y, frame_desc, kp_mp, edge_start, edge_end, conn_off, conn_idx, th, ratio):
+    """The same pointer graph through the reference's Matcher::ExtendMapMatches (host) and through
+    ppg_shim::Matcher::ExtendMapMatches (flattening -> C ABI -> GPU -> write-back).  -> (reference result, shim result)."""
+    lib = _lib("shim")
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    md, cd, ob, bd = f32(map_desc), u8(candidate), u8(observed), u8(bad)
+    eo, et, ek = i32(edge_off), i32(edge_other), u8(edge_ok)
+    uv, vc, tr = f32(proj_uv), f32(view_cos), u8(tracked)
+    kx, ky, fd, km = f32(kp_x), f32(kp_y), f32(frame_desc), i32(kp_mp)
+    es, ee, co, ci = i32(edge_start), i32(edge_end), i32(conn_off), i32(conn_idx)
+    P, n, ne = len(cd), len(kx), len(es)
+    if len(et) == 0:
+        et, ek = np.zeros(1, np.int32), np.zeros(1, np.uint8)
+    if len(ci) == 0:
+        ci = np.zeros(1, np.int32)
+    if ne == 0:
+        es, ee = np.zeros(1, np.int32), np.zeros(1, np.int32)
+    order = walk_order_permutation(cd, bd, eo).astype(np.int32)
+    nm = np.zeros(2, np.int32)
+    kp2 = np.zeros((2, max(n, 1)), np.int32)
+    me2 = np.zeros((2, max(ne, 1)), np.int32)
+    tr2 = np.zeros((2, max(P, 1)), np.uint8)
+    u8p, i32p = C.c_uint8, C.c_int
+    rc = lib.shim_extend_both(_p(_cam_params(cam)), cam.width, cam.height, int(cam.fisheye), _weights_dir().encode(), P,
+                              _p(md), _p(cd, u8p), _p(ob, u8p), _p(bd, u8p), _p(eo, i32p), _p(et, i32p), _p(ek, u8p),
+                              _p(uv), _p(vc), _p(tr, u8p), n, _p(kx), _p(ky), _p(fd), _p(km, i32p), ne, _p(es, i32p),
+                              _p(ee, i32p), _p(co, i32p), _p(ci, i32p), _p(order, i32p), len(order), C.c_float(th),
+                              C.c_float(ratio), _p(nm, i32p), _p(kp2, i32p), _p(me2, i32p), _p(tr2, u8p))
+    if rc != 0:
+        raise RuntimeError("shim_extend_both failed (see stderr)")
+    return tuple(dict(nmatches=int(nm[k]), kp_mp=kp2[k, :n], kedge_me=me2[k, :ne], tracked=tr2[k, :P]) for k in (0, 1))
+
+
+def shim_init_both(cam, kx1, ky1, desc1, prev_matched, kx2, ky2, desc2, window, ratio):
+    lib = _lib("shim")
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    kx1, ky1, d1, kx2, ky2, d2, prev = f32(kx1), f32(ky1), f32(desc1), f32(kx2), f32(ky2), f32(desc2), f32(prev_matched)
+    n1 = len(kx1)
+    nm = np.zeros(2, np.int32)
+    m12 = np.zeros((2, max(n1, 1)), np.int32)
+    pv = np.zeros((2, max(n1, 1), 2), np.float32)
+    rc = lib.shim_init_both(_p(_cam_params(cam)), cam.width, cam.height, int(cam.fisheye), _weights_dir().encode(), n1,
+                            _p(kx1), _p(ky1), _p(d1), _p(prev), len(kx2), _p(kx2), _p(ky2), _p(d2), int(window),
+                            C.c_float(ratio), _p(nm, C.c_int), _p(m12, C.c_int), _p(pv))
+    if rc != 0:
+        raise RuntimeError("shim_init_both failed (see stderr)")
+    return tuple(dict(nmatches=int(nm[k]), matches12=m12[k, :n1], prev_matched=pv[k, :n1]) for k in (0, 1))

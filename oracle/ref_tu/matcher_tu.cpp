@@ -201,6 +201,39 @@ REF_API int ref_candidate_order(int P, const unsigned char* candidate, const uns
     return (int)c.size();
 }
 
+// The real Matcher::SearchForInitialization (Matcher.cpp:582-651) on two Frames rebuilt from flat arrays.
+// prev (n1 x 2) is vbPrevMatched, in and out; matches12 (n1) out.  Returns nmatches.
+REF_API int ref_search_for_initialization(const float* params8, int width, int height, int fisheye, int n1,
+                                          const float* kx1, const float* ky1, const float* desc1, float* prev, int n2,
+                                          const float* kx2, const float* ky2, const float* desc2, int window, float ratio,
+                                          int* matches12) {
+    HarnessCamera cam(std::vector<float>(params8, params8 + 8), width, height, fisheye != 0);
+    auto fill = [&](Frame& F, int n, const float* kx, const float* ky, const float* d) {
+        F.N = n;
+        F.mpCamera = &cam;
+        F.mvKeysUn.resize(n);
+        for (int i = 0; i < n; i++) F.mvKeysUn[i] = KeyPointEx(kx[i], ky[i], 1.f);
+        F.mvKeys = F.mvKeysUn;
+        F.mDescriptors = cv::Mat(std::max(n, 1), 256, CV_32F);
+        if (n > 0) memcpy(F.mDescriptors.data, d, (size_t)n * 1024);
+        F.AssignFeaturesToGrid();
+    };
+    Frame F1, F2;
+    fill(F1, n1, kx1, ky1, desc1);
+    fill(F2, n2, kx2, ky2, desc2);
+    std::vector<cv::Point2f> vprev(n1);
+    for (int i = 0; i < n1; i++) vprev[i] = cv::Point2f(prev[2 * i], prev[2 * i + 1]);
+    std::vector<int> m12;
+    Matcher matcher(&cam, ratio);
+    const int nm = matcher.SearchForInitialization(F1, F2, vprev, m12, window);
+    for (int i = 0; i < n1; i++) {
+        matches12[i] = m12[i];
+        prev[2 * i] = vprev[i].x;
+        prev[2 * i + 1] = vprev[i].y;
+    }
+    return nm;
+}
+
 // Frame::GetFeaturesInArea alone (the window query every matcher uses): indices in the reference's visiting order.
 REF_API int ref_features_in_area(const float* params8, int width, int height, int fisheye, int n, const float* kx,
                                  const float* ky, float x, float y, float r, int* out) {

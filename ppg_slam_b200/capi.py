@@ -108,6 +108,17 @@ class BowMatchOut(C.Structure):
 
 
 # every symbol include/ppg_b200.h declares (tests/test_abi.py checks the header against this list)
+class InitMatchIn(C.Structure):
+    _fields_ = [("n1", C.c_int), ("prev_matched", C.POINTER(C.c_float)), ("n2", C.c_int),
+                ("kp2_x", C.POINTER(C.c_float)), ("kp2_y", C.POINTER(C.c_float)), ("desc2", C.POINTER(C.c_float)),
+                ("window", C.c_int), ("ratio", C.c_float)]
+
+
+class InitMatchOut(C.Structure):
+    _fields_ = [("matches12", C.POINTER(C.c_int32)), ("prev_matched", C.POINTER(C.c_float)), ("nmatches", C.c_int),
+                ("n_rescans", C.c_int)]
+
+
 SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", "ppg_api_version", "ppg_extract",
            "ppg_upload_frames", "ppg_run", "ppg_download", "ppg_sync", "ppg_extract_from_maps", "ppg_get_maps",
            "ppg_selftest_conv", "ppg_set_profiling", "ppg_get_stage_times", "ppg_launch_count", "ppg_timer_start",
@@ -122,7 +133,8 @@ SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", 
            "ppg_extract_wait", "ppg_host_alloc", "ppg_host_free", "ppg_host_register", "ppg_host_unregister",
            "ppg_assoc_stage_batch_async", "ppg_extend_fetch_batch_async", "ppg_extend_collect",
            "ppg_comm_unique_id", "ppg_comm_init", "ppg_comm_destroy", "ppg_assoc_allgather",
-           "ppg_assoc_allgather_fetch", "ppg_record_bytes"]
+           "ppg_assoc_allgather_fetch", "ppg_record_bytes",
+           "ppg_search_for_initialization"]
 
 _lib = None
 
@@ -158,7 +170,7 @@ def load():
                      "ppg_load_vocabulary", "ppg_extract_async", "ppg_extract_wait", "ppg_host_register",
                      "ppg_host_unregister", "ppg_assoc_stage_batch_async", "ppg_extend_fetch_batch_async",
                      "ppg_extend_collect", "ppg_comm_unique_id", "ppg_comm_init", "ppg_comm_destroy",
-                     "ppg_assoc_allgather", "ppg_assoc_allgather_fetch"]:
+                     "ppg_assoc_allgather", "ppg_assoc_allgather_fetch", "ppg_search_for_initialization"]:
             getattr(lib, name).restype = C.c_int
         lib.ppg_record_bytes.restype = C.c_longlong
         lib.ppg_record_bytes.argtypes = [C.c_void_p]
@@ -696,6 +708,23 @@ class Extractor:
         o.kp_row = kr.ctypes.data_as(C.POINTER(C.c_int32))
         self._check(self.lib.ppg_search_by_bow(self.h, C.byref(a), C.byref(o)))
         return dict(kp_row=kr[:len(kn)].copy(), nmatches=o.nmatches, n_rescans=o.n_rescans)
+
+    def search_for_initialization(self, desc1, prev_matched, kx2, ky2, desc2, window=50, ratio=0.9):
+        """Matcher::SearchForInitialization (Matcher.cpp:582-651); F1's descriptors are uploaded as the table here.
+        -> dict(nmatches, matches12, prev_matched, n_rescans)"""
+        d1 = np.ascontiguousarray(desc1, np.float32)
+        self.upload_map(d1)
+        pm = np.ascontiguousarray(prev_matched, np.float32).copy()
+        kx, ky, d2 = (np.ascontiguousarray(a, np.float32) for a in (kx2, ky2, desc2))
+        a = InitMatchIn()
+        a.n1, a.n2, a.window, a.ratio = len(d1), len(kx), int(window), ratio
+        a.prev_matched, a.kp2_x, a.kp2_y, a.desc2 = _fp(pm), _fp(kx), _fp(ky), _fp(d2)
+        m12 = np.full(max(len(d1), 1), -1, np.int32)
+        o = InitMatchOut()
+        o.matches12 = m12.ctypes.data_as(C.POINTER(C.c_int32))
+        o.prev_matched = _fp(pm)
+        self._check(self.lib.ppg_search_for_initialization(self.h, C.byref(a), C.byref(o)))
+        return dict(nmatches=o.nmatches, matches12=m12[:len(d1)], prev_matched=pm, n_rescans=o.n_rescans)
 
     def distinctive_descriptors(self, desc, offsets, to_table=False):
         """MapPoint::ComputeDistinctiveDescriptors for a batch of map points (packed observation descriptors +

@@ -269,6 +269,9 @@ struct WalkParams {
     float max_dist;
     const int* row_node;
     const int* kp_node;
+    // and_rule (Matcher::SearchForInitialization, Matcher.cpp:582-651): spatial windows like ExtendMapMatches, but the
+    // accept rule of the node mode (best <= max_dist && best < ratio * second) and every matched feature is taken
+    int and_rule;
 };
 
 struct WalkShared {
@@ -472,7 +475,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                     const uint32_t rest = fm & (fm - 1);
                     const float b1 = ld[k1], b2 = rest ? ld[__ffs(rest) - 1] : 1e6f;
                     bidx = (int)((lim[k1 >> 1] >> ((k1 & 1) * 16)) & 0xffffu);
-                    if (p.node_mode)
+                    if (p.node_mode || p.and_rule)
                         act = ((p.strict ? b1 < p.max_dist : b1 <= p.max_dist) && b1 < p.ratio * b2) ? 1 : 0;  // :456-458
                     else
                         act = !(b1 > p.th_high && b1 > p.ratio * b2) ? 1 : 0;  // :276
@@ -574,7 +577,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                     for (int w = 0; w < X_WARPS; w++)
                         for (int k = 0; k < 2; k++)
                             if (S.t2i[w][k] >= 0) top2_update(S.t2d[w][k], S.t2o[w][k], S.t2i[w][k], b1, o1, i1, b2, o2, i2);
-                    const bool acc = i1 >= 0 && (p.node_mode ? ((p.strict ? b1 < p.max_dist : b1 <= p.max_dist) &&
+                    const bool acc = i1 >= 0 && ((p.node_mode || p.and_rule) ? ((p.strict ? b1 < p.max_dist : b1 <= p.max_dist) &&
                                                                 b1 < p.ratio * b2)
                                                              : !(b1 > p.th_high && b1 > p.ratio * b2));
                     S.ev[1] = acc ? 1 : 0;
@@ -951,6 +954,7 @@ int run_extend(ppg_ctx* c, const FrameSrc& src, const FrameGraphSrc& gsrc, int f
     wp.strict = 0;
     wp.max_dist = 0.f;
     wp.row_node = wp.kp_node = nullptr;
+    wp.and_rule = 0;
     extend_walk_kernel<<<frames, X_THREADS, walk_smem(x->P, s->ncap, x->ecap), c->st>>>(wp);
     c->launches++;
     stage_mark(c, "extend.walk");
@@ -1292,6 +1296,113 @@ int ppg_search_by_bow(ppg_ctx* c, const ppg_bow_match_in* in, ppg_bow_match_out*
     out->nmatches = x->h_result[XR_ACCEPTED];
     out->n_rescans = x->h_result[XR_RESCANS];
     if (out->kp_row && N > 0) memcpy(out->kp_row, x->h_kp_mp, (size_t)N * 4);
+    return PPG_OK;
+}
+
+// Matcher::SearchForInitialization whole (Matcher.cpp:582-651) through the same two kernels: the rows are the features
+// of F1 in index order (their descriptors are the resident table: ppg_upload_map), the window of a row is the radius-
+// windowSize box around vbPrevMatched[i1] in F2 (prep_rows_kernel, PPG_SEARCH_WINDOW), the walk keeps vnMatches21 live
+// (a matched F2 feature is never offered again: the vector<int> quirk, see the oracle) and accepts with
+// best <= TH_LOW && best < ratio * second.
+int ppg_search_for_initialization(ppg_ctx* c, const ppg_init_match_in* in, ppg_init_match_out* out) {
+    if (!c || !in || !out || !in->prev_matched) return set_err(c, PPG_ERR_ARG, "ppg_search_for_initialization: null argument");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    int rc = ensure_extend(c);
+    if (rc != PPG_OK) return rc;
+    AssocState* s = c->assoc;
+    ExtendState* x = s->ext;
+    const int M = in->n1, N = in->n2;
+    if (M < 1 || M > s->n_rows) return set_err(c, PPG_ERR_ARG, "ppg_search_for_initialization: upload the n1 descriptors of F1 first (ppg_upload_map)");
+    if (N < 0 || N > s->ncap || (N > 0 && (!in->kp2_x || !in->kp2_y || !in->desc2)))
+        return set_err(c, PPG_ERR_ARG, "ppg_search_for_initialization: bad F2 arrays");
+    if (in->window < 0) return set_err(c, PPG_ERR_ARG, "ppg_search_for_initialization: negative window");
+    std::vector<float> zeros((size_t)M, 0.f);
+    if ((rc = assoc_stage_rows(c, 1, M, in->prev_matched, zeros.data(), (float)in->window, in->ratio)) != PPG_OK) return rc;
+    s->mode = PPG_SEARCH_WINDOW;  // r = th for every row (GetFeaturesInArea(x, y, windowSize), :596)
+    if (N > 0) {
+        PPG_CUDA(c, cudaMemcpyAsync(s->kx, in->kp2_x, (size_t)N * 4, cudaMemcpyHostToDevice, c->st));
+        PPG_CUDA(c, cudaMemcpyAsync(s->ky, in->kp2_y, (size_t)N * 4, cudaMemcpyHostToDevice, c->st));
+        PPG_CUDA(c, cudaMemcpyAsync(s->fdesc, in->desc2, (size_t)N * 1024, cudaMemcpyHostToDevice, c->st));
+    }
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));  // pageable sources
+    s->staged_n = N;
+    FrameSrc src = assoc_staged_src(s);
+    src.free_mask = s->ones;
+    if ((rc = assoc_prep(c, src, 1)) != PPG_OK) return rc;
+    ListParams lp{};
+    lp.nc = M;
+    lp.max_rows = s->max_rows;
+    lp.ncap = s->ncap;
+    lp.src = src;
+    lp.order = x->ident;
+    lp.rowp = s->rowp;
+    lp.map_f32 = s->map_f32;
+    lp.kinfo = s->kinfo;
+    lp.korder = s->korder;
+    lp.l_idx = x->l_idx;
+    lp.l_d = x->l_d;
+    lp.l_cnt = x->l_cnt;
+    lp.node_mode = 0;
+    extend_lists_kernel<<<dim3((M + XL_ROWS - 1) / XL_ROWS, 1), 256, 0, c->st>>>(lp);
+    stage_mark(c, "init_match.lists");
+    WalkParams wp{};
+    wp.nc = M;
+    wp.P = M;
+    wp.max_rows = s->max_rows;
+    wp.ncap = s->ncap;
+    wp.ecap = x->ecap;
+    wp.src = src;
+    FrameGraphSrc g{};
+    g.coff = reinterpret_cast<const uint8_t*>(x->zero_i);  // no key edges
+    g.es = g.ee = g.cidx = g.coff;
+    g.ne_val = 0;
+    wp.gsrc = g;
+    wp.order = x->ident;
+    wp.rowp = s->rowp;
+    wp.map_f32 = s->map_f32;
+    wp.kinfo = s->kinfo;
+    wp.korder = s->korder;
+    wp.l_idx = x->l_idx;
+    wp.l_d = x->l_d;
+    wp.l_cnt = x->l_cnt;
+    wp.observed = x->ones_u8;  // every match takes its feature
+    wp.bad = reinterpret_cast<const uint8_t*>(x->zero_i);
+    wp.edge_ok = reinterpret_cast<const uint8_t*>(x->zero_i);
+    wp.edge_off = x->zero_i;
+    wp.edge_other = x->zero_i;
+    wp.tracked = x->tracked;
+    wp.kp_mp = x->kp_mp;
+    wp.kedge_me = x->kedge_me;
+    wp.result = x->result;
+    wp.ratio = in->ratio;
+    wp.th_high = c->cfg.th_high;
+    wp.has_state = 0;
+    wp.node_mode = 0;
+    wp.and_rule = 1;
+    wp.strict = 0;
+    wp.max_dist = c->cfg.th_low;
+    extend_walk_kernel<<<1, X_THREADS, walk_smem(M, s->ncap, x->ecap), c->st>>>(wp);
+    stage_mark(c, "init_match.walk");
+    c->launches += 2;
+    PPG_CUDA(c, cudaGetLastError());
+    PPG_CUDA(c, cudaMemcpyAsync(x->h_result, x->result, XR_WORDS * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(x->h_kp_mp, x->kp_mp, (size_t)s->ncap * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    out->nmatches = x->h_result[XR_ACCEPTED];
+    out->n_rescans = x->h_result[XR_RESCANS];
+    if (out->matches12) {
+        for (int i = 0; i < M; i++) out->matches12[i] = -1;
+        for (int j = 0; j < N; j++)
+            if (x->h_kp_mp[j] >= 0 && x->h_kp_mp[j] < M) out->matches12[x->h_kp_mp[j]] = j;  // vnMatches21 -> vnMatches12
+    }
+    if (out->prev_matched) {  // :644-647
+        if (out->prev_matched != in->prev_matched) memcpy(out->prev_matched, in->prev_matched, (size_t)M * 8);
+        for (int j = 0; j < N; j++)
+            if (x->h_kp_mp[j] >= 0 && x->h_kp_mp[j] < M) {
+                out->prev_matched[2 * x->h_kp_mp[j]] = in->kp2_x[j];
+                out->prev_matched[2 * x->h_kp_mp[j] + 1] = in->kp2_y[j];
+            }
+    }
     return PPG_OK;
 }
 

@@ -26,6 +26,28 @@ CASES = [("EuRoC", 1, 40, 70, 120, 10.0, 0.8, False, False), ("EuRoC", 2, 44, 11
          ("EuRoC", 5, 12, 0, 30, 10.0, 0.8, False, False), ("EuRoC", 6, 45, 120, 64, 10.0, 0.8, False, True)]
 
 
+def init_pair(seed, cam, n1, n2, noise, jitter):
+    rs = np.random.RandomState(seed)
+    kx1 = rs.uniform(5, cam.width - 5, n1).astype(np.float32)
+    ky1 = rs.uniform(5, cam.height - 5, n1).astype(np.float32)
+    d1 = rs.normal(size=(n1, 256)).astype(np.float32)
+    d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
+    k = min(n1, n2) * 2 // 3
+    src = rs.choice(n1, k, replace=False)
+    kx2 = np.concatenate([kx1[src] + rs.uniform(-jitter, jitter, k), rs.uniform(5, cam.width - 5, n2 - k)]).astype(np.float32)
+    ky2 = np.concatenate([ky1[src] + rs.uniform(-jitter, jitter, k), rs.uniform(5, cam.height - 5, n2 - k)]).astype(np.float32)
+    d2 = np.concatenate([d1[src] + rs.normal(0, noise, (k, 256)), rs.normal(size=(n2 - k, 256))]).astype(np.float32)
+    q = min(k // 4, n2 - k)
+    d2[k:k + q] = d1[src[:q]] + rs.normal(0, noise * 1.5, (q, 256))  # a second, slightly worse copy nearby
+    kx2[k:k + q] = kx2[:q] + 3
+    ky2[k:k + q] = ky2[:q] - 2
+    d1[rs.choice(n1, n1 // 6, replace=False)] = d1[src[:n1 // 6]] + rs.normal(0, noise, (n1 // 6, 256))
+    d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
+    d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    p = rs.permutation(n2)
+    return kx1, ky1, d1.astype(np.float32), np.stack([kx1, ky1], 1).copy(), kx2[p], ky2[p], d2[p].astype(np.float32)
+
+
 def main():
     if not ref_build.build():
         raise SystemExit("the reference tree is not available here")
@@ -79,6 +101,21 @@ def main():
         out[pre + "kx"], out[pre + "ky"], out[pre + "queries"] = kx, ky, q
         out[pre + "ans"], out[pre + "off"] = np.array(ans, np.int32), np.array(off, np.int32)
         print(pre, "hits", len(ans))
+    # Matcher::SearchForInitialization (Matcher.cpp:582-651): two frames, F2 = moved copies of part of F1 + clutter +
+    # near-duplicates competing for the same feature
+    for c, (cname, seed, n1, n2, noise, jitter, window, ratio) in enumerate(
+            [("EuRoC", 1, 180, 200, 0.04, 30.0, 50, 0.9), ("TUM-VI", 2, 120, 90, 0.04, 40.0, 100, 0.85),
+             ("EuRoC", 3, 60, 150, 0.02, 5.0, 20, 0.6)]):
+        cam = CAMS[cname]
+        a = init_pair(seed, cam, n1, n2, noise, jitter)
+        ref = R.search_for_initialization(cam, a[0], a[1], a[2], a[3], a[4], a[5], a[6], window, ratio)
+        pre = "init%d/" % c
+        out[pre + "meta"] = np.array([list(CAMS).index(cname), window, ratio], np.float64)
+        for k, v in zip(("kx1", "ky1", "desc1", "prev", "kx2", "ky2", "desc2"), a):
+            out[pre + k] = v
+        out[pre + "ref_nmatches"] = np.array([ref["nmatches"]], np.int32)
+        out[pre + "ref_matches12"], out[pre + "ref_prev"] = ref["matches12"], ref["prev_matched"]
+        print(pre, cname, "n1", n1, "n2", n2, "nmatches", ref["nmatches"])
     path = os.path.join(ROOT, "tests", "golden", "ref_l2.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path) // 1024, "KiB")

@@ -19,5 +19,18 @@ int shim_instantiate(GeometricCamera* cam, Frame& F, std::vector<MapPoint*>& mps
     std::vector<MapPoint*> bowm;
     n += ppg_shim::search_by_bow(ex.context(), &kf, F, bowm, 0.8f, 0.7f);  // Matcher.cpp:393-477
     n += ppg_shim::extend_map_matches(ex.context(), F, mps, 10.f, 0.8f);  // Matcher.cpp:203-381
+    // class Matcher: all twelve signatures of matching/include/Matcher.h:20-64 resolve on the shim class
+    ppg_shim::Matcher m(ex.context(), cam, 0.8f);
+    std::vector<cv::Point2f> prev(F.mvKeysUn.size());
+    std::vector<int> m12;
+    std::vector<std::pair<size_t, size_t>> pairs;
+    std::set<MapPoint*> found;
+    Sim3f S;
+    n += m.ExtendMapMatches(F, mps, 10.f) + m.SearchByBoW(&kf, F, bowm) + m.SearchForInitialization(F, F, prev, m12, 50);
+    n += m.SearchByProjection(F, mps) + m.SearchByProjection(F, F, 15.f) + m.SearchByProjection(F, &kf, found, 3.f, 0.7f) +
+         m.SearchByProjection(&kf, S, mps, bowm, 10);
+    n += m.SearchByBoW(&kf, &kf, bowm) + m.SearchForTriangulation(&kf, &kf, pairs) + m.SearchBySim3(&kf, &kf, bowm, S, 7.5f);
+    n += m.Fuse(&kf, mps) + m.Fuse(&kf, S, mps, 3.f, bowm);
+    n += (m.mfNNratio > 0.f && ppg_shim::Matcher::TH_LOW < ppg_shim::Matcher::TH_HIGH && m.mpCamera == cam) ? 1 : 0;
     return n + (int)ppg_shim::search_local_points(ex.context(), F, mps, 10.f, 0.8f).accept.size();
 }

@@ -19,6 +19,11 @@ struct Mat {
     template <typename T> T* ptr(int = 0) { return nullptr; }
     template <typename T> const T* ptr(int = 0) const { return nullptr; }
 };
+struct Point2f {
+    float x = 0, y = 0;
+    Point2f() {}
+    Point2f(float a, float b) : x(a), y(b) {}
+};
 }  // namespace cv
 struct Vec2f {
     float v[2];
@@ -95,4 +100,26 @@ struct Frame {
     std::vector<MapPoint*> mvpMapPoints;
     std::vector<MapEdge*> mvpMapEdges;
     cv::Mat mDescriptors;
+};
+
+#include <set>
+struct Sim3f {};
+class Matcher {  // matching/include/Matcher.h:20-64, signatures only
+public:
+    Matcher(GeometricCamera* pCam, float nnratio = 0.6) : mpCamera(pCam), mfNNratio(nnratio) {}
+    int SearchByProjection(Frame&, const std::vector<MapPoint*>&, const float = 3) { return 0; }
+    int SearchByProjection(Frame&, const Frame&, const float) { return 0; }
+    int SearchByProjection(Frame&, KeyFrame*, const std::set<MapPoint*>&, const float, const float) { return 0; }
+    int SearchByProjection(KeyFrame*, Sim3f&, const std::vector<MapPoint*>&, std::vector<MapPoint*>&, int, float = 1.0) { return 0; }
+    int SearchByBoW(KeyFrame*, Frame&, std::vector<MapPoint*>&) { return 0; }
+    int SearchByBoW(KeyFrame*, KeyFrame*, std::vector<MapPoint*>&) { return 0; }
+    int SearchForInitialization(Frame&, Frame&, std::vector<cv::Point2f>&, std::vector<int>&, int = 10) { return 0; }
+    int SearchForTriangulation(KeyFrame*, KeyFrame*, std::vector<std::pair<size_t, size_t>>&, const bool = false) { return 0; }
+    int SearchBySim3(KeyFrame*, KeyFrame*, std::vector<MapPoint*>&, const Sim3f&, const float) { return 0; }
+    int Fuse(KeyFrame*, const std::vector<MapPoint*>&, const float = 3.0) { return 0; }
+    int Fuse(KeyFrame*, Sim3f&, const std::vector<MapPoint*>&, float, std::vector<MapPoint*>&) { return 0; }
+    int ExtendMapMatches(Frame&, const std::vector<MapPoint*>&, const float) { return 0; }
+    static constexpr float TH_LOW = 0.7f, TH_HIGH = 0.8f;
+    GeometricCamera* mpCamera;
+    float mfNNratio;
 };

@@ -56,6 +56,8 @@ def test_struct_layouts_match_header():
     assert fields("ppg_bow_out") == [f[0] for f in capi.BowOut._fields_]
     assert fields("ppg_bow_match_in") == [f[0] for f in capi.BowMatchIn._fields_]
     assert fields("ppg_bow_match_out") == [f[0] for f in capi.BowMatchOut._fields_]
+    assert fields("ppg_init_match_in") == [f[0] for f in capi.InitMatchIn._fields_]
+    assert fields("ppg_init_match_out") == [f[0] for f in capi.InitMatchOut._fields_]
 
 
 def test_no_cpu_fallback():

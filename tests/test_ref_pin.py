@@ -228,6 +228,44 @@ def test_oracle_equals_reference_extend_live():
         np.testing.assert_array_equal(got["tracked"], ref["tracked"][t["old_of_new"]])
 
 
+def _init_cases():
+    z = _l2()
+    return sorted({k.split("/")[0] for k in z.files if k.startswith("init")})
+
+
+def _init_case(name):
+    z = _l2()
+    d = {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "/")}
+    return _L2_CAMS[int(d["meta"][0])], int(d["meta"][1]), float(d["meta"][2]), d
+
+
+@pytest.mark.parametrize("name", _init_cases())
+def test_oracle_reproduces_the_reference_search_for_initialization(name):
+    """Matcher::SearchForInitialization as the reference's own C++ ran it on two Frames (vector<int> distance quirk
+    included): vnMatches12, the updated vbPrevMatched and the count."""
+    from oracle import post_ref as O
+    cam, window, ratio, d = _init_case(name)
+    got = O.search_for_initialization(cam, d["desc1"], d["prev"], d["kx2"], d["ky2"], d["desc2"], window, ratio)
+    assert got["nmatches"] == int(d["ref_nmatches"][0]) and got["nmatches"] > 10
+    np.testing.assert_array_equal(got["matches12"], d["ref_matches12"])
+    np.testing.assert_array_equal(got["prev_matched"], d["ref_prev"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _init_cases())
+def test_cuda_search_for_initialization_reproduces_the_reference(name):
+    from ppg_slam_b200 import capi
+    cam, window, ratio, d = _init_case(name)
+    e = capi.Extractor(cam, max_batch=1, max_map_points=1024)
+    try:
+        got = e.search_for_initialization(d["desc1"], d["prev"], d["kx2"], d["ky2"], d["desc2"], window, ratio)
+    finally:
+        e.close()
+    assert got["nmatches"] == int(d["ref_nmatches"][0])
+    np.testing.assert_array_equal(got["matches12"], d["ref_matches12"])
+    np.testing.assert_array_equal(got["prev_matched"], d["ref_prev"])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", _l2_cases())
 def test_cuda_extend_map_matches_reproduces_the_reference(name):
@@ -243,3 +281,39 @@ def test_cuda_extend_map_matches_reproduces_the_reference(name):
     finally:
         e.close()
     _same_as_reference(got, d)
+
+
+# ------------------------------------------------------------------------------------------------ the drop-in classes
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _l2_cases())
+def test_shim_matcher_class_equals_the_reference_on_real_objects(name):
+    """include/ppg_shim.hpp compiled against the reference's real Frame.h / MapPoint.h / PPGGraph.h / Matcher.h and
+    EXECUTED: one pointer graph of MapPoint / MapEdge / Frame objects goes through the reference's own
+    Matcher::ExtendMapMatches, an identical one through ppg_shim::Matcher::ExtendMapMatches (row ordering, row_of map,
+    C ABI, GPU, write-back into F.mvpMapPoints / F.mvpMapEdges / mnTrackedbyFrame); both must leave the same state."""
+    from oracle import ref_harness as R
+    if not R.shim_available():
+        pytest.skip("shim harness not built (built in the build container: oracle/ref_build.py)")
+    cam, th, ratio, d = _l2_case(name)
+    ref, shim = R.shim_extend_both(cam, d["map_desc"], d["candidate"], d["observed"], d["bad"], d["edge_off"],
+                                   d["edge_other"], d["edge_ok"], d["proj_uv"], d["view_cos"], d["tracked"], d["kp_x"],
+                                   d["kp_y"], d["frame_desc"], d["kp_mp"], d["edge_start"], d["edge_end"], d["conn_off"],
+                                   d["conn_idx"], th, ratio)
+    assert shim["nmatches"] == ref["nmatches"]
+    np.testing.assert_array_equal(shim["kp_mp"], ref["kp_mp"])
+    np.testing.assert_array_equal(shim["kedge_me"], ref["kedge_me"])
+    np.testing.assert_array_equal(shim["tracked"], ref["tracked"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _init_cases())
+def test_shim_search_for_initialization_equals_the_reference_on_real_frames(name):
+    from oracle import ref_harness as R
+    if not R.shim_available():
+        pytest.skip("shim harness not built (built in the build container: oracle/ref_build.py)")
+    cam, window, ratio, d = _init_case(name)
+    ref, shim = R.shim_init_both(cam, d["kx1"], d["ky1"], d["desc1"], d["prev"], d["kx2"], d["ky2"], d["desc2"], window,
+                                 ratio)
+    assert shim["nmatches"] == ref["nmatches"] == int(d["ref_nmatches"][0])
+    np.testing.assert_array_equal(shim["matches12"], ref["matches12"])
+    np.testing.assert_array_equal(shim["prev_matched"], ref["prev_matched"])
