@@ -61,18 +61,35 @@ __device__ int block_excl_scan(int v, int* ws, int* total) {
 // K5: threshold scan.  state[pix] = 1 for in-border pixels with score >= thresh (:173 skips "<", so a
 // NaN would pass); their indices are appended (unordered) to cand[].  Pixels closer than R to the border
 // can never be accepted and never suppress (:190-193), so they are dropped here.
-__global__ void __launch_bounds__(256) scan_kernel(const PostParams p) {
+// SCAN_Q quads of four pixels per thread, a block covers SCAN_Q * 256 consecutive quads: every thread has SCAN_Q
+// independent 16-byte loads in flight (the first version, one quad per thread, ran at 0.16 of the HBM copy bandwidth:
+// latency-bound), the row of a quad comes from a multiply-high with the precomputed reciprocal of W instead of a
+// division, and a warp appends its candidates with one atomic for all its quads.
+constexpr int SCAN_Q = 4;
+__global__ void __launch_bounds__(256) scan_kernel(const PostParams p, const uint32_t w_magic) {
     const int b = blockIdx.y;
-    const int HW = p.H * p.W;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;  // quad index
+    const int HW = p.H * p.W, nq = HW >> 2;
     const int lane = threadIdx.x & 31;
     const int R = p.nms_radius;
+    const int q0 = blockIdx.x * (256 * SCAN_Q) + threadIdx.x;
+    const float* prob = p.prob + (size_t)b * HW;
+    float4 v[SCAN_Q];
+#pragma unroll
+    for (int u = 0; u < SCAN_Q; u++) {
+        const int q = q0 + u * 256;
+        v[u] = q < nq ? __ldcs(reinterpret_cast<const float4*>(prob) + q) : make_float4(-1.f, -1.f, -1.f, -1.f);
+    }
     int c = 0, call = 0;
-    uint32_t idxs[4];
-    if (q * 4 < HW) {
-        const float4 v = *reinterpret_cast<const float4*>(p.prob + (size_t)b * HW + q * 4);
-        const float s[4] = {v.x, v.y, v.z, v.w};
-        const int pix = q * 4, y = pix / p.W, x0 = pix - y * p.W;
+    uint32_t stq[SCAN_Q];  // one byte per pixel of the quad: 1 = in-border candidate
+#pragma unroll
+    for (int u = 0; u < SCAN_Q; u++) {
+        const int q = q0 + u * 256;
+        stq[u] = 0;
+        if (q >= nq) continue;
+        const float s[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        const int pix = q * 4;
+        const int y = (int)__umulhi((uint32_t)pix, w_magic);  // pix / W (exact: pix < 2^32 / W, checked on the host)
+        const int x0 = pix - y * p.W;
         const bool yin = (y >= R) && (y <= p.H - R - 1);
         uint32_t st = 0;
 #pragma unroll
@@ -81,33 +98,57 @@ __global__ void __launch_bounds__(256) scan_kernel(const PostParams p) {
             const int x = x0 + k;
             const bool inb = yin && (x >= R) && (x <= p.W - R - 1);
             call += pass;
-            if (pass && inb) {
-                st |= 1u << (8 * k);
-                idxs[c++] = pix + k;
-            }
+            if (pass && inb) st |= 1u << (8 * k);
         }
+        stq[u] = st;
+        c += __popc(st);
         if (p.nms_smem) {
             // 2 bits per pixel, 4 pixels per byte (pixel k of the quad in bits 2k..2k+1)
             const uint32_t packed = (st & 1u) | ((st >> 6) & 4u) | ((st >> 12) & 16u) | ((st >> 18) & 64u);
-            p.state2[(size_t)b * (HW / 4) + q] = (uint8_t)packed;
+            p.state2[(size_t)b * nq + q] = (uint8_t)packed;
         } else {
             *reinterpret_cast<uint32_t*>(p.state + (size_t)b * HW + pix) = st;
         }
     }
-    // warp-aggregated append
+    // block-aggregated append: ONE pair of atomics per block (per-frame counters: with one pair per warp the 1 400
+    // same-address atomics of a frame serialised in L2 and set the kernel time)
+    __shared__ int s_wtot[8], s_wcall[8], s_base;
+    const int warp = threadIdx.x >> 5;
     const int inc = warp_incl_scan(c, lane);
     const int tot = __shfl_sync(FULL, inc, 31);
-    int call_w = call;
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) call_w += __shfl_xor_sync(FULL, call_w, s);
-    int base = 0;
+    const int call_w = __reduce_add_sync(FULL, call);
     if (lane == 0) {
-        if (tot) base = atomicAdd(&p.counters[b * 8 + 0], tot);
-        if (call_w) atomicAdd(&p.counters[b * 8 + 1], call_w);
+        s_wtot[warp] = tot;
+        s_wcall[warp] = call_w;
     }
-    base = __shfl_sync(FULL, base, 0);
-    uint32_t* cl = p.cand + (size_t)b * HW;
-    for (int k = 0; k < c; k++) cl[base + inc - c + k] = idxs[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0, cw = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const int x = s_wtot[w];
+            s_wtot[w] = t;  // exclusive prefix over the warps
+            t += x;
+            cw += s_wcall[w];
+        }
+        s_base = t ? atomicAdd(&p.counters[b * 8 + 0], t) : 0;
+        if (cw) atomicAdd(&p.counters[b * 8 + 1], cw);
+    }
+    __syncthreads();
+    const int base = s_base + s_wtot[warp];
+    if (c) {
+        uint32_t* cl = p.cand + (size_t)b * HW + base + inc - c;
+#pragma unroll
+        for (int u = 0; u < SCAN_Q; u++) {
+            uint32_t st = stq[u];
+            const uint32_t pix = (uint32_t)(q0 + u * 256) * 4u;
+            while (st) {
+                const int k = (__ffs(st) - 1) >> 3;
+                *cl++ = pix + k;
+                st &= st - 1;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -431,15 +472,43 @@ __global__ void __launch_bounds__(256) refine_kernel(const PostParams p, float* 
 #pragma unroll
         for (int k = 0; k < 8; k++) o[k] = 0.f;
     } else {
-        // valCount-th largest valid value by bitwise binary search (positive floats order as uints)
-        uint32_t t = 0;
-        for (int bit = 30; bit >= 0; bit--) {
-            const uint32_t c = t | (1u << bit);
-            int ge = 0;
+        // valCount-th largest valid value by bitwise binary search (positive floats order as uints): t ends as the largest
+        // threshold with at least valCount values >= t.  Two shortcuts (the ncu capture showed the kernel issue-bound on
+        // this loop, 31 rounds of 8 compares + a warp reduction): the bits above the highest bit in which the tile's
+        // largest and smallest valid values differ are common to all of them, and as soon as EXACTLY valCount values are
+        // >= t the answer is the smallest of those -- one more reduction instead of the remaining rounds.
+        uint32_t umax = 0, umin = 0xffffffffu;
 #pragma unroll
-            for (int k = 0; k < 8; k++) ge += (u[k] >= c);
-            ge = __reduce_add_sync(FULL, ge);
-            if (ge >= valCount) t = c;
+        for (int k = 0; k < 8; k++) {
+            umax = max(umax, u[k]);
+            if (u[k]) umin = min(umin, u[k]);
+        }
+        umax = __reduce_max_sync(FULL, umax);
+        umin = __reduce_min_sync(FULL, umin);
+        const uint32_t diff = umax ^ umin;
+        uint32_t t = umax;  // all valid values equal
+        if (diff) {
+            const int top = 31 - __clz(diff);
+            t = umax & ~((2u << top) - 1u);  // the common prefix: every valid value is >= it
+            int ge_t = n;                    // values >= t
+            for (int bit = top; bit >= 0 && ge_t != valCount; bit--) {
+                const uint32_t c = t | (1u << bit);
+                int ge = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) ge += (u[k] >= c);
+                ge = __reduce_add_sync(FULL, ge);
+                if (ge >= valCount) {
+                    t = c;
+                    ge_t = ge;
+                }
+            }
+            if (ge_t == valCount) {  // the valCount-th largest is the smallest value >= t
+                uint32_t m = 0xffffffffu;
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (u[k] >= t) m = min(m, u[k]);
+                t = __reduce_min_sync(FULL, m);
+            }
         }
         // sum of the top valCount values; double accumulation of <= 76 floats in (0.01, 1] is exact, so
         // the order is irrelevant (:563 std::accumulate(..., 0.0) over the sorted prefix)
@@ -1459,8 +1528,10 @@ cudaError_t post_keypoints_launch(const PostParams& p, cudaStream_t st, long lon
     if (!p.scan_fused) {
         cudaError_t e = cudaMemsetAsync(p.counters, 0, sizeof(int) * 8 * p.B, st);
         if (e != cudaSuccess) return e;
-        dim3 g((HW / 4 + 255) / 256, p.B);
-        scan_kernel<<<g, 256, 0, st>>>(p);
+        dim3 g((HW / 4 + 256 * SCAN_Q - 1) / (256 * SCAN_Q), p.B);
+        // ceil(2^32 / W): __umulhi(pix, magic) == pix / W for every pix < 2^32 / W (H * W is far below that)
+        const uint32_t w_magic = (uint32_t)(((1ull << 32) + (uint64_t)p.W - 1) / (uint64_t)p.W);
+        scan_kernel<<<g, 256, 0, st>>>(p, w_magic);
         *launches += 1;
         mark("post.scan");
     }

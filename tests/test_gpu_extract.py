@@ -37,6 +37,22 @@ def test_conv_selftest(ex_euroc):
         assert d <= 2e-2 * max(1.0, r), "layer %s: tcgen05 vs CUDA-core conv differ by %g (ref max %g)" % (name, d, r)
 
 
+@pytest.mark.parametrize("kernel", ["1", "2", "4"], ids=["generic", "halo", "transposed-everywhere"])
+def test_conv_selftest_other_kernel_choices(kernel, monkeypatch):
+    """PPG_CONV_KERNEL routes the Cin = 64 layers to the other tcgen05 kernels (A/B switch of conv_tc_plan): every choice
+    must give the same layer outputs -- in particular the non-pooled epilogue of the transposed kernel (conv2a under "4"),
+    which the default configuration does not use."""
+    from ppg_slam_b200 import capi
+    monkeypatch.setenv("PPG_CONV_KERNEL", kernel)
+    e = capi.Extractor(cameras.EUROC, max_batch=2)
+    try:
+        e.run([synth.frame(1, 752, 480), synth.frame(2, 752, 480)])
+        for name, d, r in e.selftest_conv():
+            assert d <= 2e-2 * max(1.0, r), "kernel %s layer %s: differ by %g (ref max %g)" % (kernel, name, d, r)
+    finally:
+        e.close()
+
+
 @pytest.mark.parametrize("seed", [0, 3])
 def test_dense_maps_within_tolerance(ex_euroc, net, seed):
     g = synth.frame(seed, 752, 480)
