@@ -567,7 +567,7 @@ def run_b200(args, rank, local_rank, world):
                            "batch_per_gpu": B, "map_rows": args.map_rows, "sharding": "frames (no collective)",
                            "projections": "Frame::CheckInFrustum on the device" if geo is not None else "staged by the host",
                            "device_contexts_in_flight": n_dev_ctx, "e2e_contexts_in_flight": len(ring),
-                           "e2e_host_threads": 1,
+                           "e2e_host_threads": 1, "host_cores": os.cpu_count(),
                            "l2": "per-step working set ~3.4 GB of activations streams through the 126 MB L2 "
                                  "(inputs larger than L2; no explicit flush)"},
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
@@ -639,7 +639,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--map-rows", type=int, default=MAP_ROWS)
     ap.add_argument("--dev-streams", type=int, default=4, help="contexts in flight in the device-timed arm")
-    ap.add_argument("--e2e-streams", type=int, default=4,
+    ap.add_argument("--e2e-streams", type=int, default=6,
                     help="contexts in flight in the e2e arm (one host thread drives them all)")
     ap.add_argument("--assoc", default="extend", choices=["extend", "core"],
                     help="extend: the whole Matcher::ExtendMapMatches on the GPU (default); core: its search core only")

@@ -464,6 +464,9 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
     c->dev = cfg->device;
     c->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("PPG_GRAPH")) c->use_graph = atoi(e) != 0;
+    // PPG_GRAPH_LARGE=1: replay large batches as one graph too (one driver call per step instead of ~35: for hosts
+    // whose cores are the bottleneck; on an otherwise idle host eager launches were measured 3 % faster at batch 32)
+    if (const char* e = getenv("PPG_GRAPH_LARGE")) c->graph_large = atoi(e) != 0;
     c->H = H;
     c->W = W;
     c->Hc = H / 8;
@@ -755,7 +758,7 @@ int ppg_run(ppg_ctx* c, int n) {
     c->n_ev = 0;
     // Graphs pay at small batches, where the ~30 launches are latency (p50 at batch 1: 0.775 -> 0.734 ms); at batch
     // 32 with several contexts in flight eager launches interleave better across streams (9.6 k vs 9.3 k frames/s).
-    if (!c->use_graph || c->profiling || n > 8) return enqueue_run(c, n);
+    if (!c->use_graph || c->profiling || (n > 8 && !c->graph_large)) return enqueue_run(c, n);
     // The launch sequence of a batch size is fixed (same kernels, same parameters): replay it as one CUDA graph.
     // The first call with a size runs eagerly (one-time kernel attributes are set on that path), the second one is
     // captured.

@@ -76,6 +76,7 @@ struct ppg_ctx {
     // CUDA graphs of the launch sequence of ppg_run, one per batch size (captured on the second call with that size;
     // PPG_GRAPH=0 disables).  Profiling runs bypass them (the stage events are not part of the graph).
     bool use_graph = true;
+    bool graph_large = false;  // PPG_GRAPH_LARGE=1: graphs for batches > 8 as well
     std::map<int, cudaGraphExec_t> graphs;
     std::map<int, int> graph_launches;  // kernels per replay, for launch_count
     std::map<int, int> run_calls;
