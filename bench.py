@@ -495,11 +495,15 @@ def run_b200(args, rank, local_rank, world):
         if conv1b_ms:
             ach = CONV1B_GFLOP_PER_FRAME * scale * B / conv1b_ms  # GFLOP / ms = TFLOP/s
             traffic = None
+            fused = "conv1a" not in sd  # conv1a computed by conv1b's producer warps: no separate stage
             tp = os.path.join(ROOT, "profiles", "conv1b_traffic.json")
             if os.path.exists(tp):
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tp)).get("fused_dram_bytes_per_launch" if fused else "dram_bytes_per_launch")
+            kname = ("conv_t64_fused_kernel[conv1a 1->64 3x3 + ReLU computed in the producer warps, conv1b 64->64 3x3 "
+                     "@%dx%d + ReLU + 2x2 pool; only conv1b's FLOPs are counted]" if fused else
+                     "conv_t64_kernel[conv1b 64->64 3x3 @%dx%d + ReLU + 2x2 pool]") % (cam.width, cam.height)
             roof = {"bound": "tensor",
-                    "kernel": "conv_t64_kernel[conv1b 64->64 3x3 @%dx%d + ReLU + 2x2 pool]" % (cam.width, cam.height),
+                    "kernel": kname,
                     "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
                     "peak_source": how + " (sustained bf16 cuBLAS; fp16 runs on the same pipe)",
                     "ms_per_launch": conv1b_ms, "frames_per_launch": B,

@@ -162,6 +162,9 @@ int ppg_get_maps(ppg_ctx* ctx, int frame, float* prob, float* heat_raw, float* h
  * names: up to max_layers pointers to static strings. */
 int ppg_selftest_conv(ppg_ctx* ctx, int max_layers, const char** names, float* max_abs_diff, float* max_abs_ref,
                       int* n_layers);
+/* Validation aid: the raw output tensor (NHWC, fp16 or fp32 as the layer stores it) of tensor-core layer `name`
+ * ("conv1b", "conv2a", ...) for frame `frame` of the last batch.  Copies min(max_bytes, size) bytes, *bytes = size. */
+int ppg_get_layer_output(ppg_ctx* ctx, const char* name, int frame, void* dst, size_t max_bytes, size_t* bytes);
 
 /* Per-stage device times of the last ppg_run when profiling is on (CUDA events between launches on
  * the ctx stream).  names[i] are static strings; returns the stage count through n_stages. */

@@ -121,7 +121,7 @@ class InitMatchOut(C.Structure):
 
 SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", "ppg_api_version", "ppg_extract",
            "ppg_upload_frames", "ppg_run", "ppg_download", "ppg_sync", "ppg_extract_from_maps", "ppg_get_maps",
-           "ppg_selftest_conv", "ppg_set_profiling", "ppg_get_stage_times", "ppg_launch_count", "ppg_timer_start",
+           "ppg_selftest_conv", "ppg_get_layer_output", "ppg_set_profiling", "ppg_get_stage_times", "ppg_launch_count", "ppg_timer_start",
            "ppg_timer_stop", "ppg_upload_map", "ppg_associate", "ppg_assoc_stage", "ppg_assoc_run",
            "ppg_assoc_fetch", "ppg_assoc_run_frame", "ppg_assoc_stage_batch", "ppg_assoc_run_batch",
            "ppg_assoc_fetch_batch", "ppg_assoc_fallback_rows", "ppg_assoc_device_results",
@@ -172,6 +172,9 @@ def load():
                      "ppg_extend_collect", "ppg_comm_unique_id", "ppg_comm_init", "ppg_comm_destroy",
                      "ppg_assoc_allgather", "ppg_assoc_allgather_fetch", "ppg_search_for_initialization"]:
             getattr(lib, name).restype = C.c_int
+        lib.ppg_get_layer_output.restype = C.c_int
+        lib.ppg_get_layer_output.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t,
+                                             C.POINTER(C.c_size_t)]
         lib.ppg_record_bytes.restype = C.c_longlong
         lib.ppg_record_bytes.argtypes = [C.c_void_p]
         lib.ppg_host_alloc.restype = C.c_void_p
@@ -409,6 +412,15 @@ class Extractor:
         if feature:
             r["feature"] = feat
         return r
+
+    def layer_output(self, name, frame=0):
+        """Raw output tensor of a tensor-core layer as bytes (validation aid)."""
+        n = C.c_size_t(0)
+        self._check(self.lib.ppg_get_layer_output(self.h, name.encode(), frame, None, 0, C.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        self._check(self.lib.ppg_get_layer_output(self.h, name.encode(), frame, buf.ctypes.data_as(C.c_void_p), n.value,
+                                                  C.byref(n)))
+        return buf
 
     def selftest_conv(self):
         names = (C.c_char_p * 32)()

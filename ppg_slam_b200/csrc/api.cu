@@ -519,6 +519,11 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
 #define ADD(name, wkey, bn, in, h, w, mode, relu, outp, ld, npad)                                           \
     if ((rc = add_tc_layer(c, blob, name, wkey, bn, in, h, w, mode, relu, outp, ld, npad)) != PPG_OK) return rc;
     ADD("conv1b", "backbone.conv1b", "", c->a1, H, W, EPI_F16_POOL, 1, c->a2, 64, 0)
+    {
+        // conv1a runs inside conv1b's producer warps (conv_t64.cu) unless PPG_CONV_KERNEL asks for an older arrangement
+        const char* e = getenv("PPG_CONV_KERNEL");
+        if ((!e || atoi(e) >= 5) && c->tc.back().L.v3 == 1) conv_t64_fuse_conv1a(c->tc.back().L, c->gray, c->w1a, c->b1a);
+    }
     ADD("conv2a", "backbone.conv2a", "", c->a2, H / 2, W / 2, EPI_F16, 1, c->a3, 64, 0)
     ADD("conv2b", "backbone.conv2b", "", c->a3, H / 2, W / 2, EPI_F16_POOL, 1, c->a4, 64, 0)
     ADD("conv3a", "backbone.conv3a", "", c->a4, H / 4, W / 4, EPI_F16, 1, c->a5, 128, 0)
@@ -583,7 +588,18 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
                 for (int u = 0; u < W; u++) {
                     float mx, my;
                     undistort_map_px(cfg->K, cfg->D, cfg->fisheye, u, v, &mx, &my);
-                    rl[(size_t)v * W + u] = make_int2((int)lrint((double)(mx * 32.0f)), (int)lrint((double)(my * 32.0f)));
+                    // 1/32 fixed point as cv::remap; packed for remap_kernel (post.cu): offset of the top-left texel,
+                    // the two 5-bit fractions and which of the four texels lie inside the image
+                    const int sx = (int)lrint((double)(mx * 32.0f)), sy = (int)lrint((double)(my * 32.0f));
+                    const int ix = sx >> 5, iy = sy >> 5;
+                    const bool x0 = ix >= 0 && ix < W, x1 = ix + 1 >= 0 && ix + 1 < W;
+                    const bool y0 = iy >= 0 && iy < H, y1 = iy + 1 >= 0 && iy + 1 < H;
+                    const unsigned bits = (unsigned)(sx & 31) | ((unsigned)(sy & 31) << 5) | ((unsigned)(y0 && x0) << 10) |
+                                          ((unsigned)(y0 && x1) << 11) | ((unsigned)(y1 && x0) << 12) |
+                                          ((unsigned)(y1 && x1) << 13);
+                    const long long off = (long long)iy * W + ix;
+                    const bool any = (bits >> 10) != 0;  // far outside: the offset is never dereferenced
+                    rl[(size_t)v * W + u] = make_int2(any ? (int)off : 0, (int)bits);
                 }
             PPG_CUDA(c, dalloc(&c->remap_lut, HW));
             PPG_CUDA(c, cudaMemcpy(c->remap_lut, rl.data(), HW * sizeof(int2), cudaMemcpyHostToDevice));
@@ -800,9 +816,11 @@ int ppg_run(ppg_ctx* c, int n) {
 
 static int enqueue_run(ppg_ctx* c, int n) {
     stage_mark(c, "start");
-    PPG_CUDA(c, conv1a_tc_launch(c->gray, c->w1a, c->b1a, c->a1, n, c->H, c->W, c->st));
-    c->launches++;
-    stage_mark(c, "conv1a");
+    if (c->tc.empty() || c->tc[0].L.v3 != 2) {  // otherwise conv1b computes it on the fly
+        PPG_CUDA(c, conv1a_tc_launch(c->gray, c->w1a, c->b1a, c->a1, n, c->H, c->W, c->st));
+        c->launches++;
+        stage_mark(c, "conv1a");
+    }
     // Small batches leave most of the GPU idle inside every kernel, so the branches of the network and of the
     // post-processing that do not depend on one another are forked onto side streams:
     //   st : backbone -> junction head -> keypoints (scan, NMS)   ...join heat... -> point-pair graph  ...join desc
@@ -1011,12 +1029,38 @@ int ppg_get_maps(ppg_ctx* c, int frame, float* prob, float* heat_raw, float* hea
     return PPG_OK;
 }
 
+int ppg_get_layer_output(ppg_ctx* c, const char* name, int frame, void* dst, size_t max_bytes, size_t* bytes) {
+    if (!c || !name || !bytes || frame < 0 || frame >= c->maxB) return set_err(c, PPG_ERR_ARG, "ppg_get_layer_output: bad argument");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    for (auto& l : c->tc) {
+        if (strcmp(l.name, name)) continue;
+        size_t px = (size_t)l.H * l.W, el = 2;
+        if (l.mode == EPI_F16_POOL) px /= 4;
+        if (l.mode == EPI_F16_PS2) px *= 4;
+        if (l.mode == EPI_F32) el = 4;
+        if (l.mode == EPI_SOFTMAX_D2S) px *= 64, el = 4;
+        const size_t sz = px * (l.mode == EPI_SOFTMAX_D2S ? 1 : l.out_ld) * el;
+        *bytes = sz;
+        const size_t n = sz < max_bytes ? sz : max_bytes;
+        if (dst && n)
+            PPG_CUDA(c, cudaMemcpy(dst, static_cast<const uint8_t*>(l.out) + (size_t)frame * sz, n, cudaMemcpyDeviceToHost));
+        return PPG_OK;
+    }
+    return set_err(c, PPG_ERR_ARG, "ppg_get_layer_output: no such layer");
+}
+
 // Validation of the tcgen05 convolution against a plain CUDA-core convolution over the same fp16 operands.
 int ppg_selftest_conv(ppg_ctx* c, int max_layers, const char** names, float* max_abs_diff, float* max_abs_ref,
                       int* n_layers) {
     if (!c || !names || !max_abs_diff || !max_abs_ref || !n_layers) return set_err(c, PPG_ERR_ARG, "null argument");
     PPG_CUDA(c, cudaSetDevice(c->dev));
     PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    if (!c->tc.empty() && c->tc[0].L.v3 == 2) {
+        // conv1b computed conv1a on the fly: give the check its input map from the stand-alone conv1a kernel (frame 0)
+        PPG_CUDA(c, conv1a_tc_launch(c->gray, c->w1a, c->b1a, c->a1, 1, c->H, c->W, c->st));
+        c->launches++;
+    }
     int nl = 0;
     for (auto& l : c->tc) {
         if (nl >= max_layers) break;

@@ -603,8 +603,9 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
     p.tile_w_log2 = 4;
     L.v3 = 0;
     L.wgt = nullptr;
-    // Kernel choice.  PPG_CONV_KERNEL (A/B comparison only; every setting gives the same results):
-    //   unset / 3: transposed kernel (conv_t64.cu) for the pooled 3x3 64 -> 64 layers (conv1b, conv2b: 90 % / 87 % of the
+    // Kernel choice.  PPG_CONV_KERNEL (A/B comparison only; the settings differ in the fp32 summation order of the taps, i.e. in the last bits):
+    //   unset / 5: as 3, and conv1a is computed inside conv1b's producer warps (api.cu, conv_t64.cu);
+    //   3: transposed kernel (conv_t64.cu) for the pooled 3x3 64 -> 64 layers (conv1b, conv2b: 90 % / 87 % of the
     //      tensor pipe), halo kernel for the other Cin = 64 layers.  conv2a (no pool: four times the outputs to add,
     //      convert and store per tile) is epilogue-bound on the transposed kernel -- 0.266 ms against 0.237 ms on the halo
     //      kernel per 32 frames -- so it stays on the halo kernel;
@@ -612,9 +613,9 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
     //   1: generic kernel everywhere.
     // Measured on B200 (tools/conv_variants.py): UMMA applies the 128-byte swizzle XOR on absolute shared-memory
     // address bits, so a descriptor may start at any 128-byte row of a swizzled tile with base_offset = 0.
-    int kmode = 3;
+    int kmode = 5;
     if (const char* e = getenv("PPG_CONV_KERNEL")) kmode = atoi(e);
-    if (kmode >= 3 && conv_t64_applies(cin, cout_padded, taps, mode) && (mode == EPI_F16_POOL || kmode >= 4)) {
+    if (kmode >= 3 && conv_t64_applies(cin, cout_padded, taps, mode) && (mode == EPI_F16_POOL || kmode == 4)) {
         conv_t64_plan(L, maxB, H, W);
         return;
     }

@@ -442,12 +442,12 @@ __global__ void __launch_bounds__(256) refine_kernel(const PostParams p, float* 
         u[k] = valid ? __float_as_uint(v[k]) : 0u;
         cnt += valid;
     }
-    const int inc = warp_incl_scan(cnt, lane);
-    const int n = __shfl_sync(FULL, inc, 31);
+    const int n = __reduce_add_sync(FULL, cnt);
     const int valCount = (int)(p.line_valid_ratio * (float)n);  // :554
     bool unchanged = valCount < 1, zero = false;                // :555 leaves the tile as it is
     if (!unchanged && (double)n >= 256.0 * 0.9) {               // :557
         const int k = (int)((double)n * 0.9);                   // index into the raster-ordered valid list
+        const int inc = warp_incl_scan(cnt, lane);
         const int excl = inc - cnt;
         float cand = 0.f;
         const bool mine = (k >= excl) && (k < inc);
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(256) refine_kernel(const PostParams p, float* 
         for (int k = 0; k < 8; k++) {
             if (u[k]) {
                 const float ns = __fdiv_rn(v[k], ave);
-                o[k] = ((double)ns > 1.0) ? 1.0f : ns;  // :570
+                o[k] = (ns > 1.0f) ? 1.0f : ns;  // :570 compares as double: the same predicate
             } else {
                 o[k] = 0.f;  // :573
             }
@@ -543,36 +543,40 @@ __global__ void __launch_bounds__(256) refine_kernel(const PostParams p, float* 
 
 // ------------------------------------------------------------------------------------------------
 // K9: cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) as OpenCV evaluates it for CV_32F: coordinates in
-// 1/32 fixed point (remap_lut holds rint(map*32), built once at ppg_create), four f32 weights, sequential
-// f32 sum.  4 pixels per thread.
+// 1/32 fixed point, four f32 weights, sequential f32 sum.  4 pixels per thread.
+// remap_lut (built once at ppg_create from rint(map * 32), api.cu) holds per pixel .x = iy * W + ix of the top-left
+// source texel and .y = fx | fy << 5 | in-image bits of the four texels << 10: the first version kept (sx, sy) and
+// spent two thirds of its instructions on shifts, bounds tests and address arithmetic -- it was issue-bound at 0.71 of
+// the HBM rate.
+// A thread handles pixels t, t + 256, t + 512, t + 768 of its block's 1024: every warp-wide access -- table, the four
+// gathers of a pixel, the store -- then covers 32 neighbouring pixels, i.e. one or two 128-byte lines (with four
+// CONSECUTIVE pixels per thread a gather touched four lines for a quarter of their bytes: 76 L1 wavefronts per 128
+// pixels instead of 28).
 __global__ void __launch_bounds__(256) remap_kernel(const PostParams p) {
-    const int b = blockIdx.y, HW = p.H * p.W, W = p.W, H = p.H;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q * 4 >= HW) return;
+    const int b = blockIdx.y, HW = p.H * p.W, W = p.W;
+    const int q0 = blockIdx.x * 1024 + threadIdx.x;
     const float* src = p.heat_ref + (size_t)b * HW;
-    const int4 l0 = *reinterpret_cast<const int4*>(p.remap_lut + q * 4);
-    const int4 l1 = *reinterpret_cast<const int4*>(p.remap_lut + q * 4 + 2);
-    const int sxs[4] = {l0.x, l0.z, l1.x, l1.z}, sys[4] = {l0.y, l0.w, l1.y, l1.w};
-    float o[4];
+    int2 l[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) l[k] = (q0 + k * 256 < HW) ? p.remap_lut[q0 + k * 256] : make_int2(0, 0);
+    float s[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {  // all sixteen loads first
+        const float* t = src + l[k].x;
+        const uint32_t pk = (uint32_t)l[k].y;
+        s[k][0] = (pk & 0x400u) ? t[0] : 0.f;
+        s[k][1] = (pk & 0x800u) ? t[1] : 0.f;
+        s[k][2] = (pk & 0x1000u) ? t[W] : 0.f;
+        s[k][3] = (pk & 0x2000u) ? t[W + 1] : 0.f;
+    }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int sx = sxs[k], sy = sys[k];
-        const int ix = sx >> 5, iy = sy >> 5;
-        const float fx = (float)(sx & 31) * (1.0f / 32.0f), fy = (float)(sy & 31) * (1.0f / 32.0f);
+        const uint32_t pk = (uint32_t)l[k].y;
+        const float fx = (float)(pk & 31u) * (1.0f / 32.0f), fy = (float)((pk >> 5) & 31u) * (1.0f / 32.0f);
         const float w00 = (1.0f - fy) * (1.0f - fx), w01 = (1.0f - fy) * fx, w10 = fy * (1.0f - fx), w11 = fy * fx;
-        float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
-        const bool x0 = ix >= 0 && ix < W, x1 = ix + 1 >= 0 && ix + 1 < W;
-        if (iy >= 0 && iy < H) {
-            if (x0) s00 = src[iy * W + ix];
-            if (x1) s01 = src[iy * W + ix + 1];
-        }
-        if (iy + 1 >= 0 && iy + 1 < H) {
-            if (x0) s10 = src[(iy + 1) * W + ix];
-            if (x1) s11 = src[(iy + 1) * W + ix + 1];
-        }
-        o[k] = ((s00 * w00 + s01 * w01) + s10 * w10) + s11 * w11;
+        const float o = ((s[k][0] * w00 + s[k][1] * w01) + s[k][2] * w10) + s[k][3] * w11;
+        if (q0 + k * 256 < HW) p.heat_final[(size_t)b * HW + q0 + k * 256] = o;
     }
-    *reinterpret_cast<float4*>(p.heat_final + (size_t)b * HW + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1550,7 +1554,7 @@ cudaError_t post_heat_launch(const PostParams& p, cudaStream_t st, long long* la
     *launches += 1;
     mark("post.refine");
     if (p.do_remap) {
-        dim3 g((p.H * p.W / 4 + 255) / 256, p.B);
+        dim3 g((p.H * p.W + 1023) / 1024, p.B);
         remap_kernel<<<g, 256, 0, st>>>(p);
         *launches += 1;
         mark("post.remap");

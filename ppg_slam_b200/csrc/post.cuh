@@ -48,7 +48,7 @@ struct PostParams {
     const float* desc;  // [B][Hc][Wc][256] fp32 NHWC
     // init-time tables
     const float2* undist_lut;  // [H*W] (xun, yun) of every integer pixel
-    const int2* remap_lut;     // [H*W] fixed-point (sx, sy) = rint(map*32)
+    const int2* remap_lut;     // [H*W] (iy * W + ix, fx | fy << 5 | inside bits << 10) of rint(map*32), see remap_kernel
     // scratch, per frame
     uint8_t* state;     // [B][H*W]   0 none, 1 undecided candidate, 2 accepted, 3 suppressed
     uint8_t* state2;    // [B][H*W/4] the same, 2 bits per pixel (shared-memory NMS variant)

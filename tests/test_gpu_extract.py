@@ -37,7 +37,7 @@ def test_conv_selftest(ex_euroc):
         assert d <= 2e-2 * max(1.0, r), "layer %s: tcgen05 vs CUDA-core conv differ by %g (ref max %g)" % (name, d, r)
 
 
-@pytest.mark.parametrize("kernel", ["1", "2", "4"], ids=["generic", "halo", "transposed-everywhere"])
+@pytest.mark.parametrize("kernel", ["1", "2", "3", "4"], ids=["generic", "halo", "transposed-unfused", "transposed-everywhere"])
 def test_conv_selftest_other_kernel_choices(kernel, monkeypatch):
     """PPG_CONV_KERNEL routes the Cin = 64 layers to the other tcgen05 kernels (A/B switch of conv_tc_plan): every choice
     must give the same layer outputs -- in particular the non-pooled epilogue of the transposed kernel (conv2a under "4"),
@@ -51,6 +51,32 @@ def test_conv_selftest_other_kernel_choices(kernel, monkeypatch):
             assert d <= 2e-2 * max(1.0, r), "kernel %s layer %s: differ by %g (ref max %g)" % (kernel, name, d, r)
     finally:
         e.close()
+
+
+def test_fused_conv1a_is_bit_identical_to_the_separate_kernel(monkeypatch):
+    """Default: conv1a runs inside conv1b's producer warps (same tcgen05 instruction on the same operands as the
+    stand-alone conv1a kernel, zero rows for conv1b's padding).  PPG_CONV_KERNEL=3 runs the two kernels with the
+    full-resolution map in HBM between them.  Everything downstream must be bit-identical, ragged tile edges (752 = 19 * 38
+    + 30) and a batch that leaves SMs with different tile counts included."""
+    from ppg_slam_b200 import capi
+    frames = [synth.frame(s, 752, 480) for s in (4, 5, 6)]
+    out = {}
+    for mode in ("5", "3"):
+        monkeypatch.setenv("PPG_CONV_KERNEL", mode)
+        e = capi.Extractor(cameras.EUROC, max_batch=3)
+        try:
+            recs = e.run(frames, allow_capacity=True)
+            out[mode] = (recs, [e.get_maps(i) for i in range(3)])
+        finally:
+            e.close()
+    for i in range(3):
+        for k in ("prob", "heat", "desc"):
+            assert np.array_equal(out["5"][1][i][k], out["3"][1][i][k]), (i, k)
+        a, b = out["5"][0][i], out["3"][0][i]
+        assert a["n_kp"] == b["n_kp"] and a["n_kp"] > 50
+        for k in a:
+            if isinstance(a[k], np.ndarray):
+                assert np.array_equal(a[k], b[k], equal_nan=a[k].dtype.kind == "f"), (i, k)
 
 
 @pytest.mark.parametrize("seed", [0, 3])
