@@ -20,6 +20,7 @@ SOURCES = {
     "api.cu": [],
     "conv_tc.cu": [],
     "conv_t64.cu": [],
+    "conv_t128.cu": [],
     "net_direct.cu": [],
     "conv1a_tc.cu": [],
     "post.cu": ["-fmad=false"],

@@ -281,7 +281,7 @@ static int add_tc_layer(ppg_ctx* c, const Blob& blob, const char* name, const st
     memset(&li.L.hb, 0, sizeof(li.L.hb));
     memcpy(li.L.hb.v, hb.data(), hb.size() * sizeof(float));
     if (!make_act_map(&li.L.mapA, in, c->maxB, H, W, cin, li.L.box_w, li.L.box_h) ||
-        !make_kmajor_map(&li.L.mapB, li.w, (uint64_t)taps * N, cin, (uint32_t)N, false))
+        !make_kmajor_map(&li.L.mapB, li.w, (uint64_t)taps * N, cin, li.L.v3 == 3 ? 128u : (uint32_t)N, false))
         return set_err(c, PPG_ERR_CUDA, std::string("cuTensorMapEncodeTiled failed for ") + name);
     c->tc.push_back(li);
     return PPG_OK;

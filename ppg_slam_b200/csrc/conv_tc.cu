@@ -604,7 +604,9 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
     L.v3 = 0;
     L.wgt = nullptr;
     // Kernel choice.  PPG_CONV_KERNEL (A/B comparison only; the settings differ in the fp32 summation order of the taps, i.e. in the last bits):
-    //   unset / 5: as 3, and conv1a is computed inside conv1b's producer warps (api.cu, conv_t64.cu);
+    //   unset / 6: as 5, and the 3x3 layers with Cin = 128 run on the transposed kernel of conv_t128.cu instead of the
+    //      generic one;
+    //   5: as 3, and conv1a is computed inside conv1b's producer warps (api.cu, conv_t64.cu);
     //   3: transposed kernel (conv_t64.cu) for the pooled 3x3 64 -> 64 layers (conv1b, conv2b: 90 % / 87 % of the
     //      tensor pipe), halo kernel for the other Cin = 64 layers.  conv2a (no pool: four times the outputs to add,
     //      convert and store per tile) is epilogue-bound on the transposed kernel -- 0.266 ms against 0.237 ms on the halo
@@ -613,10 +615,14 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
     //   1: generic kernel everywhere.
     // Measured on B200 (tools/conv_variants.py): UMMA applies the 128-byte swizzle XOR on absolute shared-memory
     // address bits, so a descriptor may start at any 128-byte row of a swizzled tile with base_offset = 0.
-    int kmode = 5;
+    int kmode = 6;
     if (const char* e = getenv("PPG_CONV_KERNEL")) kmode = atoi(e);
     if (kmode >= 3 && conv_t64_applies(cin, cout_padded, taps, mode) && (mode == EPI_F16_POOL || kmode == 4)) {
         conv_t64_plan(L, maxB, H, W);
+        return;
+    }
+    if (kmode >= 6 && conv_t128_applies(cin, cout_padded, taps, mode)) {
+        conv_t128_plan(L, maxB, H, W, 148);
         return;
     }
     L.v2 = (kmode >= 2 && taps == 9 && cin == 64 && cout_padded <= 128 && cout_padded % 64 == 0) ? 1 : 0;
@@ -659,6 +665,7 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
 }
 
 cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStream_t st) {
+    if (L.v3 == 3) return conv_t128_launch(L, batch, num_sms, st);
     if (L.v3) return conv_t64_launch(L, L.wgt, batch, num_sms, st);
     // one-time kernel attributes; a function-local static initialiser is thread-safe (contexts on several host
     // threads launch through here concurrently)

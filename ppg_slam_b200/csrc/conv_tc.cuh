@@ -72,7 +72,9 @@ struct ConvLayer {
     int halo_pitch;     // pixels per halo row in shared memory (= box_w)
     int flags;          // conv_tc2_kernel flags: bit 0 = interleaved tile pairs
     // v3 ("transposed") kernel, conv_t64.cu: 3x3, Cin = Cout = 64, weights as the A operand in tensor memory
-    int v3;             // 1 = transposed kernel, 2 = transposed kernel with conv1a computed by its producer warps
+    int v3;             // 1 = transposed kernel, 2 = transposed kernel with conv1a computed by its producer warps,
+                        // 3 = transposed kernel for Cin = 128 (conv_t128.cu)
+    int t_tw, t_th, t_ws;  // v3 == 3: output tile and weight ring stages chosen by conv_t128_plan
     const __half* wgt;  // [tap][Cout][Cin] fp16 (the transposed kernel loads its A operand from here)
     const uint8_t* gray;            // v3 == 2: the u8 frames and conv1a's fp32 weights [64][9] / bias [64]
     const float *w1a, *b1a;
@@ -91,6 +93,10 @@ cudaError_t conv_tc_launch(const ConvLayer& L, int batch, int num_sms, cudaStrea
 bool conv_t64_applies(int cin, int cout_padded, int taps, int mode);
 void conv_t64_plan(ConvLayer& L, int maxB, int H, int W);
 cudaError_t conv_t64_launch(const ConvLayer& L, const __half* wgt, int batch, int num_sms, cudaStream_t st);
+// Transposed kernel for Cin = 128 (conv_t128.cu); its weight tensor map has boxes of 128 rows.
+bool conv_t128_applies(int cin, int cout_padded, int taps, int mode);
+void conv_t128_plan(ConvLayer& L, int maxB, int H, int W, int num_sms);
+cudaError_t conv_t128_launch(const ConvLayer& L, int batch, int num_sms, cudaStream_t st);
 // conv1b only (the layer whose input is conv1a's output): compute conv1a inside the kernel, see conv_t64.cu
 void conv_t64_fuse_conv1a(ConvLayer& L, const uint8_t* gray, const float* w1a, const float* b1a);
 
