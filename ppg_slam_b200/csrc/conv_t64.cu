@@ -91,7 +91,7 @@ conv_t64_kernel(const __grid_constant__ CUtensorMap mapA, const __half* __restri
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&tfull[a], 1);
-            ptx::mbar_init(&tempty[a], 4);
+            ptx::mbar_init(&tempty[a], p.mode == EPI_F16_POOL ? 4 : 8);  // EPI_F16: both groups drain every tile
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&mapA);
@@ -176,18 +176,23 @@ conv_t64_kernel(const __grid_constant__ CUtensorMap mapA, const __half* __restri
             __syncwarp();
         }
     } else {
-        // ===================== epilogue: group grp drains accumulator grp (every second tile) =====================
+        // ===================== epilogue =====================
+        // pooled layers: group grp drains accumulator grp (every second tile);
+        // EPI_F16 (four times the values to add, convert and store): BOTH groups drain every tile, group grp the image rows
+        // 2 grp, 2 grp + 1 -- with one group per tile the ~1150 instructions of a warp per tile took longer than the two
+        // tile periods it has (ncu: tensor pipe 56 % active, 0.277 ms for conv2a)
         const int grp = (warp - 2) >> 2;
         const float bias = cb.v[ch];
-        const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + T_ACC0 + (uint32_t)grp * T_N;
+        const uint32_t tq0 = tmem_base + ((uint32_t)(q * 32) << 16) + T_ACC0;
         __half* const outp = reinterpret_cast<__half*>(p.out);
-        for (int it = grp; it < my_tiles; it += 2) {
-            int n, y0, x0;
-            decode(blockIdx.x + it * gridDim.x, n, y0, x0);
-            ptx::mbar_wait(&tfull[grp], (it >> 1) & 1);
-            ptx::tc_fence_after();
-            if (p.mode == EPI_F16_POOL) {
-                const int Ho = p.H >> 1, Wo = p.W >> 1;
+        if (p.mode == EPI_F16_POOL) {
+            const uint32_t tq = tq0 + (uint32_t)grp * T_N;
+            const int Ho = p.H >> 1, Wo = p.W >> 1;
+            for (int it = grp; it < my_tiles; it += 2) {
+                int n, y0, x0;
+                decode(blockIdx.x + it * gridDim.x, n, y0, x0);
+                ptx::mbar_wait(&tfull[grp], (it >> 1) & 1);
+                ptx::tc_fence_after();
 #pragma unroll
                 for (int rp = 0; rp < T_TH / 2; rp++) {
                     // two image rows = 80 consecutive accumulator columns
@@ -218,45 +223,53 @@ conv_t64_kernel(const __grid_constant__ CUtensorMap mapA, const __half* __restri
                             *reinterpret_cast<uint16_t*>(orow + (size_t)wdx * 64) = half_bits(m);
                     }
                 }
-            } else {  // EPI_F16
-                const int odd = lane & 1;
-#pragma unroll 1
-                for (int rp = 0; rp < T_TH / 2; rp++) {
-                    uint32_t ra[64], rb[16];
-                    ptx::tmem_ld64(tq + rp * 2 * T_HW, ra);
-                    ptx::tmem_ld16(tq + rp * 2 * T_HW + 64, rb);
-                    ptx::tmem_ld_wait();
-                    auto V = [&](int i) { return __uint_as_float(i < 64 ? ra[i] : rb[(i < 80 ? i : 79) - 64]); };
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tempty[grp]);
+            }
+        } else {  // EPI_F16
+            const int odd = lane & 1;
+            for (int it = 0; it < my_tiles; it++) {
+                int n, y0, x0;
+                decode(blockIdx.x + it * gridDim.x, n, y0, x0);
+                const int acc = it & 1;
+                ptx::mbar_wait(&tfull[acc], (it >> 1) & 1);
+                ptx::tc_fence_after();
+                const uint32_t tq = tq0 + (uint32_t)acc * T_N + (uint32_t)(grp * 2 * T_HW);
+                uint32_t ra[64], rb[16];
+                ptx::tmem_ld64(tq, ra);
+                ptx::tmem_ld16(tq + 64, rb);
+                ptx::tmem_ld_wait();
+                auto V = [&](int i) { return __uint_as_float(i < 64 ? ra[i] : rb[(i < 80 ? i : 79) - 64]); };
 #pragma unroll
-                    for (int rr = 0; rr < 2; rr++) {
-                        const int y = y0 + 2 * rp + rr;
-                        // the lane pair (r, r ^ 1) holds channels (c, c + 1) of the same two pixels: one exchange lets the
-                        // even lane store both channels of the first pixel and the odd lane both of the second (4-byte
-                        // stores, 8 lanes = one 32-byte sector per pixel)
-                        __half* orow = outp + ((size_t)(n * p.H + y) * p.W + x0) * 64 + (ch & ~1);
+                for (int rr = 0; rr < 2; rr++) {
+                    const int y = y0 + 2 * grp + rr;
+                    // the lane pair (r, r ^ 1) holds channels (c, c + 1) of the same two pixels: one exchange lets the
+                    // even lane store both channels of the first pixel and the odd lane both of the second (4-byte
+                    // stores, 8 lanes = one 32-byte sector per pixel)
+                    __half* orow = outp + ((size_t)(n * p.H + y) * p.W + x0) * 64 + (ch & ~1);
 #pragma unroll
-                        for (int i = 0; i < T_HW / 4; i++) {
-                            const int b = rr * T_HW + 4 * i;
-                            const float k0 = hi ? V(b + 3) : V(b), k1 = hi ? V(b + 4) : V(b + 1);
-                            const float s0 = hi ? V(b + 1) : V(b + 2), s1 = hi ? V(b + 2) : V(b + 3);
-                            float o0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16) + bias;
-                            float o1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16) + bias;
-                            if (p.relu) {
-                                o0 = fmaxf(o0, 0.f);
-                                o1 = fmaxf(o1, 0.f);
-                            }
-                            const float got = __shfl_xor_sync(0xffffffffu, odd ? o0 : o1, 1);
-                            const __half2 h2 = odd ? __floats2half2_rn(got, o1) : __floats2half2_rn(o0, got);
-                            const int ox = 4 * i + 2 * hi + odd;
-                            if (ox < T_TW && x0 + ox < p.W && y < p.H)
-                                *reinterpret_cast<__half2*>(orow + (size_t)ox * 64) = h2;
+                    for (int i = 0; i < T_HW / 4; i++) {
+                        const int b = rr * T_HW + 4 * i;
+                        const float k0 = hi ? V(b + 3) : V(b), k1 = hi ? V(b + 4) : V(b + 1);
+                        const float s0 = hi ? V(b + 1) : V(b + 2), s1 = hi ? V(b + 2) : V(b + 3);
+                        float o0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16) + bias;
+                        float o1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16) + bias;
+                        if (p.relu) {
+                            o0 = fmaxf(o0, 0.f);
+                            o1 = fmaxf(o1, 0.f);
                         }
+                        const float got = __shfl_xor_sync(0xffffffffu, odd ? o0 : o1, 1);
+                        const __half2 h2 = odd ? __floats2half2_rn(got, o1) : __floats2half2_rn(o0, got);
+                        const int ox = 4 * i + 2 * hi + odd;
+                        if (ox < T_TW && x0 + ox < p.W && y < p.H)
+                            *reinterpret_cast<__half2*>(orow + (size_t)ox * 64) = h2;
                     }
                 }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty[grp]);
         }
     }
     ptx::tc_fence_before();

@@ -604,20 +604,19 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
     L.v3 = 0;
     L.wgt = nullptr;
     // Kernel choice.  PPG_CONV_KERNEL (A/B comparison only; the settings differ in the fp32 summation order of the taps, i.e. in the last bits):
-    //   unset / 6: as 5, and the 3x3 layers with Cin = 128 run on the transposed kernel of conv_t128.cu instead of the
-    //      generic one;
+    //   unset / 7: as 6, and conv2a (64 -> 64, no pool) runs on the transposed kernel too: with both epilogue groups
+    //      draining every tile it takes 0.21-0.23 ms per 32 frames against 0.24 ms on the halo kernel;
+    //   6: as 5, and the 3x3 layers with Cin = 128 run on the transposed kernel of conv_t128.cu instead of the generic one;
     //   5: as 3, and conv1a is computed inside conv1b's producer warps (api.cu, conv_t64.cu);
     //   3: transposed kernel (conv_t64.cu) for the pooled 3x3 64 -> 64 layers (conv1b, conv2b: 90 % / 87 % of the
-    //      tensor pipe), halo kernel for the other Cin = 64 layers.  conv2a (no pool: four times the outputs to add,
-    //      convert and store per tile) is epilogue-bound on the transposed kernel -- 0.266 ms against 0.237 ms on the halo
-    //      kernel per 32 frames -- so it stays on the halo kernel;
+    //      tensor pipe), halo kernel for the other Cin = 64 layers;
     //   4: transposed kernel for conv2a too;  2: halo kernel for every Cin = 64 layer (the round-1 configuration);
     //   1: generic kernel everywhere.
     // Measured on B200 (tools/conv_variants.py): UMMA applies the 128-byte swizzle XOR on absolute shared-memory
     // address bits, so a descriptor may start at any 128-byte row of a swizzled tile with base_offset = 0.
-    int kmode = 6;
+    int kmode = 7;
     if (const char* e = getenv("PPG_CONV_KERNEL")) kmode = atoi(e);
-    if (kmode >= 3 && conv_t64_applies(cin, cout_padded, taps, mode) && (mode == EPI_F16_POOL || kmode == 4)) {
+    if (kmode >= 3 && conv_t64_applies(cin, cout_padded, taps, mode) && (mode == EPI_F16_POOL || kmode == 4 || kmode >= 7)) {
         conv_t64_plan(L, maxB, H, W);
         return;
     }

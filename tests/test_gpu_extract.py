@@ -37,8 +37,9 @@ def test_conv_selftest(ex_euroc):
         assert d <= 2e-2 * max(1.0, r), "layer %s: tcgen05 vs CUDA-core conv differ by %g (ref max %g)" % (name, d, r)
 
 
-@pytest.mark.parametrize("kernel", ["1", "2", "3", "4", "5"],
-                         ids=["generic", "halo", "transposed-unfused", "transposed-everywhere", "generic-for-cin128"])
+@pytest.mark.parametrize("kernel", ["1", "2", "3", "4", "5", "6"],
+                         ids=["generic", "halo", "transposed-unfused", "transposed-everywhere", "generic-for-cin128",
+                              "halo-for-conv2a"])
 def test_conv_selftest_other_kernel_choices(kernel, monkeypatch):
     """PPG_CONV_KERNEL routes the Cin = 64 layers to the other tcgen05 kernels (A/B switch of conv_tc_plan): every choice
     must give the same layer outputs -- in particular the non-pooled epilogue of the transposed kernel (conv2a under "4"),
@@ -62,7 +63,7 @@ def test_fused_conv1a_is_bit_identical_to_the_separate_kernel(monkeypatch):
     from ppg_slam_b200 import capi
     frames = [synth.frame(s, 752, 480) for s in (4, 5, 6)]
     out = {}
-    for mode in ("5", "3"):
+    for mode in ("5", "3"):  # both run conv2a on the halo kernel and the Cin = 128 layers on the generic one
         monkeypatch.setenv("PPG_CONV_KERNEL", mode)
         e = capi.Extractor(cameras.EUROC, max_batch=3)
         try:
