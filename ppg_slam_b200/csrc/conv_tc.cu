@@ -604,9 +604,13 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
     L.v3 = 0;
     L.wgt = nullptr;
     // Kernel choice.  PPG_CONV_KERNEL (A/B comparison only; the settings differ in the fp32 summation order of the taps, i.e. in the last bits):
-    //   unset / 7: as 6, and conv2a (64 -> 64, no pool) runs on the transposed kernel too: with both epilogue groups
+    //   8: as 7, and conv3a (64 -> 128) and edge block 0 (128 -> 256 + pixel shuffle) run on conv_t128.cu as well --
+    //      correct but not faster (0.17 / 0.093 ms against 0.10 / 0.092 ms per 32 frames: with 36 instructions per tile the
+    //      epilogue and the weight ring dominate);
+    //   unset / 7: as 6, convDb (1x1 256 -> 256, fp32 output: 0.086 against 0.105 ms, its stores are 128 contiguous bytes
+    //      per warp instead of 32 scattered 16-byte pieces) on conv_t128.cu, and conv2a (64 -> 64, no pool) runs on the transposed kernel too: with both epilogue groups
     //      draining every tile it takes 0.21-0.23 ms per 32 frames against 0.24 ms on the halo kernel;
-    //   6: as 5, and the 3x3 layers with Cin = 128 run on the transposed kernel of conv_t128.cu instead of the generic one;
+    //   6: as 5, and the 3x3 layers with Cin = 128 (plain or pooled fp16 output) run on the transposed kernel of conv_t128.cu instead of the generic one;
     //   5: as 3, and conv1a is computed inside conv1b's producer warps (api.cu, conv_t64.cu);
     //   3: transposed kernel (conv_t64.cu) for the pooled 3x3 64 -> 64 layers (conv1b, conv2b: 90 % / 87 % of the
     //      tensor pipe), halo kernel for the other Cin = 64 layers;
@@ -620,7 +624,9 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
         conv_t64_plan(L, maxB, H, W);
         return;
     }
-    if (kmode >= 6 && conv_t128_applies(cin, cout_padded, taps, mode)) {
+    if (kmode >= 6 && conv_t128_applies(cin, cout_padded, taps, mode) &&
+        (kmode >= 8 || (taps == 9 && cin == 128 && (mode == EPI_F16 || mode == EPI_F16_POOL)) ||
+         (kmode >= 7 && taps == 1 && mode == EPI_F32))) {
         conv_t128_plan(L, maxB, H, W, 148);
         return;
     }

@@ -37,9 +37,9 @@ def test_conv_selftest(ex_euroc):
         assert d <= 2e-2 * max(1.0, r), "layer %s: tcgen05 vs CUDA-core conv differ by %g (ref max %g)" % (name, d, r)
 
 
-@pytest.mark.parametrize("kernel", ["1", "2", "3", "4", "5", "6"],
+@pytest.mark.parametrize("kernel", ["1", "2", "3", "4", "5", "6", "8"],
                          ids=["generic", "halo", "transposed-unfused", "transposed-everywhere", "generic-for-cin128",
-                              "halo-for-conv2a"])
+                              "halo-for-conv2a", "t128-for-every-layer-it-can-run"])
 def test_conv_selftest_other_kernel_choices(kernel, monkeypatch):
     """PPG_CONV_KERNEL routes the Cin = 64 layers to the other tcgen05 kernels (A/B switch of conv_tc_plan): every choice
     must give the same layer outputs -- in particular the non-pooled epilogue of the transposed kernel (conv2a under "4"),
