@@ -38,6 +38,7 @@ MAP_ROWS = 8192
 TH, RATIO = 10.0, 0.8
 GFLOP_PER_FRAME = 66.633          # conv MACs x 2 at 752x480
 CONV1B_GFLOP_PER_FRAME = 2 * 13.307  # 64->64 3x3 at full resolution
+CONV1A_GFLOP_PER_FRAME = 2 * 0.208   # 1->64 3x3 at full resolution
 
 
 def _peaks():
@@ -493,14 +494,15 @@ def run_b200(args, rank, local_rank, world):
         roof = None
         scale = cam.width * cam.height / (752.0 * 480.0)  # conv FLOPs scale with the pixel count
         if conv1b_ms:
-            ach = CONV1B_GFLOP_PER_FRAME * scale * B / conv1b_ms  # GFLOP / ms = TFLOP/s
-            traffic = None
             fused = "conv1a" not in sd  # conv1a computed by conv1b's producer warps: no separate stage
+            # GFLOP / ms = TFLOP/s; the fused kernel also does conv1a's 0.42 GFLOP per frame (0.21 GMAC)
+            ach = (CONV1B_GFLOP_PER_FRAME + (CONV1A_GFLOP_PER_FRAME if fused else 0.0)) * scale * B / conv1b_ms
+            traffic = None
             tp = os.path.join(ROOT, "profiles", "conv1b_traffic.json")
             if os.path.exists(tp):
                 traffic = json.load(open(tp)).get("fused_dram_bytes_per_launch" if fused else "dram_bytes_per_launch")
             kname = ("conv_t64_fused_kernel[conv1a 1->64 3x3 + ReLU computed in the producer warps, conv1b 64->64 3x3 "
-                     "@%dx%d + ReLU + 2x2 pool; only conv1b's FLOPs are counted]" if fused else
+                     "@%dx%d + ReLU + 2x2 pool; algorithmic FLOPs of both layers]" if fused else
                      "conv_t64_kernel[conv1b 64->64 3x3 @%dx%d + ReLU + 2x2 pool]") % (cam.width, cam.height)
             roof = {"bound": "tensor",
                     "kernel": kname,
@@ -533,8 +535,10 @@ def run_b200(args, rank, local_rank, world):
                                     "frac": gbs / hbm_peak, "ms_per_launch": t_ms, "algorithmic_bytes_per_frame": 6 * P}
         hbm("desc_kernel", "post.descriptors", nkp * 5 * 1024)
         hbm("conv1a_tc_kernel", "conv1a", cam.width * cam.height * (1 + 128))
+        # convDb (1x1 256 -> 256): reads the fp16 map, writes the fp32 dense descriptors; 0.37 GMAC per frame is nothing
+        hbm("conv_t128_kernel[convDb]", "convDb", (cam.width // 8) * (cam.height // 8) * 256 * (2 + 4))
         if conv_ms:
-            tfl = (GFLOP_PER_FRAME - 0.84) * scale * B / conv_ms
+            tfl = (GFLOP_PER_FRAME - 0.84 + (CONV1A_GFLOP_PER_FRAME if "conv1a" not in sd else 0.0)) * scale * B / conv_ms
             more["all_tensor_core_convolutions"] = {"bound": "tensor", "achieved": tfl, "peak": tf_peak,
                                                     "unit": "TFLOP/s", "frac": tfl / tf_peak, "ms_per_step": conv_ms}
         if assoc_roof:

@@ -605,8 +605,8 @@ void conv_tc_plan(ConvLayer& L, int maxB, int H, int W, int cin, int cout_padded
     L.wgt = nullptr;
     // Kernel choice.  PPG_CONV_KERNEL (A/B comparison only; the settings differ in the fp32 summation order of the taps, i.e. in the last bits):
     //   8: as 7, and conv3a (64 -> 128) and edge block 0 (128 -> 256 + pixel shuffle) run on conv_t128.cu as well --
-    //      correct but not faster (0.17 / 0.093 ms against 0.10 / 0.092 ms per 32 frames: with 36 instructions per tile the
-    //      epilogue and the weight ring dominate);
+    //      correct but not faster (0.12 / 0.125 ms against 0.10 / 0.095 ms per 32 frames: with 36 instructions per tile the
+    //      epilogue -- twice the two-byte stores for the pixel shuffle -- is no longer hidden behind the tensor core);
     //   unset / 7: as 6, convDb (1x1 256 -> 256, fp32 output: 0.086 against 0.105 ms, its stores are 128 contiguous bytes
     //      per warp instead of 32 scattered 16-byte pieces) on conv_t128.cu, and conv2a (64 -> 64, no pool) runs on the transposed kernel too: with both epilogue groups
     //      draining every tile it takes 0.21-0.23 ms per 32 frames against 0.24 ms on the halo kernel;
