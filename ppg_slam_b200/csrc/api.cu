@@ -487,7 +487,11 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
     const size_t HW = (size_t)H * W;
     PPG_CUDA(c, dalloc(&c->gray, B * HW));
     PPG_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_gray), B * HW));
-    PPG_CUDA(c, dalloc(&c->a1, B * HW * 64));
+    // conv1a's full-resolution 64-channel map (46 MB per EuRoC frame) is not materialised when conv1b computes it on
+    // the fly (the default, conv_t64.cu): one frame's worth is kept for ppg_selftest_conv
+    const char* kenv = getenv("PPG_CONV_KERNEL");
+    const bool fuse_conv1a = !kenv || atoi(kenv) >= 5;
+    PPG_CUDA(c, dalloc(&c->a1, (fuse_conv1a ? (size_t)1 : (size_t)B) * HW * 64));
     PPG_CUDA(c, dalloc(&c->a2, B * HW / 4 * 64));
     PPG_CUDA(c, dalloc(&c->a3, B * HW / 4 * 64));
     PPG_CUDA(c, dalloc(&c->a4, B * HW / 16 * 64));
@@ -521,8 +525,8 @@ int ppg_create(const ppg_config* cfg, ppg_ctx** out) {
     ADD("conv1b", "backbone.conv1b", "", c->a1, H, W, EPI_F16_POOL, 1, c->a2, 64, 0)
     {
         // conv1a runs inside conv1b's producer warps (conv_t64.cu) unless PPG_CONV_KERNEL asks for an older arrangement
-        const char* e = getenv("PPG_CONV_KERNEL");
-        if ((!e || atoi(e) >= 5) && c->tc.back().L.v3 == 1) conv_t64_fuse_conv1a(c->tc.back().L, c->gray, c->w1a, c->b1a);
+        if (fuse_conv1a && c->tc.back().L.v3 == 1) conv_t64_fuse_conv1a(c->tc.back().L, c->gray, c->w1a, c->b1a);
+        if (fuse_conv1a && c->tc.back().L.v3 != 2) return set_err(c, PPG_ERR_ARG, "conv1b cannot run the fused kernel");
     }
     ADD("conv2a", "backbone.conv2a", "", c->a2, H / 2, W / 2, EPI_F16, 1, c->a3, 64, 0)
     ADD("conv2b", "backbone.conv2b", "", c->a3, H / 2, W / 2, EPI_F16_POOL, 1, c->a4, 64, 0)
