@@ -516,16 +516,82 @@ inline int search_for_initialization(ppg_ctx* ctx, Frame& F1, Frame& F2, std::ve
     return out.nmatches;
 }
 
+// Matcher::SearchForTriangulation (matching/src/Matcher.cpp:767-885) whole on the GPU (ppg_search_for_triangulation)
+// for a pinhole camera.  What depends on the two poses only -- the epipole and F12 -- is computed here with the
+// reference's own classes and expressions (:776-788, sensors/src/Pinhole.cpp:101-104); the per-pair work (descriptor
+// distances under the same vocabulary node, epipole exclusion, epipolar distance) runs on the device.
+inline int search_for_triangulation(ppg_ctx* ctx, GeometricCamera* cam, KeyFrame* pKF1, KeyFrame* pKF2,
+                                    std::vector<std::pair<size_t, size_t>>& vMatchedPairs, float th_low) {
+    SE3f T1w = pKF1->GetPose();
+    SE3f T2w = pKF2->GetPose();
+    SE3f Tw2 = pKF2->GetPoseInverse();
+    Eigen::Vector3f Cw = pKF1->GetCameraCenter();
+    Eigen::Vector3f C2 = T2w * Cw;
+    Eigen::Vector2f ep = cam->project(C2);
+    SE3f T12 = T1w * Tw2;
+    Eigen::Matrix3f R12 = T12.rotationMatrix();
+    Eigen::Vector3f t12 = T12.translation();
+    Eigen::Matrix3f t12x = SO3f::hat(t12);
+    Eigen::Matrix3f K1 = cam->toK_();
+    Eigen::Matrix3f K2 = cam->toK_();
+    Eigen::Matrix3f F12 = K1.transpose().inverse() * t12x * R12 * K2.inverse();
+
+    const int n1 = pKF1->N, n2 = pKF2->N;
+    vMatchedPairs.clear();
+    if (n1 <= 0 || n2 <= 0) return 0;
+    std::vector<float> pos1(2 * (size_t)n1), pos2(2 * (size_t)n2);
+    std::vector<int32_t> node1(n1, -1), node2(n2, -1), m12(n1, -1);
+    std::vector<uint8_t> mp1(n1), mp2(n2);
+    for (int i = 0; i < n1; i++) {
+        pos1[2 * i] = pKF1->mvKeysUn[i].mPos[0];
+        pos1[2 * i + 1] = pKF1->mvKeysUn[i].mPos[1];
+        mp1[i] = pKF1->GetMapPoint(i) ? 1 : 0;
+    }
+    for (int i = 0; i < n2; i++) {
+        pos2[2 * i] = pKF2->mvKeysUn[i].mPos[0];
+        pos2[2 * i + 1] = pKF2->mvKeysUn[i].mPos[1];
+        mp2[i] = pKF2->GetMapPoint(i) ? 1 : 0;
+    }
+    for (const auto& nf : pKF1->mFeatVec)
+        for (unsigned int i : nf.second) node1[i] = (int32_t)nf.first;
+    for (const auto& nf : pKF2->mFeatVec)
+        for (unsigned int i : nf.second) node2[i] = (int32_t)nf.first;
+    ppg_triangulation_match_in in{};
+    in.n1 = n1;
+    in.n2 = n2;
+    in.desc1 = pKF1->mDescriptors.ptr<float>(0);
+    in.desc2 = pKF2->mDescriptors.ptr<float>(0);
+    in.node1 = node1.data();
+    in.node2 = node2.data();
+    in.has_mp1 = mp1.data();
+    in.has_mp2 = mp2.data();
+    in.pos1 = pos1.data();
+    in.pos2 = pos2.data();
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) in.F12[3 * r + c] = F12(r, c);
+    in.epipole[0] = ep[0];
+    in.epipole[1] = ep[1];
+    in.th_low = th_low;
+    ppg_triangulation_match_out out{};
+    out.match12 = m12.data();
+    check(ppg_search_for_triangulation(ctx, &in, &out), ctx, "ppg_search_for_triangulation");
+    vMatchedPairs.reserve(out.nmatches);
+    for (int i = 0; i < n1; i++)
+        if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)m12[i]));  // :876-881
+    return out.nmatches;
+}
+
 #ifndef PPG_SHIM_NO_MATCHER_CLASS
 // Replaces class Matcher (matching/include/Matcher.h:20-64) for its callers: the same twelve signatures, constants and
-// public members.  The three matchers on the front-end path run on the GPU --
+// public members.  Four matchers run on the GPU --
 //   ExtendMapMatches          image <-> map association of MSTracking::SearchLocalPoints (system/src/Tracking.cpp:1007)
 //   SearchByBoW(KF, F)        relocalisation / reference-keyframe tracking
 //   SearchForInitialization   monocular initialisation (Tracking.cpp:525)
-// -- and the other nine (SearchByProjection x 4, SearchByBoW(KF, KF), SearchForTriangulation, SearchBySim3, Fuse x 2)
-// are the reference's own host code, inherited unchanged from ::Matcher (their window-search cores are available as
-// search_window above for callers that want them on the device; SearchForTriangulation's acceptance is the camera
-// model's virtual epipolarConstrain -- for KannalaBrandt8 a triangulation -- and stays on the host).
+//   SearchForTriangulation    new map points in LocalMapping, for the pinhole camera (its epipolar test is closed-form;
+//                             KannalaBrandt8::epipolarConstrain triangulates the pair and stays on the host)
+// -- and the other eight (SearchByProjection x 4, SearchByBoW(KF, KF), SearchBySim3, Fuse x 2) are the reference's own
+// host code, inherited unchanged from ::Matcher (their window-search cores are available as search_window above for
+// callers that want them on the device).
 // The ctx is the one the frame's PPGExtractor owns (PPGExtractor::context()).
 class Matcher : public ::Matcher {
 public:
@@ -542,12 +608,17 @@ public:
                                 std::vector<int>& vnMatches12, int windowSize = 10) {
         return search_for_initialization(mCtx, F1, F2, vbPrevMatched, vnMatches12, windowSize, mfNNratio);
     }
+    int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<std::pair<size_t, size_t>>& vMatchedPairs,
+                               const bool bCoarse = false) {
+        if (mpCamera->mnType != GeometricCamera::CAM_PINHOLE)
+            return ::Matcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bCoarse);
+        return search_for_triangulation(mCtx, mpCamera, pKF1, pKF2, vMatchedPairs, TH_LOW);
+    }
     // host-side matchers of the reference, unchanged
     using ::Matcher::Fuse;
     using ::Matcher::SearchByBoW;  // (KeyFrame*, KeyFrame*, ...); the (KeyFrame*, Frame&, ...) overload above hides the base's
     using ::Matcher::SearchByProjection;
     using ::Matcher::SearchBySim3;
-    using ::Matcher::SearchForTriangulation;
 
 private:
     ppg_ctx* mCtx;

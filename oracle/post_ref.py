@@ -348,3 +348,21 @@ def search_for_initialization(cam, desc1, prev_matched, kx2, ky2, desc2, window=
                                           _p(kx2, C.c_float), _p(ky2, C.c_float), _p(d2, C.c_float), int(window),
                                           C.c_float(ratio), C.c_float(th_low), _p(m12, C.c_int))
     return dict(nmatches=int(nm), matches12=m12[:n1], prev_matched=prev)
+
+
+def search_for_triangulation(desc1, node1, has_mp1, pos1, desc2, node2, has_mp2, pos2, F12, epipole, th_low=0.7):
+    """Matcher::SearchForTriangulation (Matcher.cpp:767-885) with the pinhole epipolar test (Pinhole.cpp:98-114).
+    F12 row-major 3x3, epipole (2,).  -> dict(nmatches, match12)."""
+    L = lib()
+    d1, d2 = f32(desc1), f32(desc2)
+    n1, n2 = len(d1), len(d2)
+    nd1, nd2 = np.ascontiguousarray(node1, np.int32), np.ascontiguousarray(node2, np.int32)
+    m1, m2 = np.ascontiguousarray(has_mp1, np.uint8), np.ascontiguousarray(has_mp2, np.uint8)
+    p1, p2 = f32(pos1), f32(pos2)
+    F, ep = f32(F12).reshape(9), f32(epipole).reshape(2)
+    m12 = np.full(max(n1, 1), -1, np.int32)
+    L.ppgo_search_for_triangulation.restype = C.c_int
+    nm = L.ppgo_search_for_triangulation(n1, _p(d1, C.c_float), _p(nd1, C.c_int), _p(m1, C.c_ubyte), _p(p1, C.c_float),
+                                         n2, _p(d2, C.c_float), _p(nd2, C.c_int), _p(m2, C.c_ubyte), _p(p2, C.c_float),
+                                         _p(F, C.c_float), _p(ep, C.c_float), C.c_float(th_low), _p(m12, C.c_int))
+    return dict(nmatches=int(nm), match12=m12[:n1])

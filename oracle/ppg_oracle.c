@@ -1315,3 +1315,57 @@ int ppgo_search_for_initialization(const ppgo_cfg *c, int n1, const float *desc1
     free(matches21);
     return nmatches;
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* Matcher::SearchForTriangulation, matching/src/Matcher.cpp:767-885, for the pinhole camera       */
+/* (epipolar test of sensors/src/Pinhole.cpp:98-114).  The FeatureVectors are given per feature:    */
+/* node[i] = the vocabulary node the feature hangs under (every feature of a DBoW3 FeatureVector    */
+/* belongs to exactly one node, its indices in ascending order), -1 = none.  The merge loop of      */
+/* :801-869 pairs the nodes present in both key frames, i.e. node1[i1] == node2[i2].                */
+/* For every feature i1 of KF1 without a map point (:812-818): over the features i2 of KF2 in the   */
+/* same node, in index order, without a map point (:831-836; vbMatched2 is never set in the         */
+/* reference, so "already matched" never fires): dist = DescriptorDistance; skip if dist > TH_LOW   */
+/* or dist > bestDist (:842, a tie replaces the earlier candidate); skip if closer than 10 px to    */
+/* the epipole (:846-847, Eigen norm of a 2-vector = sqrt(x*x + y*y)); keep if the epipolar line    */
+/* of kp1 passes within dsqr < 3.84 of kp2 (Pinhole.cpp:106-113: a, b, c, num, den in float, left   */
+/* to right, the comparison in double).  F12 (row-major) = K1^-T * [t12]x * R12 * K2^-1 and the     */
+/* epipole are the caller's (they depend on the poses only, :776-788, Pinhole.cpp:101-104).         */
+/* match12[i1] = i2 or -1 -> nmatches.                                                               */
+/* ------------------------------------------------------------------------------------------- */
+int ppgo_search_for_triangulation(int n1, const float *desc1, const int *node1, const unsigned char *has_mp1,
+                                  const float *pos1, int n2, const float *desc2, const int *node2,
+                                  const unsigned char *has_mp2, const float *pos2, const float *F12, const float *ep,
+                                  float th_low, int *match12) {
+    int nmatches = 0;
+    for (int i1 = 0; i1 < n1; i1++) {
+        match12[i1] = -1;
+        if (has_mp1[i1] || node1[i1] < 0) continue;
+        const float x1 = pos1[2 * i1], y1 = pos1[2 * i1 + 1];
+        const float a = x1 * F12[0] + y1 * F12[3] + F12[6];
+        const float b = x1 * F12[1] + y1 * F12[4] + F12[7];
+        const float c = x1 * F12[2] + y1 * F12[5] + F12[8];
+        const float den = a * a + b * b;
+        float bestDist = th_low;
+        int bestIdx2 = -1;
+        for (int i2 = 0; i2 < n2; i2++) {
+            if (node2[i2] != node1[i1] || has_mp2[i2]) continue;
+            const float dist = ppgo_descriptor_distance(desc1 + (size_t)i1 * 256, desc2 + (size_t)i2 * 256, 256);
+            if (dist > th_low || dist > bestDist) continue;
+            const float x2 = pos2[2 * i2], y2 = pos2[2 * i2 + 1];
+            const float ex = ep[0] - x2, ey = ep[1] - y2;
+            if (sqrtf(ex * ex + ey * ey) < 10.0f) continue;
+            if (den == 0) continue;
+            const float num = a * x2 + b * y2 + c;
+            const float dsqr = num * num / den;
+            if ((double)dsqr < 3.84) {
+                bestIdx2 = i2;
+                bestDist = dist;
+            }
+        }
+        if (bestIdx2 >= 0) {
+            match12[i1] = bestIdx2;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}

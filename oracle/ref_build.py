@@ -1,6 +1,7 @@
 """Build recipe of the reference-pinning harness (oracle/_ref/libppg_ref_*.so).  TEST INFRASTRUCTURE ONLY.
 
-Compiles the reference's OWN C++ sources for the hot path, from where they lie under /root/reference, against
+Compiles the reference's OWN C++ sources for the hot path (PPGExtractor.cpp, PPGGraph.cpp, GeometricCamera.cpp, Pinhole.cpp,
+Matcher.cpp, MapPoint.cpp, Frame.cpp), from where they lie under /root/reference, against
   * the real LibTorch (CPU) of the Python environment, and
   * the stand-ins of oracle/ref_standins/ for OpenCV, Eigen and DBoW3 (none of which is installed here; the stand-ins
     say which of their arithmetic is an assumption),
@@ -51,7 +52,8 @@ def build(force=False, verbose=False):
     os.makedirs(OUT_DIR, exist_ok=True)
     inc, lib, abi = _torch_flags()
     std = os.path.join(HERE, "ref_standins")
-    deps = [os.path.join(dp, f) for dp, _, fs in os.walk(std) for f in fs] + [os.path.join(HERE, "ppg_oracle.c")]
+    deps = [os.path.join(dp, f) for dp, _, fs in os.walk(std) for f in fs] + [os.path.join(HERE, "ppg_oracle.c")] + \
+           [os.path.join(HERE, "ref_tu", f) for f in os.listdir(os.path.join(HERE, "ref_tu")) if f.endswith(".hpp")]
     common = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fvisibility=hidden",
               "-ffunction-sections", "-fdata-sections", "-w", "-DNDEBUG_OFF",
               '-DREF_FILE(x)=<' + REF_ROOT + '/x>', "-I" + std] + \

@@ -229,6 +229,26 @@ def search_for_initialization(cam, kx1, ky1, desc1, prev_matched, kx2, ky2, desc
     return dict(nmatches=int(nm), matches12=m12[:n1], prev_matched=prev)
 
 
+def search_for_triangulation(cam, R1, t1, R2, t2, pos1, desc1, node1, has_mp1, pos2, desc2, node2, has_mp2):
+    """The reference's own Matcher::SearchForTriangulation with its own Pinhole camera on two KeyFrames rebuilt from the
+    flat arrays (poses = world -> camera).  -> dict(nmatches, match12, F12 (3x3), epipole (2,)): F12 and the epipole are
+    what the reference's classes compute from the poses (Matcher.cpp:776-788, Pinhole.cpp:101-104)."""
+    lib = _lib("matcher")
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    p1, d1, p2, d2 = f32(pos1), f32(desc1), f32(pos2), f32(desc2)
+    n1, n2 = len(p1), len(p2)
+    m12 = np.full(max(n1, 1), -1, np.int32)
+    F = np.zeros(9, np.float32)
+    ep = np.zeros(2, np.float32)
+    nm = lib.ref_search_for_triangulation(_p(_cam_params(cam)), cam.width, cam.height, _p(f32(R1).reshape(9)), _p(f32(t1)),
+                                          _p(f32(R2).reshape(9)), _p(f32(t2)), n1, _p(p1), _p(d1), _p(i32(node1), C.c_int),
+                                          _p(u8(has_mp1), C.c_ubyte), n2, _p(p2), _p(d2), _p(i32(node2), C.c_int),
+                                          _p(u8(has_mp2), C.c_ubyte), _p(m12, C.c_int), _p(F), _p(ep))
+    return dict(nmatches=int(nm), match12=m12[:n1], F12=F.reshape(3, 3), epipole=ep)
+
+
 # ---------------------------------------------------------------- include/ppg_shim.hpp executed on the reference's objects
 def shim_available():
     return os.path.exists(ref_build.lib_path("shim")) and os.path.exists(ref_build.lib_path("matcher"))
@@ -288,3 +308,25 @@ def shim_init_both(cam, kx1, ky1, desc1, prev_matched, kx2, ky2, desc2, window, 
     if rc != 0:
         raise RuntimeError("shim_init_both failed (see stderr)")
     return tuple(dict(nmatches=int(nm[k]), matches12=m12[k, :n1], prev_matched=pv[k, :n1]) for k in (0, 1))
+
+
+def shim_triangulation_both(cam, R1, t1, R2, t2, pos1, desc1, node1, has_mp1, pos2, desc2, node2, has_mp2):
+    """The same two key frames through the reference's Matcher::SearchForTriangulation (host, its own Pinhole camera) and
+    through ppg_shim::Matcher::SearchForTriangulation (poses -> F12 / epipole with the reference's classes -> C ABI ->
+    GPU).  -> (reference result, shim result)."""
+    lib = _lib("shim")
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    p1, d1, p2, d2 = f32(pos1), f32(desc1), f32(pos2), f32(desc2)
+    n1, n2 = len(p1), len(p2)
+    nm = np.zeros(2, np.int32)
+    m12 = np.zeros((2, max(n1, 1)), np.int32)
+    rc = lib.shim_triangulation_both(_p(_cam_params(cam)), cam.width, cam.height, _weights_dir().encode(),
+                                     _p(f32(R1).reshape(9)), _p(f32(t1)), _p(f32(R2).reshape(9)), _p(f32(t2)), n1, _p(p1),
+                                     _p(d1), _p(i32(node1), C.c_int), _p(u8(has_mp1), C.c_ubyte), n2, _p(p2), _p(d2),
+                                     _p(i32(node2), C.c_int), _p(u8(has_mp2), C.c_ubyte), _p(nm, C.c_int),
+                                     _p(m12, C.c_int))
+    if rc != 0:
+        raise RuntimeError("shim_triangulation_both failed (rc %d, see stderr)" % rc)
+    return tuple(dict(nmatches=int(nm[k]), match12=m12[k, :n1]) for k in (0, 1))

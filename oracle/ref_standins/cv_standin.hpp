@@ -210,6 +210,29 @@ class Mat {
     }
 };
 
+// cv::Mat_<float>(r, c) << a, b, ...  (sensors/src/Pinhole.cpp:70, :76): row-major fill
+template <typename T>
+class Mat_ : public Mat {
+   public:
+    Mat_(int r, int c) : Mat(r, c, sizeof(T) == 8 ? CV_64F : CV_32F) {}
+};
+template <typename T>
+struct MatCommaInit {
+    Mat m;
+    int k;
+    MatCommaInit operator,(T v) {
+        m.set(k / m.cols, k % m.cols, (double)v);
+        return MatCommaInit{m, k + 1};
+    }
+    operator Mat() const { return m; }
+};
+template <typename T>
+inline MatCommaInit<T> operator<<(const Mat_<T>& m, T v) {
+    Mat mm = m;
+    mm.set(0, 0, (double)v);
+    return MatCommaInit<T>{mm, 1};
+}
+
 // camera matrix K (3x3 CV_32F) / distortion D (4x1 CV_32F) -> the plain arrays ppg_oracle.c takes
 inline void kd_arrays(const Mat& K, const Mat& D, float* k9, float* d4) {
     for (int i = 0; i < 3; i++)

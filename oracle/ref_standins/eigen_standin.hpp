@@ -266,7 +266,33 @@ class Matrix {
         for (int i = 0; i < N; i++) r[i] = (*this)[i];
         return r;
     }
-    Matrix inverse() const;  // not on the path: declared only
+    // 3x3 only (sensors/src/Pinhole.cpp:103: K.transpose().inverse(), K.inverse()).  Written as Eigen 3.3 / 3.4 evaluate
+    // a fixed 3x3 inverse (Eigen/src/LU/InverseImpl.h, compute_inverse<.., 3>): cofactor(i, j) = m(i1, j1) * m(i2, j2) -
+    // m(i1, j2) * m(i2, j1) with i1 = (i + 1) % 3, i2 = (i + 2) % 3; det = (cof(0,0) * m(0,0) + cof(1,0) * m(1,0)) +
+    // cof(2,0) * m(2,0); every entry = cofactor(j, i) * (1 / det).  ASSUMPTION about Eigen's arithmetic, like the rest
+    // of this file; the product path never inverts a matrix itself (the caller hands it F12).
+    Matrix inverse() const {
+        static_assert(R == 3 && C == 3, "stand-in: only the fixed 3x3 inverse is provided");
+        const Matrix& m = *this;
+        auto cof = [&](int i, int j) {
+            const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            return m(i1, j1) * m(i2, j2) - m(i1, j2) * m(i2, j1);
+        };
+        const S c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+        const S det = (c0 * m(0, 0) + c1 * m(1, 0)) + c2 * m(2, 0);
+        const S invdet = S(1) / det;
+        Matrix r;
+        r(0, 0) = c0 * invdet;
+        r(0, 1) = c1 * invdet;
+        r(0, 2) = c2 * invdet;
+        r(1, 0) = cof(0, 1) * invdet;
+        r(1, 1) = cof(1, 1) * invdet;
+        r(1, 2) = cof(2, 1) * invdet;
+        r(2, 0) = cof(0, 2) * invdet;
+        r(2, 1) = cof(1, 2) * invdet;
+        r(2, 2) = cof(2, 2) * invdet;
+        return r;
+    }
     S determinant() const;
     S trace() const {
         S t = S();

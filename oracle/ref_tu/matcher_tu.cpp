@@ -1,6 +1,7 @@
 // Reference-pinning harness, part 2: the reference's OWN matcher and map sources compiled as they lie under
 // /root/reference (matching/src/Matcher.cpp, feature/src/MapPoint.cpp, map/src/Frame.cpp, feature/src/PPGGraph.cpp,
-// sensors/src/GeometricCamera.cpp) against the stand-ins of oracle/ref_standins.  TEST INFRASTRUCTURE ONLY.
+// sensors/src/GeometricCamera.cpp, sensors/src/Pinhole.cpp) against the stand-ins of oracle/ref_standins.
+// TEST INFRASTRUCTURE ONLY.
 //
 // ref_extend_map_matches builds the pointer graph the reference works on -- MapPoint / MapEdge / Frame / KeyPointEx /
 // KeyEdge OBJECTS -- from the flat arrays the C ABI and the oracle use (the inverse of the flattening in
@@ -40,6 +41,7 @@
 #include REF_FILE(map/src/Frame.cpp)
 #include REF_FILE(feature/src/PPGGraph.cpp)
 #include REF_FILE(sensors/src/GeometricCamera.cpp)
+#include REF_FILE(sensors/src/Pinhole.cpp)
 #undef protected
 #undef private
 
@@ -256,4 +258,45 @@ REF_API int ref_features_in_area(const float* params8, int width, int height, in
 REF_API float ref_descriptor_distance(const float* a, const float* b) {
     cv::Mat A(1, 256, CV_32F, const_cast<float*>(a)), B(1, 256, CV_32F, const_cast<float*>(b));
     return DescriptorDistance(A, B);
+}
+
+#include "keyframe_raw.hpp"
+
+// params8 = fx fy cx cy + 4 distortion coefficients; R1 / t1, R2 / t2 = the world -> camera poses T1w, T2w (row-major R).
+// match12 (n1) out; F12 (9, row-major) and ep (2) out: what Matcher.cpp:776-788 and Pinhole.cpp:101-104 compute from
+// the poses, for the callers that hand the same numbers to the oracle and to the GPU.  Returns nmatches.
+REF_API int ref_search_for_triangulation(const float* params8, int width, int height, const float* R1, const float* t1,
+                                         const float* R2, const float* t2, int n1, const float* pos1, const float* desc1,
+                                         const int* node1, const unsigned char* mp1, int n2, const float* pos2,
+                                         const float* desc2, const int* node2, const unsigned char* mp2, int* match12,
+                                         float* F12out, float* epout) {
+    Pinhole cam(std::vector<float>(params8, params8 + 8), width, height, 20.f);
+    MapPoint* some = static_cast<MapPoint*>(calloc(1, sizeof(MapPoint)));  // only tested against nullptr
+    KeyFrame* k1 = raw_keyframe(n1, pos1, desc1, node1, mp1, some, pose_of(R1, t1));
+    KeyFrame* k2 = raw_keyframe(n2, pos2, desc2, node2, mp2, some, pose_of(R2, t2));
+    {   // the same expressions as Matcher.cpp:776-788 / Pinhole.cpp:101-104, evaluated by the reference's own classes
+        SE3f T1w = k1->GetPose(), T2w = k2->GetPose(), Tw2 = k2->GetPoseInverse();
+        Eigen::Vector3f Cw = k1->GetCameraCenter();
+        Eigen::Vector3f C2 = T2w * Cw;
+        Eigen::Vector2f ep = cam.project(C2);
+        SE3f T12 = T1w * Tw2;
+        Eigen::Matrix3f R12 = T12.rotationMatrix();
+        Eigen::Vector3f t12 = T12.translation();
+        Eigen::Matrix3f t12x = SO3f::hat(t12);
+        Eigen::Matrix3f K1 = cam.toK_(), K2 = cam.toK_();
+        Eigen::Matrix3f F = K1.transpose().inverse() * t12x * R12 * K2.inverse();
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) F12out[3 * i + j] = F(i, j);
+        epout[0] = ep[0];
+        epout[1] = ep[1];
+    }
+    Matcher matcher(&cam, 0.8f);
+    std::vector<std::pair<size_t, size_t>> pairs;
+    const int nm = matcher.SearchForTriangulation(k1, k2, pairs, false);
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    for (const auto& pr : pairs) match12[pr.first] = (int)pr.second;
+    drop_keyframe(k1);
+    drop_keyframe(k2);
+    free(some);
+    return nm;
 }

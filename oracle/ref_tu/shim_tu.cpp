@@ -2,7 +2,8 @@
 // MapPoint.h, PPGGraph.h, GeometricCamera.h, Matcher.h from /root/reference) and EXECUTED on real MapPoint / MapEdge /
 // Frame objects: the same pointer graph goes once through the reference's own Matcher::ExtendMapMatches (host) and once
 // through ppg_shim::Matcher::ExtendMapMatches (flattening -> C ABI -> GPU -> write-back), and what the two leave in
-// F.mvpMapPoints / F.mvpMapEdges / mnTrackedbyFrame is handed back for comparison.  Same for SearchForInitialization.
+// F.mvpMapPoints / F.mvpMapEdges / mnTrackedbyFrame is handed back for comparison.  Same for SearchForInitialization and
+// SearchForTriangulation (two raw KeyFrames, the reference's own Pinhole camera).
 // Links libppg_b200.so; needs a GPU at run time (tests/test_ref_pin.py, -m gpu).  TEST INFRASTRUCTURE ONLY.
 #include <algorithm>
 #include <atomic>
@@ -35,11 +36,13 @@
 #include REF_FILE(map/src/Frame.cpp)
 #include REF_FILE(feature/src/PPGGraph.cpp)
 #include REF_FILE(sensors/src/GeometricCamera.cpp)
+#include REF_FILE(sensors/src/Pinhole.cpp)
 #undef protected
 #undef private
 
 #define PPG_SHIM_NO_REFERENCE_HEADERS  // they are all in already, through Matcher.cpp
 #include "ppg_shim.hpp"
+#include "keyframe_raw.hpp"
 
 namespace {
 
@@ -254,6 +257,47 @@ REF_API int shim_init_both(const float* params8, int width, int height, int fish
         return 0;
     } catch (const std::exception& e) {
         std::cerr << "shim_init_both: " << e.what() << std::endl;
+        return -1;
+    }
+}
+
+// Matcher::SearchForTriangulation: the reference's host function and ppg_shim::Matcher's GPU path on the same two key
+// frames with the reference's own Pinhole camera.  match12_2 = [2][max(n1, 1)]: 0 reference, 1 shim.
+REF_API int shim_triangulation_both(const float* params8, int width, int height, const char* weights, const float* R1,
+                                    const float* t1, const float* R2, const float* t2, int n1, const float* pos1,
+                                    const float* desc1, const int* node1, const unsigned char* mp1, int n2,
+                                    const float* pos2, const float* desc2, const int* node2, const unsigned char* mp2,
+                                    int* nmatches2, int* match12_2) {
+    try {
+        Pinhole cam(std::vector<float>(params8, params8 + 8), width, height, 20.f);
+        ppg_shim::PPGExtractor ex(&cam, std::string(weights));
+        MapPoint* some = static_cast<MapPoint*>(calloc(1, sizeof(MapPoint)));
+        KeyFrame* k1 = raw_keyframe(n1, pos1, desc1, node1, mp1, some, pose_of(R1, t1));
+        KeyFrame* k2 = raw_keyframe(n2, pos2, desc2, node2, mp2, some, pose_of(R2, t2));
+        for (int which = 0; which < 2; which++) {
+            std::vector<std::pair<size_t, size_t>> pairs;
+            if (which == 0) {
+                ::Matcher ref(&cam, 0.8f);
+                nmatches2[0] = ref.SearchForTriangulation(k1, k2, pairs, false);
+            } else {
+                ppg_shim::Matcher m(ex.context(), &cam, 0.8f);
+                nmatches2[1] = m.SearchForTriangulation(k1, k2, pairs, false);
+            }
+            int* out = match12_2 + which * std::max(n1, 1);
+            for (int i = 0; i < n1; i++) out[i] = -1;
+            size_t last = 0;
+            for (size_t k = 0; k < pairs.size(); k++) {
+                if (k > 0 && pairs[k].first <= last) return -2;  // vMatchedPairs is in ascending order of the first index
+                last = pairs[k].first;
+                out[pairs[k].first] = (int)pairs[k].second;
+            }
+        }
+        drop_keyframe(k1);
+        drop_keyframe(k2);
+        free(some);
+        return 0;
+    } catch (const std::exception& e) {
+        std::cerr << "shim_triangulation_both: " << e.what() << std::endl;
         return -1;
     }
 }

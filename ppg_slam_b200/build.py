@@ -1,7 +1,7 @@
 """In-tree build of libppg_b200.so (sm_100a only).  `python -m ppg_slam_b200.build [--force]`.
 
 nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU box with the snapshot.
-post.cu, assoc.cu, extend.cu and bow.cu are built with -fmad=false: their results must be bit-identical to the reference's
+post.cu, assoc.cu, extend.cu, bow.cu and triang.cu are built with -fmad=false: their results must be bit-identical to the reference's
 SSE2 (no-FMA) float arithmetic (CMakeLists.txt:8-9 of the reference sets no -march).
 """
 import os
@@ -27,6 +27,7 @@ SOURCES = {
     "assoc.cu": ["-fmad=false"],
     "extend.cu": ["-fmad=false"],
     "bow.cu": ["-fmad=false"],
+    "triang.cu": ["-fmad=false"],
     "voc_io.cu": [],
     "comm.cu": [],
 }

@@ -119,6 +119,18 @@ class InitMatchOut(C.Structure):
                 ("n_rescans", C.c_int)]
 
 
+class TriangulationMatchIn(C.Structure):
+    _fields_ = [("n1", C.c_int), ("n2", C.c_int), ("desc1", C.POINTER(C.c_float)), ("desc2", C.POINTER(C.c_float)),
+                ("node1", C.POINTER(C.c_int32)), ("node2", C.POINTER(C.c_int32)),
+                ("has_mp1", C.POINTER(C.c_uint8)), ("has_mp2", C.POINTER(C.c_uint8)),
+                ("pos1", C.POINTER(C.c_float)), ("pos2", C.POINTER(C.c_float)),
+                ("F12", C.c_float * 9), ("epipole", C.c_float * 2), ("th_low", C.c_float)]
+
+
+class TriangulationMatchOut(C.Structure):
+    _fields_ = [("match12", C.POINTER(C.c_int32)), ("nmatches", C.c_int)]
+
+
 SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", "ppg_api_version", "ppg_extract",
            "ppg_upload_frames", "ppg_run", "ppg_download", "ppg_sync", "ppg_extract_from_maps", "ppg_get_maps",
            "ppg_selftest_conv", "ppg_get_layer_output", "ppg_set_profiling", "ppg_get_stage_times", "ppg_launch_count", "ppg_timer_start",
@@ -134,7 +146,7 @@ SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", 
            "ppg_assoc_stage_batch_async", "ppg_extend_fetch_batch_async", "ppg_extend_collect",
            "ppg_comm_unique_id", "ppg_comm_init", "ppg_comm_destroy", "ppg_assoc_allgather",
            "ppg_assoc_allgather_fetch", "ppg_record_bytes",
-           "ppg_search_for_initialization"]
+           "ppg_search_for_initialization", "ppg_search_for_triangulation"]
 
 _lib = None
 
@@ -170,7 +182,8 @@ def load():
                      "ppg_load_vocabulary", "ppg_extract_async", "ppg_extract_wait", "ppg_host_register",
                      "ppg_host_unregister", "ppg_assoc_stage_batch_async", "ppg_extend_fetch_batch_async",
                      "ppg_extend_collect", "ppg_comm_unique_id", "ppg_comm_init", "ppg_comm_destroy",
-                     "ppg_assoc_allgather", "ppg_assoc_allgather_fetch", "ppg_search_for_initialization"]:
+                     "ppg_assoc_allgather", "ppg_assoc_allgather_fetch", "ppg_search_for_initialization",
+                     "ppg_search_for_triangulation"]:
             getattr(lib, name).restype = C.c_int
         lib.ppg_get_layer_output.restype = C.c_int
         lib.ppg_get_layer_output.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t,
@@ -737,6 +750,28 @@ class Extractor:
         o.prev_matched = _fp(pm)
         self._check(self.lib.ppg_search_for_initialization(self.h, C.byref(a), C.byref(o)))
         return dict(nmatches=o.nmatches, matches12=m12[:len(d1)], prev_matched=pm, n_rescans=o.n_rescans)
+
+    def search_for_triangulation(self, desc1, node1, has_mp1, pos1, desc2, node2, has_mp2, pos2, F12, epipole,
+                                 th_low=0.7):
+        """Matcher::SearchForTriangulation (Matcher.cpp:767-885), pinhole epipolar test.  -> dict(nmatches, match12)"""
+        f32 = lambda v: np.ascontiguousarray(v, np.float32)
+        d1, d2, p1, p2 = f32(desc1), f32(desc2), f32(pos1), f32(pos2)
+        nd1, nd2 = np.ascontiguousarray(node1, np.int32), np.ascontiguousarray(node2, np.int32)
+        m1, m2 = np.ascontiguousarray(has_mp1, np.uint8), np.ascontiguousarray(has_mp2, np.uint8)
+        a = TriangulationMatchIn()
+        a.n1, a.n2, a.th_low = len(d1), len(d2), th_low
+        a.desc1, a.desc2, a.pos1, a.pos2 = _fp(d1), _fp(d2), _fp(p1), _fp(p2)
+        a.node1 = nd1.ctypes.data_as(C.POINTER(C.c_int32))
+        a.node2 = nd2.ctypes.data_as(C.POINTER(C.c_int32))
+        a.has_mp1 = m1.ctypes.data_as(C.POINTER(C.c_uint8))
+        a.has_mp2 = m2.ctypes.data_as(C.POINTER(C.c_uint8))
+        a.F12 = (C.c_float * 9)(*[float(v) for v in f32(F12).reshape(9)])
+        a.epipole = (C.c_float * 2)(*[float(v) for v in f32(epipole).reshape(2)])
+        m12 = np.full(max(len(d1), 1), -1, np.int32)
+        o = TriangulationMatchOut()
+        o.match12 = m12.ctypes.data_as(C.POINTER(C.c_int32))
+        self._check(self.lib.ppg_search_for_triangulation(self.h, C.byref(a), C.byref(o)))
+        return dict(nmatches=o.nmatches, match12=m12[:len(d1)])
 
     def distinctive_descriptors(self, desc, offsets, to_table=False):
         """MapPoint::ComputeDistinctiveDescriptors for a batch of map points (packed observation descriptors +

@@ -222,3 +222,50 @@ def frustum_inputs(seed, cam, n_points, n_frames=1):
     f = lambda a: np.ascontiguousarray(a, np.float32)
     return dict(world_pos=f(P), normal=f(n), min_dist=f(min_d), max_dist=f(max_d), Rcw=f(np.stack(Rs)),
                 tcw=f(np.stack(ts)), Ow=f(np.stack(Os)))
+
+
+def two_view_inputs(seed, cam, n1=300, n2=320, n_nodes=40, frac_mp=0.2, noise_px=0.6, desc_noise=0.05, forward=False):
+    """Two pinhole key frames looking at the same random 3-D points (Matcher::SearchForTriangulation, Matcher.cpp:767-885):
+    world -> camera poses, undistorted pixel positions, unit descriptors (those of a common point differ by desc_noise),
+    one vocabulary node per feature (common points share it), a fraction of features already carrying a map point.
+    Pixel noise around the epipolar test's 3.84 threshold so that both of its outcomes occur."""
+    r = np.random.RandomState(seed)
+    fx, fy, cx, cy = float(cam.K[0]), float(cam.K[4]), float(cam.K[2]), float(cam.K[5])
+
+    def rot(ax, ang):
+        ax = np.asarray(ax, np.float64)
+        ax /= np.linalg.norm(ax)
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+    R1, t1 = rot(r.randn(3), 0.05 * r.rand()), 0.1 * r.randn(3)
+    R2, t2 = rot(r.randn(3), 0.15 * r.rand()), np.array([0.4, 0.05, 0.02]) * (1 + r.rand(3))
+    if forward:  # motion along the optical axis: the epipole falls inside the image (the 10-pixel exclusion of :846-847)
+        R2, t2 = rot(r.randn(3), 0.02 * r.rand()), np.array([0.01, 0.01, -0.8]) * (1 + 0.2 * r.rand(3))
+    n_common = min(n1, n2) * 2 // 3
+    X = np.stack([r.uniform(-3, 3, n_common), r.uniform(-2, 2, n_common), r.uniform(4, 12, n_common)], 1)
+
+    def proj(R, t, P):
+        Pc = P @ R.T + t
+        return np.stack([fx * Pc[:, 0] / Pc[:, 2] + cx, fy * Pc[:, 1] / Pc[:, 2] + cy], 1)
+    d_common = r.randn(n_common, 256)
+    node_common = r.randint(0, n_nodes, n_common)
+    out = {}
+    for k, (R, t, n) in enumerate(((R1, t1, n1), (R2, t2, n2)), 1):
+        pos = np.empty((n, 2))
+        pos[:n_common] = proj(R, t, X) + noise_px * r.randn(n_common, 2) * r.choice([1.0, 3.0], (n_common, 1))
+        pos[n_common:] = np.stack([r.uniform(0, cam.width, n - n_common), r.uniform(0, cam.height, n - n_common)], 1)
+        d = np.empty((n, 256))
+        d[:n_common] = d_common + desc_noise * 16 * r.randn(n_common, 256) * r.choice([0.2, 0.45, 1.2], (n_common, 1))
+        d[n_common:] = r.randn(n - n_common, 256)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        node = np.empty(n, np.int32)
+        node[:n_common] = node_common
+        node[n_common:] = r.randint(0, n_nodes, n - n_common)
+        perm = r.permutation(n)  # feature order is unrelated to the point identity
+        out["pos%d" % k] = pos[perm].astype(np.float32)
+        out["desc%d" % k] = d[perm].astype(np.float32)
+        out["node%d" % k] = node[perm]
+        out["has_mp%d" % k] = (r.rand(n) < frac_mp).astype(np.uint8)
+        out["R%d" % k] = R.astype(np.float32)
+        out["t%d" % k] = t.astype(np.float32)
+    return out

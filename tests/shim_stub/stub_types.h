@@ -31,6 +31,34 @@ struct Vec2f {
     struct Init { Vec2f* p; int k; Init operator,(float x) { p->v[k] = x; return Init{p, k + 1}; } };
     Init operator<<(float x) { v[0] = x; return Init{this, 1}; }
 };
+// Eigen / SE3.h look-alikes for the pose-only geometry of ppg_shim::search_for_triangulation (syntax check only)
+namespace Eigen {
+struct Vector2f {
+    float v[2];
+    float& operator[](int i) { return v[i]; }
+    float operator[](int i) const { return v[i]; }
+};
+struct Vector3f {
+    float v[3];
+    float operator[](int i) const { return v[i]; }
+};
+struct Matrix3f {
+    float m[9];
+    float operator()(int r, int c) const { return m[3 * r + c]; }
+    Matrix3f transpose() const { return *this; }
+    Matrix3f inverse() const { return *this; }
+    Matrix3f operator*(const Matrix3f&) const { return *this; }
+};
+}  // namespace Eigen
+struct SE3f {
+    Eigen::Matrix3f rotationMatrix() const { return Eigen::Matrix3f(); }
+    Eigen::Vector3f translation() const { return Eigen::Vector3f(); }
+    SE3f operator*(const SE3f&) const { return *this; }
+    Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return p; }
+};
+struct SO3f {
+    static Eigen::Matrix3f hat(const Eigen::Vector3f&) { return Eigen::Matrix3f(); }
+};
 struct KeyPointEx {
     KeyPointEx() {}
     KeyPointEx(float x, float y, float sc) : mfScore(sc), mbOut(true) { mPos.v[0] = x; mPos.v[1] = y; }
@@ -53,6 +81,8 @@ struct GeometricCamera {
     virtual cv::Mat toD() = 0;
     virtual int imWidth() = 0;
     virtual int imHeight() = 0;
+    virtual Eigen::Vector2f project(const Eigen::Vector3f&) = 0;
+    virtual Eigen::Matrix3f toK_() = 0;
     unsigned int mnType;
 };
 struct MapPoint;
@@ -87,7 +117,13 @@ struct MapPoint {
 struct KeyFrame {
     std::map<unsigned int, std::vector<unsigned int>> mFeatVec;
     cv::Mat mDescriptors;
+    int N = 0;
+    std::vector<KeyPointEx> mvKeysUn;
     std::vector<MapPoint*> GetMapPointMatches() { return {}; }
+    MapPoint* GetMapPoint(const size_t&) { return nullptr; }
+    SE3f GetPose() { return SE3f(); }
+    SE3f GetPoseInverse() { return SE3f(); }
+    Eigen::Vector3f GetCameraCenter() { return Eigen::Vector3f(); }
 };
 struct Frame {
     Mat3f mRcw;

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libppg_b200.so does not export %s" % name
     assert sorted(capi.SYMBOLS) == declared, "capi.SYMBOLS is out of sync with include/ppg_b200.h"
-    assert lib.ppg_api_version() == 5
+    assert lib.ppg_api_version() == 6
 
 
 def test_struct_layouts_match_header():
@@ -58,6 +58,8 @@ def test_struct_layouts_match_header():
     assert fields("ppg_bow_match_out") == [f[0] for f in capi.BowMatchOut._fields_]
     assert fields("ppg_init_match_in") == [f[0] for f in capi.InitMatchIn._fields_]
     assert fields("ppg_init_match_out") == [f[0] for f in capi.InitMatchOut._fields_]
+    assert fields("ppg_triangulation_match_in") == [f[0] for f in capi.TriangulationMatchIn._fields_]
+    assert fields("ppg_triangulation_match_out") == [f[0] for f in capi.TriangulationMatchOut._fields_]
 
 
 def test_no_cpu_fallback():

@@ -317,3 +317,120 @@ def test_shim_search_for_initialization_equals_the_reference_on_real_frames(name
     assert shim["nmatches"] == ref["nmatches"] == int(d["ref_nmatches"][0])
     np.testing.assert_array_equal(shim["matches12"], ref["matches12"])
     np.testing.assert_array_equal(shim["prev_matched"], ref["prev_matched"])
+
+
+# ---------------------------------------------------------------- Matcher::SearchForTriangulation (pinhole)
+def _tri():
+    return np.load(os.path.join(GOLD, "ref_l2_triangulation.npz"))
+
+
+def _tri_cases():
+    return sorted({k.split("/")[0] for k in _tri().files})
+
+
+def _tri_case(name):
+    z = _tri()
+    return {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "/")}
+
+
+@pytest.mark.parametrize("name", _tri_cases())
+def test_oracle_reproduces_the_reference_search_for_triangulation(name):
+    """Matcher::SearchForTriangulation (Matcher.cpp:767-885) as the reference's own C++ ran it, with its own Pinhole
+    camera (epipolarConstrain, Pinhole.cpp:98-114), on two key frames: vMatches12 and the count, given the F12 / epipole
+    the reference's classes computed from the poses."""
+    from oracle import post_ref as O
+    d = _tri_case(name)
+    got = O.search_for_triangulation(d["desc1"], d["node1"], d["has_mp1"], d["pos1"], d["desc2"], d["node2"], d["has_mp2"],
+                                     d["pos2"], d["ref_F12"], d["ref_epipole"])
+    assert got["nmatches"] == int(d["ref_nmatches"][0]) and got["nmatches"] >= 10
+    np.testing.assert_array_equal(got["match12"], d["ref_match12"])
+
+
+def test_oracle_equals_reference_search_for_triangulation_live():
+    """40 random key-frame pairs (sideways and forward motion -- the epipole inside the image --, 6 to 40 vocabulary nodes,
+    0 to 50 % of the features already tracked, empty and one-feature frames) through the reference's own function (here)
+    and the oracle; the fixture generator's poses go through the reference's SE3 / Pinhole classes."""
+    from oracle import post_ref as O, ref_harness as R
+    if not R.matcher_available():
+        pytest.skip("reference harness not built (no /root/reference on this machine)")
+    from ppg_slam_b200 import synth
+    cam = cameras.EUROC
+    total = 0
+    for seed in range(40):
+        kw = dict(n_nodes=[6, 12, 40][seed % 3], noise_px=[0.3, 0.6, 1.2][(seed // 3) % 3], forward=(seed % 4 == 3),
+                  frac_mp=[0.0, 0.2, 0.5][(seed // 2) % 3], n1=[0, 1, 57, 300, 500][seed % 5] if seed < 10 else 300)
+        x = synth.two_view_inputs(seed, cam, **kw)
+        ref = R.search_for_triangulation(cam, x["R1"], x["t1"], x["R2"], x["t2"], x["pos1"], x["desc1"], x["node1"],
+                                         x["has_mp1"], x["pos2"], x["desc2"], x["node2"], x["has_mp2"])
+        got = O.search_for_triangulation(x["desc1"], x["node1"], x["has_mp1"], x["pos1"], x["desc2"], x["node2"],
+                                         x["has_mp2"], x["pos2"], ref["F12"], ref["epipole"])
+        assert got["nmatches"] == ref["nmatches"], seed
+        np.testing.assert_array_equal(got["match12"], ref["match12"], err_msg="seed %d" % seed)
+        total += ref["nmatches"]
+    assert total > 800
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _tri_cases())
+def test_cuda_search_for_triangulation_reproduces_the_reference(name):
+    from ppg_slam_b200 import capi
+    d = _tri_case(name)
+    e = capi.Extractor(cameras.EUROC, max_batch=1)
+    try:
+        got = e.search_for_triangulation(d["desc1"], d["node1"], d["has_mp1"], d["pos1"], d["desc2"], d["node2"],
+                                         d["has_mp2"], d["pos2"], d["ref_F12"], d["ref_epipole"])
+    finally:
+        e.close()
+    assert got["nmatches"] == int(d["ref_nmatches"][0])
+    np.testing.assert_array_equal(got["match12"], d["ref_match12"])
+
+
+@pytest.mark.gpu
+def test_cuda_search_for_triangulation_equals_oracle_sweep():
+    """24 random key-frame pairs up to 500 x 520 features: ppg_search_for_triangulation against the oracle, F12 / epipole
+    from the fixture generator's poses (plain numpy here: /root/reference is not on the GPU box)."""
+    from oracle import post_ref as O
+    from ppg_slam_b200 import capi, synth
+    cam = cameras.EUROC
+    fx, fy, cx, cy = cam.K[0], cam.K[4], cam.K[2], cam.K[5]
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float64)
+    e = capi.Extractor(cam, max_batch=1)
+    total = 0
+    try:
+        for seed in range(24):
+            kw = dict(n_nodes=[6, 12, 40][seed % 3], noise_px=[0.3, 0.6, 1.2][(seed // 3) % 3], forward=(seed % 4 == 3),
+                      frac_mp=[0.0, 0.2, 0.5][(seed // 2) % 3], n1=[0, 1, 57, 300, 500][seed % 5],
+                      n2=[320, 2, 33, 520][seed % 4])
+            x = synth.two_view_inputs(100 + seed, cam, **kw)
+            R1, t1, R2, t2 = (x[k].astype(np.float64) for k in ("R1", "t1", "R2", "t2"))
+            R12, t12 = R1 @ R2.T, t1 - R1 @ R2.T @ t2  # T12 = T1w * Tw2
+            tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])
+            F12 = (np.linalg.inv(K.T) @ tx @ R12 @ np.linalg.inv(K)).astype(np.float32)
+            C2 = R2 @ (-R1.T @ t1) + t2
+            ep = np.array([fx * C2[0] / C2[2] + cx, fy * C2[1] / C2[2] + cy], np.float32)
+            args = (x["desc1"], x["node1"], x["has_mp1"], x["pos1"], x["desc2"], x["node2"], x["has_mp2"], x["pos2"], F12, ep)
+            want = O.search_for_triangulation(*args)
+            got = e.search_for_triangulation(*args)
+            assert got["nmatches"] == want["nmatches"], seed
+            np.testing.assert_array_equal(got["match12"], want["match12"], err_msg="seed %d" % seed)
+            total += want["nmatches"]
+    finally:
+        e.close()
+    assert total > 200
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _tri_cases())
+def test_shim_search_for_triangulation_equals_the_reference_on_real_keyframes(name):
+    """include/ppg_shim.hpp compiled against the reference's real KeyFrame.h / Pinhole.h / SE3.h and executed: the shim
+    derives F12 and the epipole from the key frames' poses with the reference's own classes, flattens the FeatureVectors,
+    calls the GPU and must hand back the vMatchedPairs of the reference's host function."""
+    from oracle import ref_harness as R
+    if not R.shim_available():
+        pytest.skip("shim harness not built (built in the build container: oracle/ref_build.py)")
+    d = _tri_case(name)
+    ref, shim = R.shim_triangulation_both(cameras.EUROC, d["R1"], d["t1"], d["R2"], d["t2"], d["pos1"], d["desc1"],
+                                          d["node1"], d["has_mp1"], d["pos2"], d["desc2"], d["node2"], d["has_mp2"])
+    assert shim["nmatches"] == ref["nmatches"] == int(d["ref_nmatches"][0])
+    np.testing.assert_array_equal(ref["match12"], d["ref_match12"])
+    np.testing.assert_array_equal(shim["match12"], ref["match12"])
