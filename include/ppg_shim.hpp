@@ -367,6 +367,53 @@ inline int search_by_bow(ppg_ctx* ctx, KeyFrameLike* pKF, Frame& F, std::vector<
     return out.nmatches;
 }
 
+// Matcher::SearchByBoW(KeyFrame*, KeyFrame*, ...) (matching/src/Matcher.cpp:663-754) whole on the GPU: the same call with
+// strict = 1 (`bestDist1 < TH_LOW`, :733); rows = the features of KF1 with a good map point in FeatureVector order, the
+// candidates of a row = the features of KF2 under the same node with a good map point that no earlier row has taken
+// (vbMatched2, :709).  vpMatches12[i1] = the map point of the matched KF2 feature.
+template <typename KeyFrameLike>
+inline int search_by_bow(ppg_ctx* ctx, KeyFrameLike* pKF1, KeyFrameLike* pKF2, std::vector<MapPoint*>& vpMatches12,
+                         float nnratio, float th_low) {
+    const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches();
+    const std::vector<MapPoint*> vpMapPoints2 = pKF2->GetMapPointMatches();
+    vpMatches12 = std::vector<MapPoint*>(vpMapPoints1.size(), static_cast<MapPoint*>(nullptr));  // :675
+    const int n2 = (int)vpMapPoints2.size();
+    std::vector<int32_t> row_node, row_feat, kp_node(n2 > 0 ? n2 : 1, -1);
+    std::vector<float> table;
+    for (const auto& nf : pKF1->mFeatVec)
+        for (unsigned int idx : nf.second) {
+            MapPoint* pMP = vpMapPoints1[idx];
+            if (!pMP || pMP->isBad()) continue;  // :693-697
+            row_node.push_back((int32_t)nf.first);
+            row_feat.push_back((int32_t)idx);
+            const float* d = pKF1->mDescriptors.template ptr<float>((int)idx);
+            table.insert(table.end(), d, d + PPG_DESC_DIM);
+        }
+    if (row_node.empty() || n2 == 0) return 0;
+    for (const auto& nf : pKF2->mFeatVec)
+        for (unsigned int idx : nf.second) {
+            MapPoint* pMP = vpMapPoints2[idx];
+            if (pMP && !pMP->isBad()) kp_node[idx] = (int32_t)nf.first;  // :707-714
+        }
+    check(ppg_upload_map(ctx, table.data(), (int)row_node.size()), ctx, "ppg_upload_map");
+    std::vector<int32_t> kp_row(n2, -1);
+    ppg_bow_match_in in{};
+    in.n_rows = (int)row_node.size();
+    in.row_node = row_node.data();
+    in.n_kp = n2;
+    in.frame_desc = pKF2->mDescriptors.template ptr<float>(0);
+    in.kp_node = kp_node.data();
+    in.ratio = nnratio;
+    in.max_dist = th_low;
+    in.strict = 1;
+    ppg_bow_match_out out{};
+    out.kp_row = kp_row.data();
+    check(ppg_search_by_bow(ctx, &in, &out), ctx, "ppg_search_by_bow");
+    for (int i2 = 0; i2 < n2; i2++)
+        if (kp_row[i2] >= 0) vpMatches12[row_feat[kp_row[i2]]] = vpMapPoints2[i2];  // :737
+    return out.nmatches;
+}
+
 // The whole Matcher::ExtendMapMatches (matching/src/Matcher.cpp:203-381) in one GPU call: window search with the live
 // frame state, assignment and seed growing all run in ppg_extend_map_matches; this function only flattens the
 // pointer graph into the POD form of include/ppg_b200.h and writes the result back into the Frame:
@@ -583,13 +630,14 @@ inline int search_for_triangulation(ppg_ctx* ctx, GeometricCamera* cam, KeyFrame
 
 #ifndef PPG_SHIM_NO_MATCHER_CLASS
 // Replaces class Matcher (matching/include/Matcher.h:20-64) for its callers: the same twelve signatures, constants and
-// public members.  Four matchers run on the GPU --
+// public members.  Five matchers run on the GPU --
 //   ExtendMapMatches          image <-> map association of MSTracking::SearchLocalPoints (system/src/Tracking.cpp:1007)
 //   SearchByBoW(KF, F)        relocalisation / reference-keyframe tracking
+//   SearchByBoW(KF, KF)       loop / merge candidates
 //   SearchForInitialization   monocular initialisation (Tracking.cpp:525)
 //   SearchForTriangulation    new map points in LocalMapping, for the pinhole camera (its epipolar test is closed-form;
 //                             KannalaBrandt8::epipolarConstrain triangulates the pair and stays on the host)
-// -- and the other eight (SearchByProjection x 4, SearchByBoW(KF, KF), SearchBySim3, Fuse x 2) are the reference's own
+// -- and the other seven (SearchByProjection x 4, SearchBySim3, Fuse x 2) are the reference's own
 // host code, inherited unchanged from ::Matcher (their window-search cores are available as search_window above for
 // callers that want them on the device).
 // The ctx is the one the frame's PPGExtractor owns (PPGExtractor::context()).
@@ -604,6 +652,9 @@ public:
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches) {
         return search_by_bow(mCtx, pKF, F, vpMapPointMatches, mfNNratio, TH_LOW);
     }
+    int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12) {
+        return search_by_bow(mCtx, pKF1, pKF2, vpMatches12, mfNNratio, TH_LOW);
+    }
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched,
                                 std::vector<int>& vnMatches12, int windowSize = 10) {
         return search_for_initialization(mCtx, F1, F2, vbPrevMatched, vnMatches12, windowSize, mfNNratio);
@@ -616,7 +667,6 @@ public:
     }
     // host-side matchers of the reference, unchanged
     using ::Matcher::Fuse;
-    using ::Matcher::SearchByBoW;  // (KeyFrame*, KeyFrame*, ...); the (KeyFrame*, Frame&, ...) overload above hides the base's
     using ::Matcher::SearchByProjection;
     using ::Matcher::SearchBySim3;
 

@@ -249,6 +249,37 @@ def search_for_triangulation(cam, R1, t1, R2, t2, pos1, desc1, node1, has_mp1, p
     return dict(nmatches=int(nm), match12=m12[:n1], F12=F.reshape(3, 3), epipole=ep)
 
 
+def search_by_bow_kf_f(cam, desc_kf, node_kf, state_kf, desc_f, node_f, ratio):
+    """The reference's own Matcher::SearchByBoW(KeyFrame*, Frame&, ...) (Matcher.cpp:393-477).  state_kf: 0 no map point,
+    1 good, 2 bad.  -> dict(nmatches, f2kf): f2kf[i] = key-frame feature whose map point frame feature i received."""
+    lib = _lib("matcher")
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    dk, df = f32(desc_kf), f32(desc_f)
+    out = np.full(max(len(df), 1), -1, np.int32)
+    nm = lib.ref_search_by_bow_kf_f(_p(_cam_params(cam)), cam.width, cam.height, len(dk), _p(dk),
+                                    _p(np.ascontiguousarray(node_kf, np.int32), C.c_int),
+                                    _p(np.ascontiguousarray(state_kf, np.uint8), C.c_ubyte), len(df), _p(df),
+                                    _p(np.ascontiguousarray(node_f, np.int32), C.c_int), C.c_float(ratio),
+                                    _p(out, C.c_int))
+    return dict(nmatches=int(nm), f2kf=out[:len(df)])
+
+
+def search_by_bow_kf_kf(cam, desc1, node1, state1, desc2, node2, state2, ratio):
+    """The reference's own Matcher::SearchByBoW(KeyFrame*, KeyFrame*, ...) (Matcher.cpp:663-754).
+    -> dict(nmatches, match12): match12[i1] = feature of KF2 whose map point vpMatches12[i1] is."""
+    lib = _lib("matcher")
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    d1, d2 = f32(desc1), f32(desc2)
+    out = np.full(max(len(d1), 1), -1, np.int32)
+    nm = lib.ref_search_by_bow_kf_kf(_p(_cam_params(cam)), cam.width, cam.height, len(d1), _p(d1),
+                                     _p(np.ascontiguousarray(node1, np.int32), C.c_int),
+                                     _p(np.ascontiguousarray(state1, np.uint8), C.c_ubyte), len(d2), _p(d2),
+                                     _p(np.ascontiguousarray(node2, np.int32), C.c_int),
+                                     _p(np.ascontiguousarray(state2, np.uint8), C.c_ubyte), C.c_float(ratio),
+                                     _p(out, C.c_int))
+    return dict(nmatches=int(nm), match12=out[:len(d1)])
+
+
 # ---------------------------------------------------------------- include/ppg_shim.hpp executed on the reference's objects
 def shim_available():
     return os.path.exists(ref_build.lib_path("shim")) and os.path.exists(ref_build.lib_path("matcher"))
@@ -330,3 +361,24 @@ def shim_triangulation_both(cam, R1, t1, R2, t2, pos1, desc1, node1, has_mp1, po
     if rc != 0:
         raise RuntimeError("shim_triangulation_both failed (rc %d, see stderr)" % rc)
     return tuple(dict(nmatches=int(nm[k]), match12=m12[k, :n1]) for k in (0, 1))
+
+
+def shim_bow_both(cam, kf_kf, desc1, node1, state1, desc2, node2, state2, ratio):
+    """Matcher::SearchByBoW through the reference's host function and through ppg_shim::Matcher (GPU) on the same objects.
+    kf_kf False: (KeyFrame, Frame) -> f2kf per frame feature; True: (KeyFrame, KeyFrame) -> match12 per KF1 feature.
+    -> (reference result, shim result), each dict(nmatches, out)."""
+    lib = _lib("shim")
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    d1, d2 = f32(desc1), f32(desc2)
+    n = len(d1) if kf_kf else len(d2)
+    nm = np.zeros(2, np.int32)
+    out = np.zeros((2, max(n, 1)), np.int32)
+    rc = lib.shim_bow_both(_p(_cam_params(cam)), cam.width, cam.height, _weights_dir().encode(), int(bool(kf_kf)), len(d1),
+                           _p(d1), _p(i32(node1), C.c_int), _p(u8(state1), C.c_ubyte), len(d2), _p(d2),
+                           _p(i32(node2), C.c_int), _p(u8(state2), C.c_ubyte), C.c_float(ratio), _p(nm, C.c_int),
+                           _p(out, C.c_int))
+    if rc != 0:
+        raise RuntimeError("shim_bow_both failed (see stderr)")
+    return tuple(dict(nmatches=int(nm[k]), out=out[k, :n]) for k in (0, 1))

@@ -17,6 +17,10 @@ Eigen::Vector3f KeyFrame::GetCameraCenter() {
     std::unique_lock<std::mutex> lock(mMutexPose);
     return mTwc.translation();
 }
+std::vector<MapPoint*> KeyFrame::GetMapPointMatches() {  // KeyFrame.cpp:285-289
+    std::unique_lock<std::mutex> lock(mMutexFeatures);
+    return mvpMapPoints;
+}
 MapPoint* KeyFrame::GetMapPoint(const size_t& idx) {
     std::unique_lock<std::mutex> lock(mMutexFeatures);
     return mvpMapPoints[idx];
@@ -53,6 +57,23 @@ KeyFrame* raw_keyframe(int n, const float* pos, const float* desc, const int* no
     for (int i = 0; i < n; i++) {
         if (has_mp[i]) kf->mvpMapPoints[i] = some_point;
         if (node[i] >= 0) kf->mFeatVec[(unsigned int)node[i]].push_back((unsigned int)i);  // DBoW3 fills it in feature order
+    }
+    return kf;
+}
+// Key frame for the SearchByBoW functions: state[i] = 0 no map point, 1 a good one, 2 a bad one (MapPoint::isBad());
+// the MapPoint objects come from the real constructor and are returned in `owned` (feature i -> owned[i] or nullptr).
+KeyFrame* raw_keyframe_with_points(int n, const float* desc, const int* node, const unsigned char* state,
+                                   std::vector<MapPoint*>& owned) {
+    std::vector<float> pos(2 * (size_t)std::max(n, 1), 0.f);
+    std::vector<unsigned char> none((size_t)std::max(n, 1), 0);
+    KeyFrame* kf = raw_keyframe(n, pos.data(), desc, node, none.data(), nullptr, SE3f());
+    owned.assign(n, nullptr);
+    for (int i = 0; i < n; i++) {
+        if (!state[i]) continue;
+        MapPoint* mp = new MapPoint(Eigen::Vector3f(0.f, 0.f, 1.f), kf);  // the real constructor (reads two ids of kf)
+        mp->mbBad = state[i] == 2;
+        owned[i] = mp;
+        kf->mvpMapPoints[i] = mp;
     }
     return kf;
 }

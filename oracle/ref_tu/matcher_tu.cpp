@@ -300,3 +300,54 @@ REF_API int ref_search_for_triangulation(const float* params8, int width, int he
     free(some);
     return nm;
 }
+
+// Matcher::SearchByBoW(KeyFrame*, Frame&, ...) (Matcher.cpp:393-477) on a raw key frame (state_kf: 0 no map point, 1 good,
+// 2 bad) and a Frame.  f2kf[i] = the key-frame feature whose map point frame feature i received, or -1.  -> nmatches.
+REF_API int ref_search_by_bow_kf_f(const float* params8, int width, int height, int n_kf, const float* desc_kf,
+                                   const int* node_kf, const unsigned char* state_kf, int n_f, const float* desc_f,
+                                   const int* node_f, float ratio, int* f2kf) {
+    HarnessCamera cam(std::vector<float>(params8, params8 + 8), width, height, false);
+    std::vector<MapPoint*> owned;
+    KeyFrame* kf = raw_keyframe_with_points(n_kf, desc_kf, node_kf, state_kf, owned);
+    Frame F;
+    F.N = n_f;
+    F.mpCamera = &cam;
+    F.mvKeysUn.resize(n_f);
+    F.mDescriptors = cv::Mat(std::max(n_f, 1), 256, CV_32F);
+    if (n_f > 0) memcpy(F.mDescriptors.data, desc_f, (size_t)n_f * 1024);
+    for (int i = 0; i < n_f; i++)
+        if (node_f[i] >= 0) F.mFeatVec[(unsigned int)node_f[i]].push_back((unsigned int)i);
+    std::vector<MapPoint*> out;
+    Matcher matcher(&cam, ratio);
+    const int nm = matcher.SearchByBoW(kf, F, out);
+    std::map<MapPoint*, int> feat_of;
+    for (int i = 0; i < n_kf; i++)
+        if (owned[i]) feat_of[owned[i]] = i;
+    for (int i = 0; i < n_f; i++) f2kf[i] = out[i] ? feat_of[out[i]] : -1;
+    for (MapPoint* m : owned) delete m;
+    drop_keyframe(kf);
+    return nm;
+}
+
+// Matcher::SearchByBoW(KeyFrame*, KeyFrame*, ...) (Matcher.cpp:663-754).  match12[i1] = the feature of KF2 whose map point
+// vpMatches12[i1] is, or -1.  -> nmatches.
+REF_API int ref_search_by_bow_kf_kf(const float* params8, int width, int height, int n1, const float* desc1,
+                                    const int* node1, const unsigned char* state1, int n2, const float* desc2,
+                                    const int* node2, const unsigned char* state2, float ratio, int* match12) {
+    HarnessCamera cam(std::vector<float>(params8, params8 + 8), width, height, false);
+    std::vector<MapPoint*> own1, own2;
+    KeyFrame* k1 = raw_keyframe_with_points(n1, desc1, node1, state1, own1);
+    KeyFrame* k2 = raw_keyframe_with_points(n2, desc2, node2, state2, own2);
+    std::vector<MapPoint*> out;
+    Matcher matcher(&cam, ratio);
+    const int nm = matcher.SearchByBoW(k1, k2, out);
+    std::map<MapPoint*, int> feat_of;
+    for (int i = 0; i < n2; i++)
+        if (own2[i]) feat_of[own2[i]] = i;
+    for (int i = 0; i < n1; i++) match12[i] = out[i] ? feat_of[out[i]] : -1;
+    for (MapPoint* m : own1) delete m;
+    for (MapPoint* m : own2) delete m;
+    drop_keyframe(k1);
+    drop_keyframe(k2);
+    return nm;
+}

@@ -301,3 +301,65 @@ REF_API int shim_triangulation_both(const float* params8, int width, int height,
         return -1;
     }
 }
+
+// Matcher::SearchByBoW, both overloads: the reference's host functions and ppg_shim::Matcher's GPU paths on the same raw
+// key frames (state: 0 no map point, 1 good, 2 bad) / Frame.  out2 = [2][max(n, 1)]: 0 reference, 1 shim;
+// kf_kf = 0: f2kf of the frame features (n = n2), kf_kf = 1: match12 of KF1's features (n = n1).
+REF_API int shim_bow_both(const float* params8, int width, int height, const char* weights, int kf_kf, int n1,
+                          const float* desc1, const int* node1, const unsigned char* state1, int n2, const float* desc2,
+                          const int* node2, const unsigned char* state2, float ratio, int* nmatches2, int* out2) {
+    try {
+        Pinhole cam(std::vector<float>(params8, params8 + 8), width, height, 20.f);
+        ppg_shim::PPGExtractor ex(&cam, std::string(weights));
+        std::vector<MapPoint*> own1, own2;
+        KeyFrame* k1 = raw_keyframe_with_points(n1, desc1, node1, state1, own1);
+        std::map<MapPoint*, int> feat1, feat2;
+        for (int i = 0; i < n1; i++)
+            if (own1[i]) feat1[own1[i]] = i;
+        const int n_out = std::max(kf_kf ? n1 : n2, 1);
+        if (kf_kf) {
+            KeyFrame* k2 = raw_keyframe_with_points(n2, desc2, node2, state2, own2);
+            for (int i = 0; i < n2; i++)
+                if (own2[i]) feat2[own2[i]] = i;
+            for (int which = 0; which < 2; which++) {
+                std::vector<MapPoint*> out;
+                if (which == 0) {
+                    ::Matcher ref(&cam, ratio);
+                    nmatches2[0] = ref.SearchByBoW(k1, k2, out);
+                } else {
+                    ppg_shim::Matcher m(ex.context(), &cam, ratio);
+                    nmatches2[1] = m.SearchByBoW(k1, k2, out);
+                }
+                for (int i = 0; i < n1; i++) out2[which * n_out + i] = out[i] ? feat2[out[i]] : -1;
+            }
+            for (MapPoint* m : own2) delete m;
+            drop_keyframe(k2);
+        } else {
+            for (int which = 0; which < 2; which++) {
+                Frame F;
+                F.N = n2;
+                F.mpCamera = &cam;
+                F.mvKeysUn.resize(n2);
+                F.mDescriptors = cv::Mat(std::max(n2, 1), 256, CV_32F);
+                if (n2 > 0) memcpy(F.mDescriptors.data, desc2, (size_t)n2 * 1024);
+                for (int i = 0; i < n2; i++)
+                    if (node2[i] >= 0) F.mFeatVec[(unsigned int)node2[i]].push_back((unsigned int)i);
+                std::vector<MapPoint*> out;
+                if (which == 0) {
+                    ::Matcher ref(&cam, ratio);
+                    nmatches2[0] = ref.SearchByBoW(k1, F, out);
+                } else {
+                    ppg_shim::Matcher m(ex.context(), &cam, ratio);
+                    nmatches2[1] = m.SearchByBoW(k1, F, out);
+                }
+                for (int i = 0; i < n2; i++) out2[which * n_out + i] = out[i] ? feat1[out[i]] : -1;
+            }
+        }
+        for (MapPoint* m : own1) delete m;
+        drop_keyframe(k1);
+        return 0;
+    } catch (const std::exception& e) {
+        std::cerr << "shim_bow_both: " << e.what() << std::endl;
+        return -1;
+    }
+}

@@ -269,3 +269,42 @@ def two_view_inputs(seed, cam, n1=300, n2=320, n_nodes=40, frac_mp=0.2, noise_px
         out["R%d" % k] = R.astype(np.float32)
         out["t%d" % k] = t.astype(np.float32)
     return out
+
+
+def bow_pair_inputs(seed, n1=300, n2=280, n_nodes=12, frac_none=0.25, frac_bad=0.1, noise=0.35, dup=0.15):
+    """Two feature sets for Matcher::SearchByBoW (Matcher.cpp:393-477, :663-754): unit descriptors, the second set holding
+    noisy copies of part of the first (some of them twice -- near-duplicates that fail the ratio test or compete for the same
+    feature), one vocabulary node per feature (a few features unlisted: -1), and a map-point state per feature (0 none,
+    1 good, 2 bad)."""
+    r = np.random.RandomState(seed)
+    d1 = r.randn(n1, 256)
+    node1 = r.randint(0, n_nodes, n1)
+    n_common = min(n1, n2) * 3 // 5
+    src = r.permutation(n1)[:n_common]
+    d2 = r.randn(n2, 256)
+    node2 = r.randint(0, n_nodes, n2)
+    dst = r.permutation(n2)[:n_common]
+    d2[dst] = d1[src] + noise * r.randn(n_common, 256) * r.choice([0.5, 1.0, 2.0], (n_common, 1))
+    node2[dst] = node1[src]
+    n_dup = int(dup * n_common)
+    free = np.setdiff1d(np.arange(n2), dst)[:n_dup]
+    if len(free):
+        d2[free] = d2[dst[:len(free)]] + 0.15 * r.randn(len(free), 256)
+        node2[free] = node2[dst[:len(free)]]
+    d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
+    d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    node1[r.rand(n1) < 0.03] = -1
+    node2[r.rand(n2) < 0.03] = -1
+
+    def states(n):
+        u = r.rand(n)
+        return np.where(u < frac_none, 0, np.where(u < frac_none + frac_bad, 2, 1)).astype(np.uint8)
+    return dict(desc1=d1.astype(np.float32), node1=node1.astype(np.int32), state1=states(n1),
+                desc2=d2.astype(np.float32), node2=node2.astype(np.int32), state2=states(n2))
+
+
+def bow_rows(desc, node, state):
+    """The rows Matcher::SearchByBoW visits: features with a good map point in FeatureVector order (node ascending, then
+    index).  -> (feature index of every row, row descriptors, row nodes)"""
+    idx = np.array([i for i in np.lexsort((np.arange(len(node)), node)) if node[i] >= 0 and state[i] == 1], np.int64)
+    return idx, desc[idx], node[idx].astype(np.int32)

@@ -1,4 +1,4 @@
-"""Golden vectors of Matcher::SearchForTriangulation made by the REFERENCE's own C++ (oracle/ref_build.py compiles
+"""Golden vectors of Matcher::SearchForTriangulation and of both Matcher::SearchByBoW overloads made by the REFERENCE's own C++ (oracle/ref_build.py compiles
 matching/src/Matcher.cpp and sensors/src/Pinhole.cpp from /root/reference): two pinhole key frames rebuilt from flat
 arrays, the real function, its vMatchedPairs -- plus F12 and the epipole as the reference's classes compute them from the
 poses.  Run in the build container: python tests/golden/make_golden_ref_triangulation.py"""
@@ -32,6 +32,18 @@ def main():
         out[name + "/ref_nmatches"] = np.array([ref["nmatches"]], np.int32)
         out[name + "/ref_F12"], out[name + "/ref_epipole"] = ref["F12"], ref["epipole"]
         print(name, kw, "nmatches", ref["nmatches"], "epipole", ref["epipole"])
+    # Matcher::SearchByBoW, both overloads (Matcher.cpp:393-477, :663-754), by the reference's own functions
+    for name, seed, kw, ratio in [("bow0", 21, dict(n1=90, n2=100, n_nodes=4), 0.8),
+                                  ("bow1", 22, dict(n1=70, n2=60, n_nodes=1, frac_none=0.1, frac_bad=0.25), 0.6)]:
+        x = synth.bow_pair_inputs(seed, **kw)
+        a = R.search_by_bow_kf_f(cam, x["desc1"], x["node1"], x["state1"], x["desc2"], x["node2"], ratio)
+        b = R.search_by_bow_kf_kf(cam, x["desc1"], x["node1"], x["state1"], x["desc2"], x["node2"], x["state2"], ratio)
+        for k, v in x.items():
+            out[name + "/" + k] = v
+        out[name + "/ratio"] = np.array([ratio], np.float32)
+        out[name + "/ref_f2kf"], out[name + "/ref_match12"] = a["f2kf"], b["match12"]
+        out[name + "/ref_nmatches"] = np.array([a["nmatches"], b["nmatches"]], np.int32)
+        print(name, kw, "KF-F", a["nmatches"], "KF-KF", b["nmatches"])
     path = os.path.join(ROOT, "tests", "golden", "ref_l2_triangulation.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path) // 1024, "KiB")

@@ -325,7 +325,33 @@ def _tri():
 
 
 def _tri_cases():
-    return sorted({k.split("/")[0] for k in _tri().files})
+    return sorted({k.split("/")[0] for k in _tri().files if k.startswith("tri")})
+
+
+def _bow_cases():
+    return sorted({k.split("/")[0] for k in _tri().files if k.startswith("bow")})
+
+
+def _bow_from_oracle(O, x, ratio, kf_kf):
+    """Flat arrays -> the rows / candidates the C ABI and the oracle take -> per-feature result in the reference's terms."""
+    from ppg_slam_b200 import synth
+    rows, rd, rn = synth.bow_rows(x["desc1"], x["node1"], x["state1"])
+    n1, n2 = len(x["desc1"]), len(x["desc2"])
+    kp_node = np.where(x["state2"] == 1, x["node2"], -1).astype(np.int32) if kf_kf else x["node2"]
+    if len(rows) == 0:
+        return 0, np.full(n1 if kf_kf else n2, -1, np.int32), (rows, rd, rn, kp_node)
+    got = O(x["desc2"], kp_node, rd, rn, ratio, 0.7, bool(kf_kf))
+    return got["nmatches"], _bow_result(got["kp_row"], rows, n1, kf_kf), (rows, rd, rn, kp_node)
+
+
+def _bow_result(kp_row, rows, n1, kf_kf):
+    if not kf_kf:  # f2kf: frame feature -> key-frame feature
+        return np.where(kp_row >= 0, rows[np.maximum(kp_row, 0)], -1).astype(np.int32)
+    m12 = np.full(n1, -1, np.int32)  # KF1 feature -> KF2 feature
+    for i2, r in enumerate(kp_row):
+        if r >= 0:
+            m12[rows[r]] = i2
+    return m12
 
 
 def _tri_case(name):
@@ -434,3 +460,79 @@ def test_shim_search_for_triangulation_equals_the_reference_on_real_keyframes(na
     assert shim["nmatches"] == ref["nmatches"] == int(d["ref_nmatches"][0])
     np.testing.assert_array_equal(ref["match12"], d["ref_match12"])
     np.testing.assert_array_equal(shim["match12"], ref["match12"])
+
+
+# ---------------------------------------------------------------- Matcher::SearchByBoW, both overloads
+@pytest.mark.parametrize("name", _bow_cases())
+@pytest.mark.parametrize("kf_kf", [False, True], ids=["kf-frame", "kf-kf"])
+def test_oracle_reproduces_the_reference_search_by_bow(name, kf_kf):
+    """Matcher::SearchByBoW(KF, F) (Matcher.cpp:393-477) and (KF, KF) (:663-754) as the reference's own C++ ran them on a
+    raw key frame / Frame with real MapPoint objects (good, bad, none): which feature got which map point, and the count."""
+    from oracle import post_ref as O
+    d = _tri_case(name)
+    nm, res, _ = _bow_from_oracle(O.search_by_bow, d, float(d["ratio"][0]), kf_kf)
+    assert nm == int(d["ref_nmatches"][int(kf_kf)]) and nm >= 15
+    np.testing.assert_array_equal(res, d["ref_match12"] if kf_kf else d["ref_f2kf"])
+
+
+def test_oracle_equals_reference_search_by_bow_live():
+    """30 random feature-set pairs x 2 ratios x both overloads (1 to 40 nodes, up to 60 % of the features without and 30 %
+    with a bad map point, empty and one-feature key frames) through the reference's own functions and the oracle."""
+    from oracle import post_ref as O, ref_harness as R
+    if not R.matcher_available():
+        pytest.skip("reference harness not built (no /root/reference on this machine)")
+    from ppg_slam_b200 import synth
+    cam = cameras.EUROC
+    total = 0
+    for seed in range(30):
+        kw = dict(n_nodes=[1, 4, 12, 40][seed % 4], frac_none=[0.0, 0.25, 0.6][seed % 3],
+                  frac_bad=[0.0, 0.1, 0.3][(seed // 3) % 3], n1=[0, 1, 40, 300, 500][seed % 5] if seed < 10 else 300,
+                  n2=[280, 3, 500][seed % 3])
+        x = synth.bow_pair_inputs(seed, **kw)
+        for ratio in (0.6, 0.9):
+            a = R.search_by_bow_kf_f(cam, x["desc1"], x["node1"], x["state1"], x["desc2"], x["node2"], ratio)
+            nm, res, _ = _bow_from_oracle(O.search_by_bow, x, ratio, False)
+            assert nm == a["nmatches"], (seed, ratio)
+            np.testing.assert_array_equal(res, a["f2kf"], err_msg="KF-F seed %d" % seed)
+            b = R.search_by_bow_kf_kf(cam, x["desc1"], x["node1"], x["state1"], x["desc2"], x["node2"], x["state2"], ratio)
+            nm, res, _ = _bow_from_oracle(O.search_by_bow, x, ratio, True)
+            assert nm == b["nmatches"], (seed, ratio)
+            np.testing.assert_array_equal(res, b["match12"], err_msg="KF-KF seed %d" % seed)
+            total += a["nmatches"] + b["nmatches"]
+    assert total > 3000
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _bow_cases())
+@pytest.mark.parametrize("kf_kf", [False, True], ids=["kf-frame", "kf-kf"])
+def test_cuda_search_by_bow_reproduces_the_reference(name, kf_kf):
+    from ppg_slam_b200 import capi, synth
+    d = _tri_case(name)
+    rows, rd, rn = synth.bow_rows(d["desc1"], d["node1"], d["state1"])
+    kp_node = np.where(d["state2"] == 1, d["node2"], -1).astype(np.int32) if kf_kf else d["node2"]
+    e = capi.Extractor(cameras.EUROC, max_batch=1, max_map_points=1024)
+    try:
+        e.upload_map(rd)
+        got = e.search_by_bow(rn, d["desc2"], kp_node, float(d["ratio"][0]), 0.7, kf_kf)
+    finally:
+        e.close()
+    assert got["nmatches"] == int(d["ref_nmatches"][int(kf_kf)])
+    np.testing.assert_array_equal(_bow_result(got["kp_row"], rows, len(d["desc1"]), kf_kf),
+                                  d["ref_match12"] if kf_kf else d["ref_f2kf"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _bow_cases())
+@pytest.mark.parametrize("kf_kf", [False, True], ids=["kf-frame", "kf-kf"])
+def test_shim_search_by_bow_equals_the_reference_on_real_objects(name, kf_kf):
+    """ppg_shim::Matcher::SearchByBoW (both overloads) compiled against the reference's real headers and executed on raw
+    key frames / a Frame with real MapPoint objects, next to ::Matcher."""
+    from oracle import ref_harness as R
+    if not R.shim_available():
+        pytest.skip("shim harness not built (built in the build container: oracle/ref_build.py)")
+    d = _tri_case(name)
+    ref, shim = R.shim_bow_both(cameras.EUROC, kf_kf, d["desc1"], d["node1"], d["state1"], d["desc2"], d["node2"],
+                                d["state2"], float(d["ratio"][0]))
+    assert shim["nmatches"] == ref["nmatches"] == int(d["ref_nmatches"][int(kf_kf)])
+    np.testing.assert_array_equal(ref["out"], d["ref_match12"] if kf_kf else d["ref_f2kf"])
+    np.testing.assert_array_equal(shim["out"], ref["out"])
