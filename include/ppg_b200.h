@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PPG_API_VERSION 6
+#define PPG_API_VERSION 7
 #define PPG_DESC_DIM 256 /* PPGExtractor::DESC_DIM_SIZE, PPGExtractor.cpp:44 */
 
 typedef enum {
@@ -459,15 +459,17 @@ typedef struct {
 int ppg_search_for_initialization(ppg_ctx* ctx, const ppg_init_match_in* in, ppg_init_match_out* out);
 
 /* ---- the whole Matcher::SearchForTriangulation on the GPU (matching/src/Matcher.cpp:767-885; called from
- * LocalMapping to find untracked feature pairs of two key frames) for the PINHOLE camera, whose epipolar test is
- * closed-form (sensors/src/Pinhole.cpp:98-114).  For every feature i1 of KF1 without a map point: over the features i2
- * of KF2 under the same vocabulary node (FeatureVector, ascending index) without a map point, the smallest
- * DescriptorDistance <= th_low (a tie takes the later one, :842) among those that lie at least 10 px from the epipole
- * (:846) and within dsqr < 3.84 of kp1's epipolar line.  The reference never sets vbMatched2, so the features of KF1 are
- * independent of one another: one warp per feature.  F12 and the epipole depend on the two poses only; the caller
- * computes them with the reference's own expressions (Matcher.cpp:776-788, Pinhole.cpp:101-104; ppg_shim.hpp does).
- * KannalaBrandt8::epipolarConstrain triangulates the pair (KannalaBrandt8.cpp:167-230): not provided, the shim leaves
- * fisheye cameras to the reference's host function. */
+ * LocalMapping to find untracked feature pairs of two key frames), for both camera models of the reference.  For every
+ * feature i1 of KF1 without a map point: over the features i2 of KF2 under the same vocabulary node (FeatureVector,
+ * ascending index) without a map point, the smallest DescriptorDistance <= th_low (a tie takes the later one, :842) among
+ * those that lie at least 10 px from the epipole (:846) and pass mpCamera->epipolarConstrain (:848):
+ *   camera_model 0, Pinhole (sensors/src/Pinhole.cpp:98-114): dsqr < 3.84 from kp1's epipolar line, closed form from F12;
+ *   camera_model 1, KannalaBrandt8 (sensors/src/KannalaBrandt8.cpp:167-236): unproject both pixels, parallax test,
+ *     triangulation (null vector of the 4 x 4 DLT matrix), positive depth and reprojection error < 5.991 px^2 in both
+ *     images, from cam8 / R12 / t12.
+ * The reference never sets vbMatched2, so the features of KF1 are independent of one another: one warp per feature.
+ * F12, R12, t12 and the epipole depend on the two poses only; the caller computes them with the reference's own
+ * expressions (Matcher.cpp:776-788, Pinhole.cpp:101-104; ppg_shim.hpp does). */
 typedef struct {
     int n1, n2;
     const float* desc1;      /* n1 x 256: pKF1->mDescriptors */
@@ -478,9 +480,13 @@ typedef struct {
     const uint8_t* has_mp2;  /* n2 */
     const float* pos1;       /* n1 x 2: pKF1->mvKeysUn[i].mPos */
     const float* pos2;       /* n2 x 2 */
-    float F12[9];            /* row-major K1^-T [t12]x R12 K2^-1 */
+    float F12[9];            /* row-major K1^-T [t12]x R12 K2^-1 (camera_model 0) */
     float epipole[2];        /* mpCamera->project(T2w * Cw) */
     float th_low;            /* Matcher::TH_LOW */
+    int camera_model;        /* 0 Pinhole, 1 KannalaBrandt8 (since API version 7) */
+    float cam8[8];           /* camera_model 1: fx fy cx cy k0 k1 k2 k3 (GeometricCamera::mvParameters) */
+    float R12[9];            /* camera_model 1: row-major T12.rotationMatrix(), Matcher.cpp:786 */
+    float t12[3];            /* camera_model 1: T12.translation(), :787 */
 } ppg_triangulation_match_in;
 typedef struct {
     int32_t* match12; /* n1, caller-allocated: index in KF2 or -1 (vMatches12) */

@@ -564,9 +564,10 @@ inline int search_for_initialization(ppg_ctx* ctx, Frame& F1, Frame& F2, std::ve
 }
 
 // Matcher::SearchForTriangulation (matching/src/Matcher.cpp:767-885) whole on the GPU (ppg_search_for_triangulation)
-// for a pinhole camera.  What depends on the two poses only -- the epipole and F12 -- is computed here with the
-// reference's own classes and expressions (:776-788, sensors/src/Pinhole.cpp:101-104); the per-pair work (descriptor
-// distances under the same vocabulary node, epipole exclusion, epipolar distance) runs on the device.
+// for the reference's two camera models.  What depends on the two poses only -- the epipole, R12 / t12 and F12 -- is
+// computed here with the reference's own classes and expressions (:776-788, sensors/src/Pinhole.cpp:101-104); the
+// per-pair work (descriptor distances under the same vocabulary node, epipole exclusion, and the camera's
+// epipolarConstrain: the epipolar distance of Pinhole, the two-view triangulation of KannalaBrandt8) runs on the device.
 inline int search_for_triangulation(ppg_ctx* ctx, GeometricCamera* cam, KeyFrame* pKF1, KeyFrame* pKF2,
                                     std::vector<std::pair<size_t, size_t>>& vMatchedPairs, float th_low) {
     SE3f T1w = pKF1->GetPose();
@@ -619,6 +620,12 @@ inline int search_for_triangulation(ppg_ctx* ctx, GeometricCamera* cam, KeyFrame
     in.epipole[0] = ep[0];
     in.epipole[1] = ep[1];
     in.th_low = th_low;
+    in.camera_model = cam->mnType == GeometricCamera::CAM_FISHEYE ? 1 : 0;
+    for (int i = 0; i < 8; i++) in.cam8[i] = i < (int)cam->mvParameters.size() ? cam->mvParameters[i] : 0.f;
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) in.R12[3 * r + c] = R12(r, c);
+        in.t12[r] = t12[r];
+    }
     ppg_triangulation_match_out out{};
     out.match12 = m12.data();
     check(ppg_search_for_triangulation(ctx, &in, &out), ctx, "ppg_search_for_triangulation");
@@ -635,8 +642,8 @@ inline int search_for_triangulation(ppg_ctx* ctx, GeometricCamera* cam, KeyFrame
 //   SearchByBoW(KF, F)        relocalisation / reference-keyframe tracking
 //   SearchByBoW(KF, KF)       loop / merge candidates
 //   SearchForInitialization   monocular initialisation (Tracking.cpp:525)
-//   SearchForTriangulation    new map points in LocalMapping, for the pinhole camera (its epipolar test is closed-form;
-//                             KannalaBrandt8::epipolarConstrain triangulates the pair and stays on the host)
+//   SearchForTriangulation    new map points in LocalMapping (Pinhole: closed-form epipolar distance;
+//                             KannalaBrandt8: the two-view triangulation of its epipolarConstrain, per pair on the device)
 // -- and the other seven (SearchByProjection x 4, SearchBySim3, Fuse x 2) are the reference's own
 // host code, inherited unchanged from ::Matcher (their window-search cores are available as search_window above for
 // callers that want them on the device).
@@ -661,8 +668,8 @@ public:
     }
     int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<std::pair<size_t, size_t>>& vMatchedPairs,
                                const bool bCoarse = false) {
-        if (mpCamera->mnType != GeometricCamera::CAM_PINHOLE)
-            return ::Matcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bCoarse);
+        if (mpCamera->mnType != GeometricCamera::CAM_PINHOLE && mpCamera->mnType != GeometricCamera::CAM_FISHEYE)
+            return ::Matcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bCoarse);  // a camera model of the caller's own
         return search_for_triangulation(mCtx, mpCamera, pKF1, pKF2, vMatchedPairs, TH_LOW);
     }
     // host-side matchers of the reference, unchanged

@@ -366,3 +366,60 @@ def search_for_triangulation(desc1, node1, has_mp1, pos1, desc2, node2, has_mp2,
                                          n2, _p(d2, C.c_float), _p(nd2, C.c_int), _p(m2, C.c_ubyte), _p(p2, C.c_float),
                                          _p(F, C.c_float), _p(ep, C.c_float), C.c_float(th_low), _p(m12, C.c_int))
     return dict(nmatches=int(nm), match12=m12[:n1])
+
+
+def _cam8(cam):
+    return f32([cam.K[0], cam.K[4], cam.K[2], cam.K[5]] + list(cam.D))
+
+
+def search_for_triangulation_kb8(cam, desc1, node1, has_mp1, pos1, desc2, node2, has_mp2, pos2, R12, t12, epipole,
+                                 th_low=0.7, variant=""):
+    """Matcher::SearchForTriangulation (Matcher.cpp:767-885) with KannalaBrandt8::epipolarConstrain
+    (KannalaBrandt8.cpp:167-236).  R12 row-major 3x3, t12 (3,), epipole (2,).  -> dict(nmatches, match12)."""
+    L = lib(variant)
+    d1, d2 = f32(desc1), f32(desc2)
+    n1, n2 = len(d1), len(d2)
+    nd1, nd2 = np.ascontiguousarray(node1, np.int32), np.ascontiguousarray(node2, np.int32)
+    m1, m2 = np.ascontiguousarray(has_mp1, np.uint8), np.ascontiguousarray(has_mp2, np.uint8)
+    p1, p2 = f32(pos1), f32(pos2)
+    R, t, ep, c8 = f32(R12).reshape(9), f32(t12).reshape(3), f32(epipole).reshape(2), _cam8(cam)
+    m12 = np.full(max(n1, 1), -1, np.int32)
+    L.ppgo_search_for_triangulation_kb8.restype = C.c_int
+    nm = L.ppgo_search_for_triangulation_kb8(n1, _p(d1, C.c_float), _p(nd1, C.c_int), _p(m1, C.c_ubyte),
+                                             _p(p1, C.c_float), n2, _p(d2, C.c_float), _p(nd2, C.c_int),
+                                             _p(m2, C.c_ubyte), _p(p2, C.c_float), _p(c8, C.c_float), _p(R, C.c_float),
+                                             _p(t, C.c_float), _p(ep, C.c_float), C.c_float(th_low), _p(m12, C.c_int))
+    return dict(nmatches=int(nm), match12=m12[:n1])
+
+
+def null_vector4(A):
+    """Right singular vector of the smallest singular value of a 4 x 4 float matrix (the stand-in for Eigen::JacobiSVD in
+    KannalaBrandt8::Triangulate, KannalaBrandt8.cpp:233-234)."""
+    a, v = f32(A).reshape(16), np.zeros(4, np.float32)
+    lib().ppgo_null_vector4(_p(a, C.c_float), _p(v, C.c_float))
+    return v
+
+
+def kb8_unproject(cam, p2d, variant=""):
+    c8, p, out = _cam8(cam), f32(p2d).reshape(2), np.zeros(3, np.float32)
+    lib(variant).ppgo_kb8_unproject(_p(c8, C.c_float), _p(p, C.c_float), _p(out, C.c_float))
+    return out
+
+
+def kb8_project(cam, p3d, variant=""):
+    c8, p, out = _cam8(cam), f32(p3d).reshape(3), np.zeros(2, np.float32)
+    lib(variant).ppgo_kb8_project(_p(c8, C.c_float), _p(p, C.c_float), _p(out, C.c_float))
+    return out
+
+
+def kb8_triangulate_matches(cam, pos1, pos2, R12, t12, variant=""):
+    """KannalaBrandt8::TriangulateMatches (KannalaBrandt8.cpp:175-222) -> (value, x3D)."""
+    L = lib(variant)
+    c8, p1, p2 = _cam8(cam), f32(pos1).reshape(2), f32(pos2).reshape(2)
+    R, t = f32(R12).reshape(9), f32(t12).reshape(3)
+    r1, x = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    L.ppgo_kb8_unproject(_p(c8, C.c_float), _p(p1, C.c_float), _p(r1, C.c_float))
+    L.ppgo_kb8_triangulate_matches.restype = C.c_float
+    z = L.ppgo_kb8_triangulate_matches(_p(c8, C.c_float), _p(r1, C.c_float), _p(p1, C.c_float), _p(p2, C.c_float),
+                                       _p(R, C.c_float), _p(t, C.c_float), _p(x, C.c_float))
+    return float(z), x

@@ -47,6 +47,13 @@ static float o_sinf(float a) {
     return (float)sin((double)a);
 #endif
 }
+static float o_tanf(float a) { /* std::tan(float), KannalaBrandt8.cpp:87 */
+#if PPGO_LIBM_FLOAT
+    return tanf(a);
+#else
+    return (float)tan((double)a);
+#endif
+}
 
 typedef struct {
     int width, height;
@@ -1016,12 +1023,27 @@ int ppgo_extend_map_matches(const ppgo_cfg *c, int P, const float *map_desc, con
 /* translation is added afterwards; no FMA (baseline x86-64).  Eigen is not available here, so   */
 /* this order is an assumption shared with the CUDA path ("parity unpinned" for this function). */
 /* KannalaBrandt8: atan2f as o_atan2f; `cos(psi)` / `sin(psi)` are unqualified calls on a float  */
-/* -> double routine, the product is carried in double and rounded once on assignment            */
-/* (PPGO_LIBM_FLOAT=1: cosf / sinf in float).                                                   */
+/* -> double routine, the product is carried in double and rounded once on assignment (both     */
+/* libm variants; see o_kb8_project).                                                           */
 /* out = {u, v, depth, viewCos}; returns mbTrackInView.  Not-in-view rows keep the reference's  */
 /* reset values (-1, -1, -1) and viewCos 0.                                                      */
 /* ------------------------------------------------------------------------------------------- */
 static float o_dot3(const float *a, const float *b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+
+/* KannalaBrandt8::project(const Eigen::Vector3f&), sensors/src/KannalaBrandt8.cpp:44-59.  cam8 = fx fy cx cy k0..k3. */
+static void o_kb8_project(const float *cam8, const float *Pc, float *u, float *v) {
+    const float x2y2 = Pc[0] * Pc[0] + Pc[1] * Pc[1];
+    const float theta = o_atan2f(sqrtf(x2y2), Pc[2]);
+    const float psi = o_atan2f(Pc[1], Pc[0]);
+    const float theta2 = theta * theta, theta3 = theta * theta2, theta5 = theta3 * theta2;
+    const float theta7 = theta5 * theta2, theta9 = theta7 * theta2;
+    const float r = theta + cam8[4] * theta3 + cam8[5] * theta5 + cam8[6] * theta7 + cam8[7] * theta9;
+    /* `cos(psi)` / `sin(psi)`: unqualified calls in a file without `using namespace std` -> ::cos(double); the product   */
+    /* is carried in double and rounded once on assignment.  Confirmed by the reference's own file compiled first in  */
+    /* oracle/ref_tu/matcher_tu.cpp: with PPGO_LIBM_FLOAT=1 (the literal atan2f) this function is bit-identical to it. */
+    *u = (float)((double)(cam8[0] * r) * cos((double)psi) + (double)cam8[2]);
+    *v = (float)((double)(cam8[1] * r) * sin((double)psi) + (double)cam8[3]);
+}
 
 int ppgo_check_in_frustum(const ppgo_cfg *c, const ppgo_bounds *b, const float *Rcw, const float *tcw,
                           const float *Ow, const float *P, const float *Pn, float minD, float maxD, float cos_limit,
@@ -1039,19 +1061,8 @@ int ppgo_check_in_frustum(const ppgo_cfg *c, const ppgo_bounds *b, const float *
         u = fx * Pc[0] / Pc[2] + cx;
         v = fy * Pc[1] / Pc[2] + cy;
     } else { /* KannalaBrandt8.cpp:46-58 */
-        const float x2y2 = Pc[0] * Pc[0] + Pc[1] * Pc[1];
-        const float theta = o_atan2f(sqrtf(x2y2), Pc[2]);
-        const float psi = o_atan2f(Pc[1], Pc[0]);
-        const float theta2 = theta * theta, theta3 = theta * theta2, theta5 = theta3 * theta2;
-        const float theta7 = theta5 * theta2, theta9 = theta7 * theta2;
-        const float r = theta + c->D[0] * theta3 + c->D[1] * theta5 + c->D[2] * theta7 + c->D[3] * theta9;
-#if PPGO_LIBM_FLOAT
-        u = fx * r * cosf(psi) + cx;
-        v = fy * r * sinf(psi) + cy;
-#else
-        u = (float)((double)(fx * r) * cos((double)psi) + (double)cx);
-        v = (float)((double)(fy * r) * sin((double)psi) + (double)cy);
-#endif
+        const float cam8[8] = {fx, fy, cx, cy, c->D[0], c->D[1], c->D[2], c->D[3]};
+        o_kb8_project(cam8, Pc, &u, &v);
     }
     if (!(u >= (float)b->minX && u < (float)b->maxX && v >= (float)b->minY && v < (float)b->maxY)) return 0; /* :238 */
     float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]}; /* :243 */
@@ -1358,6 +1369,170 @@ int ppgo_search_for_triangulation(int n1, const float *desc1, const int *node1, 
             const float num = a * x2 + b * y2 + c;
             const float dsqr = num * num / den;
             if ((double)dsqr < 3.84) {
+                bestIdx2 = i2;
+                bestDist = dist;
+            }
+        }
+        if (bestIdx2 >= 0) {
+            match12[i1] = bestIdx2;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* KannalaBrandt8::epipolarConstrain = TriangulateMatches(...) > 0.0001f, sensors/src/              */
+/* KannalaBrandt8.cpp:167-236: unproject both pixels (Newton iteration :62-91), reject small        */
+/* parallax, triangulate by the null vector of the 4 x 4 DLT matrix (:224-236), require positive    */
+/* depth in both cameras and a reprojection error below 5.991 px^2 in both images.  Everything is   */
+/* float, left to right as written; Eigen's matrix-vector products and dots as (a0*b0 + a1*b1) +    */
+/* a2*b2 (the stand-in's reading, see ppgo_check_in_frustum).                                       */
+/* The one step that is NOT the reference's arithmetic is Eigen::JacobiSVD (:233): Eigen iterates   */
+/* two-sided Jacobi rotations in float; ppgo_null_vector4 computes the same vector -- the right     */
+/* singular vector of the smallest singular value -- by cyclic Jacobi on A^T A in double and        */
+/* rounds it to float (sign: the reference divides by the last component, the sign cancels).        */
+/* ------------------------------------------------------------------------------------------- */
+void ppgo_null_vector4(const float *A, float *v4) { /* A row-major 4 x 4 */
+    double M[4][4], V[4][4];
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            double acc = (double)A[i] * (double)A[j];
+            for (int k = 1; k < 4; k++) acc = acc + (double)A[4 * k + i] * (double)A[4 * k + j];
+            M[i][j] = acc;
+            V[i][j] = i == j ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 12; sweep++) {
+        double off = 0.0;
+        for (int p = 0; p < 3; p++)
+            for (int q = p + 1; q < 4; q++) off = off + fabs(M[p][q]);
+        if (off == 0.0) break;
+        for (int p = 0; p < 3; p++)
+            for (int q = p + 1; q < 4; q++) {
+                const double apq = M[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (M[q][q] - M[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 4; k++) { /* columns p, q of M and V */
+                    const double mkp = M[k][p], mkq = M[k][q];
+                    M[k][p] = c * mkp - sn * mkq;
+                    M[k][q] = sn * mkp + c * mkq;
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - sn * vkq;
+                    V[k][q] = sn * vkp + c * vkq;
+                }
+                for (int k = 0; k < 4; k++) { /* rows p, q of M */
+                    const double mpk = M[p][k], mqk = M[q][k];
+                    M[p][k] = c * mpk - sn * mqk;
+                    M[q][k] = sn * mpk + c * mqk;
+                }
+            }
+    }
+    int best = 0;
+    for (int j = 1; j < 4; j++)
+        if (M[j][j] < M[best][best]) best = j;
+    for (int i = 0; i < 4; i++) v4[i] = (float)V[i][best];
+}
+
+/* KannalaBrandt8::unproject, :62-91 (precision = 1e-6f, :11; CV_PI / 2.f is a double narrowed by fmaxf / fminf) */
+void ppgo_kb8_unproject(const float *cam8, const float *p2D, float *out3) {
+    const float pw0 = (p2D[0] - cam8[2]) / cam8[0], pw1 = (p2D[1] - cam8[3]) / cam8[1];
+    float scale = 1.f;
+    float theta_d = sqrtf(pw0 * pw0 + pw1 * pw1);
+    theta_d = fminf(fmaxf((float)(-PPGO_PI / 2.0), theta_d), (float)(PPGO_PI / 2.0));
+    if ((double)theta_d > 1e-8) {
+        float theta = theta_d;
+        for (int j = 0; j < 10; j++) {
+            const float theta2 = theta * theta, theta4 = theta2 * theta2, theta6 = theta4 * theta2,
+                        theta8 = theta4 * theta4;
+            const float k0_theta2 = cam8[4] * theta2, k1_theta4 = cam8[5] * theta4;
+            const float k2_theta6 = cam8[6] * theta6, k3_theta8 = cam8[7] * theta8;
+            const float theta_fix = (theta * (1 + k0_theta2 + k1_theta4 + k2_theta6 + k3_theta8) - theta_d) /
+                                    (1 + 3 * k0_theta2 + 5 * k1_theta4 + 7 * k2_theta6 + 9 * k3_theta8);
+            theta = theta - theta_fix;
+            if (fabsf(theta_fix) < 1e-6f) break;
+        }
+        scale = o_tanf(theta) / theta_d;
+    }
+    out3[0] = pw0 * scale;
+    out3[1] = pw1 * scale;
+    out3[2] = 1.f;
+}
+
+void ppgo_kb8_project(const float *cam8, const float *P3, float *uv) { o_kb8_project(cam8, P3, uv, uv + 1); }
+
+/* KannalaBrandt8::TriangulateMatches, :175-222, with r1 = unproject(kp1.mPos) from the caller.  R12 row-major.      */
+/* Returns what the reference returns (z1, or -1 .. -5); x3D_out (3) may be NULL.                                   */
+float ppgo_kb8_triangulate_matches(const float *cam8, const float *r1, const float *pos1, const float *pos2,
+                                   const float *R12, const float *t12, float *x3D_out) {
+    float r2[3];
+    ppgo_kb8_unproject(cam8, pos2, r2);
+    float r21[3];
+    for (int i = 0; i < 3; i++) r21[i] = o_dot3(R12 + 3 * i, r2); /* :181 */
+    const float cosParallaxRays = o_dot3(r1, r21) / (sqrtf(o_dot3(r1, r1)) * sqrtf(o_dot3(r21, r21)));
+    if ((double)cosParallaxRays > 0.9998) return -1.f; /* :183 */
+    float R21[9], T2[12]; /* Tcw2 = [R21 | -R21 * t12], :198-200; Tcw1 = [I | 0] */
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) R21[3 * i + j] = R12[3 * j + i];
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) T2[4 * i + j] = R21[3 * i + j];
+        T2[4 * i + 3] = ((-R21[3 * i]) * t12[0] + (-R21[3 * i + 1]) * t12[1]) + (-R21[3 * i + 2]) * t12[2];
+    }
+    float A[16]; /* :227-231, coefficient-wise p * T.row(2) - T.row(k) */
+    for (int j = 0; j < 4; j++) {
+        const float t1r0 = j == 0 ? 1.f : 0.f, t1r1 = j == 1 ? 1.f : 0.f, t1r2 = j == 2 ? 1.f : 0.f;
+        A[j] = r1[0] * t1r2 - t1r0;
+        A[4 + j] = r1[1] * t1r2 - t1r1;
+        A[8 + j] = r2[0] * T2[8 + j] - T2[j];
+        A[12 + j] = r2[1] * T2[8 + j] - T2[4 + j];
+    }
+    float h[4];
+    ppgo_null_vector4(A, h); /* :233-234 (see the note above) */
+    const float x3D[3] = {h[0] / h[3], h[1] / h[3], h[2] / h[3]}; /* :235 */
+    const float z1 = x3D[2];
+    if (z1 <= 0) return -2.f; /* :205 */
+    const float z2 = o_dot3(R21 + 6, x3D) + T2[11];
+    if (z2 <= 0) return -3.f; /* :209 */
+    float uv[2];
+    o_kb8_project(cam8, x3D, uv, uv + 1);
+    const float e10 = uv[0] - pos1[0], e11 = uv[1] - pos1[1];
+    if ((double)(e10 * e10 + e11 * e11) > 5.991) return -4.f; /* :213-214 */
+    float x3D2[3];
+    for (int i = 0; i < 3; i++) x3D2[i] = o_dot3(R21 + 3 * i, x3D) + T2[4 * i + 3];
+    o_kb8_project(cam8, x3D2, uv, uv + 1);
+    const float e20 = uv[0] - pos2[0], e21 = uv[1] - pos2[1];
+    if ((double)(e20 * e20 + e21 * e21) > 5.991) return -5.f; /* :218-219 */
+    if (x3D_out) {
+        x3D_out[0] = x3D[0];
+        x3D_out[1] = x3D[1];
+        x3D_out[2] = x3D[2];
+    }
+    return z1;
+}
+
+/* Matcher::SearchForTriangulation, matching/src/Matcher.cpp:767-885, for the KannalaBrandt8 camera: as           */
+/* ppgo_search_for_triangulation with the epipolar test of KannalaBrandt8.cpp:167-172 (R12, t12 of :784-788 from     */
+/* the caller, row-major).  pos = mvKeysUn[i].mPos.                                                                  */
+int ppgo_search_for_triangulation_kb8(int n1, const float *desc1, const int *node1, const unsigned char *has_mp1,
+                                      const float *pos1, int n2, const float *desc2, const int *node2,
+                                      const unsigned char *has_mp2, const float *pos2, const float *cam8,
+                                      const float *R12, const float *t12, const float *ep, float th_low, int *match12) {
+    int nmatches = 0;
+    for (int i1 = 0; i1 < n1; i1++) {
+        match12[i1] = -1;
+        if (has_mp1[i1] || node1[i1] < 0) continue;
+        float r1[3];
+        ppgo_kb8_unproject(cam8, pos1 + 2 * i1, r1);
+        float bestDist = th_low;
+        int bestIdx2 = -1;
+        for (int i2 = 0; i2 < n2; i2++) {
+            if (node2[i2] != node1[i1] || has_mp2[i2]) continue;
+            const float dist = ppgo_descriptor_distance(desc1 + (size_t)i1 * 256, desc2 + (size_t)i2 * 256, 256);
+            if (dist > th_low || dist > bestDist) continue;
+            const float ex = ep[0] - pos2[2 * i2], ey = ep[1] - pos2[2 * i2 + 1];
+            if (sqrtf(ex * ex + ey * ey) < 10.0f) continue;
+            if (ppgo_kb8_triangulate_matches(cam8, r1, pos1 + 2 * i1, pos2 + 2 * i2, R12, t12, NULL) > 0.0001f) {
                 bestIdx2 = i2;
                 bestDist = dist;
             }

@@ -230,9 +230,10 @@ def search_for_initialization(cam, kx1, ky1, desc1, prev_matched, kx2, ky2, desc
 
 
 def search_for_triangulation(cam, R1, t1, R2, t2, pos1, desc1, node1, has_mp1, pos2, desc2, node2, has_mp2):
-    """The reference's own Matcher::SearchForTriangulation with its own Pinhole camera on two KeyFrames rebuilt from the
-    flat arrays (poses = world -> camera).  -> dict(nmatches, match12, F12 (3x3), epipole (2,)): F12 and the epipole are
-    what the reference's classes compute from the poses (Matcher.cpp:776-788, Pinhole.cpp:101-104)."""
+    """The reference's own Matcher::SearchForTriangulation with its own Pinhole / KannalaBrandt8 camera (by cam.fisheye) on
+    two KeyFrames rebuilt from the flat arrays (poses = world -> camera).  -> dict(nmatches, match12, F12 (3x3),
+    epipole (2,), R12 (3x3), t12 (3,)): what the reference's classes compute from the poses (Matcher.cpp:776-788,
+    Pinhole.cpp:101-104)."""
     lib = _lib("matcher")
     f32 = lambda a: np.ascontiguousarray(a, np.float32)
     i32 = lambda a: np.ascontiguousarray(a, np.int32)
@@ -240,13 +241,43 @@ def search_for_triangulation(cam, R1, t1, R2, t2, pos1, desc1, node1, has_mp1, p
     p1, d1, p2, d2 = f32(pos1), f32(desc1), f32(pos2), f32(desc2)
     n1, n2 = len(p1), len(p2)
     m12 = np.full(max(n1, 1), -1, np.int32)
-    F = np.zeros(9, np.float32)
-    ep = np.zeros(2, np.float32)
-    nm = lib.ref_search_for_triangulation(_p(_cam_params(cam)), cam.width, cam.height, _p(f32(R1).reshape(9)), _p(f32(t1)),
-                                          _p(f32(R2).reshape(9)), _p(f32(t2)), n1, _p(p1), _p(d1), _p(i32(node1), C.c_int),
-                                          _p(u8(has_mp1), C.c_ubyte), n2, _p(p2), _p(d2), _p(i32(node2), C.c_int),
-                                          _p(u8(has_mp2), C.c_ubyte), _p(m12, C.c_int), _p(F), _p(ep))
-    return dict(nmatches=int(nm), match12=m12[:n1], F12=F.reshape(3, 3), epipole=ep)
+    F, R12 = np.zeros(9, np.float32), np.zeros(9, np.float32)
+    ep, t12 = np.zeros(2, np.float32), np.zeros(3, np.float32)
+    nm = lib.ref_search_for_triangulation(_p(_cam_params(cam)), cam.width, cam.height, int(cam.fisheye),
+                                          _p(f32(R1).reshape(9)), _p(f32(t1)), _p(f32(R2).reshape(9)), _p(f32(t2)), n1,
+                                          _p(p1), _p(d1), _p(i32(node1), C.c_int), _p(u8(has_mp1), C.c_ubyte), n2, _p(p2),
+                                          _p(d2), _p(i32(node2), C.c_int), _p(u8(has_mp2), C.c_ubyte), _p(m12, C.c_int),
+                                          _p(F), _p(ep), _p(R12), _p(t12))
+    return dict(nmatches=int(nm), match12=m12[:n1], F12=F.reshape(3, 3), epipole=ep, R12=R12.reshape(3, 3), t12=t12)
+
+
+def kb8_triangulate(cam, pos1, pos2, R12, t12):
+    """The reference's own KannalaBrandt8::unproject / project / TriangulateMatches (JacobiSVD = the stand-in's).
+    -> dict(value, r1, r2, uv1 = project(3 * r1), x3D)."""
+    lib = _lib("matcher")
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    r1, r2, uv1, x = np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(2, np.float32), np.zeros(3, np.float32)
+    lib.ref_kb8_triangulate.restype = C.c_float
+    z = lib.ref_kb8_triangulate(_p(_cam_params(cam)), cam.width, cam.height, _p(f32(pos1)), _p(f32(pos2)),
+                                _p(f32(R12).reshape(9)), _p(f32(t12)), _p(r1), _p(r2), _p(uv1), _p(x))
+    return dict(value=float(z), r1=r1, r2=r2, uv1=uv1, x3D=x)
+
+
+def check_in_frustum(cam, Rcw, tcw, Ow, world_pos, normal, min_dist, max_dist, cos_limit=0.5):
+    """The reference's own Frame::CheckInFrustum (map/src/Frame.cpp:223-260) with its own Pinhole / KannalaBrandt8
+    camera on real MapPoint objects; same result layout as oracle.post_ref.check_in_frustum plus `visible` (the
+    IncreaseVisible count of :259)."""
+    lib = _lib("matcher")
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    wp, nr, mn, mx = f32(world_pos), f32(normal), f32(min_dist), f32(max_dist)
+    m = len(mn)
+    iv, out4, vis = np.zeros(max(m, 1), np.uint8), np.zeros((max(m, 1), 4), np.float32), np.zeros(max(m, 1), np.int32)
+    lib.ref_check_in_frustum.restype = None
+    lib.ref_check_in_frustum(_p(_cam_params(cam)), cam.width, cam.height, int(cam.fisheye), _p(f32(Rcw).reshape(9)),
+                             _p(f32(tcw)), _p(f32(Ow)), m, _p(wp), _p(nr), _p(mn), _p(mx), C.c_float(cos_limit),
+                             _p(iv, C.c_ubyte), _p(out4), _p(vis, C.c_int))
+    return dict(in_view=iv[:m], proj_uv=out4[:m, :2].copy(), depth=out4[:m, 2].copy(), view_cos=out4[:m, 3].copy(),
+                visible=vis[:m])
 
 
 def search_by_bow_kf_f(cam, desc_kf, node_kf, state_kf, desc_f, node_f, ratio):
@@ -342,9 +373,9 @@ def shim_init_both(cam, kx1, ky1, desc1, prev_matched, kx2, ky2, desc2, window, 
 
 
 def shim_triangulation_both(cam, R1, t1, R2, t2, pos1, desc1, node1, has_mp1, pos2, desc2, node2, has_mp2):
-    """The same two key frames through the reference's Matcher::SearchForTriangulation (host, its own Pinhole camera) and
-    through ppg_shim::Matcher::SearchForTriangulation (poses -> F12 / epipole with the reference's classes -> C ABI ->
-    GPU).  -> (reference result, shim result)."""
+    """The same two key frames through the reference's Matcher::SearchForTriangulation (host, its own Pinhole / KannalaBrandt8
+    camera by cam.fisheye) and through ppg_shim::Matcher::SearchForTriangulation (poses -> F12 / R12 / t12 / epipole with the
+    reference's classes -> C ABI -> GPU).  -> (reference result, shim result)."""
     lib = _lib("shim")
     f32 = lambda a: np.ascontiguousarray(a, np.float32)
     i32 = lambda a: np.ascontiguousarray(a, np.int32)
@@ -353,7 +384,7 @@ def shim_triangulation_both(cam, R1, t1, R2, t2, pos1, desc1, node1, has_mp1, po
     n1, n2 = len(p1), len(p2)
     nm = np.zeros(2, np.int32)
     m12 = np.zeros((2, max(n1, 1)), np.int32)
-    rc = lib.shim_triangulation_both(_p(_cam_params(cam)), cam.width, cam.height, _weights_dir().encode(),
+    rc = lib.shim_triangulation_both(_p(_cam_params(cam)), cam.width, cam.height, int(cam.fisheye), _weights_dir().encode(),
                                      _p(f32(R1).reshape(9)), _p(f32(t1)), _p(f32(R2).reshape(9)), _p(f32(t2)), n1, _p(p1),
                                      _p(d1), _p(i32(node1), C.c_int), _p(u8(has_mp1), C.c_ubyte), n2, _p(p2), _p(d2),
                                      _p(i32(node2), C.c_int), _p(u8(has_mp2), C.c_ubyte), _p(nm, C.c_int),

@@ -69,13 +69,70 @@ class Matrix;
 template <typename M>
 struct CommaInit {
     M& m;
-    int k;
-    template <typename T>
+    int k;                        // scalars placed so far (row by row, as Eigen's comma initialiser)
+    int br = 0, bc = 0, bh = 0;   // block cursor: top row, next column, height of the current band of blocks
+    template <typename T, typename std::enable_if<std::is_arithmetic<T>::value, int>::type = 0>
     CommaInit& operator,(T v) {
         const int c = m.cols();
-        m(k / c, k % c) = (typename M::Scalar)v;  // row by row, as Eigen's comma initialiser
+        m(k / c, k % c) = (typename M::Scalar)v;
         k++;
         return *this;
+    }
+    // a matrix operand: blocks fill a band left to right, the next band starts below (KannalaBrandt8.cpp:203, :207:
+    // `Tcw << R, t` on a 3 x 4)
+    template <typename S2, int R2, int C2>
+    CommaInit& operator,(const Matrix<S2, R2, C2>& b) {
+        if (bc + b.cols() > m.cols()) {
+            br += bh;
+            bc = 0;
+        }
+        for (int i = 0; i < b.rows(); i++)
+            for (int j = 0; j < b.cols(); j++) m(br + i, bc + j) = (typename M::Scalar)b(i, j);
+        bh = b.rows();
+        bc += b.cols();
+        return *this;
+    }
+};
+
+// `m.row(i)` of a non-const matrix: assignable, readable (KannalaBrandt8.cpp:211, :228-231)
+template <typename M>
+struct RowRef {
+    M& m;
+    int i;
+    typedef typename M::Scalar S;
+    typedef Matrix<S, 1, M::ColsAtCompileTime> Row;
+    operator Row() const {
+        Row r;
+        for (int j = 0; j < m.cols(); j++) r[j] = m(i, j);
+        return r;
+    }
+    RowRef& operator=(const Row& r) {
+        for (int j = 0; j < m.cols(); j++) m(i, j) = r[j];
+        return *this;
+    }
+    template <int N>
+    S dot(const Matrix<S, N, 1>& o) const {  // (a0*b0 + a1*b1) + a2*b2, as Matrix::dot
+        S acc = m(i, 0) * o[0];
+        for (int j = 1; j < N; j++) acc = acc + m(i, j) * o[j];
+        return acc;
+    }
+};
+
+// `v.head(n) / s` with a run-time n, assigned to a fixed vector (KannalaBrandt8.cpp:235)
+template <typename S>
+struct HeadDyn {
+    S v[4];
+    int n;
+    HeadDyn operator/(S s) const {
+        HeadDyn r = *this;
+        for (int i = 0; i < n; i++) r.v[i] = v[i] / s;
+        return r;
+    }
+    template <int N>
+    operator Matrix<S, N, 1, 0, N, 1>() const {
+        Matrix<S, N, 1, 0, N, 1> r;
+        for (int i = 0; i < N; i++) r[i] = v[i];
+        return r;
     }
 };
 
@@ -159,6 +216,29 @@ class Matrix {
     CommaInit<Matrix> operator<<(const Matrix& o) {  // `a << b` with a whole matrix: plain assignment
         *this = o;
         return CommaInit<Matrix>{*this, size()};
+    }
+    template <typename S2, int R2, int C2, typename std::enable_if<(R2 != R || C2 != C), int>::type = 0>
+    CommaInit<Matrix> operator<<(const Matrix<S2, R2, C2>& o) {  // first block of a row of blocks
+        CommaInit<Matrix> ci{*this, 0};
+        ci, o;
+        return ci;
+    }
+    RowRef<Matrix> row(int i) { return RowRef<Matrix>{*this, i}; }
+    Matrix<S, 1, C> row(int i) const {
+        Matrix<S, 1, C> r;
+        for (int j = 0; j < cols(); j++) r[j] = (*this)(i, j);
+        return r;
+    }
+    Matrix<S, R, 1> col(int j) const {
+        Matrix<S, R, 1> r;
+        for (int i = 0; i < rows(); i++) r[i] = (*this)(i, j);
+        return r;
+    }
+    HeadDyn<S> head(int n) const {
+        HeadDyn<S> h;
+        h.n = n;
+        for (int i = 0; i < n && i < 4; i++) h.v[i] = (*this)[i];
+        return h;
     }
 
     Matrix operator+(const Matrix& o) const {
@@ -338,6 +418,31 @@ typedef Matrix<float, Dynamic, Dynamic> MatrixXf;
 typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
 typedef Matrix<float, Dynamic, 1> VectorXf;
 typedef Matrix<double, Dynamic, 1> VectorXd;
+
+// JacobiSVD: only what KannalaBrandt8::Triangulate uses (sensors/src/KannalaBrandt8.cpp:233-234) -- the right singular
+// vector of the SMALLEST singular value of a 4 x 4 float matrix as matrixV().col(3).  NOT Eigen's two-sided Jacobi
+// iteration: the vector comes from oracle/ppg_oracle.c::ppgo_null_vector4 (cyclic Jacobi on A^T A in double, rounded to
+// float; checked against numpy.linalg.svd in tests/test_oracle_triangulation.py).  Eigen's own float iteration agrees with
+// it to a few float ulps of the vector; everything downstream of this vector in the reference is compiled unmodified.
+// The other columns of matrixV() are not computed (zero).
+extern "C" void ppgo_null_vector4(const float* A_rowmajor, float* v4);
+enum { ComputeFullU = 4, ComputeThinU = 8, ComputeFullV = 16, ComputeThinV = 32 };
+template <typename M>
+class JacobiSVD {
+   public:
+    JacobiSVD(const M& A, unsigned int = 0) {
+        static_assert(M::RowsAtCompileTime == 4 && M::ColsAtCompileTime == 4, "stand-in: 4 x 4 only");
+        float a[16], v[4];
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) a[4 * i + j] = (float)A(i, j);
+        ppgo_null_vector4(a, v);
+        for (int i = 0; i < 4; i++) V(i, 3) = (typename M::Scalar)v[i];
+    }
+    const M& matrixV() const { return V; }
+
+   private:
+    M V;
+};
 
 template <typename S, int N>
 class DiagonalMatrix {

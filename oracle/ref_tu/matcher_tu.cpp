@@ -36,6 +36,7 @@
 
 #define private public
 #define protected public
+#include REF_FILE(sensors/src/KannalaBrandt8.cpp)  // first: no `using namespace std` of a later file in effect
 #include REF_FILE(matching/src/Matcher.cpp)
 #include REF_FILE(feature/src/MapPoint.cpp)
 #include REF_FILE(map/src/Frame.cpp)
@@ -263,14 +264,21 @@ REF_API float ref_descriptor_distance(const float* a, const float* b) {
 #include "keyframe_raw.hpp"
 
 // params8 = fx fy cx cy + 4 distortion coefficients; R1 / t1, R2 / t2 = the world -> camera poses T1w, T2w (row-major R).
-// match12 (n1) out; F12 (9, row-major) and ep (2) out: what Matcher.cpp:776-788 and Pinhole.cpp:101-104 compute from
-// the poses, for the callers that hand the same numbers to the oracle and to the GPU.  Returns nmatches.
-REF_API int ref_search_for_triangulation(const float* params8, int width, int height, const float* R1, const float* t1,
-                                         const float* R2, const float* t2, int n1, const float* pos1, const float* desc1,
-                                         const int* node1, const unsigned char* mp1, int n2, const float* pos2,
-                                         const float* desc2, const int* node2, const unsigned char* mp2, int* match12,
-                                         float* F12out, float* epout) {
-    Pinhole cam(std::vector<float>(params8, params8 + 8), width, height, 20.f);
+// fisheye = 0: the reference's Pinhole camera, 1: its KannalaBrandt8 camera (epipolarConstrain = TriangulateMatches,
+// KannalaBrandt8.cpp:167-222, compiled unmodified; its JacobiSVD is the stand-in's, see eigen_standin.hpp).
+// match12 (n1) out; F12 (9, row-major), ep (2), R12 (9, row-major), t12 (3) out: what Matcher.cpp:776-788 and
+// Pinhole.cpp:101-104 compute from the poses, for the callers that hand the same numbers to the oracle and to the GPU.
+// Returns nmatches.
+REF_API int ref_search_for_triangulation(const float* params8, int width, int height, int fisheye, const float* R1,
+                                         const float* t1, const float* R2, const float* t2, int n1, const float* pos1,
+                                         const float* desc1, const int* node1, const unsigned char* mp1, int n2,
+                                         const float* pos2, const float* desc2, const int* node2,
+                                         const unsigned char* mp2, int* match12, float* F12out, float* epout,
+                                         float* R12out, float* t12out) {
+    const std::vector<float> prm(params8, params8 + 8);
+    GeometricCamera* camp = fisheye ? static_cast<GeometricCamera*>(new KannalaBrandt8(prm, width, height, 20.f))
+                                    : static_cast<GeometricCamera*>(new Pinhole(prm, width, height, 20.f));
+    GeometricCamera& cam = *camp;
     MapPoint* some = static_cast<MapPoint*>(calloc(1, sizeof(MapPoint)));  // only tested against nullptr
     KeyFrame* k1 = raw_keyframe(n1, pos1, desc1, node1, mp1, some, pose_of(R1, t1));
     KeyFrame* k2 = raw_keyframe(n2, pos2, desc2, node2, mp2, some, pose_of(R2, t2));
@@ -286,7 +294,11 @@ REF_API int ref_search_for_triangulation(const float* params8, int width, int he
         Eigen::Matrix3f K1 = cam.toK_(), K2 = cam.toK_();
         Eigen::Matrix3f F = K1.transpose().inverse() * t12x * R12 * K2.inverse();
         for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) F12out[3 * i + j] = F(i, j);
+            for (int j = 0; j < 3; j++) {
+                F12out[3 * i + j] = F(i, j);
+                if (R12out) R12out[3 * i + j] = R12(i, j);
+            }
+        for (int i = 0; i < 3 && t12out; i++) t12out[i] = t12[i];
         epout[0] = ep[0];
         epout[1] = ep[1];
     }
@@ -298,7 +310,35 @@ REF_API int ref_search_for_triangulation(const float* params8, int width, int he
     drop_keyframe(k1);
     drop_keyframe(k2);
     free(some);
+    delete camp;
     return nm;
+}
+
+// KannalaBrandt8::unproject / project / TriangulateMatches alone (sensors/src/KannalaBrandt8.cpp:44-91, :175-222) for the
+// unit checks of the oracle's restatement.  Returns TriangulateMatches' value; r1 / r2 (3 each) = the unprojected rays,
+// uv1 (2) = project(r1 * 3) (a point on the first ray), x3D (3) = the triangulated point when the value is > 0.
+REF_API float ref_kb8_triangulate(const float* params8, int width, int height, const float* pos1, const float* pos2,
+                                  const float* R12, const float* t12, float* r1, float* r2, float* uv1, float* x3D) {
+    KannalaBrandt8 cam(std::vector<float>(params8, params8 + 8), width, height, 20.f);
+    KeyPointEx k1(pos1[0], pos1[1], 1.f), k2(pos2[0], pos2[1], 1.f);
+    Eigen::Vector3f a = cam.unproject(k1.mPos), b = cam.unproject(k2.mPos);
+    Eigen::Vector2f p = cam.project(Eigen::Vector3f(a[0] * 3.f, a[1] * 3.f, 3.f));
+    for (int i = 0; i < 3; i++) {
+        r1[i] = a[i];
+        r2[i] = b[i];
+    }
+    uv1[0] = p[0];
+    uv1[1] = p[1];
+    Eigen::Matrix3f R;
+    Eigen::Vector3f t;
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) R(i, j) = R12[3 * i + j];
+        t[i] = t12[i];
+    }
+    Eigen::Vector3f X(0.f, 0.f, 0.f);
+    const float z = cam.TriangulateMatches(k1, k2, R, t, X);
+    for (int i = 0; i < 3; i++) x3D[i] = X[i];
+    return z;
 }
 
 // Matcher::SearchByBoW(KeyFrame*, Frame&, ...) (Matcher.cpp:393-477) on a raw key frame (state_kf: 0 no map point, 1 good,
@@ -350,4 +390,46 @@ REF_API int ref_search_by_bow_kf_kf(const float* params8, int width, int height,
     drop_keyframe(k1);
     drop_keyframe(k2);
     return nm;
+}
+
+// The real Frame::CheckInFrustum (map/src/Frame.cpp:223-260) with the reference's own camera classes -- Pinhole::project
+// (sensors/src/Pinhole.cpp:32-38) or KannalaBrandt8::project (sensors/src/KannalaBrandt8.cpp:44-59) -- and
+// GeometricCamera::IsInImage on real MapPoint objects (GetWorldPos / GetNormal / GetMin / MaxDistanceInvariance).
+// min_dist / max_dist are the invariance bounds themselves (0.5 mfMinDepth, 2 mfMaxDepth: exact in float).
+// out4 (m x 4) = mTrackProjX, mTrackProjY, mTrackDepth, mTrackViewCos (0 where not in view: the reference leaves it
+// unset); in_view = mbTrackInView; visible = mnVisible after the call (IncreaseVisible, :259).
+REF_API void ref_check_in_frustum(const float* params8, int width, int height, int fisheye, const float* Rcw,
+                                  const float* tcw, const float* Ow, int m, const float* world_pos, const float* normal,
+                                  const float* min_dist, const float* max_dist, float cos_limit, unsigned char* in_view,
+                                  float* out4, int* visible) {
+    GeometricCamera* cam = fisheye ? static_cast<GeometricCamera*>(new KannalaBrandt8(
+                                         std::vector<float>(params8, params8 + 8), width, height, 20.f))
+                                   : static_cast<GeometricCamera*>(
+                                         new Pinhole(std::vector<float>(params8, params8 + 8), width, height, 20.f));
+    Frame F;
+    F.mpCamera = cam;
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) F.mRcw(i, j) = Rcw[3 * i + j];
+        F.mtcw[i] = tcw[i];
+        F.mOw[i] = Ow[i];
+    }
+    KeyFrame* kf = static_cast<KeyFrame*>(calloc(1, sizeof(KeyFrame)));
+    for (int j = 0; j < m; j++) {
+        MapPoint* mp = new MapPoint(Eigen::Vector3f(world_pos[3 * j], world_pos[3 * j + 1], world_pos[3 * j + 2]), kf);
+        mp->mNormalVector = Eigen::Vector3f(normal[3 * j], normal[3 * j + 1], normal[3 * j + 2]);
+        mp->mfMinDepth = min_dist[j] * 2.0f;
+        mp->mfMaxDepth = max_dist[j] * 0.5f;
+        mp->mTrackViewCos = 0.f;
+        const int before = mp->mnVisible;
+        F.CheckInFrustum(mp, cos_limit);
+        in_view[j] = mp->mbTrackInView ? 1 : 0;
+        out4[4 * j] = mp->mTrackProjX;
+        out4[4 * j + 1] = mp->mTrackProjY;
+        out4[4 * j + 2] = mp->mTrackDepth;
+        out4[4 * j + 3] = mp->mTrackViewCos;
+        visible[j] = mp->mnVisible - before;
+        delete mp;
+    }
+    free(kf);
+    delete cam;
 }

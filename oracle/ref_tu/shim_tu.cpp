@@ -3,7 +3,7 @@
 // Frame objects: the same pointer graph goes once through the reference's own Matcher::ExtendMapMatches (host) and once
 // through ppg_shim::Matcher::ExtendMapMatches (flattening -> C ABI -> GPU -> write-back), and what the two leave in
 // F.mvpMapPoints / F.mvpMapEdges / mnTrackedbyFrame is handed back for comparison.  Same for SearchForInitialization and
-// SearchForTriangulation (two raw KeyFrames, the reference's own Pinhole camera).
+// SearchForTriangulation (two raw KeyFrames, the reference's own Pinhole / KannalaBrandt8 camera).
 // Links libppg_b200.so; needs a GPU at run time (tests/test_ref_pin.py, -m gpu).  TEST INFRASTRUCTURE ONLY.
 #include <algorithm>
 #include <atomic>
@@ -31,6 +31,7 @@
 
 #define private public
 #define protected public
+#include REF_FILE(sensors/src/KannalaBrandt8.cpp)  // first: before the `using namespace std` of Matcher.cpp
 #include REF_FILE(matching/src/Matcher.cpp)
 #include REF_FILE(feature/src/MapPoint.cpp)
 #include REF_FILE(map/src/Frame.cpp)
@@ -262,14 +263,18 @@ REF_API int shim_init_both(const float* params8, int width, int height, int fish
 }
 
 // Matcher::SearchForTriangulation: the reference's host function and ppg_shim::Matcher's GPU path on the same two key
-// frames with the reference's own Pinhole camera.  match12_2 = [2][max(n1, 1)]: 0 reference, 1 shim.
-REF_API int shim_triangulation_both(const float* params8, int width, int height, const char* weights, const float* R1,
+// frames with the reference's own Pinhole (fisheye = 0) or KannalaBrandt8 (1) camera.  match12_2 = [2][max(n1, 1)]:
+// 0 reference, 1 shim.
+REF_API int shim_triangulation_both(const float* params8, int width, int height, int fisheye, const char* weights, const float* R1,
                                     const float* t1, const float* R2, const float* t2, int n1, const float* pos1,
                                     const float* desc1, const int* node1, const unsigned char* mp1, int n2,
                                     const float* pos2, const float* desc2, const int* node2, const unsigned char* mp2,
                                     int* nmatches2, int* match12_2) {
     try {
-        Pinhole cam(std::vector<float>(params8, params8 + 8), width, height, 20.f);
+        const std::vector<float> prm(params8, params8 + 8);
+        std::unique_ptr<GeometricCamera> camp(fisheye ? static_cast<GeometricCamera*>(new KannalaBrandt8(prm, width, height, 20.f))
+                                                      : static_cast<GeometricCamera*>(new Pinhole(prm, width, height, 20.f)));
+        GeometricCamera& cam = *camp;
         ppg_shim::PPGExtractor ex(&cam, std::string(weights));
         MapPoint* some = static_cast<MapPoint*>(calloc(1, sizeof(MapPoint)));
         KeyFrame* k1 = raw_keyframe(n1, pos1, desc1, node1, mp1, some, pose_of(R1, t1));

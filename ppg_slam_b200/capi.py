@@ -124,7 +124,8 @@ class TriangulationMatchIn(C.Structure):
                 ("node1", C.POINTER(C.c_int32)), ("node2", C.POINTER(C.c_int32)),
                 ("has_mp1", C.POINTER(C.c_uint8)), ("has_mp2", C.POINTER(C.c_uint8)),
                 ("pos1", C.POINTER(C.c_float)), ("pos2", C.POINTER(C.c_float)),
-                ("F12", C.c_float * 9), ("epipole", C.c_float * 2), ("th_low", C.c_float)]
+                ("F12", C.c_float * 9), ("epipole", C.c_float * 2), ("th_low", C.c_float),
+                ("camera_model", C.c_int), ("cam8", C.c_float * 8), ("R12", C.c_float * 9), ("t12", C.c_float * 3)]
 
 
 class TriangulationMatchOut(C.Structure):
@@ -752,8 +753,9 @@ class Extractor:
         return dict(nmatches=o.nmatches, matches12=m12[:len(d1)], prev_matched=pm, n_rescans=o.n_rescans)
 
     def search_for_triangulation(self, desc1, node1, has_mp1, pos1, desc2, node2, has_mp2, pos2, F12, epipole,
-                                 th_low=0.7):
-        """Matcher::SearchForTriangulation (Matcher.cpp:767-885), pinhole epipolar test.  -> dict(nmatches, match12)"""
+                                 th_low=0.7, kb8=None):
+        """Matcher::SearchForTriangulation (Matcher.cpp:767-885).  kb8 = None: pinhole epipolar test from F12;
+        kb8 = (cam8, R12, t12): KannalaBrandt8::epipolarConstrain (F12 unused).  -> dict(nmatches, match12)"""
         f32 = lambda v: np.ascontiguousarray(v, np.float32)
         d1, d2, p1, p2 = f32(desc1), f32(desc2), f32(pos1), f32(pos2)
         nd1, nd2 = np.ascontiguousarray(node1, np.int32), np.ascontiguousarray(node2, np.int32)
@@ -767,6 +769,11 @@ class Extractor:
         a.has_mp2 = m2.ctypes.data_as(C.POINTER(C.c_uint8))
         a.F12 = (C.c_float * 9)(*[float(v) for v in f32(F12).reshape(9)])
         a.epipole = (C.c_float * 2)(*[float(v) for v in f32(epipole).reshape(2)])
+        if kb8 is not None:
+            a.camera_model = 1
+            a.cam8 = (C.c_float * 8)(*[float(v) for v in f32(kb8[0]).reshape(8)])
+            a.R12 = (C.c_float * 9)(*[float(v) for v in f32(kb8[1]).reshape(9)])
+            a.t12 = (C.c_float * 3)(*[float(v) for v in f32(kb8[2]).reshape(3)])
         m12 = np.full(max(len(d1), 1), -1, np.int32)
         o = TriangulationMatchOut()
         o.match12 = m12.ctypes.data_as(C.POINTER(C.c_int32))

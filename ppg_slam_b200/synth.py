@@ -225,7 +225,8 @@ def frustum_inputs(seed, cam, n_points, n_frames=1):
 
 
 def two_view_inputs(seed, cam, n1=300, n2=320, n_nodes=40, frac_mp=0.2, noise_px=0.6, desc_noise=0.05, forward=False):
-    """Two pinhole key frames looking at the same random 3-D points (Matcher::SearchForTriangulation, Matcher.cpp:767-885):
+    """Two key frames (pinhole or KannalaBrandt8, by cam.fisheye) looking at the same random 3-D points
+    (Matcher::SearchForTriangulation, Matcher.cpp:767-885):
     world -> camera poses, undistorted pixel positions, unit descriptors (those of a common point differ by desc_noise),
     one vocabulary node per feature (common points share it), a fraction of features already carrying a map point.
     Pixel noise around the epipolar test's 3.84 threshold so that both of its outcomes occur."""
@@ -246,6 +247,12 @@ def two_view_inputs(seed, cam, n1=300, n2=320, n_nodes=40, frac_mp=0.2, noise_px
 
     def proj(R, t, P):
         Pc = P @ R.T + t
+        if cam.fisheye:  # KannalaBrandt8::project (sensors/src/KannalaBrandt8.cpp:26-42): the positions are raw pixels
+            th = np.arctan2(np.hypot(Pc[:, 0], Pc[:, 1]), Pc[:, 2])
+            psi = np.arctan2(Pc[:, 1], Pc[:, 0])
+            k = [float(v) for v in cam.D]
+            rr = th + k[0] * th ** 3 + k[1] * th ** 5 + k[2] * th ** 7 + k[3] * th ** 9
+            return np.stack([fx * rr * np.cos(psi) + cx, fy * rr * np.sin(psi) + cy], 1)
         return np.stack([fx * Pc[:, 0] / Pc[:, 2] + cx, fy * Pc[:, 1] / Pc[:, 2] + cy], 1)
     d_common = r.randn(n_common, 256)
     node_common = r.randint(0, n_nodes, n_common)

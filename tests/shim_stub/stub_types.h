@@ -84,6 +84,7 @@ struct GeometricCamera {
     virtual Eigen::Vector2f project(const Eigen::Vector3f&) = 0;
     virtual Eigen::Matrix3f toK_() = 0;
     unsigned int mnType;
+    std::vector<float> mvParameters;  // sensors/include/GeometricCamera.h:87
 };
 struct MapPoint;
 struct MapEdge {

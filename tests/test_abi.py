@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libppg_b200.so does not export %s" % name
     assert sorted(capi.SYMBOLS) == declared, "capi.SYMBOLS is out of sync with include/ppg_b200.h"
-    assert lib.ppg_api_version() == 6
+    assert lib.ppg_api_version() == 7
 
 
 def test_struct_layouts_match_header():
