@@ -4,8 +4,10 @@
  * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference leg may load this.  The product (ppg_slam_b200/, include/) never does.
  *
- * Parity status: the reference ships no tests / golden vectors => "parity unpinned"
- * by the reference's own tests.  What pins this file instead:
+ * Parity status: the reference ships no tests / golden vectors.  What pins this file
+ * instead -- first of all the reference's own C++ compiled from /root/reference (oracle/ref_build.py,
+ * tests/test_ref_pin.py, tests/test_ref_pin_kb8.py: extractor post-processing, Frame grid, ExtendMapMatches,
+ * SearchForInitialization, SearchForTriangulation with both cameras, SearchByBoW x 2, CheckInFrustum), and:
  *   - the four OpenCV routines are checked bit-for-bit against cv2 4.13 (tests/test_oracle_cv.py);
  *   - the descriptor sampler is checked against torch.grid_sampler + F.normalize;
  *   - everything else follows the cited reference lines statement by statement.
@@ -1020,8 +1022,9 @@ int ppgo_extend_map_matches(const ppgo_cfg *c, int P, const float *map_desc, con
 /* of ExtendMapMatches: mbTrackInView, mTrackProjX/Y, mTrackDepth, mTrackViewCos.               */
 /* Eigen's evaluation order for the 3-vectors is taken as: a row of a 3x3 product and a dot /   */
 /* squared norm are (a0*b0 + a1*b1) + a2*b2 (unrolled redux of a fixed-size expression), the    */
-/* translation is added afterwards; no FMA (baseline x86-64).  Eigen is not available here, so   */
-/* this order is an assumption shared with the CUDA path ("parity unpinned" for this function). */
+/* translation is added afterwards; no FMA (baseline x86-64).  Eigen is not available here: this */
+/* order is the stand-in's (oracle/ref_standins), against which the reference's own Frame.cpp,   */
+/* Pinhole.cpp and KannalaBrandt8.cpp run this function in tests/test_ref_pin_kb8.py.             */
 /* KannalaBrandt8: atan2f as o_atan2f; `cos(psi)` / `sin(psi)` are unqualified calls on a float  */
 /* -> double routine, the product is carried in double and rounded once on assignment (both     */
 /* libm variants; see o_kb8_project).                                                           */
