@@ -494,6 +494,39 @@ typedef struct {
 } ppg_triangulation_match_out;
 int ppg_search_for_triangulation(ppg_ctx* ctx, const ppg_triangulation_match_in* in, ppg_triangulation_match_out* out);
 
+/* ---- the whole Matcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th) on the GPU
+ * (matching/src/Matcher.cpp:31-87; MSTracking::TrackWithMotionModel, system/src/Tracking.cpp:811/817, every tracked
+ * frame) and the whole Matcher::SearchByProjection(Frame &CurrentFrame, KeyFrame*, sAlreadyFound, th, descDist)
+ * (:1337-1411; relocalisation, Tracking.cpp:1297/1311).  Both are sequential: an accepted match occupies its keypoint
+ * for the later map points.  The rows are the map points that passed the reference's projection tests (:38-56 /
+ * :1347-1371: the caller evaluates them with the reference's own camera, ppg_shim.hpp does), in loop order; their
+ * descriptors (pMP->GetDescriptor()) are the resident table (ppg_upload_map, n_rows rows).  For every row: the window of
+ * radius th around proj_uv in the current frame (Frame::GetFeaturesInArea), the smallest DescriptorDistance over the
+ * window's keypoints that are not occupied (first minimum in visiting order), accepted iff <= max_dist (Matcher::TH_HIGH
+ * for the motion model, descDist for relocalisation); the keypoint then holds the row.
+ * kp_mp: CurrentFrame.mvpMapPoints as rows of this table -- -1 none (or a map point without observations, which does
+ * not occupy, :71-73), -2 a map point outside the table that occupies, >= 0 a row (occupies iff observed[row]).
+ * The relocalisation variant tests the pointer alone (:1386): pass observed = NULL (all ones) and -2 for every
+ * assigned keypoint. */
+typedef struct {
+    int n_rows;
+    const float* proj_uv;    /* n_rows x 2 */
+    const uint8_t* observed; /* n_rows: pMP->Observations() > 0; NULL = all */
+    int n;                   /* keypoints of CurrentFrame */
+    const float* kp_x;       /* n: mvKeysUn[i].mPos[0] */
+    const float* kp_y;
+    const float* desc;       /* n x 256: CurrentFrame.mDescriptors */
+    const int32_t* kp_mp;    /* n, or NULL = all -1 */
+    float th;                /* window radius */
+    float max_dist;          /* TH_HIGH / descDist */
+} ppg_projection_match_in;
+typedef struct {
+    int32_t* kp_mp; /* n, caller-allocated: CurrentFrame.mvpMapPoints after the call (same coding) */
+    int nmatches;
+    int n_rescans;  /* diagnostics: rows whose stored window list ran dry and were rescanned */
+} ppg_projection_match_out;
+int ppg_search_by_projection(ppg_ctx* ctx, const ppg_projection_match_in* in, ppg_projection_match_out* out);
+
 /* Device pointers of the staged association results (n_rows each), for the sharded all-gather that
  * the multi-GPU host layer issues through NCCL (ppg_slam_b200/sharded.py). */
 int ppg_assoc_device_results(ppg_ctx* ctx, void** best_idx, void** second_idx, void** best_dist, void** second_dist,

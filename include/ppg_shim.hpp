@@ -14,6 +14,7 @@
 #include <stdexcept>
 #include <map>
 #include <string>
+#include <set>
 #include <unordered_map>
 #include <vector>
 
@@ -563,6 +564,105 @@ inline int search_for_initialization(ppg_ctx* ctx, Frame& F1, Frame& F2, std::ve
     return out.nmatches;
 }
 
+// Matcher::SearchByProjection(CurrentFrame, LastFrame, th) (matching/src/Matcher.cpp:31-87; every frame tracked with the
+// motion model, system/src/Tracking.cpp:811) and SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, descDist)
+// (:1337-1411; relocalisation) whole on the GPU (ppg_search_by_projection).  The projection tests of the reference's loop
+// (:38-56 / :1347-1371) run here with the reference's own classes and expressions, in loop order; the map points that pass
+// are the rows.  The sequential part -- window, best free keypoint, accept, occupy -- runs on the device.
+namespace detail {
+inline int projection_match(ppg_ctx* ctx, Frame& CurrentFrame, const std::vector<MapPoint*>& rows,
+                            const std::vector<float>& proj_uv, bool pointer_occupies, float th, float max_dist) {
+    const int N = CurrentFrame.N, M = (int)rows.size();
+    if (M == 0 || N <= 0) return 0;
+    std::vector<float> table((size_t)M * 256), kx(N), ky(N);
+    std::vector<uint8_t> observed(M);
+    std::unordered_map<MapPoint*, int> row_of;
+    for (int r = 0; r < M; r++) {
+        const cv::Mat d = rows[r]->GetDescriptor();
+        std::memcpy(&table[(size_t)r * 256], d.ptr<float>(0), 1024);
+        observed[r] = rows[r]->Observations() > 0 ? 1 : 0;
+        row_of.emplace(rows[r], r);  // a map point listed twice keeps its first row (it cannot be tracked twice anyway)
+    }
+    std::vector<int32_t> kp_mp(N, -1), out_kp(N, -1);
+    for (int i = 0; i < N; i++) {
+        kx[i] = CurrentFrame.mvKeysUn[i].mPos[0];
+        ky[i] = CurrentFrame.mvKeysUn[i].mPos[1];
+        MapPoint* m = CurrentFrame.mvpMapPoints[i];
+        if (!m) continue;
+        if (pointer_occupies) {  // :1386 tests the pointer alone
+            kp_mp[i] = -2;
+            continue;
+        }
+        auto it = row_of.find(m);
+        kp_mp[i] = it != row_of.end() ? it->second : (m->Observations() > 0 ? -2 : -1);  // :71-73
+    }
+    check(ppg_upload_map(ctx, table.data(), M), ctx, "ppg_upload_map");
+    ppg_projection_match_in in{};
+    in.n_rows = M;
+    in.proj_uv = proj_uv.data();
+    in.observed = pointer_occupies ? nullptr : observed.data();
+    in.n = N;
+    in.kp_x = kx.data();
+    in.kp_y = ky.data();
+    in.desc = CurrentFrame.mDescriptors.ptr<float>(0);
+    in.kp_mp = kp_mp.data();
+    in.th = th;
+    in.max_dist = max_dist;
+    ppg_projection_match_out out{};
+    out.kp_mp = out_kp.data();
+    check(ppg_search_by_projection(ctx, &in, &out), ctx, "ppg_search_by_projection");
+    for (int i = 0; i < N; i++)
+        if (out_kp[i] >= 0 && out_kp[i] != kp_mp[i]) CurrentFrame.mvpMapPoints[i] = rows[out_kp[i]];  // :84 / :1403
+    return out.nmatches;
+}
+}  // namespace detail
+
+inline int search_by_projection(ppg_ctx* ctx, Frame& CurrentFrame, const Frame& LastFrame, float th, float th_high) {
+    const SE3f Tcw = CurrentFrame.GetPose();
+    std::vector<MapPoint*> rows;
+    std::vector<float> uvs;
+    for (int i = 0; i < LastFrame.N; i++) {
+        MapPoint* pMP = LastFrame.mvpMapPoints[i];
+        if (!pMP || LastFrame.mvbOutlier[i]) continue;  // :38-41
+        Eigen::Vector3f x3Dw = pMP->GetWorldPos();
+        Eigen::Vector3f x3Dc = Tcw * x3Dw;
+        const float invzc = 1.0 / x3Dc(2);
+        if (invzc < 0) continue;  // :49-50
+        Eigen::Vector2f uv = CurrentFrame.mpCamera->project(x3Dc);
+        if (!CurrentFrame.mpCamera->IsInImage(uv(0), uv(1))) continue;  // :54-55
+        rows.push_back(pMP);
+        uvs.push_back(uv(0));
+        uvs.push_back(uv(1));
+    }
+    return detail::projection_match(ctx, CurrentFrame, rows, uvs, false, th, th_high);
+}
+
+inline int search_by_projection(ppg_ctx* ctx, Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound,
+                                float th, float descDist) {
+    const SE3f Tcw = CurrentFrame.GetPose();
+    Eigen::Vector3f Ow = Tcw.inverse().translation();
+    const std::vector<MapPoint*> vpMPs = pKF->GetMapPointMatches();
+    std::vector<MapPoint*> rows;
+    std::vector<float> uvs;
+    for (size_t i = 0, iend = vpMPs.size(); i < iend; i++) {
+        MapPoint* pMP = vpMPs[i];
+        if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;  // :1350-1352
+        Eigen::Vector3f x3Dw = pMP->GetWorldPos();
+        Eigen::Vector3f x3Dc = Tcw * x3Dw;
+        const Eigen::Vector2f uv = CurrentFrame.mpCamera->project(x3Dc);
+        if (!CurrentFrame.mpCamera->IsInImage(uv(0), uv(1))) continue;  // :1360-1361
+        Eigen::Vector3f PO = x3Dw - Ow;
+        float dist3D = PO.norm();
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        if (dist3D < minDistance || dist3D > maxDistance) continue;  // :1370-1371
+        rows.push_back(pMP);
+        uvs.push_back(uv(0));
+        uvs.push_back(uv(1));
+    }
+    return detail::projection_match(ctx, CurrentFrame, rows, uvs, true, th, descDist);
+}
+
 // Matcher::SearchForTriangulation (matching/src/Matcher.cpp:767-885) whole on the GPU (ppg_search_for_triangulation)
 // for the reference's two camera models.  What depends on the two poses only -- the epipole, R12 / t12 and F12 -- is
 // computed here with the reference's own classes and expressions (:776-788, sensors/src/Pinhole.cpp:101-104); the
@@ -637,14 +737,16 @@ inline int search_for_triangulation(ppg_ctx* ctx, GeometricCamera* cam, KeyFrame
 
 #ifndef PPG_SHIM_NO_MATCHER_CLASS
 // Replaces class Matcher (matching/include/Matcher.h:20-64) for its callers: the same twelve signatures, constants and
-// public members.  Five matchers run on the GPU --
+// public members.  Seven matchers run on the GPU --
 //   ExtendMapMatches          image <-> map association of MSTracking::SearchLocalPoints (system/src/Tracking.cpp:1007)
 //   SearchByBoW(KF, F)        relocalisation / reference-keyframe tracking
 //   SearchByBoW(KF, KF)       loop / merge candidates
 //   SearchForInitialization   monocular initialisation (Tracking.cpp:525)
+//   SearchByProjection(F, F)  tracking with the motion model, every frame (Tracking.cpp:811 / :817)
+//   SearchByProjection(F, KF, sFound, ...)  relocalisation (Tracking.cpp:1297 / :1311)
 //   SearchForTriangulation    new map points in LocalMapping (Pinhole: closed-form epipolar distance;
 //                             KannalaBrandt8: the two-view triangulation of its epipolarConstrain, per pair on the device)
-// -- and the other seven (SearchByProjection x 4, SearchBySim3, Fuse x 2) are the reference's own
+// -- and the other five (SearchByProjection x 2, SearchBySim3, Fuse x 2) are the reference's own
 // host code, inherited unchanged from ::Matcher (their window-search cores are available as search_window above for
 // callers that want them on the device).
 // The ctx is the one the frame's PPGExtractor owns (PPGExtractor::context()).
@@ -672,7 +774,14 @@ public:
             return ::Matcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bCoarse);  // a camera model of the caller's own
         return search_for_triangulation(mCtx, mpCamera, pKF1, pKF2, vMatchedPairs, TH_LOW);
     }
-    // host-side matchers of the reference, unchanged
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th) {
+        return search_by_projection(mCtx, CurrentFrame, LastFrame, th, TH_HIGH);
+    }
+    int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th,
+                           const float descDist) {
+        return search_by_projection(mCtx, CurrentFrame, pKF, sAlreadyFound, th, descDist);
+    }
+    // host-side matchers of the reference, unchanged (the other two SearchByProjection overloads included)
     using ::Matcher::Fuse;
     using ::Matcher::SearchByProjection;
     using ::Matcher::SearchBySim3;

@@ -368,6 +368,24 @@ def search_for_triangulation(desc1, node1, has_mp1, pos1, desc2, node2, has_mp2,
     return dict(nmatches=int(nm), match12=m12[:n1])
 
 
+def search_by_projection(cam, map_desc, proj_uv, observed, kp_x, kp_y, frame_desc, kp_mp, th, max_dist):
+    """The sequential part of Matcher::SearchByProjection(CurrentFrame, LastFrame, th) (Matcher.cpp:31-87) and of
+    SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, descDist) (:1337-1411).  Rows = projected map points in loop
+    order; kp_mp = CurrentFrame.mvpMapPoints as rows (-1 none / unobserved, -2 occupied by a point outside the table).
+    -> dict(nmatches, kp_mp)"""
+    cfg = make_cfg(cam)
+    md, uv, kx, ky, fd = f32(map_desc), f32(proj_uv), f32(kp_x), f32(kp_y), f32(frame_desc)
+    m, n = len(md), len(kx)
+    ob = np.ones(max(m, 1), np.uint8) if observed is None else np.ascontiguousarray(observed, np.uint8)
+    km = np.full(max(n, 1), -1, np.int32) if kp_mp is None else np.ascontiguousarray(kp_mp, np.int32).copy()
+    L = lib()
+    L.ppgo_search_by_projection.restype = C.c_int
+    nm = L.ppgo_search_by_projection(C.byref(cfg), m, _p(md, C.c_float), _p(uv, C.c_float), _p(ob, C.c_ubyte), n,
+                                     _p(kx, C.c_float), _p(ky, C.c_float), _p(fd, C.c_float), _p(km, C.c_int),
+                                     C.c_float(th), C.c_float(max_dist))
+    return dict(nmatches=int(nm), kp_mp=km[:n])
+
+
 def _cam8(cam):
     return f32([cam.K[0], cam.K[4], cam.K[2], cam.K[5]] + list(cam.D))
 

@@ -1547,3 +1547,52 @@ int ppgo_search_for_triangulation_kb8(int n1, const float *desc1, const int *nod
     }
     return nmatches;
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* Matcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th), matching/src/    */
+/* Matcher.cpp:31-87 (tracking with the motion model, system/src/Tracking.cpp:811/817), and        */
+/* Matcher::SearchByProjection(Frame &CurrentFrame, KeyFrame*, sAlreadyFound, th, descDist),        */
+/* :1337-1411 (relocalisation, Tracking.cpp:1297/1311): the sequential part of both.  The rows are  */
+/* the map points that passed the caller's projection tests (:38-56 / :1347-1371), in the order of  */
+/* the reference's loop; proj_uv = mpCamera->project(Tcw * x3Dw).  For every row: window of radius  */
+/* th (Frame::GetFeaturesInArea), best DescriptorDistance (strict <: first minimum in visiting       */
+/* order) over the window features that are not occupied, accept iff best <= max_dist (TH_HIGH /    */
+/* descDist) -> CurrentFrame.mvpMapPoints[bestIdx2] = pMP, which the later rows see.                */
+/* Occupied (:71-73): mvpMapPoints[i2] && Observations() > 0 -- kp_mp[i2] >= 0 && observed[row],   */
+/* or kp_mp[i2] == -2 (a map point outside the table with observations).  The relocalisation         */
+/* variant tests mvpMapPoints[i2] alone (:1386): the caller passes observed = all ones and -2 for   */
+/* every pre-assigned keypoint.  kp_mp (n) in / out; -> nmatches.                                    */
+/* ------------------------------------------------------------------------------------------- */
+int ppgo_search_by_projection(const ppgo_cfg *c, int n_rows, const float *map_desc, const float *proj_uv,
+                              const unsigned char *observed, int n, const float *kx, const float *ky,
+                              const float *frame_desc, int *kp_mp, float th, float max_dist) {
+    ppgo_bounds b;
+    ppgo_image_bounds(c, &b);
+    int *goff = malloc(sizeof(int) * (64 * 48 + 1)), *gidx = malloc(sizeof(int) * (n > 0 ? n : 1));
+    ppgo_grid_build(&b, n, kx, ky, goff, gidx);
+    int *win = malloc(sizeof(int) * (n > 0 ? n : 1));
+    int nmatches = 0;
+    for (int r = 0; r < n_rows; r++) {
+        const int nw = ppgo_features_in_area(&b, goff, gidx, kx, ky, proj_uv[2 * r], proj_uv[2 * r + 1], th, win);
+        if (nw == 0) continue; /* :59-60 */
+        float bestDist = 1e6f;
+        int bestIdx2 = -1;
+        for (int k = 0; k < nw; k++) {
+            const int i2 = win[k];
+            if (kp_mp[i2] == -2 || (kp_mp[i2] >= 0 && observed[kp_mp[i2]])) continue; /* :71-73 */
+            const float dist = ppgo_descriptor_distance(map_desc + (size_t)r * 256, frame_desc + (size_t)i2 * 256, 256);
+            if (dist < bestDist) {
+                bestDist = dist;
+                bestIdx2 = i2;
+            }
+        }
+        if (bestDist <= max_dist) { /* :82 */
+            kp_mp[bestIdx2] = r;
+            nmatches++;
+        }
+    }
+    free(goff);
+    free(gidx);
+    free(win);
+    return nmatches;
+}

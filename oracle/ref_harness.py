@@ -280,6 +280,25 @@ def check_in_frustum(cam, Rcw, tcw, Ow, world_pos, normal, min_dist, max_dist, c
                 visible=vis[:m])
 
 
+def search_by_projection(cam, mode, x, th, desc_dist=0.7):
+    """The reference's own Matcher::SearchByProjection(CurrentFrame, LastFrame, th) (mode 0) / (CurrentFrame, pKF,
+    sAlreadyFound, th, descDist) (mode 1) on objects rebuilt from synth.projection_inputs.
+    -> dict(nmatches, kp_mp (source feature indices, -1 / -2 / -3), row_valid, proj_uv)"""
+    lib = _lib("matcher")
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    n_src, n = len(x["state"]), len(x["kp_x"])
+    km = np.ascontiguousarray(x["kp_mp"], np.int32).copy()
+    uv, valid = np.zeros((max(n_src, 1), 2), np.float32), np.zeros(max(n_src, 1), np.uint8)
+    nm = lib.ref_search_by_projection(_p(_cam_params(cam)), cam.width, cam.height, int(cam.fisheye), int(mode),
+                                      _p(f32(x["Rcw"]).reshape(9)), _p(f32(x["tcw"])), n_src, _p(f32(x["world_pos"])),
+                                      _p(f32(x["mp_desc"])), _p(u8(x["state"]), C.c_ubyte),
+                                      _p(u8(x["observed"]), C.c_ubyte), _p(f32(x["min_dist"])), _p(f32(x["max_dist"])), n,
+                                      _p(f32(x["kp_x"])), _p(f32(x["kp_y"])), _p(f32(x["desc"])), _p(km, C.c_int),
+                                      C.c_float(th), C.c_float(desc_dist), _p(uv), _p(valid, C.c_ubyte))
+    return dict(nmatches=int(nm), kp_mp=km, row_valid=valid[:n_src], proj_uv=uv[:n_src])
+
+
 def search_by_bow_kf_f(cam, desc_kf, node_kf, state_kf, desc_f, node_f, ratio):
     """The reference's own Matcher::SearchByBoW(KeyFrame*, Frame&, ...) (Matcher.cpp:393-477).  state_kf: 0 no map point,
     1 good, 2 bad.  -> dict(nmatches, f2kf): f2kf[i] = key-frame feature whose map point frame feature i received."""
@@ -392,6 +411,28 @@ def shim_triangulation_both(cam, R1, t1, R2, t2, pos1, desc1, node1, has_mp1, po
     if rc != 0:
         raise RuntimeError("shim_triangulation_both failed (rc %d, see stderr)" % rc)
     return tuple(dict(nmatches=int(nm[k]), match12=m12[k, :n1]) for k in (0, 1))
+
+
+def shim_projection_both(cam, mode, x, th, desc_dist=0.7):
+    """Matcher::SearchByProjection (mode 0 / 1, see search_by_projection) through the reference's host function and through
+    ppg_shim::Matcher (projection tests with the reference's classes -> C ABI -> GPU) on identical objects.
+    -> (reference result, shim result)"""
+    lib = _lib("shim")
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    n_src, n = len(x["state"]), len(x["kp_x"])
+    km = np.ascontiguousarray(x["kp_mp"], np.int32)
+    nm = np.zeros(2, np.int32)
+    out = np.zeros((2, max(n, 1)), np.int32)
+    rc = lib.shim_projection_both(_p(_cam_params(cam)), cam.width, cam.height, int(cam.fisheye), _weights_dir().encode(),
+                                  int(mode), _p(f32(x["Rcw"]).reshape(9)), _p(f32(x["tcw"])), n_src,
+                                  _p(f32(x["world_pos"])), _p(f32(x["mp_desc"])), _p(u8(x["state"]), C.c_ubyte),
+                                  _p(u8(x["observed"]), C.c_ubyte), _p(f32(x["min_dist"])), _p(f32(x["max_dist"])), n,
+                                  _p(f32(x["kp_x"])), _p(f32(x["kp_y"])), _p(f32(x["desc"])), _p(km, C.c_int),
+                                  C.c_float(th), C.c_float(desc_dist), _p(nm, C.c_int), _p(out, C.c_int))
+    if rc != 0:
+        raise RuntimeError("shim_projection_both failed (rc %d, see stderr)" % rc)
+    return tuple(dict(nmatches=int(nm[k]), kp_mp=out[k, :n]) for k in (0, 1))
 
 
 def shim_bow_both(cam, kf_kf, desc1, node1, state1, desc2, node2, state2, ratio):

@@ -84,5 +84,117 @@ void drop_keyframe(KeyFrame* kf) {
     kf->mvpMapPoints.~vector();
     free(kf);
 }
-}  // namespace
+// One Matcher::SearchByProjection case on objects rebuilt from flat arrays; MatcherT = ::Matcher or ppg_shim::Matcher.
+//   mode 0: SearchByProjection(CurrentFrame, LastFrame, th) (Matcher.cpp:31-87);
+//   mode 1: SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, descDist) (:1337-1411).
+//   source side (LastFrame / pKF), n_src features: state 0 no map point, 1 a map point, 2 an outlier (mode 0) / a bad
+//     point (mode 1), 3 in sAlreadyFound (mode 1); world_pos, mp_desc (GetDescriptor), observed (Observations() > 0),
+//     min_dist / max_dist (Get*DistanceInvariance, mode 1).
+//   CurrentFrame: pose Rcw / tcw, n keypoints, descriptors, kp_mp in / out: -1 none, k >= 0 the map point of source
+//     feature k, -2 / -3 a map point outside the source with / without observations.
+// Optional out, per source feature: whether the reference's tests let it search (row_valid) and its projection (proj_uv),
+// by the same expressions as :43-56 / :1355-1371 -- what a caller hands to the C ABI.
+template <class MatcherT>
+int projection_case(MatcherT& matcher, GeometricCamera* cam, int mode, const float* Rcw, const float* tcw, int n_src,
+                    const float* world_pos, const float* mp_desc, const unsigned char* state,
+                    const unsigned char* observed, const float* min_dist, const float* max_dist, int n, const float* kx,
+                    const float* ky, const float* desc, int* kp_mp, float th, float desc_dist, float* proj_uv,
+                    unsigned char* row_valid) {
+    KeyFrame* kf0 = static_cast<KeyFrame*>(calloc(1, sizeof(KeyFrame)));
+    auto point = [&](const float* P, const float* d, bool obs, bool bad, float mn, float mx) {
+        MapPoint* mp = new MapPoint(Eigen::Vector3f(P[0], P[1], P[2]), kf0);
+        mp->nObs = obs ? 1 : 0;
+        mp->mbBad = bad;
+        mp->mfMinDepth = mn * 2.0f;
+        mp->mfMaxDepth = mx * 0.5f;
+        mp->mDescriptor = cv::Mat(1, 256, CV_32F);
+        if (d) memcpy(mp->mDescriptor.data, d, 1024);
+        return mp;
+    };
+    std::vector<MapPoint*> src(n_src, nullptr);
+    for (int i = 0; i < n_src; i++)
+        if (state[i])
+            src[i] = point(world_pos + 3 * i, mp_desc + (size_t)i * 256, observed[i] != 0, mode == 1 && state[i] == 2,
+                           min_dist ? min_dist[i] : 0.f, max_dist ? max_dist[i] : 1e30f);
+    const float zero3[3] = {0, 0, 1};
+    MapPoint* outside_obs = point(zero3, nullptr, true, false, 0.f, 1e30f);
+    MapPoint* outside_unobs = point(zero3, nullptr, false, false, 0.f, 1e30f);
 
+    Frame F;  // CurrentFrame
+    F.N = n;
+    F.mpCamera = cam;
+    F.mTcw = pose_of(Rcw, tcw);
+    F.mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) F.mvKeysUn[i] = KeyPointEx(kx[i], ky[i], 1.f);
+    F.mvKeys = F.mvKeysUn;
+    F.mDescriptors = cv::Mat(std::max(n, 1), 256, CV_32F);
+    if (n > 0) memcpy(F.mDescriptors.data, desc, (size_t)n * 1024);
+    F.mvpMapPoints.assign(n, nullptr);
+    for (int i = 0; i < n; i++)
+        F.mvpMapPoints[i] = kp_mp[i] >= 0 ? src[kp_mp[i]]
+                                          : (kp_mp[i] == -2 ? outside_obs : (kp_mp[i] == -3 ? outside_unobs : nullptr));
+    F.AssignFeaturesToGrid();
+
+    if (row_valid && proj_uv) {  // the caller's side of the split: which source features search, and where
+        const SE3f Tcw = F.GetPose();
+        Eigen::Vector3f Ow = Tcw.inverse().translation();
+        for (int i = 0; i < n_src; i++) {
+            row_valid[i] = 0;
+            proj_uv[2 * i] = proj_uv[2 * i + 1] = -1.f;
+            MapPoint* pMP = src[i];
+            if (!pMP) continue;
+            if (mode == 0 ? state[i] == 2 : (pMP->isBad() || state[i] == 3)) continue;
+            Eigen::Vector3f x3Dw = pMP->GetWorldPos();
+            Eigen::Vector3f x3Dc = Tcw * x3Dw;
+            if (mode == 0) {
+                const float invzc = 1.0 / x3Dc(2);
+                if (invzc < 0) continue;
+            }
+            Eigen::Vector2f uv = cam->project(x3Dc);
+            if (!cam->IsInImage(uv(0), uv(1))) continue;
+            if (mode == 1) {
+                Eigen::Vector3f PO = x3Dw - Ow;
+                float dist3D = PO.norm();
+                if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+            }
+            row_valid[i] = 1;
+            proj_uv[2 * i] = uv(0);
+            proj_uv[2 * i + 1] = uv(1);
+        }
+    }
+
+    int nm = 0;
+    if (mode == 0) {
+        Frame L;  // LastFrame
+        L.N = n_src;
+        L.mpCamera = cam;
+        L.mvpMapPoints = src;
+        L.mvbOutlier.assign(n_src, false);
+        for (int i = 0; i < n_src; i++) L.mvbOutlier[i] = state[i] == 2;
+        nm = matcher.SearchByProjection(F, L, th);
+    } else {
+        std::vector<float> pos(2 * (size_t)std::max(n_src, 1), 0.f), dsc(256 * (size_t)std::max(n_src, 1), 0.f);
+        std::vector<int> node((size_t)std::max(n_src, 1), -1);
+        std::vector<unsigned char> none((size_t)std::max(n_src, 1), 0);
+        KeyFrame* kf = raw_keyframe(n_src, pos.data(), dsc.data(), node.data(), none.data(), nullptr, SE3f());
+        kf->mvpMapPoints = src;
+        std::set<MapPoint*> found;
+        for (int i = 0; i < n_src; i++)
+            if (state[i] == 3) found.insert(src[i]);
+        nm = matcher.SearchByProjection(F, kf, found, th, desc_dist);
+        drop_keyframe(kf);
+    }
+    std::map<MapPoint*, int> idx_of;
+    for (int i = 0; i < n_src; i++)
+        if (src[i]) idx_of[src[i]] = i;
+    for (int i = 0; i < n; i++) {
+        MapPoint* m = F.mvpMapPoints[i];
+        kp_mp[i] = !m ? -1 : (m == outside_obs ? -2 : (m == outside_unobs ? -3 : idx_of[m]));
+    }
+    for (MapPoint* m : src) delete m;
+    delete outside_obs;
+    delete outside_unobs;
+    free(kf0);
+    return nm;
+}
+}  // namespace

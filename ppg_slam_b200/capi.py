@@ -128,6 +128,17 @@ class TriangulationMatchIn(C.Structure):
                 ("camera_model", C.c_int), ("cam8", C.c_float * 8), ("R12", C.c_float * 9), ("t12", C.c_float * 3)]
 
 
+class ProjectionMatchIn(C.Structure):
+    _fields_ = [("n_rows", C.c_int), ("proj_uv", C.POINTER(C.c_float)), ("observed", C.POINTER(C.c_uint8)),
+                ("n", C.c_int), ("kp_x", C.POINTER(C.c_float)), ("kp_y", C.POINTER(C.c_float)),
+                ("desc", C.POINTER(C.c_float)), ("kp_mp", C.POINTER(C.c_int32)), ("th", C.c_float),
+                ("max_dist", C.c_float)]
+
+
+class ProjectionMatchOut(C.Structure):
+    _fields_ = [("kp_mp", C.POINTER(C.c_int32)), ("nmatches", C.c_int), ("n_rescans", C.c_int)]
+
+
 class TriangulationMatchOut(C.Structure):
     _fields_ = [("match12", C.POINTER(C.c_int32)), ("nmatches", C.c_int)]
 
@@ -147,7 +158,7 @@ SYMBOLS = ["ppg_default_config", "ppg_create", "ppg_destroy", "ppg_last_error", 
            "ppg_assoc_stage_batch_async", "ppg_extend_fetch_batch_async", "ppg_extend_collect",
            "ppg_comm_unique_id", "ppg_comm_init", "ppg_comm_destroy", "ppg_assoc_allgather",
            "ppg_assoc_allgather_fetch", "ppg_record_bytes",
-           "ppg_search_for_initialization", "ppg_search_for_triangulation"]
+           "ppg_search_for_initialization", "ppg_search_for_triangulation", "ppg_search_by_projection"]
 
 _lib = None
 
@@ -184,7 +195,7 @@ def load():
                      "ppg_host_unregister", "ppg_assoc_stage_batch_async", "ppg_extend_fetch_batch_async",
                      "ppg_extend_collect", "ppg_comm_unique_id", "ppg_comm_init", "ppg_comm_destroy",
                      "ppg_assoc_allgather", "ppg_assoc_allgather_fetch", "ppg_search_for_initialization",
-                     "ppg_search_for_triangulation"]:
+                     "ppg_search_for_triangulation", "ppg_search_by_projection"]:
             getattr(lib, name).restype = C.c_int
         lib.ppg_get_layer_output.restype = C.c_int
         lib.ppg_get_layer_output.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t,
@@ -751,6 +762,33 @@ class Extractor:
         o.prev_matched = _fp(pm)
         self._check(self.lib.ppg_search_for_initialization(self.h, C.byref(a), C.byref(o)))
         return dict(nmatches=o.nmatches, matches12=m12[:len(d1)], prev_matched=pm, n_rescans=o.n_rescans)
+
+    def search_by_projection(self, map_desc, proj_uv, observed, kp_x, kp_y, desc, kp_mp, th, max_dist):
+        """Matcher::SearchByProjection(CurrentFrame, LastFrame, th) (Matcher.cpp:31-87) / (CurrentFrame, pKF, sAlreadyFound,
+        th, descDist) (:1337-1411) whole: rows = the projected map points in loop order (map_desc, proj_uv, observed or
+        None), kp_mp = CurrentFrame.mvpMapPoints as rows (-1 / -2, or None).  -> dict(nmatches, kp_mp, n_rescans)"""
+        f32 = lambda v: np.ascontiguousarray(v, np.float32)
+        md, uv, kx, ky, d = f32(map_desc), f32(proj_uv), f32(kp_x), f32(kp_y), f32(desc)
+        m, n = len(md), len(kx)
+        if m > 0:
+            self.upload_map(md)
+        a = ProjectionMatchIn()
+        a.n_rows, a.n, a.th, a.max_dist = m, n, th, max_dist
+        a.proj_uv, a.kp_x, a.kp_y, a.desc = _fp(uv), _fp(kx), _fp(ky), _fp(d)
+        keep = []
+        if observed is not None:
+            ob = np.ascontiguousarray(observed, np.uint8)
+            keep.append(ob)
+            a.observed = ob.ctypes.data_as(C.POINTER(C.c_uint8))
+        if kp_mp is not None:
+            km = np.ascontiguousarray(kp_mp, np.int32)
+            keep.append(km)
+            a.kp_mp = km.ctypes.data_as(C.POINTER(C.c_int32))
+        res = np.full(max(n, 1), -1, np.int32)
+        o = ProjectionMatchOut()
+        o.kp_mp = res.ctypes.data_as(C.POINTER(C.c_int32))
+        self._check(self.lib.ppg_search_by_projection(self.h, C.byref(a), C.byref(o)))
+        return dict(nmatches=o.nmatches, kp_mp=res[:n], n_rescans=o.n_rescans)
 
     def search_for_triangulation(self, desc1, node1, has_mp1, pos1, desc2, node2, has_mp2, pos2, F12, epipole,
                                  th_low=0.7, kb8=None):

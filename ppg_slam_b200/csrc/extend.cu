@@ -79,6 +79,7 @@ struct ExtendState {
     // node mode (SearchByBoW): no map graph -> zero CSR / flags, identity order, every row "observed"
     int *zero_i = nullptr, *ident = nullptr, *row_node = nullptr, *kp_node = nullptr;
     uint8_t* ones_u8 = nullptr;
+    uint8_t* proj_obs = nullptr;  // [max_rows] Observations() > 0 of the rows of ppg_search_by_projection
     // pinned mirrors for the fetch
     int *h_kp_mp = nullptr, *h_kedge_me = nullptr, *h_result = nullptr;
     uint8_t* h_tracked = nullptr;
@@ -272,6 +273,9 @@ struct WalkParams {
     // and_rule (Matcher::SearchForInitialization, Matcher.cpp:582-651): spatial windows like ExtendMapMatches, but the
     // accept rule of the node mode (best <= max_dist && best < ratio * second) and every matched feature is taken
     int and_rule;
+    // best_only (Matcher::SearchByProjection x 2, Matcher.cpp:31-87 / :1337-1411): spatial windows, accept = best <= max_dist,
+    // no second best; every accepted row takes its keypoint
+    int best_only;
 };
 
 struct WalkShared {
@@ -470,12 +474,15 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                 }
                 fm &= valid;
                 const int nfree = __popc(fm);
-                if (nfree >= 2 || (cnt <= X_LIST && nfree == 1)) {
+                // (best_only needs the first free entry alone: the entries cut off the sorted list are all farther)
+                if (nfree >= 2 || (nfree == 1 && (cnt <= X_LIST || p.best_only))) {
                     const int k1 = __ffs(fm) - 1;
                     const uint32_t rest = fm & (fm - 1);
                     const float b1 = ld[k1], b2 = rest ? ld[__ffs(rest) - 1] : 1e6f;
                     bidx = (int)((lim[k1 >> 1] >> ((k1 & 1) * 16)) & 0xffffu);
-                    if (p.node_mode || p.and_rule)
+                    if (p.best_only)
+                        act = b1 <= p.max_dist ? 1 : 0;  // :82 / :1401
+                    else if (p.node_mode || p.and_rule)
                         act = ((p.strict ? b1 < p.max_dist : b1 <= p.max_dist) && b1 < p.ratio * b2) ? 1 : 0;  // :456-458
                     else
                         act = !(b1 > p.th_high && b1 > p.ratio * b2) ? 1 : 0;  // :276
@@ -577,7 +584,8 @@ __global__ void __launch_bounds__(X_THREADS, 1) extend_walk_kernel(const WalkPar
                     for (int w = 0; w < X_WARPS; w++)
                         for (int k = 0; k < 2; k++)
                             if (S.t2i[w][k] >= 0) top2_update(S.t2d[w][k], S.t2o[w][k], S.t2i[w][k], b1, o1, i1, b2, o2, i2);
-                    const bool acc = i1 >= 0 && ((p.node_mode || p.and_rule) ? ((p.strict ? b1 < p.max_dist : b1 <= p.max_dist) &&
+                    const bool acc = i1 >= 0 && (p.best_only ? b1 <= p.max_dist
+                                                 : (p.node_mode || p.and_rule) ? ((p.strict ? b1 < p.max_dist : b1 <= p.max_dist) &&
                                                                 b1 < p.ratio * b2)
                                                              : !(b1 > p.th_high && b1 > p.ratio * b2));
                     S.ev[1] = acc ? 1 : 0;
@@ -848,6 +856,7 @@ int ensure_extend(ppg_ctx* c) {
     PPG_CUDA(c, dalloc(&x->zero_i, R + N + 2));
     PPG_CUDA(c, cudaMemset(x->zero_i, 0, (R + N + 2) * 4));
     PPG_CUDA(c, dalloc(&x->ones_u8, R));
+    PPG_CUDA(c, dalloc(&x->proj_obs, R));
     PPG_CUDA(c, cudaMemset(x->ones_u8, 1, R));
     PPG_CUDA(c, dalloc(&x->row_node, R));
     PPG_CUDA(c, dalloc(&x->kp_node, N));
@@ -955,6 +964,7 @@ int run_extend(ppg_ctx* c, const FrameSrc& src, const FrameGraphSrc& gsrc, int f
     wp.max_dist = 0.f;
     wp.row_node = wp.kp_node = nullptr;
     wp.and_rule = 0;
+    wp.best_only = 0;
     extend_walk_kernel<<<frames, X_THREADS, walk_smem(x->P, s->ncap, x->ecap), c->st>>>(wp);
     c->launches++;
     stage_mark(c, "extend.walk");
@@ -1011,7 +1021,7 @@ void extend_destroy(AssocState* s) {
     if (!x) return;
     void* bufs[] = {x->row_hdr, x->observed, x->bad, x->edge_ok, x->edge_off, x->edge_other, x->order, x->l_idx, x->l_d, x->l_cnt,
                     x->tracked, x->kp_mp, x->kedge_me, x->result, x->g_es, x->g_ee, x->g_coff, x->g_cidx,
-                    x->zero_i, x->ident, x->row_node, x->kp_node, x->ones_u8};
+                    x->zero_i, x->ident, x->row_node, x->kp_node, x->ones_u8, x->proj_obs};
     for (void* b : bufs)
         if (b) cudaFree(b);
     void* hbufs[] = {x->h_kp_mp, x->h_kedge_me, x->h_result, x->h_tracked};
@@ -1379,6 +1389,7 @@ int ppg_search_for_initialization(ppg_ctx* c, const ppg_init_match_in* in, ppg_i
     wp.has_state = 0;
     wp.node_mode = 0;
     wp.and_rule = 1;
+    wp.best_only = 0;
     wp.strict = 0;
     wp.max_dist = c->cfg.th_low;
     extend_walk_kernel<<<1, X_THREADS, walk_smem(M, s->ncap, x->ecap), c->st>>>(wp);
@@ -1403,6 +1414,116 @@ int ppg_search_for_initialization(ppg_ctx* c, const ppg_init_match_in* in, ppg_i
                 out->prev_matched[2 * x->h_kp_mp[j] + 1] = in->kp2_y[j];
             }
     }
+    return PPG_OK;
+}
+
+// Matcher::SearchByProjection(CurrentFrame, LastFrame, th) (Matcher.cpp:31-87) and SearchByProjection(CurrentFrame, pKF,
+// sAlreadyFound, th, descDist) (:1337-1411) whole through the same two kernels: the rows are the projected map points in
+// loop order (their descriptors are the resident table), the window of a row is the radius-th box around its projection
+// (prep_rows_kernel, PPG_SEARCH_WINDOW), the walk keeps CurrentFrame.mvpMapPoints live and accepts with best <= max_dist.
+int ppg_search_by_projection(ppg_ctx* c, const ppg_projection_match_in* in, ppg_projection_match_out* out) {
+    if (!c || !in || !out || !out->kp_mp) return set_err(c, PPG_ERR_ARG, "ppg_search_by_projection: null argument");
+    PPG_CUDA(c, cudaSetDevice(c->dev));
+    int rc = ensure_extend(c);
+    if (rc != PPG_OK) return rc;
+    AssocState* s = c->assoc;
+    ExtendState* x = s->ext;
+    const int M = in->n_rows, N = in->n;
+    if (N < 0 || N > s->ncap || (N > 0 && (!in->kp_x || !in->kp_y || !in->desc)))
+        return set_err(c, PPG_ERR_ARG, "ppg_search_by_projection: bad keypoint arrays");
+    if (in->kp_mp)
+        for (int i = 0; i < N; i++)
+            if (in->kp_mp[i] < -2 || in->kp_mp[i] >= M)
+                return set_err(c, PPG_ERR_ARG, "ppg_search_by_projection: kp_mp row out of range");
+    out->nmatches = out->n_rescans = 0;
+    if (M == 0 || N == 0) {  // the reference's loop body never reaches a window
+        for (int i = 0; i < N; i++) out->kp_mp[i] = in->kp_mp ? in->kp_mp[i] : -1;
+        return PPG_OK;
+    }
+    if (M < 0 || M > s->n_rows || !in->proj_uv)
+        return set_err(c, PPG_ERR_ARG, "ppg_search_by_projection: upload the n_rows descriptors first (ppg_upload_map)");
+    if (!(in->th >= 0.f)) return set_err(c, PPG_ERR_ARG, "ppg_search_by_projection: negative window");
+    std::vector<float> zeros((size_t)M, 0.f);
+    if ((rc = assoc_stage_rows(c, 1, M, in->proj_uv, zeros.data(), in->th, 1.f)) != PPG_OK) return rc;
+    s->mode = PPG_SEARCH_WINDOW;  // r = th for every row (GetFeaturesInArea(u, v, th), :58)
+    PPG_CUDA(c, cudaMemcpyAsync(s->kx, in->kp_x, (size_t)N * 4, cudaMemcpyHostToDevice, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(s->ky, in->kp_y, (size_t)N * 4, cudaMemcpyHostToDevice, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(s->fdesc, in->desc, (size_t)N * 1024, cudaMemcpyHostToDevice, c->st));
+    if (in->kp_mp)
+        PPG_CUDA(c, cudaMemcpyAsync(x->kp_mp, in->kp_mp, (size_t)N * 4, cudaMemcpyHostToDevice, c->st));
+    else
+        PPG_CUDA(c, cudaMemsetAsync(x->kp_mp, 0xff, (size_t)N * 4, c->st));
+    PPG_CUDA(c, cudaMemsetAsync(x->tracked, 0, (size_t)M, c->st));
+    const uint8_t* obs = x->ones_u8;
+    if (in->observed) {  // per-row Observations() > 0: borrowed from the map-graph flags of this ctx
+        PPG_CUDA(c, cudaMemcpyAsync(x->proj_obs, in->observed, (size_t)M, cudaMemcpyHostToDevice, c->st));
+        obs = x->proj_obs;
+    }
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));  // pageable sources
+    s->staged_n = N;
+    FrameSrc src = assoc_staged_src(s);
+    src.free_mask = s->ones;
+    if ((rc = assoc_prep(c, src, 1)) != PPG_OK) return rc;
+    ListParams lp{};
+    lp.nc = M;
+    lp.max_rows = s->max_rows;
+    lp.ncap = s->ncap;
+    lp.src = src;
+    lp.order = x->ident;
+    lp.rowp = s->rowp;
+    lp.map_f32 = s->map_f32;
+    lp.kinfo = s->kinfo;
+    lp.korder = s->korder;
+    lp.l_idx = x->l_idx;
+    lp.l_d = x->l_d;
+    lp.l_cnt = x->l_cnt;
+    lp.node_mode = 0;
+    extend_lists_kernel<<<dim3((M + XL_ROWS - 1) / XL_ROWS, 1), 256, 0, c->st>>>(lp);
+    stage_mark(c, "proj_match.lists");
+    WalkParams wp{};
+    wp.nc = M;
+    wp.P = M;
+    wp.max_rows = s->max_rows;
+    wp.ncap = s->ncap;
+    wp.ecap = x->ecap;
+    wp.src = src;
+    FrameGraphSrc g{};
+    g.coff = reinterpret_cast<const uint8_t*>(x->zero_i);  // no key edges
+    g.es = g.ee = g.cidx = g.coff;
+    g.ne_val = 0;
+    wp.gsrc = g;
+    wp.order = x->ident;
+    wp.rowp = s->rowp;
+    wp.map_f32 = s->map_f32;
+    wp.kinfo = s->kinfo;
+    wp.korder = s->korder;
+    wp.l_idx = x->l_idx;
+    wp.l_d = x->l_d;
+    wp.l_cnt = x->l_cnt;
+    wp.observed = obs;
+    wp.bad = reinterpret_cast<const uint8_t*>(x->zero_i);
+    wp.edge_ok = reinterpret_cast<const uint8_t*>(x->zero_i);
+    wp.edge_off = x->zero_i;
+    wp.edge_other = x->zero_i;
+    wp.tracked = x->tracked;
+    wp.kp_mp = x->kp_mp;
+    wp.kedge_me = x->kedge_me;
+    wp.result = x->result;
+    wp.ratio = 1.f;
+    wp.th_high = c->cfg.th_high;
+    wp.has_state = 1;
+    wp.best_only = 1;
+    wp.max_dist = in->max_dist;
+    extend_walk_kernel<<<1, X_THREADS, walk_smem(M, s->ncap, x->ecap), c->st>>>(wp);
+    stage_mark(c, "proj_match.walk");
+    c->launches += 2;
+    PPG_CUDA(c, cudaGetLastError());
+    PPG_CUDA(c, cudaMemcpyAsync(x->h_result, x->result, XR_WORDS * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaMemcpyAsync(x->h_kp_mp, x->kp_mp, (size_t)N * 4, cudaMemcpyDeviceToHost, c->st));
+    PPG_CUDA(c, cudaStreamSynchronize(c->st));
+    out->nmatches = x->h_result[XR_ACCEPTED];
+    out->n_rescans = x->h_result[XR_RESCANS];
+    memcpy(out->kp_mp, x->h_kp_mp, (size_t)N * 4);
     return PPG_OK;
 }
 

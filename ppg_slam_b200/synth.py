@@ -315,3 +315,101 @@ def bow_rows(desc, node, state):
     index).  -> (feature index of every row, row descriptors, row nodes)"""
     idx = np.array([i for i in np.lexsort((np.arange(len(node)), node)) if node[i] >= 0 and state[i] == 1], np.int64)
     return idx, desc[idx], node[idx].astype(np.int32)
+
+
+def projection_inputs(seed, cam, n_src=300, n=340, noise_px=2.0, desc_noise=0.35, frac_dup=0.25, frac_assigned=0.1):
+    """A current frame and a source of map points (the last frame / a key frame) for Matcher::SearchByProjection
+    (Matcher.cpp:31-87, :1337-1411): a pose, map points that project onto (or near, or next to) the current frame's
+    keypoints -- several of them onto the SAME keypoint with near-identical descriptors, so that the order of the walk and
+    the live occupancy decide --, points behind the camera and outside the image, source features without a point,
+    outliers / bad points, unobserved points (they do not occupy), pre-assigned keypoints, distance bands."""
+    r = np.random.RandomState(seed)
+    fx, fy, cx, cy = float(cam.K[0]), float(cam.K[4]), float(cam.K[2]), float(cam.K[5])
+
+    def proj(Pc):
+        if cam.fisheye:
+            th = np.arctan2(np.hypot(Pc[:, 0], Pc[:, 1]), Pc[:, 2])
+            psi = np.arctan2(Pc[:, 1], Pc[:, 0])
+            k = [float(v) for v in cam.D]
+            rr = th + k[0] * th ** 3 + k[1] * th ** 5 + k[2] * th ** 7 + k[3] * th ** 9
+            return np.stack([fx * rr * np.cos(psi) + cx, fy * rr * np.sin(psi) + cy], 1)
+        return np.stack([fx * Pc[:, 0] / Pc[:, 2] + cx, fy * Pc[:, 1] / Pc[:, 2] + cy], 1)
+    w = r.normal(0, 0.05, 3)
+    ang = np.linalg.norm(w)
+    k = w / ang
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    Rcw = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+    tcw = r.normal(0, 0.2, 3)
+    # camera-frame points spread over (and a little beyond) the field of view
+    z = r.uniform(1.5, 10.0, n_src)
+    span = 0.55 if not cam.fisheye else 0.9
+    Pc = np.stack([r.uniform(-span, span, n_src) * z * cam.width / (2 * fx) * 2,
+                   r.uniform(-span, span, n_src) * z * cam.height / (2 * fy) * 2, z], 1)
+    n_dup = int(frac_dup * n_src)
+    for i in range(n_src - n_dup, n_src):  # the same spot as an earlier point, a little deeper
+        j = r.randint(0, n_src - n_dup)
+        Pc[i] = Pc[j] * (1 + 0.02 * r.rand())
+    behind = r.rand(n_src) < 0.04
+    Pc[behind, 2] *= -1
+    uv = proj(np.where(behind[:, None], Pc * [1, 1, -1], Pc))
+    world = (Pc - tcw) @ Rcw  # Rcw^T (Pc - tcw)
+    # current-frame keypoints: on the projections (with noise around the window radius), the rest anywhere
+    kp = np.stack([r.uniform(0, cam.width, n), r.uniform(0, cam.height, n)], 1)
+    kd = r.randn(n, 256)
+    n_on = min(n, n_src - n_dup) * 3 // 4
+    tgt = r.permutation(n_src - n_dup)[:n_on]
+    kp[:n_on] = uv[tgt] + noise_px * r.randn(n_on, 2) * r.choice([0.5, 1.0, 4.0], (n_on, 1))
+    kd /= np.linalg.norm(kd, axis=1, keepdims=True)
+    md = r.randn(n_src, 256)
+    md /= np.linalg.norm(md, axis=1, keepdims=True)
+    md[tgt] = kd[:n_on] + desc_noise / 16 * r.randn(n_on, 256) * r.choice([0.3, 1.0, 2.2], (n_on, 1))
+    for i in range(n_src - n_dup, n_src):
+        j = int(np.argmin(np.abs(Pc[:n_src - n_dup] - Pc[i] / np.linalg.norm(Pc[i]) * np.linalg.norm(Pc[:n_src - n_dup], axis=1, keepdims=True)).sum(1)))
+        md[i] = md[j] + 0.01 * r.randn(256)
+    md /= np.linalg.norm(md, axis=1, keepdims=True)
+    perm = r.permutation(n)
+    kp, kd = kp[perm], kd[perm]
+    u = r.rand(n_src)
+    state = np.where(u < 0.08, 0, np.where(u < 0.16, 2, np.where(u < 0.2, 3, 1))).astype(np.uint8)
+    observed = (r.rand(n_src) < 0.8).astype(np.uint8)
+    d3 = np.linalg.norm(Pc, axis=1)
+    min_d = d3 * r.uniform(0.3, 1.03, n_src)
+    max_d = d3 * r.uniform(0.97, 3.0, n_src)
+    kp_mp = np.full(n, -1, np.int32)
+    pre = np.nonzero(r.rand(n) < frac_assigned)[0]
+    for i in pre:
+        c = r.randint(3)
+        kp_mp[i] = -2 if c == 0 else (-3 if c == 1 else r.randint(n_src))
+    for i in pre:  # a pre-assigned source feature must hold a point
+        if kp_mp[i] >= 0 and state[kp_mp[i]] == 0:
+            kp_mp[i] = -2
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    return dict(Rcw=f(Rcw), tcw=f(tcw), world_pos=f(world), mp_desc=f(md), state=state, observed=observed,
+                min_dist=f(min_d), max_dist=f(max_d), kp_x=f(kp[:, 0]), kp_y=f(kp[:, 1]), desc=f(kd), kp_mp=kp_mp)
+
+
+def projection_rows(x, mode, ref_row_valid, ref_proj_uv):
+    """Flat source features -> the rows the C ABI / the oracle take (the features the reference's tests let through, in
+    loop order) and CurrentFrame.mvpMapPoints recoded as rows.  -> dict(rows, map_desc, proj_uv, observed, kp_mp)"""
+    rows = np.nonzero(ref_row_valid)[0].astype(np.int32)
+    row_of = {int(s): k for k, s in enumerate(rows)}
+    km = np.full(len(x["kp_mp"]), -1, np.int32)
+    for i, v in enumerate(x["kp_mp"]):
+        v = int(v)
+        if mode == 1:  # relocalisation tests the pointer alone (:1386)
+            km[i] = -1 if v == -1 else -2
+        elif v >= 0:
+            km[i] = row_of[v] if v in row_of else (-2 if x["observed"][v] else -1)
+        else:
+            km[i] = -2 if v == -2 else -1
+    return dict(rows=rows, map_desc=x["mp_desc"][rows], proj_uv=ref_proj_uv[rows],
+                observed=None if mode == 1 else x["observed"][rows], kp_mp=km)
+
+
+def projection_result(x, rows, kp_mp_rows):
+    """kp_mp in rows after the call -> the reference's coding (source feature index; untouched keypoints keep theirs)."""
+    out = np.array(x["kp_mp"], np.int32).copy()
+    for i, v in enumerate(kp_mp_rows):
+        if v >= 0:
+            out[i] = rows[v]
+    return out

@@ -37,10 +37,14 @@ struct Vector2f {
     float v[2];
     float& operator[](int i) { return v[i]; }
     float operator[](int i) const { return v[i]; }
+    float operator()(int i) const { return v[i]; }
 };
 struct Vector3f {
     float v[3];
     float operator[](int i) const { return v[i]; }
+    float operator()(int i) const { return v[i]; }
+    Vector3f operator-(const Vector3f&) const { return *this; }
+    float norm() const { return 0.f; }
 };
 struct Matrix3f {
     float m[9];
@@ -54,6 +58,7 @@ struct SE3f {
     Eigen::Matrix3f rotationMatrix() const { return Eigen::Matrix3f(); }
     Eigen::Vector3f translation() const { return Eigen::Vector3f(); }
     SE3f operator*(const SE3f&) const { return *this; }
+    SE3f inverse() const { return *this; }
     Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return p; }
 };
 struct SO3f {
@@ -83,6 +88,7 @@ struct GeometricCamera {
     virtual int imHeight() = 0;
     virtual Eigen::Vector2f project(const Eigen::Vector3f&) = 0;
     virtual Eigen::Matrix3f toK_() = 0;
+    bool IsInImage(const float&, const float&) const { return true; }
     unsigned int mnType;
     std::vector<float> mvParameters;  // sensors/include/GeometricCamera.h:87
 };
@@ -93,10 +99,7 @@ struct MapEdge {
     MapPoint* theOtherPt(MapPoint* p) { return p == mpMPs ? mpMPe : (p == mpMPe ? mpMPs : nullptr); }
     bool isBad() { return mbBad; }
 };
-struct Vec3f {
-    float v[3];
-    float operator[](int i) const { return v[i]; }
-};
+typedef Eigen::Vector3f Vec3f;
 struct Mat3f {
     float m[9];
     float operator()(int r, int c) const { return m[3 * r + c]; }
@@ -127,6 +130,10 @@ struct KeyFrame {
     Eigen::Vector3f GetCameraCenter() { return Eigen::Vector3f(); }
 };
 struct Frame {
+    int N = 0;
+    GeometricCamera* mpCamera = nullptr;
+    std::vector<bool> mvbOutlier;
+    SE3f GetPose() const { return SE3f(); }
     Mat3f mRcw;
     Vec3f mtcw, mOw;
     std::map<unsigned int, double> mBowVec;                      // DBoW3::BowVector
