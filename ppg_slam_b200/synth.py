@@ -384,8 +384,10 @@ def projection_inputs(seed, cam, n_src=300, n=340, noise_px=2.0, desc_noise=0.35
         if kp_mp[i] >= 0 and state[kp_mp[i]] == 0:
             kp_mp[i] = -2
     f = lambda a: np.ascontiguousarray(a, np.float32)
+    inside = (~behind) & (uv[:, 0] >= 0) & (uv[:, 0] < cam.width) & (uv[:, 1] >= 0) & (uv[:, 1] < cam.height)
     return dict(Rcw=f(Rcw), tcw=f(tcw), world_pos=f(world), mp_desc=f(md), state=state, observed=observed,
-                min_dist=f(min_d), max_dist=f(max_d), kp_x=f(kp[:, 0]), kp_y=f(kp[:, 1]), desc=f(kd), kp_mp=kp_mp)
+                min_dist=f(min_d), max_dist=f(max_d), kp_x=f(kp[:, 0]), kp_y=f(kp[:, 1]), desc=f(kd), kp_mp=kp_mp,
+                uv_numpy=f(uv), inside_numpy=inside.astype(np.uint8))  # the projection in numpy (no reference needed)
 
 
 def projection_rows(x, mode, ref_row_valid, ref_proj_uv):

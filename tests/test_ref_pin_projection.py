@@ -130,13 +130,8 @@ def test_cuda_search_by_projection_equals_oracle_sweep():
                 th = [15.0, 7.0, 60.0, 30.0][seed % 4]
                 mode = seed % 2
                 x = synth.projection_inputs(500 + seed, cam, n_src=n_src, n=n, frac_dup=[0.25, 0.6][seed % 2])
-                rs = np.random.RandomState(seed)
-                valid = (x["state"] == 1) & (rs.rand(n_src) < 0.9)  # any subset: the split is the caller's
-                uv = np.stack([rs.uniform(0, cam.width, n_src), rs.uniform(0, cam.height, n_src)], 1).astype(np.float32)
-                on = rs.rand(n_src) < 0.8  # most rows land on a keypoint
-                tgt = rs.randint(0, n, n_src)
-                uv[on, 0] = x["kp_x"][tgt[on]] + rs.randn(on.sum()).astype(np.float32) * 2
-                uv[on, 1] = x["kp_y"][tgt[on]] + rs.randn(on.sum()).astype(np.float32) * 2
+                valid = (x["state"] == 1) & (x["inside_numpy"] > 0)  # the split is the caller's: numpy's projection here
+                uv = x["uv_numpy"]
                 d = dict(x, mode=mode, th=th, dd=[0.8, 0.5][mode])
                 nm0, want, _ = _run(lambda *a: O.search_by_projection(cam, *a), d, valid, uv)
                 q = synth.projection_rows(d, mode, valid, uv)
