@@ -41,6 +41,7 @@ constexpr int X_LCAP = PPG_EXTEND_MAX_DEGREE;        // map edges per map point 
 constexpr int X_WCAP = PPG_EXTEND_MAX_WEIGHTS;       // weight-matrix entries per seed
 constexpr int X_THREADS = 256, X_WARPS = X_THREADS / 32;
 constexpr int X_NOEVENT = 1 << 20;
+constexpr int G_CELLS = 64 * 48;                     // FRAME_GRID_COLS x FRAME_GRID_ROWS (GeometricCamera.h:79-80)
 
 // Where the point-pair graph of frame f lives: staged arrays (one frame) or the extraction output blocks.
 struct FrameGraphSrc {
@@ -80,6 +81,10 @@ struct ExtendState {
     int *zero_i = nullptr, *ident = nullptr, *row_node = nullptr, *kp_node = nullptr;
     uint8_t* ones_u8 = nullptr;
     uint8_t* proj_obs = nullptr;  // [max_rows] Observations() > 0 of the rows of ppg_search_by_projection
+    // Frame grid of every frame of the batch in GetFeaturesInArea's visiting order (grid_index_kernel)
+    float2* gs_xy = nullptr;      // [bcap][ncap] positions by rank
+    uint16_t* gs_idx = nullptr;   // [bcap][ncap] keypoint index by rank
+    uint16_t* gs_start = nullptr; // [bcap][G_CELLS + 1] first rank of every cell (cx * 48 + cy)
     // pinned mirrors for the fetch
     int *h_kp_mp = nullptr, *h_kedge_me = nullptr, *h_result = nullptr;
     uint8_t* h_tracked = nullptr;
@@ -104,7 +109,80 @@ struct ListParams {
     int node_mode;
     const int* row_node;
     const int* kp_node;
+    // spatial mode: the frame grid by rank (grid_index_kernel)
+    const float2* gs_xy;
+    const uint16_t* gs_idx;
+    const uint16_t* gs_start;
 };
+
+// The frame grid of Frame::AssignFeaturesToGrid (Frame.cpp:138-156) as a CSR in GetFeaturesInArea's visiting order
+// (Frame.cpp:294-312: cell columns ix ascending, rows iy ascending, the keypoints of a cell in insertion = index order):
+// rank-sorted positions / indices of the indexable, free keypoints and the first rank of every cell.  A search window
+// then is, per cell column, ONE contiguous interval of ranks.  One CTA per frame; kinfo from prep_frame_kernel.
+__global__ void __launch_bounds__(256) grid_index_kernel(const FrameSrc src, int ncap, const uint32_t* __restrict__ kinfo,
+                                                         float2* __restrict__ gs_xy, uint16_t* __restrict__ gs_idx,
+                                                         uint16_t* __restrict__ gs_start) {
+    __shared__ uint32_t cnt[G_CELLS];
+    __shared__ uint16_t start[G_CELLS + 1];
+    __shared__ uint32_t wsum[8];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = min(src.n_of(f), ncap);
+    const uint32_t* info = kinfo + (size_t)f * ncap;
+    for (int k = tid; k < G_CELLS; k += 256) cnt[k] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const uint32_t v = info[i];
+        if (v & 0x10000u) atomicAdd(&cnt[(v & 0xffu) * 48 + ((v >> 8) & 0xffu)], 1u);
+    }
+    __syncthreads();
+    {   // exclusive scan of the 3072 counters: 12 per thread
+        uint32_t loc[12], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            loc[k] = sum;
+            sum += cnt[tid * 12 + k];
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1) {
+            const uint32_t t = __shfl_up_sync(AFULL, inc, m);
+            if (lane >= m) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint32_t base = inc - sum;
+        for (int w = 0; w < warp; w++) base += wsum[w];
+#pragma unroll
+        for (int k = 0; k < 12; k++) start[tid * 12 + k] = (uint16_t)(base + loc[k]);
+        if (tid == 255) start[G_CELLS] = (uint16_t)(base + sum);
+    }
+    __syncthreads();
+    for (int k = tid; k < G_CELLS; k += 256) cnt[k] = 0;  // now: keypoints of the cell placed so far
+    __syncthreads();
+    if (warp == 0) {  // ascending index, 32 at a time: rank = first rank of the cell + earlier keypoints of the same cell
+        const float* kx = src.kx_of(f);
+        const float* ky = src.ky_of(f);
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const uint32_t v = i < n ? info[i] : 0u;
+            const bool ok = (v & 0x10000u) != 0u;
+            const uint32_t cell = (v & 0xffu) * 48 + ((v >> 8) & 0xffu);
+            const unsigned grp = __match_any_sync(AFULL, ok ? cell : (uint32_t)(G_CELLS + lane));
+            const int off = __popc(grp & ((1u << lane) - 1u));
+            uint32_t before = 0;
+            if (ok) before = cnt[cell];
+            __syncwarp();
+            if (ok && off == 0) cnt[cell] = before + __popc(grp);
+            __syncwarp();
+            if (ok) {
+                const size_t o = (size_t)f * ncap + start[cell] + before + off;
+                gs_xy[o] = make_float2(kx[i], ky[i]);
+                gs_idx[o] = (uint16_t)i;
+            }
+        }
+    }
+    for (int k = tid; k <= G_CELLS; k += 256) gs_start[(size_t)f * (G_CELLS + 1) + k] = start[k];
+}
 
 // DescriptorDistance with both rows already in registers (same operation order as exact_distance).
 __device__ __forceinline__ float exact_distance_rr(const float (&av)[8], const float (&bv)[8]) {
@@ -124,10 +202,15 @@ constexpr int XL_ROWS = 64;  // rows per CTA (8 per warp): the frame's keypoint 
 // grid (ceil(nc / XL_ROWS), frames).  The window scan reads the keypoint table from shared memory; the hits of a row
 // are collected first and their descriptor rows are then fetched four at a time (the first version took one
 // dependent round of global loads per 32 keypoints scanned and one per hit: 0.39 ms per 32 frames x 8192 rows).
-__global__ void __launch_bounds__(256) extend_lists_kernel(const ListParams p) {
-    __shared__ float s_kx[1024], s_ky[1024];
-    __shared__ uint32_t s_info[1024], s_ord[1024];
+__global__ void __launch_bounds__(256, 4) extend_lists_kernel(const ListParams p) {
+    __shared__ uint32_t s_ord[1024];
     __shared__ uint16_t s_hit[8][1024];
+    // node mode: the node of every feature; spatial mode: the frame grid by rank (positions, indices, cell starts)
+    __shared__ __align__(8) uint8_t s_mode[1024 * 8 + 1024 * 2 + (G_CELLS + 2) * 2];
+    uint32_t* s_info = reinterpret_cast<uint32_t*>(s_mode);
+    float2* s_sxy = reinterpret_cast<float2*>(s_mode);
+    uint16_t* s_sidx = reinterpret_cast<uint16_t*>(s_mode + 1024 * 8);
+    uint16_t* s_start = s_sidx + 1024;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, f = blockIdx.y;
     const int n = min(p.src.n_of(f), p.ncap);
     if (p.node_mode) {
@@ -136,15 +219,17 @@ __global__ void __launch_bounds__(256) extend_lists_kernel(const ListParams p) {
             s_ord[i] = (uint32_t)i;  // vIndicesF is filled in feature order
         }
     } else {
-        const float* kx = p.src.kx_of(f);
-        const float* ky = p.src.ky_of(f);
-        const uint32_t* kinfo = p.kinfo + (size_t)f * p.ncap;
         const uint32_t* korder = p.korder + (size_t)f * p.ncap;
-        for (int i = threadIdx.x; i < n; i += 256) {
-            s_kx[i] = kx[i];
-            s_ky[i] = ky[i];
-            s_info[i] = kinfo[i];
-            s_ord[i] = korder[i];
+        const float2* gxy = p.gs_xy + (size_t)f * p.ncap;
+        const uint16_t* gidx = p.gs_idx + (size_t)f * p.ncap;
+        const uint16_t* gst = p.gs_start + (size_t)f * (G_CELLS + 1);
+        for (int k = threadIdx.x; k <= G_CELLS; k += 256) s_start[k] = gst[k];
+        for (int i = threadIdx.x; i < n; i += 256) s_ord[i] = korder[i];
+        __syncthreads();
+        const int ng = s_start[G_CELLS];  // indexable, free keypoints
+        for (int i = threadIdx.x; i < ng; i += 256) {
+            s_sxy[i] = gxy[i];
+            s_sidx[i] = gidx[i];
         }
     }
     __syncthreads();
@@ -153,6 +238,7 @@ __global__ void __launch_bounds__(256) extend_lists_kernel(const ListParams p) {
         const int q = blockIdx.x * XL_ROWS + r * 8 + warp;
         if (q >= p.nc) break;
         const int row = p.order[q];
+        const int row_next = q + 8 < p.nc && r + 1 < XL_ROWS / 8 ? p.order[q + 8] : -1;  // this warp's next row
         const size_t o = (size_t)f * p.max_rows + row, ol = (size_t)f * p.max_rows + q;
         RowParam rp;
         rp.cells = 0;
@@ -172,39 +258,51 @@ __global__ void __launch_bounds__(256) extend_lists_kernel(const ListParams p) {
             float a[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) a[k] = p.map_f32[(size_t)row * 256 + lane + 32 * k];
-            // window scan, four groups of 32 keypoints per iteration.  The distance test of Frame.cpp:305-309 goes first:
-            // two subtractions reject ~98 % of the keypoints, the literal cell-range / indexable test runs only for the
-            // few that pass.  (Neither the reordering nor the unrolling moved the kernel time by more than 3 %: with
-            // ~10 window hits per map point the exact distances -- 1 KB from L2 and ~80 instructions each -- dominate.)
             const uint32_t cx0 = rp.cells & 0xff, cx1 = (rp.cells >> 8) & 0xff, cy0 = (rp.cells >> 16) & 0xff,
                            cy1 = rp.cells >> 24;
-            for (int c0 = 0; c0 < n; c0 += 128) {
-                bool in[4];
+            if (p.node_mode) {
+                // the features of the row's node, four groups of 32 per iteration (Matcher.cpp:417-418)
+                for (int c0 = 0; c0 < n; c0 += 128) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int c = c0 + 32 * u + lane;
-                    if (p.node_mode)
-                        in[u] = c < n && (int)s_info[c] == my_node;  // Matcher.cpp:417-418
-                    else
-                        in[u] = c < n && fabsf(s_kx[c] - rp.u) < rp.r && fabsf(s_ky[c] - rp.v) < rp.r;
+                    for (int u = 0; u < 4; u++) {
+                        const int c = c0 + 32 * u + lane;
+                        const bool in = c < n && (int)s_info[c] == my_node;
+                        const unsigned mask = __ballot_sync(AFULL, in);
+                        if (in) s_hit[warp][nh + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)c;
+                        nh += __popc(mask);
+                    }
                 }
-                if (!p.node_mode) {
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (in[u]) {  // Frame::GetFeaturesInArea's cell range (Frame.cpp:270-303) + PosInGrid
-                            const uint32_t info = s_info[c0 + 32 * u + lane];
-                            const uint32_t cx = info & 0xff, cy = (info >> 8) & 0xff;
-                            in[u] = (info & 0x10000u) && cx >= cx0 && cx <= cx1 && cy >= cy0 && cy <= cy1;
+            } else {
+                // Frame::GetFeaturesInArea (Frame.cpp:262-315) over the grid: the cells [cx0, cx1] x [cy0, cy1] of one
+                // column are one interval of ranks; a lane takes a column and walks its interval (about one keypoint per
+                // column for a 80 x 80 px window), the distance test of :305-309 decides.  The order in which the hits
+                // are collected does not matter: the list below is sorted by (distance, visiting order).  (The first
+                // version tested all ~350 keypoints of the frame for every map point: 40 % of the kernel's instructions.)
+                const int ncol = (int)cx1 - (int)cx0 + 1;
+                for (int c0 = 0; c0 < ncol; c0 += 32) {
+                    int rk = 0, rk_end = 0;  // my column's interval of ranks
+                    if (c0 + lane < ncol) {
+                        const int col = ((int)cx0 + c0 + lane) * 48;
+                        rk = s_start[col + cy0];
+                        rk_end = s_start[col + cy1 + 1];
+                    }
+                    while (__any_sync(AFULL, rk < rk_end)) {
+                        bool in = false;
+                        if (rk < rk_end) {
+                            const float2 pt = s_sxy[rk];
+                            in = fabsf(pt.x - rp.u) < rp.r && fabsf(pt.y - rp.v) < rp.r;
                         }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const unsigned mask = __ballot_sync(AFULL, in[u]);
-                    if (in[u]) s_hit[warp][nh + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)(c0 + 32 * u + lane);
-                    nh += __popc(mask);
+                        const unsigned mask = __ballot_sync(AFULL, in);
+                        if (in) s_hit[warp][nh + __popc(mask & ((1u << lane) - 1u))] = s_sidx[rk];
+                        nh += __popc(mask);
+                        rk++;
+                    }
                 }
             }
             __syncwarp();
+            // the next row's map descriptor on its way to L1 while this row's hits are scored (8 lines of 128 bytes)
+            if (row_next >= 0 && lane < 8)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.map_f32 + (size_t)row_next * 256 + lane * 32));
             for (int h0 = 0; h0 < nh; h0 += 4) {
                 int cc[4];
                 float b[4][8];
@@ -214,6 +312,10 @@ __global__ void __launch_bounds__(256) extend_lists_kernel(const ListParams p) {
 #pragma unroll
                     for (int k = 0; k < 8; k++) b[u][k] = fdesc[(size_t)cc[u] * 256 + lane + 32 * k];
                 }
+                // and the next four hits' rows (4 x 8 lines, one per lane) while these four are reduced and inserted
+                if (h0 + 4 + (lane >> 3) < nh)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(
+                        fdesc + (size_t)s_hit[warp][h0 + 4 + (lane >> 3)] * 256 + (lane & 7) * 32));
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     if (h0 + u >= nh) break;  // warp-uniform
@@ -857,6 +959,9 @@ int ensure_extend(ppg_ctx* c) {
     PPG_CUDA(c, cudaMemset(x->zero_i, 0, (R + N + 2) * 4));
     PPG_CUDA(c, dalloc(&x->ones_u8, R));
     PPG_CUDA(c, dalloc(&x->proj_obs, R));
+    PPG_CUDA(c, dalloc(&x->gs_xy, B * N));
+    PPG_CUDA(c, dalloc(&x->gs_idx, B * N));
+    PPG_CUDA(c, dalloc(&x->gs_start, B * (G_CELLS + 1)));
     PPG_CUDA(c, cudaMemset(x->ones_u8, 1, R));
     PPG_CUDA(c, dalloc(&x->row_node, R));
     PPG_CUDA(c, dalloc(&x->kp_node, N));
@@ -873,6 +978,11 @@ int ensure_extend(ppg_ctx* c) {
     static bool attr_done[64];
     static std::mutex attr_mu;
     PPG_CUDA(c, once_per_device(attr_done, attr_mu, [] {
+                 // four CTAs of the lists kernel per SM (64 registers, 37 KB of static shared memory each): its stalls
+                 // are dependency and L2 latency with ~5 warps per scheduler (ncu), so residency is what it needs
+                 cudaError_t e = cudaFuncSetAttribute(extend_lists_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                      (int)cudaSharedmemCarveoutMaxShared);
+                 if (e != cudaSuccess) return e;
                  return cudaFuncSetAttribute(extend_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
              }));
     return PPG_OK;
@@ -904,6 +1014,20 @@ FrameGraphSrc extracted_graph(const ppg_ctx* c) {
     return g;
 }
 
+// grid_index_kernel (spatial modes) + extend_lists_kernel for `frames` frames on the ctx stream
+void launch_lists(ppg_ctx* c, ListParams lp, int frames) {
+    ExtendState* x = c->assoc->ext;
+    lp.gs_xy = x->gs_xy;
+    lp.gs_idx = x->gs_idx;
+    lp.gs_start = x->gs_start;
+    if (!lp.node_mode) {
+        grid_index_kernel<<<frames, 256, 0, c->st>>>(lp.src, lp.ncap, lp.kinfo, x->gs_xy, x->gs_idx, x->gs_start);
+        c->launches++;
+    }
+    extend_lists_kernel<<<dim3((lp.nc + XL_ROWS - 1) / XL_ROWS, frames), 256, 0, c->st>>>(lp);
+    c->launches++;
+}
+
 // prep + lists + walk on the ctx stream
 int run_extend(ppg_ctx* c, const FrameSrc& src, const FrameGraphSrc& gsrc, int frames, int has_state) {
     AssocState* s = c->assoc;
@@ -926,8 +1050,7 @@ int run_extend(ppg_ctx* c, const FrameSrc& src, const FrameGraphSrc& gsrc, int f
         lp.l_cnt = x->l_cnt;
         lp.node_mode = 0;
         lp.row_node = lp.kp_node = nullptr;
-        extend_lists_kernel<<<dim3((x->nc + XL_ROWS - 1) / XL_ROWS, frames), 256, 0, c->st>>>(lp);
-        c->launches++;
+        launch_lists(c, lp, frames);
         stage_mark(c, "extend.lists");
     }
     WalkParams wp;
@@ -1021,7 +1144,7 @@ void extend_destroy(AssocState* s) {
     if (!x) return;
     void* bufs[] = {x->row_hdr, x->observed, x->bad, x->edge_ok, x->edge_off, x->edge_other, x->order, x->l_idx, x->l_d, x->l_cnt,
                     x->tracked, x->kp_mp, x->kedge_me, x->result, x->g_es, x->g_ee, x->g_coff, x->g_cidx,
-                    x->zero_i, x->ident, x->row_node, x->kp_node, x->ones_u8, x->proj_obs};
+                    x->zero_i, x->ident, x->row_node, x->kp_node, x->ones_u8, x->proj_obs, x->gs_xy, x->gs_idx, x->gs_start};
     for (void* b : bufs)
         if (b) cudaFree(b);
     void* hbufs[] = {x->h_kp_mp, x->h_kedge_me, x->h_result, x->h_tracked};
@@ -1259,7 +1382,7 @@ int ppg_search_by_bow(ppg_ctx* c, const ppg_bow_match_in* in, ppg_bow_match_out*
     lp.node_mode = 1;
     lp.row_node = x->row_node;
     lp.kp_node = x->kp_node;
-    extend_lists_kernel<<<dim3((M + XL_ROWS - 1) / XL_ROWS, 1), 256, 0, c->st>>>(lp);
+    launch_lists(c, lp, 1);
     stage_mark(c, "bow_match.lists");
     WalkParams wp{};
     wp.nc = M;
@@ -1298,7 +1421,7 @@ int ppg_search_by_bow(ppg_ctx* c, const ppg_bow_match_in* in, ppg_bow_match_out*
     wp.kp_node = x->kp_node;
     extend_walk_kernel<<<1, X_THREADS, walk_smem(M, s->ncap, x->ecap), c->st>>>(wp);
     stage_mark(c, "bow_match.walk");
-    c->launches += 2;
+    c->launches += 1;  // the walk (launch_lists counts its own)
     PPG_CUDA(c, cudaGetLastError());
     PPG_CUDA(c, cudaMemcpyAsync(x->h_result, x->result, XR_WORDS * 4, cudaMemcpyDeviceToHost, c->st));
     PPG_CUDA(c, cudaMemcpyAsync(x->h_kp_mp, x->kp_mp, (size_t)s->ncap * 4, cudaMemcpyDeviceToHost, c->st));
@@ -1353,7 +1476,7 @@ int ppg_search_for_initialization(ppg_ctx* c, const ppg_init_match_in* in, ppg_i
     lp.l_d = x->l_d;
     lp.l_cnt = x->l_cnt;
     lp.node_mode = 0;
-    extend_lists_kernel<<<dim3((M + XL_ROWS - 1) / XL_ROWS, 1), 256, 0, c->st>>>(lp);
+    launch_lists(c, lp, 1);
     stage_mark(c, "init_match.lists");
     WalkParams wp{};
     wp.nc = M;
@@ -1394,7 +1517,7 @@ int ppg_search_for_initialization(ppg_ctx* c, const ppg_init_match_in* in, ppg_i
     wp.max_dist = c->cfg.th_low;
     extend_walk_kernel<<<1, X_THREADS, walk_smem(M, s->ncap, x->ecap), c->st>>>(wp);
     stage_mark(c, "init_match.walk");
-    c->launches += 2;
+    c->launches += 1;
     PPG_CUDA(c, cudaGetLastError());
     PPG_CUDA(c, cudaMemcpyAsync(x->h_result, x->result, XR_WORDS * 4, cudaMemcpyDeviceToHost, c->st));
     PPG_CUDA(c, cudaMemcpyAsync(x->h_kp_mp, x->kp_mp, (size_t)s->ncap * 4, cudaMemcpyDeviceToHost, c->st));
@@ -1478,7 +1601,7 @@ int ppg_search_by_projection(ppg_ctx* c, const ppg_projection_match_in* in, ppg_
     lp.l_d = x->l_d;
     lp.l_cnt = x->l_cnt;
     lp.node_mode = 0;
-    extend_lists_kernel<<<dim3((M + XL_ROWS - 1) / XL_ROWS, 1), 256, 0, c->st>>>(lp);
+    launch_lists(c, lp, 1);
     stage_mark(c, "proj_match.lists");
     WalkParams wp{};
     wp.nc = M;
@@ -1516,7 +1639,7 @@ int ppg_search_by_projection(ppg_ctx* c, const ppg_projection_match_in* in, ppg_
     wp.max_dist = in->max_dist;
     extend_walk_kernel<<<1, X_THREADS, walk_smem(M, s->ncap, x->ecap), c->st>>>(wp);
     stage_mark(c, "proj_match.walk");
-    c->launches += 2;
+    c->launches += 1;
     PPG_CUDA(c, cudaGetLastError());
     PPG_CUDA(c, cudaMemcpyAsync(x->h_result, x->result, XR_WORDS * 4, cudaMemcpyDeviceToHost, c->st));
     PPG_CUDA(c, cudaMemcpyAsync(x->h_kp_mp, x->kp_mp, (size_t)N * 4, cudaMemcpyDeviceToHost, c->st));
