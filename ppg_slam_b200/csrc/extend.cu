@@ -42,6 +42,7 @@ constexpr int X_WCAP = PPG_EXTEND_MAX_WEIGHTS;       // weight-matrix entries pe
 constexpr int X_THREADS = 256, X_WARPS = X_THREADS / 32;
 constexpr int X_NOEVENT = 1 << 20;
 constexpr int G_CELLS = 64 * 48;                     // FRAME_GRID_COLS x FRAME_GRID_ROWS (GeometricCamera.h:79-80)
+constexpr int G_STRIDE = (G_CELLS + 1 + 7) / 8 * 8;  // cell-start table of a frame, padded to whole 16-byte vectors
 
 // Where the point-pair graph of frame f lives: staged arrays (one frame) or the extraction output blocks.
 struct FrameGraphSrc {
@@ -84,7 +85,7 @@ struct ExtendState {
     // Frame grid of every frame of the batch in GetFeaturesInArea's visiting order (grid_index_kernel)
     float2* gs_xy = nullptr;      // [bcap][ncap] positions by rank
     uint16_t* gs_idx = nullptr;   // [bcap][ncap] keypoint index by rank
-    uint16_t* gs_start = nullptr; // [bcap][G_CELLS + 1] first rank of every cell (cx * 48 + cy)
+    uint16_t* gs_start = nullptr; // [bcap][G_STRIDE] first rank of every cell (cx * 48 + cy), [G_CELLS] = total
     // pinned mirrors for the fetch
     int *h_kp_mp = nullptr, *h_kedge_me = nullptr, *h_result = nullptr;
     uint8_t* h_tracked = nullptr;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(256) grid_index_kernel(const FrameSrc src, int
             }
         }
     }
-    for (int k = tid; k <= G_CELLS; k += 256) gs_start[(size_t)f * (G_CELLS + 1) + k] = start[k];
+    for (int k = tid; k < G_STRIDE; k += 256) gs_start[(size_t)f * G_STRIDE + k] = start[min(k, G_CELLS)];
 }
 
 // DescriptorDistance with both rows already in registers (same operation order as exact_distance).
@@ -197,6 +198,36 @@ __device__ __forceinline__ float exact_distance_rr(const float (&av)[8], const f
     return sqrtf(s);
 }
 
+// Four DescriptorDistances against the same row at once, with the SAME sums as exact_distance_rr: the xor butterfly adds
+// own + partner at every level and float addition is commutative, so a lane may as well keep only the distances its
+// half of the partners is responsible for -- two after the first level, one after the second -- which takes 6 shuffles
+// and 6 additions instead of 20 + 20 and one square root instead of four; 4 shuffles hand the results to every lane.
+__device__ __forceinline__ void exact_distance4_rr(const float (&av)[8], const float (&bv)[4][8], int lane, float (&d)[4]) {
+    float s[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        s[u] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float t = av[k] - bv[u][k];
+            s[u] = s[u] + t * t;
+        }
+    }
+    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0;
+    float k0 = h16 ? s[2] : s[0], k1 = h16 ? s[3] : s[1];
+    const float g0 = h16 ? s[0] : s[2], g1 = h16 ? s[1] : s[3];
+    k0 = k0 + __shfl_xor_sync(AFULL, g0, 16);
+    k1 = k1 + __shfl_xor_sync(AFULL, g1, 16);
+    float v = h8 ? k1 : k0;
+    const float g = h8 ? k0 : k1;
+    v = v + __shfl_xor_sync(AFULL, g, 8);
+#pragma unroll
+    for (int m = 4; m >= 1; m >>= 1) v = v + __shfl_xor_sync(AFULL, v, m);
+    v = sqrtf(v);  // lanes 0-7: distance 0, 8-15: 1, 16-23: 2, 24-31: 3
+#pragma unroll
+    for (int u = 0; u < 4; u++) d[u] = __shfl_sync(AFULL, v, 8 * u);
+}
+
 constexpr int XL_ROWS = 64;  // rows per CTA (8 per warp): the frame's keypoint table is staged once for all of them
 
 // grid (ceil(nc / XL_ROWS), frames).  The window scan reads the keypoint table from shared memory; the hits of a row
@@ -206,13 +237,29 @@ __global__ void __launch_bounds__(256, 4) extend_lists_kernel(const ListParams p
     __shared__ uint32_t s_ord[1024];
     __shared__ uint16_t s_hit[8][1024];
     // node mode: the node of every feature; spatial mode: the frame grid by rank (positions, indices, cell starts)
-    __shared__ __align__(8) uint8_t s_mode[1024 * 8 + 1024 * 2 + (G_CELLS + 2) * 2];
+    __shared__ __align__(16) uint8_t s_mode[1024 * 8 + 1024 * 2 + G_STRIDE * 2];
     uint32_t* s_info = reinterpret_cast<uint32_t*>(s_mode);
     float2* s_sxy = reinterpret_cast<float2*>(s_mode);
     uint16_t* s_sidx = reinterpret_cast<uint16_t*>(s_mode + 1024 * 8);
     uint16_t* s_start = s_sidx + 1024;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, f = blockIdx.y;
     const int n = min(p.src.n_of(f), p.ncap);
+    // this warp's eight rows: ids and window parameters in lanes 0-7, fetched next to the staging loads below (two
+    // dependent round trips per CTA instead of two per row)
+    int pre_row = -1, pre_node = -1;
+    RowParam pre_rp;
+    pre_rp.u = pre_rp.v = pre_rp.r = pre_rp.na2 = 0.f;
+    pre_rp.cells = 0xffffffffu;
+    if (lane < XL_ROWS / 8) {
+        const int ql = blockIdx.x * XL_ROWS + lane * 8 + warp;
+        if (ql < p.nc) {
+            pre_row = p.order[ql];
+            if (p.node_mode)
+                pre_node = p.row_node[pre_row];
+            else
+                pre_rp = p.rowp[(size_t)f * p.max_rows + pre_row];
+        }
+    }
     if (p.node_mode) {
         for (int i = threadIdx.x; i < n; i += 256) {
             s_info[i] = (uint32_t)p.kp_node[i];
@@ -222,11 +269,11 @@ __global__ void __launch_bounds__(256, 4) extend_lists_kernel(const ListParams p
         const uint32_t* korder = p.korder + (size_t)f * p.ncap;
         const float2* gxy = p.gs_xy + (size_t)f * p.ncap;
         const uint16_t* gidx = p.gs_idx + (size_t)f * p.ncap;
-        const uint16_t* gst = p.gs_start + (size_t)f * (G_CELLS + 1);
-        for (int k = threadIdx.x; k <= G_CELLS; k += 256) s_start[k] = gst[k];
+        const uint16_t* gst = p.gs_start + (size_t)f * G_STRIDE;
+        const int ng = gst[G_CELLS];  // indexable, free keypoints
+        for (int k = threadIdx.x; k < G_STRIDE / 8; k += 256)
+            reinterpret_cast<uint4*>(s_start)[k] = reinterpret_cast<const uint4*>(gst)[k];
         for (int i = threadIdx.x; i < n; i += 256) s_ord[i] = korder[i];
-        __syncthreads();
-        const int ng = s_start[G_CELLS];  // indexable, free keypoints
         for (int i = threadIdx.x; i < ng; i += 256) {
             s_sxy[i] = gxy[i];
             s_sidx[i] = gidx[i];
@@ -237,18 +284,16 @@ __global__ void __launch_bounds__(256, 4) extend_lists_kernel(const ListParams p
     for (int r = 0; r < XL_ROWS / 8; r++) {
         const int q = blockIdx.x * XL_ROWS + r * 8 + warp;
         if (q >= p.nc) break;
-        const int row = p.order[q];
-        const int row_next = q + 8 < p.nc && r + 1 < XL_ROWS / 8 ? p.order[q + 8] : -1;  // this warp's next row
-        const size_t o = (size_t)f * p.max_rows + row, ol = (size_t)f * p.max_rows + q;
+        const int row = __shfl_sync(AFULL, pre_row, r);
+        const int row_next = r + 1 < XL_ROWS / 8 ? __shfl_sync(AFULL, pre_row, (r + 1) & 31) : -1;  // -1 past the end
+        const size_t ol = (size_t)f * p.max_rows + q;
         RowParam rp;
-        rp.cells = 0;
-        int my_node = -1;
-        if (p.node_mode) {
-            my_node = p.row_node[row];
-            if (my_node < 0) rp.cells = 0xffffffffu;
-        } else {
-            rp = p.rowp[o];
-        }
+        rp.u = __shfl_sync(AFULL, pre_rp.u, r);
+        rp.v = __shfl_sync(AFULL, pre_rp.v, r);
+        rp.r = __shfl_sync(AFULL, pre_rp.r, r);
+        rp.cells = __shfl_sync(AFULL, pre_rp.cells, r);
+        const int my_node = __shfl_sync(AFULL, pre_node, r);
+        if (p.node_mode) rp.cells = my_node < 0 ? 0xffffffffu : 0u;
         // the sorted list lives across the warp: lane k holds its k-th entry (empty = +inf)
         float ld = INFINITY;
         uint32_t lo = 0xffffffffu;
@@ -316,10 +361,12 @@ __global__ void __launch_bounds__(256, 4) extend_lists_kernel(const ListParams p
                 if (h0 + 4 + (lane >> 3) < nh)
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(
                         fdesc + (size_t)s_hit[warp][h0 + 4 + (lane >> 3)] * 256 + (lane & 7) * 32));
+                float d4[4];
+                exact_distance4_rr(a, b, lane, d4);
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     if (h0 + u >= nh) break;  // warp-uniform
-                    const float d = exact_distance_rr(a, b[u]);
+                    const float d = d4[u];
                     const uint32_t ord = s_ord[cc[u]];
                     // entries that stay in front of the new one form a prefix of the lanes
                     const bool before = ld < d || (ld == d && lo < ord);
@@ -961,7 +1008,7 @@ int ensure_extend(ppg_ctx* c) {
     PPG_CUDA(c, dalloc(&x->proj_obs, R));
     PPG_CUDA(c, dalloc(&x->gs_xy, B * N));
     PPG_CUDA(c, dalloc(&x->gs_idx, B * N));
-    PPG_CUDA(c, dalloc(&x->gs_start, B * (G_CELLS + 1)));
+    PPG_CUDA(c, dalloc(&x->gs_start, B * G_STRIDE));
     PPG_CUDA(c, cudaMemset(x->ones_u8, 1, R));
     PPG_CUDA(c, dalloc(&x->row_node, R));
     PPG_CUDA(c, dalloc(&x->kp_node, N));
