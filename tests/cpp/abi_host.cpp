@@ -106,8 +106,28 @@ int main(int argc, char** argv) {
     int self = 0;
     for (int i = 0; i < N; i++) self += kp_mp[i] == i;
     CHECK(xo.n_kp == N && self >= N - N / 10);  // distance 0 to itself; a few keypoints may be out of the grid
-    std::printf("abi_host ok (gpu): %d keypoints, %d edges, %d matched to themselves, nmatches %d\n", N, out.n_edges, self,
-                xo.nmatches);
+    // Matcher::SearchByProjection whole (ppg_search_by_projection): the same table projected onto the frame's own
+    // keypoints, nothing assigned yet -- every row takes its own keypoint (distance 0 is the first minimum)
+    std::vector<int32_t> kp_mp2(N, -7);
+    ppg_projection_match_in pin{};
+    pin.n_rows = N;
+    pin.proj_uv = uv.data();
+    pin.observed = nullptr;
+    pin.n = N;
+    pin.kp_x = kx.data();
+    pin.kp_y = ky.data();
+    pin.desc = fd.data();
+    pin.kp_mp = nullptr;
+    pin.th = 15.f;
+    pin.max_dist = 0.8f;
+    ppg_projection_match_out pout{};
+    pout.kp_mp = kp_mp2.data();
+    CHECK(ppg_search_by_projection(ctx, &pin, &pout) == PPG_OK);
+    int self2 = 0;
+    for (int i = 0; i < N; i++) self2 += kp_mp2[i] == i;
+    CHECK(pout.nmatches >= self2 && pout.nmatches <= N && self2 >= N - N / 10);
+    std::printf("abi_host ok (gpu): %d keypoints, %d edges, %d matched to themselves, nmatches %d; projection matcher %d\n", N,
+                out.n_edges, self, xo.nmatches, pout.nmatches);
     ppg_destroy(ctx);
     return 0;
 }
