@@ -299,6 +299,19 @@ def search_by_projection(cam, mode, x, th, desc_dist=0.7):
     return dict(nmatches=int(nm), kp_mp=km, row_valid=valid[:n_src], proj_uv=uv[:n_src])
 
 
+def distinctive_descriptor(obs_desc, state=None, point_bad=False):
+    """The reference's own MapPoint::ComputeDistinctiveDescriptors on a MapPoint observed by len(obs_desc) raw key frames
+    (state per observation: 0 good, 1 key frame bad, 2 index -1).  -> mDescriptor (256,), all -1 when untouched."""
+    lib = _lib("matcher")
+    d = np.ascontiguousarray(obs_desc, np.float32).reshape(-1, 256)
+    st = np.zeros(max(len(d), 1), np.uint8) if state is None else np.ascontiguousarray(state, np.uint8)
+    out = np.zeros(256, np.float32)
+    lib.ref_distinctive_descriptor.restype = None
+    lib.ref_distinctive_descriptor(len(d), _p(d if len(d) else np.zeros((1, 256), np.float32)), _p(st, C.c_ubyte),
+                                   int(point_bad), _p(out))
+    return out
+
+
 def search_by_bow_kf_f(cam, desc_kf, node_kf, state_kf, desc_f, node_f, ratio):
     """The reference's own Matcher::SearchByBoW(KeyFrame*, Frame&, ...) (Matcher.cpp:393-477).  state_kf: 0 no map point,
     1 good, 2 bad.  -> dict(nmatches, f2kf): f2kf[i] = key-frame feature whose map point frame feature i received."""

@@ -21,6 +21,10 @@ std::vector<MapPoint*> KeyFrame::GetMapPointMatches() {  // KeyFrame.cpp:285-289
     std::unique_lock<std::mutex> lock(mMutexFeatures);
     return mvpMapPoints;
 }
+bool KeyFrame::isBad() {  // KeyFrame.cpp:456-460
+    std::unique_lock<std::mutex> lock(mMutexConnections);
+    return mbBad;
+}
 MapPoint* KeyFrame::GetMapPoint(const size_t& idx) {
     std::unique_lock<std::mutex> lock(mMutexFeatures);
     return mvpMapPoints[idx];

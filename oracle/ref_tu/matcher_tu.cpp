@@ -452,3 +452,32 @@ REF_API int ref_search_by_projection(const float* params8, int width, int height
     delete cam;
     return nm;
 }
+
+// The real MapPoint::ComputeDistinctiveDescriptors (feature/src/MapPoint.cpp:234-302) on a MapPoint whose observations
+// are raw key frames, one per row of obs_desc (state: 0 good, 1 the key frame isBad(), 2 index -1).  mObservations is a
+// std::map keyed by KeyFrame*: the key frames are carved out of ONE allocation in row order, so the map iterates them in
+// that order.  out_desc (256) = mDescriptor after the call (the initial one, all -1, when the function returns early).
+REF_API void ref_distinctive_descriptor(int n_obs, const float* obs_desc, const unsigned char* state, int point_bad,
+                                        float* out_desc) {
+    KeyFrame* kfs = static_cast<KeyFrame*>(calloc((size_t)std::max(n_obs, 1), sizeof(KeyFrame)));
+    std::vector<float> pos(2, 0.f);
+    for (int i = 0; i < n_obs; i++) {
+        KeyFrame* kf = kfs + i;
+        new (&kf->mDescriptors) cv::Mat(1, 256, CV_32F);
+        memcpy(kf->mDescriptors.data, obs_desc + (size_t)i * 256, 1024);
+        new (&kf->mMutexConnections) std::mutex();
+        kf->mbBad = state[i] == 1;
+    }
+    KeyFrame* kf0 = static_cast<KeyFrame*>(calloc(1, sizeof(KeyFrame)));
+    MapPoint* mp = new MapPoint(Eigen::Vector3f(0.f, 0.f, 1.f), kf0);
+    mp->mbBad = point_bad != 0;
+    mp->mDescriptor = cv::Mat(1, 256, CV_32F);
+    for (int k = 0; k < 256; k++) mp->mDescriptor.at<float>(0, k) = -1.f;
+    for (int i = 0; i < n_obs; i++) mp->mObservations[kfs + i] = state[i] == 2 ? -1 : 0;
+    mp->ComputeDistinctiveDescriptors();
+    memcpy(out_desc, mp->mDescriptor.data, 1024);
+    delete mp;
+    for (int i = 0; i < n_obs; i++) (kfs + i)->mDescriptors.~Mat();
+    free(kfs);
+    free(kf0);
+}
