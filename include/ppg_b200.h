@@ -507,7 +507,9 @@ int ppg_search_for_triangulation(ppg_ctx* ctx, const ppg_triangulation_match_in*
  * kp_mp: CurrentFrame.mvpMapPoints as rows of this table -- -1 none (or a map point without observations, which does
  * not occupy, :71-73), -2 a map point outside the table that occupies, >= 0 a row (occupies iff observed[row]).
  * The relocalisation variant tests the pointer alone (:1386): pass observed = NULL (all ones) and -2 for every
- * assigned keypoint. */
+ * assigned keypoint.  Matcher::SearchByProjection(KeyFrame*, Sim3f&, vpPoints, vpMatched, th, ratioHamming) (:479-568,
+ * loop closing) has the same structure over a key frame's keypoints (vpMatched[idx] occupies, :543) with max_dist =
+ * TH_LOW * ratioHamming: the same call. */
 typedef struct {
     int n_rows;
     const float* proj_uv;    /* n_rows x 2 */

@@ -570,9 +570,12 @@ inline int search_for_initialization(ppg_ctx* ctx, Frame& F1, Frame& F2, std::ve
 // (:38-56 / :1347-1371) run here with the reference's own classes and expressions, in loop order; the map points that pass
 // are the rows.  The sequential part -- window, best free keypoint, accept, occupy -- runs on the device.
 namespace detail {
-inline int projection_match(ppg_ctx* ctx, Frame& CurrentFrame, const std::vector<MapPoint*>& rows,
+// keys / descriptors / slots: mvKeysUn, mDescriptors and the map-point vector (F.mvpMapPoints or vpMatched) of the frame
+// or key frame that is searched
+inline int projection_match(ppg_ctx* ctx, int N, const std::vector<KeyPointEx>& keys, const cv::Mat& descriptors,
+                            std::vector<MapPoint*>& slots, const std::vector<MapPoint*>& rows,
                             const std::vector<float>& proj_uv, bool pointer_occupies, float th, float max_dist) {
-    const int N = CurrentFrame.N, M = (int)rows.size();
+    const int M = (int)rows.size();
     if (M == 0 || N <= 0) return 0;
     std::vector<float> table((size_t)M * 256), kx(N), ky(N);
     std::vector<uint8_t> observed(M);
@@ -585,9 +588,9 @@ inline int projection_match(ppg_ctx* ctx, Frame& CurrentFrame, const std::vector
     }
     std::vector<int32_t> kp_mp(N, -1), out_kp(N, -1);
     for (int i = 0; i < N; i++) {
-        kx[i] = CurrentFrame.mvKeysUn[i].mPos[0];
-        ky[i] = CurrentFrame.mvKeysUn[i].mPos[1];
-        MapPoint* m = CurrentFrame.mvpMapPoints[i];
+        kx[i] = keys[i].mPos[0];
+        ky[i] = keys[i].mPos[1];
+        MapPoint* m = slots[i];
         if (!m) continue;
         if (pointer_occupies) {  // :1386 tests the pointer alone
             kp_mp[i] = -2;
@@ -604,7 +607,7 @@ inline int projection_match(ppg_ctx* ctx, Frame& CurrentFrame, const std::vector
     in.n = N;
     in.kp_x = kx.data();
     in.kp_y = ky.data();
-    in.desc = CurrentFrame.mDescriptors.ptr<float>(0);
+    in.desc = descriptors.ptr<float>(0);
     in.kp_mp = kp_mp.data();
     in.th = th;
     in.max_dist = max_dist;
@@ -612,7 +615,7 @@ inline int projection_match(ppg_ctx* ctx, Frame& CurrentFrame, const std::vector
     out.kp_mp = out_kp.data();
     check(ppg_search_by_projection(ctx, &in, &out), ctx, "ppg_search_by_projection");
     for (int i = 0; i < N; i++)
-        if (out_kp[i] >= 0 && out_kp[i] != kp_mp[i]) CurrentFrame.mvpMapPoints[i] = rows[out_kp[i]];  // :84 / :1403
+        if (out_kp[i] >= 0 && out_kp[i] != kp_mp[i]) slots[i] = rows[out_kp[i]];  // :84 / :1403 / :561
     return out.nmatches;
 }
 }  // namespace detail
@@ -634,7 +637,8 @@ inline int search_by_projection(ppg_ctx* ctx, Frame& CurrentFrame, const Frame& 
         uvs.push_back(uv(0));
         uvs.push_back(uv(1));
     }
-    return detail::projection_match(ctx, CurrentFrame, rows, uvs, false, th, th_high);
+    return detail::projection_match(ctx, CurrentFrame.N, CurrentFrame.mvKeysUn, CurrentFrame.mDescriptors,
+                                    CurrentFrame.mvpMapPoints, rows, uvs, false, th, th_high);
 }
 
 inline int search_by_projection(ppg_ctx* ctx, Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound,
@@ -660,7 +664,44 @@ inline int search_by_projection(ppg_ctx* ctx, Frame& CurrentFrame, KeyFrame* pKF
         uvs.push_back(uv(0));
         uvs.push_back(uv(1));
     }
-    return detail::projection_match(ctx, CurrentFrame, rows, uvs, true, th, descDist);
+    return detail::projection_match(ctx, CurrentFrame.N, CurrentFrame.mvKeysUn, CurrentFrame.mDescriptors,
+                                    CurrentFrame.mvpMapPoints, rows, uvs, true, th, descDist);
+}
+
+// Matcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (matching/src/Matcher.cpp:479-568; loop
+// closing, system/src/LoopClosing.cpp:585 / :614 / :792) whole: the same sequential structure over a key frame's
+// keypoints -- a key-frame feature that holds a match is skipped (:543-544), an accepted point occupies its feature
+// (:561).  The loop head (:491-525: bad / already found, depth, image, distance band, viewing angle) runs here.
+inline int search_by_projection(ppg_ctx* ctx, GeometricCamera* cam, KeyFrame* pKF, Sim3f& Scw,
+                                const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th,
+                                float ratioHamming, float th_low) {
+    SE3f Tcw = SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale());
+    Eigen::Vector3f Ow = Tcw.inverse().translation();
+    std::set<MapPoint*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+    spAlreadyFound.erase(static_cast<MapPoint*>(nullptr));
+    std::vector<MapPoint*> rows;
+    std::vector<float> uvs;
+    for (int iMP = 0, iendMP = (int)vpPoints.size(); iMP < iendMP; iMP++) {
+        MapPoint* pMP = vpPoints[iMP];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;  // :491-492
+        Eigen::Vector3f p3Dw = pMP->GetWorldPos();
+        Eigen::Vector3f p3Dc = Tcw * p3Dw;
+        if (p3Dc(2) < 0.0) continue;  // :499-500
+        const Eigen::Vector2f uv = cam->project(p3Dc);
+        if (!pKF->mpCamera->IsInImage(uv(0), uv(1))) continue;  // :506-507
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        Eigen::Vector3f PO = p3Dw - Ow;
+        const float dist = PO.norm();
+        if (dist < minDistance || dist > maxDistance) continue;  // :515-516
+        Eigen::Vector3f Pn = pMP->GetNormal();
+        if (PO.dot(Pn) < 0.5 * dist) continue;  // :522-523
+        rows.push_back(pMP);
+        uvs.push_back(uv(0));
+        uvs.push_back(uv(1));
+    }
+    return detail::projection_match(ctx, pKF->N, pKF->mvKeysUn, pKF->mDescriptors, vpMatched, rows, uvs, true, (float)th,
+                                    th_low * ratioHamming);
 }
 
 // Matcher::SearchForTriangulation (matching/src/Matcher.cpp:767-885) whole on the GPU (ppg_search_for_triangulation)
@@ -737,16 +778,17 @@ inline int search_for_triangulation(ppg_ctx* ctx, GeometricCamera* cam, KeyFrame
 
 #ifndef PPG_SHIM_NO_MATCHER_CLASS
 // Replaces class Matcher (matching/include/Matcher.h:20-64) for its callers: the same twelve signatures, constants and
-// public members.  Seven matchers run on the GPU --
+// public members.  Eight matchers run on the GPU --
 //   ExtendMapMatches          image <-> map association of MSTracking::SearchLocalPoints (system/src/Tracking.cpp:1007)
 //   SearchByBoW(KF, F)        relocalisation / reference-keyframe tracking
 //   SearchByBoW(KF, KF)       loop / merge candidates
 //   SearchForInitialization   monocular initialisation (Tracking.cpp:525)
 //   SearchByProjection(F, F)  tracking with the motion model, every frame (Tracking.cpp:811 / :817)
 //   SearchByProjection(F, KF, sFound, ...)  relocalisation (Tracking.cpp:1297 / :1311)
+//   SearchByProjection(KF, Scw, ...)        loop closing (LoopClosing.cpp:585 / :614 / :792)
 //   SearchForTriangulation    new map points in LocalMapping (Pinhole: closed-form epipolar distance;
 //                             KannalaBrandt8: the two-view triangulation of its epipolarConstrain, per pair on the device)
-// -- and the other five (SearchByProjection x 2, SearchBySim3, Fuse x 2) are the reference's own
+// -- and the other four (SearchByProjection(F, vpMapPoints, th), SearchBySim3, Fuse x 2) are the reference's own
 // host code, inherited unchanged from ::Matcher (their window-search cores are available as search_window above for
 // callers that want them on the device).
 // The ctx is the one the frame's PPGExtractor owns (PPGExtractor::context()).
@@ -781,7 +823,11 @@ public:
                            const float descDist) {
         return search_by_projection(mCtx, CurrentFrame, pKF, sAlreadyFound, th, descDist);
     }
-    // host-side matchers of the reference, unchanged (the other two SearchByProjection overloads included)
+    int SearchByProjection(KeyFrame* pKF, Sim3f& Scw, const std::vector<MapPoint*>& vpPoints,
+                           std::vector<MapPoint*>& vpMatched, int th, float ratioHamming = 1.0) {
+        return search_by_projection(mCtx, mpCamera, pKF, Scw, vpPoints, vpMatched, th, ratioHamming, TH_LOW);
+    }
+    // host-side matchers of the reference, unchanged (SearchByProjection(F, vpMapPoints, th) included)
     using ::Matcher::Fuse;
     using ::Matcher::SearchByProjection;
     using ::Matcher::SearchBySim3;

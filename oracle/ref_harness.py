@@ -282,7 +282,8 @@ def check_in_frustum(cam, Rcw, tcw, Ow, world_pos, normal, min_dist, max_dist, c
 
 def search_by_projection(cam, mode, x, th, desc_dist=0.7):
     """The reference's own Matcher::SearchByProjection(CurrentFrame, LastFrame, th) (mode 0) / (CurrentFrame, pKF,
-    sAlreadyFound, th, descDist) (mode 1) on objects rebuilt from synth.projection_inputs.
+    sAlreadyFound, th, descDist) (mode 1) / (pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (mode 2; x["scale"] = the
+    similarity's scale) on objects rebuilt from synth.projection_inputs.
     -> dict(nmatches, kp_mp (source feature indices, -1 / -2 / -3), row_valid, proj_uv)"""
     lib = _lib("matcher")
     f32 = lambda a: np.ascontiguousarray(a, np.float32)
@@ -295,7 +296,8 @@ def search_by_projection(cam, mode, x, th, desc_dist=0.7):
                                       _p(f32(x["mp_desc"])), _p(u8(x["state"]), C.c_ubyte),
                                       _p(u8(x["observed"]), C.c_ubyte), _p(f32(x["min_dist"])), _p(f32(x["max_dist"])), n,
                                       _p(f32(x["kp_x"])), _p(f32(x["kp_y"])), _p(f32(x["desc"])), _p(km, C.c_int),
-                                      C.c_float(th), C.c_float(desc_dist), _p(uv), _p(valid, C.c_ubyte))
+                                      C.c_float(th), C.c_float(desc_dist), _p(uv), _p(valid, C.c_ubyte),
+                                      _p(f32(x["normal"])), C.c_float(x.get("scale", 1.0)))
     return dict(nmatches=int(nm), kp_mp=km, row_valid=valid[:n_src], proj_uv=uv[:n_src])
 
 
@@ -442,7 +444,8 @@ def shim_projection_both(cam, mode, x, th, desc_dist=0.7):
                                   _p(f32(x["world_pos"])), _p(f32(x["mp_desc"])), _p(u8(x["state"]), C.c_ubyte),
                                   _p(u8(x["observed"]), C.c_ubyte), _p(f32(x["min_dist"])), _p(f32(x["max_dist"])), n,
                                   _p(f32(x["kp_x"])), _p(f32(x["kp_y"])), _p(f32(x["desc"])), _p(km, C.c_int),
-                                  C.c_float(th), C.c_float(desc_dist), _p(nm, C.c_int), _p(out, C.c_int))
+                                  C.c_float(th), C.c_float(desc_dist), _p(nm, C.c_int), _p(out, C.c_int),
+                                  _p(f32(x["normal"])), C.c_float(x.get("scale", 1.0)))
     if rc != 0:
         raise RuntimeError("shim_projection_both failed (rc %d, see stderr)" % rc)
     return tuple(dict(nmatches=int(nm[k]), kp_mp=out[k, :n]) for k in (0, 1))

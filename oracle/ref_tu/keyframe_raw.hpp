@@ -21,6 +21,14 @@ std::vector<MapPoint*> KeyFrame::GetMapPointMatches() {  // KeyFrame.cpp:285-289
     std::unique_lock<std::mutex> lock(mMutexFeatures);
     return mvpMapPoints;
 }
+// KeyFrame::GetFeaturesInArea (KeyFrame.cpp:479-521) is the twin of Frame::GetFeaturesInArea over the grid the key frame
+// copied from its frame (KeyFrame.cpp: mGrid(F.mGrid)); KeyFrame.cpp is not compiled, so a raw key frame answers through
+// the reference's REAL Frame::GetFeaturesInArea of a shadow Frame with the same keypoints (kf_shadow, filled by the
+// harness).
+static std::map<const KeyFrame*, Frame*> kf_shadow;
+std::vector<size_t> KeyFrame::GetFeaturesInArea(const float& x, const float& y, const float& r) const {
+    return kf_shadow.at(this)->GetFeaturesInArea(x, y, r);
+}
 bool KeyFrame::isBad() {  // KeyFrame.cpp:456-460
     std::unique_lock<std::mutex> lock(mMutexConnections);
     return mbBad;
@@ -90,7 +98,11 @@ void drop_keyframe(KeyFrame* kf) {
 }
 // One Matcher::SearchByProjection case on objects rebuilt from flat arrays; MatcherT = ::Matcher or ppg_shim::Matcher.
 //   mode 0: SearchByProjection(CurrentFrame, LastFrame, th) (Matcher.cpp:31-87);
-//   mode 1: SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, descDist) (:1337-1411).
+//   mode 1: SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, descDist) (:1337-1411);
+//   mode 2: SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (:479-568; loop closing): the "current"
+//     side is a raw KEY FRAME (keypoints, descriptors, the camera, a shadow Frame for its grid), kp_mp is vpMatched, the
+//     source features with a point are vpPoints (state 2 = bad), Scw = (Rcw, tcw * scale, scale), desc_dist is
+//     ratioHamming; normal = GetNormal() of the source points (the viewing-angle test of :522-525).
 //   source side (LastFrame / pKF), n_src features: state 0 no map point, 1 a map point, 2 an outlier (mode 0) / a bad
 //     point (mode 1), 3 in sAlreadyFound (mode 1); world_pos, mp_desc (GetDescriptor), observed (Observations() > 0),
 //     min_dist / max_dist (Get*DistanceInvariance, mode 1).
@@ -103,7 +115,7 @@ int projection_case(MatcherT& matcher, GeometricCamera* cam, int mode, const flo
                     const float* world_pos, const float* mp_desc, const unsigned char* state,
                     const unsigned char* observed, const float* min_dist, const float* max_dist, int n, const float* kx,
                     const float* ky, const float* desc, int* kp_mp, float th, float desc_dist, float* proj_uv,
-                    unsigned char* row_valid) {
+                    unsigned char* row_valid, const float* normal = nullptr, float scale = 1.f) {
     KeyFrame* kf0 = static_cast<KeyFrame*>(calloc(1, sizeof(KeyFrame)));
     auto point = [&](const float* P, const float* d, bool obs, bool bad, float mn, float mx) {
         MapPoint* mp = new MapPoint(Eigen::Vector3f(P[0], P[1], P[2]), kf0);
@@ -118,8 +130,11 @@ int projection_case(MatcherT& matcher, GeometricCamera* cam, int mode, const flo
     std::vector<MapPoint*> src(n_src, nullptr);
     for (int i = 0; i < n_src; i++)
         if (state[i])
-            src[i] = point(world_pos + 3 * i, mp_desc + (size_t)i * 256, observed[i] != 0, mode == 1 && state[i] == 2,
+            src[i] = point(world_pos + 3 * i, mp_desc + (size_t)i * 256, observed[i] != 0, mode >= 1 && state[i] == 2,
                            min_dist ? min_dist[i] : 0.f, max_dist ? max_dist[i] : 1e30f);
+    if (normal)
+        for (int i = 0; i < n_src; i++)
+            if (src[i]) src[i]->mNormalVector = Eigen::Vector3f(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]);
     const float zero3[3] = {0, 0, 1};
     MapPoint* outside_obs = point(zero3, nullptr, true, false, 0.f, 1e30f);
     MapPoint* outside_unobs = point(zero3, nullptr, false, false, 0.f, 1e30f);
@@ -140,26 +155,40 @@ int projection_case(MatcherT& matcher, GeometricCamera* cam, int mode, const flo
     F.AssignFeaturesToGrid();
 
     if (row_valid && proj_uv) {  // the caller's side of the split: which source features search, and where
-        const SE3f Tcw = F.GetPose();
+        SE3f Tcw = F.GetPose();
+        if (mode == 2) {  // :482: the pose comes out of the similarity
+            Eigen::Matrix3f Rm;
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) Rm(i, j) = Rcw[3 * i + j];
+            Sim3f Scw(Rm, Eigen::Vector3f(tcw[0] * scale, tcw[1] * scale, tcw[2] * scale), scale);
+            Tcw = SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale());
+        }
         Eigen::Vector3f Ow = Tcw.inverse().translation();
         for (int i = 0; i < n_src; i++) {
             row_valid[i] = 0;
             proj_uv[2 * i] = proj_uv[2 * i + 1] = -1.f;
             MapPoint* pMP = src[i];
             if (!pMP) continue;
-            if (mode == 0 ? state[i] == 2 : (pMP->isBad() || state[i] == 3)) continue;
+            bool found = false;  // mode 2: spAlreadyFound = the points vpMatched holds on entry (:485-486)
+            for (int k = 0; k < n && mode == 2; k++) found = found || kp_mp[k] == i;
+            if (mode == 0 ? state[i] == 2 : (mode == 1 ? (pMP->isBad() || state[i] == 3) : (pMP->isBad() || found))) continue;
             Eigen::Vector3f x3Dw = pMP->GetWorldPos();
             Eigen::Vector3f x3Dc = Tcw * x3Dw;
             if (mode == 0) {
                 const float invzc = 1.0 / x3Dc(2);
                 if (invzc < 0) continue;
             }
+            if (mode == 2 && x3Dc(2) < 0.0) continue;  // :499-500
             Eigen::Vector2f uv = cam->project(x3Dc);
             if (!cam->IsInImage(uv(0), uv(1))) continue;
-            if (mode == 1) {
+            if (mode >= 1) {
                 Eigen::Vector3f PO = x3Dw - Ow;
                 float dist3D = PO.norm();
                 if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+                if (mode == 2) {
+                    Eigen::Vector3f Pn = pMP->GetNormal();
+                    if (PO.dot(Pn) < 0.5 * dist3D) continue;  // :522-525
+                }
             }
             row_valid[i] = 1;
             proj_uv[2 * i] = uv(0);
@@ -176,6 +205,28 @@ int projection_case(MatcherT& matcher, GeometricCamera* cam, int mode, const flo
         L.mvbOutlier.assign(n_src, false);
         for (int i = 0; i < n_src; i++) L.mvbOutlier[i] = state[i] == 2;
         nm = matcher.SearchByProjection(F, L, th);
+    } else if (mode == 2) {
+        std::vector<float> pos(2 * (size_t)std::max(n, 1));
+        std::vector<int> node((size_t)std::max(n, 1), -1);
+        std::vector<unsigned char> none((size_t)std::max(n, 1), 0);
+        for (int i = 0; i < n; i++) {
+            pos[2 * i] = kx[i];
+            pos[2 * i + 1] = ky[i];
+        }
+        KeyFrame* kf = raw_keyframe(n, pos.data(), desc, node.data(), none.data(), nullptr, SE3f());
+        kf->mpCamera = cam;
+        kf_shadow[kf] = &F;  // F carries the same keypoints and the grid (AssignFeaturesToGrid above)
+        std::vector<MapPoint*> vpPoints, vpMatched(F.mvpMapPoints);
+        for (int i = 0; i < n_src; i++)
+            if (src[i]) vpPoints.push_back(src[i]);
+        Eigen::Matrix3f Rm;
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) Rm(i, j) = Rcw[3 * i + j];
+        Sim3f Scw(Rm, Eigen::Vector3f(tcw[0] * scale, tcw[1] * scale, tcw[2] * scale), scale);
+        nm = matcher.SearchByProjection(kf, Scw, vpPoints, vpMatched, (int)th, desc_dist);
+        F.mvpMapPoints = vpMatched;
+        kf_shadow.erase(kf);
+        drop_keyframe(kf);
     } else {
         std::vector<float> pos(2 * (size_t)std::max(n_src, 1), 0.f), dsc(256 * (size_t)std::max(n_src, 1), 0.f);
         std::vector<int> node((size_t)std::max(n_src, 1), -1);

@@ -436,19 +436,21 @@ REF_API void ref_check_in_frustum(const float* params8, int width, int height, i
 
 // The real Matcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th) (Matcher.cpp:31-87; mode 0) and
 // Matcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, sAlreadyFound, th, descDist) (:1337-1411; mode 1) on
-// objects rebuilt from flat arrays, with the reference's own Pinhole / KannalaBrandt8 camera (projection_case in
-// keyframe_raw.hpp documents the arrays).  Returns nmatches.
+// objects rebuilt from flat arrays, with the reference's own Pinhole / KannalaBrandt8 camera; mode 2:
+// SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (:479-568) (projection_case in keyframe_raw.hpp
+// documents the arrays).  Returns nmatches.
 REF_API int ref_search_by_projection(const float* params8, int width, int height, int fisheye, int mode, const float* Rcw,
                                      const float* tcw, int n_src, const float* world_pos, const float* mp_desc,
                                      const unsigned char* state, const unsigned char* observed, const float* min_dist,
                                      const float* max_dist, int n, const float* kx, const float* ky, const float* desc,
-                                     int* kp_mp, float th, float desc_dist, float* proj_uv, unsigned char* row_valid) {
+                                     int* kp_mp, float th, float desc_dist, float* proj_uv, unsigned char* row_valid,
+                                     const float* normal, float scale) {
     const std::vector<float> prm(params8, params8 + 8);
     GeometricCamera* cam = fisheye ? static_cast<GeometricCamera*>(new KannalaBrandt8(prm, width, height, 20.f))
                                    : static_cast<GeometricCamera*>(new Pinhole(prm, width, height, 20.f));
     Matcher matcher(cam, 0.9f);
     const int nm = projection_case(matcher, cam, mode, Rcw, tcw, n_src, world_pos, mp_desc, state, observed, min_dist,
-                                   max_dist, n, kx, ky, desc, kp_mp, th, desc_dist, proj_uv, row_valid);
+                                   max_dist, n, kx, ky, desc, kp_mp, th, desc_dist, proj_uv, row_valid, normal, scale);
     delete cam;
     return nm;
 }

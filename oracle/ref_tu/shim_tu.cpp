@@ -377,23 +377,23 @@ REF_API int shim_projection_both(const float* params8, int width, int height, in
                                  const float* mp_desc, const unsigned char* state, const unsigned char* observed,
                                  const float* min_dist, const float* max_dist, int n, const float* kx, const float* ky,
                                  const float* desc, const int* kp_mp, float th, float desc_dist, int* nmatches2,
-                                 int* kp_mp_2) {
+                                 int* kp_mp_2, const float* normal, float scale) {
     try {
         const std::vector<float> prm(params8, params8 + 8);
         std::unique_ptr<GeometricCamera> camp(fisheye ? static_cast<GeometricCamera*>(new KannalaBrandt8(prm, width, height, 20.f))
                                                       : static_cast<GeometricCamera*>(new Pinhole(prm, width, height, 20.f)));
-        ppg_shim::PPGExtractor ex(camp.get(), std::string(weights));
         for (int which = 0; which < 2; which++) {
             int* out = kp_mp_2 + which * std::max(n, 1);
             for (int i = 0; i < n; i++) out[i] = kp_mp[i];
             if (which == 0) {
                 ::Matcher ref(camp.get(), 0.9f);
                 nmatches2[0] = projection_case(ref, camp.get(), mode, Rcw, tcw, n_src, world_pos, mp_desc, state, observed,
-                                               min_dist, max_dist, n, kx, ky, desc, out, th, desc_dist, nullptr, nullptr);
+                                               min_dist, max_dist, n, kx, ky, desc, out, th, desc_dist, nullptr, nullptr, normal, scale);
             } else {
+                ppg_shim::PPGExtractor ex(camp.get(), std::string(weights));  // needs the GPU: after the host leg
                 ppg_shim::Matcher m(ex.context(), camp.get(), 0.9f);
                 nmatches2[1] = projection_case(m, camp.get(), mode, Rcw, tcw, n_src, world_pos, mp_desc, state, observed,
-                                               min_dist, max_dist, n, kx, ky, desc, out, th, desc_dist, nullptr, nullptr);
+                                               min_dist, max_dist, n, kx, ky, desc, out, th, desc_dist, nullptr, nullptr, normal, scale);
             }
         }
         return 0;

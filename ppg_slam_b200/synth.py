@@ -384,10 +384,13 @@ def projection_inputs(seed, cam, n_src=300, n=340, noise_px=2.0, desc_noise=0.35
         if kp_mp[i] >= 0 and state[kp_mp[i]] == 0:
             kp_mp[i] = -2
     f = lambda a: np.ascontiguousarray(a, np.float32)
+    Ow = -Rcw.T @ tcw
+    nrm = (world - Ow) / np.linalg.norm(world - Ow, axis=1, keepdims=True) + r.normal(0, 0.5, world.shape)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)  # mean viewing direction, roughly along the ray (GetNormal)
     inside = (~behind) & (uv[:, 0] >= 0) & (uv[:, 0] < cam.width) & (uv[:, 1] >= 0) & (uv[:, 1] < cam.height)
     return dict(Rcw=f(Rcw), tcw=f(tcw), world_pos=f(world), mp_desc=f(md), state=state, observed=observed,
                 min_dist=f(min_d), max_dist=f(max_d), kp_x=f(kp[:, 0]), kp_y=f(kp[:, 1]), desc=f(kd), kp_mp=kp_mp,
-                uv_numpy=f(uv), inside_numpy=inside.astype(np.uint8))  # the projection in numpy (no reference needed)
+                uv_numpy=f(uv), inside_numpy=inside.astype(np.uint8), normal=f(nrm))  # the projection in numpy (no reference needed)
 
 
 def projection_rows(x, mode, ref_row_valid, ref_proj_uv):
@@ -398,14 +401,14 @@ def projection_rows(x, mode, ref_row_valid, ref_proj_uv):
     km = np.full(len(x["kp_mp"]), -1, np.int32)
     for i, v in enumerate(x["kp_mp"]):
         v = int(v)
-        if mode == 1:  # relocalisation tests the pointer alone (:1386)
+        if mode >= 1:  # relocalisation (:1386) and the key-frame variant (:543) test the pointer alone
             km[i] = -1 if v == -1 else -2
         elif v >= 0:
             km[i] = row_of[v] if v in row_of else (-2 if x["observed"][v] else -1)
         else:
             km[i] = -2 if v == -2 else -1
     return dict(rows=rows, map_desc=x["mp_desc"][rows], proj_uv=ref_proj_uv[rows],
-                observed=None if mode == 1 else x["observed"][rows], kp_mp=km)
+                observed=None if mode >= 1 else x["observed"][rows], kp_mp=km)
 
 
 def projection_result(x, rows, kp_mp_rows):

@@ -1,5 +1,6 @@
-"""Golden vectors of Matcher::SearchByProjection(CurrentFrame, LastFrame, th) (Matcher.cpp:31-87) and
-Matcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, descDist) (:1337-1411) made by the REFERENCE's own C++
+"""Golden vectors of Matcher::SearchByProjection(CurrentFrame, LastFrame, th) (Matcher.cpp:31-87),
+Matcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, descDist) (:1337-1411) and
+Matcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (:479-568) made by the REFERENCE's own C++
 (oracle/ref_build.py compiles matching/src/Matcher.cpp, map/src/Frame.cpp, feature/src/MapPoint.cpp and the two camera
 classes from /root/reference): Frame / MapPoint / KeyFrame objects rebuilt from flat arrays, the real function, the
 resulting CurrentFrame.mvpMapPoints -- plus which source features the reference's projection tests let through and
@@ -19,7 +20,12 @@ CASES = [  # name, camera, seed, mode, th, descDist / TH_HIGH
     ("proj1", "TUM-VI", 52, 0, 7.0, 0.8),
     ("proj2", "EuRoC", 53, 1, 10.0, 0.5),
     ("proj3", "UMA-VI", 54, 1, 3.0, 64.0),
+    # mode 2 = SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (:479-568): the last number is
+    # ratioHamming (accept <= TH_LOW * ratioHamming), the similarity's scale is stored as <case>/scale
+    ("proj4", "EuRoC", 55, 2, 8.0, 1.5),
+    ("proj5", "TUM-VI", 56, 2, 4.0, 1.0),
 ]
+SCALE = {"proj4": 1.3, "proj5": 0.8}
 
 
 def main():
@@ -27,6 +33,7 @@ def main():
     for name, cname, seed, mode, th, dd in CASES:
         cam = cameras.ALL[cname]
         x = synth.projection_inputs(seed, cam, n_src=96, n=110)
+        x["scale"] = np.float32(SCALE.get(name, 1.0))
         ref = R.search_by_projection(cam, mode, x, th, dd)
         for k, v in x.items():
             out[name + "/" + k] = v

@@ -28,6 +28,7 @@ struct Point2f {
 struct Vec2f {
     float v[2];
     float& operator[](int i) { return v[i]; }
+    float operator[](int i) const { return v[i]; }
     struct Init { Vec2f* p; int k; Init operator,(float x) { p->v[k] = x; return Init{p, k + 1}; } };
     Init operator<<(float x) { v[0] = x; return Init{this, 1}; }
 };
@@ -44,6 +45,8 @@ struct Vector3f {
     float operator[](int i) const { return v[i]; }
     float operator()(int i) const { return v[i]; }
     Vector3f operator-(const Vector3f&) const { return *this; }
+    Vector3f operator/(float) const { return *this; }
+    float dot(const Vector3f&) const { return 0.f; }
     float norm() const { return 0.f; }
 };
 struct Matrix3f {
@@ -55,6 +58,8 @@ struct Matrix3f {
 };
 }  // namespace Eigen
 struct SE3f {
+    SE3f() {}
+    SE3f(const Eigen::Matrix3f&, const Eigen::Vector3f&) {}
     Eigen::Matrix3f rotationMatrix() const { return Eigen::Matrix3f(); }
     Eigen::Vector3f translation() const { return Eigen::Vector3f(); }
     SE3f operator*(const SE3f&) const { return *this; }
@@ -119,6 +124,7 @@ struct MapPoint {
     cv::Mat GetDescriptor() { return cv::Mat(); }
 };
 struct KeyFrame {
+    GeometricCamera* mpCamera = nullptr;
     std::map<unsigned int, std::vector<unsigned int>> mFeatVec;
     cv::Mat mDescriptors;
     int N = 0;
@@ -147,7 +153,11 @@ struct Frame {
 };
 
 #include <set>
-struct Sim3f {};
+struct Sim3f {
+    Eigen::Matrix3f rotationMatrix() const { return Eigen::Matrix3f(); }
+    Eigen::Vector3f translation() const { return Eigen::Vector3f(); }
+    float scale() const { return 1.f; }
+};
 class Matcher {  // matching/include/Matcher.h:20-64, signatures only
 public:
     Matcher(GeometricCamera* pCam, float nnratio = 0.6) : mpCamera(pCam), mfNNratio(nnratio) {}

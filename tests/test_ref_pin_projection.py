@@ -1,6 +1,7 @@
 """Matcher::SearchByProjection(CurrentFrame, LastFrame, th) (matching/src/Matcher.cpp:31-87: every frame tracked with
-the motion model) and Matcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, descDist) (:1337-1411:
-relocalisation), WHOLE -- both are sequential, an accepted match occupies its keypoint for the later map points -- pinned
+the motion model), Matcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, descDist) (:1337-1411:
+relocalisation) and Matcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (:479-568: loop
+closing), WHOLE -- both are sequential, an accepted match occupies its keypoint for the later map points -- pinned
 to the reference's own C++ (oracle/ref_build.py): tests/golden/ref_l2_projection.npz holds what the real functions did to
 Frame / MapPoint / KeyFrame objects (tests/golden/make_golden_ref_projection.py); the oracle (CPU) and
 ppg_search_by_projection (GPU) must reproduce CurrentFrame.mvpMapPoints and the count exactly, and the drop-in class
@@ -28,13 +29,20 @@ def _case(name):
     d = {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "/")}
     d["cam"] = cameras.ALL[str(d["camera"])]
     d["mode"], d["th"], d["dd"] = int(d["mode_th_dd"][0]), float(d["mode_th_dd"][1]), float(d["mode_th_dd"][2])
+    d["accept_dist"] = _max_dist(d["mode"], d["dd"])
     return d
+
+
+def _max_dist(mode, dd):
+    """what the functions accept: TH_HIGH (mode 0, stored), descDist (mode 1), TH_LOW * ratioHamming (mode 2, :559)"""
+    return float(np.float32(0.7) * np.float32(dd)) if mode == 2 else dd
 
 
 def _run(fn, d, valid, uv):
     """rows / recoding as a caller of the C ABI does it (synth.projection_rows) -> the reference's coding of the result"""
     q = synth.projection_rows(d, d["mode"], valid, uv)
-    got = fn(q["map_desc"], q["proj_uv"], q["observed"], d["kp_x"], d["kp_y"], d["desc"], q["kp_mp"], d["th"], d["dd"])
+    got = fn(q["map_desc"], q["proj_uv"], q["observed"], d["kp_x"], d["kp_y"], d["desc"], q["kp_mp"], d["th"],
+             d["accept_dist"])
     return got["nmatches"], synth.projection_result(d, q["rows"], got["kp_mp"]), q
 
 
@@ -66,7 +74,7 @@ def test_fixture_needs_the_live_state():
         for r in range(len(q["rows"])):
             one = O.search_by_projection(d["cam"], q["map_desc"][r:r + 1], q["proj_uv"][r:r + 1],
                                          None if q["observed"] is None else q["observed"][r:r + 1], d["kp_x"], d["kp_y"],
-                                         d["desc"], frozen, d["th"], d["dd"])
+                                         d["desc"], frozen, d["th"], d["accept_dist"])
             k = np.nonzero(one["kp_mp"] == 0)[0]
             if len(k):
                 taken.setdefault(int(k[0]), []).append(int(q["rows"][r]))
@@ -77,13 +85,14 @@ def test_fixture_needs_the_live_state():
 def _live_cases():
     for ci, cam in enumerate((cameras.EUROC, cameras.TUMVI, cameras.UMA, cameras.TUMVI1024)):
         for seed in range(6):
-            for mode, th, dd in ((0, 15.0, 0.8), (0, 7.0, 0.8), (0, 30.0, 0.8), (1, 10.0, 0.5), (1, 3.0, 64.0)):
+            for mode, th, dd in ((0, 15.0, 0.8), (0, 7.0, 0.8), (0, 30.0, 0.8), (1, 10.0, 0.5), (1, 3.0, 64.0),
+                                 (2, 8.0, 1.5), (2, 4.0, 1.0)):
                 yield cam, 400 + 10 * ci + seed, mode, th, dd, dict(n_src=[300, 40, 500, 1][seed % 4],
                                                                       n=[340, 500, 60, 5][(seed // 2) % 4])
 
 
 def test_oracle_equals_reference_search_by_projection_live():
-    """120 random configurations on four calibrations (both camera models), both functions, window radii 3 - 30, 1 - 500
+    """168 random configurations on four calibrations (both camera models), the three functions, window radii 3 - 30, 1 - 500
     source features against 5 - 500 keypoints: the reference's own functions (here) and the oracle."""
     from oracle import post_ref as O, ref_harness as R
     if not R.matcher_available():
@@ -91,13 +100,14 @@ def test_oracle_equals_reference_search_by_projection_live():
     total = 0
     for cam, seed, mode, th, dd, kw in _live_cases():
         x = synth.projection_inputs(seed, cam, **kw)
+        x["scale"] = [1.0, 1.7, 0.6][seed % 3]
         ref = R.search_by_projection(cam, mode, x, th, dd)
-        d = dict(x, mode=mode, th=th, dd=dd)
+        d = dict(x, mode=mode, th=th, dd=dd, accept_dist=_max_dist(mode, dd))
         nm, res, _ = _run(lambda *a: O.search_by_projection(cam, *a), d, ref["row_valid"], ref["proj_uv"])
         assert nm == ref["nmatches"], (cam.name, seed, mode, th)
         np.testing.assert_array_equal(res, ref["kp_mp"], err_msg="%s seed %d mode %d th %g" % (cam.name, seed, mode, th))
         total += nm
-    assert total > 3000
+    assert total > 4000
 
 
 @pytest.mark.gpu
@@ -132,11 +142,11 @@ def test_cuda_search_by_projection_equals_oracle_sweep():
                 x = synth.projection_inputs(500 + seed, cam, n_src=n_src, n=n, frac_dup=[0.25, 0.6][seed % 2])
                 valid = (x["state"] == 1) & (x["inside_numpy"] > 0)  # the split is the caller's: numpy's projection here
                 uv = x["uv_numpy"]
-                d = dict(x, mode=mode, th=th, dd=[0.8, 0.5][mode])
+                d = dict(x, mode=mode, th=th, dd=[0.8, 0.5][mode], accept_dist=[0.8, 0.5][mode])
                 nm0, want, _ = _run(lambda *a: O.search_by_projection(cam, *a), d, valid, uv)
                 q = synth.projection_rows(d, mode, valid, uv)
                 got = e.search_by_projection(q["map_desc"], q["proj_uv"], q["observed"], d["kp_x"], d["kp_y"], d["desc"],
-                                             q["kp_mp"], d["th"], d["dd"])
+                                             q["kp_mp"], d["th"], d["accept_dist"])
                 assert got["nmatches"] == nm0, (cam.name, seed)
                 np.testing.assert_array_equal(synth.projection_result(d, q["rows"], got["kp_mp"]), want,
                                               err_msg="%s seed %d" % (cam.name, seed))
