@@ -314,6 +314,29 @@ def distinctive_descriptor(obs_desc, state=None, point_bad=False):
     return out
 
 
+def search_by_sim3(cam, x, th):
+    """The reference's own Matcher::SearchBySim3 on two raw key frames with real MapPoint objects (synth.sim3_inputs).
+    -> dict(nfound, matches12 (KF2 feature per KF1 feature, -1 none), valid1 / uv1, valid2 / uv2: which features the loop
+    heads let search and where they project into the other key frame)"""
+    lib = _lib("matcher")
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    n1, n2 = len(x["pos1"]), len(x["pos2"])
+    m12 = np.ascontiguousarray(x["matches12"], np.int32).copy()
+    v1, v2 = np.zeros(max(n1, 1), np.uint8), np.zeros(max(n2, 1), np.uint8)
+    uv1, uv2 = np.zeros((max(n1, 1), 2), np.float32), np.zeros((max(n2, 1), 2), np.float32)
+    nf = lib.ref_search_by_sim3(_p(_cam_params(cam)), cam.width, cam.height, int(cam.fisheye), _p(f32(x["R1"]).reshape(9)),
+                                _p(f32(x["t1"])), _p(f32(x["R2"]).reshape(9)), _p(f32(x["t2"])),
+                                _p(f32(x["R12"]).reshape(9)), _p(f32(x["t12"])), C.c_float(float(x["s12"])), n1,
+                                _p(f32(x["pos1"])), _p(f32(x["desc1"])), _p(u8(x["state1"]), C.c_ubyte),
+                                _p(f32(x["world1"])), _p(f32(x["mp_desc1"])), _p(f32(x["min_dist1"])),
+                                _p(f32(x["max_dist1"])), n2, _p(f32(x["pos2"])), _p(f32(x["desc2"])),
+                                _p(u8(x["state2"]), C.c_ubyte), _p(f32(x["world2"])), _p(f32(x["mp_desc2"])),
+                                _p(f32(x["min_dist2"])), _p(f32(x["max_dist2"])), _p(m12, C.c_int), C.c_float(th),
+                                _p(v1, C.c_ubyte), _p(uv1), _p(v2, C.c_ubyte), _p(uv2))
+    return dict(nfound=int(nf), matches12=m12[:n1], valid1=v1[:n1], uv1=uv1[:n1], valid2=v2[:n2], uv2=uv2[:n2])
+
+
 def search_by_bow_kf_f(cam, desc_kf, node_kf, state_kf, desc_f, node_f, ratio):
     """The reference's own Matcher::SearchByBoW(KeyFrame*, Frame&, ...) (Matcher.cpp:393-477).  state_kf: 0 no map point,
     1 good, 2 bad.  -> dict(nmatches, f2kf): f2kf[i] = key-frame feature whose map point frame feature i received."""

@@ -483,3 +483,118 @@ REF_API void ref_distinctive_descriptor(int n_obs, const float* obs_desc, const 
     free(kfs);
     free(kf0);
 }
+
+// The real Matcher::SearchBySim3 (Matcher.cpp:1149-1335; loop closing) on two raw key frames whose features carry real
+// MapPoint objects.  Per key frame k: n_k features (positions, descriptors), state_k (0 no map point, 1 a point, 2 a bad
+// point), world_pos_k / mp_desc_k / min_dist_k / max_dist_k of the points, the pose R_k / t_k (world -> camera).
+// S12 = (R12, t12, s12).  matches12 (n1) in / out: the KF2 FEATURE whose map point vpMatches12[i1] is, or -1.
+// Also out, per feature of either key frame: whether the loop head lets it search (valid_k) and where it projects into
+// the other key frame (uv_k), by the same expressions as :1189-1213 / :1253-1277.  The key-frame grids answer through the
+// reference's real Frame::GetFeaturesInArea of shadow frames (keyframe_raw.hpp).  Returns nFound.
+REF_API int ref_search_by_sim3(const float* params8, int width, int height, int fisheye, const float* R1, const float* t1,
+                               const float* R2, const float* t2, const float* R12, const float* t12, float s12, int n1,
+                               const float* pos1, const float* desc1, const unsigned char* state1, const float* world1,
+                               const float* mpdesc1, const float* mind1, const float* maxd1, int n2, const float* pos2,
+                               const float* desc2, const unsigned char* state2, const float* world2,
+                               const float* mpdesc2, const float* mind2, const float* maxd2, int* matches12, float th,
+                               unsigned char* valid1, float* uv1, unsigned char* valid2, float* uv2) {
+    const std::vector<float> prm(params8, params8 + 8);
+    GeometricCamera* cam = fisheye ? static_cast<GeometricCamera*>(new KannalaBrandt8(prm, width, height, 20.f))
+                                   : static_cast<GeometricCamera*>(new Pinhole(prm, width, height, 20.f));
+    KeyFrame* kf0 = static_cast<KeyFrame*>(calloc(1, sizeof(KeyFrame)));
+    struct Side {
+        KeyFrame* kf;
+        Frame shadow;
+        std::vector<MapPoint*> pts;
+    } S[2];
+    const int n[2] = {n1, n2};
+    const float* pos[2] = {pos1, pos2};
+    const float* desc[2] = {desc1, desc2};
+    const unsigned char* state[2] = {state1, state2};
+    const float* world[2] = {world1, world2};
+    const float* mpdesc[2] = {mpdesc1, mpdesc2};
+    const float* mind[2] = {mind1, mind2};
+    const float* maxd[2] = {maxd1, maxd2};
+    const float* Rk[2] = {R1, R2};
+    const float* tk[2] = {t1, t2};
+    for (int k = 0; k < 2; k++) {
+        std::vector<int> node((size_t)std::max(n[k], 1), -1);
+        std::vector<unsigned char> none((size_t)std::max(n[k], 1), 0);
+        S[k].kf = raw_keyframe(n[k], pos[k], desc[k], node.data(), none.data(), nullptr, pose_of(Rk[k], tk[k]));
+        S[k].kf->mpCamera = cam;
+        Frame& F = S[k].shadow;
+        F.N = n[k];
+        F.mpCamera = cam;
+        F.mvKeysUn = S[k].kf->mvKeysUn;
+        F.mvKeys = F.mvKeysUn;
+        F.AssignFeaturesToGrid();
+        kf_shadow[S[k].kf] = &F;
+        S[k].pts.assign(n[k], nullptr);
+        for (int i = 0; i < n[k]; i++) {
+            if (!state[k][i]) continue;
+            MapPoint* mp = new MapPoint(Eigen::Vector3f(world[k][3 * i], world[k][3 * i + 1], world[k][3 * i + 2]), kf0);
+            mp->mbBad = state[k][i] == 2;
+            mp->mfMinDepth = mind[k][i] * 2.0f;
+            mp->mfMaxDepth = maxd[k][i] * 0.5f;
+            mp->mDescriptor = cv::Mat(1, 256, CV_32F);
+            memcpy(mp->mDescriptor.data, mpdesc[k] + (size_t)i * 256, 1024);
+            mp->mObservations[S[k].kf] = i;  // GetIndexInKeyFrame (:1171)
+            S[k].pts[i] = mp;
+        }
+        S[k].kf->mvpMapPoints = S[k].pts;
+    }
+    Eigen::Matrix3f Rm;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) Rm(i, j) = R12[3 * i + j];
+    const Sim3f S12(Rm, Eigen::Vector3f(t12[0], t12[1], t12[2]), s12);
+    std::vector<MapPoint*> vpMatches12(n1, nullptr);
+    for (int i = 0; i < n1; i++)
+        if (matches12[i] >= 0) vpMatches12[i] = S[1].pts[matches12[i]];
+    {   // the loop heads, for the callers that feed the oracle's frozen search core
+        SE3f T1w = S[0].kf->GetPose(), T2w = S[1].kf->GetPose();
+        Sim3f S21 = S12.inverse();
+        std::vector<bool> am1(n1, false), am2(n2, false);
+        for (int i = 0; i < n1; i++)
+            if (vpMatches12[i]) {
+                am1[i] = true;
+                int idx2 = vpMatches12[i]->GetIndexInKeyFrame(S[1].kf);
+                if (idx2 >= 0 && idx2 < n2) am2[idx2] = true;
+            }
+        for (int k = 0; k < 2; k++) {
+            unsigned char* valid = k == 0 ? valid1 : valid2;
+            float* uvo = k == 0 ? uv1 : uv2;
+            for (int i = 0; i < n[k]; i++) {
+                valid[i] = 0;
+                uvo[2 * i] = uvo[2 * i + 1] = -1.f;
+                MapPoint* pMP = S[k].pts[i];
+                if (!pMP || (k == 0 ? am1[i] : am2[i])) continue;
+                if (pMP->isBad()) continue;
+                Eigen::Vector3f p3Dw = pMP->GetWorldPos();
+                Eigen::Vector3f own = (k == 0 ? T1w : T2w) * p3Dw;
+                Eigen::Vector3f other = k == 0 ? S21 * own : S12 * own;
+                if (other(2) < 0.0) continue;
+                const Eigen::Vector2f uv = cam->project(other);
+                if (!cam->IsInImage(uv[0], uv[1])) continue;
+                const float dist3D = other.norm();
+                if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+                valid[i] = 1;
+                uvo[2 * i] = uv[0];
+                uvo[2 * i + 1] = uv[1];
+            }
+        }
+    }
+    Matcher matcher(cam, 0.75f);
+    const int nFound = matcher.SearchBySim3(S[0].kf, S[1].kf, vpMatches12, S12, th);
+    std::map<MapPoint*, int> idx2_of;
+    for (int i = 0; i < n2; i++)
+        if (S[1].pts[i]) idx2_of[S[1].pts[i]] = i;
+    for (int i = 0; i < n1; i++) matches12[i] = vpMatches12[i] ? idx2_of[vpMatches12[i]] : -1;
+    for (int k = 0; k < 2; k++) {
+        kf_shadow.erase(S[k].kf);
+        for (MapPoint* m : S[k].pts) delete m;
+        drop_keyframe(S[k].kf);
+    }
+    free(kf0);
+    delete cam;
+    return nFound;
+}

@@ -418,3 +418,71 @@ def projection_result(x, rows, kp_mp_rows):
         if v >= 0:
             out[i] = rows[v]
     return out
+
+
+def sim3_inputs(seed, cam, n1=300, n2=320, noise_px=1.0, desc_noise=0.3, scale=1.03):
+    """Two key frames of two maps that see the same place (Matcher::SearchBySim3, Matcher.cpp:1149-1335): each feature may
+    carry its OWN map point (the two maps are not merged yet) -- those of a common 3-D point lie close to each other in
+    the world and have similar descriptors --, a similarity S12 (camera 2 -> camera 1) that is a little off the truth,
+    bad points, features without a point, distance bands, a few entries of vpMatches12 already filled."""
+    r = np.random.RandomState(seed)
+    fx, fy, cx, cy = float(cam.K[0]), float(cam.K[4]), float(cam.K[2]), float(cam.K[5])
+
+    def rot(ax, ang):
+        ax = np.asarray(ax, np.float64)
+        ax /= np.linalg.norm(ax)
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+
+    def proj(Pc):
+        if cam.fisheye:
+            th = np.arctan2(np.hypot(Pc[:, 0], Pc[:, 1]), Pc[:, 2])
+            psi = np.arctan2(Pc[:, 1], Pc[:, 0])
+            k = [float(v) for v in cam.D]
+            rr = th + k[0] * th ** 3 + k[1] * th ** 5 + k[2] * th ** 7 + k[3] * th ** 9
+            return np.stack([fx * rr * np.cos(psi) + cx, fy * rr * np.sin(psi) + cy], 1)
+        return np.stack([fx * Pc[:, 0] / Pc[:, 2] + cx, fy * Pc[:, 1] / Pc[:, 2] + cy], 1)
+    poses = [(rot(r.randn(3), 0.05 * r.rand()), 0.1 * r.randn(3)),
+             (rot(r.randn(3), 0.12 * r.rand()), np.array([0.3, 0.04, 0.02]) * (1 + r.rand(3)))]
+    n_common = min(n1, n2) * 2 // 3
+    span = 0.45 if not cam.fisheye else 0.8
+    z = r.uniform(3.0, 11.0, n_common)
+    X = np.stack([r.uniform(-span, span, n_common) * z * cam.width / fx, r.uniform(-span, span, n_common) * z * cam.height / fy,
+                  z], 1)
+    d_common = r.randn(n_common, 256)
+    out = {}
+    for k, ((R, t), n) in enumerate(zip(poses, (n1, n2)), 1):
+        nc = min(n_common, n)
+        Pc = np.empty((n, 3))
+        Pc[:nc] = X[:nc] @ R.T + t
+        zz = r.uniform(3.0, 11.0, n - nc)
+        Pc[nc:] = np.stack([r.uniform(-span, span, n - nc) * zz * cam.width / fx,
+                            r.uniform(-span, span, n - nc) * zz * cam.height / fy, zz], 1)
+        pos = proj(Pc) + noise_px * r.randn(n, 2)
+        d = np.empty((n, 256))
+        d[:nc] = d_common[:nc] + desc_noise * r.randn(nc, 256) * r.choice([0.5, 1.0, 3.0], (nc, 1))
+        d[nc:] = r.randn(n - nc, 256)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        world = (Pc - t) @ R + r.normal(0, 0.01, (n, 3))  # the key frame's own map point of the feature
+        md = d + 0.02 * r.randn(n, 256)
+        md /= np.linalg.norm(md, axis=1, keepdims=True)
+        d3 = np.linalg.norm(Pc, axis=1)
+        u = r.rand(n)
+        perm = r.permutation(n)
+        f = lambda a: np.ascontiguousarray(a[perm], np.float32)
+        out.update({"R%d" % k: R.astype(np.float32), "t%d" % k: t.astype(np.float32), "pos%d" % k: f(pos),
+                    "desc%d" % k: f(d), "state%d" % k: np.where(u < 0.12, 0, np.where(u < 0.18, 2, 1)).astype(np.uint8)[perm],
+                    "world%d" % k: f(world), "mp_desc%d" % k: f(md),
+                    "min_dist%d" % k: f(d3 * r.uniform(0.3, 1.0, n)), "max_dist%d" % k: f(d3 * r.uniform(1.0, 3.0, n))})
+    (R1, t1), (R2, t2) = poses
+    R12 = R1 @ R2.T
+    t12 = t1 - R12 @ t2
+    out["R12"], out["t12"] = R12.astype(np.float32), (t12 * scale + r.normal(0, 0.003, 3)).astype(np.float32)
+    out["s12"] = np.float32(scale)
+    m12 = np.full(n1, -1, np.int32)
+    for i in np.nonzero(r.rand(n1) < 0.05)[0]:
+        j = r.randint(n2)
+        if out["state2"][j]:
+            m12[i] = j
+    out["matches12"] = m12
+    return out
